@@ -1,0 +1,228 @@
+"""Generate the golden fixtures under tests/golden/ from the REFERENCE ITSELF -- test infrastructure only.
+
+Run in the build container (the only place /root/reference exists):
+
+    python oracle/make_golden.py [--ref /root/reference]
+
+It imports the reference's own modules (`src/dcgan.py`, `src/train_gan.py`) and executes them with the
+installed torch on CPU fp32, then stores inputs that cannot be regenerated and all outputs as compressed
+npz files.  Nothing at test/bench run time reads /root/reference; the fixtures travel instead.
+
+Fixtures
+  step_small_nc1.npz / step_small_nc3.npz
+      reference `dcgan.Generator/Discriminator` (nz=16, ngf=ndf=8) driven by the op sequence of
+      `train_gan.py:121-150` with explicit noise, 2 iterations, batch 3.  Initial weights come from
+      `dcgan_oracle.init_state(RandomState(seed))`, so tests regenerate them.
+  main_small_nc3.npz
+      the UNMODIFIED `train_gan.main(args)` (matplotlib stubbed, `get_dataloaders` patched to a seeded
+      in-memory dataset of 10 images -> batches 4,4,2; save_interval=2 so the train-mode visualisation
+      forward of train_gan.py:166-169 runs 3 times).  Initial weights (torch RNG), fixed noise and
+      per-iteration noise are recorded from the run; history JSON and final state dicts are the outputs.
+  step_full_nc1.npz
+      full-size nets (nz=100, ngf=ndf=64, nc=1), batch 2, 1 iteration; scalars, D probabilities, a
+      strided sample of the fake image and per-tensor checksums of grads / post-step weights.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import tempfile
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import dcgan_oracle as orc  # noqa: E402
+
+GOLDEN_DIR = os.path.join(os.path.dirname(HERE), 'tests', 'golden')
+
+
+def load_state(module, sd_np):
+    module.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in sd_np.items()})
+
+
+def to_np(sd):
+    return {k: v.detach().cpu().numpy().copy() for k, v in sd.items()}
+
+
+def synthetic_real(seed, n, nc, size=224):
+    """Uniform[-1,1) images from numpy's RandomState -- regenerated identically by the tests."""
+    return (np.random.RandomState(seed).rand(n, nc, size, size).astype(np.float32) * 2 - 1)
+
+
+def synthetic_noise(seed, n, nz):
+    return np.random.RandomState(seed).randn(n, nz, 1, 1).astype(np.float32)
+
+
+def reference_step(dcgan, netG, netD, optG, optD, real, noise):
+    """The op sequence of train_gan.py:121-150, executed with the reference's modules and stock torch."""
+    crit = torch.nn.BCELoss()
+    b = real.size(0)
+    netD.zero_grad()
+    label = torch.full((b,), 0.9, dtype=torch.float)
+    out_real = netD(real).view(-1)
+    errD_real = crit(out_real, label)
+    errD_real.backward()
+    fake = netG(noise)
+    label.fill_(0.0)
+    out_fake = netD(fake.detach()).view(-1)
+    errD_fake = crit(out_fake, label)
+    errD_fake.backward()
+    errD = errD_real + errD_fake
+    gradsD = {k: p.grad.detach().numpy().copy() for k, p in netD.named_parameters()}
+    optD.step()
+    netG.zero_grad()
+    label.fill_(0.9)
+    out2 = netD(fake).view(-1)
+    errG = crit(out2, label)
+    errG.backward()
+    gradsG = {k: p.grad.detach().numpy().copy() for k, p in netG.named_parameters()}
+    optG.step()
+    return dict(errG=errG.item(), errD=errD.item(), D_x=out_real.mean().item(), D_G_z1=out_fake.mean().item(),
+                D_G_z2=out2.mean().item(), fake=fake.detach().numpy().copy(), p_real=out_real.detach().numpy().copy(),
+                p_fake=out_fake.detach().numpy().copy(), p_fake_for_G=out2.detach().numpy().copy(),
+                grads_D=gradsD, grads_G=gradsG)
+
+
+def make_step_fixture(dcgan, name, nz, fm, nc, batch, iters, seed, full=False):
+    rng = np.random.RandomState(seed)
+    sdG = orc.init_state(orc.generator_plan(nz, nc, fm), True, rng)
+    sdD = orc.init_state(orc.discriminator_plan(nc, fm), False, rng)
+    netG, netD = dcgan.Generator(nz, nc, fm), dcgan.Discriminator(nc, fm)
+    load_state(netG, sdG)
+    load_state(netD, sdD)
+    optD = torch.optim.Adam(netD.parameters(), lr=2e-4, betas=(0.5, 0.999))
+    optG = torch.optim.Adam(netG.parameters(), lr=2e-4, betas=(0.5, 0.999))
+    out = dict(meta=json.dumps(dict(nz=nz, fm=fm, nc=nc, batch=batch, iters=iters, seed=seed, lr=2e-4, beta1=0.5,
+                                    real_seed=seed + 1, noise_seed=seed + 2, torch=torch.__version__)))
+    real = synthetic_real(seed + 1, batch, nc)
+    noises = synthetic_noise(seed + 2, batch * iters, nz).reshape(iters, batch, nz, 1, 1)
+    for it in range(iters):
+        r = reference_step(dcgan, netG, netD, optG, optD, torch.from_numpy(real), torch.from_numpy(noises[it]))
+        for k in ('errG', 'errD', 'D_x', 'D_G_z1', 'D_G_z2'):
+            out[f'it{it}.{k}'] = np.float64(r[k])
+        for k in ('p_real', 'p_fake', 'p_fake_for_G'):
+            out[f'it{it}.{k}'] = r[k]
+        if full:
+            out[f'it{it}.fake_sample'] = r['fake'][:, :, ::7, ::7].copy()
+            out[f'it{it}.fake_sum'] = np.float64(r['fake'].astype(np.float64).sum())
+            out[f'it{it}.fake_sqsum'] = np.float64((r['fake'].astype(np.float64) ** 2).sum())
+            for net in ('grads_D', 'grads_G'):
+                for k, v in r[net].items():
+                    out[f'it{it}.{net}.{k}.l2'] = np.float64(np.sqrt((v.astype(np.float64) ** 2).sum()))
+                    out[f'it{it}.{net}.{k}.sample'] = v.reshape(-1)[::max(1, v.size // 64)][:64].copy()
+        else:
+            out[f'it{it}.fake'] = r['fake'][:, :, ::3, ::3].copy()     # strided sample keeps the fixture small
+            if it == 0:
+                for net in ('grads_D', 'grads_G'):
+                    for k, v in r[net].items():
+                        out[f'it{it}.{net}.{k}'] = v
+    for tag, net in (('G', netG), ('D', netD)):
+        for k, v in to_np(net.state_dict()).items():
+            if full and v.size > 4096:
+                out[f'final.{tag}.{k}.l2'] = np.float64(np.sqrt((v.astype(np.float64) ** 2).sum()))
+                out[f'final.{tag}.{k}.sample'] = v.reshape(-1)[::max(1, v.size // 256)][:256].copy()
+            else:
+                out[f'final.{tag}.{k}'] = v
+    path = os.path.join(GOLDEN_DIR, name)
+    np.savez_compressed(path, **out)
+    print('wrote', path, os.path.getsize(path) // 1024, 'KiB')
+
+
+def make_main_fixture(ref_src, name):
+    """Run the reference's unmodified train_gan.main on CPU and record what the oracle needs to replay it."""
+    # matplotlib is not installed in the image: stub it before importing train_gan
+    mpl = types.ModuleType('matplotlib')
+    mpl.use = lambda *a, **k: None
+    plt = types.ModuleType('matplotlib.pyplot')
+    for fn in ('figure', 'plot', 'title', 'xlabel', 'ylabel', 'legend', 'grid', 'tight_layout', 'savefig', 'close'):
+        setattr(plt, fn, lambda *a, **k: None)
+    mpl.pyplot = plt
+    sys.modules.setdefault('matplotlib', mpl)
+    sys.modules.setdefault('matplotlib.pyplot', plt)
+    import train_gan  # the reference's file, unmodified
+
+    nz, fm, nc, bs, n_img, data_seed = 16, 8, 3, 4, 10, 777
+    real = synthetic_real(data_seed, n_img, nc)
+
+    def fake_get_dataloaders(data_dir, batch_size, num_workers):
+        ds = torch.utils.data.TensorDataset(torch.from_numpy(real), torch.zeros(n_img, dtype=torch.long))
+        dl = torch.utils.data.DataLoader(ds, batch_size=batch_size, shuffle=False)
+        return dl, dl
+
+    rec = dict(randn=[], init=[])
+    real_randn = torch.randn
+
+    def rec_randn(*a, **k):
+        t = real_randn(*a, **k)
+        rec['randn'].append(t.detach().cpu().numpy().copy())
+        return t
+
+    real_adam = torch.optim.Adam
+
+    def rec_adam(params, *a, **k):
+        params = list(params)
+        rec['init'].append([p.detach().cpu().numpy().copy() for p in params])
+        return real_adam(params, *a, **k)
+
+    train_gan.get_dataloaders = fake_get_dataloaders
+    train_gan.optim.Adam = rec_adam
+    torch.randn = rec_randn
+    tmp = tempfile.mkdtemp(prefix='golden_main_')
+    args = argparse.Namespace(
+        data_dir=tmp, model_dir=os.path.join(tmp, 'models'), output_dir=os.path.join(tmp, 'results'),
+        results_dir=os.path.join(tmp, 'results', 'metrics'), figures_dir=os.path.join(tmp, 'results', 'figures'),
+        num_channels=nc, latent_dim=nz, feature_maps_g=fm, feature_maps_d=fm, epochs=1, batch_size=bs, lr=2e-4,
+        beta1=0.5, workers=0, vis_batch_size=5, save_interval=2, checkpoint_interval=10, cpu=True)
+    torch.manual_seed(1234)
+    try:
+        train_gan.main(args)
+    finally:
+        torch.randn = real_randn
+        train_gan.optim.Adam = real_adam
+    hist = json.load(open(os.path.join(args.results_dir, 'gan_training_history.json')))
+    sdG = to_np(torch.load(os.path.join(args.model_dir, 'gan', 'generator_final.pth')))
+    sdD = to_np(torch.load(os.path.join(args.model_dir, 'gan', 'discriminator_final.pth')))
+    out = dict(meta=json.dumps(dict(nz=nz, fm=fm, nc=nc, batch=bs, n_img=n_img, data_seed=data_seed, lr=2e-4, beta1=0.5,
+                                    save_interval=2, vis_batch=5, torch=torch.__version__,
+                                    files=sorted(os.listdir(os.path.join(args.output_dir, 'gan_images'))))),
+               history=json.dumps(hist), fixed_noise=rec['randn'][0])
+    for i, z in enumerate(rec['randn'][1:]):
+        out[f'noise{i}'] = z
+    keysD = orc.param_keys(orc.discriminator_plan(nc, fm))
+    keysG = orc.param_keys(orc.generator_plan(nz, nc, fm))
+    for k, v in zip(keysD, rec['init'][0]):      # optimizerD is created first (train_gan.py:94)
+        out[f'init.D.{k}'] = v
+    for k, v in zip(keysG, rec['init'][1]):
+        out[f'init.G.{k}'] = v
+    for k, v in sdG.items():
+        out[f'final.G.{k}'] = v
+    for k, v in sdD.items():
+        out[f'final.D.{k}'] = v
+    path = os.path.join(GOLDEN_DIR, name)
+    np.savez_compressed(path, **out)
+    print('wrote', path, os.path.getsize(path) // 1024, 'KiB', 'history:', {k: v[:3] for k, v in hist.items()})
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--ref', default='/root/reference')
+    a = ap.parse_args()
+    ref_src = os.path.join(a.ref, 'src')
+    sys.path.insert(0, ref_src)
+    import dcgan  # the reference's file, unmodified
+    assert os.path.abspath(dcgan.__file__).startswith(os.path.abspath(a.ref)), dcgan.__file__
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    torch.manual_seed(0)
+    make_step_fixture(dcgan, 'step_small_nc1.npz', nz=16, fm=8, nc=1, batch=3, iters=2, seed=100)
+    make_step_fixture(dcgan, 'step_small_nc3.npz', nz=16, fm=8, nc=3, batch=3, iters=2, seed=200)
+    make_step_fixture(dcgan, 'step_full_nc1.npz', nz=100, fm=64, nc=1, batch=2, iters=1, seed=300, full=True)
+    make_main_fixture(ref_src, 'main_small_nc3.npz')
+
+
+if __name__ == '__main__':
+    main()
