@@ -77,7 +77,7 @@ def test_main_small_replays_unmodified_train_gan():
             if k.endswith('num_batches_tracked'):
                 assert int(v) == int(g[f'final.{tag}.{k}']), k
             elif 'running' in k:
-                close(v, g[f'final.{tag}.{k}'], rtol=2e-2, atol=1e-4, what=f'final.{tag}.{k}')
+                close(v, g[f'final.{tag}.{k}'], rtol=2e-2, atol=2e-3, what=f'final.{tag}.{k}')
             else:
                 # three chaotic iterations (one borderline LeakyReLU decision in iteration 0 already differs, see
                 # parity_utils): every weight stays inside the sign-flip envelope and the mean drift is << lr
