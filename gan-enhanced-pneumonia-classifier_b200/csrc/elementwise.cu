@@ -1,0 +1,416 @@
+// BatchNorm2d (train/eval) statistics + apply, activations, their backward, Sigmoid+BCE, Adam and the
+// layout copy: the HBM-bound kernels of the DCGAN step.  fp32 math throughout, f32 or bf16 storage.
+// Reference semantics: torch native_batch_norm(+backward), relu/leaky_relu/tanh/sigmoid,
+// binary_cross_entropy and optim.Adam as called from dcgan.py:27-47,66-85 and train_gan.py:90-95,128-150.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace b200gan {
+
+__device__ __forceinline__ float act_fwd(float z, int act, float slope) {
+  switch (act) {
+    case B200GAN_ACT_RELU: return z > 0.f ? z : 0.f;
+    case B200GAN_ACT_LRELU: return z > 0.f ? z : z * slope;
+    case B200GAN_ACT_TANH: return tanhf(z);
+    case B200GAN_ACT_SIGMOID: return 1.f / (1.f + expf(-z));
+    default: return z;
+  }
+}
+// derivative of the activation given pre-activation z and (for tanh / sigmoid) the saved output a
+__device__ __forceinline__ float act_grad(float z, float a, int act, float slope) {
+  switch (act) {
+    case B200GAN_ACT_RELU: return z > 0.f ? 1.f : 0.f;
+    case B200GAN_ACT_LRELU: return z > 0.f ? 1.f : slope;
+    case B200GAN_ACT_TANH: return 1.f - a * a;
+    case B200GAN_ACT_SIGMOID: return (1.f - a) * a;
+    default: return 1.f;
+  }
+}
+
+__device__ __forceinline__ int64_t pix_offset(const View& v, int64_t pix) {
+  const int w = (int)(pix % v.w);
+  const int64_t t = pix / v.w;
+  const int h = (int)(t % v.h);
+  const int64_t n = t / v.h;
+  return n * v.sn + (int64_t)h * v.sh + (int64_t)w * v.sw;
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-channel reductions.  Thread layout: cl = tid % lanes_c is the channel lane (consecutive threads
+// read consecutive channels of one pixel: coalesced for NHWC), pr = tid / lanes_c the pixel row of
+// the block; a thread owns channels cl + j*lanes_c, j < 4 (so C <= 4*256).
+// MODE 0: sums (y, y^2).  MODE 1: sums (dz, dz*xhat) for the BatchNorm backward.
+// ------------------------------------------------------------------------------------------------
+struct ReduceArgs {
+  View y, da, a;
+  const float *scale, *shift, *mean, *invstd;
+  int act; float slope;
+  double* sums;
+  int lanes_c, rows;
+};
+
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256) channel_reduce_kernel(ReduceArgs g) {
+  __shared__ float red[256];
+  const int cl = threadIdx.x % g.lanes_c, pr = threadIdx.x / g.lanes_c;
+  const int C = g.y.c;
+  float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+  float sc[4], sh[4], mu[4], is[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = cl + j * g.lanes_c;
+    const bool ok = c < C;
+    sc[j] = (MODE == 1 && g.scale && ok) ? g.scale[c] : 1.f;
+    sh[j] = (MODE == 1 && g.scale && ok) ? g.shift[c] : 0.f;
+    mu[j] = (MODE == 1 && g.mean && ok) ? g.mean[c] : 0.f;
+    is[j] = (MODE == 1 && g.invstd && ok) ? g.invstd[c] : 1.f;
+  }
+  const int64_t P = (int64_t)g.y.n * g.y.h * g.y.w;
+  if (pr < g.rows) {
+    for (int64_t p = (int64_t)blockIdx.x * g.rows + pr; p < P; p += (int64_t)gridDim.x * g.rows) {
+      const T* yb = reinterpret_cast<const T*>(g.y.ptr) + pix_offset(g.y, p);
+      const T* db = MODE == 1 ? reinterpret_cast<const T*>(g.da.ptr) + pix_offset(g.da, p) : nullptr;
+      const T* ab = (MODE == 1 && g.a.ptr) ? reinterpret_cast<const T*>(g.a.ptr) + pix_offset(g.a, p) : nullptr;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = cl + j * g.lanes_c;
+        if (c < C) {
+          const float y = ld_as_float(yb + (int64_t)c * g.y.sc);
+          if (MODE == 0) {
+            s0[j] += y;
+            s1[j] = fmaf(y, y, s1[j]);
+          } else {
+            const float d = ld_as_float(db + (int64_t)c * g.da.sc);
+            const float a = ab ? ld_as_float(ab + (int64_t)c * g.a.sc) : 0.f;
+            const float z = fmaf(y, sc[j], sh[j]);
+            const float dz = d * act_grad(z, a, g.act, g.slope);
+            s0[j] += dz;
+            s1[j] = fmaf(dz, (y - mu[j]) * is[j], s1[j]);
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = cl + j * g.lanes_c;
+    if (j * g.lanes_c >= C) break;
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+      __syncthreads();
+      red[threadIdx.x] = which ? s1[j] : s0[j];
+      __syncthreads();
+      if (pr == 0 && c < C) {
+        float t = 0.f;
+        for (int r = 0; r < g.rows; ++r) t += red[r * g.lanes_c + cl];
+        atomicAdd(g.sums + which * C + c, (double)t);
+      }
+    }
+  }
+}
+
+static void reduce_geometry(int C, int* lanes_c, int* rows) {
+  *lanes_c = C < 256 ? C : 256;
+  *rows = 256 / *lanes_c;
+}
+
+int ew_bn_stats(const b200gan_view* y, double* sums, cudaStream_t st) {
+  B200_CHECK_ARG(y->c <= 1024, "bn_stats: at most 1024 channels (got %d)", y->c);
+  ReduceArgs g{};
+  g.y = to_view(y); g.sums = sums;
+  reduce_geometry(y->c, &g.lanes_c, &g.rows);
+  B200_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * y->c, st));
+  const int64_t P = (int64_t)y->n * y->h * y->w;
+  int64_t blocks = (P + (int64_t)g.rows * 64 - 1) / ((int64_t)g.rows * 64);   // ~64 pixels per thread
+  if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
+  if (blocks < 1) blocks = 1;
+  if (y->dtype == B200GAN_F32) channel_reduce_kernel<float, 0><<<(unsigned)blocks, 256, 0, st>>>(g);
+  else channel_reduce_kernel<__nv_bfloat16, 0><<<(unsigned)blocks, 256, 0, st>>>(g);
+  B200_LAUNCH_CHECK("bn_stats");
+  return 0;
+}
+
+int ew_bn_bwd_reduce(const b200gan_view* da, const b200gan_view* y, const b200gan_view* a, const float* scale,
+                     const float* shift, const float* mean, const float* invstd, int act, float slope, double* sums,
+                     cudaStream_t st) {
+  B200_CHECK_ARG(y->c <= 1024, "bn_act_bwd_reduce: at most 1024 channels (got %d)", y->c);
+  B200_CHECK_ARG(da->dtype == y->dtype && (!a || a->dtype == y->dtype), "bn_act_bwd_reduce: mixed dtypes");
+  ReduceArgs g{};
+  g.y = to_view(y); g.da = to_view(da);
+  if (a) g.a = to_view(a); else g.a.ptr = nullptr;
+  g.scale = scale; g.shift = shift; g.mean = mean; g.invstd = invstd; g.act = act; g.slope = slope; g.sums = sums;
+  reduce_geometry(y->c, &g.lanes_c, &g.rows);
+  B200_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * y->c, st));
+  const int64_t P = (int64_t)y->n * y->h * y->w;
+  int64_t blocks = (P + (int64_t)g.rows * 64 - 1) / ((int64_t)g.rows * 64);
+  if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
+  if (blocks < 1) blocks = 1;
+  if (y->dtype == B200GAN_F32) channel_reduce_kernel<float, 1><<<(unsigned)blocks, 256, 0, st>>>(g);
+  else channel_reduce_kernel<__nv_bfloat16, 1><<<(unsigned)blocks, 256, 0, st>>>(g);
+  B200_LAUNCH_CHECK("bn_act_bwd_reduce");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void bn_finalize_kernel(const double* sums, int C, double count, const float* gamma, const float* beta,
+                                   float* rmean, float* rvar, int64_t* nbt, float momentum, float eps, float* scale,
+                                   float* shift, float* smean, float* sinvstd) {
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const double mean = sums[c] / count;
+    double var = sums[C + c] / count - mean * mean;     // biased variance
+    if (var < 0.0) var = 0.0;
+    const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float sc = gamma[c] * invstd;
+    scale[c] = sc;
+    shift[c] = beta[c] - (float)mean * sc;
+    smean[c] = (float)mean;
+    sinvstd[c] = invstd;
+    if (rmean) {
+      const double unbiased = count > 1.0 ? var * (count / (count - 1.0)) : var;
+      rmean[c] = (1.f - momentum) * rmean[c] + momentum * (float)mean;
+      rvar[c] = (1.f - momentum) * rvar[c] + momentum * (float)unbiased;
+    }
+  }
+  if (threadIdx.x == 0 && nbt) *nbt += 1;
+}
+
+int ew_bn_finalize(double* sums, int C, int64_t count, const float* gamma, const float* beta, float* rmean, float* rvar,
+                   int64_t* nbt, float momentum, float eps, float* scale, float* shift, float* smean, float* sinvstd,
+                   cudaStream_t st) {
+  bn_finalize_kernel<<<1, 256, 0, st>>>(sums, C, (double)count, gamma, beta, rmean, rvar, nbt, momentum, eps, scale, shift,
+                                        smean, sinvstd);
+  B200_LAUNCH_CHECK("bn_finalize");
+  return 0;
+}
+
+__global__ void bn_eval_coeffs_kernel(int C, const float* gamma, const float* beta, const float* rmean, const float* rvar,
+                                      float eps, float* scale, float* shift) {
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float sc = gamma[c] / sqrtf(rvar[c] + eps);
+    scale[c] = sc;
+    shift[c] = beta[c] - rmean[c] * sc;
+  }
+}
+
+int ew_bn_eval_coeffs(int C, const float* gamma, const float* beta, const float* rmean, const float* rvar, float eps,
+                      float* scale, float* shift, cudaStream_t st) {
+  bn_eval_coeffs_kernel<<<1, 256, 0, st>>>(C, gamma, beta, rmean, rvar, eps, scale, shift);
+  B200_LAUNCH_CHECK("bn_eval_coeffs");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+template <typename T, typename TD>
+__global__ void __launch_bounds__(256) bn_act_fwd_kernel(View y, View a, const float* scale, const float* shift, int act,
+                                                         float slope) {
+  const int64_t total = (int64_t)y.n * y.h * y.w * y.c;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % y.c);
+    const int64_t pix = i / y.c;
+    float z = ld_as_float(reinterpret_cast<const T*>(y.ptr) + pix_offset(y, pix) + (int64_t)c * y.sc);
+    if (scale) z = fmaf(z, scale[c], shift[c]);
+    st_from_float(reinterpret_cast<TD*>(a.ptr) + pix_offset(a, pix) + (int64_t)c * a.sc, act_fwd(z, act, slope));
+  }
+}
+
+static unsigned ew_blocks(int64_t total) {
+  int64_t b = (total + 256 * 4 - 1) / (256 * 4);
+  if (b > 16 * kNumSMs) b = 16 * kNumSMs;
+  if (b < 1) b = 1;
+  return (unsigned)b;
+}
+
+int ew_bn_act_fwd(const b200gan_view* y, const float* scale, const float* shift, int act, float slope, const b200gan_view* a,
+                  cudaStream_t st) {
+  B200_CHECK_ARG(y->n == a->n && y->h == a->h && y->w == a->w && y->c == a->c, "bn_act_fwd: extent mismatch");
+  const int64_t total = (int64_t)y->n * y->h * y->w * y->c;
+  const unsigned nb = ew_blocks(total);
+  const View vy = to_view(y), va = to_view(a);
+  if (y->dtype == B200GAN_F32 && a->dtype == B200GAN_F32) bn_act_fwd_kernel<float, float><<<nb, 256, 0, st>>>(vy, va, scale, shift, act, slope);
+  else if (y->dtype == B200GAN_F32) bn_act_fwd_kernel<float, __nv_bfloat16><<<nb, 256, 0, st>>>(vy, va, scale, shift, act, slope);
+  else if (a->dtype == B200GAN_F32) bn_act_fwd_kernel<__nv_bfloat16, float><<<nb, 256, 0, st>>>(vy, va, scale, shift, act, slope);
+  else bn_act_fwd_kernel<__nv_bfloat16, __nv_bfloat16><<<nb, 256, 0, st>>>(vy, va, scale, shift, act, slope);
+  B200_LAUNCH_CHECK("bn_act_fwd");
+  return 0;
+}
+
+struct BwdApplyArgs {
+  View da, y, a, dy;
+  const float *scale, *shift, *mean, *invstd, *gamma;
+  const double* sums;
+  double count;
+  int act; float slope;
+  float *dgamma, *dbeta;
+};
+
+template <typename T, typename TD>
+__global__ void __launch_bounds__(256) bn_act_bwd_apply_kernel(BwdApplyArgs g) {
+  const int C = g.y.c;
+  if (g.scale && blockIdx.x == 0) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      if (g.dbeta) g.dbeta[c] += (float)g.sums[c];
+      if (g.dgamma) g.dgamma[c] += (float)g.sums[C + c];
+    }
+  }
+  const int64_t total = (int64_t)g.y.n * g.y.h * g.y.w * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int64_t pix = i / C;
+    const float y = ld_as_float(reinterpret_cast<const T*>(g.y.ptr) + pix_offset(g.y, pix) + (int64_t)c * g.y.sc);
+    const float d = ld_as_float(reinterpret_cast<const T*>(g.da.ptr) + pix_offset(g.da, pix) + (int64_t)c * g.da.sc);
+    const float a = g.a.ptr ? ld_as_float(reinterpret_cast<const T*>(g.a.ptr) + pix_offset(g.a, pix) + (int64_t)c * g.a.sc) : 0.f;
+    float r;
+    if (g.scale) {
+      const float z = fmaf(y, g.scale[c], g.shift[c]);
+      const float dz = d * act_grad(z, a, g.act, g.slope);
+      const float xhat = (y - g.mean[c]) * g.invstd[c];
+      const float m1 = (float)(g.sums[c] / g.count), m2 = (float)(g.sums[C + c] / g.count);
+      r = g.gamma[c] * g.invstd[c] * (dz - m1 - xhat * m2);
+    } else {
+      r = d * act_grad(y, a, g.act, g.slope);
+    }
+    st_from_float(reinterpret_cast<TD*>(g.dy.ptr) + pix_offset(g.dy, pix) + (int64_t)c * g.dy.sc, r);
+  }
+}
+
+int ew_bn_act_bwd_apply(const b200gan_view* da, const b200gan_view* y, const b200gan_view* a, const float* scale,
+                        const float* shift, const float* mean, const float* invstd, const float* gamma, double* sums,
+                        int64_t count, int act, float slope, const b200gan_view* dy, float* dgamma, float* dbeta,
+                        cudaStream_t st) {
+  B200_CHECK_ARG(da->dtype == y->dtype && (!a || a->dtype == y->dtype), "bn_act_bwd_apply: da, y and a must share a dtype");
+  BwdApplyArgs g{};
+  g.da = to_view(da); g.y = to_view(y); g.dy = to_view(dy);
+  if (a) g.a = to_view(a); else g.a.ptr = nullptr;
+  g.scale = scale; g.shift = shift; g.mean = mean; g.invstd = invstd; g.gamma = gamma; g.sums = sums; g.count = (double)count;
+  g.act = act; g.slope = slope; g.dgamma = dgamma; g.dbeta = dbeta;
+  const int64_t total = (int64_t)y->n * y->h * y->w * y->c;
+  const unsigned nb = ew_blocks(total);
+  if (y->dtype == B200GAN_F32 && dy->dtype == B200GAN_F32) bn_act_bwd_apply_kernel<float, float><<<nb, 256, 0, st>>>(g);
+  else if (y->dtype == B200GAN_F32) bn_act_bwd_apply_kernel<float, __nv_bfloat16><<<nb, 256, 0, st>>>(g);
+  else if (dy->dtype == B200GAN_F32) bn_act_bwd_apply_kernel<__nv_bfloat16, float><<<nb, 256, 0, st>>>(g);
+  else bn_act_bwd_apply_kernel<__nv_bfloat16, __nv_bfloat16><<<nb, 256, 0, st>>>(g);
+  B200_LAUNCH_CHECK("bn_act_bwd_apply");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Sigmoid + BCE(mean) against a constant target, forward and backward, one CTA (B <= a few thousand).
+// torch: loss_i = (t-1)*max(log1p(-p),-100) - t*max(log p,-100);  dL/dp = (p-t)/max((1-p)p,1e-12)/B
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bce_sigmoid_kernel(const float* logit, int B, float t, float gscale, float* prob,
+                                                          float* out2, float* dlogit) {
+  __shared__ float red[2][8];
+  float ls = 0.f, ps = 0.f;
+  for (int i = threadIdx.x; i < B; i += blockDim.x) {
+    const float p = 1.f / (1.f + expf(-logit[i]));
+    if (prob) prob[i] = p;
+    const float lp = fmaxf(logf(p), -100.f), l1p = fmaxf(log1pf(-p), -100.f);
+    ls += (t - 1.f) * l1p - t * lp;
+    ps += p;
+    if (dlogit) {
+      const float pq = (1.f - p) * p;
+      const float dp = (p - t) / fmaxf(pq, 1e-12f) / (float)B;
+      dlogit[i] = gscale * dp * pq;
+    }
+  }
+  ls = warp_sum(ls);
+  ps = warp_sum(ps);
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = ls; red[1][threadIdx.x >> 5] = ps; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, b = 0.f;
+    for (int w = 0; w < 8; ++w) { a += red[0][w]; b += red[1][w]; }
+    out2[0] = a / (float)B;
+    out2[1] = b / (float)B;
+  }
+}
+
+int ew_bce_sigmoid(const float* logit, int B, float target, float gscale, float* prob, float* out2, float* dlogit,
+                   cudaStream_t st) {
+  bce_sigmoid_kernel<<<1, 256, 0, st>>>(logit, B, target, gscale, prob, out2, dlogit);
+  B200_LAUNCH_CHECK("bce_sigmoid");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// torch.optim.Adam, one flat arena.  exp_avg.lerp_(g, 1-b1); exp_avg_sq = b2*v + (1-b2) g^2;
+// denom = sqrt(v)/sqrt(1-b2^t) + eps; p -= lr/(1-b1^t) * m/denom
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, float one_m_b1, float b2, float one_m_b2,
+                                         float step_size, float bc2_sqrt, float eps) {
+  m = m + (g - m) * one_m_b1;
+  v = v * b2 + one_m_b2 * g * g;
+  const float denom = sqrtf(v) / bc2_sqrt + eps;
+  p = p - step_size * (m / denom);
+}
+
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                   float* __restrict__ v, int64_t n, float one_m_b1, float b2, float one_m_b2,
+                                                   float step_size, float bc2_sqrt, float eps, float gscale, int vec_ok) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+  const int64_t n4 = vec_ok ? n / 4 : 0;
+  for (int64_t i = tid; i < n4; i += nth) {
+    float4 pp = reinterpret_cast<float4*>(p)[i], mm = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
+    const float4 gg = reinterpret_cast<const float4*>(g)[i];
+    adam_one(pp.x, gg.x * gscale, mm.x, vv.x, one_m_b1, b2, one_m_b2, step_size, bc2_sqrt, eps);
+    adam_one(pp.y, gg.y * gscale, mm.y, vv.y, one_m_b1, b2, one_m_b2, step_size, bc2_sqrt, eps);
+    adam_one(pp.z, gg.z * gscale, mm.z, vv.z, one_m_b1, b2, one_m_b2, step_size, bc2_sqrt, eps);
+    adam_one(pp.w, gg.w * gscale, mm.w, vv.w, one_m_b1, b2, one_m_b2, step_size, bc2_sqrt, eps);
+    reinterpret_cast<float4*>(p)[i] = pp;
+    reinterpret_cast<float4*>(m)[i] = mm;
+    reinterpret_cast<float4*>(v)[i] = vv;
+  }
+  for (int64_t i = n4 * 4 + tid; i < n; i += nth) {
+    float pp = p[i], mm = m[i], vv = v[i];
+    adam_one(pp, g[i] * gscale, mm, vv, one_m_b1, b2, one_m_b2, step_size, bc2_sqrt, eps);
+    p[i] = pp; m[i] = mm; v[i] = vv;
+  }
+}
+
+int ew_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps, int step,
+            float gscale, cudaStream_t st) {
+  const double bc1 = 1.0 - pow((double)b1, (double)step), bc2 = 1.0 - pow((double)b2, (double)step);
+  const float step_size = (float)((double)lr / bc1), bc2_sqrt = (float)sqrt(bc2);
+  const int vec_ok = ((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0) ? 1 : 0;
+  adam_kernel<<<ew_blocks(n / 4 + 1), 256, 0, st>>>(p, g, m, v, n, 1.f - b1, b2, 1.f - b2, step_size, bc2_sqrt, eps, gscale, vec_ok);
+  B200_LAUNCH_CHECK("adam");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+template <typename TS, typename TD>
+__global__ void __launch_bounds__(256) copy_view_kernel(View s, View d) {
+  const int64_t total = (int64_t)s.n * s.h * s.w * s.c;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % s.c);
+    const int64_t pix = i / s.c;
+    const float v = ld_as_float(reinterpret_cast<const TS*>(s.ptr) + pix_offset(s, pix) + (int64_t)c * s.sc);
+    st_from_float(reinterpret_cast<TD*>(d.ptr) + pix_offset(d, pix) + (int64_t)c * d.sc, v);
+  }
+}
+
+int ew_copy_view(const b200gan_view* s, const b200gan_view* d, cudaStream_t st) {
+  B200_CHECK_ARG(s->n == d->n && s->h == d->h && s->w == d->w && s->c == d->c, "copy_view: extent mismatch");
+  const int64_t total = (int64_t)s->n * s->h * s->w * s->c;
+  const unsigned b = ew_blocks(total);
+  if (s->dtype == B200GAN_F32 && d->dtype == B200GAN_F32) copy_view_kernel<float, float><<<b, 256, 0, st>>>(to_view(s), to_view(d));
+  else if (s->dtype == B200GAN_F32) copy_view_kernel<float, __nv_bfloat16><<<b, 256, 0, st>>>(to_view(s), to_view(d));
+  else if (d->dtype == B200GAN_F32) copy_view_kernel<__nv_bfloat16, float><<<b, 256, 0, st>>>(to_view(s), to_view(d));
+  else copy_view_kernel<__nv_bfloat16, __nv_bfloat16><<<b, 256, 0, st>>>(to_view(s), to_view(d));
+  B200_LAUNCH_CHECK("copy_view");
+  return 0;
+}
+
+__global__ void fill_kernel(float* p, int64_t n, float v) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+int ew_fill(float* p, int64_t n, float v, cudaStream_t st) {
+  if (n <= 0) return 0;
+  fill_kernel<<<ew_blocks(n), 256, 0, st>>>(p, n, v);
+  B200_LAUNCH_CHECK("fill");
+  return 0;
+}
+
+}  // namespace b200gan

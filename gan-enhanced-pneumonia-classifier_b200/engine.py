@@ -1,0 +1,331 @@
+"""Host-side orchestration of the DCGAN Generator / Discriminator forward and backward on the B200 kernels.
+
+Everything numeric happens in libb200gan.so (hand-written sm_100a CUDA, see csrc/); this file only sequences
+the C-ABI calls per layer, owns the activation buffers (torch tensors used as plain device memory) and
+exposes the result to autograd through two `torch.autograd.Function`s, so that the reference's own training
+loop (`train_gan.py:119-150`: `netD(real)`, `errD.backward()`, `netD(fake.detach())`, `netD(fake)` ...) runs
+unchanged on top of it.
+
+Reference behaviour mirrored here (file:line in /root/reference/src):
+  dcgan.py:25-48   Generator.main      ConvT(k7,s1,p0)-BN-ReLU, 4x[ConvT(k4,s2,p1)-BN-ReLU], ConvT(k4,s2,p1)-Tanh
+  dcgan.py:64-86   Discriminator.main  Conv(k4,s2,p1)-LReLU, 4x[Conv(k4,s2,p1)-BN-LReLU], Conv(k7,s1,p0)-Sigmoid
+  dcgan.py:89-90   Discriminator.forward flattens to (N,)
+BatchNorm side effects (running stats with unbiased variance, num_batches_tracked) happen in every training-mode
+forward, including forwards under no_grad (train_gan.py:166-169).
+
+Internal layout: activations are NHWC in the compute dtype (float32 for the parity mode, bfloat16 for the
+tensor-core mode); the reference's NCHW fp32 tensors are read and written in place through strided views at the
+network edges, so no layout-conversion pass exists.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+from typing import List, Optional
+
+import torch
+
+from . import _lib as L
+
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+LRELU_SLOPE = 0.2
+
+
+def default_compute_dtype() -> torch.dtype:
+    """bf16 (tensor-core mode) unless B200GAN_DTYPE=fp32 selects the fp32 parity mode."""
+    v = os.environ.get('B200GAN_DTYPE', 'bf16').lower()
+    if v in ('fp32', 'float32', 'f32'):
+        return torch.float32
+    if v in ('bf16', 'bfloat16'):
+        return torch.bfloat16
+    raise ValueError(f'B200GAN_DTYPE={v!r}: expected fp32 or bf16')
+
+
+def default_algo() -> int:
+    v = os.environ.get('B200GAN_ALGO', 'auto').lower()
+    return {'auto': L.ALGO_AUTO, 'simt': L.ALGO_SIMT, 'tcgen05': L.ALGO_TCGEN05}[v]
+
+
+@dataclass
+class LayerSpec:
+    conv_idx: int
+    bn_idx: Optional[int]
+    cin: int
+    cout: int
+    k: int
+    stride: int
+    pad: int
+    act: int
+
+
+def generator_specs(latent_dim: int, nc: int, ngf: int) -> List[LayerSpec]:
+    ch = [latent_dim, ngf * 8, ngf * 4, ngf * 2, ngf, ngf // 2, nc]
+    out = []
+    for i in range(6):
+        k, s, p = (7, 1, 0) if i == 0 else (4, 2, 1)
+        out.append(LayerSpec(3 * i, 3 * i + 1 if i < 5 else None, ch[i], ch[i + 1], k, s, p,
+                             L.ACT_RELU if i < 5 else L.ACT_TANH))
+    return out
+
+
+def discriminator_specs(nc: int, ndf: int) -> List[LayerSpec]:
+    ch = [nc, ndf // 2, ndf, ndf * 2, ndf * 4, ndf * 8, 1]
+    conv_idx = [0, 2, 5, 8, 11, 14]
+    out = []
+    for i in range(6):
+        k, s, p = (7, 1, 0) if i == 5 else (4, 2, 1)
+        out.append(LayerSpec(conv_idx[i], conv_idx[i] + 1 if 1 <= i <= 4 else None, ch[i], ch[i + 1], k, s, p,
+                             L.ACT_LRELU if i < 5 else L.ACT_SIGMOID))
+    return out
+
+
+class Act:
+    """A device tensor plus the b200gan_view describing it as logical (N,H,W,C)."""
+    __slots__ = ('t', 'v')
+
+    def __init__(self, t: torch.Tensor, nchw: bool):
+        self.t = t
+        self.v = L.view_nchw(t) if nchw else L.view_nhwc(t)
+
+    @property
+    def n(self):
+        return self.v.n
+
+
+class LayerParams:
+    __slots__ = ('w', 'gamma', 'beta', 'rm', 'rv', 'nbt')
+
+    def __init__(self, w, gamma=None, beta=None, rm=None, rv=None, nbt=None):
+        self.w, self.gamma, self.beta, self.rm, self.rv, self.nbt = w, gamma, beta, rm, rv, nbt
+
+
+def params_from_module(module, specs) -> List[LayerParams]:
+    out = []
+    for sp in specs:
+        conv = module.main[sp.conv_idx]
+        if sp.bn_idx is None:
+            out.append(LayerParams(conv.weight))
+        else:
+            bn = module.main[sp.bn_idx]
+            out.append(LayerParams(conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.num_batches_tracked))
+    return out
+
+
+def _check_f32(t, what):
+    if t.dtype != torch.float32 or not t.is_contiguous() or not t.is_cuda:
+        raise L.B200GanError(f'{what} must be a contiguous float32 CUDA tensor (got {t.dtype}, contiguous={t.is_contiguous()}, {t.device})')
+
+
+class LayerCtx:
+    __slots__ = ('x', 'y', 'a', 'scale', 'shift', 'mean', 'invstd')
+
+
+class NetEngine:
+    """Forward / backward of one network (transposed=True: Generator, False: Discriminator)."""
+
+    def __init__(self, specs: List[LayerSpec], transposed: bool, dtype: torch.dtype, algo: int = L.ALGO_AUTO):
+        self.specs, self.transposed, self.dtype, self.algo = specs, transposed, dtype, algo
+        self._conv = [L.Conv(sp.k, sp.stride, sp.pad, algo) for sp in specs]
+        self.launches = 0     # kernels launched through this engine (bench.py's gpu_launches claim)
+
+    # -- thin wrappers over the C ABI --------------------------------------------------------------
+    def _fprop(self, i, x: Act, w, y: Act, st):
+        name = 'b200gan_convT2d_fprop' if self.transposed else 'b200gan_conv2d_fprop'
+        L.call(name, C.byref(self._conv[i]), C.byref(x.v), L.ptr(w), None, C.byref(y.v), st)
+        self.launches += (self.specs[i].stride ** 2) if self.transposed else 1
+
+    def _dgrad(self, i, dy: Act, w, dx: Act, st):
+        name = 'b200gan_convT2d_dgrad' if self.transposed else 'b200gan_conv2d_dgrad'
+        L.call(name, C.byref(self._conv[i]), C.byref(dy.v), L.ptr(w), None, C.byref(dx.v), st)
+        self.launches += 1 if self.transposed else (self.specs[i].stride ** 2)
+
+    def _wgrad(self, i, x: Act, dy: Act, dw, st):
+        name = 'b200gan_convT2d_wgrad' if self.transposed else 'b200gan_conv2d_wgrad'
+        L.call(name, C.byref(self._conv[i]), C.byref(x.v), C.byref(dy.v), L.ptr(dw), st)
+        self.launches += 1
+
+    def out_hw(self, i, h, w):
+        sp = self.specs[i]
+        if self.transposed:
+            return (h - 1) * sp.stride - 2 * sp.pad + sp.k, (w - 1) * sp.stride - 2 * sp.pad + sp.k
+        return (h + 2 * sp.pad - sp.k) // sp.stride + 1, (w + 2 * sp.pad - sp.k) // sp.stride + 1
+
+    # -- forward -----------------------------------------------------------------------------------
+    def forward(self, x: Act, params: List[LayerParams], training: bool, save: bool, out: Optional[Act] = None,
+                last_act: bool = True):
+        """Runs all six layers.  `out` optionally receives the final activation (e.g. the fp32 NCHW tensor
+        handed back to torch); with last_act=False the last layer's pre-activation is returned instead
+        (the Discriminator logits, so that Sigmoid can be fused with the BCE loss).
+        Returns (final Act, [LayerCtx] or None)."""
+        st = L.stream_ptr()
+        dev = x.t.device
+        ctxs = [] if save else None
+        cur = x
+        nl = len(self.specs)
+        for i, sp in enumerate(self.specs):
+            p = params[i]
+            _check_f32(p.w, 'conv weight')
+            oh, ow = self.out_hw(i, cur.v.h, cur.v.w)
+            last = i == nl - 1
+            ydt = torch.float32 if (last and not self.transposed) else self.dtype      # D logits stay fp32
+            y = Act(torch.empty((cur.v.n, oh, ow, sp.cout), device=dev, dtype=ydt), nchw=False)
+            self._fprop(i, cur, p.w, y, st)
+            lc = LayerCtx() if save else None
+            if save:
+                lc.x, lc.y = cur, y
+                lc.scale = lc.shift = lc.mean = lc.invstd = None
+            scale = shift = None
+            if sp.bn_idx is not None:
+                cch = sp.cout
+                scale = torch.empty(cch, device=dev, dtype=torch.float32)
+                shift = torch.empty(cch, device=dev, dtype=torch.float32)
+                if training:
+                    sums = torch.empty(2 * cch, device=dev, dtype=torch.float64)
+                    mean = torch.empty(cch, device=dev, dtype=torch.float32)
+                    invstd = torch.empty(cch, device=dev, dtype=torch.float32)
+                    L.call('b200gan_bn_stats', C.byref(y.v), L.ptr(sums), st)
+                    L.call('b200gan_bn_finalize', L.ptr(sums), cch, cur.v.n * oh * ow, L.ptr(p.gamma), L.ptr(p.beta),
+                           L.ptr(p.rm), L.ptr(p.rv), L.ptr(p.nbt), BN_MOMENTUM, BN_EPS, L.ptr(scale), L.ptr(shift),
+                           L.ptr(mean), L.ptr(invstd), st)
+                    self.launches += 2
+                    if save:
+                        lc.mean, lc.invstd = mean, invstd
+                else:
+                    L.call('b200gan_bn_eval_coeffs', cch, L.ptr(p.gamma), L.ptr(p.beta), L.ptr(p.rm), L.ptr(p.rv), BN_EPS,
+                           L.ptr(scale), L.ptr(shift), st)
+                    self.launches += 1
+                if save:
+                    lc.scale, lc.shift = scale, shift
+            if last and not last_act:
+                a = y
+            else:
+                if last and out is not None:
+                    a = out
+                else:
+                    a = Act(torch.empty((cur.v.n, oh, ow, sp.cout), device=dev, dtype=ydt if last else self.dtype), nchw=False)
+                L.call('b200gan_bn_act_fwd', C.byref(y.v), L.ptr(scale), L.ptr(shift), sp.act, LRELU_SLOPE, C.byref(a.v), st)
+                self.launches += 1
+            if save:
+                lc.a = a
+                ctxs.append(lc)
+            cur = a
+        return cur, ctxs
+
+    # -- backward ----------------------------------------------------------------------------------
+    def backward(self, ctxs: List[LayerCtx], params: List[LayerParams], dout: Optional[Act], grads: List[Optional[torch.Tensor]],
+                 dinput: Optional[Act] = None, need_wgrad: bool = True, dlogit: Optional[Act] = None):
+        """`dout`: gradient w.r.t. the final activation (or `dlogit`: w.r.t. the last conv output, when the
+        loss kernel already applied Sigmoid').  `grads` is the flat list over `param_order()` of fp32 tensors
+        that are ACCUMULATED into (autograd semantics); entries may be None to skip.  `dinput`, when given,
+        receives the gradient w.r.t. the network input."""
+        st = L.stream_ptr()
+        nl = len(self.specs)
+        gi = len(grads)
+        d = dout
+        for i in reversed(range(nl)):
+            sp, p, lc = self.specs[i], params[i], ctxs[i]
+            dev = lc.y.t.device
+            nparam = 3 if sp.bn_idx is not None else 1
+            gi -= nparam
+            if i == nl - 1 and dlogit is not None:
+                dy = dlogit
+            else:
+                dy = Act(torch.empty(lc.y.t.shape, device=dev, dtype=self.dtype), nchw=False)
+                need_a = sp.act in (L.ACT_TANH, L.ACT_SIGMOID)
+                # da, y, a must share a dtype: for tanh/sigmoid only `a` is read, so it stands in for y
+                yv = lc.a if need_a else lc.y
+                av = C.byref(lc.a.v) if need_a else None
+                if sp.bn_idx is not None:
+                    sums = torch.empty(2 * sp.cout, device=dev, dtype=torch.float64)
+                    cnt = lc.y.v.n * lc.y.v.h * lc.y.v.w
+                    L.call('b200gan_bn_act_bwd_reduce', C.byref(d.v), C.byref(yv.v), av, L.ptr(lc.scale), L.ptr(lc.shift),
+                           L.ptr(lc.mean), L.ptr(lc.invstd), sp.act, LRELU_SLOPE, L.ptr(sums), st)
+                    dg = grads[gi + 1] if need_wgrad else None
+                    db = grads[gi + 2] if need_wgrad else None
+                    L.call('b200gan_bn_act_bwd_apply', C.byref(d.v), C.byref(yv.v), av, L.ptr(lc.scale), L.ptr(lc.shift),
+                           L.ptr(lc.mean), L.ptr(lc.invstd), L.ptr(p.gamma), L.ptr(sums), cnt, sp.act, LRELU_SLOPE,
+                           C.byref(dy.v), L.ptr(dg), L.ptr(db), st)
+                    self.launches += 2
+                else:
+                    L.call('b200gan_bn_act_bwd_apply', C.byref(d.v), C.byref(yv.v), av, None, None, None, None, None, None, 0,
+                           sp.act, LRELU_SLOPE, C.byref(dy.v), None, None, st)
+                    self.launches += 1
+            if need_wgrad and grads[gi] is not None:
+                self._wgrad(i, lc.x, dy, grads[gi], st)
+            if i > 0:
+                d = Act(torch.empty(lc.x.t.shape, device=dev, dtype=self.dtype), nchw=False)
+                self._dgrad(i, dy, p.w, d, st)
+            elif dinput is not None:
+                self._dgrad(i, dy, p.w, dinput, st)
+        return dinput
+
+    def param_order(self, module):
+        """The parameters in `module.parameters()` order: conv weight, then BN weight, bias per layer."""
+        out = []
+        for sp in self.specs:
+            out.append(module.main[sp.conv_idx].weight)
+            if sp.bn_idx is not None:
+                out += [module.main[sp.bn_idx].weight, module.main[sp.bn_idx].bias]
+        return out
+
+
+def _forward_raw(module, engine: NetEngine, x: torch.Tensor, save: bool):
+    """Shared by the autograd and the no-grad paths: fp32 NCHW in, fp32 NCHW out (the reference's interface)."""
+    params = params_from_module(module, engine.specs)
+    training = module.training
+    if save and not training:
+        raise L.B200GanError('backward through an eval-mode network is not on the DCGAN training path and is not implemented')
+    xin = x.detach()
+    if xin.dtype != torch.float32:
+        xin = xin.float()
+    if xin.dim() != 4 or xin.shape[1] != engine.specs[0].cin:
+        raise L.B200GanError(f'expected input of shape (N,{engine.specs[0].cin},H,W), got {tuple(xin.shape)}')
+    n, h, w = xin.shape[0], xin.shape[2], xin.shape[3]
+    for i in range(len(engine.specs)):
+        h, w = engine.out_hw(i, h, w)
+        if h < 1 or w < 1:
+            raise L.B200GanError(f'input spatial size {tuple(xin.shape[2:])} is too small for this network (the reference is hard-wired to 224x224)')
+    out_t = torch.empty((n, engine.specs[-1].cout, h, w), device=x.device, dtype=torch.float32)
+    _, ctxs = engine.forward(Act(xin, nchw=True), params, training, save, out=Act(out_t, nchw=True))
+    return out_t, ctxs
+
+
+class _NetFunction(torch.autograd.Function):
+    """autograd bridge: forward/backward of a whole network through the C ABI."""
+
+    @staticmethod
+    def forward(ctx, module, engine: NetEngine, x, *flat_params):
+        out_t, ctxs = _forward_raw(module, engine, x, save=True)
+        ctx.engine, ctx.module, ctx.ctxs, ctx.xshape = engine, module, ctxs, tuple(x.shape)
+        return out_t
+
+    @staticmethod
+    def backward(ctx, dout):
+        engine, module, ctxs = ctx.engine, ctx.module, ctx.ctxs
+        if ctxs is None:
+            raise L.B200GanError('backward called twice on the same forward (activations were released)')
+        params = params_from_module(module, engine.specs)
+        plist = engine.param_order(module)
+        needs = ctx.needs_input_grad        # (module, engine, x, *params)
+        grads = [torch.zeros_like(p, dtype=torch.float32) if needs[3 + j] else None for j, p in enumerate(plist)]
+        dout = dout.contiguous()
+        if dout.dtype != torch.float32:
+            dout = dout.float()
+        dx = dinput = None
+        if needs[2]:
+            dx = torch.empty(ctx.xshape, device=dout.device, dtype=torch.float32)
+            dinput = Act(dx, nchw=True)
+        engine.backward(ctxs, params, Act(dout, nchw=True), grads, dinput=dinput,
+                        need_wgrad=any(g is not None for g in grads))
+        ctx.ctxs = None
+        return (None, None, dx, *grads)
+
+
+def run_network(module, engine: NetEngine, x: torch.Tensor) -> torch.Tensor:
+    """What `Generator.forward` / `Discriminator.forward` call for CUDA inputs."""
+    plist = engine.param_order(module)
+    if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in plist)):
+        return _NetFunction.apply(module, engine, x, *plist)
+    return _forward_raw(module, engine, x, save=False)[0]

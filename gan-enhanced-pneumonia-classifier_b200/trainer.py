@@ -1,0 +1,141 @@
+"""Fused DCGAN training step: the inner loop of the reference's `train_gan.py:119-150` as one call.
+
+`DCGANTrainer.step(real, noise)` performs, with the same arithmetic and side effects as the reference loop,
+
+    D.zero_grad; D(real) -> BCE(.,0.9) -> backward; G(noise); D(fake.detach()) -> BCE(.,0) -> backward;
+    Adam(D);  G.zero_grad; D(fake) -> BCE(.,0.9) -> backward through D into G; Adam(G)
+
+but (a) every op is a libb200gan.so kernel launched on the current stream with no host synchronisation,
+(b) parameters, gradients and Adam moments of each network live in flat fp32 arenas (the nn.Module
+parameters are re-pointed into them, so `state_dict()`/checkpoints are unaffected) and the optimizer is one
+fused multi-tensor launch per network, (c) Sigmoid + BCE + their backward are one kernel, (d) the dead
+D-weight-gradient work of the G step (its result is discarded by `netD.zero_grad()` at train_gan.py:122) is
+skipped, (e) the five per-iteration history scalars are left on the device in a (5,) tensor, and (f) under
+data parallelism the two gradient arenas are all-reduced over NCCL (sum, then scaled by 1/world inside the Adam
+kernel) -- the reference has no multi-GPU path; semantics are "mean of per-rank gradients", BatchNorm
+statistics stay local to each rank.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib as L
+from . import engine as E
+
+REAL_LABEL = 0.9      # train_gan.py:92
+FAKE_LABEL = 0.0      # train_gan.py:93
+
+
+class _Arena:
+    """Flat fp32 storage for a network's parameters, gradients and Adam state."""
+
+    def __init__(self, params):
+        dev = params[0].device
+        sizes = [p.numel() for p in params]
+        # keep every tensor 16-byte aligned inside the arena (vectorised Adam, future TMA use)
+        offs, o = [], 0
+        for s in sizes:
+            offs.append(o)
+            o += (s + 3) // 4 * 4
+        self.numel = o
+        self.param = torch.zeros(o, device=dev, dtype=torch.float32)
+        self.grad = torch.zeros(o, device=dev, dtype=torch.float32)
+        self.exp_avg = torch.zeros(o, device=dev, dtype=torch.float32)
+        self.exp_avg_sq = torch.zeros(o, device=dev, dtype=torch.float32)
+        self.grads = []
+        with torch.no_grad():
+            for p, off, s in zip(params, offs, sizes):
+                view = self.param[off:off + s].view(p.shape)
+                view.copy_(p.data)
+                p.data = view                          # the module now reads/writes the arena
+                self.grads.append(self.grad[off:off + s].view(p.shape))
+        self.step = 0
+
+
+class DCGANTrainer:
+    def __init__(self, netG, netD, lr: float = 2e-4, beta1: float = 0.5, beta2: float = 0.999, eps: float = 1e-8,
+                 dtype: Optional[torch.dtype] = None, algo: Optional[int] = None, process_group=None):
+        dtype = dtype or E.default_compute_dtype()
+        algo = E.default_algo() if algo is None else algo
+        self.netG, self.netD = netG, netD
+        self.lr, self.beta1, self.beta2, self.eps = lr, beta1, beta2, eps
+        self.engG = E.NetEngine(netG._specs(), True, dtype, algo)
+        self.engD = E.NetEngine(netD._specs(), False, dtype, algo)
+        self.arenaG = _Arena(self.engG.param_order(netG))
+        self.arenaD = _Arena(self.engD.param_order(netD))
+        self.dtype = dtype
+        self.pg = process_group
+        self.world = 1
+        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(process_group)
+        self.extra_launches = 0
+
+    # ------------------------------------------------------------------------------------------------
+    @property
+    def launches(self):
+        """Number of libb200gan kernels launched so far (bench.py's gpu_launches claim)."""
+        return self.engG.launches + self.engD.launches + self.extra_launches
+
+    def _bce(self, logits, target, want_grad=True):
+        n = logits.t.shape[0]
+        dev = logits.t.device
+        out2 = torch.empty(2, device=dev, dtype=torch.float32)
+        dl = torch.empty((n, 1, 1, 1), device=dev, dtype=torch.float32) if want_grad else None
+        L.call('b200gan_bce_sigmoid', L.ptr(logits.t), n, target, 1.0, None, L.ptr(out2), L.ptr(dl), L.stream_ptr())
+        self.extra_launches += 1
+        return out2, (E.Act(dl, nchw=False) if want_grad else None)
+
+    def _adam(self, arena):
+        arena.step += 1
+        if self.world > 1:
+            torch.distributed.all_reduce(arena.grad, group=self.pg)
+        L.call('b200gan_adam', L.ptr(arena.param), L.ptr(arena.grad), L.ptr(arena.exp_avg), L.ptr(arena.exp_avg_sq),
+               arena.numel, self.lr, self.beta1, self.beta2, self.eps, arena.step, 1.0 / self.world, L.stream_ptr())
+        self.extra_launches += 1
+
+    def _as_input(self, t):
+        """Accept the reference's NCHW tensors (fp32 or bf16) without copying."""
+        if t.dim() != 4:
+            raise L.B200GanError(f'expected a 4-d NCHW tensor, got shape {tuple(t.shape)}')
+        if t.dtype not in (torch.float32, torch.bfloat16):
+            t = t.float()
+        return E.Act(t, nchw=True)
+
+    def step(self, real: torch.Tensor, noise: torch.Tensor) -> torch.Tensor:
+        """One adversarial iteration.  Returns a (5,) float32 CUDA tensor
+        [errD, errG, D_x, D_G_z1, D_G_z2] (the history scalars of train_gan.py:153-157), not synchronised."""
+        netG, netD = self.netG, self.netD
+        pG = E.params_from_module(netG, self.engG.specs)
+        pD = E.params_from_module(netD, self.engD.specs)
+        # (1) D step ------------------------------------------------------------- train_gan.py:122-141
+        self.arenaD.grad.zero_()
+        logit_r, ctx_r = self.engD.forward(self._as_input(real), pD, True, True, last_act=False)
+        m_real, dl = self._bce(logit_r, REAL_LABEL)
+        self.engD.backward(ctx_r, pD, None, self.arenaD.grads, dlogit=dl)
+        del ctx_r
+        fake, ctx_g = self.engG.forward(self._as_input(noise), pG, True, True)
+        logit_f, ctx_f = self.engD.forward(fake, pD, True, True, last_act=False)
+        m_fake, dl = self._bce(logit_f, FAKE_LABEL)
+        self.engD.backward(ctx_f, pD, None, self.arenaD.grads, dlogit=dl)
+        del ctx_f
+        self._adam(self.arenaD)
+        # (2) G step ------------------------------------------------------------- train_gan.py:144-150
+        self.arenaG.grad.zero_()
+        logit_g, ctx_d = self.engD.forward(fake, pD, True, True, last_act=False)
+        m_g, dl = self._bce(logit_g, REAL_LABEL)
+        dfake = E.Act(torch.empty_like(fake.t), nchw=False)
+        self.engD.backward(ctx_d, pD, None, [None] * len(self.arenaD.grads), dinput=dfake, need_wgrad=False, dlogit=dl)
+        del ctx_d
+        self.engG.backward(ctx_g, pG, dfake, self.arenaG.grads)
+        del ctx_g
+        self._adam(self.arenaG)
+        # errD = errD_real + errD_fake (train_gan.py:140); D_x, D_G_z1, D_G_z2 are mean probabilities
+        return torch.stack([m_real[0] + m_fake[0], m_g[0], m_real[1], m_fake[1], m_g[1]])
+
+    @torch.no_grad()
+    def sample(self, noise: torch.Tensor) -> torch.Tensor:
+        """The visualisation forward of train_gan.py:166-169 (train-mode under no_grad: BatchNorm buffers move)."""
+        return self.netG(noise)

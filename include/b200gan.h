@@ -1,0 +1,153 @@
+/*
+ * b200gan.h -- C ABI of libb200gan.so: the B200 (sm_100a) kernels behind the DCGAN adversarial
+ * training step of harlanljones/gan-enhanced-pneumonia-classifier (src/dcgan.py + src/train_gan.py).
+ *
+ * The reference has no native code and no FFI: the boundary it offers for this path is the set of
+ * PyTorch operator calls its nn.Modules and training loop make.  Each entry point below replaces one
+ * of those operator calls (cited as reference file:line); a reference maintainer binds them with the
+ * ctypes stub shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain C types only; every pointer inside a view is a DEVICE pointer owned by the caller;
+ *   - all launches are asynchronous on the `stream` argument (a cudaStream_t passed as void*);
+ *   - return value: 0 on success, a negative b200gan_status otherwise; the message of the last error
+ *     of the calling thread is available from b200gan_last_error_string();
+ *   - the library never allocates persistent device memory; workspace is passed in by the caller;
+ *   - no CPU, cuDNN or Triton fallback exists: unsupported shapes return B200GAN_ERR_UNSUPPORTED.
+ */
+#ifndef B200GAN_H_
+#define B200GAN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200GAN_VERSION 100   /* major*10000 + minor*100 + patch */
+
+typedef enum b200gan_status {
+  B200GAN_OK = 0,
+  B200GAN_ERR_BAD_ARG = -1,
+  B200GAN_ERR_UNSUPPORTED = -2,
+  B200GAN_ERR_CUDA = -3,
+  B200GAN_ERR_WORKSPACE = -4,
+  B200GAN_ERR_NCCL = -5
+} b200gan_status;
+
+typedef enum b200gan_dtype { B200GAN_F32 = 0, B200GAN_BF16 = 1 } b200gan_dtype;
+
+typedef enum b200gan_act {
+  B200GAN_ACT_NONE = 0,
+  B200GAN_ACT_RELU = 1,     /* dcgan.py:28,32,36,40,44 */
+  B200GAN_ACT_LRELU = 2,    /* dcgan.py:66,70,74,78,82 (slope passed separately, 0.2 in the reference) */
+  B200GAN_ACT_TANH = 3,     /* dcgan.py:47 */
+  B200GAN_ACT_SIGMOID = 4   /* dcgan.py:85 */
+} b200gan_act;
+
+typedef enum b200gan_algo {
+  B200GAN_ALGO_AUTO = 0,    /* tcgen05 implicit GEMM when the shape/dtype qualifies, SIMT otherwise */
+  B200GAN_ALGO_SIMT = 1,    /* fp32-accumulating CUDA-core kernels (any shape, f32 or bf16 storage) */
+  B200GAN_ALGO_TCGEN05 = 2  /* force the tensor-core path; B200GAN_ERR_UNSUPPORTED if it does not apply */
+} b200gan_algo;
+
+/* A strided 4-d activation view: logical element (n,h,w,c) lives at ptr + n*sn + h*sh + w*sw + c*sc
+ * (strides in ELEMENTS).  The reference's NCHW tensors, the library's NHWC tensors and the zero-row
+ * padded NHWC tensors of the tensor-core path are all expressed this way. */
+typedef struct b200gan_view {
+  void*   ptr;
+  int32_t dtype;            /* b200gan_dtype */
+  int32_t n, h, w, c;
+  int64_t sn, sh, sw, sc;
+} b200gan_view;
+
+/* Convolution geometry shared by Conv2d and ConvTranspose2d: square kernel k, stride, padding.
+ * `weight` is always the fp32 master tensor in the reference's own layout:
+ *   Conv2d          (Cout, Cin, k, k)   dcgan.py:65,68,72,76,80,84
+ *   ConvTranspose2d (Cin, Cout, k, k)   dcgan.py:26,30,34,38,42,46
+ * `wpacked` is NULL or the bf16 repack produced by b200gan_pack_conv_weight for the tensor-core path. */
+typedef struct b200gan_conv {
+  int32_t k, stride, pad;
+  int32_t algo;             /* b200gan_algo */
+} b200gan_conv;
+
+int         b200gan_version(void);
+const char* b200gan_last_error_string(void);
+/* Fills name (<=255 chars + NUL) with the device name; returns SM count, or a negative status. */
+int         b200gan_device_info(int device, char* name, int* cc_major, int* cc_minor);
+
+/* ---- nn.Conv2d: forward (dcgan.py:65-84), input gradient and weight gradient (autograd of it,
+ *      reached from train_gan.py:129,137,148).  dw is fp32 (Cout,Cin,k,k) and is ACCUMULATED into
+ *      (`+=`), matching autograd's accumulation over the real and fake passes (train_gan.py:129,137). */
+int b200gan_conv2d_fprop(const b200gan_conv* cv, const b200gan_view* x, const float* weight, const void* wpacked,
+                         const b200gan_view* y, void* stream);
+int b200gan_conv2d_dgrad(const b200gan_conv* cv, const b200gan_view* dy, const float* weight, const void* wpacked,
+                         const b200gan_view* dx, void* stream);
+int b200gan_conv2d_wgrad(const b200gan_conv* cv, const b200gan_view* x, const b200gan_view* dy, float* dweight,
+                         void* stream);
+
+/* ---- nn.ConvTranspose2d: forward (dcgan.py:26-46), input gradient, weight gradient (Cin,Cout,k,k). */
+int b200gan_convT2d_fprop(const b200gan_conv* cv, const b200gan_view* x, const float* weight, const void* wpacked,
+                          const b200gan_view* y, void* stream);
+int b200gan_convT2d_dgrad(const b200gan_conv* cv, const b200gan_view* dy, const float* weight, const void* wpacked,
+                          const b200gan_view* dx, void* stream);
+int b200gan_convT2d_wgrad(const b200gan_conv* cv, const b200gan_view* x, const b200gan_view* dy, float* dweight,
+                          void* stream);
+
+/* ---- nn.BatchNorm2d in training mode (dcgan.py:27,31,35,39,43,69,73,77,81) -------------------------
+ * bn_stats:     sums[0..C) += sum y, sums[C..2C) += sum y^2 over (N,H,W)          (double accumulators)
+ * bn_finalize:  mean / biased var -> scale = gamma*invstd, shift = beta - mean*scale, saves mean and
+ *               invstd for backward, updates running_mean/var (momentum, UNBIASED var) and
+ *               num_batches_tracked (int64) exactly like torch; then clears `sums` for the next use.
+ *               running_* / num_batches_tracked may be NULL (no tracking). */
+int b200gan_bn_stats(const b200gan_view* y, double* sums, void* stream);
+int b200gan_bn_finalize(double* sums, int32_t channels, int64_t count, const float* gamma, const float* beta,
+                        float* running_mean, float* running_var, int64_t* num_batches_tracked,
+                        float momentum, float eps, float* scale, float* shift, float* save_mean,
+                        float* save_invstd, void* stream);
+/* eval mode (generate_synthetic.py:34): scale/shift from the running statistics. */
+int b200gan_bn_eval_coeffs(int32_t channels, const float* gamma, const float* beta, const float* running_mean,
+                           const float* running_var, float eps, float* scale, float* shift, void* stream);
+
+/* a = act(y*scale[c] + shift[c]); scale == NULL means no BatchNorm (dcgan.py:66 first D layer, :47 tanh, :85). */
+int b200gan_bn_act_fwd(const b200gan_view* y, const float* scale, const float* shift, int32_t act, float slope,
+                       const b200gan_view* a, void* stream);
+
+/* Backward of act(BN(y)).  da: gradient w.r.t. the activation output; y: the saved conv output;
+ * a: the saved activation output (only read for TANH / SIGMOID, may be NULL otherwise).
+ * bwd_reduce: sums[0..C) += sum dz, sums[C..2C) += sum dz*xhat with dz = da*act'(.)   (native_batch_norm_backward)
+ * bwd_apply:  dy = gamma*invstd*(dz - sum dz/count - xhat * sum(dz*xhat)/count); dgamma += sum dz*xhat,
+ *             dbeta += sum dz (written by the first CTA); with scale == NULL: dy = dz (no BatchNorm). */
+int b200gan_bn_act_bwd_reduce(const b200gan_view* da, const b200gan_view* y, const b200gan_view* a,
+                              const float* scale, const float* shift, const float* save_mean,
+                              const float* save_invstd, int32_t act, float slope, double* sums, void* stream);
+int b200gan_bn_act_bwd_apply(const b200gan_view* da, const b200gan_view* y, const b200gan_view* a,
+                             const float* scale, const float* shift, const float* save_mean,
+                             const float* save_invstd, const float* gamma, double* sums, int64_t count,
+                             int32_t act, float slope, const b200gan_view* dy, float* dgamma, float* dbeta,
+                             void* stream);
+
+/* ---- Sigmoid (dcgan.py:85) + nn.BCELoss(mean) against a constant target (train_gan.py:90,92-93,
+ *      125-128,134-136,145-147) and their backward, in one pass over the B logits:
+ *   prob[i]   = 1/(1+exp(-logit[i]))
+ *   out[0]    = mean_i -(t*max(log p,-100) + (1-t)*max(log1p(-p),-100))      (the loss)
+ *   out[1]    = mean_i prob[i]                                               (D_x / D_G_z, train_gan.py:130,138,149)
+ *   dlogit[i] = grad_scale * (p-t)/max(p(1-p),1e-12)/B * p(1-p)              (dlogit may be NULL) */
+int b200gan_bce_sigmoid(const float* logit, int32_t batch, float target, float grad_scale, float* prob,
+                        float* out2, float* dlogit, void* stream);
+
+/* ---- torch.optim.Adam (train_gan.py:94-95,141,150) over one flat fp32 arena: lr, betas, eps, no weight
+ *      decay, no amsgrad; `step` is the 1-based step count of this update.  grad_scale multiplies the
+ *      gradient first (1/world_size for data-parallel sums). */
+int b200gan_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t numel, float lr,
+                 float beta1, float beta2, float eps, int32_t step, float grad_scale, void* stream);
+
+/* ---- layout plumbing: dst(n,h,w,c) = (dst dtype) src(n,h,w,c) for two views of equal extents. */
+int b200gan_copy_view(const b200gan_view* src, const b200gan_view* dst, void* stream);
+int b200gan_fill_f32(float* ptr, int64_t numel, float value, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* B200GAN_H_ */

@@ -1,0 +1,152 @@
+"""Drop-in parity on the GPU: the reference's own training-loop op sequence (train_gan.py:121-150) driven over
+OUR Generator / Discriminator (CUDA kernels behind the C ABI) against fixtures produced by the reference itself."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import dcgan_oracle as orc
+import gan_enhanced_pneumonia_classifier_b200 as pkg
+from conftest import GOLDEN
+from parity_utils import close, grad_close, synthetic_noise, synthetic_real, weights_close
+
+pytestmark = pytest.mark.gpu
+
+
+def build(m, dtype):
+    rng = np.random.RandomState(m['seed'])
+    sdG = orc.init_state(orc.generator_plan(m['nz'], m['nc'], m['fm']), True, rng)
+    sdD = orc.init_state(orc.discriminator_plan(m['nc'], m['fm']), False, rng)
+    G, D = pkg.Generator(m['nz'], m['nc'], m['fm']), pkg.Discriminator(m['nc'], m['fm'])
+    G.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in sdG.items()})
+    D.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in sdD.items()})
+    G, D = G.cuda(), D.cuda()
+    G.compute_dtype = D.compute_dtype = dtype
+    return G, D
+
+
+def reference_loop_step(G, D, optG, optD, real, noise):
+    """train_gan.py:121-150 verbatim in structure (module calls, BCELoss, backward, optimizer steps)."""
+    crit = torch.nn.BCELoss()
+    b = real.size(0)
+    D.zero_grad()
+    label = torch.full((b,), 0.9, dtype=torch.float, device=real.device)
+    out_real = D(real).view(-1)
+    errD_real = crit(out_real, label)
+    errD_real.backward()
+    fake = G(noise)
+    label.fill_(0.0)
+    out_fake = D(fake.detach()).view(-1)
+    errD_fake = crit(out_fake, label)
+    errD_fake.backward()
+    errD = errD_real + errD_fake
+    gD = {k: p.grad.detach().cpu().numpy().copy() for k, p in D.named_parameters()}
+    optD.step()
+    G.zero_grad()
+    label.fill_(0.9)
+    out2 = D(fake).view(-1)
+    errG = crit(out2, label)
+    errG.backward()
+    gG = {k: p.grad.detach().cpu().numpy().copy() for k, p in G.named_parameters()}
+    optG.step()
+    return dict(errG=errG.item(), errD=errD.item(), D_x=out_real.mean().item(), D_G_z1=out_fake.mean().item(),
+                D_G_z2=out2.mean().item(), fake=fake.detach().cpu().numpy(), p_real=out_real.detach().cpu().numpy(),
+                p_fake=out_fake.detach().cpu().numpy(), p_fake_for_G=out2.detach().cpu().numpy(), grads_D=gD, grads_G=gG)
+
+
+@pytest.mark.parametrize('name', ['step_small_nc1.npz', 'step_small_nc3.npz'])
+def test_fp32_mode_matches_reference_fixture(name):
+    g = np.load(os.path.join(GOLDEN, name))
+    m = json.loads(str(g['meta']))
+    G, D = build(m, torch.float32)
+    optD = torch.optim.Adam(D.parameters(), lr=m['lr'], betas=(m['beta1'], 0.999))
+    optG = torch.optim.Adam(G.parameters(), lr=m['lr'], betas=(m['beta1'], 0.999))
+    real = torch.from_numpy(synthetic_real(m['real_seed'], m['batch'], m['nc'])).cuda()
+    noises = synthetic_noise(m['noise_seed'], m['batch'] * m['iters'], m['nz']).reshape(m['iters'], m['batch'], m['nz'], 1, 1)
+    for it in range(m['iters']):
+        r = reference_loop_step(G, D, optG, optD, real, torch.from_numpy(noises[it]).cuda())
+        tol = dict(rtol=1e-4, atol=1e-6) if it == 0 else dict(rtol=2e-3, atol=1e-5)
+        for k in ('errG', 'errD', 'D_x', 'D_G_z1', 'D_G_z2', 'p_real', 'p_fake', 'p_fake_for_G'):
+            close(r[k], g[f'it{it}.{k}'], what=f'it{it}.{k}', **tol)
+        close(r['fake'][:, :, ::3, ::3], g[f'it{it}.fake'], rtol=tol['rtol'], atol=1e-5 if it == 0 else 1e-3, what='fake')
+        if it == 0:
+            for net in ('grads_D', 'grads_G'):
+                for k, v in r[net].items():
+                    grad_close(v, g[f'it0.{net}.{k}'], f'{net}.{k}')
+    for tag, net in (('G', G), ('D', D)):
+        for k, v in net.state_dict().items():
+            ref = g[f'final.{tag}.{k}']
+            v = v.cpu().numpy()
+            if k.endswith('num_batches_tracked'):
+                assert int(v) == int(ref), k
+            elif 'running' in k:
+                close(v, ref, rtol=1e-3, atol=1e-5, what=k)
+            else:
+                weights_close(v, ref, what=f'final.{tag}.{k}', steps=m['iters'], rtol=1e-3, atol=1e-5, frac=0.97)
+
+
+def test_bf16_mode_within_tolerance_of_fp32_reference():
+    g = np.load(os.path.join(GOLDEN, 'step_small_nc1.npz'))
+    m = json.loads(str(g['meta']))
+    G, D = build(m, torch.bfloat16)
+    optD = torch.optim.Adam(D.parameters(), lr=m['lr'], betas=(m['beta1'], 0.999))
+    optG = torch.optim.Adam(G.parameters(), lr=m['lr'], betas=(m['beta1'], 0.999))
+    real = torch.from_numpy(synthetic_real(m['real_seed'], m['batch'], m['nc'])).cuda()
+    noises = synthetic_noise(m['noise_seed'], m['batch'] * m['iters'], m['nz']).reshape(m['iters'], m['batch'], m['nz'], 1, 1)
+    r = reference_loop_step(G, D, optG, optD, real, torch.from_numpy(noises[0]).cuda())
+    # north star: bf16 rtol 2e-2 against the fp32 reference (probabilities, losses, generator output)
+    for k in ('errG', 'errD', 'D_x', 'D_G_z1', 'D_G_z2', 'p_real', 'p_fake', 'p_fake_for_G'):
+        close(r[k], g[f'it0.{k}'], rtol=2e-2, atol=2e-3, what=k)
+    close(r['fake'][:, :, ::3, ::3], g['it0.fake'], rtol=2e-2, atol=2e-2, what='fake')
+    for net in ('grads_D', 'grads_G'):
+        for k, v in r[net].items():
+            grad_close(v, g[f'it0.{net}.{k}'], f'{net}.{k}', bulk=2e-2, l2=6e-2, worst=0.3)
+    for tag, net in (('G', G), ('D', D)):
+        for k, v in net.state_dict().items():
+            if k.endswith('weight') or k.endswith('bias'):
+                # one Adam step moves every weight by ~lr; bf16 gradient noise may flip near-zero ones (2*lr)
+                assert np.abs(v.cpu().numpy() - g[f'final.{tag}.{k}']).max() <= 2.05 * m['lr'] * m['iters'] + 1e-6, k
+
+
+def test_full_size_fp32_checksums():
+    g = np.load(os.path.join(GOLDEN, 'step_full_nc1.npz'))
+    m = json.loads(str(g['meta']))
+    G, D = build(m, torch.float32)
+    optD = torch.optim.Adam(D.parameters(), lr=m['lr'], betas=(m['beta1'], 0.999))
+    optG = torch.optim.Adam(G.parameters(), lr=m['lr'], betas=(m['beta1'], 0.999))
+    real = torch.from_numpy(synthetic_real(m['real_seed'], m['batch'], m['nc'])).cuda()
+    noise = torch.from_numpy(synthetic_noise(m['noise_seed'], m['batch'], m['nz'])).cuda()
+    r = reference_loop_step(G, D, optG, optD, real, noise)
+    for k in ('errG', 'errD', 'D_x', 'D_G_z1', 'D_G_z2', 'p_real', 'p_fake', 'p_fake_for_G'):
+        close(r[k], g[f'it0.{k}'], rtol=1e-4, atol=1e-6, what=k)
+    close(r['fake'][:, :, ::7, ::7], g['it0.fake_sample'], atol=1e-5, what='fake_sample')
+    for net in ('grads_D', 'grads_G'):
+        for k, v in r[net].items():
+            l2 = np.sqrt((v.astype(np.float64) ** 2).sum())
+            close(l2, g[f'it0.{net}.{k}.l2'], rtol=1e-3, what=f'{net}.{k}.l2')
+            grad_close(v.reshape(-1)[::max(1, v.size // 64)][:64], g[f'it0.{net}.{k}.sample'], f'{net}.{k}', bulk=1e-4)
+
+
+def test_state_dict_roundtrip_eval_forward_and_vis_side_effects():
+    """generate_synthetic.py's path: load_state_dict -> eval() -> forward under no_grad; plus SURVEY fact X5:
+    a train-mode forward under no_grad still updates the BatchNorm buffers."""
+    m = dict(seed=7, nz=16, nc=3, fm=8)
+    G, _ = build(m, torch.float32)
+    z = torch.from_numpy(synthetic_noise(3, 4, 16)).cuda()
+    sd_np = {k: v.cpu().numpy().copy() for k, v in G.state_dict().items()}
+    oracle = orc.GeneratorOracle(16, 3, 8, {k: v.copy() for k, v in sd_np.items()})
+    with torch.no_grad():
+        out_train = G(z)                                   # train mode: buffers move
+    ref_train, _ = oracle.forward(z.cpu().numpy(), train=True)
+    close(out_train.cpu().numpy(), ref_train, rtol=1e-4, atol=1e-5, what='train-mode no_grad forward')
+    assert int(G.main[1].num_batches_tracked) == 1
+    close(G.main[1].running_mean.cpu().numpy(), oracle.sd['main.1.running_mean'], rtol=1e-4, atol=1e-6, what='running_mean')
+    close(G.main[4].running_var.cpu().numpy(), oracle.sd['main.4.running_var'], rtol=1e-4, atol=1e-6, what='running_var')
+    G.eval()
+    with torch.no_grad():
+        out_eval = G(z)
+    ref_eval, _ = oracle.forward(z.cpu().numpy(), train=False)
+    close(out_eval.cpu().numpy(), ref_eval, rtol=1e-4, atol=1e-5, what='eval forward')
+    assert int(G.main[1].num_batches_tracked) == 1        # eval does not touch the buffers

@@ -107,3 +107,23 @@ def test_step_full_size_checksums():
             l2 = np.sqrt((v.astype(np.float64) ** 2).sum())
             close(l2, g[f'it0.{net}.{k}.l2'], rtol=5e-4, what=f'{net}.{k}.l2')
             grad_close(v.reshape(-1)[::max(1, v.size // 64)][:64], g[f'it0.{net}.{k}.sample'], f'{net}.{k}')
+
+
+def test_torch_port_matches_fixture():
+    """oracle/torch_cpu_port.py (the CPU timing baseline) reproduces the reference fixture on the same inputs."""
+    import torch
+    import torch_cpu_port as port
+    g = np.load(os.path.join(GOLDEN, 'step_small_nc1.npz'))
+    m = json.loads(str(g['meta']))
+    rng = np.random.RandomState(m['seed'])
+    sdG = orc.init_state(orc.generator_plan(m['nz'], m['nc'], m['fm']), True, rng)
+    sdD = orc.init_state(orc.discriminator_plan(m['nc'], m['fm']), False, rng)
+    st = port.CpuStepper(nz=m['nz'], nc=m['nc'], ngf=m['fm'], ndf=m['fm'], lr=m['lr'], beta1=m['beta1'])
+    st.G.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in sdG.items()})
+    st.D.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in sdD.items()})
+    real = torch.from_numpy(synthetic_real(m['real_seed'], m['batch'], m['nc']))
+    noises = synthetic_noise(m['noise_seed'], m['batch'] * m['iters'], m['nz']).reshape(m['iters'], m['batch'], m['nz'], 1, 1)
+    for it in range(m['iters']):
+        errD, errG, D_x, z1, z2 = st.step(real, torch.from_numpy(noises[it]))
+        for k, v in (('errD', errD), ('errG', errG), ('D_x', D_x), ('D_G_z1', z1), ('D_G_z2', z2)):
+            close(v, g[f'it{it}.{k}'], rtol=1e-6, atol=1e-7, what=f'it{it}.{k}')
