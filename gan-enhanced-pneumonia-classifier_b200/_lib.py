@@ -43,6 +43,7 @@ PROTOTYPES = {
     'b200gan_convT2d_fprop': [_CP, _VP, _vp, _vp, _VP, _vp],
     'b200gan_convT2d_dgrad': [_CP, _VP, _vp, _vp, _VP, _vp],
     'b200gan_convT2d_wgrad': [_CP, _VP, _VP, _vp, _vp],
+    'b200gan_pack_conv_weight': [_vp, _i32, _i32, _i32, _i32, _vp, _vp],
     'b200gan_bn_stats': [_VP, _vp, _vp],
     'b200gan_bn_finalize': [_vp, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _vp, _vp, _vp, _vp, _vp],
     'b200gan_bn_eval_coeffs': [_i32, _vp, _vp, _vp, _vp, _f32, _vp, _vp, _vp],

@@ -30,6 +30,7 @@ int simt_conv_wgrad(const b200gan_conv*, const b200gan_view* x, const b200gan_vi
 int tc_conv_fprop(const b200gan_conv*, const b200gan_view* x, const void* wpacked, const b200gan_view* y, cudaStream_t);
 int tc_conv_dgrad(const b200gan_conv*, const b200gan_view* dy, const void* wpacked, const b200gan_view* dx, cudaStream_t);
 int tc_conv_wgrad(const b200gan_conv*, const b200gan_view* x, const b200gan_view* dy, float* dw, cudaStream_t);
+int tc_pack_weight(const float* w, int Co, int Ci, int k, int form, void* out, cudaStream_t);
 // elementwise.cu
 int ew_bn_stats(const b200gan_view*, double*, cudaStream_t);
 int ew_bn_bwd_reduce(const b200gan_view*, const b200gan_view*, const b200gan_view*, const float*, const float*, const float*,
@@ -138,6 +139,11 @@ int b200gan_convT2d_dgrad(const b200gan_conv* cv, const b200gan_view* dy, const 
 }
 int b200gan_convT2d_wgrad(const b200gan_conv* cv, const b200gan_view* x, const b200gan_view* dy, float* dweight, void* stream) {
   return conv_dispatch(WGRAD, cv, dy, x, nullptr, nullptr, dweight, stream, "convT2d_wgrad");
+}
+
+int b200gan_pack_conv_weight(const float* weight, int32_t co, int32_t ci, int32_t k, int32_t form, void* out, void* stream) {
+  B200_CHECK_ARG(weight && out && co > 0 && ci > 0 && (form == 0 || form == 1), "pack_conv_weight: bad argument");
+  return tc_pack_weight(weight, co, ci, k, form, out, (cudaStream_t)stream);
 }
 
 int b200gan_bn_stats(const b200gan_view* y, double* sums, void* stream) {

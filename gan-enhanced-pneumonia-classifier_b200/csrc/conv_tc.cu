@@ -1,10 +1,430 @@
-// tcgen05 / TMEM / TMA implicit-GEMM convolutions (sm_100a).  Placeholder until the tensor-core kernels
-// land: every entry reports "does not qualify" (1) so the dispatcher uses the SIMT path, or fails
-// loudly when B200GAN_ALGO_TCGEN05 is forced.
+// tcgen05 / TMEM / TMA implicit-GEMM convolutions for sm_100a (B200): the tensor-core path of the k4 s2 p1
+// layers of the DCGAN (dcgan.py:30-46 ConvTranspose2d, :68-80 Conv2d) and of their input gradients.
+//
+// One kernel, two geometries (all tensors NHWC bf16, fp32 accumulation in TMEM):
+//   DOWN  (Conv2d fprop, ConvTranspose2d dgrad):  out[n,oh,ow,:] = sum_{kh,kw} in[n,2oh-1+kh,2ow-1+kw,:] . W[:, (kh,kw,:)]
+//         GEMM  M = N*OH*OW, K = 16*Cin, N = Cout
+//   UP    (ConvTranspose2d fprop, Conv2d dgrad), one GEMM per output parity class (py,px) (blockIdx.z):
+//         out[n,2q+py,2r+px,:] = sum_{jh,jw in {0,1}} in[n,q+ch-jh,r+cw-jw,:] . Wc[:, (jh,jw,:)],  ch=(py+1)/2
+//         GEMM  M = N*H*W, K = 4*Cin, N = Cout  -- no zero-insertion, no multiply-by-zero work.
+// A tile (128 GEMM rows x KC channels) is ONE 4-d TMA box {KC, TW*s, TH*s, TN} with element strides {1,s,s,1}
+// over the NHWC tensor: TN images x TH rows x TW columns of output pixels; convolution padding is the TMA
+// out-of-bounds zero fill (negative / past-the-end coordinates), so no im2col buffer and no padded copies exist.
+// The weight tile (BN x KC, K-major, pre-packed bf16) is one 3-d TMA box.  Both land in 128B- (KC=64) or
+// 64B- (KC=32) swizzled shared memory and are consumed by tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN,
+// K=16) issued by one thread; a STAGES-deep mbarrier ring decouples TMA from MMA; four epilogue warps read
+// the accumulator with tcgen05.ld and store bf16 NHWC rows.
+#include <cuda.h>
+#include <stdio.h>
+
 #include "common.cuh"
 
 namespace b200gan {
-int tc_conv_fprop(const b200gan_conv*, const b200gan_view*, const void*, const b200gan_view*, cudaStream_t) { return 1; }
-int tc_conv_dgrad(const b200gan_conv*, const b200gan_view*, const void*, const b200gan_view*, cudaStream_t) { return 1; }
+
+// ---------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok;
+}
+// Bounded spin: a pipeline bug must surface as a trapped kernel (sticky CUDA error), never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 24)) {
+      printf("b200gan: mbarrier wait timed out (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], bf16 x bf16 -> fp32, issued by ONE thread
+__device__ __forceinline__ void tcgen05_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_ld_32x32b_x32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, "
+      "%19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tcgen05_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
+// version=1 [46,48), layout type [61,64) (2 = SWIZZLE_128B, 4 = SWIZZLE_64B)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)layout_type << 61;
+  return d;
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor) for kind::f16: D=f32, A=B=bf16
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------------------------------
+struct TcConvParams {
+  int tiles_w, tiles_h, tiles_n;     // tiles of the GEMM-row pixel space (TW x TH x TN pixels each, product 128)
+  int tw_log2, th_log2;              // log2(TW), log2(TH)
+  int a_mul;                         // input coordinate = tile origin * a_mul + tap offset
+  int taps;                          // 16 (DOWN) or 4 (UP)
+  int chunks;                        // Cin / KC
+  int8_t tap_dh[4][16], tap_dw[4][16];   // [class][tap]
+  int QH, QW, NB;                    // valid extent of the pixel space (rows beyond are discarded)
+  __nv_bfloat16* out;
+  int64_t o_sn, o_sh, o_sw;
+  int o_mul;                         // output pixel = q*o_mul + class parity
+  int cout;
+};
+
+template <int BN, int KC, int STAGES>
+struct TcSmem {
+  static constexpr int A_BYTES = 128 * KC * 2;
+  static constexpr int B_BYTES = BN * KC * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN, int KC, int STAGES>
+__global__ void __launch_bounds__(192, 1)
+conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcConvParams p) {
+  using S = TcSmem<BN, KC, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* accum_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cls = blockIdx.z;
+  // tile origin
+  int t = blockIdx.x;
+  const int tw_i = t % p.tiles_w; t /= p.tiles_w;
+  const int th_i = t % p.tiles_h;
+  const int tn_i = t / p.tiles_h;
+  const int TW = 1 << p.tw_log2, TH = 1 << p.th_log2, TN = 128 >> (p.tw_log2 + p.th_log2);
+  const int w0 = tw_i * TW, h0 = th_i * TH, n0 = tn_i * TN;
+  const int cout0 = blockIdx.y * BN;
+  const int num_kb = p.taps * p.chunks;
+  constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+  }
+  if (warp == 1) {   // TMEM allocation by one full warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer (one lane) =====
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        const int tap = kb / p.chunks, chunk = kb - tap * p.chunks;
+        uint8_t* sa = smem + s * S::STAGE_BYTES;
+        uint8_t* sb = sa + S::A_BYTES;
+        mbar_expect_tx(&full_bar[s], S::STAGE_BYTES);
+        tma_load_4d(sa, &map_a, &full_bar[s], chunk * KC, w0 * p.a_mul + p.tap_dw[cls][tap], h0 * p.a_mul + p.tap_dh[cls][tap], n0);
+        tma_load_3d(sb, &map_b, &full_bar[s], kb * KC, cout0, cls);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===== MMA issuer (one lane) =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
+      constexpr uint32_t LT = KC == 64 ? 2u : 4u;          // SWIZZLE_128B : SWIZZLE_64B
+      constexpr uint32_t SBO = 8 * KC * 2;                 // 8 rows of KC bf16
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tcgen05_fence_after();
+        const uint32_t sa = smem_u32(smem + s * S::STAGE_BYTES), sb = sa + S::A_BYTES;
+#pragma unroll
+        for (int k = 0; k < KC / 16; ++k) {
+          const uint64_t adesc = make_smem_desc(sa + k * 32, 16, SBO, LT);
+          const uint64_t bdesc = make_smem_desc(sb + k * 32, 16, SBO, LT);
+          tcgen05_mma_f16(tmem_base, adesc, bdesc, idesc, (kb | k) != 0);
+        }
+        tcgen05_commit(&empty_bar[s]);                     // frees the smem stage when these MMAs retire
+      }
+      tcgen05_commit(accum_bar);                           // accumulator complete
+    }
+    __syncwarp();
+  } else {
+    // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int tw = row & (TW - 1), th = (row >> p.tw_log2) & (TH - 1), tn = row >> (p.tw_log2 + p.th_log2);
+    const int ow = w0 + tw, oh = h0 + th, n = n0 + tn;
+    const bool valid = ow < p.QW && oh < p.QH && n < p.NB;
+    const int py = cls >> 1, px = cls & 1;
+    __nv_bfloat16* orow = p.out + (int64_t)n * p.o_sn + (int64_t)(oh * p.o_mul + (p.o_mul > 1 ? py : 0)) * p.o_sh +
+                          (int64_t)(ow * p.o_mul + (p.o_mul > 1 ? px : 0)) * p.o_sw + cout0;
+    mbar_wait(accum_bar, 0);
+    tcgen05_fence_after();
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t r[32];
+      tcgen05_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + c0, r);
+      tcgen05_wait_ld();
+      if (valid) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          if (cout0 + c0 + j < p.cout) {
+            uint4 v;
+            __nv_bfloat162 b0 = __floats2bfloat162_rn(__uint_as_float(r[j + 0]), __uint_as_float(r[j + 1]));
+            __nv_bfloat162 b1 = __floats2bfloat162_rn(__uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+            __nv_bfloat162 b2 = __floats2bfloat162_rn(__uint_as_float(r[j + 4]), __uint_as_float(r[j + 5]));
+            __nv_bfloat162 b3 = __floats2bfloat162_rn(__uint_as_float(r[j + 6]), __uint_as_float(r[j + 7]));
+            v.x = *reinterpret_cast<uint32_t*>(&b0); v.y = *reinterpret_cast<uint32_t*>(&b1);
+            v.z = *reinterpret_cast<uint32_t*>(&b2); v.w = *reinterpret_cast<uint32_t*>(&b3);
+            *reinterpret_cast<uint4*>(orow + c0 + j) = v;
+          }
+        }
+      }
+    }
+    tcgen05_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+static int ilog2_exact(int v) {
+  int l = 0;
+  while ((1 << l) < v) ++l;
+  return (1 << l) == v ? l : -1;
+}
+
+// choose TW x TH x TN = 128 output pixels per tile: powers of two dividing the spatial extent
+static void pick_tile(int qh, int qw, int* tw, int* th) {
+  int w = 1;
+  while (w * 2 <= 16 && qw % (w * 2) == 0) w *= 2;
+  int h = 1;
+  while (h * 2 * w <= 128 && h * 2 <= 16 && qh % (h * 2) == 0) h *= 2;
+  *tw = w; *th = h;
+}
+
+static bool nhwc_dense_bf16(const b200gan_view* v) {
+  return v->dtype == B200GAN_BF16 && v->sc == 1 && v->sw == v->c && v->sh == (int64_t)v->w * v->c &&
+         v->sn == (int64_t)v->h * v->w * v->c && (reinterpret_cast<uintptr_t>(v->ptr) & 15) == 0;
+}
+
+template <int BN, int KC, int STAGES>
+static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcConvParams& p, dim3 grid, cudaStream_t st) {
+  using S = TcSmem<BN, KC, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    B200_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, KC, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    configured = true;
+  }
+  conv_gemm_tc_kernel<BN, KC, STAGES><<<grid, 192, S::TOTAL, st>>>(ma, mb, p);
+  B200_LAUNCH_CHECK("conv_gemm_tc_kernel");
+  return 0;
+}
+
+// `in`: the gathered operand (NHWC bf16 dense), `out`: result (NHWC bf16 dense), up=false: DOWN geometry
+// (in is the fine side), up=true: UP geometry (in is the coarse side).  wpacked: see b200gan_pack_conv_weight.
+static int tc_conv_common(const b200gan_conv* cv, const b200gan_view* in, const void* wpacked, const b200gan_view* out, bool up,
+                          cudaStream_t st) {
+  if (cv->k != 4 || cv->stride != 2 || cv->pad != 1) return 1;
+  if (!wpacked) return 1;
+  if (!nhwc_dense_bf16(in) || !nhwc_dense_bf16(out)) return 1;
+  const int cin = in->c, cout = out->c;
+  if (cin % 32 != 0 || cout % 32 != 0) return 1;
+  const int KC = cin % 64 == 0 ? 64 : 32;
+  const int BN = cout % 128 == 0 ? 128 : (cout % 64 == 0 ? 64 : 32);
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return B200GAN_ERR_CUDA; }
+  // GEMM-row pixel space: DOWN -> output pixels (OH,OW); UP -> input pixels (H,W) per parity class
+  const int QH = up ? in->h : out->h, QW = up ? in->w : out->w, NB = in->n;
+  int TW, TH;
+  pick_tile(QH, QW, &TW, &TH);
+  const int TN = 128 / (TW * TH);
+  TcConvParams p{};
+  p.tiles_w = QW / TW; p.tiles_h = QH / TH; p.tiles_n = (NB + TN - 1) / TN;
+  p.tw_log2 = ilog2_exact(TW); p.th_log2 = ilog2_exact(TH);
+  p.a_mul = up ? 1 : 2;
+  p.taps = up ? 4 : 16;
+  p.chunks = cin / KC;
+  for (int cls = 0; cls < 4; ++cls)
+    for (int t = 0; t < p.taps; ++t) {
+      if (up) {
+        const int py = cls >> 1, px = cls & 1, jh = t >> 1, jw = t & 1;
+        p.tap_dh[cls][t] = (int8_t)((py + 1) / 2 - jh);
+        p.tap_dw[cls][t] = (int8_t)((px + 1) / 2 - jw);
+      } else {
+        p.tap_dh[cls][t] = (int8_t)((t >> 2) - 1);
+        p.tap_dw[cls][t] = (int8_t)((t & 3) - 1);
+      }
+    }
+  p.QH = QH; p.QW = QW; p.NB = NB;
+  p.out = reinterpret_cast<__nv_bfloat16*>(out->ptr);
+  p.o_sn = out->sn; p.o_sh = out->sh; p.o_sw = out->sw; p.o_mul = up ? 2 : 1; p.cout = cout;
+
+  CUtensorMap ma, mb;
+  {
+    const int s = up ? 1 : 2;
+    cuuint64_t gdim[4] = {(cuuint64_t)cin, (cuuint64_t)in->w, (cuuint64_t)in->h, (cuuint64_t)in->n};
+    cuuint64_t gstr[3] = {(cuuint64_t)cin * 2, (cuuint64_t)in->w * cin * 2, (cuuint64_t)in->h * in->w * cin * 2};
+    cuuint32_t box[4] = {(cuuint32_t)KC, (cuuint32_t)(TW * s), (cuuint32_t)(TH * s), (cuuint32_t)TN};
+    cuuint32_t estr[4] = {1, (cuuint32_t)s, (cuuint32_t)s, 1};
+    CUresult r = enc(&ma, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, in->ptr, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(A) failed: %d", (int)r); return B200GAN_ERR_CUDA; }
+  }
+  {
+    const int ktot = p.taps * cin, ncls = up ? 4 : 1;
+    cuuint64_t gdim[3] = {(cuuint64_t)ktot, (cuuint64_t)cout, (cuuint64_t)ncls};
+    cuuint64_t gstr[2] = {(cuuint64_t)ktot * 2, (cuuint64_t)ktot * cout * 2};
+    cuuint32_t box[3] = {(cuuint32_t)KC, (cuuint32_t)BN, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&mb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(wpacked), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(B) failed: %d", (int)r); return B200GAN_ERR_CUDA; }
+  }
+  dim3 grid((unsigned)(p.tiles_w * p.tiles_h * p.tiles_n), (unsigned)(cout / BN), up ? 4 : 1);
+  if (KC == 64) {
+    if (BN == 128) return launch_tc<128, 64, 4>(ma, mb, p, grid, st);
+    if (BN == 64) return launch_tc<64, 64, 4>(ma, mb, p, grid, st);
+    return launch_tc<32, 64, 4>(ma, mb, p, grid, st);
+  }
+  if (BN == 128) return launch_tc<128, 32, 4>(ma, mb, p, grid, st);
+  if (BN == 64) return launch_tc<64, 32, 4>(ma, mb, p, grid, st);
+  return launch_tc<32, 32, 4>(ma, mb, p, grid, st);
+}
+
+int tc_conv_fprop(const b200gan_conv* cv, const b200gan_view* x, const void* wpacked, const b200gan_view* y, cudaStream_t st) {
+  return tc_conv_common(cv, x, wpacked, y, /*up=*/false, st);
+}
+int tc_conv_dgrad(const b200gan_conv* cv, const b200gan_view* dy, const void* wpacked, const b200gan_view* dx, cudaStream_t st) {
+  return tc_conv_common(cv, dy, wpacked, dx, /*up=*/true, st);
+}
 int tc_conv_wgrad(const b200gan_conv*, const b200gan_view*, const b200gan_view*, float*, cudaStream_t) { return 1; }
+
+// ---------------------------------------------------------------------------------------------------
+// weight repack: fp32 master (Co,Ci,4,4) [conv geometry] -> bf16 K-major GEMM operand
+//   form 0 (DOWN): Wp[co][(kh,kw,ci)]                       rows = Co, K = 16*Ci
+//   form 1 (UP)  : Wp[cls][ci][(jh,jw,co)], kh = rh + 2*jh   rows = Ci, K = 4*Co, rh = (py+1)%2
+// ---------------------------------------------------------------------------------------------------
+__global__ void pack_weight_kernel(const float* __restrict__ w, int Co, int Ci, int form, __nv_bfloat16* __restrict__ out) {
+  const int64_t total = (int64_t)Co * Ci * 16;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    float v;
+    if (form == 0) {
+      const int ci = (int)(i % Ci);
+      const int tap = (int)((i / Ci) % 16);
+      const int co = (int)(i / ((int64_t)Ci * 16));
+      v = w[((int64_t)co * Ci + ci) * 16 + tap];
+    } else {
+      const int co = (int)(i % Co);
+      const int j = (int)((i / Co) % 4);
+      const int ci = (int)((i / ((int64_t)Co * 4)) % Ci);
+      const int cls = (int)(i / ((int64_t)Co * 4 * Ci));
+      const int py = cls >> 1, px = cls & 1, jh = j >> 1, jw = j & 1;
+      const int kh = (py + 1) % 2 + 2 * jh, kw = (px + 1) % 2 + 2 * jw;
+      v = w[((int64_t)co * Ci + ci) * 16 + kh * 4 + kw];
+    }
+    out[i] = __float2bfloat16_rn(v);
+  }
+}
+
+int tc_pack_weight(const float* w, int Co, int Ci, int k, int form, void* out, cudaStream_t st) {
+  if (k != 4) { set_error("pack_conv_weight: only k=4 (stride 2, pad 1) layers have a tensor-core path"); return B200GAN_ERR_UNSUPPORTED; }
+  const int64_t total = (int64_t)Co * Ci * 16;
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > 4 * kNumSMs) blocks = 4 * kNumSMs;
+  pack_weight_kernel<<<(unsigned)blocks, 256, 0, st>>>(w, Co, Ci, form, reinterpret_cast<__nv_bfloat16*>(out));
+  B200_LAUNCH_CHECK("pack_weight_kernel");
+  return 0;
+}
+
 }  // namespace b200gan

@@ -95,12 +95,18 @@ int b200gan_convT2d_dgrad(const b200gan_conv* cv, const b200gan_view* dy, const 
 int b200gan_convT2d_wgrad(const b200gan_conv* cv, const b200gan_view* x, const b200gan_view* dy, float* dweight,
                           void* stream);
 
+/* ---- bf16 repack of a k=4 conv weight for the tcgen05 implicit GEMM (`wpacked` above).  `weight` is the fp32
+ *      master in conv geometry (Co,Ci,4,4) -- i.e. the Conv2d weight, or the ConvTranspose2d weight (Cin,Cout,4,4)
+ *      read as (Co=Cin, Ci=Cout).  form 0 ("down": Conv2d fprop / ConvTranspose2d dgrad): [Co][(kh,kw,Ci)];
+ *      form 1 ("up": ConvTranspose2d fprop / Conv2d dgrad): [parity class][Ci][(jh,jw,Co)].  out: Co*Ci*16 bf16. */
+int b200gan_pack_conv_weight(const float* weight, int32_t co, int32_t ci, int32_t k, int32_t form, void* out, void* stream);
+
 /* ---- nn.BatchNorm2d in training mode (dcgan.py:27,31,35,39,43,69,73,77,81) -------------------------
- * bn_stats:     sums[0..C) += sum y, sums[C..2C) += sum y^2 over (N,H,W)          (double accumulators)
+ * bn_stats:     sums[0..C) = sum y, sums[C..2C) = sum y^2 over (N,H,W)   (double accumulators, overwritten)
  * bn_finalize:  mean / biased var -> scale = gamma*invstd, shift = beta - mean*scale, saves mean and
  *               invstd for backward, updates running_mean/var (momentum, UNBIASED var) and
- *               num_batches_tracked (int64) exactly like torch; then clears `sums` for the next use.
- *               running_* / num_batches_tracked may be NULL (no tracking). */
+ *               num_batches_tracked (int64) exactly like torch.  running_* / num_batches_tracked may be NULL
+ *               (no tracking).  Under synchronised BatchNorm the caller all-reduces `sums` between the two. */
 int b200gan_bn_stats(const b200gan_view* y, double* sums, void* stream);
 int b200gan_bn_finalize(double* sums, int32_t channels, int64_t count, const float* gamma, const float* beta,
                         float* running_mean, float* running_var, int64_t* num_batches_tracked,
@@ -116,7 +122,7 @@ int b200gan_bn_act_fwd(const b200gan_view* y, const float* scale, const float* s
 
 /* Backward of act(BN(y)).  da: gradient w.r.t. the activation output; y: the saved conv output;
  * a: the saved activation output (only read for TANH / SIGMOID, may be NULL otherwise).
- * bwd_reduce: sums[0..C) += sum dz, sums[C..2C) += sum dz*xhat with dz = da*act'(.)   (native_batch_norm_backward)
+ * bwd_reduce: sums[0..C) = sum dz, sums[C..2C) = sum dz*xhat with dz = da*act'(.)     (native_batch_norm_backward)
  * bwd_apply:  dy = gamma*invstd*(dz - sum dz/count - xhat * sum(dz*xhat)/count); dgamma += sum dz*xhat,
  *             dbeta += sum dz (written by the first CTA); with scale == NULL: dy = dz (no BatchNorm). */
 int b200gan_bn_act_bwd_reduce(const b200gan_view* da, const b200gan_view* y, const b200gan_view* a,

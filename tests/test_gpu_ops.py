@@ -101,7 +101,8 @@ def test_convT2d_on_reference_nchw_views(mode):
     w0 = (rng.randn(10, 9, 7, 7) * 0.1).astype(np.float32)
     cv0 = L.Conv(7, 1, 0, L.ALGO_SIMT)
     y0 = torch.empty((3, 9, 7, 7), device='cuda')
-    L.call('b200gan_convT2d_fprop', C.byref(cv0), C.byref(L.view_nchw(dev(z))), L.ptr(dev(w0)), None, C.byref(L.view_nchw(y0)), st())
+    zd, w0d = dev(z), dev(w0)          # keep the device tensors alive across the asynchronous launch
+    L.call('b200gan_convT2d_fprop', C.byref(cv0), C.byref(L.view_nchw(zd)), L.ptr(w0d), None, C.byref(L.view_nchw(y0)), st())
     close(y0.cpu().numpy(), orc.convT2d_fprop(z, w0, 1, 0), what='G0 fprop')
 
 
@@ -175,7 +176,8 @@ def test_bn_eval_tanh_sigmoid_and_copy():
     gamma, beta = rng.normal(1, .1, c).astype(np.float32), rng.normal(0, .1, c).astype(np.float32)
     rm, rv = rng.randn(c).astype(np.float32), (rng.rand(c) + .5).astype(np.float32)
     scale, shift = torch.empty(c, device='cuda'), torch.empty(c, device='cuda')
-    L.call('b200gan_bn_eval_coeffs', c, L.ptr(dev(gamma)), L.ptr(dev(beta)), L.ptr(dev(rm)), L.ptr(dev(rv)), 1e-5, L.ptr(scale), L.ptr(shift), st())
+    gd, bd, rmd, rvd = dev(gamma), dev(beta), dev(rm), dev(rv)
+    L.call('b200gan_bn_eval_coeffs', c, L.ptr(gd), L.ptr(bd), L.ptr(rmd), L.ptr(rvd), 1e-5, L.ptr(scale), L.ptr(shift), st())
     yd = dev(y)                                                 # NCHW view in, NHWC bf16 out (mixed dtypes + layouts)
     a = torch.empty((2, 5, 5, c), device='cuda', dtype=torch.bfloat16)
     L.call('b200gan_bn_act_fwd', C.byref(L.view_nchw(yd)), L.ptr(scale), L.ptr(shift), L.ACT_TANH, 0.0, C.byref(L.view_nhwc(a)), st())
@@ -213,7 +215,8 @@ def test_adam_matches_torch_formula(numel):
     for step in (1, 2, 3, 10):
         g = (rng.randn(numel) * 10.0 ** rng.randint(-6, 1, numel)).astype(np.float32)
         orc.adam_step(po, g, m, v, step, 2e-4, 0.5)
-        L.call('b200gan_adam', L.ptr(pd), L.ptr(dev(g)), L.ptr(md), L.ptr(vd), numel, 2e-4, 0.5, 0.999, 1e-8, step, 1.0, st())
+        gdev = dev(g)
+        L.call('b200gan_adam', L.ptr(pd), L.ptr(gdev), L.ptr(md), L.ptr(vd), numel, 2e-4, 0.5, 0.999, 1e-8, step, 1.0, st())
         close(pd.cpu().numpy(), po, rtol=1e-6, atol=1e-7, what=f'param step {step}')
         close(md.cpu().numpy(), m, rtol=1e-5, atol=1e-12, what='exp_avg')
         close(vd.cpu().numpy(), v, rtol=1e-5, atol=1e-20, what='exp_avg_sq')

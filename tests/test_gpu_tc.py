@@ -1,0 +1,94 @@
+"""tcgen05 implicit-GEMM convolutions (forced with ALGO_TCGEN05, so a silent SIMT fallback cannot pass) against
+the numpy oracle (small shapes) and the fp32-accumulating SIMT kernels (every layer shape of the DCGAN)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+import dcgan_oracle as orc
+import gan_enhanced_pneumonia_classifier_b200 as pkg
+from parity_utils import close
+
+L = pkg._lib
+pytestmark = pytest.mark.gpu
+
+
+def st():
+    return L.stream_ptr()
+
+
+def bf16_exact(shape, scale, seed):
+    g = torch.Generator(device='cuda').manual_seed(seed)
+    return (torch.randn(shape, device='cuda', generator=g) * scale).to(torch.bfloat16)
+
+
+def pack(w, form):
+    co, ci, k, _ = w.shape
+    out = torch.empty(co * ci * k * k, device='cuda', dtype=torch.bfloat16)
+    L.call('b200gan_pack_conv_weight', L.ptr(w), co, ci, k, form, L.ptr(out), st())
+    return out
+
+
+def run_pair(n, ci, h, w_, co, direction):
+    """direction 'down': y = conv2d(x) with x (n,h,w,ci) -> (n,h/2,w/2,co); 'up': dx = conv2d_dgrad(dy)."""
+    cv_tc, cv_simt = L.Conv(4, 2, 1, L.ALGO_TCGEN05), L.Conv(4, 2, 1, L.ALGO_SIMT)
+    wt = bf16_exact((co, ci, 4, 4), 0.05, 1).float().contiguous()          # bf16-representable fp32 master
+    if direction == 'down':
+        x = bf16_exact((n, h, w_, ci), 1.0, 2)
+        y_tc = torch.full((n, h // 2, w_ // 2, co), float('nan'), device='cuda', dtype=torch.bfloat16)
+        y_ref = torch.empty_like(y_tc)
+        wp = pack(wt, 0)
+        L.call('b200gan_conv2d_fprop', C.byref(cv_tc), C.byref(L.view_nhwc(x)), L.ptr(wt), L.ptr(wp), C.byref(L.view_nhwc(y_tc)), st())
+        L.call('b200gan_conv2d_fprop', C.byref(cv_simt), C.byref(L.view_nhwc(x)), L.ptr(wt), None, C.byref(L.view_nhwc(y_ref)), st())
+        torch.cuda.synchronize()
+        return x, wt, y_tc, y_ref
+    dy = bf16_exact((n, h, w_, co), 1.0, 3)                                  # coarse side (n,h,w,co) -> fine (n,2h,2w,ci)
+    dx_tc = torch.full((n, 2 * h, 2 * w_, ci), float('nan'), device='cuda', dtype=torch.bfloat16)
+    dx_ref = torch.empty_like(dx_tc)
+    wp = pack(wt, 1)
+    L.call('b200gan_conv2d_dgrad', C.byref(cv_tc), C.byref(L.view_nhwc(dy)), L.ptr(wt), L.ptr(wp), C.byref(L.view_nhwc(dx_tc)), st())
+    L.call('b200gan_conv2d_dgrad', C.byref(cv_simt), C.byref(L.view_nhwc(dy)), L.ptr(wt), None, C.byref(L.view_nhwc(dx_ref)), st())
+    torch.cuda.synchronize()
+    return dy, wt, dx_tc, dx_ref
+
+
+def report(tag, got, ref):
+    g, r = got.float(), ref.float()
+    err = (g - r).abs().max().item()
+    print(f'{tag}: max|diff|={err:.4e} ref max={r.abs().max().item():.3e} nan={torch.isnan(g).sum().item()}')
+    return err
+
+
+# (n, cin, h, w, cout): every k4s2p1 layer shape of the DCGAN at a small batch + ragged batches
+DOWN = [(2, 64, 16, 16, 128), (3, 32, 112, 112, 64), (5, 64, 56, 56, 128), (9, 128, 28, 28, 256), (130, 256, 14, 14, 512),
+        (2, 32, 8, 24, 32), (3, 64, 12, 20, 64)]
+UP = [(2, 128, 8, 8, 64), (130, 512, 7, 7, 256), (9, 256, 14, 14, 128), (5, 128, 28, 28, 64), (3, 64, 56, 56, 32),
+      (2, 32, 4, 12, 32), (3, 64, 6, 10, 64)]
+
+
+@pytest.mark.parametrize('case', DOWN)
+def test_tc_down_conv_matches_simt(case):
+    n, ci, h, w_, co = case
+    x, wt, y_tc, y_ref = run_pair(n, ci, h, w_, co, 'down')
+    report(f'down {case}', y_tc, y_ref)
+    assert not torch.isnan(y_tc.float()).any()
+    close(y_tc.float().cpu().numpy(), y_ref.float().cpu().numpy(), rtol=1.6e-2, atol=2e-2, what=f'down {case}')
+
+
+@pytest.mark.parametrize('case', UP)
+def test_tc_up_conv_matches_simt(case):
+    n, co, h, w_, ci = case          # dy has `co` channels, result has `ci`
+    dy, wt, dx_tc, dx_ref = run_pair(n, ci, h, w_, co, 'up')
+    report(f'up {case}', dx_tc, dx_ref)
+    assert not torch.isnan(dx_tc.float()).any()
+    close(dx_tc.float().cpu().numpy(), dx_ref.float().cpu().numpy(), rtol=1.6e-2, atol=2e-2, what=f'up {case}')
+
+
+def test_tc_against_numpy_oracle():
+    x, wt, y_tc, _ = run_pair(2, 64, 16, 16, 128, 'down')
+    ref = orc.conv2d_fprop(x.float().cpu().numpy().transpose(0, 3, 1, 2), wt.cpu().numpy(), 2, 1)
+    close(y_tc.float().cpu().numpy().transpose(0, 3, 1, 2), ref, rtol=1e-2, atol=1e-2, what='down vs oracle')
+    dy, wt, dx_tc, _ = run_pair(2, 64, 8, 8, 128, 'up')
+    ref = orc.conv2d_dgrad(dy.float().cpu().numpy().transpose(0, 3, 1, 2), wt.cpu().numpy(), 2, 1, (16, 16))
+    close(dx_tc.float().cpu().numpy().transpose(0, 3, 1, 2), ref, rtol=1e-2, atol=1e-2, what='up vs oracle')
