@@ -388,7 +388,228 @@ int tc_conv_fprop(const b200gan_conv* cv, const b200gan_view* x, const void* wpa
 int tc_conv_dgrad(const b200gan_conv* cv, const b200gan_view* dy, const void* wpacked, const b200gan_view* dx, cudaStream_t st) {
   return tc_conv_common(cv, dy, wpacked, dx, /*up=*/true, st);
 }
-int tc_conv_wgrad(const b200gan_conv*, const b200gan_view*, const b200gan_view*, float*, cudaStream_t) { return 1; }
+
+// ---------------------------------------------------------------------------------------------------
+// weight gradient on tensor cores.  conv geometry: x (N,H,W,Ci) fine side, dy (N,OH,OW,Co) coarse side,
+//   dw[co,ci,kh,kw] += sum_{n,oh,ow} dy[n,oh,ow,co] * x[n,2oh-1+kh,2ow-1+kw,ci]
+// Per tap this is a GEMM D[co][ci] = A^T B with the PIXEL index as the reduction: both operands are
+// "MN-major" (channels contiguous), which tcgen05 reads directly from the NHWC tiles TMA delivers:
+//   A: 64 pixels x 128 co of dy  = two 4-d boxes {64ch, TW, TH, TN}            (reused by all taps of the CTA)
+//   B: 64 pixels x NCI ci of x at tap (kh,kw) = boxes {64ch, 2TW, 2TH, TN}, element strides {1,2,2,1}
+// A CTA owns 128 output channels x T taps x NCI input channels = 128 x 512 fp32 accumulators (all of TMEM),
+// walks a contiguous range of 64-pixel K-blocks (split-K over blockIdx.z) and adds its partial result into
+// the fp32 (Co,Ci,4,4) gradient with red.global.add.f32.
+// ---------------------------------------------------------------------------------------------------
+struct TcWgradParams {
+  int tiles_w, tiles_h, tiles_n;
+  int tw_log2, th_log2;
+  int kb_total, kb_per_split;
+  int T;            // taps per CTA
+  int ci_groups;    // Ci / NCI
+  int Co, Ci;
+  float* dw;
+};
+
+template <int NCI>
+struct TcWgradSmem {
+  static constexpr int BK = 64;                           // pixels per K-block
+  static constexpr int A_SLOTS = 3, STAGES = 4;
+  static constexpr int A_BYTES = BK * 128 * 2;            // 64 pixels x 128 co
+  static constexpr int B_BYTES = BK * NCI * 2;
+  static constexpr int TOTAL = A_SLOTS * A_BYTES + STAGES * B_BYTES + 1024 + 256;
+};
+
+template <int NCI>
+__global__ void __launch_bounds__(192, 1)
+conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x, const TcWgradParams p) {
+  using S = TcWgradSmem<NCI>;
+  constexpr int CB = NCI >= 64 ? 64 : NCI;                // channels per B box (128B or 64B rows)
+  constexpr int NBOX = NCI / CB;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + S::A_SLOTS * S::A_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + S::STAGES * S::B_BYTES);
+  uint64_t* empty_bar = full_bar + S::STAGES;
+  uint64_t* accum_bar = empty_bar + S::STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int co0 = blockIdx.x * 128;
+  const int tap_groups = 16 / p.T;
+  const int tg = blockIdx.y % tap_groups, cg = blockIdx.y / tap_groups;
+  const int tap0 = tg * p.T, ci0 = cg * NCI;
+  const int kb_beg = blockIdx.z * p.kb_per_split;
+  const int kb_end = min(kb_beg + p.kb_per_split, p.kb_total);
+  const int nkb = kb_end - kb_beg;
+  const int steps = nkb * p.T;
+  const int TW = 1 << p.tw_log2, TH = 1 << p.th_log2, TN = 64 >> (p.tw_log2 + p.th_log2);
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < S::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_dy) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int st = 0; st < steps; ++st) {
+        const int s = st % S::STAGES;
+        const uint32_t ph = (st / S::STAGES) & 1;
+        const int kbl = st / p.T, tl = st - kbl * p.T;
+        int t = kb_beg + kbl;
+        const int tw_i = t % p.tiles_w; t /= p.tiles_w;
+        const int th_i = t % p.tiles_h;
+        const int tn_i = t / p.tiles_h;
+        const int w0 = tw_i * TW, h0 = th_i * TH, n0 = tn_i * TN;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* sb = smem_b + s * S::B_BYTES;
+        if (tl == 0) {
+          uint8_t* sa = smem_a + (kbl % S::A_SLOTS) * S::A_BYTES;
+          mbar_expect_tx(&full_bar[s], S::A_BYTES + S::B_BYTES);
+          tma_load_4d(sa, &map_dy, &full_bar[s], co0, w0, h0, n0);
+          tma_load_4d(sa + S::A_BYTES / 2, &map_dy, &full_bar[s], co0 + 64, w0, h0, n0);
+        } else {
+          mbar_expect_tx(&full_bar[s], S::B_BYTES);
+        }
+        const int tap = tap0 + tl, kh = tap >> 2, kw = tap & 3;
+#pragma unroll
+        for (int b = 0; b < NBOX; ++b)
+          tma_load_4d(sb + b * (S::BK * CB * 2), &map_x, &full_bar[s], ci0 + b * CB, 2 * w0 - 1 + kw, 2 * h0 - 1 + kh, n0);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, NCI, 1, 1);       // both operands MN-major
+      constexpr uint32_t B_LT = CB == 64 ? 2u : 4u;
+      constexpr uint32_t B_ROW = CB * 2;                                // bytes per pixel row of a B box
+      for (int st = 0; st < steps; ++st) {
+        const int s = st % S::STAGES;
+        const uint32_t ph = (st / S::STAGES) & 1;
+        const int kbl = st / p.T, tl = st - kbl * p.T;
+        mbar_wait(&full_bar[s], ph);
+        tcgen05_fence_after();
+        const uint32_t sa = smem_u32(smem_a + (kbl % S::A_SLOTS) * S::A_BYTES);
+        const uint32_t sb = smem_u32(smem_b + s * S::B_BYTES);
+#pragma unroll
+        for (int k = 0; k < S::BK / 16; ++k) {
+          // MN-major canonical layout: LBO = distance between 64-channel groups, SBO = 8 pixel rows
+          const uint64_t adesc = make_smem_desc(sa + k * 16 * 128, S::A_BYTES / 2, 8 * 128, 2u);
+          const uint64_t bdesc = make_smem_desc(sb + k * 16 * B_ROW, S::BK * B_ROW, 8 * B_ROW, B_LT);
+          tcgen05_mma_f16(tmem_base + tl * NCI, adesc, bdesc, idesc, (kbl | k) != 0);
+        }
+        tcgen05_commit(&empty_bar[s]);
+      }
+      tcgen05_commit(accum_bar);
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3;
+    const int co = co0 + q * 32 + lane;
+    mbar_wait(accum_bar, 0);
+    tcgen05_fence_after();
+    if (steps > 0) {
+#pragma unroll 1
+      for (int c0 = 0; c0 < p.T * NCI; c0 += 32) {
+        uint32_t r[32];
+        tcgen05_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + c0, r);
+        tcgen05_wait_ld();
+        if (co < p.Co) {
+          const int tl = c0 / NCI, cil = c0 - tl * NCI;
+          float* dst = p.dw + ((int64_t)co * p.Ci + ci0 + cil) * 16 + tap0 + tl;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) atomicAdd(dst + j * 16, __uint_as_float(r[j]));
+        }
+      }
+    }
+    tcgen05_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+  }
+}
+
+template <int NCI>
+static int launch_wgrad(const CUtensorMap& mdy, const CUtensorMap& mx, const TcWgradParams& p, dim3 grid, cudaStream_t st) {
+  using S = TcWgradSmem<NCI>;
+  static bool configured = false;
+  if (!configured) {
+    B200_CUDA(cudaFuncSetAttribute(conv_wgrad_tc_kernel<NCI>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    configured = true;
+  }
+  conv_wgrad_tc_kernel<NCI><<<grid, 192, S::TOTAL, st>>>(mdy, mx, p);
+  B200_LAUNCH_CHECK("conv_wgrad_tc_kernel");
+  return 0;
+}
+
+int tc_conv_wgrad(const b200gan_conv* cv, const b200gan_view* x, const b200gan_view* dy, float* dw, cudaStream_t st) {
+  if (cv->k != 4 || cv->stride != 2 || cv->pad != 1) return 1;
+  if (!nhwc_dense_bf16(x) || !nhwc_dense_bf16(dy)) return 1;
+  const int Ci = x->c, Co = dy->c;
+  if (Co % 64 != 0 || (Ci != 32 && Ci != 64 && Ci != 128 && Ci % 256 != 0)) return 1;
+  const int NCI = Ci >= 256 ? 256 : Ci;
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return B200GAN_ERR_CUDA; }
+  int TW = 1, TH = 1;
+  while (TW * 2 <= 8 && dy->w % (TW * 2) == 0) TW *= 2;
+  while (TH * 2 * TW <= 64 && TH * 2 <= 8 && dy->h % (TH * 2) == 0) TH *= 2;
+  const int TN = 64 / (TW * TH);
+  TcWgradParams p{};
+  p.tiles_w = dy->w / TW; p.tiles_h = dy->h / TH; p.tiles_n = (dy->n + TN - 1) / TN;
+  p.tw_log2 = ilog2_exact(TW); p.th_log2 = ilog2_exact(TH);
+  p.kb_total = p.tiles_w * p.tiles_h * p.tiles_n;
+  p.T = 512 / NCI;
+  p.ci_groups = Ci / NCI;
+  p.Co = Co; p.Ci = Ci; p.dw = dw;
+  const int out_tiles = ((Co + 127) / 128) * (16 / p.T) * p.ci_groups;
+  int splits = (2 * kNumSMs + out_tiles - 1) / out_tiles;
+  if (splits > p.kb_total) splits = p.kb_total;
+  if (splits < 1) splits = 1;
+  p.kb_per_split = (p.kb_total + splits - 1) / splits;
+  splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
+
+  CUtensorMap mdy, mx;
+  {
+    cuuint64_t gdim[4] = {(cuuint64_t)Co, (cuuint64_t)dy->w, (cuuint64_t)dy->h, (cuuint64_t)dy->n};
+    cuuint64_t gstr[3] = {(cuuint64_t)Co * 2, (cuuint64_t)dy->w * Co * 2, (cuuint64_t)dy->h * dy->w * Co * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TN};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&mdy, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, dy->ptr, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(dy) failed: %d", (int)r); return B200GAN_ERR_CUDA; }
+  }
+  {
+    const int CB = NCI >= 64 ? 64 : NCI;
+    cuuint64_t gdim[4] = {(cuuint64_t)Ci, (cuuint64_t)x->w, (cuuint64_t)x->h, (cuuint64_t)x->n};
+    cuuint64_t gstr[3] = {(cuuint64_t)Ci * 2, (cuuint64_t)x->w * Ci * 2, (cuuint64_t)x->h * x->w * Ci * 2};
+    cuuint32_t box[4] = {(cuuint32_t)CB, (cuuint32_t)(2 * TW), (cuuint32_t)(2 * TH), (cuuint32_t)TN};
+    cuuint32_t estr[4] = {1, 2, 2, 1};
+    CUresult r = enc(&mx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, x->ptr, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CB == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(x) failed: %d", (int)r); return B200GAN_ERR_CUDA; }
+  }
+  dim3 grid((unsigned)((Co + 127) / 128), (unsigned)((16 / p.T) * p.ci_groups), (unsigned)splits);
+  switch (NCI) {
+    case 32: return launch_wgrad<32>(mdy, mx, p, grid, st);
+    case 64: return launch_wgrad<64>(mdy, mx, p, grid, st);
+    case 128: return launch_wgrad<128>(mdy, mx, p, grid, st);
+    default: return launch_wgrad<256>(mdy, mx, p, grid, st);
+  }
+}
 
 // ---------------------------------------------------------------------------------------------------
 // weight repack: fp32 master (Co,Ci,4,4) [conv geometry] -> bf16 K-major GEMM operand
