@@ -119,7 +119,7 @@ def _check_f32(t, what):
 
 
 class LayerCtx:
-    __slots__ = ('x', 'y', 'a', 'scale', 'shift', 'mean', 'invstd')
+    __slots__ = ('x', 'y', 'a', 'scale', 'shift', 'mean', 'invstd', 'wp_down', 'wp_up')
 
 
 class NetEngine:
@@ -131,15 +131,34 @@ class NetEngine:
         self.launches = 0     # kernels launched through this engine (bench.py's gpu_launches claim)
 
     # -- thin wrappers over the C ABI --------------------------------------------------------------
-    def _fprop(self, i, x: Act, w, y: Act, st):
-        name = 'b200gan_convT2d_fprop' if self.transposed else 'b200gan_conv2d_fprop'
-        L.call(name, C.byref(self._conv[i]), C.byref(x.v), L.ptr(w), None, C.byref(y.v), st)
-        self.launches += (self.specs[i].stride ** 2) if self.transposed else 1
+    def _tc_layer(self, i):
+        """Layers whose convolutions qualify for the tcgen05 implicit GEMM (bf16, k4 s2 p1, channels % 32 == 0)."""
+        sp = self.specs[i]
+        return (self.dtype == torch.bfloat16 and self.algo != L.ALGO_SIMT and sp.k == 4 and sp.stride == 2 and sp.pad == 1
+                and sp.cin % 32 == 0 and sp.cout % 32 == 0)
 
-    def _dgrad(self, i, dy: Act, w, dx: Act, st):
-        name = 'b200gan_convT2d_dgrad' if self.transposed else 'b200gan_conv2d_dgrad'
-        L.call(name, C.byref(self._conv[i]), C.byref(dy.v), L.ptr(w), None, C.byref(dx.v), st)
-        self.launches += 1 if self.transposed else (self.specs[i].stride ** 2)
+    def _pack(self, i, w, st):
+        """bf16 GEMM-operand repacks of the fp32 master weight: ('down' form, 'up' form), see b200gan_pack_conv_weight."""
+        if not self._tc_layer(i):
+            return None, None
+        co, ci = w.shape[0], w.shape[1]
+        down = torch.empty(w.numel(), device=w.device, dtype=torch.bfloat16)
+        up = torch.empty(w.numel(), device=w.device, dtype=torch.bfloat16)
+        L.call('b200gan_pack_conv_weight', L.ptr(w), co, ci, 4, 0, L.ptr(down), st)
+        L.call('b200gan_pack_conv_weight', L.ptr(w), co, ci, 4, 1, L.ptr(up), st)
+        self.launches += 2
+        return down, up
+
+    def _fprop(self, i, x: Act, w, y: Act, st, wp_down=None, wp_up=None):
+        # ConvTranspose2d forward is the 'up' geometry, Conv2d forward the 'down' geometry
+        name, wp = ('b200gan_convT2d_fprop', wp_up) if self.transposed else ('b200gan_conv2d_fprop', wp_down)
+        L.call(name, C.byref(self._conv[i]), C.byref(x.v), L.ptr(w), L.ptr(wp), C.byref(y.v), st)
+        self.launches += 1 if (wp is not None or not self.transposed) else self.specs[i].stride ** 2
+
+    def _dgrad(self, i, dy: Act, w, dx: Act, st, wp_down=None, wp_up=None):
+        name, wp = ('b200gan_convT2d_dgrad', wp_down) if self.transposed else ('b200gan_conv2d_dgrad', wp_up)
+        L.call(name, C.byref(self._conv[i]), C.byref(dy.v), L.ptr(w), L.ptr(wp), C.byref(dx.v), st)
+        self.launches += 1 if (wp is not None or self.transposed) else self.specs[i].stride ** 2
 
     def _wgrad(self, i, x: Act, dy: Act, dw, st):
         name = 'b200gan_convT2d_wgrad' if self.transposed else 'b200gan_conv2d_wgrad'
@@ -171,10 +190,12 @@ class NetEngine:
             last = i == nl - 1
             ydt = torch.float32 if (last and not self.transposed) else self.dtype      # D logits stay fp32
             y = Act(torch.empty((cur.v.n, oh, ow, sp.cout), device=dev, dtype=ydt), nchw=False)
-            self._fprop(i, cur, p.w, y, st)
+            wp_down, wp_up = self._pack(i, p.w, st)
+            self._fprop(i, cur, p.w, y, st, wp_down, wp_up)
             lc = LayerCtx() if save else None
             if save:
                 lc.x, lc.y = cur, y
+                lc.wp_down, lc.wp_up = wp_down, wp_up
                 lc.scale = lc.shift = lc.mean = lc.invstd = None
             scale = shift = None
             if sp.bn_idx is not None:
@@ -256,9 +277,9 @@ class NetEngine:
                 self._wgrad(i, lc.x, dy, grads[gi], st)
             if i > 0:
                 d = Act(torch.empty(lc.x.t.shape, device=dev, dtype=self.dtype), nchw=False)
-                self._dgrad(i, dy, p.w, d, st)
+                self._dgrad(i, dy, p.w, d, st, lc.wp_down, lc.wp_up)
             elif dinput is not None:
-                self._dgrad(i, dy, p.w, dinput, st)
+                self._dgrad(i, dy, p.w, dinput, st, lc.wp_down, lc.wp_up)
         return dinput
 
     def param_order(self, module):
