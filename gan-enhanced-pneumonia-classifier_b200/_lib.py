@@ -33,7 +33,7 @@ class Conv(C.Structure):
 
 _VP = C.POINTER(View)
 _CP = C.POINTER(Conv)
-_vp, _i32, _i64, _f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+_vp, _i32, _i64, _f32, _f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_double
 
 # name -> argtypes (every function returns int status unless noted); mirrors include/b200gan.h one to one
 PROTOTYPES = {
@@ -51,7 +51,7 @@ PROTOTYPES = {
     'b200gan_bn_act_bwd_reduce': [_VP, _VP, _VP, _vp, _vp, _vp, _vp, _i32, _f32, _vp, _vp],
     'b200gan_bn_act_bwd_apply': [_VP, _VP, _VP, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _VP, _vp, _vp, _vp],
     'b200gan_bce_sigmoid': [_vp, _i32, _f32, _f32, _vp, _vp, _vp, _vp],
-    'b200gan_adam': [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _i32, _f32, _vp],
+    'b200gan_adam': [_vp, _vp, _vp, _vp, _i64, _f64, _f64, _f64, _f64, _i32, _f32, _vp],
     'b200gan_copy_view': [_VP, _VP, _vp],
     'b200gan_fill_f32': [_vp, _i64, _f32, _vp],
 }

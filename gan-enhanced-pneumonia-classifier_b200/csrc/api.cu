@@ -31,6 +31,15 @@ int tc_conv_fprop(const b200gan_conv*, const b200gan_view* x, const void* wpacke
 int tc_conv_dgrad(const b200gan_conv*, const b200gan_view* dy, const void* wpacked, const b200gan_view* dx, cudaStream_t);
 int tc_conv_wgrad(const b200gan_conv*, const b200gan_view* x, const b200gan_view* dy, float* dw, cudaStream_t);
 int tc_pack_weight(const float* w, int Co, int Ci, int k, int form, void* out, cudaStream_t);
+// shape-specialised CUDA-core kernels (conv_thin.cu): same return convention
+int thin_down(const b200gan_view* fine, const float* w, const b200gan_view* coarse, int act, float slope, cudaStream_t);
+int thin_up(const b200gan_view* coarse, const float* w, const b200gan_view* fine, int act, cudaStream_t);
+int thin_wgrad(const b200gan_view* fine, const b200gan_view* coarse, float* dw, cudaStream_t);
+int window_fprop(const b200gan_conv*, const b200gan_view* x, const float* w, const b200gan_view* y, cudaStream_t);
+int window_dgrad(const b200gan_conv*, const b200gan_view* dy, const float* w, const b200gan_view* dx, cudaStream_t);
+int window_wgrad(const b200gan_conv*, const b200gan_view* x, const b200gan_view* dy, float* dw, cudaStream_t);
+int latent_fprop(const b200gan_conv*, const b200gan_view* z, const float* w, const b200gan_view* y, cudaStream_t);
+int latent_wgrad(const b200gan_conv*, const b200gan_view* dy_fine, const b200gan_view* z, float* dw, cudaStream_t);
 // elementwise.cu
 int ew_bn_stats(const b200gan_view*, double*, cudaStream_t);
 int ew_bn_bwd_reduce(const b200gan_view*, const b200gan_view*, const b200gan_view*, const float*, const float*, const float*,
@@ -43,7 +52,7 @@ int ew_bn_act_bwd_apply(const b200gan_view*, const b200gan_view*, const b200gan_
                         const float*, const float*, double*, int64_t, int, float, const b200gan_view*, float*, float*,
                         cudaStream_t);
 int ew_bce_sigmoid(const float*, int, float, float, float*, float*, float*, cudaStream_t);
-int ew_adam(float*, const float*, float*, float*, int64_t, float, float, float, float, int, float, cudaStream_t);
+int ew_adam(float*, const float*, float*, float*, int64_t, double, double, double, double, int, float, cudaStream_t);
 int ew_copy_view(const b200gan_view*, const b200gan_view*, cudaStream_t);
 int ew_fill(float*, int64_t, float, cudaStream_t);
 
@@ -88,9 +97,24 @@ static int conv_dispatch(Prim prim, const b200gan_conv* cv, const b200gan_view* 
     else t = tc_conv_wgrad(cv, fine, coarse, dw, st);
     if (t <= 0) return t;                       // done (0) or hard error (<0)
     if (cv->algo == B200GAN_ALGO_TCGEN05) {
-      if (g_err[0] == 0) set_error("%s: shape/dtype not supported by the tcgen05 path", what);
+      set_error("%s: shape/dtype not supported by the tcgen05 path", what);
       return B200GAN_ERR_UNSUPPORTED;
     }
+    // shape-specialised CUDA-core kernels for the thin image-side layers, the latent GEMM and the 7x7 GEMV
+    const bool k4 = cv->k == 4 && cv->stride == 2 && cv->pad == 1;
+    if (prim == FPROP) {
+      if (k4) t = thin_down(fine, w, coarse, B200GAN_ACT_NONE, 0.f, st);
+      if (t > 0) t = window_fprop(cv, fine, w, coarse, st);
+    } else if (prim == DGRAD) {
+      if (k4) t = thin_up(coarse, w, fine, B200GAN_ACT_NONE, st);
+      if (t > 0) t = window_dgrad(cv, coarse, w, fine, st);
+      if (t > 0) t = latent_fprop(cv, coarse, w, fine, st);
+    } else {
+      if (k4) t = thin_wgrad(fine, coarse, dw, st);
+      if (t > 0) t = window_wgrad(cv, fine, coarse, dw, st);
+      if (t > 0) t = latent_wgrad(cv, fine, coarse, dw, st);
+    }
+    if (t <= 0) return t;
   }
   if (prim == FPROP) return simt_conv_fprop(cv, fine, w, coarse, st);
   if (prim == DGRAD) return simt_conv_dgrad(cv, coarse, w, fine, st);
@@ -212,8 +236,8 @@ int b200gan_bce_sigmoid(const float* logit, int32_t batch, float target, float g
   return ew_bce_sigmoid(logit, batch, target, grad_scale, prob, out2, dlogit, (cudaStream_t)stream);
 }
 
-int b200gan_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t numel, float lr, float beta1,
-                 float beta2, float eps, int32_t step, float grad_scale, void* stream) {
+int b200gan_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t numel, double lr, double beta1,
+                 double beta2, double eps, int32_t step, float grad_scale, void* stream) {
   B200_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && numel > 0 && step >= 1, "adam: bad argument");
   return ew_adam(param, grad, exp_avg, exp_avg_sq, numel, lr, beta1, beta2, eps, step, grad_scale, (cudaStream_t)stream);
 }

@@ -36,6 +36,205 @@ __device__ __forceinline__ int64_t pix_offset(const View& v, int64_t pix) {
   return n * v.sn + (int64_t)h * v.sh + (int64_t)w * v.sw;
 }
 
+
+// ================================================================================================
+// Fast paths: dense NHWC tensors ([P][C] contiguous, C % VEC == 0) processed as 16-byte vectors with the
+// per-channel coefficients hoisted into registers.  These are the kernels the training step actually runs;
+// the strided scalar kernels below remain for the reference's NCHW edge tensors and odd channel counts.
+// ================================================================================================
+template <typename T> struct Vec;
+template <> struct Vec<float> {
+  static constexpr int N = 4;
+  __device__ static void load(const float* p, float* v) { const float4 t = *reinterpret_cast<const float4*>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+  __device__ static void store(float* p, const float* v) { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+};
+template <> struct Vec<__nv_bfloat16> {
+  static constexpr int N = 8;
+  __device__ static void load(const __nv_bfloat16* p, float* v) {
+    const uint4 t = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+  }
+  __device__ static void store(__nv_bfloat16* p, const float* v) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { __nv_bfloat162 b = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]); w[i] = *reinterpret_cast<uint32_t*>(&b); }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+
+static bool dense_nhwc(const b200gan_view* v) {
+  return v->sc == 1 && v->sw == v->c && v->sh == (int64_t)v->w * v->c && v->sn == (int64_t)v->h * v->w * v->c &&
+         (reinterpret_cast<uintptr_t>(v->ptr) & 15) == 0;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) bn_act_fwd_dense_kernel(const T* __restrict__ y, T* __restrict__ a, int64_t nvec, int C,
+                                                               const float* __restrict__ scale, const float* __restrict__ shift,
+                                                               int act, float slope) {
+  constexpr int V = Vec<T>::N;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool hoist = (stride * V) % C == 0;
+  float sc[V], sh[V];
+  int c0 = (int)((i * V) % C);
+#pragma unroll
+  for (int j = 0; j < V; ++j) { sc[j] = scale ? scale[c0 + j] : 1.f; sh[j] = scale ? shift[c0 + j] : 0.f; }
+  for (; i < nvec; i += stride) {
+    if (!hoist && scale) {
+      c0 = (int)((i * V) % C);
+#pragma unroll
+      for (int j = 0; j < V; ++j) { sc[j] = scale[c0 + j]; sh[j] = shift[c0 + j]; }
+    }
+    float v[V];
+    Vec<T>::load(y + i * V, v);
+#pragma unroll
+    for (int j = 0; j < V; ++j) v[j] = act_fwd(fmaf(v[j], sc[j], sh[j]), act, slope);
+    Vec<T>::store(a + i * V, v);
+  }
+}
+
+struct BwdDenseArgs {
+  const void *da, *y, *a;
+  void* dy;
+  int64_t nvec;
+  int C;
+  const float *scale, *shift, *mean, *invstd, *gamma;
+  const double* sums;
+  double count;
+  int act; float slope;
+  float *dgamma, *dbeta;
+};
+
+// dy = k1*dz + p*y + q  with k1 = gamma*invstd, p = -k1*m2*invstd, q = k1*(m2*invstd*mean - m1)
+// (algebraically gamma*invstd*(dz - m1 - xhat*m2)); no BatchNorm: dy = dz.
+template <typename T>
+__global__ void __launch_bounds__(256) bn_act_bwd_apply_dense_kernel(BwdDenseArgs g) {
+  constexpr int V = Vec<T>::N;
+  const int C = g.C;
+  if (g.scale && blockIdx.x == 0) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      if (g.dbeta) g.dbeta[c] += (float)g.sums[c];
+      if (g.dgamma) g.dgamma[c] += (float)g.sums[C + c];
+    }
+  }
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool hoist = (stride * V) % C == 0;
+  float sc[V], sh[V], k1[V], pp[V], qq[V];
+  auto coeffs = [&](int c0) {
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      const int c = c0 + j;
+      if (g.scale) {
+        const float is = g.invstd[c], mu = g.mean[c];
+        const float m1 = (float)(g.sums[c] / g.count), m2 = (float)(g.sums[C + c] / g.count);
+        sc[j] = g.scale[c]; sh[j] = g.shift[c];
+        k1[j] = g.gamma[c] * is;
+        pp[j] = -k1[j] * m2 * is;
+        qq[j] = k1[j] * (m2 * is * mu - m1);
+      } else {
+        sc[j] = 1.f; sh[j] = 0.f; k1[j] = 1.f; pp[j] = 0.f; qq[j] = 0.f;
+      }
+    }
+  };
+  coeffs((int)((i * V) % C));
+  const T* da = reinterpret_cast<const T*>(g.da);
+  const T* y = reinterpret_cast<const T*>(g.y);
+  const T* a = reinterpret_cast<const T*>(g.a);
+  T* dy = reinterpret_cast<T*>(g.dy);
+  for (; i < g.nvec; i += stride) {
+    if (!hoist) coeffs((int)((i * V) % C));
+    float d[V], yv[V], av[V];
+    Vec<T>::load(da + i * V, d);
+    Vec<T>::load(y + i * V, yv);
+    if (a) Vec<T>::load(a + i * V, av);
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      const float z = fmaf(yv[j], sc[j], sh[j]);
+      const float dz = d[j] * act_grad(z, a ? av[j] : 0.f, g.act, g.slope);
+      d[j] = fmaf(k1[j], dz, fmaf(pp[j], yv[j], qq[j]));
+    }
+    Vec<T>::store(dy + i * V, d);
+  }
+}
+
+struct ReduceDenseArgs {
+  const void *y, *da, *a;
+  int64_t P;
+  int C;
+  const float *scale, *shift, *mean, *invstd;
+  int act; float slope;
+  double* sums;
+};
+
+// thread = (vector lane vl over C/V, pixel row pr); block-level smem reduction, one double atomic per channel per block
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256) channel_reduce_dense_kernel(ReduceDenseArgs g) {
+  constexpr int V = Vec<T>::N;
+  __shared__ float red[2][256 * V / 8 + 1][8];          // [which][row-major scratch]; sized for V = 8 worst case below
+  const int C = g.C, lanes = C / V, rows = 256 / lanes;
+  const int vl = threadIdx.x % lanes, pr = threadIdx.x / lanes;
+  const int c0 = vl * V;
+  float s0[V], s1[V], sc[V], sh[V], mu[V], is[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    s0[j] = 0.f; s1[j] = 0.f;
+    sc[j] = (MODE == 1 && g.scale) ? g.scale[c0 + j] : 1.f;
+    sh[j] = (MODE == 1 && g.scale) ? g.shift[c0 + j] : 0.f;
+    mu[j] = (MODE == 1 && g.mean) ? g.mean[c0 + j] : 0.f;
+    is[j] = (MODE == 1 && g.invstd) ? g.invstd[c0 + j] : 1.f;
+  }
+  const T* y = reinterpret_cast<const T*>(g.y);
+  const T* da = reinterpret_cast<const T*>(g.da);
+  const T* a = reinterpret_cast<const T*>(g.a);
+  if (pr < rows) {
+    for (int64_t p = (int64_t)blockIdx.x * rows + pr; p < g.P; p += (int64_t)gridDim.x * rows) {
+      float yv[V];
+      Vec<T>::load(y + p * C + c0, yv);
+      if (MODE == 0) {
+#pragma unroll
+        for (int j = 0; j < V; ++j) { s0[j] += yv[j]; s1[j] = fmaf(yv[j], yv[j], s1[j]); }
+      } else {
+        float d[V], av[V];
+        Vec<T>::load(da + p * C + c0, d);
+        if (a) Vec<T>::load(a + p * C + c0, av);
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+          const float z = fmaf(yv[j], sc[j], sh[j]);
+          const float dz = d[j] * act_grad(z, a ? av[j] : 0.f, g.act, g.slope);
+          s0[j] += dz;
+          s1[j] = fmaf(dz, (yv[j] - mu[j]) * is[j], s1[j]);
+        }
+      }
+    }
+  }
+  // reduce over pixel rows: first fold rows with shuffles where a warp holds several rows of the same lane set
+  float* r0 = &red[0][0][0];
+  float* r1 = &red[1][0][0];
+  // scratch layout [row][C]; rows*C = 256*V floats at most
+  if (pr < rows) {
+#pragma unroll
+    for (int j = 0; j < V; ++j) { r0[pr * C + c0 + j] = s0[j]; r1[pr * C + c0 + j] = s1[j]; }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) {
+    const int which = c >= C, cc = which ? c - C : c;
+    const float* r = which ? r1 : r0;
+    float t = 0.f;
+    for (int rr = 0; rr < rows; ++rr) t += r[rr * C + cc];
+    atomicAdd(g.sums + c, (double)t);
+  }
+}
+
+template <typename T>
+static bool reduce_dense_ok(const b200gan_view* y) {
+  constexpr int V = sizeof(T) == 2 ? 8 : 4;
+  const int C = y->c;
+  return dense_nhwc(y) && C % V == 0 && C / V <= 256 && 256 % (C / V) == 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // per-channel reductions.  Thread layout: cl = tid % lanes_c is the channel lane (consecutive threads
 // read consecutive channels of one pixel: coalesced for NHWC), pr = tid / lanes_c the pixel row of
@@ -122,6 +321,19 @@ int ew_bn_stats(const b200gan_view* y, double* sums, cudaStream_t st) {
   reduce_geometry(y->c, &g.lanes_c, &g.rows);
   B200_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * y->c, st));
   const int64_t P = (int64_t)y->n * y->h * y->w;
+  if ((y->dtype == B200GAN_F32 && reduce_dense_ok<float>(y)) || (y->dtype == B200GAN_BF16 && reduce_dense_ok<__nv_bfloat16>(y))) {
+    ReduceDenseArgs d{};
+    d.y = y->ptr; d.P = P; d.C = y->c; d.sums = sums;
+    const int V = y->dtype == B200GAN_F32 ? 4 : 8;
+    const int rows = 256 / (y->c / V);
+    int64_t nb = (P + (int64_t)rows * 32 - 1) / ((int64_t)rows * 32);
+    if (nb > 8 * kNumSMs) nb = 8 * kNumSMs;
+    if (nb < 1) nb = 1;
+    if (y->dtype == B200GAN_F32) channel_reduce_dense_kernel<float, 0><<<(unsigned)nb, 256, 0, st>>>(d);
+    else channel_reduce_dense_kernel<__nv_bfloat16, 0><<<(unsigned)nb, 256, 0, st>>>(d);
+    B200_LAUNCH_CHECK("bn_stats(dense)");
+    return 0;
+  }
   int64_t blocks = (P + (int64_t)g.rows * 64 - 1) / ((int64_t)g.rows * 64);   // ~64 pixels per thread
   if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
   if (blocks < 1) blocks = 1;
@@ -143,6 +355,21 @@ int ew_bn_bwd_reduce(const b200gan_view* da, const b200gan_view* y, const b200ga
   reduce_geometry(y->c, &g.lanes_c, &g.rows);
   B200_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * y->c, st));
   const int64_t P = (int64_t)y->n * y->h * y->w;
+  if (dense_nhwc(da) && (!a || dense_nhwc(a)) &&
+      ((y->dtype == B200GAN_F32 && reduce_dense_ok<float>(y)) || (y->dtype == B200GAN_BF16 && reduce_dense_ok<__nv_bfloat16>(y)))) {
+    ReduceDenseArgs d{};
+    d.y = y->ptr; d.da = da->ptr; d.a = a ? a->ptr : nullptr; d.P = P; d.C = y->c; d.sums = sums;
+    d.scale = scale; d.shift = shift; d.mean = mean; d.invstd = invstd; d.act = act; d.slope = slope;
+    const int V = y->dtype == B200GAN_F32 ? 4 : 8;
+    const int rows = 256 / (y->c / V);
+    int64_t nb = (P + (int64_t)rows * 32 - 1) / ((int64_t)rows * 32);
+    if (nb > 8 * kNumSMs) nb = 8 * kNumSMs;
+    if (nb < 1) nb = 1;
+    if (y->dtype == B200GAN_F32) channel_reduce_dense_kernel<float, 1><<<(unsigned)nb, 256, 0, st>>>(d);
+    else channel_reduce_dense_kernel<__nv_bfloat16, 1><<<(unsigned)nb, 256, 0, st>>>(d);
+    B200_LAUNCH_CHECK("bn_act_bwd_reduce(dense)");
+    return 0;
+  }
   int64_t blocks = (P + (int64_t)g.rows * 64 - 1) / ((int64_t)g.rows * 64);
   if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
   if (blocks < 1) blocks = 1;
@@ -225,6 +452,24 @@ int ew_bn_act_fwd(const b200gan_view* y, const float* scale, const float* shift,
                   cudaStream_t st) {
   B200_CHECK_ARG(y->n == a->n && y->h == a->h && y->w == a->w && y->c == a->c, "bn_act_fwd: extent mismatch");
   const int64_t total = (int64_t)y->n * y->h * y->w * y->c;
+  {
+    const int V = y->dtype == B200GAN_F32 ? 4 : 8;
+    // without BatchNorm nothing is per-channel: any dense tensor whose size is a multiple of the vector width qualifies
+    const bool chan_free = scale == nullptr;
+    if (y->dtype == a->dtype && dense_nhwc(y) && dense_nhwc(a) && (y->c % V == 0 || (chan_free && total % V == 0))) {
+      const int64_t nvec = total / V;
+      const int Cv = (y->c % V == 0) ? y->c : V;
+      int64_t nbk = (nvec + 256 * 4 - 1) / (256 * 4);
+      if (nbk > 16 * kNumSMs) nbk = 16 * kNumSMs;
+      if (nbk < 1) nbk = 1;
+      if (y->dtype == B200GAN_F32)
+        bn_act_fwd_dense_kernel<float><<<(unsigned)nbk, 256, 0, st>>>((const float*)y->ptr, (float*)a->ptr, nvec, Cv, scale, shift, act, slope);
+      else
+        bn_act_fwd_dense_kernel<__nv_bfloat16><<<(unsigned)nbk, 256, 0, st>>>((const __nv_bfloat16*)y->ptr, (__nv_bfloat16*)a->ptr, nvec, Cv, scale, shift, act, slope);
+      B200_LAUNCH_CHECK("bn_act_fwd(dense)");
+      return 0;
+    }
+  }
   const unsigned nb = ew_blocks(total);
   const View vy = to_view(y), va = to_view(a);
   if (y->dtype == B200GAN_F32 && a->dtype == B200GAN_F32) bn_act_fwd_kernel<float, float><<<nb, 256, 0, st>>>(vy, va, scale, shift, act, slope);
@@ -285,6 +530,24 @@ int ew_bn_act_bwd_apply(const b200gan_view* da, const b200gan_view* y, const b20
   g.scale = scale; g.shift = shift; g.mean = mean; g.invstd = invstd; g.gamma = gamma; g.sums = sums; g.count = (double)count;
   g.act = act; g.slope = slope; g.dgamma = dgamma; g.dbeta = dbeta;
   const int64_t total = (int64_t)y->n * y->h * y->w * y->c;
+  {
+    const int V = y->dtype == B200GAN_F32 ? 4 : 8;
+    const bool chan_free = scale == nullptr;
+    if (y->dtype == dy->dtype && dense_nhwc(y) && dense_nhwc(da) && dense_nhwc(dy) && (!a || dense_nhwc(a)) &&
+        (y->c % V == 0 || (chan_free && total % V == 0))) {
+      BwdDenseArgs d{};
+      d.da = da->ptr; d.y = y->ptr; d.a = a ? a->ptr : nullptr; d.dy = dy->ptr; d.nvec = total / V; d.C = (y->c % V == 0) ? y->c : V;
+      d.scale = scale; d.shift = shift; d.mean = mean; d.invstd = invstd; d.gamma = gamma; d.sums = sums; d.count = (double)count;
+      d.act = act; d.slope = slope; d.dgamma = dgamma; d.dbeta = dbeta;
+      int64_t nbk = (d.nvec + 256 * 4 - 1) / (256 * 4);
+      if (nbk > 16 * kNumSMs) nbk = 16 * kNumSMs;
+      if (nbk < 1) nbk = 1;
+      if (y->dtype == B200GAN_F32) bn_act_bwd_apply_dense_kernel<float><<<(unsigned)nbk, 256, 0, st>>>(d);
+      else bn_act_bwd_apply_dense_kernel<__nv_bfloat16><<<(unsigned)nbk, 256, 0, st>>>(d);
+      B200_LAUNCH_CHECK("bn_act_bwd_apply(dense)");
+      return 0;
+    }
+  }
   const unsigned nb = ew_blocks(total);
   if (y->dtype == B200GAN_F32 && dy->dtype == B200GAN_F32) bn_act_bwd_apply_kernel<float, float><<<nb, 256, 0, st>>>(g);
   else if (y->dtype == B200GAN_F32) bn_act_bwd_apply_kernel<float, __nv_bfloat16><<<nb, 256, 0, st>>>(g);
@@ -368,12 +631,13 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
   }
 }
 
-int ew_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps, int step,
+int ew_adam(float* p, const float* g, float* m, float* v, int64_t n, double lr, double b1, double b2, double eps, int step,
             float gscale, cudaStream_t st) {
-  const double bc1 = 1.0 - pow((double)b1, (double)step), bc2 = 1.0 - pow((double)b2, (double)step);
-  const float step_size = (float)((double)lr / bc1), bc2_sqrt = (float)sqrt(bc2);
+  const double bc1 = 1.0 - pow(b1, (double)step), bc2 = 1.0 - pow(b2, (double)step);
+  const float step_size = (float)(lr / bc1), bc2_sqrt = (float)sqrt(bc2);
   const int vec_ok = ((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0) ? 1 : 0;
-  adam_kernel<<<ew_blocks(n / 4 + 1), 256, 0, st>>>(p, g, m, v, n, 1.f - b1, b2, 1.f - b2, step_size, bc2_sqrt, eps, gscale, vec_ok);
+  adam_kernel<<<ew_blocks(n / 4 + 1), 256, 0, st>>>(p, g, m, v, n, (float)(1.0 - b1), (float)b2, (float)(1.0 - b2), step_size, bc2_sqrt,
+                                                    (float)eps, gscale, vec_ok);
   B200_LAUNCH_CHECK("adam");
   return 0;
 }

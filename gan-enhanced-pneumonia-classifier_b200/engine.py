@@ -253,7 +253,7 @@ class NetEngine:
             if i == nl - 1 and dlogit is not None:
                 dy = dlogit
             else:
-                dy = Act(torch.empty(lc.y.t.shape, device=dev, dtype=self.dtype), nchw=False)
+                dy = Act(torch.empty(lc.y.t.shape, device=dev, dtype=lc.y.t.dtype), nchw=False)   # D logits: fp32
                 need_a = sp.act in (L.ACT_TANH, L.ACT_SIGMOID)
                 # da, y, a must share a dtype: for tanh/sigmoid only `a` is read, so it stands in for y
                 yv = lc.a if need_a else lc.y

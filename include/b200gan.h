@@ -145,9 +145,10 @@ int b200gan_bce_sigmoid(const float* logit, int32_t batch, float target, float g
 
 /* ---- torch.optim.Adam (train_gan.py:94-95,141,150) over one flat fp32 arena: lr, betas, eps, no weight
  *      decay, no amsgrad; `step` is the 1-based step count of this update.  grad_scale multiplies the
- *      gradient first (1/world_size for data-parallel sums). */
-int b200gan_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t numel, float lr,
-                 float beta1, float beta2, float eps, int32_t step, float grad_scale, void* stream);
+ *      gradient first (1/world_size for data-parallel sums).  Hyper-parameters are doubles, as torch holds them
+ *      (Python floats): `1 - beta2` is formed in double and rounded once, exactly like torch's scalar handling. */
+int b200gan_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t numel, double lr,
+                 double beta1, double beta2, double eps, int32_t step, float grad_scale, void* stream);
 
 /* ---- layout plumbing: dst(n,h,w,c) = (dst dtype) src(n,h,w,c) for two views of equal extents. */
 int b200gan_copy_view(const b200gan_view* src, const b200gan_view* dst, void* stream);
