@@ -121,6 +121,7 @@ struct TcConvParams {
   int a_mul;                         // input coordinate = tile origin * a_mul + tap offset
   int taps;                          // 16 (DOWN) or 4 (UP)
   int chunks;                        // Cin / KC
+  int n_tiles, ncls, num_tiles;      // Cout tiles, parity classes (1 or 4), total tiles = spatial * n_tiles * ncls
   int8_t tap_dh[4][16], tap_dw[4][16];   // [class][tap]
   int QH, QW, NB;                    // valid extent of the pixel space (rows beyond are discarded)
   __nv_bfloat16* out;
@@ -137,6 +138,15 @@ struct TcSmem {
   static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Persistent kernel: each CTA walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... of the (M-tile, N-tile, class)
+// space.  Warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2..5 = epilogue.  The accumulator is
+// double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps the MMA stream of tile i+1, and the
+// smem ring keeps running across tile boundaries.  No integer division sits on the per-k-block path of the two
+// single-thread roles (a first version spent ~100 instructions per step there).
 template <int BN, int KC, int STAGES>
 __global__ void __launch_bounds__(192, 1)
 conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcConvParams p) {
@@ -145,25 +155,18 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* accum_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+  uint64_t* acc_full = empty_bar + STAGES;     // [2]
+  uint64_t* acc_empty = acc_full + 2;          // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int cls = blockIdx.z;
-  // tile origin
-  int t = blockIdx.x;
-  const int tw_i = t % p.tiles_w; t /= p.tiles_w;
-  const int th_i = t % p.tiles_h;
-  const int tn_i = t / p.tiles_h;
   const int TW = 1 << p.tw_log2, TH = 1 << p.th_log2, TN = 128 >> (p.tw_log2 + p.th_log2);
-  const int w0 = tw_i * TW, h0 = th_i * TH, n0 = tn_i * TN;
-  const int cout0 = blockIdx.y * BN;
-  const int num_kb = p.taps * p.chunks;
-  constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+  constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+  const int num_tiles = p.num_tiles;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    mbar_init(accum_bar, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
@@ -180,16 +183,28 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   if (warp == 0) {
     // ===== TMA producer (one lane) =====
     if (lane == 0) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        const int tap = kb / p.chunks, chunk = kb - tap * p.chunks;
-        uint8_t* sa = smem + s * S::STAGE_BYTES;
-        uint8_t* sb = sa + S::A_BYTES;
-        mbar_expect_tx(&full_bar[s], S::STAGE_BYTES);
-        tma_load_4d(sa, &map_a, &full_bar[s], chunk * KC, w0 * p.a_mul + p.tap_dw[cls][tap], h0 * p.a_mul + p.tap_dh[cls][tap], n0);
-        tma_load_3d(sb, &map_b, &full_bar[s], kb * KC, cout0, cls);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        int r = t;
+        const int cls = r % p.ncls; r /= p.ncls;
+        const int nt = r % p.n_tiles; r /= p.n_tiles;
+        const int tw_i = r % p.tiles_w; r /= p.tiles_w;
+        const int th_i = r % p.tiles_h;
+        const int tn_i = r / p.tiles_h;
+        const int w0 = tw_i * TW * p.a_mul, h0 = th_i * TH * p.a_mul, n0 = tn_i * TN, cout0 = nt * BN;
+        int kcol = 0;
+        for (int tap = 0; tap < p.taps; ++tap) {
+          const int cw = w0 + p.tap_dw[cls][tap], chh = h0 + p.tap_dh[cls][tap];
+          for (int chunk = 0; chunk < p.chunks; ++chunk, kcol += KC) {
+            mbar_wait(&empty_bar[s], ph ^ 1);
+            uint8_t* sa = smem + s * S::STAGE_BYTES;
+            mbar_expect_tx(&full_bar[s], S::STAGE_BYTES);
+            tma_load_4d(sa, &map_a, &full_bar[s], chunk * KC, cw, chh, n0);
+            tma_load_3d(sa + S::A_BYTES, &map_b, &full_bar[s], kcol, cout0, cls);
+            if (++s == STAGES) { s = 0; ph ^= 1; }
+          }
+        }
       }
     }
     __syncwarp();
@@ -199,21 +214,30 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
       constexpr uint32_t LT = KC == 64 ? 2u : 4u;          // SWIZZLE_128B : SWIZZLE_64B
       constexpr uint32_t SBO = 8 * KC * 2;                 // 8 rows of KC bf16
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&full_bar[s], ph);
+      const int num_kb = p.taps * p.chunks;
+      int s = 0;
+      uint32_t ph = 0;
+      int lt = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++lt) {
+        const int buf = lt & 1;
+        mbar_wait(&acc_empty[buf], ((lt >> 1) & 1) ^ 1);   // epilogue has drained this accumulator
         tcgen05_fence_after();
-        const uint32_t sa = smem_u32(smem + s * S::STAGE_BYTES), sb = sa + S::A_BYTES;
+        const uint32_t tmem_d = tmem_base + buf * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[s], ph);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_u32(smem + s * S::STAGE_BYTES), sb = sa + S::A_BYTES;
 #pragma unroll
-        for (int k = 0; k < KC / 16; ++k) {
-          const uint64_t adesc = make_smem_desc(sa + k * 32, 16, SBO, LT);
-          const uint64_t bdesc = make_smem_desc(sb + k * 32, 16, SBO, LT);
-          tcgen05_mma_f16(tmem_base, adesc, bdesc, idesc, (kb | k) != 0);
+          for (int k = 0; k < KC / 16; ++k) {
+            const uint64_t adesc = make_smem_desc(sa + k * 32, 16, SBO, LT);
+            const uint64_t bdesc = make_smem_desc(sb + k * 32, 16, SBO, LT);
+            tcgen05_mma_f16(tmem_d, adesc, bdesc, idesc, (kb | k) != 0);
+          }
+          tcgen05_commit(&empty_bar[s]);                   // frees the smem stage when these MMAs retire
+          if (++s == STAGES) { s = 0; ph ^= 1; }
         }
-        tcgen05_commit(&empty_bar[s]);                     // frees the smem stage when these MMAs retire
+        tcgen05_commit(&acc_full[buf]);                    // accumulator complete
       }
-      tcgen05_commit(accum_bar);                           // accumulator complete
     }
     __syncwarp();
   } else {
@@ -221,36 +245,50 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int tw = row & (TW - 1), th = (row >> p.tw_log2) & (TH - 1), tn = row >> (p.tw_log2 + p.th_log2);
-    const int ow = w0 + tw, oh = h0 + th, n = n0 + tn;
-    const bool valid = ow < p.QW && oh < p.QH && n < p.NB;
-    const int py = cls >> 1, px = cls & 1;
-    __nv_bfloat16* orow = p.out + (int64_t)n * p.o_sn + (int64_t)(oh * p.o_mul + (p.o_mul > 1 ? py : 0)) * p.o_sh +
-                          (int64_t)(ow * p.o_mul + (p.o_mul > 1 ? px : 0)) * p.o_sw + cout0;
-    mbar_wait(accum_bar, 0);
-    tcgen05_fence_after();
+    int lt = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++lt) {
+      int r = t;
+      const int cls = r % p.ncls; r /= p.ncls;
+      const int nt = r % p.n_tiles; r /= p.n_tiles;
+      const int tw_i = r % p.tiles_w; r /= p.tiles_w;
+      const int th_i = r % p.tiles_h;
+      const int tn_i = r / p.tiles_h;
+      const int ow = tw_i * TW + tw, oh = th_i * TH + th, n = tn_i * TN + tn, cout0 = nt * BN;
+      const bool valid = ow < p.QW && oh < p.QH && n < p.NB;
+      const int py = cls >> 1, px = cls & 1;
+      __nv_bfloat16* orow = p.out + (int64_t)n * p.o_sn + (int64_t)(oh * p.o_mul + (p.o_mul > 1 ? py : 0)) * p.o_sh +
+                            (int64_t)(ow * p.o_mul + (p.o_mul > 1 ? px : 0)) * p.o_sw + cout0;
+      const int buf = lt & 1;
+      mbar_wait(&acc_full[buf], (lt >> 1) & 1);
+      tcgen05_fence_after();
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t r[32];
-      tcgen05_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + c0, r);
-      tcgen05_wait_ld();
-      if (valid) {
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tcgen05_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + c0, v);
+        tcgen05_wait_ld();
+        if (valid) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          if (cout0 + c0 + j < p.cout) {
-            uint4 v;
-            __nv_bfloat162 b0 = __floats2bfloat162_rn(__uint_as_float(r[j + 0]), __uint_as_float(r[j + 1]));
-            __nv_bfloat162 b1 = __floats2bfloat162_rn(__uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-            __nv_bfloat162 b2 = __floats2bfloat162_rn(__uint_as_float(r[j + 4]), __uint_as_float(r[j + 5]));
-            __nv_bfloat162 b3 = __floats2bfloat162_rn(__uint_as_float(r[j + 6]), __uint_as_float(r[j + 7]));
-            v.x = *reinterpret_cast<uint32_t*>(&b0); v.y = *reinterpret_cast<uint32_t*>(&b1);
-            v.z = *reinterpret_cast<uint32_t*>(&b2); v.w = *reinterpret_cast<uint32_t*>(&b3);
-            *reinterpret_cast<uint4*>(orow + c0 + j) = v;
+          for (int j = 0; j < 32; j += 8) {
+            if (cout0 + c0 + j < p.cout) {
+              uint4 o;
+              __nv_bfloat162 b0 = __floats2bfloat162_rn(__uint_as_float(v[j + 0]), __uint_as_float(v[j + 1]));
+              __nv_bfloat162 b1 = __floats2bfloat162_rn(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+              __nv_bfloat162 b2 = __floats2bfloat162_rn(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5]));
+              __nv_bfloat162 b3 = __floats2bfloat162_rn(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7]));
+              o.x = *reinterpret_cast<uint32_t*>(&b0); o.y = *reinterpret_cast<uint32_t*>(&b1);
+              o.z = *reinterpret_cast<uint32_t*>(&b2); o.w = *reinterpret_cast<uint32_t*>(&b3);
+              *reinterpret_cast<uint4*>(orow + c0 + j) = o;
+            }
           }
         }
       }
+      // all TMEM reads of this warp are complete (wait::ld above): hand the accumulator back to the MMA warp
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
     }
-    tcgen05_fence_before();
   }
+  tcgen05_fence_before();
   __syncthreads();
   if (warp == 1) {
     tcgen05_fence_after();
@@ -371,15 +409,20 @@ static int tc_conv_common(const b200gan_conv* cv, const b200gan_view* in, const 
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(B) failed: %d", (int)r); return B200GAN_ERR_CUDA; }
   }
-  dim3 grid((unsigned)(p.tiles_w * p.tiles_h * p.tiles_n), (unsigned)(cout / BN), up ? 4 : 1);
+  p.n_tiles = cout / BN;
+  p.ncls = up ? 4 : 1;
+  p.num_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles * p.ncls;
+  // persistent: two CTAs per SM (every configuration below fits 2 x (smem, 2*BN TMEM columns) per SM)
+  const int ctas = p.num_tiles < 2 * kNumSMs ? p.num_tiles : 2 * kNumSMs;
+  dim3 grid((unsigned)ctas, 1, 1);
   if (KC == 64) {
-    if (BN == 128) return launch_tc<128, 64, 4>(ma, mb, p, grid, st);
-    if (BN == 64) return launch_tc<64, 64, 4>(ma, mb, p, grid, st);
-    return launch_tc<32, 64, 4>(ma, mb, p, grid, st);
+    if (BN == 128) return launch_tc<128, 64, 3>(ma, mb, p, grid, st);   // 3 x 32 KB
+    if (BN == 64) return launch_tc<64, 64, 4>(ma, mb, p, grid, st);     // 4 x 24 KB
+    return launch_tc<32, 64, 5>(ma, mb, p, grid, st);                   // 5 x 20 KB
   }
-  if (BN == 128) return launch_tc<128, 32, 4>(ma, mb, p, grid, st);
-  if (BN == 64) return launch_tc<64, 32, 4>(ma, mb, p, grid, st);
-  return launch_tc<32, 32, 4>(ma, mb, p, grid, st);
+  if (BN == 128) return launch_tc<128, 32, 6>(ma, mb, p, grid, st);     // 6 x 16 KB
+  if (BN == 64) return launch_tc<64, 32, 8>(ma, mb, p, grid, st);       // 8 x 12 KB
+  return launch_tc<32, 32, 8>(ma, mb, p, grid, st);                     // 8 x 10 KB
 }
 
 int tc_conv_fprop(const b200gan_conv* cv, const b200gan_view* x, const void* wpacked, const b200gan_view* y, cudaStream_t st) {
@@ -413,7 +456,9 @@ struct TcWgradParams {
 template <int NCI>
 struct TcWgradSmem {
   static constexpr int BK = 64;                           // pixels per K-block
-  static constexpr int A_SLOTS = 3, STAGES = 4;
+  // B tiles are small for narrow layers: keep >= 64 KB of TMA loads in flight (latency-bound otherwise).
+  // The A slot ring is safe while STAGES <= (A_SLOTS - 1) * T with T = 512 / NCI taps per CTA.
+  static constexpr int A_SLOTS = 3, STAGES = NCI == 32 ? 16 : (NCI == 64 ? 12 : (NCI == 128 ? 8 : 4));
   static constexpr int A_BYTES = BK * 128 * 2;            // 64 pixels x 128 co
   static constexpr int B_BYTES = BK * NCI * 2;
   static constexpr int TOTAL = A_SLOTS * A_BYTES + STAGES * B_BYTES + 1024 + 256;
@@ -463,29 +508,33 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_co
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int st = 0; st < steps; ++st) {
-        const int s = st % S::STAGES;
-        const uint32_t ph = (st / S::STAGES) & 1;
-        const int kbl = st / p.T, tl = st - kbl * p.T;
-        int t = kb_beg + kbl;
-        const int tw_i = t % p.tiles_w; t /= p.tiles_w;
-        const int th_i = t % p.tiles_h;
-        const int tn_i = t / p.tiles_h;
+      int t0 = kb_beg;
+      int tw_i = t0 % p.tiles_w; t0 /= p.tiles_w;
+      int th_i = t0 % p.tiles_h;
+      int tn_i = t0 / p.tiles_h;
+      int s = 0, aslot = 0;
+      uint32_t ph = 0;
+      for (int kbl = 0; kbl < nkb; ++kbl) {
         const int w0 = tw_i * TW, h0 = th_i * TH, n0 = tn_i * TN;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        uint8_t* sb = smem_b + s * S::B_BYTES;
-        if (tl == 0) {
-          uint8_t* sa = smem_a + (kbl % S::A_SLOTS) * S::A_BYTES;
-          mbar_expect_tx(&full_bar[s], S::A_BYTES + S::B_BYTES);
-          tma_load_4d(sa, &map_dy, &full_bar[s], co0, w0, h0, n0);
-          tma_load_4d(sa + S::A_BYTES / 2, &map_dy, &full_bar[s], co0 + 64, w0, h0, n0);
-        } else {
-          mbar_expect_tx(&full_bar[s], S::B_BYTES);
-        }
-        const int tap = tap0 + tl, kh = tap >> 2, kw = tap & 3;
+        for (int tl = 0; tl < p.T; ++tl) {
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* sb = smem_b + s * S::B_BYTES;
+          if (tl == 0) {
+            uint8_t* sa = smem_a + aslot * S::A_BYTES;
+            mbar_expect_tx(&full_bar[s], S::A_BYTES + S::B_BYTES);
+            tma_load_4d(sa, &map_dy, &full_bar[s], co0, w0, h0, n0);
+            tma_load_4d(sa + S::A_BYTES / 2, &map_dy, &full_bar[s], co0 + 64, w0, h0, n0);
+          } else {
+            mbar_expect_tx(&full_bar[s], S::B_BYTES);
+          }
+          const int tap = tap0 + tl, kh = tap >> 2, kw = tap & 3;
 #pragma unroll
-        for (int b = 0; b < NBOX; ++b)
-          tma_load_4d(sb + b * (S::BK * CB * 2), &map_x, &full_bar[s], ci0 + b * CB, 2 * w0 - 1 + kw, 2 * h0 - 1 + kh, n0);
+          for (int b = 0; b < NBOX; ++b)
+            tma_load_4d(sb + b * (S::BK * CB * 2), &map_x, &full_bar[s], ci0 + b * CB, 2 * w0 - 1 + kw, 2 * h0 - 1 + kh, n0);
+          if (++s == S::STAGES) { s = 0; ph ^= 1; }
+        }
+        if (++aslot == S::A_SLOTS) aslot = 0;
+        if (++tw_i == p.tiles_w) { tw_i = 0; if (++th_i == p.tiles_h) { th_i = 0; ++tn_i; } }
       }
     }
     __syncwarp();
@@ -494,22 +543,25 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_co
       constexpr uint32_t idesc = make_idesc_bf16(128, NCI, 1, 1);       // both operands MN-major
       constexpr uint32_t B_LT = CB == 64 ? 2u : 4u;
       constexpr uint32_t B_ROW = CB * 2;                                // bytes per pixel row of a B box
-      for (int st = 0; st < steps; ++st) {
-        const int s = st % S::STAGES;
-        const uint32_t ph = (st / S::STAGES) & 1;
-        const int kbl = st / p.T, tl = st - kbl * p.T;
-        mbar_wait(&full_bar[s], ph);
-        tcgen05_fence_after();
-        const uint32_t sa = smem_u32(smem_a + (kbl % S::A_SLOTS) * S::A_BYTES);
-        const uint32_t sb = smem_u32(smem_b + s * S::B_BYTES);
+      int s = 0, aslot = 0;
+      uint32_t ph = 0;
+      for (int kbl = 0; kbl < nkb; ++kbl) {
+        const uint32_t sa = smem_u32(smem_a + aslot * S::A_BYTES);
+        for (int tl = 0; tl < p.T; ++tl) {
+          mbar_wait(&full_bar[s], ph);
+          tcgen05_fence_after();
+          const uint32_t sb = smem_u32(smem_b + s * S::B_BYTES);
 #pragma unroll
-        for (int k = 0; k < S::BK / 16; ++k) {
-          // MN-major canonical layout: LBO = distance between 64-channel groups, SBO = 8 pixel rows
-          const uint64_t adesc = make_smem_desc(sa + k * 16 * 128, S::A_BYTES / 2, 8 * 128, 2u);
-          const uint64_t bdesc = make_smem_desc(sb + k * 16 * B_ROW, S::BK * B_ROW, 8 * B_ROW, B_LT);
-          tcgen05_mma_f16(tmem_base + tl * NCI, adesc, bdesc, idesc, (kbl | k) != 0);
+          for (int k = 0; k < S::BK / 16; ++k) {
+            // MN-major canonical layout: LBO = distance between 64-channel groups, SBO = 8 pixel rows
+            const uint64_t adesc = make_smem_desc(sa + k * 16 * 128, S::A_BYTES / 2, 8 * 128, 2u);
+            const uint64_t bdesc = make_smem_desc(sb + k * 16 * B_ROW, S::BK * B_ROW, 8 * B_ROW, B_LT);
+            tcgen05_mma_f16(tmem_base + tl * NCI, adesc, bdesc, idesc, (kbl | k) != 0);
+          }
+          tcgen05_commit(&empty_bar[s]);
+          if (++s == S::STAGES) { s = 0; ph ^= 1; }
         }
-        tcgen05_commit(&empty_bar[s]);
+        if (++aslot == S::A_SLOTS) aslot = 0;
       }
       tcgen05_commit(accum_bar);
     }
@@ -575,7 +627,7 @@ int tc_conv_wgrad(const b200gan_conv* cv, const b200gan_view* x, const b200gan_v
   p.ci_groups = Ci / NCI;
   p.Co = Co; p.Ci = Ci; p.dw = dw;
   const int out_tiles = ((Co + 127) / 128) * (16 / p.T) * p.ci_groups;
-  int splits = (2 * kNumSMs + out_tiles - 1) / out_tiles;
+  int splits = ((NCI <= 64 ? 1 : 2) * kNumSMs + out_tiles - 1) / out_tiles;   // each CTA owns all 512 TMEM columns of its SM
   if (splits > p.kb_total) splits = p.kb_total;
   if (splits < 1) splits = 1;
   p.kb_per_split = (p.kb_total + splits - 1) / splits;

@@ -32,7 +32,7 @@ static bool dense_bf16_c(const b200gan_view* v, int c) {
 // one thread = one coarse pixel x 32 channels; weights broadcast from shared memory.
 // ---------------------------------------------------------------------------------------------------
 template <int NC, typename TF>
-__global__ void __launch_bounds__(256) thin_down_kernel(View fine, const float* __restrict__ w, __nv_bfloat16* __restrict__ out,
+__global__ void __launch_bounds__(256, 2) thin_down_kernel(View fine, const float* __restrict__ w, __nv_bfloat16* __restrict__ out,
                                                         int N, int H, int W, int act, float slope) {
   __shared__ __align__(16) float ws[16 * NC][32];
   for (int i = threadIdx.x; i < 512 * NC; i += blockDim.x) {

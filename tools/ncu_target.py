@@ -1,0 +1,40 @@
+#!/usr/bin/env python
+"""Launch each hot kernel of the step a few times at the benchmark shapes (B=512) so that one short
+`ncu --set full` pass can capture them (see profiles/)."""
+import ctypes as C, os, sys
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import gan_enhanced_pneumonia_classifier_b200 as pkg
+L = pkg._lib
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 512
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+st = L.stream_ptr
+bf = torch.bfloat16
+def rnd(shape, dt=bf): return torch.randn(shape, device='cuda').to(dt)
+auto = L.Conv(4, 2, 1, L.ALGO_AUTO)
+# thin layers (D0/G5, nc=1)
+img = rnd((B, 224, 224, 1)); c32 = rnd((B, 112, 112, 32)); w0 = rnd((32, 1, 4, 4), torch.float32) * 0.02
+out32 = torch.empty_like(c32); outimg = torch.empty_like(img); dw0 = torch.zeros_like(w0)
+# middle layers
+def mid(ci, h, co):
+    x = rnd((B, h, h, ci)); dy = rnd((B, h // 2, h // 2, co)); w = rnd((co, ci, 4, 4), torch.float32) * 0.02
+    wd = torch.empty(w.numel(), device='cuda', dtype=bf); wu = torch.empty(w.numel(), device='cuda', dtype=bf)
+    L.call('b200gan_pack_conv_weight', L.ptr(w), co, ci, 4, 0, L.ptr(wd), st()); L.call('b200gan_pack_conv_weight', L.ptr(w), co, ci, 4, 1, L.ptr(wu), st())
+    return dict(x=x, dy=dy, w=w, wd=wd, wu=wu, y=torch.empty_like(dy), dx=torch.empty_like(x), dw=torch.zeros_like(w))
+d1, d3, d4 = mid(32, 112, 64), mid(128, 28, 256), mid(256, 14, 512)
+# elementwise
+yb = rnd((B, 56, 56, 64)); dab = rnd((B, 56, 56, 64)); dyb = torch.empty_like(yb)
+sc, sh, mu, isd, gam = (torch.rand(64, device='cuda') + 0.5 for _ in range(5)); sums = torch.zeros(128, device='cuda', dtype=torch.float64)
+for _ in range(reps):
+    L.call('b200gan_conv2d_fprop', C.byref(auto), C.byref(L.view_nhwc(img)), L.ptr(w0), None, C.byref(L.view_nhwc(out32)), st())
+    L.call('b200gan_conv2d_dgrad', C.byref(auto), C.byref(L.view_nhwc(c32)), L.ptr(w0), None, C.byref(L.view_nhwc(outimg)), st())
+    L.call('b200gan_conv2d_wgrad', C.byref(auto), C.byref(L.view_nhwc(img)), C.byref(L.view_nhwc(c32)), L.ptr(dw0), st())
+    for d in (d1, d3, d4):
+        L.call('b200gan_conv2d_fprop', C.byref(auto), C.byref(L.view_nhwc(d['x'])), L.ptr(d['w']), L.ptr(d['wd']), C.byref(L.view_nhwc(d['y'])), st())
+        L.call('b200gan_conv2d_dgrad', C.byref(auto), C.byref(L.view_nhwc(d['dy'])), L.ptr(d['w']), L.ptr(d['wu']), C.byref(L.view_nhwc(d['dx'])), st())
+        L.call('b200gan_conv2d_wgrad', C.byref(auto), C.byref(L.view_nhwc(d['x'])), C.byref(L.view_nhwc(d['dy'])), L.ptr(d['dw']), st())
+    L.call('b200gan_bn_act_bwd_reduce', C.byref(L.view_nhwc(dab)), C.byref(L.view_nhwc(yb)), None, L.ptr(sc), L.ptr(sh), L.ptr(mu), L.ptr(isd), L.ACT_LRELU, 0.2, L.ptr(sums), st())
+    L.call('b200gan_bn_act_bwd_apply', C.byref(L.view_nhwc(dab)), C.byref(L.view_nhwc(yb)), None, L.ptr(sc), L.ptr(sh), L.ptr(mu), L.ptr(isd), L.ptr(gam), L.ptr(sums), B * 56 * 56, L.ACT_LRELU, 0.2, C.byref(L.view_nhwc(dyb)), None, None, st())
+    torch.cuda.synchronize()
+print('done')
