@@ -130,7 +130,7 @@ def time_dominant_kernel(pkg, torch, batch, peaks, iters=20):
     flush = torch.empty(256 * 1024 * 1024, device='cuda', dtype=torch.uint8)      # > 126 MB L2
 
     def launch():
-        L.call('b200gan_conv2d_fprop', C.byref(cv), C.byref(L.view_nhwc(x)), L.ptr(w), L.ptr(wp), C.byref(L.view_nhwc(y)), L.stream_ptr())
+        L.call('b200gan_conv2d_fprop', C.byref(cv), C.byref(L.view_nhwc(x)), L.ptr(w), L.ptr(wp), C.byref(L.view_nhwc(y)), None, L.stream_ptr())
     for _ in range(3):
         launch()
     torch.cuda.synchronize()

@@ -33,16 +33,27 @@ class Conv(C.Structure):
 
 _VP = C.POINTER(View)
 _CP = C.POINTER(Conv)
+
+
+class Fuse(C.Structure):
+    """struct b200gan_fuse: optional fusions around one convolution call (see include/b200gan.h)."""
+    _fields_ = [('out_act', C.c_int32), ('out_slope', C.c_float), ('dy_act', C.c_int32), ('dy_slope', C.c_float), ('dy_ref', _VP),
+                ('bn_sums', C.c_void_p), ('prev_act', C.c_int32), ('prev_slope', C.c_float), ('prev_y', _VP),
+                ('prev_scale', C.c_void_p), ('prev_shift', C.c_void_p), ('prev_mean', C.c_void_p), ('prev_invstd', C.c_void_p),
+                ('prev_sums', C.c_void_p)]
+
+
+_FP = C.POINTER(Fuse)
 _vp, _i32, _i64, _f32, _f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_double
 
 # name -> argtypes (every function returns int status unless noted); mirrors include/b200gan.h one to one
 PROTOTYPES = {
-    'b200gan_conv2d_fprop': [_CP, _VP, _vp, _vp, _VP, _vp],
-    'b200gan_conv2d_dgrad': [_CP, _VP, _vp, _vp, _VP, _vp],
-    'b200gan_conv2d_wgrad': [_CP, _VP, _VP, _vp, _vp],
-    'b200gan_convT2d_fprop': [_CP, _VP, _vp, _vp, _VP, _vp],
-    'b200gan_convT2d_dgrad': [_CP, _VP, _vp, _vp, _VP, _vp],
-    'b200gan_convT2d_wgrad': [_CP, _VP, _VP, _vp, _vp],
+    'b200gan_conv2d_fprop': [_CP, _VP, _vp, _vp, _VP, _FP, _vp],
+    'b200gan_conv2d_dgrad': [_CP, _VP, _vp, _vp, _VP, _FP, _vp],
+    'b200gan_conv2d_wgrad': [_CP, _VP, _VP, _vp, _FP, _vp],
+    'b200gan_convT2d_fprop': [_CP, _VP, _vp, _vp, _VP, _FP, _vp],
+    'b200gan_convT2d_dgrad': [_CP, _VP, _vp, _vp, _VP, _FP, _vp],
+    'b200gan_convT2d_wgrad': [_CP, _VP, _VP, _vp, _FP, _vp],
     'b200gan_pack_conv_weight': [_vp, _i32, _i32, _i32, _i32, _vp, _vp],
     'b200gan_bn_stats': [_VP, _vp, _vp],
     'b200gan_bn_finalize': [_vp, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _vp, _vp, _vp, _vp, _vp],
@@ -125,6 +136,16 @@ def view_rows(t, n, h, w, c, row_period, row_offset=0):
     sh = w * c
     base = t.data_ptr() + row_offset * sh * t.element_size()
     return View(base, _DTYPES[t.dtype], n, h, w, c, row_period * sh, sh, sw, sc)
+
+
+def fuse(out_act=ACT_NONE, out_slope=0.0, dy_act=ACT_NONE, dy_slope=0.0, dy_ref=None, bn_sums=None, prev_act=ACT_NONE, prev_slope=0.0,
+         prev_y=None, prev_scale=None, prev_shift=None, prev_mean=None, prev_invstd=None, prev_sums=None):
+    """Build a b200gan_fuse.  dy_ref / prev_y are View objects (kept alive by the caller for the duration of the call);
+    the remaining pointers are tensors."""
+    def p(t):
+        return t.data_ptr() if t is not None else None
+    return Fuse(out_act, out_slope, dy_act, dy_slope, C.pointer(dy_ref) if dy_ref is not None else None, p(bn_sums), prev_act, prev_slope,
+                C.pointer(prev_y) if prev_y is not None else None, p(prev_scale), p(prev_shift), p(prev_mean), p(prev_invstd), p(prev_sums))
 
 
 def device_info(device=0):

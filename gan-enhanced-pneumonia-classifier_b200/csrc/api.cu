@@ -23,18 +23,23 @@ int cuda_fail(cudaError_t e, const char* what) {
 }
 
 // SIMT kernels (conv_simt.cu)
-int simt_conv_fprop(const b200gan_conv*, const b200gan_view* x, const float* w, const b200gan_view* y, cudaStream_t);
-int simt_conv_dgrad(const b200gan_conv*, const b200gan_view* dy, const float* w, const b200gan_view* dx, cudaStream_t);
-int simt_conv_wgrad(const b200gan_conv*, const b200gan_view* x, const b200gan_view* dy, float* dw, cudaStream_t);
+int simt_conv_fprop(const b200gan_conv*, const b200gan_view* x, const float* w, const b200gan_view* y, const ConvFuse&, cudaStream_t);
+int simt_conv_dgrad(const b200gan_conv*, const b200gan_view* dy, const float* w, const b200gan_view* dx, const ConvFuse&, cudaStream_t);
+int simt_conv_wgrad(const b200gan_conv*, const b200gan_view* x, const b200gan_view* dy, float* dw, const ConvFuse&, bool grad_is_coarse,
+                    cudaStream_t);
 // tensor-core kernels (conv_tc.cu): return 1 when the problem does not qualify (caller falls back / errors)
-int tc_conv_fprop(const b200gan_conv*, const b200gan_view* x, const void* wpacked, const b200gan_view* y, cudaStream_t);
-int tc_conv_dgrad(const b200gan_conv*, const b200gan_view* dy, const void* wpacked, const b200gan_view* dx, cudaStream_t);
+int tc_conv_fprop(const b200gan_conv*, const b200gan_view* x, const void* wpacked, const b200gan_view* y, const TcEpi&, cudaStream_t);
+int tc_conv_dgrad(const b200gan_conv*, const b200gan_view* dy, const void* wpacked, const b200gan_view* dx, const TcEpi&, cudaStream_t);
 int tc_conv_wgrad(const b200gan_conv*, const b200gan_view* x, const b200gan_view* dy, float* dw, cudaStream_t);
 int tc_pack_weight(const float* w, int Co, int Ci, int k, int form, void* out, cudaStream_t);
-// shape-specialised CUDA-core kernels (conv_thin.cu): same return convention
-int thin_down(const b200gan_view* fine, const float* w, const b200gan_view* coarse, int act, float slope, cudaStream_t);
-int thin_up(const b200gan_view* coarse, const float* w, const b200gan_view* fine, int act, cudaStream_t);
-int thin_wgrad(const b200gan_view* fine, const b200gan_view* coarse, float* dw, cudaStream_t);
+// image-side layers on warp-level MMAs (conv_thin_mma.cu): same return convention
+int thin_down(const b200gan_view* fine, const b200gan_view* fine_ref, int fine_act, const float* w, const b200gan_view* coarse, int out_act,
+              float slope, cudaStream_t);
+int thin_up(const b200gan_view* coarse, const b200gan_view* coarse_ref, int coarse_act, float slope, const float* w, const b200gan_view* fine,
+            int out_act, cudaStream_t);
+int thin_wgrad(const b200gan_view* fine, const b200gan_view* fine_ref, int fine_act, const b200gan_view* coarse, const b200gan_view* coarse_ref,
+               int coarse_act, float slope, float* dw, cudaStream_t);
+// latent GEMM and 7x7 GEMV (conv_thin.cu): same return convention
 int window_fprop(const b200gan_conv*, const b200gan_view* x, const float* w, const b200gan_view* y, cudaStream_t);
 int window_dgrad(const b200gan_conv*, const b200gan_view* dy, const float* w, const b200gan_view* dx, cudaStream_t);
 int window_wgrad(const b200gan_conv*, const b200gan_view* x, const b200gan_view* dy, float* dw, cudaStream_t);
@@ -51,6 +56,7 @@ int ew_bn_act_fwd(const b200gan_view*, const float*, const float*, int, float, c
 int ew_bn_act_bwd_apply(const b200gan_view*, const b200gan_view*, const b200gan_view*, const float*, const float*, const float*,
                         const float*, const float*, double*, int64_t, int, float, const b200gan_view*, float*, float*,
                         cudaStream_t);
+int ew_act_bwd_inplace(const b200gan_view* d, const b200gan_view* y, const float* scale, const float* shift, int act, float slope, cudaStream_t);
 int ew_bce_sigmoid(const float*, int, float, float, float*, float*, float*, cudaStream_t);
 int ew_adam(float*, const float*, float*, float*, int64_t, double, double, double, double, int, float, cudaStream_t);
 int ew_copy_view(const b200gan_view*, const b200gan_view*, cudaStream_t);
@@ -80,8 +86,14 @@ static int check_pair(const b200gan_conv* cv, const b200gan_view* fine, const b2
 
 enum Prim { FPROP, DGRAD, WGRAD };
 
-static int conv_dispatch(Prim prim, const b200gan_conv* cv, const b200gan_view* fine, const b200gan_view* coarse,
-                         const float* w, const void* wpacked, float* dw, void* stream, const char* what) {
+static bool same_extent(const b200gan_view* a, const b200gan_view* b) { return a->n == b->n && a->h == b->h && a->w == b->w && a->c == b->c; }
+
+// Conv-geometry dispatcher.  fine/coarse are the two activation sides of the k/stride/pad geometry; `transposed` says the
+// call came through the ConvTranspose2d entry points (its forward is the DGRAD primitive, its input gradient the FPROP one).
+// The gradient operand of the call (for the dy_* fusion) is: DGRAD prim -> coarse, FPROP prim -> fine, WGRAD -> coarse for
+// Conv2d and fine for ConvTranspose2d.
+static int conv_dispatch(Prim prim, bool transposed, const b200gan_conv* cv, const b200gan_view* fine, const b200gan_view* coarse,
+                         const float* w, const void* wpacked, float* dw, const b200gan_fuse* fuse, void* stream, const char* what) {
   int rc;
   if ((rc = check_conv(cv))) return rc;
   if ((rc = check_view(fine, what))) return rc;
@@ -90,35 +102,103 @@ static int conv_dispatch(Prim prim, const b200gan_conv* cv, const b200gan_view* 
   if (prim != WGRAD && !w) { set_error("%s: null weight", what); return B200GAN_ERR_BAD_ARG; }
   if (prim == WGRAD && !dw) { set_error("%s: null dweight", what); return B200GAN_ERR_BAD_ARG; }
   cudaStream_t st = (cudaStream_t)stream;
+
+  // ---- resolve the requested fusions -------------------------------------------------------------
+  const bool is_fwd = (prim == FPROP && !transposed) || (prim == DGRAD && transposed);     // the API's forward call
+  const b200gan_view* result = prim == FPROP ? coarse : fine;                                // written by FPROP / DGRAD prims
+  const b200gan_view* gathered = prim == FPROP ? fine : coarse;
+  ConvFuse fz;
+  double* bn_sums = nullptr;
+  bool prev = false;
+  if (fuse) {
+    const bool has_out = fuse->out_act != B200GAN_ACT_NONE, has_dy = fuse->dy_act != B200GAN_ACT_NONE;
+    prev = fuse->prev_sums != nullptr;
+    if (is_fwd) {
+      B200_CHECK_ARG(!has_dy && !prev, "%s: dy_* / prev_* fusions do not apply to a forward convolution", what);
+      B200_CHECK_ARG(fuse->out_act >= B200GAN_ACT_NONE && fuse->out_act <= B200GAN_ACT_SIGMOID, "%s: bad out_act %d", what, fuse->out_act);
+      B200_CHECK_ARG(!(has_out && fuse->bn_sums), "%s: out_act and bn_sums are mutually exclusive (BatchNorm sits before the activation)", what);
+      fz.out_act = fuse->out_act; fz.out_slope = fuse->out_slope;
+      bn_sums = fuse->bn_sums;
+    } else {
+      B200_CHECK_ARG(!has_out && !fuse->bn_sums, "%s: out_act / bn_sums only apply to a forward convolution", what);
+      B200_CHECK_ARG(prim != WGRAD || !prev, "%s: prev_* fusion only applies to an input-gradient convolution", what);
+      if (has_dy) {
+        B200_CHECK_ARG(fuse->dy_act >= B200GAN_ACT_NONE && fuse->dy_act <= B200GAN_ACT_SIGMOID && fuse->dy_ref, "%s: dy_act needs dy_ref", what);
+        if ((rc = check_view(fuse->dy_ref, what))) return rc;
+        const b200gan_view* g = prim == WGRAD ? (transposed ? fine : coarse) : gathered;
+        B200_CHECK_ARG(same_extent(fuse->dy_ref, g), "%s: dy_ref extents differ from dy", what);
+        fz.g_ref = fuse->dy_ref; fz.g_act = fuse->dy_act; fz.g_slope = fuse->dy_slope;
+      }
+      if (prev) {
+        B200_CHECK_ARG(fuse->prev_y && fuse->prev_scale && fuse->prev_shift && fuse->prev_mean && fuse->prev_invstd, "%s: prev_* pointers missing", what);
+        if ((rc = check_view(fuse->prev_y, what))) return rc;
+        B200_CHECK_ARG(same_extent(fuse->prev_y, result) && fuse->prev_y->dtype == result->dtype, "%s: prev_y must match dx in extents and dtype", what);
+        if (fuse->prev_act != B200GAN_ACT_RELU && fuse->prev_act != B200GAN_ACT_LRELU && fuse->prev_act != B200GAN_ACT_NONE) {
+          set_error("%s: prev_act must be NONE, RELU or LRELU (the activations that follow a BatchNorm in dcgan.py)", what);
+          return B200GAN_ERR_UNSUPPORTED;
+        }
+      }
+    }
+  }
+  const bool grad_is_coarse = !transposed;      // WGRAD only
+  const bool plain = fz.out_act == B200GAN_ACT_NONE && !fz.g_ref;
+
+  // ---- kernel selection ----------------------------------------------------------------------------
+  int t = 1;
   if (cv->algo != B200GAN_ALGO_SIMT) {
-    int t = 1;
-    if (prim == FPROP) t = tc_conv_fprop(cv, fine, wpacked, coarse, st);
-    else if (prim == DGRAD) t = tc_conv_dgrad(cv, coarse, wpacked, fine, st);
-    else t = tc_conv_wgrad(cv, fine, coarse, dw, st);
-    if (t <= 0) return t;                       // done (0) or hard error (<0)
-    if (cv->algo == B200GAN_ALGO_TCGEN05) {
-      set_error("%s: shape/dtype not supported by the tcgen05 path", what);
+    if (plain) {
+      // the tensor-core kernels absorb the BatchNorm fusions in their epilogue
+      TcEpi epi;
+      if (bn_sums) { epi.mode = 1; epi.sums = bn_sums; }
+      if (prev) {
+        epi.mode = 2; epi.sums = fuse->prev_sums; epi.prev_y = fuse->prev_y; epi.scale = fuse->prev_scale; epi.shift = fuse->prev_shift;
+        epi.mean = fuse->prev_mean; epi.invstd = fuse->prev_invstd; epi.act = fuse->prev_act; epi.slope = fuse->prev_slope;
+      }
+      if (prim == FPROP) t = tc_conv_fprop(cv, fine, wpacked, coarse, epi, st);
+      else if (prim == DGRAD) t = tc_conv_dgrad(cv, coarse, wpacked, fine, epi, st);
+      else t = tc_conv_wgrad(cv, fine, coarse, dw, st);
+      if (t < 0) return t;
+      if (t == 0) { bn_sums = nullptr; prev = false; }
+    }
+    if (t > 0 && cv->algo == B200GAN_ALGO_TCGEN05) {
+      set_error("%s: shape/dtype/fusion not supported by the tcgen05 path", what);
       return B200GAN_ERR_UNSUPPORTED;
     }
-    // shape-specialised CUDA-core kernels for the thin image-side layers, the latent GEMM and the 7x7 GEMV
+    // image-side layers (warp-level MMA, fused activations), the latent GEMM and the 7x7 GEMV
     const bool k4 = cv->k == 4 && cv->stride == 2 && cv->pad == 1;
-    if (prim == FPROP) {
-      if (k4) t = thin_down(fine, w, coarse, B200GAN_ACT_NONE, 0.f, st);
-      if (t > 0) t = window_fprop(cv, fine, w, coarse, st);
-    } else if (prim == DGRAD) {
-      if (k4) t = thin_up(coarse, w, fine, B200GAN_ACT_NONE, st);
-      if (t > 0) t = window_dgrad(cv, coarse, w, fine, st);
-      if (t > 0) t = latent_fprop(cv, coarse, w, fine, st);
-    } else {
-      if (k4) t = thin_wgrad(fine, coarse, dw, st);
-      if (t > 0) t = window_wgrad(cv, fine, coarse, dw, st);
-      if (t > 0) t = latent_wgrad(cv, fine, coarse, dw, st);
+    if (t > 0 && k4) {
+      if (prim == FPROP) t = thin_down(fine, fz.g_ref, fz.g_act, w, coarse, fz.out_act, fz.g_ref ? fz.g_slope : fz.out_slope, st);
+      else if (prim == DGRAD) t = thin_up(coarse, fz.g_ref, fz.g_act, fz.g_slope, w, fine, fz.out_act, st);
+      else t = thin_wgrad(fine, grad_is_coarse ? nullptr : fz.g_ref, fz.g_act, coarse, grad_is_coarse ? fz.g_ref : nullptr, fz.g_act, fz.g_slope, dw, st);
+      if (t < 0) return t;
     }
-    if (t <= 0) return t;
+    if (t > 0 && plain) {
+      if (prim == FPROP) t = window_fprop(cv, fine, w, coarse, st);
+      else if (prim == DGRAD) {
+        t = window_dgrad(cv, coarse, w, fine, st);
+        if (t > 0) t = latent_fprop(cv, coarse, w, fine, st);
+      } else {
+        t = window_wgrad(cv, fine, coarse, dw, st);
+        if (t > 0) t = latent_wgrad(cv, fine, coarse, dw, st);
+      }
+      if (t < 0) return t;
+    }
   }
-  if (prim == FPROP) return simt_conv_fprop(cv, fine, w, coarse, st);
-  if (prim == DGRAD) return simt_conv_dgrad(cv, coarse, w, fine, st);
-  return simt_conv_wgrad(cv, fine, coarse, dw, st);
+  if (t > 0) {
+    if (prim == FPROP) t = simt_conv_fprop(cv, fine, w, coarse, fz, st);
+    else if (prim == DGRAD) t = simt_conv_dgrad(cv, coarse, w, fine, fz, st);
+    else t = simt_conv_wgrad(cv, fine, coarse, dw, fz, grad_is_coarse, st);
+    if (t) return t;
+  }
+  // ---- BatchNorm fusions not absorbed by the kernel: the equivalent passes ---------------------------------
+  if (bn_sums && (rc = ew_bn_stats(result, bn_sums, st))) return rc;
+  if (prev) {
+    if ((rc = ew_bn_bwd_reduce(result, fuse->prev_y, nullptr, fuse->prev_scale, fuse->prev_shift, fuse->prev_mean, fuse->prev_invstd,
+                               fuse->prev_act, fuse->prev_slope, fuse->prev_sums, st)))
+      return rc;
+    if ((rc = ew_act_bwd_inplace(result, fuse->prev_y, fuse->prev_scale, fuse->prev_shift, fuse->prev_act, fuse->prev_slope, st))) return rc;
+  }
+  return 0;
 }
 
 }  // namespace b200gan
@@ -141,28 +221,30 @@ int b200gan_device_info(int device, char* name, int* cc_major, int* cc_minor) {
 }
 
 int b200gan_conv2d_fprop(const b200gan_conv* cv, const b200gan_view* x, const float* weight, const void* wpacked,
-                         const b200gan_view* y, void* stream) {
-  return conv_dispatch(FPROP, cv, x, y, weight, wpacked, nullptr, stream, "conv2d_fprop");
+                         const b200gan_view* y, const b200gan_fuse* fuse, void* stream) {
+  return conv_dispatch(FPROP, false, cv, x, y, weight, wpacked, nullptr, fuse, stream, "conv2d_fprop");
 }
 int b200gan_conv2d_dgrad(const b200gan_conv* cv, const b200gan_view* dy, const float* weight, const void* wpacked,
-                         const b200gan_view* dx, void* stream) {
-  return conv_dispatch(DGRAD, cv, dx, dy, weight, wpacked, nullptr, stream, "conv2d_dgrad");
+                         const b200gan_view* dx, const b200gan_fuse* fuse, void* stream) {
+  return conv_dispatch(DGRAD, false, cv, dx, dy, weight, wpacked, nullptr, fuse, stream, "conv2d_dgrad");
 }
-int b200gan_conv2d_wgrad(const b200gan_conv* cv, const b200gan_view* x, const b200gan_view* dy, float* dweight, void* stream) {
-  return conv_dispatch(WGRAD, cv, x, dy, nullptr, nullptr, dweight, stream, "conv2d_wgrad");
+int b200gan_conv2d_wgrad(const b200gan_conv* cv, const b200gan_view* x, const b200gan_view* dy, float* dweight, const b200gan_fuse* fuse,
+                         void* stream) {
+  return conv_dispatch(WGRAD, false, cv, x, dy, nullptr, nullptr, dweight, fuse, stream, "conv2d_wgrad");
 }
 // ConvTranspose2d == the conv input-gradient on the same geometry: its input is the coarse side, its
 // output the fine side, and its weight (Cin_T, Cout_T, k, k) is the conv weight (Co, Ci, k, k).
 int b200gan_convT2d_fprop(const b200gan_conv* cv, const b200gan_view* x, const float* weight, const void* wpacked,
-                          const b200gan_view* y, void* stream) {
-  return conv_dispatch(DGRAD, cv, y, x, weight, wpacked, nullptr, stream, "convT2d_fprop");
+                          const b200gan_view* y, const b200gan_fuse* fuse, void* stream) {
+  return conv_dispatch(DGRAD, true, cv, y, x, weight, wpacked, nullptr, fuse, stream, "convT2d_fprop");
 }
 int b200gan_convT2d_dgrad(const b200gan_conv* cv, const b200gan_view* dy, const float* weight, const void* wpacked,
-                          const b200gan_view* dx, void* stream) {
-  return conv_dispatch(FPROP, cv, dy, dx, weight, wpacked, nullptr, stream, "convT2d_dgrad");
+                          const b200gan_view* dx, const b200gan_fuse* fuse, void* stream) {
+  return conv_dispatch(FPROP, true, cv, dy, dx, weight, wpacked, nullptr, fuse, stream, "convT2d_dgrad");
 }
-int b200gan_convT2d_wgrad(const b200gan_conv* cv, const b200gan_view* x, const b200gan_view* dy, float* dweight, void* stream) {
-  return conv_dispatch(WGRAD, cv, dy, x, nullptr, nullptr, dweight, stream, "convT2d_wgrad");
+int b200gan_convT2d_wgrad(const b200gan_conv* cv, const b200gan_view* x, const b200gan_view* dy, float* dweight, const b200gan_fuse* fuse,
+                          void* stream) {
+  return conv_dispatch(WGRAD, true, cv, dy, x, nullptr, nullptr, dweight, fuse, stream, "convT2d_wgrad");
 }
 
 int b200gan_pack_conv_weight(const float* weight, int32_t co, int32_t ci, int32_t k, int32_t form, void* out, void* stream) {

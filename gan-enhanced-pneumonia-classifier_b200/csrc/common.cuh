@@ -76,4 +76,56 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 constexpr int kNumSMs = 148;   // B200
 
+// 8 bf16 <-> 8 floats through one 16-byte vector
+__device__ __forceinline__ void unpack8(const uint4& t, float* v) {
+  const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+}
+__device__ __forceinline__ uint4 pack8(const float* v) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { __nv_bfloat162 b = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]); w[i] = *reinterpret_cast<uint32_t*>(&b); }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// act'(.) expressed through the SAVED OUTPUT a of the activation (what the forward pass keeps): LeakyReLU and ReLU
+// preserve the sign of their argument, tanh' = 1 - a^2, sigmoid' = a (1 - a).
+__device__ __forceinline__ float act_grad_from_output(float a, int act, float slope) {
+  switch (act) {
+    case B200GAN_ACT_RELU: return a > 0.f ? 1.f : 0.f;
+    case B200GAN_ACT_LRELU: return a > 0.f ? 1.f : slope;
+    case B200GAN_ACT_TANH: return 1.f - a * a;
+    case B200GAN_ACT_SIGMOID: return a * (1.f - a);
+    default: return 1.f;
+  }
+}
+__device__ __forceinline__ float act_apply(float z, int act, float slope) {
+  switch (act) {
+    case B200GAN_ACT_RELU: return z > 0.f ? z : 0.f;
+    case B200GAN_ACT_LRELU: return z > 0.f ? z : z * slope;
+    case B200GAN_ACT_TANH: return tanhf(z);
+    case B200GAN_ACT_SIGMOID: return 1.f / (1.f + expf(-z));
+    default: return z;
+  }
+}
+// one element of a view whose dtype is only known at run time
+__device__ __forceinline__ float ld_rt(const void* base, int dtype, int64_t off) {
+  return dtype == B200GAN_F32 ? reinterpret_cast<const float*>(base)[off] : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base)[off]);
+}
+
+struct TcEpi {                       // host-side description of the requested epilogue fusion
+  int mode = 0;
+  double* sums = nullptr;
+  const b200gan_view* prev_y = nullptr;
+  const float *scale = nullptr, *shift = nullptr, *mean = nullptr, *invstd = nullptr;
+  int act = 0; float slope = 0.f;
+};
+
+// Fusions requested around one convolution call, resolved from b200gan_fuse by the dispatcher (api.cu).
+struct ConvFuse {
+  int out_act = B200GAN_ACT_NONE; float out_slope = 0.f;        // activation on the result
+  const b200gan_view* g_ref = nullptr; int g_act = B200GAN_ACT_NONE; float g_slope = 0.f;   // gradient operand *= act'(g_ref)
+};
+
 }  // namespace b200gan

@@ -23,6 +23,10 @@ struct GatherParams {
   void* out;
   int64_t o_sn, o_sh, o_sw, o_sc;
   int o_mul, o_off_h, o_off_w;         // output pixel = (qh*o_mul + o_off_h, qw*o_mul + o_off_w)
+  // fusions (ConvFuse): gathered operand *= act'(ref) with ref addressed like `in`; activation on the result
+  const void* ref; int ref_dtype; int64_t r_sn, r_sh, r_sw, r_sc;
+  int g_act; float g_slope;
+  int out_act; float out_slope;
 };
 
 template <typename TIn, typename TOut>
@@ -48,6 +52,7 @@ __global__ void __launch_bounds__(256) gather_gemm_kernel(GatherParams p) {
   }
   const int a_h0 = aqh * p.i_mul + p.i_base_h, a_w0 = aqw * p.i_mul + p.i_base_w;
   const TIn* in = reinterpret_cast<const TIn*>(p.in) + (int64_t)an * p.i_sn;
+  const int64_t ref_n = (int64_t)an * p.r_sn;
 
   const int b_col = tid & 63, b_k = (tid >> 6) * 4;
   const int bcn = n0 + b_col;
@@ -70,8 +75,12 @@ __global__ void __launch_bounds__(256) gather_gemm_kernel(GatherParams p) {
         const int tap = kk / p.CK, ck = kk - tap * p.CK;
         const int jh = tap / p.TW, jw = tap - jh * p.TW;
         const int ih = a_h0 + jh * p.i_tstep, iw = a_w0 + jw * p.i_tstep;
-        if ((unsigned)ih < (unsigned)p.IH && (unsigned)iw < (unsigned)p.IW)
+        if ((unsigned)ih < (unsigned)p.IH && (unsigned)iw < (unsigned)p.IW) {
           v = ld_as_float(in + (int64_t)ih * p.i_sh + (int64_t)iw * p.i_sw + (int64_t)ck * p.i_sc);
+          if (p.ref)
+            v *= act_grad_from_output(ld_rt(p.ref, p.ref_dtype, ref_n + (int64_t)ih * p.r_sh + (int64_t)iw * p.r_sw + (int64_t)ck * p.r_sc),
+                                      p.g_act, p.g_slope);
+        }
       }
       As[a_k + e][a_row] = v;
     }
@@ -113,9 +122,19 @@ __global__ void __launch_bounds__(256) gather_gemm_kernel(GatherParams p) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int cn = n0 + tx * 4 + j;
-      if (cn < p.CN) st_from_float(o + (int64_t)cn * p.o_sc, acc[i][j]);
+      if (cn < p.CN) st_from_float(o + (int64_t)cn * p.o_sc, act_apply(acc[i][j], p.out_act, p.out_slope));
     }
   }
+}
+
+static void set_fuse(GatherParams& p, const ConvFuse& f) {
+  p.ref = nullptr; p.g_act = B200GAN_ACT_NONE; p.g_slope = 0.f;
+  if (f.g_ref) {
+    p.ref = f.g_ref->ptr; p.ref_dtype = f.g_ref->dtype;
+    p.r_sn = f.g_ref->sn; p.r_sh = f.g_ref->sh; p.r_sw = f.g_ref->sw; p.r_sc = f.g_ref->sc;
+    p.g_act = f.g_act; p.g_slope = f.g_slope;
+  }
+  p.out_act = f.out_act; p.out_slope = f.out_slope;
 }
 
 static int launch_gather(const GatherParams& p, int in_dtype, int out_dtype, cudaStream_t st) {
@@ -135,8 +154,10 @@ static int launch_gather(const GatherParams& p, int in_dtype, int out_dtype, cud
 }
 
 // y = conv(x, w): conv geometry Co = y.c, Ci = x.c
-int simt_conv_fprop(const b200gan_conv* cv, const b200gan_view* x, const float* w, const b200gan_view* y, cudaStream_t st) {
+int simt_conv_fprop(const b200gan_conv* cv, const b200gan_view* x, const float* w, const b200gan_view* y, const ConvFuse& fz,
+                    cudaStream_t st) {
   GatherParams p{};
+  set_fuse(p, fz);
   p.N = x->n; p.QH = y->h; p.QW = y->w;
   p.in = x->ptr; p.i_sn = x->sn; p.i_sh = x->sh; p.i_sw = x->sw; p.i_sc = x->sc; p.IH = x->h; p.IW = x->w;
   p.i_mul = cv->stride; p.i_base_h = p.i_base_w = -cv->pad; p.i_tstep = 1;
@@ -148,11 +169,13 @@ int simt_conv_fprop(const b200gan_conv* cv, const b200gan_view* x, const float* 
 }
 
 // dx = conv_dgrad(dy, w): conv geometry Co = dy.c, Ci = dx.c; one launch per output parity class
-int simt_conv_dgrad(const b200gan_conv* cv, const b200gan_view* dy, const float* w, const b200gan_view* dx, cudaStream_t st) {
+int simt_conv_dgrad(const b200gan_conv* cv, const b200gan_view* dy, const float* w, const b200gan_view* dx, const ConvFuse& fz,
+                    cudaStream_t st) {
   const int s = cv->stride, k = cv->k, pad = cv->pad;
   for (int ph = 0; ph < s; ++ph)
     for (int pw = 0; pw < s; ++pw) {
       GatherParams p{};
+      set_fuse(p, fz);
       p.N = dx->n; p.QH = (dx->h - ph + s - 1) / s; p.QW = (dx->w - pw + s - 1) / s;
       if (p.QH <= 0 || p.QW <= 0) continue;
       p.in = dy->ptr; p.i_sn = dy->sn; p.i_sh = dy->sh; p.i_sw = dy->sw; p.i_sc = dy->sc; p.IH = dy->h; p.IW = dy->w;
@@ -180,6 +203,8 @@ struct WgradParams {
   int IH, IW, CI, k, stride, pad;
   float* dw;
   int64_t pix_per_split;
+  // fused activation backward on the gradient operand: which = 0 none, 1 dy (coarse side), 2 x (fine side)
+  const void* ref; int ref_dtype; int64_t r_sn, r_sh, r_sw, r_sc; int which, g_act; float g_slope;
 };
 
 template <typename TX, typename TD>
@@ -231,12 +256,20 @@ __global__ void __launch_bounds__(256) wgrad_kernel(WgradParams p) {
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const int co = co0 + l4 + e;
-      As[lk][l4 + e] = (pv && co < p.CO) ? ld_as_float(dyp + (int64_t)co * p.d_sc) : 0.f;
+      float av = (pv && co < p.CO) ? ld_as_float(dyp + (int64_t)co * p.d_sc) : 0.f;
+      if (p.which == 1 && pv && co < p.CO)
+        av *= act_grad_from_output(ld_rt(p.ref, p.ref_dtype, (int64_t)n * p.r_sn + (int64_t)oh * p.r_sh + (int64_t)ow * p.r_sw + (int64_t)co * p.r_sc),
+                                   p.g_act, p.g_slope);
+      As[lk][l4 + e] = av;
       float v = 0.f;
       if (pv && b_ok[e]) {
         const int ih = ih0 + b_kh[e], iw = iw0 + b_kw[e];
-        if ((unsigned)ih < (unsigned)p.IH && (unsigned)iw < (unsigned)p.IW)
+        if ((unsigned)ih < (unsigned)p.IH && (unsigned)iw < (unsigned)p.IW) {
           v = ld_as_float(xp + (int64_t)ih * p.x_sh + (int64_t)iw * p.x_sw + (int64_t)b_ci[e] * p.x_sc);
+          if (p.which == 2)
+            v *= act_grad_from_output(ld_rt(p.ref, p.ref_dtype, (int64_t)n * p.r_sn + (int64_t)ih * p.r_sh + (int64_t)iw * p.r_sw + (int64_t)b_ci[e] * p.r_sc),
+                                      p.g_act, p.g_slope);
+        }
       }
       Bs[lk][l4 + e] = v;
     }
@@ -269,8 +302,17 @@ __global__ void __launch_bounds__(256) wgrad_kernel(WgradParams p) {
 }
 
 // conv geometry: x (N,IH,IW,Ci) fine side, dy (N,OH,OW,Co) coarse side, dw (Co,Ci,k,k) accumulated
-int simt_conv_wgrad(const b200gan_conv* cv, const b200gan_view* x, const b200gan_view* dy, float* dw, cudaStream_t st) {
+// fz.g_ref applies to dy when grad_is_coarse, to x otherwise (ConvTranspose2d: the gradient is the fine side)
+int simt_conv_wgrad(const b200gan_conv* cv, const b200gan_view* x, const b200gan_view* dy, float* dw, const ConvFuse& fz, bool grad_is_coarse,
+                    cudaStream_t st) {
   WgradParams p{};
+  p.which = 0; p.ref = nullptr;
+  if (fz.g_ref) {
+    p.which = grad_is_coarse ? 1 : 2;
+    p.ref = fz.g_ref->ptr; p.ref_dtype = fz.g_ref->dtype;
+    p.r_sn = fz.g_ref->sn; p.r_sh = fz.g_ref->sh; p.r_sw = fz.g_ref->sw; p.r_sc = fz.g_ref->sc;
+    p.g_act = fz.g_act; p.g_slope = fz.g_slope;
+  }
   p.N = dy->n; p.OH = dy->h; p.OW = dy->w; p.CO = dy->c;
   p.dy = dy->ptr; p.d_sn = dy->sn; p.d_sh = dy->sh; p.d_sw = dy->sw; p.d_sc = dy->sc;
   p.x = x->ptr; p.x_sn = x->sn; p.x_sh = x->sh; p.x_sw = x->sw; p.x_sc = x->sc;

@@ -128,7 +128,29 @@ struct TcConvParams {
   int64_t o_sn, o_sh, o_sw;
   int o_mul;                         // output pixel = q*o_mul + class parity
   int cout;
+  // epilogue fusions (template EPI): 1 = BatchNorm statistics of the result, 2 = previous layer's activation backward +
+  // BatchNorm-backward sums (b200gan_fuse.bn_sums / prev_*)
+  double* sums;                      // [2*cout], zeroed by the host wrapper
+  const __nv_bfloat16* prev_y;       // same dense NHWC layout as out
+  const float *prev_scale, *prev_shift, *prev_mean, *prev_invstd;
+  float prev_neg;                    // act'(z) for z <= 0: 0 (ReLU), slope (LeakyReLU), 1 (none)
 };
+
+
+// Column sums over the 32 lanes of a warp for 32 columns held as v[0..31] per lane: 31 shuffles (reduce-scatter butterfly)
+// instead of 32 x 5.  On return v[0] of lane j is the sum of column j.
+__device__ __forceinline__ void warp_column_sums(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = up ? v[i] : v[i + off];
+      const float keep = up ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+}
 
 template <int BN, int KC, int STAGES>
 struct TcSmem {
@@ -147,7 +169,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps the MMA stream of tile i+1, and the
 // smem ring keeps running across tile boundaries.  No integer division sits on the per-k-block path of the two
 // single-thread roles (a first version spent ~100 instructions per step there).
-template <int BN, int KC, int STAGES>
+template <int BN, int KC, int STAGES, int EPI>
 __global__ void __launch_bounds__(192, 1)
 conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcConvParams p) {
   using S = TcSmem<BN, KC, STAGES>;
@@ -158,6 +180,15 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   uint64_t* acc_full = empty_bar + STAGES;     // [2]
   uint64_t* acc_empty = acc_full + 2;          // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  // EPI != 0: per-CTA channel accumulators [2][cout] (flushed once at the end), EPI == 2: {scale, shift, mean, invstd}[cout]
+  float* ch_acc = reinterpret_cast<float*>(smem + STAGES * S::STAGE_BYTES + 256);
+  float4* ch_coef = reinterpret_cast<float4*>(ch_acc + 2 * p.cout);
+  if (EPI != 0) {
+    for (int c = threadIdx.x; c < 2 * p.cout; c += blockDim.x) ch_acc[c] = 0.f;
+    if (EPI == 2)
+      for (int c = threadIdx.x; c < p.cout; c += blockDim.x)
+        ch_coef[c] = make_float4(p.prev_scale[c], p.prev_shift[c], p.prev_mean[c], p.prev_invstd[c]);
+  }
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int TW = 1 << p.tw_log2, TH = 1 << p.th_log2, TN = 128 >> (p.tw_log2 + p.th_log2);
@@ -266,19 +297,50 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         uint32_t v[32];
         tcgen05_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + c0, v);
         tcgen05_wait_ld();
+        float s0[32], s1[32];
+        if (EPI == 2) {
+          // dz = dx * act'(scale*y_prev + shift); sums of dz and dz*(y_prev - mean) (x invstd at the flush)
+          const uint4* yp = reinterpret_cast<const uint4*>(p.prev_y + (orow - p.out) + c0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float yv[8];
+            unpack8(valid ? __ldg(yp + j) : make_uint4(0u, 0u, 0u, 0u), yv);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float4 cf = ch_coef[cout0 + c0 + 8 * j + e];
+              const float z = fmaf(yv[e], cf.x, cf.y);
+              v[8 * j + e] = __float_as_uint(__uint_as_float(v[8 * j + e]) * (z > 0.f ? 1.f : p.prev_neg));
+              s1[8 * j + e] = yv[e] - cf.z;
+            }
+          }
+        }
+        // round to the stored precision; the statistics are those of the stored tensor
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          __nv_bfloat162 b = __floats2bfloat162_rn(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+          pk[j] = *reinterpret_cast<uint32_t*>(&b);
+        }
+        if (EPI != 0) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float lo = valid ? __uint_as_float(pk[j] << 16) : 0.f, hi = valid ? __uint_as_float(pk[j] & 0xffff0000u) : 0.f;
+            s0[2 * j] = lo; s0[2 * j + 1] = hi;
+            if (EPI == 1) { s1[2 * j] = lo * lo; s1[2 * j + 1] = hi * hi; }
+            else { s1[2 * j] *= lo; s1[2 * j + 1] *= hi; }
+          }
+          warp_column_sums(s0, lane);
+          warp_column_sums(s1, lane);
+          if (cout0 + c0 + lane < p.cout) {
+            atomicAdd(&ch_acc[cout0 + c0 + lane], s0[0]);
+            atomicAdd(&ch_acc[p.cout + cout0 + c0 + lane], s1[0]);
+          }
+        }
         if (valid) {
 #pragma unroll
           for (int j = 0; j < 32; j += 8) {
-            if (cout0 + c0 + j < p.cout) {
-              uint4 o;
-              __nv_bfloat162 b0 = __floats2bfloat162_rn(__uint_as_float(v[j + 0]), __uint_as_float(v[j + 1]));
-              __nv_bfloat162 b1 = __floats2bfloat162_rn(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-              __nv_bfloat162 b2 = __floats2bfloat162_rn(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5]));
-              __nv_bfloat162 b3 = __floats2bfloat162_rn(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7]));
-              o.x = *reinterpret_cast<uint32_t*>(&b0); o.y = *reinterpret_cast<uint32_t*>(&b1);
-              o.z = *reinterpret_cast<uint32_t*>(&b2); o.w = *reinterpret_cast<uint32_t*>(&b3);
-              *reinterpret_cast<uint4*>(orow + c0 + j) = o;
-            }
+            if (cout0 + c0 + j < p.cout)
+              *reinterpret_cast<uint4*>(orow + c0 + j) = make_uint4(pk[j / 2], pk[j / 2 + 1], pk[j / 2 + 2], pk[j / 2 + 3]);
           }
         }
       }
@@ -286,6 +348,15 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[buf]);
+    }
+    if (EPI != 0) {
+      // the four epilogue warps (128 threads) flush the CTA's channel sums: one double atomic per channel and quantity
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int c = threadIdx.x - 64; c < p.cout; c += 128) {
+        const float a0 = ch_acc[c], a1 = ch_acc[p.cout + c];
+        if (a0 != 0.f) atomicAdd(p.sums + c, (double)a0);
+        if (a1 != 0.f) atomicAdd(p.sums + p.cout + c, (double)a1 * (EPI == 2 ? (double)ch_coef[c].w : 1.0));
+      }
     }
   }
   tcgen05_fence_before();
@@ -334,28 +405,41 @@ static bool nhwc_dense_bf16(const b200gan_view* v) {
          v->sn == (int64_t)v->h * v->w * v->c && (reinterpret_cast<uintptr_t>(v->ptr) & 15) == 0;
 }
 
-template <int BN, int KC, int STAGES>
-static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcConvParams& p, dim3 grid, cudaStream_t st) {
+template <int BN, int KC, int STAGES, int EPI>
+static int launch_tc_epi(const CUtensorMap& ma, const CUtensorMap& mb, const TcConvParams& p, dim3 grid, cudaStream_t st) {
   using S = TcSmem<BN, KC, STAGES>;
-  static bool configured = false;
-  if (!configured) {
-    B200_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, KC, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
-    configured = true;
+  // channel accumulators / coefficients live behind the barrier block (EPI != 0), sized by the layer's channel count
+  const int smem = S::TOTAL + (EPI == 0 ? 0 : p.cout * 8 + (EPI == 2 ? p.cout * 16 : 0) + 16);
+  static int configured = 0;
+  if (configured < smem) {
+    B200_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, KC, STAGES, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = smem;
   }
-  conv_gemm_tc_kernel<BN, KC, STAGES><<<grid, 192, S::TOTAL, st>>>(ma, mb, p);
+  conv_gemm_tc_kernel<BN, KC, STAGES, EPI><<<grid, 192, smem, st>>>(ma, mb, p);
   B200_LAUNCH_CHECK("conv_gemm_tc_kernel");
   return 0;
+}
+
+template <int BN, int KC, int STAGES>
+static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcConvParams& p, int epi, dim3 grid, cudaStream_t st) {
+  if (epi == 1) return launch_tc_epi<BN, KC, STAGES, 1>(ma, mb, p, grid, st);
+  if (epi == 2) return launch_tc_epi<BN, KC, STAGES, 2>(ma, mb, p, grid, st);
+  return launch_tc_epi<BN, KC, STAGES, 0>(ma, mb, p, grid, st);
 }
 
 // `in`: the gathered operand (NHWC bf16 dense), `out`: result (NHWC bf16 dense), up=false: DOWN geometry
 // (in is the fine side), up=true: UP geometry (in is the coarse side).  wpacked: see b200gan_pack_conv_weight.
 static int tc_conv_common(const b200gan_conv* cv, const b200gan_view* in, const void* wpacked, const b200gan_view* out, bool up,
-                          cudaStream_t st) {
+                          const TcEpi& epi, cudaStream_t st) {
   if (cv->k != 4 || cv->stride != 2 || cv->pad != 1) return 1;
   if (!wpacked) return 1;
   if (!nhwc_dense_bf16(in) || !nhwc_dense_bf16(out)) return 1;
   const int cin = in->c, cout = out->c;
   if (cin % 32 != 0 || cout % 32 != 0) return 1;
+  if (epi.mode != 0 && cout > 1024) return 1;
+  if (epi.mode == 2 && (!nhwc_dense_bf16(epi.prev_y) || epi.prev_y->n != out->n || epi.prev_y->h != out->h || epi.prev_y->w != out->w ||
+                        epi.prev_y->c != out->c))
+    return 1;
   const int KC = cin % 64 == 0 ? 64 : 32;
   const int BN = cout % 128 == 0 ? 128 : (cout % 64 == 0 ? 64 : 32);
   EncodeTiledFn enc = get_encode();
@@ -385,6 +469,15 @@ static int tc_conv_common(const b200gan_conv* cv, const b200gan_view* in, const 
   p.QH = QH; p.QW = QW; p.NB = NB;
   p.out = reinterpret_cast<__nv_bfloat16*>(out->ptr);
   p.o_sn = out->sn; p.o_sh = out->sh; p.o_sw = out->sw; p.o_mul = up ? 2 : 1; p.cout = cout;
+  if (epi.mode != 0) {
+    p.sums = epi.sums;
+    B200_CUDA(cudaMemsetAsync(epi.sums, 0, sizeof(double) * 2 * cout, st));
+    if (epi.mode == 2) {
+      p.prev_y = reinterpret_cast<const __nv_bfloat16*>(epi.prev_y->ptr);
+      p.prev_scale = epi.scale; p.prev_shift = epi.shift; p.prev_mean = epi.mean; p.prev_invstd = epi.invstd;
+      p.prev_neg = epi.act == B200GAN_ACT_RELU ? 0.f : (epi.act == B200GAN_ACT_LRELU ? epi.slope : 1.f);
+    }
+  }
 
   CUtensorMap ma, mb;
   {
@@ -415,21 +508,26 @@ static int tc_conv_common(const b200gan_conv* cv, const b200gan_view* in, const 
   // persistent: two CTAs per SM (every configuration below fits 2 x (smem, 2*BN TMEM columns) per SM)
   const int ctas = p.num_tiles < 2 * kNumSMs ? p.num_tiles : 2 * kNumSMs;
   dim3 grid((unsigned)ctas, 1, 1);
+  const int e = epi.mode;
   if (KC == 64) {
-    if (BN == 128) return launch_tc<128, 64, 3>(ma, mb, p, grid, st);   // 3 x 32 KB
-    if (BN == 64) return launch_tc<64, 64, 4>(ma, mb, p, grid, st);     // 4 x 24 KB
-    return launch_tc<32, 64, 5>(ma, mb, p, grid, st);                   // 5 x 20 KB
+    if (BN == 128) return launch_tc<128, 64, 3>(ma, mb, p, e, grid, st);   // 3 x 32 KB
+    if (BN == 64) return launch_tc<64, 64, 4>(ma, mb, p, e, grid, st);     // 4 x 24 KB
+    return launch_tc<32, 64, 5>(ma, mb, p, e, grid, st);                   // 5 x 20 KB
   }
-  if (BN == 128) return launch_tc<128, 32, 6>(ma, mb, p, grid, st);     // 6 x 16 KB
-  if (BN == 64) return launch_tc<64, 32, 8>(ma, mb, p, grid, st);       // 8 x 12 KB
-  return launch_tc<32, 32, 8>(ma, mb, p, grid, st);                     // 8 x 10 KB
+  if (BN == 128) return launch_tc<128, 32, 6>(ma, mb, p, e, grid, st);     // 6 x 16 KB
+  if (BN == 64) return launch_tc<64, 32, 8>(ma, mb, p, e, grid, st);       // 8 x 12 KB
+  return launch_tc<32, 32, 8>(ma, mb, p, e, grid, st);                     // 8 x 10 KB
 }
 
-int tc_conv_fprop(const b200gan_conv* cv, const b200gan_view* x, const void* wpacked, const b200gan_view* y, cudaStream_t st) {
-  return tc_conv_common(cv, x, wpacked, y, /*up=*/false, st);
+// `epi` describes an optional epilogue fusion (mode 0: none).  Both return 0 when the kernel ran (fusion included),
+// 1 when the problem does not qualify for the tensor-core path.
+int tc_conv_fprop(const b200gan_conv* cv, const b200gan_view* x, const void* wpacked, const b200gan_view* y, const TcEpi& epi,
+                  cudaStream_t st) {
+  return tc_conv_common(cv, x, wpacked, y, /*up=*/false, epi, st);
 }
-int tc_conv_dgrad(const b200gan_conv* cv, const b200gan_view* dy, const void* wpacked, const b200gan_view* dx, cudaStream_t st) {
-  return tc_conv_common(cv, dy, wpacked, dx, /*up=*/true, st);
+int tc_conv_dgrad(const b200gan_conv* cv, const b200gan_view* dy, const void* wpacked, const b200gan_view* dx, const TcEpi& epi,
+                  cudaStream_t st) {
+  return tc_conv_common(cv, dy, wpacked, dx, /*up=*/true, epi, st);
 }
 
 // ---------------------------------------------------------------------------------------------------

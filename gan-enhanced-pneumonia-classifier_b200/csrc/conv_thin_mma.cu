@@ -1,0 +1,445 @@
+// The image-side layers of the DCGAN: D0 = Conv2d(nc->32, k4 s2 p1) + LeakyReLU (dcgan.py:65-66) and
+// G5 = ConvTranspose2d(32->nc, k4 s2 p1) + Tanh (dcgan.py:46-47), nc in {1,3}, forward, input gradient and weight
+// gradient.  They move the largest activation of each network (N x 112 x 112 x 32) against a 1- or 3-channel image:
+// ~14 FLOP per byte, far below the B200 ridge, so the design goal is one pass over HBM per operand:
+//   * a CTA stages a band of image rows (any dtype / strides: the reference's NCHW fp32 tensors are read in place)
+//     and/or of 32-channel rows in shared memory once, zero padding included, and every tap re-reads shared memory;
+//   * the arithmetic runs on warp-level tensor-core MMAs (mma.sync m16n8k16, bf16 x bf16 -> fp32): with K = 16 taps
+//     (down / wgrad) or N = 4 parity classes (up) these GEMMs are far too thin for a 128-row tcgen05 tile, and the
+//     legacy MMA path is already >10x faster than the HBM floor here;
+//   * the activation around the convolution is fused: LeakyReLU / Tanh on the way out, and the activation BACKWARD
+//     (gradient x act'(saved output)) while the gradient operand is staged, so no elementwise pass touches these tensors.
+// Conv geometry names: fine = (N, 2H, 2W, nc) image side, coarse = (N, H, W, 32) dense bf16 NHWC, w = (32, nc, 4, 4) fp32.
+#include "common.cuh"
+
+namespace b200gan {
+
+namespace {
+
+struct ThinArgs {
+  View fine, fine_ref;                 // fine_ref.ptr == nullptr: no transform on the fine operand
+  const __nv_bfloat16* coarse;         // gathered coarse operand (up, wgrad)
+  const __nv_bfloat16* coarse_ref;     // nullptr: no transform on the coarse operand
+  __nv_bfloat16* coarse_out;           // result of down
+  const float* w;
+  float* dw;
+  int N, H, W;                         // coarse extents
+  int R, tiles_per_img, num_tiles;     // coarse rows per tile
+  int fine_act, coarse_act, out_act;   // b200gan_act: derivative applied to the staged operand / activation of the result
+  float slope;
+  int fine_vec, ref_vec;               // 4-wide vector loads along W are legal for fine / fine_ref
+};
+
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* smem_row) {
+  const uint32_t addr = (uint32_t)__cvta_generic_to_shared(smem_row);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* smem_row) {
+  const uint32_t addr = (uint32_t)__cvta_generic_to_shared(smem_row);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 b = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&b);
+}
+
+// four elements consecutive along W of a strided view, runtime dtype
+__device__ __forceinline__ void load4_rt(const View& v, int64_t off, int vec, float (&o)[4]) {
+  if (v.dtype == B200GAN_F32) {
+    const float* p = reinterpret_cast<const float*>(v.ptr) + off;
+    if (vec) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+      o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[e] = __ldg(p + e * v.sw);
+    }
+  } else {
+    const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(v.ptr) + off;
+    if (vec) {
+      const uint2 t = __ldg(reinterpret_cast<const uint2*>(p));
+      o[0] = __uint_as_float(t.x << 16); o[1] = __uint_as_float(t.x & 0xffff0000u);
+      o[2] = __uint_as_float(t.y << 16); o[3] = __uint_as_float(t.y & 0xffff0000u);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[e] = __bfloat162float(p[e * v.sw]);
+    }
+  }
+}
+
+// Stage fine rows [ih0, ih0+rows) of image n as bf16: S[(ci*rows + row)*pitch + s], s = iw + 1 in [0, IW+1]; s = 0 and
+// s = IW+1 (iw = -1, IW) and rows outside the image are the zero padding of the convolution.  IW % 4 == 0.
+template <int NC>
+__device__ __forceinline__ void stage_fine(__nv_bfloat16* S, int pitch, int rows, const ThinArgs& a, int n, int ih0) {
+  const int IH = 2 * a.H, IW = 2 * a.W, IW4 = IW >> 2;
+  const int total = NC * rows * IW4;
+  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+    const int j = idx % IW4;
+    const int t = idx / IW4;
+    const int row = t % rows, ci = t / rows;
+    const int ih = ih0 + row;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if ((unsigned)ih < (unsigned)IH) {
+      load4_rt(a.fine, (int64_t)n * a.fine.sn + (int64_t)ih * a.fine.sh + (int64_t)(4 * j) * a.fine.sw + (int64_t)ci * a.fine.sc, a.fine_vec, v);
+      if (a.fine_ref.ptr) {
+        float r[4];
+        load4_rt(a.fine_ref, (int64_t)n * a.fine_ref.sn + (int64_t)ih * a.fine_ref.sh + (int64_t)(4 * j) * a.fine_ref.sw + (int64_t)ci * a.fine_ref.sc,
+                 a.ref_vec, r);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[e] *= act_grad_from_output(r[e], a.fine_act, a.slope);
+      }
+    }
+    __nv_bfloat16* d = S + (ci * rows + row) * pitch + 4 * j + 1;      // odd index: [1] [2,3] [4]
+    d[0] = __float2bfloat16_rn(v[0]);
+    *reinterpret_cast<uint32_t*>(d + 1) = pack_bf16x2(v[1], v[2]);
+    d[3] = __float2bfloat16_rn(v[3]);
+  }
+  for (int idx = threadIdx.x; idx < NC * rows * 2; idx += blockDim.x)
+    S[(idx >> 1) * pitch + ((idx & 1) ? IW + 1 : 0)] = __float2bfloat16_rn(0.f);
+}
+
+constexpr int CP = 40;   // bf16 elements per staged coarse pixel: 32 channels + 8 pad (80 B pitch: conflict-free ldmatrix)
+
+// Stage coarse rows [q0, q0+rows) x cols [c0, c0+cols) of image n (zeros outside the image) as S[(row*cols + col)*CP + ch]
+__device__ __forceinline__ void stage_coarse(__nv_bfloat16* S, int rows, int cols, const ThinArgs& a, int n, int q0, int c0) {
+  const int total = rows * cols * 4;
+  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+    const int chunk = idx & 3, pix = idx >> 2;
+    const int col = pix % cols, row = pix / cols;
+    const int q = q0 + row, r = c0 + col;
+    uint4 val = make_uint4(0u, 0u, 0u, 0u);
+    if ((unsigned)q < (unsigned)a.H && (unsigned)r < (unsigned)a.W) {
+      const int64_t off = (((int64_t)n * a.H + q) * a.W + r) * 32 + chunk * 8;
+      val = __ldg(reinterpret_cast<const uint4*>(a.coarse + off));
+      if (a.coarse_ref) {
+        const uint4 rv = __ldg(reinterpret_cast<const uint4*>(a.coarse_ref + off));
+        float d[8], f[8];
+        unpack8(val, d);
+        unpack8(rv, f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) d[e] *= act_grad_from_output(f[e], a.coarse_act, a.slope);
+        val = pack8(d);
+      }
+    }
+    *reinterpret_cast<uint4*>(S + pix * CP + chunk * 8) = val;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// DOWN: coarse[n,oh,ow,:] = act( sum_{kh,kw,ci} fine[n,2oh-1+kh,2ow-1+kw,ci] * w[:,ci,kh,kw] )
+// GEMM per 16 consecutive ow: M = 16 pixels, K = 16 taps (one k-step per input channel), N = 32 channels.
+// MMA column n = 8j + g of n-tile j is mapped to channel 8*(g>>1) + 2j + (g&1), so that lane (g,t) ends up with the
+// eight consecutive channels 8t..8t+7 of its pixel: one 16-byte store per pixel row, fully coalesced across the warp.
+// ---------------------------------------------------------------------------------------------------
+template <int NC>
+__global__ void __launch_bounds__(256) thin_down_mma_kernel(const ThinArgs a) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  __nv_bfloat16* S = reinterpret_cast<__nv_bfloat16*>(smem_raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int rows = 2 * a.R + 2, pitch = 2 * a.W + 2;
+  uint32_t bw[NC][4][2];
+#pragma unroll
+  for (int ci = 0; ci < NC; ++ci)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int ch = 8 * (g >> 1) + 2 * j + (g & 1);
+      const float* wp = a.w + (ch * NC + ci) * 16;
+      bw[ci][j][0] = pack_bf16x2(__ldg(wp + 2 * t), __ldg(wp + 2 * t + 1));
+      bw[ci][j][1] = pack_bf16x2(__ldg(wp + 2 * t + 8), __ldg(wp + 2 * t + 9));
+    }
+  const int WB = a.W >> 4, mtiles = a.R * WB;
+  const int kh_lo = t >> 1, kw0 = (t & 1) * 2;
+  for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+    const int n = tile / a.tiles_per_img, oh0 = (tile - n * a.tiles_per_img) * a.R;
+    __syncthreads();                       // previous tile fully consumed
+    stage_fine<NC>(S, pitch, rows, a, n, 2 * oh0 - 1);
+    __syncthreads();
+    for (int mt = warp; mt < mtiles; mt += 8) {
+      const int rr = mt / WB, c = mt - rr * WB;
+      const int oh = oh0 + rr;
+      if (oh >= a.H) break;
+      float acc[4][4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
+      const int ow = 16 * c + g;
+#pragma unroll
+      for (int ci = 0; ci < NC; ++ci) {
+        const __nv_bfloat16* base = S + (ci * rows + 2 * rr + kh_lo) * pitch + 2 * ow + kw0;
+        uint32_t af[4];
+        af[0] = *reinterpret_cast<const uint32_t*>(base);
+        af[1] = *reinterpret_cast<const uint32_t*>(base + 16);
+        af[2] = *reinterpret_cast<const uint32_t*>(base + 2 * pitch);
+        af[3] = *reinterpret_cast<const uint32_t*>(base + 2 * pitch + 16);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) mma_bf16_16816(acc[j], af, bw[ci][j][0], bw[ci][j][1]);
+      }
+      if (a.out_act == B200GAN_ACT_LRELU) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) acc[j][e] = acc[j][e] > 0.f ? acc[j][e] : acc[j][e] * a.slope;
+      } else if (a.out_act == B200GAN_ACT_RELU) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) acc[j][e] = fmaxf(acc[j][e], 0.f);
+      }
+      __nv_bfloat16* o = a.coarse_out + (((int64_t)n * a.H + oh) * a.W + ow) * 32 + 8 * t;
+      uint4 lo, hi;
+      lo.x = pack_bf16x2(acc[0][0], acc[0][1]); lo.y = pack_bf16x2(acc[1][0], acc[1][1]);
+      lo.z = pack_bf16x2(acc[2][0], acc[2][1]); lo.w = pack_bf16x2(acc[3][0], acc[3][1]);
+      hi.x = pack_bf16x2(acc[0][2], acc[0][3]); hi.y = pack_bf16x2(acc[1][2], acc[1][3]);
+      hi.z = pack_bf16x2(acc[2][2], acc[2][3]); hi.w = pack_bf16x2(acc[3][2], acc[3][3]);
+      *reinterpret_cast<uint4*>(o) = lo;
+      *reinterpret_cast<uint4*>(o + 8 * 32) = hi;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// UP: fine[n,2q+py,2r+px,ci] = act( sum_{co} sum_{di,dj} coarse[n,q+di,r+dj,co] * w[co,ci,py+1-2di,px+1-2dj] )
+// GEMM per 16 consecutive r: M = 16 coarse positions, K = 9 neighbours x 32 channels (18 k-steps), N = 4 parity classes x nc
+// (zero weights where a neighbour does not reach a class: the MMA work is free, the 32-channel tensor is read once).
+// ---------------------------------------------------------------------------------------------------
+template <int NC>
+__global__ void __launch_bounds__(256) thin_up_mma_kernel(const ThinArgs a) {
+  constexpr int NT = (4 * NC + 7) / 8;
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  uint2* Bf = reinterpret_cast<uint2*>(smem_raw);                                 // [18*NT][32] fragment-ordered weights
+  __nv_bfloat16* S = reinterpret_cast<__nv_bfloat16*>(smem_raw + 18 * NT * 32 * 8);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  for (int idx = threadIdx.x; idx < 18 * NT * 32; idx += blockDim.x) {
+    const int ln = idx & 31, f = idx >> 5, nt = f % NT, ks = f / NT, nbr = ks >> 1, h = ks & 1;
+    const int gg = ln >> 2, tt = ln & 3, nn = 8 * nt + gg;
+    float wv[4] = {0.f, 0.f, 0.f, 0.f};
+    if (nn < 4 * NC) {
+      const int cls = nn / NC, ci = nn - cls * NC, py = cls >> 1, px = cls & 1;
+      const int di = nbr / 3 - 1, dj = nbr % 3 - 1, kh = py + 1 - 2 * di, kw = px + 1 - 2 * dj;
+      if (kh >= 0 && kh < 4 && kw >= 0 && kw < 4) {
+        const int kk[4] = {2 * tt, 2 * tt + 1, 2 * tt + 8, 2 * tt + 9};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) wv[e] = __ldg(a.w + ((16 * h + kk[e]) * NC + ci) * 16 + kh * 4 + kw);
+      }
+    }
+    Bf[idx] = make_uint2(pack_bf16x2(wv[0], wv[1]), pack_bf16x2(wv[2], wv[3]));
+  }
+  const int cols = a.W + 2, WB = a.W >> 4, mtiles = a.R * WB;
+  const int prow = (lane & 7) + 8 * ((lane >> 3) & 1), koff = 8 * (lane >> 4);
+  const bool pair_store = NC == 1 && a.fine_vec;
+  for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+    const int n = tile / a.tiles_per_img, q0 = (tile - n * a.tiles_per_img) * a.R;
+    __syncthreads();
+    stage_coarse(S, a.R + 2, cols, a, n, q0 - 1, -1);
+    __syncthreads();
+    for (int mt = warp; mt < mtiles; mt += 8) {
+      const int rr = mt / WB, c = mt - rr * WB;
+      const int q = q0 + rr;
+      if (q >= a.H) break;
+      float acc[NT][4];
+#pragma unroll
+      for (int j = 0; j < NT; ++j)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
+#pragma unroll
+      for (int nbr = 0; nbr < 9; ++nbr) {
+        const int di = nbr / 3 - 1, dj = nbr % 3 - 1;
+        const __nv_bfloat16* base = S + ((rr + 1 + di) * cols + 16 * c + prow + 1 + dj) * CP + koff;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t af[4];
+          ldmatrix_x4(af, base + 16 * h);
+#pragma unroll
+          for (int j = 0; j < NT; ++j) {
+            const uint2 b = Bf[((nbr * 2 + h) * NT + j) * 32 + lane];
+            mma_bf16_16816(acc[j], af, b.x, b.y);
+          }
+        }
+      }
+      // lane (g,t): rows (coarse positions) r = 16c+g and +8; columns n = 8j + 2t + e -> (class, ci)
+#pragma unroll
+      for (int j = 0; j < NT; ++j)
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int r = 16 * c + g + 8 * half;
+          float v0 = acc[j][2 * half], v1 = acc[j][2 * half + 1];
+          if (a.out_act == B200GAN_ACT_TANH) { v0 = tanhf(v0); v1 = tanhf(v1); }
+          const int n0 = 8 * j + 2 * t;
+          if (pair_store) {
+            if (n0 < 4) {                                                  // n0 = 2*py, columns px = 0,1 are adjacent pixels
+              const int64_t off = (int64_t)n * a.fine.sn + (int64_t)(2 * q + (n0 >> 1)) * a.fine.sh + 2 * r;
+              if (a.fine.dtype == B200GAN_F32) *reinterpret_cast<float2*>(reinterpret_cast<float*>(a.fine.ptr) + off) = make_float2(v0, v1);
+              else *reinterpret_cast<uint32_t*>(reinterpret_cast<__nv_bfloat16*>(a.fine.ptr) + off) = pack_bf16x2(v0, v1);
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int nn = n0 + e;
+              if (nn < 4 * NC) {
+                const int cls = nn / NC, ci = nn - cls * NC;
+                const int64_t off = (int64_t)n * a.fine.sn + (int64_t)(2 * q + (cls >> 1)) * a.fine.sh + (int64_t)(2 * r + (cls & 1)) * a.fine.sw +
+                                    (int64_t)ci * a.fine.sc;
+                const float v = e ? v1 : v0;
+                if (a.fine.dtype == B200GAN_F32) reinterpret_cast<float*>(a.fine.ptr)[off] = v;
+                else reinterpret_cast<__nv_bfloat16*>(a.fine.ptr)[off] = __float2bfloat16_rn(v);
+              }
+            }
+          }
+        }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// WGRAD: dw[co,ci,kh,kw] += sum_{n,oh,ow} coarse[n,oh,ow,co] * fine[n,2oh-1+kh,2ow-1+kw,ci]
+// GEMM: M = 32 channels (two m-tiles, A = coarse^T through ldmatrix.trans), N = 16 taps per input channel (two n-tiles),
+// K = pixels, 16 consecutive ow per k-step.  Each warp keeps its accumulators over the whole kernel; one shared-memory and
+// one global fp32 atomic reduction per CTA at the end.
+// ---------------------------------------------------------------------------------------------------
+template <int NC>
+__global__ void __launch_bounds__(256) thin_wgrad_mma_kernel(const ThinArgs a) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  float* red = reinterpret_cast<float*>(smem_raw);                                  // [512*NC]
+  __nv_bfloat16* Sc = reinterpret_cast<__nv_bfloat16*>(smem_raw + 512 * NC * 4);    // [R][W][CP]
+  const int rows = 2 * a.R + 2, pitch = 2 * a.W + 2;
+  __nv_bfloat16* Sf = Sc + a.R * a.W * CP;                                          // [NC][rows][pitch]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  for (int i = threadIdx.x; i < 512 * NC; i += blockDim.x) red[i] = 0.f;
+  float acc[2][2 * NC][4];
+#pragma unroll
+  for (int m = 0; m < 2; ++m)
+#pragma unroll
+    for (int j = 0; j < 2 * NC; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[m][j][e] = 0.f;
+  const int WB = a.W >> 4, ksteps = a.R * WB;
+  const int px_l = (lane & 7) + 8 * (lane >> 4), co_l = 8 * ((lane >> 3) & 1);
+  const int kw = g & 3, khg = g >> 2;
+  for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+    const int n = tile / a.tiles_per_img, oh0 = (tile - n * a.tiles_per_img) * a.R;
+    __syncthreads();
+    stage_coarse(Sc, a.R, a.W, a, n, oh0, 0);
+    stage_fine<NC>(Sf, pitch, rows, a, n, 2 * oh0 - 1);
+    __syncthreads();
+    for (int ks = warp; ks < ksteps; ks += 8) {
+      const int rr = ks / WB, c = ks - rr * WB;
+      uint32_t af[2][4];
+#pragma unroll
+      for (int m = 0; m < 2; ++m) ldmatrix_x4_trans(af[m], Sc + (rr * a.W + 16 * c + px_l) * CP + 16 * m + co_l);
+#pragma unroll
+      for (int ci = 0; ci < NC; ++ci)
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          const unsigned short* p = reinterpret_cast<const unsigned short*>(Sf) + (ci * rows + 2 * rr + 2 * hf + khg) * pitch + 2 * (16 * c + 2 * t) + kw;
+          const uint32_t b0 = (uint32_t)p[0] | ((uint32_t)p[2] << 16);
+          const uint32_t b1 = (uint32_t)p[16] | ((uint32_t)p[18] << 16);
+#pragma unroll
+          for (int m = 0; m < 2; ++m) mma_bf16_16816(acc[m][ci * 2 + hf], af[m], b0, b1);
+        }
+    }
+  }
+  // acc[m][ci*2+hf][e]: co = 16m + g + 8*(e>>1), tap = 8hf + 2t + (e&1)
+#pragma unroll
+  for (int m = 0; m < 2; ++m)
+#pragma unroll
+    for (int j = 0; j < 2 * NC; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int co = 16 * m + g + 8 * (e >> 1), ci = j >> 1, tap = 8 * (j & 1) + 2 * t + (e & 1);
+        atomicAdd(&red[(co * NC + ci) * 16 + tap], acc[m][j][e]);
+      }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 512 * NC; i += blockDim.x) atomicAdd(a.dw + i, red[i]);
+}
+
+bool dense_bf16_32(const b200gan_view* v) {
+  return v->dtype == B200GAN_BF16 && v->c == 32 && v->sc == 1 && v->sw == 32 && v->sh == (int64_t)v->w * 32 &&
+         v->sn == (int64_t)v->h * v->w * 32 && (reinterpret_cast<uintptr_t>(v->ptr) & 15) == 0;
+}
+
+// 4-wide loads along W: unit W stride, every row start a multiple of 4 elements, base pointer aligned to 4 elements
+int vec4_ok(const b200gan_view* v) {
+  const uintptr_t bytes = v->dtype == B200GAN_F32 ? 16 : 8;
+  return v->sw == 1 && v->sn % 4 == 0 && v->sh % 4 == 0 && v->sc % 4 == 0 && (reinterpret_cast<uintptr_t>(v->ptr) % bytes) == 0;
+}
+
+// returns false when the problem is not of the thin shape
+bool thin_setup(ThinArgs* a, const b200gan_view* fine, const b200gan_view* fine_ref, int fine_act, const b200gan_view* coarse,
+                const b200gan_view* coarse_ref, int coarse_act, float slope) {
+  if (!dense_bf16_32(coarse) || (fine->c != 1 && fine->c != 3)) return false;
+  if (coarse->w % 16 != 0 || coarse->w > 128 || fine->h != 2 * coarse->h || fine->w != 2 * coarse->w || fine->n != coarse->n) return false;
+  if (coarse_ref && (!dense_bf16_32(coarse_ref) || coarse_ref->n != coarse->n || coarse_ref->h != coarse->h || coarse_ref->w != coarse->w)) return false;
+  if (fine_ref && (fine_ref->n != fine->n || fine_ref->h != fine->h || fine_ref->w != fine->w || fine_ref->c != fine->c)) return false;
+  a->fine = to_view(fine);
+  if (fine_ref) a->fine_ref = to_view(fine_ref); else a->fine_ref.ptr = nullptr;
+  a->coarse = reinterpret_cast<const __nv_bfloat16*>(coarse->ptr);
+  a->coarse_out = reinterpret_cast<__nv_bfloat16*>(coarse->ptr);
+  a->coarse_ref = coarse_ref ? reinterpret_cast<const __nv_bfloat16*>(coarse_ref->ptr) : nullptr;
+  a->N = coarse->n; a->H = coarse->h; a->W = coarse->w;
+  a->R = coarse->h < 8 ? coarse->h : 8;
+  a->tiles_per_img = (a->H + a->R - 1) / a->R;
+  a->num_tiles = a->N * a->tiles_per_img;
+  a->fine_act = fine_act; a->coarse_act = coarse_act; a->out_act = B200GAN_ACT_NONE; a->slope = slope;
+  a->fine_vec = vec4_ok(fine);
+  a->ref_vec = fine_ref ? vec4_ok(fine_ref) : 0;
+  return true;
+}
+
+template <typename K>
+int launch_thin(K kernel, const ThinArgs& a, size_t smem, int ctas_per_sm, cudaStream_t st, const char* name) {
+  B200_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int grid = ctas_per_sm * kNumSMs;
+  if (grid > a.num_tiles) grid = a.num_tiles;
+  kernel<<<grid, 256, smem, st>>>(a);
+  B200_LAUNCH_CHECK(name);
+  return 0;
+}
+
+}  // namespace
+
+// Each wrapper returns 1 when the problem is not of its shape (the dispatcher then uses the generic kernels).
+
+// fine (gathered; optionally multiplied by act'(fine_ref)) -> coarse = out_act(conv)
+int thin_down(const b200gan_view* fine, const b200gan_view* fine_ref, int fine_act, const float* w, const b200gan_view* coarse, int out_act,
+              float slope, cudaStream_t st) {
+  ThinArgs a{};
+  if (out_act != B200GAN_ACT_NONE && out_act != B200GAN_ACT_LRELU && out_act != B200GAN_ACT_RELU) return 1;
+  if (!thin_setup(&a, fine, fine_ref, fine_act, coarse, nullptr, B200GAN_ACT_NONE, slope)) return 1;
+  a.w = w; a.out_act = out_act;
+  const size_t smem = (size_t)fine->c * (2 * a.R + 2) * (2 * a.W + 2) * 2;
+  if (fine->c == 1) return launch_thin(thin_down_mma_kernel<1>, a, smem, 6, st, "thin_down_mma_kernel");
+  return launch_thin(thin_down_mma_kernel<3>, a, smem, 4, st, "thin_down_mma_kernel");
+}
+
+// coarse (gathered; optionally multiplied by act'(coarse_ref)) -> fine = out_act(transposed conv)
+int thin_up(const b200gan_view* coarse, const b200gan_view* coarse_ref, int coarse_act, float slope, const float* w, const b200gan_view* fine,
+            int out_act, cudaStream_t st) {
+  ThinArgs a{};
+  if (out_act != B200GAN_ACT_NONE && out_act != B200GAN_ACT_TANH) return 1;
+  if (!thin_setup(&a, fine, nullptr, B200GAN_ACT_NONE, coarse, coarse_ref, coarse_act, slope)) return 1;
+  a.w = w; a.out_act = out_act;
+  const int NT = (4 * fine->c + 7) / 8;
+  const size_t smem = (size_t)18 * NT * 32 * 8 + (size_t)(a.R + 2) * (a.W + 2) * CP * 2;
+  if (fine->c == 1) return launch_thin(thin_up_mma_kernel<1>, a, smem, 2, st, "thin_up_mma_kernel");
+  return launch_thin(thin_up_mma_kernel<3>, a, smem, 2, st, "thin_up_mma_kernel");
+}
+
+// dw (32, nc, 4, 4) fp32 += coarse^T x im2col(fine); either operand may carry the fused activation backward
+int thin_wgrad(const b200gan_view* fine, const b200gan_view* fine_ref, int fine_act, const b200gan_view* coarse, const b200gan_view* coarse_ref,
+               int coarse_act, float slope, float* dw, cudaStream_t st) {
+  ThinArgs a{};
+  if (!thin_setup(&a, fine, fine_ref, fine_act, coarse, coarse_ref, coarse_act, slope)) return 1;
+  a.dw = dw;
+  const size_t smem = (size_t)512 * fine->c * 4 + (size_t)a.R * a.W * CP * 2 + (size_t)fine->c * (2 * a.R + 2) * (2 * a.W + 2) * 2;
+  if (fine->c == 1) return launch_thin(thin_wgrad_mma_kernel<1>, a, smem, 2, st, "thin_wgrad_mma_kernel");
+  return launch_thin(thin_wgrad_mma_kernel<3>, a, smem, 2, st, "thin_wgrad_mma_kernel");
+}
+
+}  // namespace b200gan

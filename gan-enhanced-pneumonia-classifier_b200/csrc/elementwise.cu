@@ -558,6 +558,32 @@ int ew_bn_act_bwd_apply(const b200gan_view* da, const b200gan_view* y, const b20
 }
 
 // ------------------------------------------------------------------------------------------------
+// d *= act'(scale[c]*y + shift[c]) in place (the unfused form of the `prev_*` input-gradient epilogue, b200gan_fuse)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) act_bwd_inplace_kernel(View d, View y, const float* scale, const float* shift, int act, float slope) {
+  const int64_t total = (int64_t)y.n * y.h * y.w * y.c;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % y.c);
+    const int64_t pix = i / y.c;
+    float z = ld_as_float(reinterpret_cast<const T*>(y.ptr) + pix_offset(y, pix) + (int64_t)c * y.sc);
+    if (scale) z = fmaf(z, scale[c], shift[c]);
+    T* dp = reinterpret_cast<T*>(d.ptr) + pix_offset(d, pix) + (int64_t)c * d.sc;
+    st_from_float(dp, ld_as_float(dp) * act_grad(z, 0.f, act, slope));
+  }
+}
+
+int ew_act_bwd_inplace(const b200gan_view* d, const b200gan_view* y, const float* scale, const float* shift, int act, float slope,
+                       cudaStream_t st) {
+  B200_CHECK_ARG(d->dtype == y->dtype && d->n == y->n && d->h == y->h && d->w == y->w && d->c == y->c, "act_bwd_inplace: d and y differ");
+  const int64_t total = (int64_t)y->n * y->h * y->w * y->c;
+  if (y->dtype == B200GAN_F32) act_bwd_inplace_kernel<float><<<ew_blocks(total), 256, 0, st>>>(to_view(d), to_view(y), scale, shift, act, slope);
+  else act_bwd_inplace_kernel<__nv_bfloat16><<<ew_blocks(total), 256, 0, st>>>(to_view(d), to_view(y), scale, shift, act, slope);
+  B200_LAUNCH_CHECK("act_bwd_inplace");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Sigmoid + BCE(mean) against a constant target, forward and backward, one CTA (B <= a few thousand).
 // torch: loss_i = (t-1)*max(log1p(-p),-100) - t*max(log p,-100);  dL/dp = (p-t)/max((1-p)p,1e-12)/B
 // ------------------------------------------------------------------------------------------------

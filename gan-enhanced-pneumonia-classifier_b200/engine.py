@@ -119,7 +119,9 @@ def _check_f32(t, what):
 
 
 class LayerCtx:
-    __slots__ = ('x', 'y', 'a', 'scale', 'shift', 'mean', 'invstd', 'wp_down', 'wp_up')
+    """What the forward pass keeps per layer: input x, conv output y (BatchNorm layers only), activation output a,
+    BatchNorm coefficients, packed weights, and (filled during backward) the BatchNorm-backward sums."""
+    __slots__ = ('x', 'y', 'a', 'scale', 'shift', 'mean', 'invstd', 'wp_down', 'wp_up', 'bsums')
 
 
 class NetEngine:
@@ -128,7 +130,7 @@ class NetEngine:
     def __init__(self, specs: List[LayerSpec], transposed: bool, dtype: torch.dtype, algo: int = L.ALGO_AUTO):
         self.specs, self.transposed, self.dtype, self.algo = specs, transposed, dtype, algo
         self._conv = [L.Conv(sp.k, sp.stride, sp.pad, algo) for sp in specs]
-        self.launches = 0     # kernels launched through this engine (bench.py's gpu_launches claim)
+        self.launches = 0     # C-ABI calls that launch kernels, made through this engine (bench.py's gpu_launches claim)
 
     # -- thin wrappers over the C ABI --------------------------------------------------------------
     def _tc_layer(self, i):
@@ -136,6 +138,12 @@ class NetEngine:
         sp = self.specs[i]
         return (self.dtype == torch.bfloat16 and self.algo != L.ALGO_SIMT and sp.k == 4 and sp.stride == 2 and sp.pad == 1
                 and sp.cin % 32 == 0 and sp.cout % 32 == 0)
+
+    def _act_fused(self, i):
+        """Layers without BatchNorm whose activation rides on the convolution (b200gan_fuse.out_act / dy_act): the k4 s2 p1
+        image-side layers D0 (LeakyReLU) and G5 (Tanh)."""
+        sp = self.specs[i]
+        return sp.bn_idx is None and sp.k == 4 and sp.act in (L.ACT_LRELU, L.ACT_RELU, L.ACT_TANH)
 
     def _pack(self, i, w, st):
         """bf16 GEMM-operand repacks of the fp32 master weight: ('down' form, 'up' form), see b200gan_pack_conv_weight."""
@@ -149,20 +157,20 @@ class NetEngine:
         self.launches += 2
         return down, up
 
-    def _fprop(self, i, x: Act, w, y: Act, st, wp_down=None, wp_up=None):
+    def _fprop(self, i, x: Act, w, y: Act, st, wp_down=None, wp_up=None, fuse=None):
         # ConvTranspose2d forward is the 'up' geometry, Conv2d forward the 'down' geometry
         name, wp = ('b200gan_convT2d_fprop', wp_up) if self.transposed else ('b200gan_conv2d_fprop', wp_down)
-        L.call(name, C.byref(self._conv[i]), C.byref(x.v), L.ptr(w), L.ptr(wp), C.byref(y.v), st)
-        self.launches += 1 if (wp is not None or not self.transposed) else self.specs[i].stride ** 2
+        L.call(name, C.byref(self._conv[i]), C.byref(x.v), L.ptr(w), L.ptr(wp), C.byref(y.v), C.byref(fuse) if fuse is not None else None, st)
+        self.launches += 1
 
-    def _dgrad(self, i, dy: Act, w, dx: Act, st, wp_down=None, wp_up=None):
+    def _dgrad(self, i, dy: Act, w, dx: Act, st, wp_down=None, wp_up=None, fuse=None):
         name, wp = ('b200gan_convT2d_dgrad', wp_down) if self.transposed else ('b200gan_conv2d_dgrad', wp_up)
-        L.call(name, C.byref(self._conv[i]), C.byref(dy.v), L.ptr(w), L.ptr(wp), C.byref(dx.v), st)
-        self.launches += 1 if (wp is not None or self.transposed) else self.specs[i].stride ** 2
+        L.call(name, C.byref(self._conv[i]), C.byref(dy.v), L.ptr(w), L.ptr(wp), C.byref(dx.v), C.byref(fuse) if fuse is not None else None, st)
+        self.launches += 1
 
-    def _wgrad(self, i, x: Act, dy: Act, dw, st):
+    def _wgrad(self, i, x: Act, dy: Act, dw, st, fuse=None):
         name = 'b200gan_convT2d_wgrad' if self.transposed else 'b200gan_conv2d_wgrad'
-        L.call(name, C.byref(self._conv[i]), C.byref(x.v), C.byref(dy.v), L.ptr(dw), st)
+        L.call(name, C.byref(self._conv[i]), C.byref(x.v), C.byref(dy.v), L.ptr(dw), C.byref(fuse) if fuse is not None else None, st)
         self.launches += 1
 
     def out_hw(self, i, h, w):
@@ -189,44 +197,48 @@ class NetEngine:
             oh, ow = self.out_hw(i, cur.v.h, cur.v.w)
             last = i == nl - 1
             ydt = torch.float32 if (last and not self.transposed) else self.dtype      # D logits stay fp32
-            y = Act(torch.empty((cur.v.n, oh, ow, sp.cout), device=dev, dtype=ydt), nchw=False)
+            shape = (cur.v.n, oh, ow, sp.cout)
             wp_down, wp_up = self._pack(i, p.w, st)
-            self._fprop(i, cur, p.w, y, st, wp_down, wp_up)
             lc = LayerCtx() if save else None
             if save:
-                lc.x, lc.y = cur, y
-                lc.wp_down, lc.wp_up = wp_down, wp_up
-                lc.scale = lc.shift = lc.mean = lc.invstd = None
-            scale = shift = None
+                lc.x, lc.y, lc.wp_down, lc.wp_up = cur, None, wp_down, wp_up
+                lc.scale = lc.shift = lc.mean = lc.invstd = lc.bsums = None
             if sp.bn_idx is not None:
+                # conv (+ BatchNorm statistics in its epilogue) -> finalize -> normalise + activation
                 cch = sp.cout
+                y = Act(torch.empty(shape, device=dev, dtype=self.dtype), nchw=False)
                 scale = torch.empty(cch, device=dev, dtype=torch.float32)
                 shift = torch.empty(cch, device=dev, dtype=torch.float32)
                 if training:
                     sums = torch.empty(2 * cch, device=dev, dtype=torch.float64)
                     mean = torch.empty(cch, device=dev, dtype=torch.float32)
                     invstd = torch.empty(cch, device=dev, dtype=torch.float32)
-                    L.call('b200gan_bn_stats', C.byref(y.v), L.ptr(sums), st)
+                    self._fprop(i, cur, p.w, y, st, wp_down, wp_up, fuse=L.fuse(bn_sums=sums))
                     L.call('b200gan_bn_finalize', L.ptr(sums), cch, cur.v.n * oh * ow, L.ptr(p.gamma), L.ptr(p.beta),
                            L.ptr(p.rm), L.ptr(p.rv), L.ptr(p.nbt), BN_MOMENTUM, BN_EPS, L.ptr(scale), L.ptr(shift),
                            L.ptr(mean), L.ptr(invstd), st)
-                    self.launches += 2
                     if save:
                         lc.mean, lc.invstd = mean, invstd
                 else:
+                    self._fprop(i, cur, p.w, y, st, wp_down, wp_up)
                     L.call('b200gan_bn_eval_coeffs', cch, L.ptr(p.gamma), L.ptr(p.beta), L.ptr(p.rm), L.ptr(p.rv), BN_EPS,
                            L.ptr(scale), L.ptr(shift), st)
-                    self.launches += 1
-                if save:
-                    lc.scale, lc.shift = scale, shift
-            if last and not last_act:
-                a = y
-            else:
-                if last and out is not None:
-                    a = out
-                else:
-                    a = Act(torch.empty((cur.v.n, oh, ow, sp.cout), device=dev, dtype=ydt if last else self.dtype), nchw=False)
+                a = Act(torch.empty(shape, device=dev, dtype=self.dtype), nchw=False)
                 L.call('b200gan_bn_act_fwd', C.byref(y.v), L.ptr(scale), L.ptr(shift), sp.act, LRELU_SLOPE, C.byref(a.v), st)
+                self.launches += 2
+                if save:
+                    lc.y, lc.scale, lc.shift = y, scale, shift
+            elif last and not last_act:
+                a = Act(torch.empty(shape, device=dev, dtype=ydt), nchw=False)          # logits
+                self._fprop(i, cur, p.w, a, st, wp_down, wp_up)
+            elif self._act_fused(i):
+                a = out if (last and out is not None) else Act(torch.empty(shape, device=dev, dtype=ydt), nchw=False)
+                self._fprop(i, cur, p.w, a, st, wp_down, wp_up, fuse=L.fuse(out_act=sp.act, out_slope=LRELU_SLOPE))
+            else:
+                y = Act(torch.empty(shape, device=dev, dtype=ydt), nchw=False)
+                self._fprop(i, cur, p.w, y, st, wp_down, wp_up)
+                a = out if (last and out is not None) else Act(torch.empty(shape, device=dev, dtype=ydt), nchw=False)
+                L.call('b200gan_bn_act_fwd', C.byref(y.v), None, None, sp.act, LRELU_SLOPE, C.byref(a.v), st)
                 self.launches += 1
             if save:
                 lc.a = a
@@ -240,46 +252,55 @@ class NetEngine:
         """`dout`: gradient w.r.t. the final activation (or `dlogit`: w.r.t. the last conv output, when the
         loss kernel already applied Sigmoid').  `grads` is the flat list over `param_order()` of fp32 tensors
         that are ACCUMULATED into (autograd semantics); entries may be None to skip.  `dinput`, when given,
-        receives the gradient w.r.t. the network input."""
+        receives the gradient w.r.t. the network input.
+
+        Per layer, going down: the incoming gradient d is w.r.t. the layer's activation output.
+          * BatchNorm layers: the input-gradient convolution of the layer ABOVE already applied the activation backward and
+            accumulated the BatchNorm-backward sums in its epilogue (b200gan_fuse.prev_*), so d is dz; one pass finishes
+            native_batch_norm_backward in place (dy, dgamma, dbeta);
+          * D0 / G5 (no BatchNorm): the activation backward rides on the operand read of wgrad / dgrad (dy_act, dy_ref)."""
         st = L.stream_ptr()
         nl = len(self.specs)
         gi = len(grads)
         d = dout
         for i in reversed(range(nl)):
             sp, p, lc = self.specs[i], params[i], ctxs[i]
-            dev = lc.y.t.device
+            dev = lc.a.t.device
             nparam = 3 if sp.bn_idx is not None else 1
             gi -= nparam
+            fuse_kw = {}
             if i == nl - 1 and dlogit is not None:
                 dy = dlogit
+            elif sp.bn_idx is not None:
+                cnt = lc.y.v.n * lc.y.v.h * lc.y.v.w
+                dg = grads[gi + 1] if need_wgrad else None
+                db = grads[gi + 2] if need_wgrad else None
+                L.call('b200gan_bn_act_bwd_apply', C.byref(d.v), C.byref(lc.y.v), None, L.ptr(lc.scale), L.ptr(lc.shift),
+                       L.ptr(lc.mean), L.ptr(lc.invstd), L.ptr(p.gamma), L.ptr(lc.bsums), cnt, L.ACT_NONE, LRELU_SLOPE,
+                       C.byref(d.v), L.ptr(dg), L.ptr(db), st)
+                self.launches += 1
+                dy = d
+            elif self._act_fused(i):
+                dy = d
+                fuse_kw = dict(dy_act=sp.act, dy_slope=LRELU_SLOPE, dy_ref=lc.a.v)
             else:
-                dy = Act(torch.empty(lc.y.t.shape, device=dev, dtype=lc.y.t.dtype), nchw=False)   # D logits: fp32
-                need_a = sp.act in (L.ACT_TANH, L.ACT_SIGMOID)
-                # da, y, a must share a dtype: for tanh/sigmoid only `a` is read, so it stands in for y
-                yv = lc.a if need_a else lc.y
-                av = C.byref(lc.a.v) if need_a else None
-                if sp.bn_idx is not None:
-                    sums = torch.empty(2 * sp.cout, device=dev, dtype=torch.float64)
-                    cnt = lc.y.v.n * lc.y.v.h * lc.y.v.w
-                    L.call('b200gan_bn_act_bwd_reduce', C.byref(d.v), C.byref(yv.v), av, L.ptr(lc.scale), L.ptr(lc.shift),
-                           L.ptr(lc.mean), L.ptr(lc.invstd), sp.act, LRELU_SLOPE, L.ptr(sums), st)
-                    dg = grads[gi + 1] if need_wgrad else None
-                    db = grads[gi + 2] if need_wgrad else None
-                    L.call('b200gan_bn_act_bwd_apply', C.byref(d.v), C.byref(yv.v), av, L.ptr(lc.scale), L.ptr(lc.shift),
-                           L.ptr(lc.mean), L.ptr(lc.invstd), L.ptr(p.gamma), L.ptr(sums), cnt, sp.act, LRELU_SLOPE,
-                           C.byref(dy.v), L.ptr(dg), L.ptr(db), st)
-                    self.launches += 2
-                else:
-                    L.call('b200gan_bn_act_bwd_apply', C.byref(d.v), C.byref(yv.v), av, None, None, None, None, None, None, 0,
-                           sp.act, LRELU_SLOPE, C.byref(dy.v), None, None, st)
-                    self.launches += 1
+                # activation without BatchNorm and without a fused kernel (Sigmoid of the module-level Discriminator forward)
+                dy = Act(torch.empty(lc.a.t.shape, device=dev, dtype=lc.a.t.dtype), nchw=False)
+                L.call('b200gan_bn_act_bwd_apply', C.byref(d.v), C.byref(lc.a.v), C.byref(lc.a.v), None, None, None, None, None, None, 0,
+                       sp.act, LRELU_SLOPE, C.byref(dy.v), None, None, st)
+                self.launches += 1
             if need_wgrad and grads[gi] is not None:
-                self._wgrad(i, lc.x, dy, grads[gi], st)
+                self._wgrad(i, lc.x, dy, grads[gi], st, fuse=L.fuse(**fuse_kw) if fuse_kw else None)
             if i > 0:
+                below, lb = self.specs[i - 1], ctxs[i - 1]
+                if below.bn_idx is not None:
+                    lb.bsums = torch.empty(2 * below.cout, device=dev, dtype=torch.float64)
+                    fuse_kw.update(prev_act=below.act, prev_slope=LRELU_SLOPE, prev_y=lb.y.v, prev_scale=lb.scale, prev_shift=lb.shift,
+                                   prev_mean=lb.mean, prev_invstd=lb.invstd, prev_sums=lb.bsums)
                 d = Act(torch.empty(lc.x.t.shape, device=dev, dtype=self.dtype), nchw=False)
-                self._dgrad(i, dy, p.w, d, st, lc.wp_down, lc.wp_up)
+                self._dgrad(i, dy, p.w, d, st, lc.wp_down, lc.wp_up, fuse=L.fuse(**fuse_kw) if fuse_kw else None)
             elif dinput is not None:
-                self._dgrad(i, dy, p.w, dinput, st, lc.wp_down, lc.wp_up)
+                self._dgrad(i, dy, p.w, dinput, st, lc.wp_down, lc.wp_up, fuse=L.fuse(**fuse_kw) if fuse_kw else None)
         return dinput
 
     def param_order(self, module):

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define B200GAN_VERSION 100   /* major*10000 + minor*100 + patch */
+#define B200GAN_VERSION 200   /* major*10000 + minor*100 + patch */
 
 typedef enum b200gan_status {
   B200GAN_OK = 0,
@@ -72,6 +72,42 @@ typedef struct b200gan_conv {
   int32_t algo;             /* b200gan_algo */
 } b200gan_conv;
 
+/* Optional fusions around one convolution call (NULL or all-zero = plain convolution).  They describe WHAT is computed,
+ * not how: where a kernel cannot fuse an item the library runs the equivalent extra pass itself, so results never
+ * depend on which kernel was selected.
+ *
+ *  out_act / out_slope   fprop:  y = act(conv(x)) for the layers without BatchNorm: LeakyReLU(0.2) after the first
+ *                        Conv2d (dcgan.py:65-66), Tanh after the last ConvTranspose2d (dcgan.py:46-47).
+ *  dy_act / dy_slope / dy_ref   dgrad, wgrad: the gradient operand `dy` is the gradient w.r.t. the OUTPUT of the activation
+ *                        that follows this convolution; dy_eff = dy * act'(.) is formed while dy is read, with act' taken
+ *                        from dy_ref = the saved activation output (same extents as dy; LeakyReLU/ReLU: its sign,
+ *                        Tanh: 1 - a^2, Sigmoid: a(1-a)).  Replaces leaky_relu_backward / tanh_backward of autograd.
+ *  bn_sums               fprop:  per-channel batch statistics of the stored result, OVERWRITTEN: bn_sums[0..C) = sum y,
+ *                        bn_sums[C..2C) = sum y^2 over (N,H,W) -- the same contract as b200gan_bn_stats, which it replaces
+ *                        (native_batch_norm's statistics pass, dcgan.py:27,31,35,39,43,69,73,77,81).
+ *  prev_*                dgrad:  the result dx is the gradient w.r.t. a_prev = act(BN(y_prev)), the previous layer's
+ *                        output; the epilogue applies that activation's backward and the BatchNorm-backward reductions:
+ *                          dz = dx * act'(prev_scale[c]*y_prev + prev_shift[c])          (stored INSTEAD of dx)
+ *                          prev_sums[0..C) = sum dz,  prev_sums[C..2C) = sum dz*(y_prev - prev_mean[c])*prev_invstd[c]
+ *                        (OVERWRITTEN; the same contract as b200gan_bn_act_bwd_reduce, which it replaces).  The caller then
+ *                        finishes native_batch_norm_backward with b200gan_bn_act_bwd_apply(da = dz, act = NONE). */
+typedef struct b200gan_fuse {
+  int32_t out_act;
+  float   out_slope;
+  int32_t dy_act;
+  float   dy_slope;
+  const b200gan_view* dy_ref;
+  double* bn_sums;
+  int32_t prev_act;
+  float   prev_slope;
+  const b200gan_view* prev_y;
+  const float* prev_scale;
+  const float* prev_shift;
+  const float* prev_mean;
+  const float* prev_invstd;
+  double* prev_sums;
+} b200gan_fuse;
+
 int         b200gan_version(void);
 const char* b200gan_last_error_string(void);
 /* Fills name (<=255 chars + NUL) with the device name; returns SM count, or a negative status. */
@@ -81,19 +117,19 @@ int         b200gan_device_info(int device, char* name, int* cc_major, int* cc_m
  *      reached from train_gan.py:129,137,148).  dw is fp32 (Cout,Cin,k,k) and is ACCUMULATED into
  *      (`+=`), matching autograd's accumulation over the real and fake passes (train_gan.py:129,137). */
 int b200gan_conv2d_fprop(const b200gan_conv* cv, const b200gan_view* x, const float* weight, const void* wpacked,
-                         const b200gan_view* y, void* stream);
+                         const b200gan_view* y, const b200gan_fuse* fuse, void* stream);
 int b200gan_conv2d_dgrad(const b200gan_conv* cv, const b200gan_view* dy, const float* weight, const void* wpacked,
-                         const b200gan_view* dx, void* stream);
+                         const b200gan_view* dx, const b200gan_fuse* fuse, void* stream);
 int b200gan_conv2d_wgrad(const b200gan_conv* cv, const b200gan_view* x, const b200gan_view* dy, float* dweight,
-                         void* stream);
+                         const b200gan_fuse* fuse, void* stream);
 
 /* ---- nn.ConvTranspose2d: forward (dcgan.py:26-46), input gradient, weight gradient (Cin,Cout,k,k). */
 int b200gan_convT2d_fprop(const b200gan_conv* cv, const b200gan_view* x, const float* weight, const void* wpacked,
-                          const b200gan_view* y, void* stream);
+                          const b200gan_view* y, const b200gan_fuse* fuse, void* stream);
 int b200gan_convT2d_dgrad(const b200gan_conv* cv, const b200gan_view* dy, const float* weight, const void* wpacked,
-                          const b200gan_view* dx, void* stream);
+                          const b200gan_view* dx, const b200gan_fuse* fuse, void* stream);
 int b200gan_convT2d_wgrad(const b200gan_conv* cv, const b200gan_view* x, const b200gan_view* dy, float* dweight,
-                          void* stream);
+                          const b200gan_fuse* fuse, void* stream);
 
 /* ---- bf16 repack of a k=4 conv weight for the tcgen05 implicit GEMM (`wpacked` above).  `weight` is the fp32
  *      master in conv geometry (Co,Ci,4,4) -- i.e. the Conv2d weight, or the ConvTranspose2d weight (Cin,Cout,4,4)

@@ -62,16 +62,16 @@ def test_conv2d_fprop_dgrad_wgrad(case, mode):
     xd, dyd, wd = nhwc(x, dt), nhwc(dy, dt), dev(wt)
     # fprop
     y = torch.empty((n, oh, ow, co), device='cuda', dtype=dt)
-    L.call('b200gan_conv2d_fprop', C.byref(cv), C.byref(L.view_nhwc(xd)), L.ptr(wd), None, C.byref(L.view_nhwc(y)), st())
+    L.call('b200gan_conv2d_fprop', C.byref(cv), C.byref(L.view_nhwc(xd)), L.ptr(wd), None, C.byref(L.view_nhwc(y)), None, st())
     close(to_nchw(y), orc.conv2d_fprop(x, wt, s, p), what='fprop', **TOL[mode])
     # dgrad
     dx = torch.empty((n, h, w, ci), device='cuda', dtype=dt)
-    L.call('b200gan_conv2d_dgrad', C.byref(cv), C.byref(L.view_nhwc(dyd)), L.ptr(wd), None, C.byref(L.view_nhwc(dx)), st())
+    L.call('b200gan_conv2d_dgrad', C.byref(cv), C.byref(L.view_nhwc(dyd)), L.ptr(wd), None, C.byref(L.view_nhwc(dx)), None, st())
     close(to_nchw(dx), orc.conv2d_dgrad(dy, wt, s, p, (h, w)), what='dgrad', **TOL[mode])
     # wgrad accumulates: start from a non-zero buffer
     base = rng.randn(co, ci, k, k).astype(np.float32)
     dw = dev(base)
-    L.call('b200gan_conv2d_wgrad', C.byref(cv), C.byref(L.view_nhwc(xd)), C.byref(L.view_nhwc(dyd)), L.ptr(dw), st())
+    L.call('b200gan_conv2d_wgrad', C.byref(cv), C.byref(L.view_nhwc(xd)), C.byref(L.view_nhwc(dyd)), L.ptr(dw), None, st())
     ref = orc.conv2d_wgrad(x, dy, k, s, p)
     close(dw.cpu().numpy() - base, ref, rtol=1e-4, atol=1e-4 * max(1.0, np.abs(ref).max()), what='wgrad')
 
@@ -88,13 +88,13 @@ def test_convT2d_on_reference_nchw_views(mode):
     cv = L.Conv(k, s, p, L.ALGO_SIMT)
     xd, dyd, wd = dev(x), dev(dy), dev(wt)                     # NCHW fp32, as the reference holds them
     y = torch.empty((n, cout, oh, oh), device='cuda')
-    L.call('b200gan_convT2d_fprop', C.byref(cv), C.byref(L.view_nchw(xd)), L.ptr(wd), None, C.byref(L.view_nchw(y)), st())
+    L.call('b200gan_convT2d_fprop', C.byref(cv), C.byref(L.view_nchw(xd)), L.ptr(wd), None, C.byref(L.view_nchw(y)), None, st())
     close(y.cpu().numpy(), orc.convT2d_fprop(x, wt, s, p), what='convT fprop')
     dx = torch.empty_like(xd)
-    L.call('b200gan_convT2d_dgrad', C.byref(cv), C.byref(L.view_nchw(dyd)), L.ptr(wd), None, C.byref(L.view_nchw(dx)), st())
+    L.call('b200gan_convT2d_dgrad', C.byref(cv), C.byref(L.view_nchw(dyd)), L.ptr(wd), None, C.byref(L.view_nchw(dx)), None, st())
     close(dx.cpu().numpy(), orc.convT2d_dgrad(dy, wt, s, p), what='convT dgrad')
     dw = torch.zeros_like(wd)
-    L.call('b200gan_convT2d_wgrad', C.byref(cv), C.byref(L.view_nchw(xd)), C.byref(L.view_nchw(dyd)), L.ptr(dw), st())
+    L.call('b200gan_convT2d_wgrad', C.byref(cv), C.byref(L.view_nchw(xd)), C.byref(L.view_nchw(dyd)), L.ptr(dw), None, st())
     close(dw.cpu().numpy(), orc.convT2d_wgrad(x, dy, k, s, p), rtol=1e-4, atol=1e-4, what='convT wgrad')
     # G0: latent (N,nz,1,1) -> (N,C,7,7)
     z = rng.randn(3, 10, 1, 1).astype(np.float32)
@@ -102,7 +102,7 @@ def test_convT2d_on_reference_nchw_views(mode):
     cv0 = L.Conv(7, 1, 0, L.ALGO_SIMT)
     y0 = torch.empty((3, 9, 7, 7), device='cuda')
     zd, w0d = dev(z), dev(w0)          # keep the device tensors alive across the asynchronous launch
-    L.call('b200gan_convT2d_fprop', C.byref(cv0), C.byref(L.view_nchw(zd)), L.ptr(w0d), None, C.byref(L.view_nchw(y0)), st())
+    L.call('b200gan_convT2d_fprop', C.byref(cv0), C.byref(L.view_nchw(zd)), L.ptr(w0d), None, C.byref(L.view_nchw(y0)), None, st())
     close(y0.cpu().numpy(), orc.convT2d_fprop(z, w0, 1, 0), what='G0 fprop')
 
 
@@ -112,11 +112,11 @@ def test_conv_shape_errors_are_loud():
     y = torch.zeros((1, 5, 4, 4), device='cuda')            # wrong OH
     w = torch.zeros((4, 4, 4, 4), device='cuda')
     with pytest.raises(L.B200GanError, match='shapes do not match'):
-        L.call('b200gan_conv2d_fprop', C.byref(cv), C.byref(L.view_nhwc(x)), L.ptr(w), None, C.byref(L.view_nhwc(y)), st())
+        L.call('b200gan_conv2d_fprop', C.byref(cv), C.byref(L.view_nhwc(x)), L.ptr(w), None, C.byref(L.view_nhwc(y)), None, st())
     cvt = L.Conv(4, 2, 1, L.ALGO_TCGEN05)                   # forced tensor-core path on a shape it cannot take
     y2 = torch.zeros((1, 4, 4, 4), device='cuda')
     with pytest.raises(L.B200GanError):
-        L.call('b200gan_conv2d_fprop', C.byref(cvt), C.byref(L.view_nhwc(x)), L.ptr(w), None, C.byref(L.view_nhwc(y2)), st())
+        L.call('b200gan_conv2d_fprop', C.byref(cvt), C.byref(L.view_nhwc(x)), L.ptr(w), None, C.byref(L.view_nhwc(y2)), None, st())
 
 
 @pytest.mark.parametrize('mode', ['fp32', 'bf16'])

@@ -39,16 +39,16 @@ def run_pair(n, ci, h, w_, co, direction):
         y_tc = torch.full((n, h // 2, w_ // 2, co), float('nan'), device='cuda', dtype=torch.bfloat16)
         y_ref = torch.empty_like(y_tc)
         wp = pack(wt, 0)
-        L.call('b200gan_conv2d_fprop', C.byref(cv_tc), C.byref(L.view_nhwc(x)), L.ptr(wt), L.ptr(wp), C.byref(L.view_nhwc(y_tc)), st())
-        L.call('b200gan_conv2d_fprop', C.byref(cv_simt), C.byref(L.view_nhwc(x)), L.ptr(wt), None, C.byref(L.view_nhwc(y_ref)), st())
+        L.call('b200gan_conv2d_fprop', C.byref(cv_tc), C.byref(L.view_nhwc(x)), L.ptr(wt), L.ptr(wp), C.byref(L.view_nhwc(y_tc)), None, st())
+        L.call('b200gan_conv2d_fprop', C.byref(cv_simt), C.byref(L.view_nhwc(x)), L.ptr(wt), None, C.byref(L.view_nhwc(y_ref)), None, st())
         torch.cuda.synchronize()
         return x, wt, y_tc, y_ref
     dy = bf16_exact((n, h, w_, co), 1.0, 3)                                  # coarse side (n,h,w,co) -> fine (n,2h,2w,ci)
     dx_tc = torch.full((n, 2 * h, 2 * w_, ci), float('nan'), device='cuda', dtype=torch.bfloat16)
     dx_ref = torch.empty_like(dx_tc)
     wp = pack(wt, 1)
-    L.call('b200gan_conv2d_dgrad', C.byref(cv_tc), C.byref(L.view_nhwc(dy)), L.ptr(wt), L.ptr(wp), C.byref(L.view_nhwc(dx_tc)), st())
-    L.call('b200gan_conv2d_dgrad', C.byref(cv_simt), C.byref(L.view_nhwc(dy)), L.ptr(wt), None, C.byref(L.view_nhwc(dx_ref)), st())
+    L.call('b200gan_conv2d_dgrad', C.byref(cv_tc), C.byref(L.view_nhwc(dy)), L.ptr(wt), L.ptr(wp), C.byref(L.view_nhwc(dx_tc)), None, st())
+    L.call('b200gan_conv2d_dgrad', C.byref(cv_simt), C.byref(L.view_nhwc(dy)), L.ptr(wt), None, C.byref(L.view_nhwc(dx_ref)), None, st())
     torch.cuda.synchronize()
     return dy, wt, dx_tc, dx_ref
 
@@ -107,8 +107,8 @@ def test_tc_wgrad_matches_simt(case):
     base = torch.randn((co, ci, 4, 4), device='cuda')
     dw_tc, dw_ref = base.clone(), base.clone()
     cv_tc, cv_simt = L.Conv(4, 2, 1, L.ALGO_TCGEN05), L.Conv(4, 2, 1, L.ALGO_SIMT)
-    L.call('b200gan_conv2d_wgrad', C.byref(cv_tc), C.byref(L.view_nhwc(x)), C.byref(L.view_nhwc(dy)), L.ptr(dw_tc), st())
-    L.call('b200gan_conv2d_wgrad', C.byref(cv_simt), C.byref(L.view_nhwc(x)), C.byref(L.view_nhwc(dy)), L.ptr(dw_ref), st())
+    L.call('b200gan_conv2d_wgrad', C.byref(cv_tc), C.byref(L.view_nhwc(x)), C.byref(L.view_nhwc(dy)), L.ptr(dw_tc), None, st())
+    L.call('b200gan_conv2d_wgrad', C.byref(cv_simt), C.byref(L.view_nhwc(x)), C.byref(L.view_nhwc(dy)), L.ptr(dw_ref), None, st())
     torch.cuda.synchronize()
     a, b = (dw_tc - base).cpu().numpy(), (dw_ref - base).cpu().numpy()
     print(f'wgrad {case}: max|diff|={np.abs(a - b).max():.4e} ref max={np.abs(b).max():.3e}')
@@ -121,6 +121,6 @@ def test_tc_wgrad_against_numpy_oracle():
     dy = bf16_exact((n, h // 2, h // 2, co), 1.0, 7)
     dw = torch.zeros((co, ci, 4, 4), device='cuda')
     cv = L.Conv(4, 2, 1, L.ALGO_TCGEN05)
-    L.call('b200gan_conv2d_wgrad', C.byref(cv), C.byref(L.view_nhwc(x)), C.byref(L.view_nhwc(dy)), L.ptr(dw), st())
+    L.call('b200gan_conv2d_wgrad', C.byref(cv), C.byref(L.view_nhwc(x)), C.byref(L.view_nhwc(dy)), L.ptr(dw), None, st())
     ref = orc.conv2d_wgrad(x.float().cpu().numpy().transpose(0, 3, 1, 2), dy.float().cpu().numpy().transpose(0, 3, 1, 2), 4, 2, 1)
     close(dw.cpu().numpy(), ref, rtol=1e-3, atol=1e-3, what='wgrad vs oracle')

@@ -27,7 +27,7 @@ def rnd(shape, seed, dtype=torch.float32, scale=1.0):
 @pytest.mark.parametrize('nc', [1, 3])
 @pytest.mark.parametrize('fine_kind', ['nchw_f32', 'nhwc_bf16'])
 def test_thin_layers_match_generic(nc, fine_kind):
-    n, h = 3, 20                                   # fine 40x40, coarse 20x20
+    n, h = 3, 16                                   # fine 32x32, coarse 16x16 (W % 16 == 0: the warp-MMA kernels)
     w = rnd((32, nc, 4, 4), 1, scale=0.1)
     if fine_kind == 'nchw_f32':
         fine = rnd((n, nc, 2 * h, 2 * h), 2)
@@ -40,29 +40,30 @@ def test_thin_layers_match_generic(nc, fine_kind):
     coarse = rnd((n, h, h, 32), 3, torch.bfloat16)
     # down: conv2d fprop (D0) -- fine -> coarse
     ya, yb = torch.empty_like(coarse), torch.empty_like(coarse)
-    L.call('b200gan_conv2d_fprop', C.byref(AUTO), C.byref(fview(fine)), L.ptr(w), None, C.byref(L.view_nhwc(ya)), st())
-    L.call('b200gan_conv2d_fprop', C.byref(SIMT), C.byref(fview(fine)), L.ptr(w), None, C.byref(L.view_nhwc(yb)), st())
+    L.call('b200gan_conv2d_fprop', C.byref(AUTO), C.byref(fview(fine)), L.ptr(w), None, C.byref(L.view_nhwc(ya)), None, st())
+    L.call('b200gan_conv2d_fprop', C.byref(SIMT), C.byref(fview(fine)), L.ptr(w), None, C.byref(L.view_nhwc(yb)), None, st())
     close(ya.float().cpu().numpy(), yb.float().cpu().numpy(), rtol=1e-2, atol=1e-2, what='thin down')
     # up: conv2d dgrad (D0 dgrad / G5 fprop) -- coarse -> fine
     da, db = fine_out(), fine_out()
-    L.call('b200gan_conv2d_dgrad', C.byref(AUTO), C.byref(L.view_nhwc(coarse)), L.ptr(w), None, C.byref(fview(da)), st())
-    L.call('b200gan_conv2d_dgrad', C.byref(SIMT), C.byref(L.view_nhwc(coarse)), L.ptr(w), None, C.byref(fview(db)), st())
+    L.call('b200gan_conv2d_dgrad', C.byref(AUTO), C.byref(L.view_nhwc(coarse)), L.ptr(w), None, C.byref(fview(da)), None, st())
+    L.call('b200gan_conv2d_dgrad', C.byref(SIMT), C.byref(L.view_nhwc(coarse)), L.ptr(w), None, C.byref(fview(db)), None, st())
     close(da.float().cpu().numpy(), db.float().cpu().numpy(), rtol=1e-2, atol=2e-2, what='thin up')
     # wgrad
     base = rnd((32, nc, 4, 4), 4)
     wa, wb = base.clone(), base.clone()
-    L.call('b200gan_conv2d_wgrad', C.byref(AUTO), C.byref(fview(fine)), C.byref(L.view_nhwc(coarse)), L.ptr(wa), st())
-    L.call('b200gan_conv2d_wgrad', C.byref(SIMT), C.byref(fview(fine)), C.byref(L.view_nhwc(coarse)), L.ptr(wb), st())
+    L.call('b200gan_conv2d_wgrad', C.byref(AUTO), C.byref(fview(fine)), C.byref(L.view_nhwc(coarse)), L.ptr(wa), None, st())
+    L.call('b200gan_conv2d_wgrad', C.byref(SIMT), C.byref(fview(fine)), C.byref(L.view_nhwc(coarse)), L.ptr(wb), None, st())
     ref = (wb - base).cpu().numpy()
-    close((wa - base).cpu().numpy(), ref, rtol=1e-3, atol=1e-3 * np.abs(ref).max(), what='thin wgrad')
+    # the warp-MMA kernel stages the image as bf16 (the SIMT reference keeps fp32 image values): bf16 tolerance
+    close((wa - base).cpu().numpy(), ref, rtol=5e-3, atol=5e-3 * np.abs(ref).max(), what='thin wgrad')
 
 
 def test_thin_down_against_oracle():
-    n, h, nc = 2, 8, 3
+    n, h, nc = 2, 16, 3
     w = rnd((32, nc, 4, 4), 1, scale=0.1)
     fine = rnd((n, nc, 2 * h, 2 * h), 2)
     y = torch.empty((n, h, h, 32), device='cuda', dtype=torch.bfloat16)
-    L.call('b200gan_conv2d_fprop', C.byref(AUTO), C.byref(L.view_nchw(fine)), L.ptr(w), None, C.byref(L.view_nhwc(y)), st())
+    L.call('b200gan_conv2d_fprop', C.byref(AUTO), C.byref(L.view_nchw(fine)), L.ptr(w), None, C.byref(L.view_nhwc(y)), None, st())
     ref = orc.conv2d_fprop(fine.cpu().numpy(), w.cpu().numpy(), 2, 1)
     close(y.float().cpu().numpy().transpose(0, 3, 1, 2), ref, rtol=1e-2, atol=1e-2, what='thin down vs oracle')
 
@@ -73,18 +74,18 @@ def test_window_gemv_matches_generic():
     x = rnd((n, k, k, c), 1, torch.bfloat16)
     w = rnd((1, c, k, k), 2, scale=0.05)
     ya, yb = torch.empty((n, 1, 1, 1), device='cuda'), torch.empty((n, 1, 1, 1), device='cuda')
-    L.call('b200gan_conv2d_fprop', C.byref(cva), C.byref(L.view_nhwc(x)), L.ptr(w), None, C.byref(L.view_nhwc(ya)), st())
-    L.call('b200gan_conv2d_fprop', C.byref(cvs), C.byref(L.view_nhwc(x)), L.ptr(w), None, C.byref(L.view_nhwc(yb)), st())
+    L.call('b200gan_conv2d_fprop', C.byref(cva), C.byref(L.view_nhwc(x)), L.ptr(w), None, C.byref(L.view_nhwc(ya)), None, st())
+    L.call('b200gan_conv2d_fprop', C.byref(cvs), C.byref(L.view_nhwc(x)), L.ptr(w), None, C.byref(L.view_nhwc(yb)), None, st())
     close(ya.cpu().numpy(), yb.cpu().numpy(), rtol=1e-4, atol=1e-4, what='window fprop')
     dl = rnd((n, 1, 1, 1), 3)
     da, db = torch.empty_like(x), torch.empty_like(x)
-    L.call('b200gan_conv2d_dgrad', C.byref(cva), C.byref(L.view_nhwc(dl)), L.ptr(w), None, C.byref(L.view_nhwc(da)), st())
-    L.call('b200gan_conv2d_dgrad', C.byref(cvs), C.byref(L.view_nhwc(dl)), L.ptr(w), None, C.byref(L.view_nhwc(db)), st())
+    L.call('b200gan_conv2d_dgrad', C.byref(cva), C.byref(L.view_nhwc(dl)), L.ptr(w), None, C.byref(L.view_nhwc(da)), None, st())
+    L.call('b200gan_conv2d_dgrad', C.byref(cvs), C.byref(L.view_nhwc(dl)), L.ptr(w), None, C.byref(L.view_nhwc(db)), None, st())
     close(da.float().cpu().numpy(), db.float().cpu().numpy(), rtol=1e-2, atol=1e-3, what='window dgrad')
     base = rnd((1, c, k, k), 4)
     wa, wb = base.clone(), base.clone()
-    L.call('b200gan_conv2d_wgrad', C.byref(cva), C.byref(L.view_nhwc(x)), C.byref(L.view_nhwc(dl)), L.ptr(wa), st())
-    L.call('b200gan_conv2d_wgrad', C.byref(cvs), C.byref(L.view_nhwc(x)), C.byref(L.view_nhwc(dl)), L.ptr(wb), st())
+    L.call('b200gan_conv2d_wgrad', C.byref(cva), C.byref(L.view_nhwc(x)), C.byref(L.view_nhwc(dl)), L.ptr(wa), None, st())
+    L.call('b200gan_conv2d_wgrad', C.byref(cvs), C.byref(L.view_nhwc(x)), C.byref(L.view_nhwc(dl)), L.ptr(wb), None, st())
     close((wa - base).cpu().numpy(), (wb - base).cpu().numpy(), rtol=1e-3, atol=1e-3, what='window wgrad')
 
 
@@ -95,13 +96,13 @@ def test_latent_gemm_matches_generic():
     w = rnd((nz, c, k, k), 2, scale=0.05)
     ya = torch.empty((n, k, k, c), device='cuda', dtype=torch.bfloat16)
     yb = torch.empty_like(ya)
-    L.call('b200gan_convT2d_fprop', C.byref(cva), C.byref(L.view_nchw(z)), L.ptr(w), None, C.byref(L.view_nhwc(ya)), st())
-    L.call('b200gan_convT2d_fprop', C.byref(cvs), C.byref(L.view_nchw(z)), L.ptr(w), None, C.byref(L.view_nhwc(yb)), st())
+    L.call('b200gan_convT2d_fprop', C.byref(cva), C.byref(L.view_nchw(z)), L.ptr(w), None, C.byref(L.view_nhwc(ya)), None, st())
+    L.call('b200gan_convT2d_fprop', C.byref(cvs), C.byref(L.view_nchw(z)), L.ptr(w), None, C.byref(L.view_nhwc(yb)), None, st())
     close(ya.float().cpu().numpy(), yb.float().cpu().numpy(), rtol=1e-2, atol=1e-2, what='latent fprop')
     dy = rnd((n, k, k, c), 3, torch.bfloat16)
     base = rnd((nz, c, k, k), 4)
     wa, wb = base.clone(), base.clone()
-    L.call('b200gan_convT2d_wgrad', C.byref(cva), C.byref(L.view_nchw(z)), C.byref(L.view_nhwc(dy)), L.ptr(wa), st())
-    L.call('b200gan_convT2d_wgrad', C.byref(cvs), C.byref(L.view_nchw(z)), C.byref(L.view_nhwc(dy)), L.ptr(wb), st())
+    L.call('b200gan_convT2d_wgrad', C.byref(cva), C.byref(L.view_nchw(z)), C.byref(L.view_nhwc(dy)), L.ptr(wa), None, st())
+    L.call('b200gan_convT2d_wgrad', C.byref(cvs), C.byref(L.view_nchw(z)), C.byref(L.view_nhwc(dy)), L.ptr(wb), None, st())
     ref = (wb - base).cpu().numpy()
     close((wa - base).cpu().numpy(), ref, rtol=1e-3, atol=1e-3 * np.abs(ref).max(), what='latent wgrad')

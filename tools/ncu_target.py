@@ -27,13 +27,13 @@ d1, d3, d4 = mid(32, 112, 64), mid(128, 28, 256), mid(256, 14, 512)
 yb = rnd((B, 56, 56, 64)); dab = rnd((B, 56, 56, 64)); dyb = torch.empty_like(yb)
 sc, sh, mu, isd, gam = (torch.rand(64, device='cuda') + 0.5 for _ in range(5)); sums = torch.zeros(128, device='cuda', dtype=torch.float64)
 for _ in range(reps):
-    L.call('b200gan_conv2d_fprop', C.byref(auto), C.byref(L.view_nhwc(img)), L.ptr(w0), None, C.byref(L.view_nhwc(out32)), st())
-    L.call('b200gan_conv2d_dgrad', C.byref(auto), C.byref(L.view_nhwc(c32)), L.ptr(w0), None, C.byref(L.view_nhwc(outimg)), st())
-    L.call('b200gan_conv2d_wgrad', C.byref(auto), C.byref(L.view_nhwc(img)), C.byref(L.view_nhwc(c32)), L.ptr(dw0), st())
+    L.call('b200gan_conv2d_fprop', C.byref(auto), C.byref(L.view_nhwc(img)), L.ptr(w0), None, C.byref(L.view_nhwc(out32)), None, st())
+    L.call('b200gan_conv2d_dgrad', C.byref(auto), C.byref(L.view_nhwc(c32)), L.ptr(w0), None, C.byref(L.view_nhwc(outimg)), None, st())
+    L.call('b200gan_conv2d_wgrad', C.byref(auto), C.byref(L.view_nhwc(img)), C.byref(L.view_nhwc(c32)), L.ptr(dw0), None, st())
     for d in (d1, d3, d4):
-        L.call('b200gan_conv2d_fprop', C.byref(auto), C.byref(L.view_nhwc(d['x'])), L.ptr(d['w']), L.ptr(d['wd']), C.byref(L.view_nhwc(d['y'])), st())
-        L.call('b200gan_conv2d_dgrad', C.byref(auto), C.byref(L.view_nhwc(d['dy'])), L.ptr(d['w']), L.ptr(d['wu']), C.byref(L.view_nhwc(d['dx'])), st())
-        L.call('b200gan_conv2d_wgrad', C.byref(auto), C.byref(L.view_nhwc(d['x'])), C.byref(L.view_nhwc(d['dy'])), L.ptr(d['dw']), st())
+        L.call('b200gan_conv2d_fprop', C.byref(auto), C.byref(L.view_nhwc(d['x'])), L.ptr(d['w']), L.ptr(d['wd']), C.byref(L.view_nhwc(d['y'])), None, st())
+        L.call('b200gan_conv2d_dgrad', C.byref(auto), C.byref(L.view_nhwc(d['dy'])), L.ptr(d['w']), L.ptr(d['wu']), C.byref(L.view_nhwc(d['dx'])), None, st())
+        L.call('b200gan_conv2d_wgrad', C.byref(auto), C.byref(L.view_nhwc(d['x'])), C.byref(L.view_nhwc(d['dy'])), L.ptr(d['dw']), None, st())
     L.call('b200gan_bn_act_bwd_reduce', C.byref(L.view_nhwc(dab)), C.byref(L.view_nhwc(yb)), None, L.ptr(sc), L.ptr(sh), L.ptr(mu), L.ptr(isd), L.ACT_LRELU, 0.2, L.ptr(sums), st())
     L.call('b200gan_bn_act_bwd_apply', C.byref(L.view_nhwc(dab)), C.byref(L.view_nhwc(yb)), None, L.ptr(sc), L.ptr(sh), L.ptr(mu), L.ptr(isd), L.ptr(gam), L.ptr(sums), B * 56 * 56, L.ACT_LRELU, 0.2, C.byref(L.view_nhwc(dyb)), None, None, st())
     torch.cuda.synchronize()

@@ -25,7 +25,7 @@ with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
 agg = collections.defaultdict(lambda: [0, 0.0])
 for e in prof.events():
     if e.device_type == torch.autograd.DeviceType.CUDA:
-        name = re.sub(r'\(.*', '', e.name).replace('void b200gan::', '').replace('b200gan::', '')
+        name = re.sub(r'\(.*', '', e.name.replace('(anonymous namespace)::', '')).replace('void b200gan::', '').replace('b200gan::', '')
         agg[name[:80]][0] += 1; agg[name[:80]][1] += e.device_time if hasattr(e, 'device_time') else e.cuda_time
 tot = sum(v[1] for v in agg.values())
 print(f'total GPU kernel time {tot/1e3/a.steps:.3f} ms/step over {a.steps} steps')
