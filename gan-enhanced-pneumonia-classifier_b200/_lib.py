@@ -62,7 +62,7 @@ PROTOTYPES = {
     'b200gan_bn_act_bwd_reduce': [_VP, _VP, _VP, _vp, _vp, _vp, _vp, _i32, _f32, _vp, _vp],
     'b200gan_bn_act_bwd_apply': [_VP, _VP, _VP, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _VP, _vp, _vp, _vp],
     'b200gan_bce_sigmoid': [_vp, _i32, _f32, _f32, _vp, _vp, _vp, _vp],
-    'b200gan_adam': [_vp, _vp, _vp, _vp, _i64, _f64, _f64, _f64, _f64, _i32, _f32, _vp],
+    'b200gan_adam': [_vp, _vp, _vp, _vp, _i64, _f64, _f64, _f64, _f64, _i32, _vp, _f32, _vp],
     'b200gan_copy_view': [_VP, _VP, _vp],
     'b200gan_fill_f32': [_vp, _i64, _f32, _vp],
 }

@@ -48,7 +48,7 @@ int latent_wgrad(const b200gan_conv*, const b200gan_view* dy_fine, const b200gan
 // elementwise.cu
 int ew_bn_stats(const b200gan_view*, double*, cudaStream_t);
 int ew_bn_bwd_reduce(const b200gan_view*, const b200gan_view*, const b200gan_view*, const float*, const float*, const float*,
-                     const float*, int, float, double*, cudaStream_t);
+                     const float*, int, float, double*, const b200gan_view* dz_out, cudaStream_t);
 int ew_bn_finalize(double*, int, int64_t, const float*, const float*, float*, float*, int64_t*, float, float, float*, float*,
                    float*, float*, cudaStream_t);
 int ew_bn_eval_coeffs(int, const float*, const float*, const float*, const float*, float, float*, float*, cudaStream_t);
@@ -58,7 +58,7 @@ int ew_bn_act_bwd_apply(const b200gan_view*, const b200gan_view*, const b200gan_
                         cudaStream_t);
 int ew_act_bwd_inplace(const b200gan_view* d, const b200gan_view* y, const float* scale, const float* shift, int act, float slope, cudaStream_t);
 int ew_bce_sigmoid(const float*, int, float, float, float*, float*, float*, cudaStream_t);
-int ew_adam(float*, const float*, float*, float*, int64_t, double, double, double, double, int, float, cudaStream_t);
+int ew_adam(float*, const float*, float*, float*, int64_t, double, double, double, double, int, const int64_t*, float, cudaStream_t);
 int ew_copy_view(const b200gan_view*, const b200gan_view*, cudaStream_t);
 int ew_fill(float*, int64_t, float, cudaStream_t);
 
@@ -193,10 +193,11 @@ static int conv_dispatch(Prim prim, bool transposed, const b200gan_conv* cv, con
   // ---- BatchNorm fusions not absorbed by the kernel: the equivalent passes ---------------------------------
   if (bn_sums && (rc = ew_bn_stats(result, bn_sums, st))) return rc;
   if (prev) {
-    if ((rc = ew_bn_bwd_reduce(result, fuse->prev_y, nullptr, fuse->prev_scale, fuse->prev_shift, fuse->prev_mean, fuse->prev_invstd,
-                               fuse->prev_act, fuse->prev_slope, fuse->prev_sums, st)))
-      return rc;
-    if ((rc = ew_act_bwd_inplace(result, fuse->prev_y, fuse->prev_scale, fuse->prev_shift, fuse->prev_act, fuse->prev_slope, st))) return rc;
+    // one dense pass (dz stored in place + sums) when the layout allows, reduce + in-place pass otherwise
+    rc = ew_bn_bwd_reduce(result, fuse->prev_y, nullptr, fuse->prev_scale, fuse->prev_shift, fuse->prev_mean, fuse->prev_invstd,
+                          fuse->prev_act, fuse->prev_slope, fuse->prev_sums, result, st);
+    if (rc < 0) return rc;
+    if (rc == 2 && (rc = ew_act_bwd_inplace(result, fuse->prev_y, fuse->prev_scale, fuse->prev_shift, fuse->prev_act, fuse->prev_slope, st))) return rc;
   }
   return 0;
 }
@@ -294,7 +295,7 @@ int b200gan_bn_act_bwd_reduce(const b200gan_view* da, const b200gan_view* y, con
   if (a && (rc = check_view(a, "bn_act_bwd_reduce"))) return rc;
   B200_CHECK_ARG(scale && shift && save_mean && save_invstd && sums, "bn_act_bwd_reduce: null pointer");
   B200_CHECK_ARG((act != B200GAN_ACT_TANH && act != B200GAN_ACT_SIGMOID) || a, "bn_act_bwd_reduce: tanh/sigmoid need the saved output");
-  return ew_bn_bwd_reduce(da, y, a, scale, shift, save_mean, save_invstd, act, slope, sums, (cudaStream_t)stream);
+  return ew_bn_bwd_reduce(da, y, a, scale, shift, save_mean, save_invstd, act, slope, sums, nullptr, (cudaStream_t)stream);
 }
 
 int b200gan_bn_act_bwd_apply(const b200gan_view* da, const b200gan_view* y, const b200gan_view* a, const float* scale,
@@ -319,9 +320,9 @@ int b200gan_bce_sigmoid(const float* logit, int32_t batch, float target, float g
 }
 
 int b200gan_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t numel, double lr, double beta1,
-                 double beta2, double eps, int32_t step, float grad_scale, void* stream) {
-  B200_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && numel > 0 && step >= 1, "adam: bad argument");
-  return ew_adam(param, grad, exp_avg, exp_avg_sq, numel, lr, beta1, beta2, eps, step, grad_scale, (cudaStream_t)stream);
+                 double beta2, double eps, int32_t step, const int64_t* step_dev, float grad_scale, void* stream) {
+  B200_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && numel > 0 && (step >= 1 || step_dev), "adam: bad argument");
+  return ew_adam(param, grad, exp_avg, exp_avg_sq, numel, lr, beta1, beta2, eps, step < 1 ? 1 : step, step_dev, grad_scale, (cudaStream_t)stream);
 }
 
 int b200gan_copy_view(const b200gan_view* src, const b200gan_view* dst, void* stream) {

@@ -95,6 +95,13 @@ __device__ __forceinline__ void tcgen05_ld_32x32b_x32(uint32_t taddr, uint32_t* 
         "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
 }
+__device__ __forceinline__ void tcgen05_ld_32x32b_x16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
 __device__ __forceinline__ void tcgen05_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
@@ -137,11 +144,11 @@ struct TcConvParams {
 };
 
 
-// Column sums over the 32 lanes of a warp for 32 columns held as v[0..31] per lane: 31 shuffles (reduce-scatter butterfly)
-// instead of 32 x 5.  On return v[0] of lane j is the sum of column j.
-__device__ __forceinline__ void warp_column_sums(float (&v)[32], int lane) {
+// Column sums over the 32 lanes of a warp for 16 columns held as v[0..15] per lane: 16 shuffles (reduce-scatter butterfly)
+// instead of 16 x 5.  On return v[0] of lanes j and j+16 is the sum of column j.
+__device__ __forceinline__ void warp_column_sums(float (&v)[16], int lane) {
 #pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) {
+  for (int off = 8; off >= 1; off >>= 1) {
     const bool up = (lane & off) != 0;
 #pragma unroll
     for (int i = 0; i < off; ++i) {
@@ -150,6 +157,7 @@ __device__ __forceinline__ void warp_column_sums(float (&v)[32], int lane) {
       v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
     }
   }
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 16);
 }
 
 template <int BN, int KC, int STAGES>
@@ -165,12 +173,15 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 
 // Persistent kernel: each CTA walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... of the (M-tile, N-tile, class)
-// space.  Warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2..5 = epilogue.  The accumulator is
+// space.  Warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2..9 = epilogue (TMEM lane quarter = warp % 4,
+// column half = (warp - 2) / 4: eight warps keep enough global loads / stores in flight for the fused epilogues).  The accumulator is
 // double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps the MMA stream of tile i+1, and the
 // smem ring keeps running across tile boundaries.  No integer division sits on the per-k-block path of the two
 // single-thread roles (a first version spent ~100 instructions per step there).
+constexpr int kTcThreads = 320;
+
 template <int BN, int KC, int STAGES, int EPI>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(kTcThreads, 2)
 conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcConvParams p) {
   using S = TcSmem<BN, KC, STAGES>;
   extern __shared__ uint8_t smem_raw[];
@@ -197,7 +208,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
@@ -272,8 +283,9 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     }
     __syncwarp();
   } else {
-    // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
-    const int q = warp & 3;
+    // ===== epilogue: warps 2..9 =====
+    const int q = warp & 3, hcol = (warp - 2) >> 2;
+    constexpr int CW = BN / 2;                       // columns per warp
     const int row = q * 32 + lane;
     const int tw = row & (TW - 1), th = (row >> p.tw_log2) & (TH - 1), tn = row >> (p.tw_log2 + p.th_log2);
     int lt = 0;
@@ -284,27 +296,41 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       const int tw_i = r % p.tiles_w; r /= p.tiles_w;
       const int th_i = r % p.tiles_h;
       const int tn_i = r / p.tiles_h;
-      const int ow = tw_i * TW + tw, oh = th_i * TH + th, n = tn_i * TN + tn, cout0 = nt * BN;
+      const int ow = tw_i * TW + tw, oh = th_i * TH + th, n = tn_i * TN + tn, cout0 = nt * BN + hcol * CW;
       const bool valid = ow < p.QW && oh < p.QH && n < p.NB;
       const int py = cls >> 1, px = cls & 1;
-      __nv_bfloat16* orow = p.out + (int64_t)n * p.o_sn + (int64_t)(oh * p.o_mul + (p.o_mul > 1 ? py : 0)) * p.o_sh +
-                            (int64_t)(ow * p.o_mul + (p.o_mul > 1 ? px : 0)) * p.o_sw + cout0;
+      const int64_t ooff = (int64_t)n * p.o_sn + (int64_t)(oh * p.o_mul + (p.o_mul > 1 ? py : 0)) * p.o_sh +
+                           (int64_t)(ow * p.o_mul + (p.o_mul > 1 ? px : 0)) * p.o_sw + cout0;
+      __nv_bfloat16* orow = p.out + ooff;
+      const uint4* yp = reinterpret_cast<const uint4*>(p.prev_y + ooff);
+      uint4 ynext[2];
+      if (EPI == 2) {                                // the first piece of y_prev is requested before the accumulator is waited for
+        ynext[0] = valid ? __ldg(yp) : make_uint4(0u, 0u, 0u, 0u);
+        ynext[1] = valid ? __ldg(yp + 1) : make_uint4(0u, 0u, 0u, 0u);
+      }
       const int buf = lt & 1;
       mbar_wait(&acc_full[buf], (lt >> 1) & 1);
       tcgen05_fence_after();
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t v[32];
-        tcgen05_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + c0, v);
+      for (int c0 = 0; c0 < CW; c0 += 16) {
+        uint32_t v[16];
+        tcgen05_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + hcol * CW + c0, v);
+        float s0[16], s1[16];
+        uint4 ycur[2];
+        if (EPI == 2) {
+          ycur[0] = ynext[0]; ycur[1] = ynext[1];
+          if (c0 + 16 < CW) {
+            ynext[0] = valid ? __ldg(yp + (c0 + 16) / 8) : make_uint4(0u, 0u, 0u, 0u);
+            ynext[1] = valid ? __ldg(yp + (c0 + 16) / 8 + 1) : make_uint4(0u, 0u, 0u, 0u);
+          }
+        }
         tcgen05_wait_ld();
-        float s0[32], s1[32];
         if (EPI == 2) {
           // dz = dx * act'(scale*y_prev + shift); sums of dz and dz*(y_prev - mean) (x invstd at the flush)
-          const uint4* yp = reinterpret_cast<const uint4*>(p.prev_y + (orow - p.out) + c0);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
+          for (int j = 0; j < 2; ++j) {
             float yv[8];
-            unpack8(valid ? __ldg(yp + j) : make_uint4(0u, 0u, 0u, 0u), yv);
+            unpack8(ycur[j], yv);
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
               const float4 cf = ch_coef[cout0 + c0 + 8 * j + e];
@@ -315,15 +341,19 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           }
         }
         // round to the stored precision; the statistics are those of the stored tensor
-        uint32_t pk[16];
+        uint32_t pk[8];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
+        for (int j = 0; j < 8; ++j) {
           __nv_bfloat162 b = __floats2bfloat162_rn(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
           pk[j] = *reinterpret_cast<uint32_t*>(&b);
         }
+        if (valid) {
+          *reinterpret_cast<uint4*>(orow + c0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          *reinterpret_cast<uint4*>(orow + c0 + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
         if (EPI != 0) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
+          for (int j = 0; j < 8; ++j) {
             const float lo = valid ? __uint_as_float(pk[j] << 16) : 0.f, hi = valid ? __uint_as_float(pk[j] & 0xffff0000u) : 0.f;
             s0[2 * j] = lo; s0[2 * j + 1] = hi;
             if (EPI == 1) { s1[2 * j] = lo * lo; s1[2 * j + 1] = hi * hi; }
@@ -331,16 +361,9 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           }
           warp_column_sums(s0, lane);
           warp_column_sums(s1, lane);
-          if (cout0 + c0 + lane < p.cout) {
+          if (lane < 16) {
             atomicAdd(&ch_acc[cout0 + c0 + lane], s0[0]);
             atomicAdd(&ch_acc[p.cout + cout0 + c0 + lane], s1[0]);
-          }
-        }
-        if (valid) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            if (cout0 + c0 + j < p.cout)
-              *reinterpret_cast<uint4*>(orow + c0 + j) = make_uint4(pk[j / 2], pk[j / 2 + 1], pk[j / 2 + 2], pk[j / 2 + 3]);
           }
         }
       }
@@ -350,9 +373,9 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       if (lane == 0) mbar_arrive(&acc_empty[buf]);
     }
     if (EPI != 0) {
-      // the four epilogue warps (128 threads) flush the CTA's channel sums: one double atomic per channel and quantity
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      for (int c = threadIdx.x - 64; c < p.cout; c += 128) {
+      // the eight epilogue warps (256 threads) flush the CTA's channel sums: one double atomic per channel and quantity
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      for (int c = threadIdx.x - 64; c < p.cout; c += 256) {
         const float a0 = ch_acc[c], a1 = ch_acc[p.cout + c];
         if (a0 != 0.f) atomicAdd(p.sums + c, (double)a0);
         if (a1 != 0.f) atomicAdd(p.sums + p.cout + c, (double)a1 * (EPI == 2 ? (double)ch_coef[c].w : 1.0));
@@ -415,7 +438,7 @@ static int launch_tc_epi(const CUtensorMap& ma, const CUtensorMap& mb, const TcC
     B200_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, KC, STAGES, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = smem;
   }
-  conv_gemm_tc_kernel<BN, KC, STAGES, EPI><<<grid, 192, smem, st>>>(ma, mb, p);
+  conv_gemm_tc_kernel<BN, KC, STAGES, EPI><<<grid, kTcThreads, smem, st>>>(ma, mb, p);
   B200_LAUNCH_CHECK("conv_gemm_tc_kernel");
   return 0;
 }

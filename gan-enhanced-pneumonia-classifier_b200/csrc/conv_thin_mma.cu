@@ -392,12 +392,16 @@ bool thin_setup(ThinArgs* a, const b200gan_view* fine, const b200gan_view* fine_
   return true;
 }
 
-template <typename K>
-int launch_thin(K kernel, const ThinArgs& a, size_t smem, int ctas_per_sm, cudaStream_t st, const char* name) {
-  B200_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+template <void (*Kernel)(const ThinArgs)>
+int launch_thin(const ThinArgs& a, size_t smem, int ctas_per_sm, cudaStream_t st, const char* name) {
+  static size_t configured = 0;            // one instance per kernel (the kernel is a template argument)
+  if (configured < smem) {
+    B200_CUDA(cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
   int grid = ctas_per_sm * kNumSMs;
   if (grid > a.num_tiles) grid = a.num_tiles;
-  kernel<<<grid, 256, smem, st>>>(a);
+  Kernel<<<grid, 256, smem, st>>>(a);
   B200_LAUNCH_CHECK(name);
   return 0;
 }
@@ -414,8 +418,8 @@ int thin_down(const b200gan_view* fine, const b200gan_view* fine_ref, int fine_a
   if (!thin_setup(&a, fine, fine_ref, fine_act, coarse, nullptr, B200GAN_ACT_NONE, slope)) return 1;
   a.w = w; a.out_act = out_act;
   const size_t smem = (size_t)fine->c * (2 * a.R + 2) * (2 * a.W + 2) * 2;
-  if (fine->c == 1) return launch_thin(thin_down_mma_kernel<1>, a, smem, 6, st, "thin_down_mma_kernel");
-  return launch_thin(thin_down_mma_kernel<3>, a, smem, 4, st, "thin_down_mma_kernel");
+  if (fine->c == 1) return launch_thin<thin_down_mma_kernel<1>>(a, smem, 6, st, "thin_down_mma_kernel");
+  return launch_thin<thin_down_mma_kernel<3>>(a, smem, 4, st, "thin_down_mma_kernel");
 }
 
 // coarse (gathered; optionally multiplied by act'(coarse_ref)) -> fine = out_act(transposed conv)
@@ -427,8 +431,8 @@ int thin_up(const b200gan_view* coarse, const b200gan_view* coarse_ref, int coar
   a.w = w; a.out_act = out_act;
   const int NT = (4 * fine->c + 7) / 8;
   const size_t smem = (size_t)18 * NT * 32 * 8 + (size_t)(a.R + 2) * (a.W + 2) * CP * 2;
-  if (fine->c == 1) return launch_thin(thin_up_mma_kernel<1>, a, smem, 2, st, "thin_up_mma_kernel");
-  return launch_thin(thin_up_mma_kernel<3>, a, smem, 2, st, "thin_up_mma_kernel");
+  if (fine->c == 1) return launch_thin<thin_up_mma_kernel<1>>(a, smem, 2, st, "thin_up_mma_kernel");
+  return launch_thin<thin_up_mma_kernel<3>>(a, smem, 2, st, "thin_up_mma_kernel");
 }
 
 // dw (32, nc, 4, 4) fp32 += coarse^T x im2col(fine); either operand may carry the fused activation backward
@@ -438,8 +442,8 @@ int thin_wgrad(const b200gan_view* fine, const b200gan_view* fine_ref, int fine_
   if (!thin_setup(&a, fine, fine_ref, fine_act, coarse, coarse_ref, coarse_act, slope)) return 1;
   a.dw = dw;
   const size_t smem = (size_t)512 * fine->c * 4 + (size_t)a.R * a.W * CP * 2 + (size_t)fine->c * (2 * a.R + 2) * (2 * a.W + 2) * 2;
-  if (fine->c == 1) return launch_thin(thin_wgrad_mma_kernel<1>, a, smem, 2, st, "thin_wgrad_mma_kernel");
-  return launch_thin(thin_wgrad_mma_kernel<3>, a, smem, 2, st, "thin_wgrad_mma_kernel");
+  if (fine->c == 1) return launch_thin<thin_wgrad_mma_kernel<1>>(a, smem, 2, st, "thin_wgrad_mma_kernel");
+  return launch_thin<thin_wgrad_mma_kernel<3>>(a, smem, 2, st, "thin_wgrad_mma_kernel");
 }
 
 }  // namespace b200gan

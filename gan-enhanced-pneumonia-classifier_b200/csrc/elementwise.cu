@@ -167,6 +167,7 @@ struct ReduceDenseArgs {
   const float *scale, *shift, *mean, *invstd;
   int act; float slope;
   double* sums;
+  void* dz_out;        // MODE 1 only: when non-NULL, dz is also stored here (may alias da) and the sums are those of the stored dz
 };
 
 // thread = (vector lane vl over C/V, pixel row pr); block-level smem reduction, one double atomic per channel per block
@@ -203,7 +204,16 @@ __global__ void __launch_bounds__(256) channel_reduce_dense_kernel(ReduceDenseAr
 #pragma unroll
         for (int j = 0; j < V; ++j) {
           const float z = fmaf(yv[j], sc[j], sh[j]);
-          const float dz = d[j] * act_grad(z, a ? av[j] : 0.f, g.act, g.slope);
+          d[j] *= act_grad(z, a ? av[j] : 0.f, g.act, g.slope);
+        }
+        if (g.dz_out) {
+          T* o = reinterpret_cast<T*>(g.dz_out) + p * C + c0;
+          Vec<T>::store(o, d);
+          Vec<T>::load(o, d);          // the value as stored (bf16 rounding)
+        }
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+          const float dz = d[j];
           s0[j] += dz;
           s1[j] = fmaf(dz, (yv[j] - mu[j]) * is[j], s1[j]);
         }
@@ -343,9 +353,11 @@ int ew_bn_stats(const b200gan_view* y, double* sums, cudaStream_t st) {
   return 0;
 }
 
+// dz_out (optional): dense fast path only -- dz is stored there (may alias da); returns 2 instead of 0 when it was NOT written
+// (generic strided path), so that the caller runs the in-place pass.
 int ew_bn_bwd_reduce(const b200gan_view* da, const b200gan_view* y, const b200gan_view* a, const float* scale,
                      const float* shift, const float* mean, const float* invstd, int act, float slope, double* sums,
-                     cudaStream_t st) {
+                     const b200gan_view* dz_out, cudaStream_t st) {
   B200_CHECK_ARG(y->c <= 1024, "bn_act_bwd_reduce: at most 1024 channels (got %d)", y->c);
   B200_CHECK_ARG(da->dtype == y->dtype && (!a || a->dtype == y->dtype), "bn_act_bwd_reduce: mixed dtypes");
   ReduceArgs g{};
@@ -355,11 +367,13 @@ int ew_bn_bwd_reduce(const b200gan_view* da, const b200gan_view* y, const b200ga
   reduce_geometry(y->c, &g.lanes_c, &g.rows);
   B200_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * y->c, st));
   const int64_t P = (int64_t)y->n * y->h * y->w;
-  if (dense_nhwc(da) && (!a || dense_nhwc(a)) &&
+  void* dzp = (dz_out && dense_nhwc(dz_out) && dz_out->dtype == y->dtype) ? dz_out->ptr : nullptr;
+  if (dense_nhwc(da) && (!a || dense_nhwc(a)) && (!dz_out || dzp) &&
       ((y->dtype == B200GAN_F32 && reduce_dense_ok<float>(y)) || (y->dtype == B200GAN_BF16 && reduce_dense_ok<__nv_bfloat16>(y)))) {
     ReduceDenseArgs d{};
     d.y = y->ptr; d.da = da->ptr; d.a = a ? a->ptr : nullptr; d.P = P; d.C = y->c; d.sums = sums;
     d.scale = scale; d.shift = shift; d.mean = mean; d.invstd = invstd; d.act = act; d.slope = slope;
+    d.dz_out = dzp;
     const int V = y->dtype == B200GAN_F32 ? 4 : 8;
     const int rows = 256 / (y->c / V);
     int64_t nb = (P + (int64_t)rows * 32 - 1) / ((int64_t)rows * 32);
@@ -376,7 +390,7 @@ int ew_bn_bwd_reduce(const b200gan_view* da, const b200gan_view* y, const b200ga
   if (y->dtype == B200GAN_F32) channel_reduce_kernel<float, 1><<<(unsigned)blocks, 256, 0, st>>>(g);
   else channel_reduce_kernel<__nv_bfloat16, 1><<<(unsigned)blocks, 256, 0, st>>>(g);
   B200_LAUNCH_CHECK("bn_act_bwd_reduce");
-  return 0;
+  return dz_out ? 2 : 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -636,7 +650,21 @@ __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, 
 
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                    float* __restrict__ v, int64_t n, float one_m_b1, float b2, float one_m_b2,
-                                                   float step_size, float bc2_sqrt, float eps, float gscale, int vec_ok) {
+                                                   float step_size, float bc2_sqrt, float eps, float gscale, int vec_ok,
+                                                   const int64_t* __restrict__ step_dev, double lr, double b1, double b2d) {
+  if (step_dev) {
+    // step count held on the device (CUDA-graph replay: nothing about the step may be baked into the launch parameters);
+    // same double-precision bias corrections as the host path below
+    __shared__ float sh[2];
+    if (threadIdx.x == 0) {
+      const double t = (double)*step_dev;
+      sh[0] = (float)(lr / (1.0 - pow(b1, t)));
+      sh[1] = (float)sqrt(1.0 - pow(b2d, t));
+    }
+    __syncthreads();
+    step_size = sh[0];
+    bc2_sqrt = sh[1];
+  }
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
   const int64_t n4 = vec_ok ? n / 4 : 0;
   for (int64_t i = tid; i < n4; i += nth) {
@@ -658,12 +686,12 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
 }
 
 int ew_adam(float* p, const float* g, float* m, float* v, int64_t n, double lr, double b1, double b2, double eps, int step,
-            float gscale, cudaStream_t st) {
+            const int64_t* step_dev, float gscale, cudaStream_t st) {
   const double bc1 = 1.0 - pow(b1, (double)step), bc2 = 1.0 - pow(b2, (double)step);
   const float step_size = (float)(lr / bc1), bc2_sqrt = (float)sqrt(bc2);
   const int vec_ok = ((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0) ? 1 : 0;
   adam_kernel<<<ew_blocks(n / 4 + 1), 256, 0, st>>>(p, g, m, v, n, (float)(1.0 - b1), (float)b2, (float)(1.0 - b2), step_size, bc2_sqrt,
-                                                    (float)eps, gscale, vec_ok);
+                                                    (float)eps, gscale, vec_ok, step_dev, lr, b1, b2);
   B200_LAUNCH_CHECK("adam");
   return 0;
 }

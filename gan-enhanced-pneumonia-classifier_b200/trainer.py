@@ -10,14 +10,17 @@ but (a) every op is a libb200gan.so kernel launched on the current stream with n
 parameters are re-pointed into them, so `state_dict()`/checkpoints are unaffected) and the optimizer is one
 fused multi-tensor launch per network, (c) Sigmoid + BCE + their backward are one kernel, (d) the dead
 D-weight-gradient work of the G step (its result is discarded by `netD.zero_grad()` at train_gan.py:122) is
-skipped, (e) the five per-iteration history scalars are left on the device in a (5,) tensor, and (f) under
+skipped, (e) the five per-iteration history scalars are left on the device in a (5,) tensor, (f) under
 data parallelism the two gradient arenas are all-reduced over NCCL (sum, then scaled by 1/world inside the Adam
 kernel) -- the reference has no multi-GPU path; semantics are "mean of per-rank gradients", BatchNorm
-statistics stay local to each rank.
+statistics stay local to each rank -- and (g) the whole iteration (about 150 kernel launches)
+is captured once per input shape into a CUDA graph and replayed: the Adam step counts and BatchNorm's
+num_batches_tracked advance on the device, so nothing about the iteration is baked into the captured launches.
 """
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional
 
 import torch
@@ -52,12 +55,17 @@ class _Arena:
                 view.copy_(p.data)
                 p.data = view                          # the module now reads/writes the arena
                 self.grads.append(self.grad[off:off + s].view(p.shape))
-        self.step = 0
+        self.step = 0                                                    # host mirror of step_dev
+        self.step_dev = torch.zeros(1, device=dev, dtype=torch.int64)   # read by the Adam kernel (graph-replay safe)
+
+
+class _Captured:
+    __slots__ = ('graph', 'real', 'noise', 'out', 'launches')
 
 
 class DCGANTrainer:
     def __init__(self, netG, netD, lr: float = 2e-4, beta1: float = 0.5, beta2: float = 0.999, eps: float = 1e-8,
-                 dtype: Optional[torch.dtype] = None, algo: Optional[int] = None, process_group=None):
+                 dtype: Optional[torch.dtype] = None, algo: Optional[int] = None, process_group=None, use_graph: Optional[bool] = None):
         dtype = dtype or E.default_compute_dtype()
         algo = E.default_algo() if algo is None else algo
         self.netG, self.netD = netG, netD
@@ -72,12 +80,19 @@ class DCGANTrainer:
         if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
             self.world = torch.distributed.get_world_size(process_group)
         self.extra_launches = 0
+        if use_graph is None:
+            use_graph = os.environ.get('B200GAN_GRAPH', '1') != '0'
+        self.use_graph = use_graph
+        self._graphs = {}
+        self._warm = set()
+        self._static_in = {}
+        self._replayed_launches = 0
 
     # ------------------------------------------------------------------------------------------------
     @property
     def launches(self):
-        """Number of libb200gan kernels launched so far (bench.py's gpu_launches claim)."""
-        return self.engG.launches + self.engD.launches + self.extra_launches
+        """Number of kernel-launching libb200gan calls made so far, replayed graph nodes included (bench.py's gpu_launches claim)."""
+        return self.engG.launches + self.engD.launches + self.extra_launches + self._replayed_launches
 
     def _bce(self, logits, target, want_grad=True):
         n = logits.t.shape[0]
@@ -89,11 +104,11 @@ class DCGANTrainer:
         return out2, (E.Act(dl, nchw=False) if want_grad else None)
 
     def _adam(self, arena):
-        arena.step += 1
+        arena.step_dev.add_(1)                   # device-side step count (a captured node under graph replay)
         if self.world > 1:
             torch.distributed.all_reduce(arena.grad, group=self.pg)
         L.call('b200gan_adam', L.ptr(arena.param), L.ptr(arena.grad), L.ptr(arena.exp_avg), L.ptr(arena.exp_avg_sq),
-               arena.numel, self.lr, self.beta1, self.beta2, self.eps, arena.step, 1.0 / self.world, L.stream_ptr())
+               arena.numel, self.lr, self.beta1, self.beta2, self.eps, 0, L.ptr(arena.step_dev), 1.0 / self.world, L.stream_ptr())
         self.extra_launches += 1
 
     def _as_input(self, t):
@@ -104,10 +119,63 @@ class DCGANTrainer:
             t = t.float()
         return E.Act(t, nchw=True)
 
-    def step(self, real: torch.Tensor, noise: torch.Tensor) -> torch.Tensor:
-        """One adversarial iteration.  Returns a (5,) float32 CUDA tensor
-        [errD, errG, D_x, D_G_z1, D_G_z2] (the history scalars of train_gan.py:153-157), not synchronised."""
+    def step(self, real: torch.Tensor, noise: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """One adversarial iteration.  `noise` (N, nz, 1, 1) defaults to torch.randn on the device (train_gan.py:132).
+        Returns a (5,) float32 CUDA tensor [errD, errG, D_x, D_G_z1, D_G_z2] (the history scalars of
+        train_gan.py:153-157), not synchronised.  The first call for an input shape runs kernel by kernel; the second
+        captures the iteration into a CUDA graph; later calls replay it."""
+        self.arenaD.step += 1
+        self.arenaG.step += 1
+        if not self.use_graph:
+            return self._step_eager(real, noise)
+        key = (tuple(real.shape), real.dtype, None if noise is None else (tuple(noise.shape), noise.dtype))
+        if key not in self._warm:
+            # lazy one-time initialisation (function attributes, driver entry points) must not happen under capture
+            self._warm.add(key)
+            return self._step_eager(real, noise)
+        cap = self._graphs.get(key)
+        if cap is None:
+            cap = self._capture(real, noise, key)
+        if real.data_ptr() != cap.real.data_ptr():
+            cap.real.copy_(real)
+        if noise is not None and noise.data_ptr() != cap.noise.data_ptr():
+            cap.noise.copy_(noise)
+        cap.graph.replay()
+        self._replayed_launches += cap.launches
+        return cap.out.clone()
+
+    def input_buffers(self, real_shape, real_dtype=torch.float32, noise_shape=None):
+        """The static input tensors of the captured iteration for this shape (created on first use): filling them directly
+        (e.g. with a non-blocking H2D copy) and passing them to `step` avoids the device-to-device staging copy."""
+        key = (tuple(real_shape), real_dtype, None if noise_shape is None else (tuple(noise_shape), torch.float32))
+        bufs = self._static_in
+        if key not in bufs:
+            dev = self.arenaG.param.device
+            bufs[key] = (torch.zeros(real_shape, device=dev, dtype=real_dtype),
+                         None if noise_shape is None else torch.zeros(noise_shape, device=dev, dtype=torch.float32))
+        return bufs[key]
+
+    def _capture(self, real, noise, key):
+        cap = _Captured()
+        cap.real, cap.noise = self.input_buffers(real.shape, real.dtype, None if noise is None else noise.shape)
+        cap.real.copy_(real)
+        if noise is not None:
+            cap.noise.copy_(noise)
+        l0 = self.engG.launches + self.engD.launches + self.extra_launches
+        torch.cuda.synchronize()
+        cap.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(cap.graph):
+            cap.out = self._step_eager(cap.real, cap.noise)
+        cap.launches = self.engG.launches + self.engD.launches + self.extra_launches - l0
+        # capture records, it does not execute: take the recorded launches back out of the eager counters
+        self.extra_launches -= cap.launches
+        self._graphs[key] = cap
+        return cap
+
+    def _step_eager(self, real: torch.Tensor, noise: Optional[torch.Tensor]) -> torch.Tensor:
         netG, netD = self.netG, self.netD
+        if noise is None:
+            noise = torch.randn((real.shape[0], self.engG.specs[0].cin, 1, 1), device=real.device, dtype=torch.float32)
         pG = E.params_from_module(netG, self.engG.specs)
         pD = E.params_from_module(netD, self.engD.specs)
         # (1) D step ------------------------------------------------------------- train_gan.py:122-141

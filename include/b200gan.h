@@ -182,9 +182,11 @@ int b200gan_bce_sigmoid(const float* logit, int32_t batch, float target, float g
 /* ---- torch.optim.Adam (train_gan.py:94-95,141,150) over one flat fp32 arena: lr, betas, eps, no weight
  *      decay, no amsgrad; `step` is the 1-based step count of this update.  grad_scale multiplies the
  *      gradient first (1/world_size for data-parallel sums).  Hyper-parameters are doubles, as torch holds them
- *      (Python floats): `1 - beta2` is formed in double and rounded once, exactly like torch's scalar handling. */
+ *      (Python floats): `1 - beta2` is formed in double and rounded once, exactly like torch's scalar handling.
+ *      step_dev (optional): DEVICE address of the int64 step count; when given it overrides `step`, so that the launch can be
+ *      replayed from a CUDA graph while the count advances on the device. */
 int b200gan_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t numel, double lr,
-                 double beta1, double beta2, double eps, int32_t step, float grad_scale, void* stream);
+                 double beta1, double beta2, double eps, int32_t step, const int64_t* step_dev, float grad_scale, void* stream);
 
 /* ---- layout plumbing: dst(n,h,w,c) = (dst dtype) src(n,h,w,c) for two views of equal extents. */
 int b200gan_copy_view(const b200gan_view* src, const b200gan_view* dst, void* stream);

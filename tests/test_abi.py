@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol():
 def test_bad_arguments_fail_loudly_without_a_gpu():
     # argument validation happens before any CUDA call, so it is testable on the CPU box
     with pytest.raises(L.B200GanError, match='bad argument'):
-        L.call('b200gan_adam', None, None, None, None, 0, 1e-3, 0.5, 0.999, 1e-8, 1, 1.0, None)
+        L.call('b200gan_adam', None, None, None, None, 0, 1e-3, 0.5, 0.999, 1e-8, 1, None, 1.0, None)
     v = L.View(0, 0, 1, 1, 1, 1, 1, 1, 1, 1)
     with pytest.raises(L.B200GanError, match='null view'):
         L.call('b200gan_bn_stats', ctypes.byref(v), None, None)

@@ -216,7 +216,7 @@ def test_adam_matches_torch_formula(numel):
         g = (rng.randn(numel) * 10.0 ** rng.randint(-6, 1, numel)).astype(np.float32)
         orc.adam_step(po, g, m, v, step, 2e-4, 0.5)
         gdev = dev(g)
-        L.call('b200gan_adam', L.ptr(pd), L.ptr(gdev), L.ptr(md), L.ptr(vd), numel, 2e-4, 0.5, 0.999, 1e-8, step, 1.0, st())
+        L.call('b200gan_adam', L.ptr(pd), L.ptr(gdev), L.ptr(md), L.ptr(vd), numel, 2e-4, 0.5, 0.999, 1e-8, step, None, 1.0, st())
         close(pd.cpu().numpy(), po, rtol=1e-6, atol=1e-7, what=f'param step {step}')
         close(md.cpu().numpy(), m, rtol=1e-5, atol=1e-12, what='exp_avg')
         close(vd.cpu().numpy(), v, rtol=1e-5, atol=1e-20, what='exp_avg_sq')

@@ -159,3 +159,34 @@ def test_state_dict_roundtrip_eval_forward_and_vis_side_effects():
     ref_eval, _ = oracle.forward(z.cpu().numpy(), train=False)
     close(out_eval.cpu().numpy(), ref_eval, rtol=1e-4, atol=1e-5, what='eval forward')
     assert int(G.main[1].num_batches_tracked) == 1        # eval does not touch the buffers
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_graph_replay_matches_kernel_by_kernel(dtype):
+    """DCGANTrainer.step replayed from its CUDA graph (third call onwards) against the same trainer launching kernel by kernel:
+    losses, BatchNorm buffers, num_batches_tracked and the Adam step count must advance identically (the step count and the
+    BatchNorm counters live on the device precisely so that replay is exact)."""
+    from gan_enhanced_pneumonia_classifier_b200.trainer import DCGANTrainer
+    m = dict(seed=3, nz=16, nc=1, fm=8)
+    real = torch.from_numpy(synthetic_real(5, 4, 1)).cuda()
+    noises = [torch.from_numpy(synthetic_noise(10 + i, 4, 16)).cuda() for i in range(5)]
+    hist, nets = {}, {}
+    for mode in (False, True):
+        G, D = build(m, dtype)
+        tr = DCGANTrainer(G, D, dtype=dtype, use_graph=mode)
+        hist[mode] = torch.stack([tr.step(real, z) for z in noises]).cpu().numpy()
+        nets[mode] = (G, D, tr)
+    assert len(nets[True][2]._graphs) == 1 and nets[True][2].launches == nets[False][2].launches
+    tol = dict(rtol=1e-4, atol=1e-5) if dtype == torch.float32 else dict(rtol=2e-2, atol=2e-3)
+    close(hist[True], hist[False], what='history scalars, graph vs eager', **tol)
+    for a, b in zip(nets[True][:2], nets[False][:2]):
+        sa, sb = a.state_dict(), b.state_dict()
+        for k in sa:
+            if k.endswith('num_batches_tracked'):
+                assert int(sa[k]) == int(sb[k]), k
+            elif 'running' in k:
+                close(sa[k].cpu().numpy(), sb[k].cpu().numpy(), what=k, **tol)
+            else:
+                weights_close(sa[k].cpu().numpy(), sb[k].cpu().numpy(), what=k, steps=5, rtol=tol['rtol'], atol=max(tol['atol'], 2e-6),
+                              frac=0.98 if dtype == torch.float32 else 0.9)
+    assert int(nets[True][2].arenaD.step_dev) == 5 and int(nets[True][2].arenaG.step_dev) == 5
