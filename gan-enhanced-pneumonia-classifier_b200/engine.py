@@ -248,11 +248,12 @@ class NetEngine:
 
     # -- backward ----------------------------------------------------------------------------------
     def backward(self, ctxs: List[LayerCtx], params: List[LayerParams], dout: Optional[Act], grads: List[Optional[torch.Tensor]],
-                 dinput: Optional[Act] = None, need_wgrad: bool = True, dlogit: Optional[Act] = None):
+                 dinput: Optional[Act] = None, need_wgrad: bool = True, dlogit: Optional[Act] = None, on_ready=None):
         """`dout`: gradient w.r.t. the final activation (or `dlogit`: w.r.t. the last conv output, when the
         loss kernel already applied Sigmoid').  `grads` is the flat list over `param_order()` of fp32 tensors
         that are ACCUMULATED into (autograd semantics); entries may be None to skip.  `dinput`, when given,
-        receives the gradient w.r.t. the network input.
+        receives the gradient w.r.t. the network input.  `on_ready(j)` is called as soon as the launches that finish the
+        gradient of parameter j (index into `param_order()`) have been issued (data-parallel bucket all-reduce, dp.py).
 
         Per layer, going down: the incoming gradient d is w.r.t. the layer's activation output.
           * BatchNorm layers: the input-gradient convolution of the layer ABOVE already applied the activation backward and
@@ -291,6 +292,9 @@ class NetEngine:
                 self.launches += 1
             if need_wgrad and grads[gi] is not None:
                 self._wgrad(i, lc.x, dy, grads[gi], st, fuse=L.fuse(**fuse_kw) if fuse_kw else None)
+            if need_wgrad and on_ready is not None:
+                for j in range(gi + nparam - 1, gi - 1, -1):
+                    on_ready(j)
             if i > 0:
                 below, lb = self.specs[i - 1], ctxs[i - 1]
                 if below.bn_idx is not None:

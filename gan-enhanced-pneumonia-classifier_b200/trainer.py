@@ -27,6 +27,7 @@ import torch
 
 from . import _lib as L
 from . import engine as E
+from .dp import GradBuckets
 
 REAL_LABEL = 0.9      # train_gan.py:92
 FAKE_LABEL = 0.0      # train_gan.py:93
@@ -49,6 +50,7 @@ class _Arena:
         self.exp_avg = torch.zeros(o, device=dev, dtype=torch.float32)
         self.exp_avg_sq = torch.zeros(o, device=dev, dtype=torch.float32)
         self.grads = []
+        self.slices = [(off, off + s) for off, s in zip(offs, sizes)]    # per parameter, in param_order()
         with torch.no_grad():
             for p, off, s in zip(params, offs, sizes):
                 view = self.param[off:off + s].view(p.shape)
@@ -80,6 +82,8 @@ class DCGANTrainer:
         if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
             self.world = torch.distributed.get_world_size(process_group)
         self.extra_launches = 0
+        self.bucketsD = GradBuckets(self.arenaD.grad, self.arenaD.slices, process_group)
+        self.bucketsG = GradBuckets(self.arenaG.grad, self.arenaG.slices, process_group)
         if use_graph is None:
             use_graph = os.environ.get('B200GAN_GRAPH', '1') != '0'
         self.use_graph = use_graph
@@ -103,10 +107,9 @@ class DCGANTrainer:
         self.extra_launches += 1
         return out2, (E.Act(dl, nchw=False) if want_grad else None)
 
-    def _adam(self, arena):
+    def _adam(self, arena, buckets):
         arena.step_dev.add_(1)                   # device-side step count (a captured node under graph replay)
-        if self.world > 1:
-            torch.distributed.all_reduce(arena.grad, group=self.pg)
+        buckets.finish()                         # every gradient bucket all-reduced (sum); 1/world is applied inside the kernel
         L.call('b200gan_adam', L.ptr(arena.param), L.ptr(arena.grad), L.ptr(arena.exp_avg), L.ptr(arena.exp_avg_sq),
                arena.numel, self.lr, self.beta1, self.beta2, self.eps, 0, L.ptr(arena.step_dev), 1.0 / self.world, L.stream_ptr())
         self.extra_launches += 1
@@ -187,9 +190,10 @@ class DCGANTrainer:
         fake, ctx_g = self.engG.forward(self._as_input(noise), pG, True, True)
         logit_f, ctx_f = self.engD.forward(fake, pD, True, True, last_act=False)
         m_fake, dl = self._bce(logit_f, FAKE_LABEL)
-        self.engD.backward(ctx_f, pD, None, self.arenaD.grads, dlogit=dl)
+        self.bucketsD.begin()                    # real + fake gradients have both accumulated once this backward has written them
+        self.engD.backward(ctx_f, pD, None, self.arenaD.grads, dlogit=dl, on_ready=self.bucketsD.ready)
         del ctx_f
-        self._adam(self.arenaD)
+        self._adam(self.arenaD, self.bucketsD)
         # (2) G step ------------------------------------------------------------- train_gan.py:144-150
         self.arenaG.grad.zero_()
         logit_g, ctx_d = self.engD.forward(fake, pD, True, True, last_act=False)
@@ -197,9 +201,10 @@ class DCGANTrainer:
         dfake = E.Act(torch.empty_like(fake.t), nchw=False)
         self.engD.backward(ctx_d, pD, None, [None] * len(self.arenaD.grads), dinput=dfake, need_wgrad=False, dlogit=dl)
         del ctx_d
-        self.engG.backward(ctx_g, pG, dfake, self.arenaG.grads)
+        self.bucketsG.begin()
+        self.engG.backward(ctx_g, pG, dfake, self.arenaG.grads, on_ready=self.bucketsG.ready)
         del ctx_g
-        self._adam(self.arenaG)
+        self._adam(self.arenaG, self.bucketsG)
         # errD = errD_real + errD_fake (train_gan.py:140); D_x, D_G_z1, D_G_z2 are mean probabilities
         return torch.stack([m_real[0] + m_fake[0], m_g[0], m_real[1], m_fake[1], m_g[1]])
 

@@ -385,6 +385,44 @@ def train_iteration(G, D, optG, optD, real, noise):
     }
 
 
+def train_iteration_dp(Gs, Ds, optGs, optDs, reals, noises):
+    """Data-parallel semantics of the B200 build (the reference itself is single-device): R emulated
+    ranks, each with its own replica (identical weights, LOCAL BatchNorm statistics and buffers) and its own shard
+    (reals[r], noises[r]).  Each optimizer update uses the MEAN over ranks of the per-rank gradients -- what an all-reduce
+    (sum) followed by a 1/R scaling delivers.  Returns the per-rank results of `train_iteration`'s bookkeeping plus the
+    averaged gradients."""
+    R = len(Gs)
+    dt = reals[0].dtype
+    out = [dict() for _ in range(R)]
+    gDs, caches = [], []
+    for r in range(R):
+        G, D = Gs[r], Ds[r]
+        p_real, c_real = D.probs(reals[r], train=True)
+        gD, _ = D.backward_from_probs(c_real, bce_bwd(p_real, REAL_LABEL), need_input_grad=False)
+        fake, c_g = G.forward(noises[r], train=True)
+        p_fake, c_fake = D.probs(fake, train=True)
+        g2, _ = D.backward_from_probs(c_fake, bce_bwd(p_fake, FAKE_LABEL), need_input_grad=False)
+        gDs.append(accumulate(gD, g2))
+        caches.append((fake, c_g))
+        out[r].update(errD=float(dt.type(bce_fwd(p_real, REAL_LABEL) + bce_fwd(p_fake, FAKE_LABEL))),
+                      D_x=float(p_real.mean(dtype=np.float64)), D_G_z1=float(p_fake.mean(dtype=np.float64)))
+    gD_mean = {k: (sum(g[k].astype(np.float64) for g in gDs) / R).astype(dt) for k in gDs[0]}
+    for r in range(R):
+        optDs[r].step(Ds[r].sd, gD_mean)
+    gGs = []
+    for r in range(R):
+        fake, c_g = caches[r]
+        p2, c2 = Ds[r].probs(fake, train=True)
+        _, dfake = Ds[r].backward_from_probs(c2, bce_bwd(p2, REAL_LABEL), need_input_grad=True)
+        gG, _ = Gs[r].backward(c_g, dfake, need_input_grad=False)
+        gGs.append(gG)
+        out[r].update(errG=float(bce_fwd(p2, REAL_LABEL)), D_G_z2=float(p2.mean(dtype=np.float64)))
+    gG_mean = {k: (sum(g[k].astype(np.float64) for g in gGs) / R).astype(dt) for k in gGs[0]}
+    for r in range(R):
+        optGs[r].step(Gs[r].sd, gG_mean)
+    return out, gD_mean, gG_mean
+
+
 def run_training(G, D, optG, optD, real_batches, noises, fixed_noise=None, save_interval=500):
     """train_gan.py:112-171 for one epoch over `real_batches`, including the train-mode visualisation
     forward (train_gan.py:166-169) that mutates G's BatchNorm buffers."""

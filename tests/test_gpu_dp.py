@@ -1,0 +1,83 @@
+"""Two-GPU data-parallel parity: DCGANTrainer on two NCCL ranks (one process per GPU, bucketed gradient all-reduce on a
+communication stream, graph replay) against the CPU oracle's DP emulation.  Needs two GPUs: skipped on a one-GPU box
+(run it with `gpurun --gpus 2 -- python -m pytest tests/test_gpu_dp.py -m gpu`)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+import dcgan_oracle as orc
+from parity_utils import close, synthetic_noise, synthetic_real, weights_close
+
+pytestmark = pytest.mark.gpu
+NZ, NC, FM, B, WORLD, STEPS = 16, 1, 8, 4, 2, 3
+
+
+def _state(seed=21):
+    rng = np.random.RandomState(seed)
+    return (orc.init_state(orc.generator_plan(NZ, NC, FM), True, rng), orc.init_state(orc.discriminator_plan(NC, FM), False, rng))
+
+
+def _shard(rank, it):
+    return synthetic_real(300 + 10 * it + rank, B, NC), synthetic_noise(400 + 10 * it + rank, B, NZ)
+
+
+def _worker(rank, port, out_dir, use_graph):
+    import torch.distributed as dist
+    import gan_enhanced_pneumonia_classifier_b200 as pkg
+    from gan_enhanced_pneumonia_classifier_b200.trainer import DCGANTrainer
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=WORLD, device_id=torch.device('cuda', rank))
+    try:
+        sdG, sdD = _state()
+        G, D = pkg.Generator(NZ, NC, FM), pkg.Discriminator(NC, FM)
+        G.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in sdG.items()})
+        D.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in sdD.items()})
+        tr = DCGANTrainer(G.cuda(), D.cuda(), dtype=torch.float32, use_graph=use_graph)
+        hist = []
+        for it in range(STEPS):
+            real, noise = _shard(rank, it)
+            hist.append(tr.step(torch.from_numpy(real).cuda(), torch.from_numpy(noise).cuda()).cpu().numpy())
+        np.savez(os.path.join(out_dir, f'rank{rank}.npz'), hist=np.stack(hist), collectives=tr.bucketsD.collectives + tr.bucketsG.collectives,
+                 **{f'G.{k}': v.cpu().numpy() for k, v in G.state_dict().items()}, **{f'D.{k}': v.cpu().numpy() for k, v in D.state_dict().items()})
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs')
+@pytest.mark.parametrize('use_graph', [False, True])
+def test_two_nccl_ranks_match_dp_emulation(tmp_path, use_graph):
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        port = s.getsockname()[1]
+    mp.start_processes(_worker, args=(port, str(tmp_path), use_graph), nprocs=WORLD, join=True, start_method='spawn')
+    sdG, sdD = _state()
+    Gs = [orc.GeneratorOracle(NZ, NC, FM, {k: v.copy() for k, v in sdG.items()}) for _ in range(WORLD)]
+    Ds = [orc.DiscriminatorOracle(NC, FM, {k: v.copy() for k, v in sdD.items()}) for _ in range(WORLD)]
+    oG = [orc.AdamOracle(orc.param_keys(g.plan), 2e-4, 0.5) for g in Gs]
+    oD = [orc.AdamOracle(orc.param_keys(d.plan), 2e-4, 0.5) for d in Ds]
+    ref_hist = [[] for _ in range(WORLD)]
+    for it in range(STEPS):
+        shards = [_shard(r, it) for r in range(WORLD)]
+        out, _, _ = orc.train_iteration_dp(Gs, Ds, oG, oD, [s[0] for s in shards], [s[1] for s in shards])
+        for r in range(WORLD):
+            ref_hist[r].append([out[r][k] for k in ('errD', 'errG', 'D_x', 'D_G_z1', 'D_G_z2')])
+    for r in range(WORLD):
+        got = np.load(os.path.join(str(tmp_path), f'rank{r}.npz'))
+        assert int(got['collectives']) > 0
+        close(got['hist'][0], np.array(ref_hist[r][0]), rtol=1e-4, atol=1e-6, what=f'rank {r} first-iteration history')
+        close(got['hist'], np.array(ref_hist[r]), rtol=5e-3, atol=1e-4, what=f'rank {r} history')
+        for tag, net in (('G', Gs[r]), ('D', Ds[r])):
+            for k, v in net.sd.items():
+                if k.endswith('num_batches_tracked'):
+                    assert int(got[f'{tag}.{k}']) == int(v)
+                elif 'running' in k:
+                    close(got[f'{tag}.{k}'], v, rtol=2e-3, atol=1e-4, what=f'rank {r} {tag}.{k}')
+                else:
+                    weights_close(got[f'{tag}.{k}'], v, what=f'rank {r} {tag}.{k}', steps=STEPS, rtol=2e-3, atol=5e-6, frac=0.97)
+    a, b = np.load(os.path.join(str(tmp_path), 'rank0.npz')), np.load(os.path.join(str(tmp_path), 'rank1.npz'))
+    assert np.array_equal(a['G.main.0.weight'], b['G.main.0.weight']), 'replicas must stay bit-identical on the weights'
