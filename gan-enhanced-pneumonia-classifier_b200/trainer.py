@@ -62,7 +62,7 @@ class _Arena:
 
 
 class _Captured:
-    __slots__ = ('graph', 'real', 'noise', 'out', 'launches')
+    __slots__ = ('graph', 'real', 'noise', 'out', 'launches')     # graph: [(CUDAGraph, exchange 'D'/'G'/None after it)]
 
 
 class DCGANTrainer:
@@ -107,9 +107,8 @@ class DCGANTrainer:
         self.extra_launches += 1
         return out2, (E.Act(dl, nchw=False) if want_grad else None)
 
-    def _adam(self, arena, buckets):
+    def _adam(self, arena):
         arena.step_dev.add_(1)                   # device-side step count (a captured node under graph replay)
-        buckets.finish()                         # every gradient bucket all-reduced (sum); 1/world is applied inside the kernel
         L.call('b200gan_adam', L.ptr(arena.param), L.ptr(arena.grad), L.ptr(arena.exp_avg), L.ptr(arena.exp_avg_sq),
                arena.numel, self.lr, self.beta1, self.beta2, self.eps, 0, L.ptr(arena.step_dev), 1.0 / self.world, L.stream_ptr())
         self.extra_launches += 1
@@ -126,7 +125,7 @@ class DCGANTrainer:
         """One adversarial iteration.  `noise` (N, nz, 1, 1) defaults to torch.randn on the device (train_gan.py:132).
         Returns a (5,) float32 CUDA tensor [errD, errG, D_x, D_G_z1, D_G_z2] (the history scalars of
         train_gan.py:153-157), not synchronised.  The first call for an input shape runs kernel by kernel; the second
-        captures the iteration into a CUDA graph; later calls replay it."""
+        captures the iteration into CUDA graph(s); later calls replay."""
         self.arenaD.step += 1
         self.arenaG.step += 1
         if not self.use_graph:
@@ -143,7 +142,10 @@ class DCGANTrainer:
             cap.real.copy_(real)
         if noise is not None and noise.data_ptr() != cap.noise.data_ptr():
             cap.noise.copy_(noise)
-        cap.graph.replay()
+        for graph, exchange in cap.graph:
+            graph.replay()
+            if exchange is not None:
+                self._exchange(exchange, overlap=False)
         self._replayed_launches += cap.launches
         return cap.out.clone()
 
@@ -158,7 +160,23 @@ class DCGANTrainer:
                          None if noise_shape is None else torch.zeros(noise_shape, device=dev, dtype=torch.float32))
         return bufs[key]
 
+    def _exchange(self, which: str, overlap: bool):
+        """Gradient exchange between ranks before the Adam update of network `which` ('D' or 'G'): sum over ranks (the 1/world
+        factor is applied inside the Adam kernel).  overlap=True: buckets were launched on the communication stream while
+        the backward pass ran (dp.GradBuckets), only the stragglers and the stream join remain; overlap=False (between
+        graph replays): one all-reduce of the whole arena on the current stream."""
+        if self.world == 1:
+            return
+        arena, buckets = (self.arenaD, self.bucketsD) if which == 'D' else (self.arenaG, self.bucketsG)
+        if overlap:
+            buckets.finish()
+        else:
+            torch.distributed.all_reduce(arena.grad, group=self.pg)
+
     def _capture(self, real, noise, key):
+        """Single GPU: the whole iteration is ONE graph.  Data parallel: the iteration is cut at the two gradient exchanges into
+        three graphs sharing one memory pool, and the NCCL all-reduces run between the replays (collectives are kept out of
+        the captures: capturing them together with the side-stream fork/join deadlocked NCCL 2.28 on this stack)."""
         cap = _Captured()
         cap.real, cap.noise = self.input_buffers(real.shape, real.dtype, None if noise is None else noise.shape)
         cap.real.copy_(real)
@@ -166,9 +184,23 @@ class DCGANTrainer:
             cap.noise.copy_(noise)
         l0 = self.engG.launches + self.engD.launches + self.extra_launches
         torch.cuda.synchronize()
-        cap.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(cap.graph):
-            cap.out = self._step_eager(cap.real, cap.noise)
+        gen = self._segments(cap.real, cap.noise, overlap=False)
+        cap.graph = []
+        pool = torch.cuda.graph_pool_handle()
+        done = False
+        while not done:
+            g = torch.cuda.CUDAGraph()
+            exchange = None
+            with torch.cuda.graph(g, pool=pool):
+                while True:
+                    try:
+                        exchange = next(gen)
+                    except StopIteration as e:
+                        cap.out, done, exchange = e.value, True, None
+                        break
+                    if self.world > 1:
+                        break                    # cut the graph here; the exchange runs between replays
+            cap.graph.append((g, exchange))
         cap.launches = self.engG.launches + self.engD.launches + self.extra_launches - l0
         # capture records, it does not execute: take the recorded launches back out of the eager counters
         self.extra_launches -= cap.launches
@@ -176,11 +208,23 @@ class DCGANTrainer:
         return cap
 
     def _step_eager(self, real: torch.Tensor, noise: Optional[torch.Tensor]) -> torch.Tensor:
+        gen = self._segments(real, noise, overlap=True)
+        while True:
+            try:
+                self._exchange(next(gen), overlap=True)
+            except StopIteration as e:
+                return e.value
+
+    def _segments(self, real: torch.Tensor, noise: Optional[torch.Tensor], overlap: bool):
+        """The iteration as a generator that yields 'D' / 'G' at the two points where the gradients of that network are complete
+        on this rank and must be exchanged before its Adam update; returns the history tensor."""
         netG, netD = self.netG, self.netD
         if noise is None:
             noise = torch.randn((real.shape[0], self.engG.specs[0].cin, 1, 1), device=real.device, dtype=torch.float32)
         pG = E.params_from_module(netG, self.engG.specs)
         pD = E.params_from_module(netD, self.engD.specs)
+        readyD = self.bucketsD.ready if (overlap and self.world > 1) else None
+        readyG = self.bucketsG.ready if (overlap and self.world > 1) else None
         # (1) D step ------------------------------------------------------------- train_gan.py:122-141
         self.arenaD.grad.zero_()
         logit_r, ctx_r = self.engD.forward(self._as_input(real), pD, True, True, last_act=False)
@@ -191,9 +235,10 @@ class DCGANTrainer:
         logit_f, ctx_f = self.engD.forward(fake, pD, True, True, last_act=False)
         m_fake, dl = self._bce(logit_f, FAKE_LABEL)
         self.bucketsD.begin()                    # real + fake gradients have both accumulated once this backward has written them
-        self.engD.backward(ctx_f, pD, None, self.arenaD.grads, dlogit=dl, on_ready=self.bucketsD.ready)
+        self.engD.backward(ctx_f, pD, None, self.arenaD.grads, dlogit=dl, on_ready=readyD)
         del ctx_f
-        self._adam(self.arenaD, self.bucketsD)
+        yield 'D'
+        self._adam(self.arenaD)
         # (2) G step ------------------------------------------------------------- train_gan.py:144-150
         self.arenaG.grad.zero_()
         logit_g, ctx_d = self.engD.forward(fake, pD, True, True, last_act=False)
@@ -202,9 +247,10 @@ class DCGANTrainer:
         self.engD.backward(ctx_d, pD, None, [None] * len(self.arenaD.grads), dinput=dfake, need_wgrad=False, dlogit=dl)
         del ctx_d
         self.bucketsG.begin()
-        self.engG.backward(ctx_g, pG, dfake, self.arenaG.grads, on_ready=self.bucketsG.ready)
+        self.engG.backward(ctx_g, pG, dfake, self.arenaG.grads, on_ready=readyG)
         del ctx_g
-        self._adam(self.arenaG, self.bucketsG)
+        yield 'G'
+        self._adam(self.arenaG)
         # errD = errD_real + errD_fake (train_gan.py:140); D_x, D_G_z1, D_G_z2 are mean probabilities
         return torch.stack([m_real[0] + m_fake[0], m_g[0], m_real[1], m_fake[1], m_g[1]])
 

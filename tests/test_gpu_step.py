@@ -178,7 +178,10 @@ def test_graph_replay_matches_kernel_by_kernel(dtype):
         nets[mode] = (G, D, tr)
     assert len(nets[True][2]._graphs) == 1 and nets[True][2].launches == nets[False][2].launches
     tol = dict(rtol=1e-4, atol=1e-5) if dtype == torch.float32 else dict(rtol=2e-2, atol=2e-3)
-    close(hist[True], hist[False], what='history scalars, graph vs eager', **tol)
+    # the second call is already a graph replay: tight on the first two iterations, trajectory-noise tolerance afterwards
+    # (fp32 atomics make two kernel-by-kernel runs differ by the same amount)
+    close(hist[True][:2], hist[False][:2], what='history scalars, graph vs eager (iterations 1-2)', **tol)
+    close(hist[True], hist[False], what='history scalars, graph vs eager', rtol=max(tol['rtol'], 5e-3), atol=max(tol['atol'], 1e-4))
     for a, b in zip(nets[True][:2], nets[False][:2]):
         sa, sb = a.state_dict(), b.state_dict()
         for k in sa:
@@ -192,3 +195,31 @@ def test_graph_replay_matches_kernel_by_kernel(dtype):
                 weights_close(sa[k].cpu().numpy(), sb[k].cpu().numpy(), what=k, steps=5, rtol=tol['rtol'], atol=max(tol['atol'], 2e-6),
                               frac=0.98 if dtype == torch.float32 else 0.9)
     assert int(nets[True][2].arenaD.step_dev) == 5 and int(nets[True][2].arenaG.step_dev) == 5
+
+
+def test_fused_trainer_matches_oracle_over_three_iterations():
+    """DCGANTrainer.step (fused BCE, skipped dead D-wgrad, flat arenas, fused Adam) against the oracle's train_iteration:
+    history scalars and every post-step tensor of both state_dicts, fp32 mode, three iterations."""
+    from gan_enhanced_pneumonia_classifier_b200.trainer import DCGANTrainer
+    m = dict(seed=21, nz=16, nc=1, fm=8)
+    G, D = build(m, torch.float32)
+    tr = DCGANTrainer(G, D, dtype=torch.float32, use_graph=False)
+    rng = np.random.RandomState(m['seed'])
+    sdG = orc.init_state(orc.generator_plan(16, 1, 8), True, rng)
+    sdD = orc.init_state(orc.discriminator_plan(1, 8), False, rng)
+    oG, oD = orc.GeneratorOracle(16, 1, 8, sdG), orc.DiscriminatorOracle(1, 8, sdD)
+    aG, aD = orc.AdamOracle(orc.param_keys(oG.plan), 2e-4, 0.5), orc.AdamOracle(orc.param_keys(oD.plan), 2e-4, 0.5)
+    for it in range(3):
+        real, noise = synthetic_real(300 + it, 4, 1), synthetic_noise(400 + it, 4, 16)
+        got = tr.step(torch.from_numpy(real).cuda(), torch.from_numpy(noise).cuda()).cpu().numpy()
+        r = orc.train_iteration(oG, oD, aG, aD, real, noise)
+        want = np.array([r[k] for k in ('errD', 'errG', 'D_x', 'D_G_z1', 'D_G_z2')])
+        close(got, want, what=f'history it{it}', **(dict(rtol=1e-4, atol=1e-6) if it == 0 else dict(rtol=2e-3, atol=1e-5)))
+    for tag, net, o in (('G', G, oG), ('D', D, oD)):
+        for k, v in net.state_dict().items():
+            if k.endswith('num_batches_tracked'):
+                assert int(v) == int(o.sd[k]), k
+            elif 'running' in k:
+                close(v.cpu().numpy(), o.sd[k], rtol=1e-3, atol=1e-5, what=k)
+            else:
+                weights_close(v.cpu().numpy(), o.sd[k], what=f'{tag}.{k}', steps=3, rtol=1e-3, atol=1e-5, frac=0.97)
