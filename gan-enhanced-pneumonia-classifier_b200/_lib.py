@@ -50,10 +50,10 @@ _vp, _i32, _i64, _f32, _f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_d
 PROTOTYPES = {
     'b200gan_conv2d_fprop': [_CP, _VP, _vp, _vp, _VP, _FP, _vp],
     'b200gan_conv2d_dgrad': [_CP, _VP, _vp, _vp, _VP, _FP, _vp],
-    'b200gan_conv2d_wgrad': [_CP, _VP, _VP, _vp, _FP, _vp],
+    'b200gan_conv2d_wgrad': [_CP, _VP, _VP, _vp, _vp, _FP, _vp],
     'b200gan_convT2d_fprop': [_CP, _VP, _vp, _vp, _VP, _FP, _vp],
     'b200gan_convT2d_dgrad': [_CP, _VP, _vp, _vp, _VP, _FP, _vp],
-    'b200gan_convT2d_wgrad': [_CP, _VP, _VP, _vp, _FP, _vp],
+    'b200gan_convT2d_wgrad': [_CP, _VP, _VP, _vp, _vp, _FP, _vp],
     'b200gan_pack_conv_weight': [_vp, _i32, _i32, _i32, _i32, _vp, _vp],
     'b200gan_bn_stats': [_VP, _vp, _vp],
     'b200gan_bn_finalize': [_vp, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _vp, _vp, _vp, _vp, _vp],

@@ -30,7 +30,7 @@ int simt_conv_wgrad(const b200gan_conv*, const b200gan_view* x, const b200gan_vi
 // tensor-core kernels (conv_tc.cu): return 1 when the problem does not qualify (caller falls back / errors)
 int tc_conv_fprop(const b200gan_conv*, const b200gan_view* x, const void* wpacked, const b200gan_view* y, const TcEpi&, cudaStream_t);
 int tc_conv_dgrad(const b200gan_conv*, const b200gan_view* dy, const void* wpacked, const b200gan_view* dx, const TcEpi&, cudaStream_t);
-int tc_conv_wgrad(const b200gan_conv*, const b200gan_view* x, const b200gan_view* dy, float* dw, cudaStream_t);
+int tc_conv_wgrad(const b200gan_conv*, const b200gan_view* x, const b200gan_view* dy, float* dw, float* workspace, cudaStream_t);
 int tc_pack_weight(const float* w, int Co, int Ci, int k, int form, void* out, cudaStream_t);
 // image-side layers on warp-level MMAs (conv_thin_mma.cu): same return convention
 int thin_down(const b200gan_view* fine, const b200gan_view* fine_ref, int fine_act, const float* w, const b200gan_view* coarse, int out_act,
@@ -93,7 +93,8 @@ static bool same_extent(const b200gan_view* a, const b200gan_view* b) { return a
 // The gradient operand of the call (for the dy_* fusion) is: DGRAD prim -> coarse, FPROP prim -> fine, WGRAD -> coarse for
 // Conv2d and fine for ConvTranspose2d.
 static int conv_dispatch(Prim prim, bool transposed, const b200gan_conv* cv, const b200gan_view* fine, const b200gan_view* coarse,
-                         const float* w, const void* wpacked, float* dw, const b200gan_fuse* fuse, void* stream, const char* what) {
+                         const float* w, const void* wpacked, float* dw, float* workspace, const b200gan_fuse* fuse, void* stream,
+                         const char* what) {
   int rc;
   if ((rc = check_conv(cv))) return rc;
   if ((rc = check_view(fine, what))) return rc;
@@ -156,7 +157,7 @@ static int conv_dispatch(Prim prim, bool transposed, const b200gan_conv* cv, con
       }
       if (prim == FPROP) t = tc_conv_fprop(cv, fine, wpacked, coarse, epi, st);
       else if (prim == DGRAD) t = tc_conv_dgrad(cv, coarse, wpacked, fine, epi, st);
-      else t = tc_conv_wgrad(cv, fine, coarse, dw, st);
+      else t = tc_conv_wgrad(cv, fine, coarse, dw, workspace, st);
       if (t < 0) return t;
       if (t == 0) { bn_sums = nullptr; prev = false; }
     }
@@ -223,29 +224,29 @@ int b200gan_device_info(int device, char* name, int* cc_major, int* cc_minor) {
 
 int b200gan_conv2d_fprop(const b200gan_conv* cv, const b200gan_view* x, const float* weight, const void* wpacked,
                          const b200gan_view* y, const b200gan_fuse* fuse, void* stream) {
-  return conv_dispatch(FPROP, false, cv, x, y, weight, wpacked, nullptr, fuse, stream, "conv2d_fprop");
+  return conv_dispatch(FPROP, false, cv, x, y, weight, wpacked, nullptr, nullptr, fuse, stream, "conv2d_fprop");
 }
 int b200gan_conv2d_dgrad(const b200gan_conv* cv, const b200gan_view* dy, const float* weight, const void* wpacked,
                          const b200gan_view* dx, const b200gan_fuse* fuse, void* stream) {
-  return conv_dispatch(DGRAD, false, cv, dx, dy, weight, wpacked, nullptr, fuse, stream, "conv2d_dgrad");
+  return conv_dispatch(DGRAD, false, cv, dx, dy, weight, wpacked, nullptr, nullptr, fuse, stream, "conv2d_dgrad");
 }
-int b200gan_conv2d_wgrad(const b200gan_conv* cv, const b200gan_view* x, const b200gan_view* dy, float* dweight, const b200gan_fuse* fuse,
-                         void* stream) {
-  return conv_dispatch(WGRAD, false, cv, x, dy, nullptr, nullptr, dweight, fuse, stream, "conv2d_wgrad");
+int b200gan_conv2d_wgrad(const b200gan_conv* cv, const b200gan_view* x, const b200gan_view* dy, float* dweight, float* workspace,
+                         const b200gan_fuse* fuse, void* stream) {
+  return conv_dispatch(WGRAD, false, cv, x, dy, nullptr, nullptr, dweight, workspace, fuse, stream, "conv2d_wgrad");
 }
 // ConvTranspose2d == the conv input-gradient on the same geometry: its input is the coarse side, its
 // output the fine side, and its weight (Cin_T, Cout_T, k, k) is the conv weight (Co, Ci, k, k).
 int b200gan_convT2d_fprop(const b200gan_conv* cv, const b200gan_view* x, const float* weight, const void* wpacked,
                           const b200gan_view* y, const b200gan_fuse* fuse, void* stream) {
-  return conv_dispatch(DGRAD, true, cv, y, x, weight, wpacked, nullptr, fuse, stream, "convT2d_fprop");
+  return conv_dispatch(DGRAD, true, cv, y, x, weight, wpacked, nullptr, nullptr, fuse, stream, "convT2d_fprop");
 }
 int b200gan_convT2d_dgrad(const b200gan_conv* cv, const b200gan_view* dy, const float* weight, const void* wpacked,
                           const b200gan_view* dx, const b200gan_fuse* fuse, void* stream) {
-  return conv_dispatch(FPROP, true, cv, dy, dx, weight, wpacked, nullptr, fuse, stream, "convT2d_dgrad");
+  return conv_dispatch(FPROP, true, cv, dy, dx, weight, wpacked, nullptr, nullptr, fuse, stream, "convT2d_dgrad");
 }
-int b200gan_convT2d_wgrad(const b200gan_conv* cv, const b200gan_view* x, const b200gan_view* dy, float* dweight, const b200gan_fuse* fuse,
-                          void* stream) {
-  return conv_dispatch(WGRAD, true, cv, dy, x, nullptr, nullptr, dweight, fuse, stream, "convT2d_wgrad");
+int b200gan_convT2d_wgrad(const b200gan_conv* cv, const b200gan_view* x, const b200gan_view* dy, float* dweight, float* workspace,
+                          const b200gan_fuse* fuse, void* stream) {
+  return conv_dispatch(WGRAD, true, cv, dy, x, nullptr, nullptr, dweight, workspace, fuse, stream, "convT2d_wgrad");
 }
 
 int b200gan_pack_conv_weight(const float* weight, int32_t co, int32_t ci, int32_t k, int32_t form, void* out, void* stream) {

@@ -556,70 +556,80 @@ int tc_conv_dgrad(const b200gan_conv* cv, const b200gan_view* dy, const void* wp
 // ---------------------------------------------------------------------------------------------------
 // weight gradient on tensor cores.  conv geometry: x (N,H,W,Ci) fine side, dy (N,OH,OW,Co) coarse side,
 //   dw[co,ci,kh,kw] += sum_{n,oh,ow} dy[n,oh,ow,co] * x[n,2oh-1+kh,2ow-1+kw,ci]
-// Per tap this is a GEMM D[co][ci] = A^T B with the PIXEL index as the reduction: both operands are
-// "MN-major" (channels contiguous), which tcgen05 reads directly from the NHWC tiles TMA delivers:
-//   A: 64 pixels x 128 co of dy  = two 4-d boxes {64ch, TW, TH, TN}            (reused by all taps of the CTA)
-//   B: 64 pixels x NCI ci of x at tap (kh,kw) = boxes {64ch, 2TW, 2TH, TN}, element strides {1,2,2,1}
-// A CTA owns 128 output channels x T taps x NCI input channels = 128 x 512 fp32 accumulators (all of TMEM),
-// walks a contiguous range of 64-pixel K-blocks (split-K over blockIdx.z) and adds its partial result into
-// the fp32 (Co,Ci,4,4) gradient with red.global.add.f32.
+// Per tap this is a GEMM with the PIXEL index as the reduction, so both operands are "MN-major" (channels contiguous),
+// which tcgen05 reads directly from the NHWC tiles TMA delivers (64 pixels per K-block, 4 MMAs of K = 16 pixels):
+//   A (M = 128): x at MT = 128/CIC taps side by side -- 4 taps x 32 channels, 2 taps x 64 channels or 1 tap x a 128-channel
+//                chunk: thin layers fill the 128 MMA rows with taps instead of wasting them -- boxes {<=64 ch, 2TW, 2TH, TN}
+//                with element strides {1,2,2,1};
+//   B (N = NCO): dy, NCO = 64/128/256 output channels, boxes {64 ch, TW, TH, TN}, loaded once per K-block and reused by the
+//                G accumulator groups (= G*MT taps) the CTA owns; G*NCO <= 512 TMEM columns.
+// A CTA walks a contiguous range of K-blocks (split-K over blockIdx.z).  Epilogue: TMEM lane = (tap, ci), column = co; with a
+// workspace in the K-major layout ws[co][tap][ci] the 32 lanes of a warp hit 32 consecutive floats, so every
+// red.global.add is one coalesced 128-byte transaction (the first version added straight into the (Co,Ci,4,4) master
+// layout: 32 scattered 4-byte atomics per instruction, ~45 us of epilogue per CTA); wgrad_finalize_kernel then transposes
+// the workspace into dw and clears it.
 // ---------------------------------------------------------------------------------------------------
 struct TcWgradParams {
   int tiles_w, tiles_h, tiles_n;
   int tw_log2, th_log2;
   int kb_total, kb_per_split;
-  int T;            // taps per CTA
-  int ci_groups;    // Ci / NCI
+  int tap_blocks, ci_chunks, co_chunks;     // blockIdx.x = (co chunk * ci_chunks + ci chunk) * tap_blocks + tap block
   int Co, Ci;
-  float* dw;
+  float* out;        // workspace ws[co][tap][ci] (ws_layout = 1) or the gradient dw[co][ci][tap] itself (ws_layout = 0)
+  int ws_layout;
 };
 
-template <int NCI>
+template <int CIC, int NCO, int G, int STAGES>
 struct TcWgradSmem {
-  static constexpr int BK = 64;                           // pixels per K-block
-  // B tiles are small for narrow layers: keep >= 64 KB of TMA loads in flight (latency-bound otherwise).
-  // The A slot ring is safe while STAGES <= (A_SLOTS - 1) * T with T = 512 / NCI taps per CTA.
-  static constexpr int A_SLOTS = 3, STAGES = NCI == 32 ? 16 : (NCI == 64 ? 12 : (NCI == 128 ? 8 : 4));
-  static constexpr int A_BYTES = BK * 128 * 2;            // 64 pixels x 128 co
-  static constexpr int B_BYTES = BK * NCI * 2;
-  static constexpr int TOTAL = A_SLOTS * A_BYTES + STAGES * B_BYTES + 1024 + 256;
+  static constexpr int BK = 64;                            // pixels per K-block
+  static constexpr int DY_SLOTS = 3;                       // safe while STAGES <= (DY_SLOTS - 1) * G
+  static constexpr int A_BYTES = BK * 128 * 2;             // one group: 64 pixels x 128 (tap, ci) rows
+  static constexpr int B_BYTES = BK * NCO * 2;
+  static constexpr int TOTAL = STAGES * A_BYTES + DY_SLOTS * B_BYTES + 1024 + 256;
+  static_assert(STAGES <= (DY_SLOTS - 1) * G, "dy slot ring too short for the A stage ring");
 };
 
-template <int NCI>
+template <int CIC, int NCO, int G, int STAGES>
 __global__ void __launch_bounds__(192, 1)
-conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x, const TcWgradParams p) {
-  using S = TcWgradSmem<NCI>;
-  constexpr int CB = NCI >= 64 ? 64 : NCI;                // channels per B box (128B or 64B rows)
-  constexpr int NBOX = NCI / CB;
+conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dy, const TcWgradParams p) {
+  using S = TcWgradSmem<CIC, NCO, G, STAGES>;
+  constexpr int MT = 128 / CIC;                            // taps per accumulator group
+  constexpr int ABOX = CIC >= 64 ? 64 : CIC;               // channels per x box (128B or 64B rows)
+  constexpr int A_NBOX = 128 / ABOX;                       // x boxes per group (taps x channel halves)
+  constexpr int A_ROW = ABOX * 2;                          // bytes per pixel row of an x box
+  constexpr int A_BOX_BYTES = S::BK * A_ROW;
+  constexpr uint32_t A_LT = ABOX == 64 ? 2u : 4u;          // SWIZZLE_128B : SWIZZLE_64B
+  constexpr int B_NBOX = NCO / 64;
+  constexpr uint32_t TMEM_COLS = G * NCO <= 256 ? 256 : 512;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + S::A_SLOTS * S::A_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + S::STAGES * S::B_BYTES);
-  uint64_t* empty_bar = full_bar + S::STAGES;
-  uint64_t* accum_bar = empty_bar + S::STAGES;
+  uint8_t* smem_b = smem + STAGES * S::A_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + S::DY_SLOTS * S::B_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* accum_bar = empty_bar + STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int co0 = blockIdx.x * 128;
-  const int tap_groups = 16 / p.T;
-  const int tg = blockIdx.y % tap_groups, cg = blockIdx.y / tap_groups;
-  const int tap0 = tg * p.T, ci0 = cg * NCI;
+  int u = blockIdx.x;
+  const int tap_block = u % p.tap_blocks; u /= p.tap_blocks;
+  const int ci_chunk = u % p.ci_chunks;
+  const int co_chunk = u / p.ci_chunks;
+  const int tap0 = tap_block * (G * MT), ci0 = ci_chunk * (CIC >= 128 ? 128 : CIC), co0 = co_chunk * NCO;
   const int kb_beg = blockIdx.z * p.kb_per_split;
   const int kb_end = min(kb_beg + p.kb_per_split, p.kb_total);
   const int nkb = kb_end - kb_beg;
-  const int steps = nkb * p.T;
   const int TW = 1 << p.tw_log2, TH = 1 << p.th_log2, TN = 64 >> (p.tw_log2 + p.th_log2);
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < S::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(accum_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_dy) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   tcgen05_fence_before();
@@ -633,76 +643,87 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_co
       int tw_i = t0 % p.tiles_w; t0 /= p.tiles_w;
       int th_i = t0 % p.tiles_h;
       int tn_i = t0 / p.tiles_h;
-      int s = 0, aslot = 0;
+      int s = 0, slot = 0;
       uint32_t ph = 0;
       for (int kbl = 0; kbl < nkb; ++kbl) {
         const int w0 = tw_i * TW, h0 = th_i * TH, n0 = tn_i * TN;
-        for (int tl = 0; tl < p.T; ++tl) {
+#pragma unroll 1
+        for (int g = 0; g < G; ++g) {
           mbar_wait(&empty_bar[s], ph ^ 1);
-          uint8_t* sb = smem_b + s * S::B_BYTES;
-          if (tl == 0) {
-            uint8_t* sa = smem_a + aslot * S::A_BYTES;
+          uint8_t* sa = smem_a + s * S::A_BYTES;
+          if (g == 0) {
+            uint8_t* sb = smem_b + slot * S::B_BYTES;
             mbar_expect_tx(&full_bar[s], S::A_BYTES + S::B_BYTES);
-            tma_load_4d(sa, &map_dy, &full_bar[s], co0, w0, h0, n0);
-            tma_load_4d(sa + S::A_BYTES / 2, &map_dy, &full_bar[s], co0 + 64, w0, h0, n0);
-          } else {
-            mbar_expect_tx(&full_bar[s], S::B_BYTES);
-          }
-          const int tap = tap0 + tl, kh = tap >> 2, kw = tap & 3;
 #pragma unroll
-          for (int b = 0; b < NBOX; ++b)
-            tma_load_4d(sb + b * (S::BK * CB * 2), &map_x, &full_bar[s], ci0 + b * CB, 2 * w0 - 1 + kw, 2 * h0 - 1 + kh, n0);
-          if (++s == S::STAGES) { s = 0; ph ^= 1; }
+            for (int b = 0; b < B_NBOX; ++b) tma_load_4d(sb + b * (S::BK * 128), &map_dy, &full_bar[s], co0 + b * 64, w0, h0, n0);
+          } else {
+            mbar_expect_tx(&full_bar[s], S::A_BYTES);
+          }
+#pragma unroll
+          for (int b = 0; b < A_NBOX; ++b) {
+            // box b of the group: tap (g*MT + b / boxes-per-tap), channel half (b % boxes-per-tap)
+            constexpr int BPT = A_NBOX / MT;                 // boxes per tap: 1 (CIC <= 64) or 2 (CIC = 128)
+            const int tap = tap0 + g * MT + b / BPT, kh = tap >> 2, kw = tap & 3;
+            tma_load_4d(sa + b * A_BOX_BYTES, &map_x, &full_bar[s], ci0 + (b % BPT) * 64, 2 * w0 - 1 + kw, 2 * h0 - 1 + kh, n0);
+          }
+          if (++s == STAGES) { s = 0; ph ^= 1; }
         }
-        if (++aslot == S::A_SLOTS) aslot = 0;
+        if (++slot == S::DY_SLOTS) slot = 0;
         if (++tw_i == p.tiles_w) { tw_i = 0; if (++th_i == p.tiles_h) { th_i = 0; ++tn_i; } }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(128, NCI, 1, 1);       // both operands MN-major
-      constexpr uint32_t B_LT = CB == 64 ? 2u : 4u;
-      constexpr uint32_t B_ROW = CB * 2;                                // bytes per pixel row of a B box
-      int s = 0, aslot = 0;
+      constexpr uint32_t idesc = make_idesc_bf16(128, NCO, 1, 1);       // both operands MN-major
+      int s = 0, slot = 0;
       uint32_t ph = 0;
       for (int kbl = 0; kbl < nkb; ++kbl) {
-        const uint32_t sa = smem_u32(smem_a + aslot * S::A_BYTES);
-        for (int tl = 0; tl < p.T; ++tl) {
+        const uint32_t sb = smem_u32(smem_b + slot * S::B_BYTES);
+#pragma unroll 1
+        for (int g = 0; g < G; ++g) {
           mbar_wait(&full_bar[s], ph);
           tcgen05_fence_after();
-          const uint32_t sb = smem_u32(smem_b + s * S::B_BYTES);
+          const uint32_t sa = smem_u32(smem_a + s * S::A_BYTES);
 #pragma unroll
           for (int k = 0; k < S::BK / 16; ++k) {
-            // MN-major canonical layout: LBO = distance between 64-channel groups, SBO = 8 pixel rows
-            const uint64_t adesc = make_smem_desc(sa + k * 16 * 128, S::A_BYTES / 2, 8 * 128, 2u);
-            const uint64_t bdesc = make_smem_desc(sb + k * 16 * B_ROW, S::BK * B_ROW, 8 * B_ROW, B_LT);
-            tcgen05_mma_f16(tmem_base + tl * NCI, adesc, bdesc, idesc, (kbl | k) != 0);
+            // MN-major canonical layout: LBO = distance between swizzle atoms along M/N (one TMA box), SBO = 8 pixel rows
+            const uint64_t adesc = make_smem_desc(sa + k * 16 * A_ROW, A_BOX_BYTES, 8 * A_ROW, A_LT);
+            const uint64_t bdesc = make_smem_desc(sb + k * 16 * 128, S::BK * 128, 8 * 128, 2u);
+            tcgen05_mma_f16(tmem_base + g * NCO, adesc, bdesc, idesc, (kbl | k) != 0);
           }
           tcgen05_commit(&empty_bar[s]);
-          if (++s == S::STAGES) { s = 0; ph ^= 1; }
+          if (++s == STAGES) { s = 0; ph ^= 1; }
         }
-        if (++aslot == S::A_SLOTS) aslot = 0;
+        if (++slot == S::DY_SLOTS) slot = 0;
       }
       tcgen05_commit(accum_bar);
     }
     __syncwarp();
   } else {
     const int q = warp & 3;
-    const int co = co0 + q * 32 + lane;
+    const int m = q * 32 + lane;                                        // accumulator row = (tap within group, channel)
+    const int t_in = m / (CIC >= 128 ? 128 : CIC), ci = ci0 + m % (CIC >= 128 ? 128 : CIC);
     mbar_wait(accum_bar, 0);
     tcgen05_fence_after();
-    if (steps > 0) {
+    if (nkb > 0) {
 #pragma unroll 1
-      for (int c0 = 0; c0 < p.T * NCI; c0 += 32) {
-        uint32_t r[32];
-        tcgen05_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + c0, r);
-        tcgen05_wait_ld();
-        if (co < p.Co) {
-          const int tl = c0 / NCI, cil = c0 - tl * NCI;
-          float* dst = p.dw + ((int64_t)co * p.Ci + ci0 + cil) * 16 + tap0 + tl;
+      for (int g = 0; g < G; ++g) {
+        const int tap = tap0 + g * MT + t_in;
+#pragma unroll 1
+        for (int c0 = 0; c0 < NCO; c0 += 32) {
+          uint32_t r[32];
+          tcgen05_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + g * NCO + c0, r);
+          tcgen05_wait_ld();
+          if (p.ws_layout) {
+            float* dst = p.out + ((int64_t)(co0 + c0) * 16 + tap) * p.Ci + ci;      // + j * 16 * Ci per column
 #pragma unroll
-          for (int j = 0; j < 32; ++j) atomicAdd(dst + j * 16, __uint_as_float(r[j]));
+            for (int j = 0; j < 32; ++j) atomicAdd(dst + (int64_t)j * 16 * p.Ci, __uint_as_float(r[j]));
+          } else {
+            float* dst = p.out + ((int64_t)(co0 + c0) * p.Ci + ci) * 16 + tap;      // + j * Ci * 16 per column
+#pragma unroll
+            for (int j = 0; j < 32; ++j) atomicAdd(dst + (int64_t)j * p.Ci * 16, __uint_as_float(r[j]));
+          }
         }
       }
     }
@@ -711,29 +732,50 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_co
   __syncthreads();
   if (warp == 1) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
   }
 }
 
-template <int NCI>
-static int launch_wgrad(const CUtensorMap& mdy, const CUtensorMap& mx, const TcWgradParams& p, dim3 grid, cudaStream_t st) {
-  using S = TcWgradSmem<NCI>;
+// dw[co][ci][tap] += ws[co][tap][ci]; ws = 0 (the workspace is handed back zeroed)
+__global__ void __launch_bounds__(256) wgrad_finalize_kernel(float* __restrict__ ws, float* __restrict__ dw, int Co, int Ci) {
+  __shared__ float t[16][33];
+  const int co = blockIdx.y, c0 = blockIdx.x * 32;
+  const int lane = threadIdx.x & 31, row = threadIdx.x >> 5;              // 8 rows of 32 lanes
+  for (int tap = row; tap < 16; tap += 8) {
+    float* src = ws + ((int64_t)co * 16 + tap) * Ci + c0 + lane;
+    t[tap][lane] = (c0 + lane < Ci) ? *src : 0.f;
+    if (c0 + lane < Ci) *src = 0.f;
+  }
+  __syncthreads();
+  // 32 channels x 16 taps = 512 consecutive floats of dw
+  for (int i = threadIdx.x; i < 512; i += 256) {
+    const int cil = i >> 4, tap = i & 15;
+    if (c0 + cil < Ci) dw[((int64_t)co * Ci + c0 + cil) * 16 + tap] += t[tap][cil];
+  }
+}
+
+template <int CIC, int NCO, int G, int STAGES>
+static int launch_wgrad(const CUtensorMap& mx, const CUtensorMap& mdy, const TcWgradParams& p, dim3 grid, cudaStream_t st) {
+  using S = TcWgradSmem<CIC, NCO, G, STAGES>;
   static bool configured = false;
   if (!configured) {
-    B200_CUDA(cudaFuncSetAttribute(conv_wgrad_tc_kernel<NCI>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    B200_CUDA(cudaFuncSetAttribute(conv_wgrad_tc_kernel<CIC, NCO, G, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     configured = true;
   }
-  conv_wgrad_tc_kernel<NCI><<<grid, 192, S::TOTAL, st>>>(mdy, mx, p);
+  conv_wgrad_tc_kernel<CIC, NCO, G, STAGES><<<grid, 192, S::TOTAL, st>>>(mx, mdy, p);
   B200_LAUNCH_CHECK("conv_wgrad_tc_kernel");
   return 0;
 }
 
-int tc_conv_wgrad(const b200gan_conv* cv, const b200gan_view* x, const b200gan_view* dy, float* dw, cudaStream_t st) {
+// workspace: NULL (direct, scattered atomics into dw) or Co*Ci*16 floats, all zero on entry and all zero again on return
+int tc_conv_wgrad(const b200gan_conv* cv, const b200gan_view* x, const b200gan_view* dy, float* dw, float* workspace, cudaStream_t st) {
   if (cv->k != 4 || cv->stride != 2 || cv->pad != 1) return 1;
   if (!nhwc_dense_bf16(x) || !nhwc_dense_bf16(dy)) return 1;
   const int Ci = x->c, Co = dy->c;
-  if (Co % 64 != 0 || (Ci != 32 && Ci != 64 && Ci != 128 && Ci % 256 != 0)) return 1;
-  const int NCI = Ci >= 256 ? 256 : Ci;
+  if (Co % 64 != 0 || (Ci != 32 && Ci != 64 && Ci % 128 != 0)) return 1;
+  const int CIC = Ci >= 128 ? 128 : Ci;
+  const int NCO = (CIC == 128 && Co % 256 == 0) ? 256 : ((CIC >= 64 && Co % 128 == 0) ? 128 : 64);
+  const int G = NCO == 256 ? 2 : 4, MT = 128 / CIC;
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return B200GAN_ERR_CUDA; }
   int TW = 1, TH = 1;
@@ -744,11 +786,12 @@ int tc_conv_wgrad(const b200gan_conv* cv, const b200gan_view* x, const b200gan_v
   p.tiles_w = dy->w / TW; p.tiles_h = dy->h / TH; p.tiles_n = (dy->n + TN - 1) / TN;
   p.tw_log2 = ilog2_exact(TW); p.th_log2 = ilog2_exact(TH);
   p.kb_total = p.tiles_w * p.tiles_h * p.tiles_n;
-  p.T = 512 / NCI;
-  p.ci_groups = Ci / NCI;
-  p.Co = Co; p.Ci = Ci; p.dw = dw;
-  const int out_tiles = ((Co + 127) / 128) * (16 / p.T) * p.ci_groups;
-  int splits = ((NCI <= 64 ? 1 : 2) * kNumSMs + out_tiles - 1) / out_tiles;   // each CTA owns all 512 TMEM columns of its SM
+  p.tap_blocks = 16 / (G * MT); p.ci_chunks = Ci / CIC; p.co_chunks = Co / NCO;
+  p.Co = Co; p.Ci = Ci;
+  p.out = workspace ? workspace : dw; p.ws_layout = workspace ? 1 : 0;
+  const int units = p.tap_blocks * p.ci_chunks * p.co_chunks;
+  const int ctas_per_sm = (G * NCO <= 256) ? 2 : 1;                      // TMEM columns (and shared memory) per CTA
+  int splits = (ctas_per_sm * kNumSMs + units - 1) / units;
   if (splits > p.kb_total) splits = p.kb_total;
   if (splits < 1) splits = 1;
   p.kb_per_split = (p.kb_total + splits - 1) / splits;
@@ -765,7 +808,7 @@ int tc_conv_wgrad(const b200gan_conv* cv, const b200gan_view* x, const b200gan_v
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(dy) failed: %d", (int)r); return B200GAN_ERR_CUDA; }
   }
   {
-    const int CB = NCI >= 64 ? 64 : NCI;
+    const int CB = CIC >= 64 ? 64 : CIC;
     cuuint64_t gdim[4] = {(cuuint64_t)Ci, (cuuint64_t)x->w, (cuuint64_t)x->h, (cuuint64_t)x->n};
     cuuint64_t gstr[3] = {(cuuint64_t)Ci * 2, (cuuint64_t)x->w * Ci * 2, (cuuint64_t)x->h * x->w * Ci * 2};
     cuuint32_t box[4] = {(cuuint32_t)CB, (cuuint32_t)(2 * TW), (cuuint32_t)(2 * TH), (cuuint32_t)TN};
@@ -775,13 +818,21 @@ int tc_conv_wgrad(const b200gan_conv* cv, const b200gan_view* x, const b200gan_v
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(x) failed: %d", (int)r); return B200GAN_ERR_CUDA; }
   }
-  dim3 grid((unsigned)((Co + 127) / 128), (unsigned)((16 / p.T) * p.ci_groups), (unsigned)splits);
-  switch (NCI) {
-    case 32: return launch_wgrad<32>(mdy, mx, p, grid, st);
-    case 64: return launch_wgrad<64>(mdy, mx, p, grid, st);
-    case 128: return launch_wgrad<128>(mdy, mx, p, grid, st);
-    default: return launch_wgrad<256>(mdy, mx, p, grid, st);
+  dim3 grid((unsigned)units, 1, (unsigned)splits);
+  int rc;
+  if (CIC == 32) rc = launch_wgrad<32, 64, 4, 4>(mx, mdy, p, grid, st);                 // 4 x 16 KB + 3 x 8 KB: two CTAs per SM
+  else if (CIC == 64 && NCO == 128) rc = launch_wgrad<64, 128, 4, 8>(mx, mdy, p, grid, st);
+  else if (CIC == 64) rc = launch_wgrad<64, 64, 4, 4>(mx, mdy, p, grid, st);
+  else if (NCO == 256) rc = launch_wgrad<128, 256, 2, 4>(mx, mdy, p, grid, st);
+  else if (NCO == 128) rc = launch_wgrad<128, 128, 4, 8>(mx, mdy, p, grid, st);
+  else rc = launch_wgrad<128, 64, 4, 4>(mx, mdy, p, grid, st);
+  if (rc) return rc;
+  if (workspace) {
+    dim3 fg((unsigned)((Ci + 31) / 32), (unsigned)Co);
+    wgrad_finalize_kernel<<<fg, 256, 0, st>>>(workspace, dw, Co, Ci);
+    B200_LAUNCH_CHECK("wgrad_finalize_kernel");
   }
+  return 0;
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -75,30 +75,48 @@ __device__ __forceinline__ void load4_rt(const View& v, int64_t off, int vec, fl
 
 // Stage fine rows [ih0, ih0+rows) of image n as bf16: S[(ci*rows + row)*pitch + s], s = iw + 1 in [0, IW+1]; s = 0 and
 // s = IW+1 (iw = -1, IW) and rows outside the image are the zero padding of the convolution.  IW % 4 == 0.
+// Loads are issued four deep per thread before anything is stored: the staging loops are what keeps HBM busy here
+// (each SM needs ~40 KB in flight), a one-load-at-a-time loop runs at a fifth of the bandwidth.
 template <int NC>
 __device__ __forceinline__ void stage_fine(__nv_bfloat16* S, int pitch, int rows, const ThinArgs& a, int n, int ih0) {
   const int IH = 2 * a.H, IW = 2 * a.W, IW4 = IW >> 2;
   const int total = NC * rows * IW4;
-  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-    const int j = idx % IW4;
-    const int t = idx / IW4;
-    const int row = t % rows, ci = t / rows;
-    const int ih = ih0 + row;
-    float v[4] = {0.f, 0.f, 0.f, 0.f};
-    if ((unsigned)ih < (unsigned)IH) {
-      load4_rt(a.fine, (int64_t)n * a.fine.sn + (int64_t)ih * a.fine.sh + (int64_t)(4 * j) * a.fine.sw + (int64_t)ci * a.fine.sc, a.fine_vec, v);
-      if (a.fine_ref.ptr) {
-        float r[4];
-        load4_rt(a.fine_ref, (int64_t)n * a.fine_ref.sn + (int64_t)ih * a.fine_ref.sh + (int64_t)(4 * j) * a.fine_ref.sw + (int64_t)ci * a.fine_ref.sc,
-                 a.ref_vec, r);
+  constexpr int U = 4;
+  for (int base = threadIdx.x; base < total; base += U * blockDim.x) {
+    float v[U][4], r[U][4];
+    int dst[U];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) v[e] *= act_grad_from_output(r[e], a.fine_act, a.slope);
+    for (int u = 0; u < U; ++u) {
+      const int idx = base + u * blockDim.x;
+      dst[u] = -1;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { v[u][e] = 0.f; r[u][e] = 0.f; }
+      if (idx < total) {
+        const int j = idx % IW4;
+        const int t = idx / IW4;
+        const int row = t % rows, ci = t / rows;
+        const int ih = ih0 + row;
+        dst[u] = (ci * rows + row) * pitch + 4 * j + 1;
+        if ((unsigned)ih < (unsigned)IH) {
+          load4_rt(a.fine, (int64_t)n * a.fine.sn + (int64_t)ih * a.fine.sh + (int64_t)(4 * j) * a.fine.sw + (int64_t)ci * a.fine.sc, a.fine_vec, v[u]);
+          if (a.fine_ref.ptr)
+            load4_rt(a.fine_ref, (int64_t)n * a.fine_ref.sn + (int64_t)ih * a.fine_ref.sh + (int64_t)(4 * j) * a.fine_ref.sw + (int64_t)ci * a.fine_ref.sc,
+                     a.ref_vec, r[u]);
+        }
       }
     }
-    __nv_bfloat16* d = S + (ci * rows + row) * pitch + 4 * j + 1;      // odd index: [1] [2,3] [4]
-    d[0] = __float2bfloat16_rn(v[0]);
-    *reinterpret_cast<uint32_t*>(d + 1) = pack_bf16x2(v[1], v[2]);
-    d[3] = __float2bfloat16_rn(v[3]);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (dst[u] < 0) continue;
+      if (a.fine_ref.ptr) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[u][e] *= act_grad_from_output(r[u][e], a.fine_act, a.slope);
+      }
+      __nv_bfloat16* d = S + dst[u];                                   // odd index: [1] [2,3] [4]
+      d[0] = __float2bfloat16_rn(v[u][0]);
+      *reinterpret_cast<uint32_t*>(d + 1) = pack_bf16x2(v[u][1], v[u][2]);
+      d[3] = __float2bfloat16_rn(v[u][3]);
+    }
   }
   for (int idx = threadIdx.x; idx < NC * rows * 2; idx += blockDim.x)
     S[(idx >> 1) * pitch + ((idx & 1) ? IW + 1 : 0)] = __float2bfloat16_rn(0.f);
@@ -106,28 +124,59 @@ __device__ __forceinline__ void stage_fine(__nv_bfloat16* S, int pitch, int rows
 
 constexpr int CP = 40;   // bf16 elements per staged coarse pixel: 32 channels + 8 pad (80 B pitch: conflict-free ldmatrix)
 
-// Stage coarse rows [q0, q0+rows) x cols [c0, c0+cols) of image n (zeros outside the image) as S[(row*cols + col)*CP + ch]
+__device__ __forceinline__ void cp_async_16_zfill(void* smem_dst, const void* gmem_src, bool valid) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  const int bytes = valid ? 16 : 0;                                     // src-size 0: the 16 destination bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gmem_src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// Stage coarse rows [q0, q0+rows) x cols [c0, c0+cols) of image n (zeros outside the image) as S[(row*cols + col)*CP + ch].
+// Plain operand: 16-byte cp.async straight into shared memory (every copy of the tile in flight at once); with the fused
+// activation backward: four-deep register staging.  The caller must cp_async_wait_all() + __syncthreads() before reading.
 __device__ __forceinline__ void stage_coarse(__nv_bfloat16* S, int rows, int cols, const ThinArgs& a, int n, int q0, int c0) {
   const int total = rows * cols * 4;
-  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-    const int chunk = idx & 3, pix = idx >> 2;
-    const int col = pix % cols, row = pix / cols;
-    const int q = q0 + row, r = c0 + col;
-    uint4 val = make_uint4(0u, 0u, 0u, 0u);
-    if ((unsigned)q < (unsigned)a.H && (unsigned)r < (unsigned)a.W) {
-      const int64_t off = (((int64_t)n * a.H + q) * a.W + r) * 32 + chunk * 8;
-      val = __ldg(reinterpret_cast<const uint4*>(a.coarse + off));
-      if (a.coarse_ref) {
-        const uint4 rv = __ldg(reinterpret_cast<const uint4*>(a.coarse_ref + off));
-        float d[8], f[8];
-        unpack8(val, d);
-        unpack8(rv, f);
+  if (!a.coarse_ref) {
+    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+      const int chunk = idx & 3, pix = idx >> 2;
+      const int col = pix % cols, row = pix / cols;
+      const int q = q0 + row, r = c0 + col;
+      const bool ok = (unsigned)q < (unsigned)a.H && (unsigned)r < (unsigned)a.W;
+      const int64_t off = ok ? (((int64_t)n * a.H + q) * a.W + r) * 32 + chunk * 8 : 0;
+      cp_async_16_zfill(S + pix * CP + chunk * 8, a.coarse + off, ok);
+    }
+    return;
+  }
+  constexpr int U = 4;
+  for (int base = threadIdx.x; base < total; base += U * blockDim.x) {
+    uint4 val[U], rv[U];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) d[e] *= act_grad_from_output(f[e], a.coarse_act, a.slope);
-        val = pack8(d);
+    for (int u = 0; u < U; ++u) {
+      const int idx = base + u * blockDim.x;
+      val[u] = make_uint4(0u, 0u, 0u, 0u);
+      rv[u] = make_uint4(0u, 0u, 0u, 0u);
+      if (idx < total) {
+        const int chunk = idx & 3, pix = idx >> 2;
+        const int col = pix % cols, row = pix / cols;
+        const int q = q0 + row, r = c0 + col;
+        if ((unsigned)q < (unsigned)a.H && (unsigned)r < (unsigned)a.W) {
+          const int64_t off = (((int64_t)n * a.H + q) * a.W + r) * 32 + chunk * 8;
+          val[u] = __ldg(reinterpret_cast<const uint4*>(a.coarse + off));
+          rv[u] = __ldg(reinterpret_cast<const uint4*>(a.coarse_ref + off));
+        }
       }
     }
-    *reinterpret_cast<uint4*>(S + pix * CP + chunk * 8) = val;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int idx = base + u * blockDim.x;
+      if (idx >= total) continue;
+      float d[8], f[8];
+      unpack8(val[u], d);
+      unpack8(rv[u], f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) d[e] *= act_grad_from_output(f[e], a.coarse_act, a.slope);
+      *reinterpret_cast<uint4*>(S + (idx >> 2) * CP + (idx & 3) * 8) = pack8(d);
+    }
   }
 }
 
@@ -238,6 +287,7 @@ __global__ void __launch_bounds__(256) thin_up_mma_kernel(const ThinArgs a) {
     const int n = tile / a.tiles_per_img, q0 = (tile - n * a.tiles_per_img) * a.R;
     __syncthreads();
     stage_coarse(S, a.R + 2, cols, a, n, q0 - 1, -1);
+    cp_async_wait_all();
     __syncthreads();
     for (int mt = warp; mt < mtiles; mt += 8) {
       const int rr = mt / WB, c = mt - rr * WB;
@@ -327,6 +377,7 @@ __global__ void __launch_bounds__(256) thin_wgrad_mma_kernel(const ThinArgs a) {
     __syncthreads();
     stage_coarse(Sc, a.R, a.W, a, n, oh0, 0);
     stage_fine<NC>(Sf, pitch, rows, a, n, 2 * oh0 - 1);
+    cp_async_wait_all();
     __syncthreads();
     for (int ks = warp; ks < ksteps; ks += 8) {
       const int rr = ks / WB, c = ks - rr * WB;

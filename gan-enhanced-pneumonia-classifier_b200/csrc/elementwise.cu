@@ -109,8 +109,10 @@ struct BwdDenseArgs {
 
 // dy = k1*dz + p*y + q  with k1 = gamma*invstd, p = -k1*m2*invstd, q = k1*(m2*invstd*mean - m1)
 // (algebraically gamma*invstd*(dz - m1 - xhat*m2)); no BatchNorm: dy = dz.
-template <typename T>
-__global__ void __launch_bounds__(256) bn_act_bwd_apply_dense_kernel(BwdDenseArgs g) {
+// HAS_ACT = false: da already is dz (the activation backward was applied by the producing convolution's epilogue,
+// b200gan_fuse.prev_*): no activation coefficients are held, which keeps the kernel at <= 64 registers (4 CTAs per SM).
+template <typename T, bool HAS_ACT>
+__global__ void __launch_bounds__(256, 3) bn_act_bwd_apply_dense_kernel(BwdDenseArgs g) {
   constexpr int V = Vec<T>::N;
   const int C = g.C;
   if (g.scale && blockIdx.x == 0) {
@@ -130,12 +132,13 @@ __global__ void __launch_bounds__(256) bn_act_bwd_apply_dense_kernel(BwdDenseArg
       if (g.scale) {
         const float is = g.invstd[c], mu = g.mean[c];
         const float m1 = (float)(g.sums[c] / g.count), m2 = (float)(g.sums[C + c] / g.count);
-        sc[j] = g.scale[c]; sh[j] = g.shift[c];
+        if (HAS_ACT) { sc[j] = g.scale[c]; sh[j] = g.shift[c]; }
         k1[j] = g.gamma[c] * is;
         pp[j] = -k1[j] * m2 * is;
         qq[j] = k1[j] * (m2 * is * mu - m1);
       } else {
-        sc[j] = 1.f; sh[j] = 0.f; k1[j] = 1.f; pp[j] = 0.f; qq[j] = 0.f;
+        if (HAS_ACT) { sc[j] = 1.f; sh[j] = 0.f; }
+        k1[j] = 1.f; pp[j] = 0.f; qq[j] = 0.f;
       }
     }
   };
@@ -144,19 +147,33 @@ __global__ void __launch_bounds__(256) bn_act_bwd_apply_dense_kernel(BwdDenseArg
   const T* y = reinterpret_cast<const T*>(g.y);
   const T* a = reinterpret_cast<const T*>(g.a);
   T* dy = reinterpret_cast<T*>(g.dy);
-  for (; i < g.nvec; i += stride) {
-    if (!hoist) coeffs((int)((i * V) % C));
-    float d[V], yv[V], av[V];
-    Vec<T>::load(da + i * V, d);
-    Vec<T>::load(y + i * V, yv);
-    if (a) Vec<T>::load(a + i * V, av);
+  // two vectors per thread and iteration, all loads issued before the first store: the pass is pure HBM streaming and
+  // needs ~40 KB in flight per SM (one vector pair at a time measured 49 % of the copy bandwidth)
+  constexpr int U = 2;
+  for (; i < g.nvec; i += U * stride) {
+    float d[U][V], yv[U][V], av[U][V];
 #pragma unroll
-    for (int j = 0; j < V; ++j) {
-      const float z = fmaf(yv[j], sc[j], sh[j]);
-      const float dz = d[j] * act_grad(z, a ? av[j] : 0.f, g.act, g.slope);
-      d[j] = fmaf(k1[j], dz, fmaf(pp[j], yv[j], qq[j]));
+    for (int u = 0; u < U; ++u) {
+      const int64_t k = i + u * stride;
+      if (k < g.nvec) {
+        Vec<T>::load(da + k * V, d[u]);
+        Vec<T>::load(y + k * V, yv[u]);
+        if (HAS_ACT && a) Vec<T>::load(a + k * V, av[u]);
+      }
     }
-    Vec<T>::store(dy + i * V, d);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t k = i + u * stride;
+      if (k >= g.nvec) break;
+      if (!hoist) coeffs((int)((k * V) % C));
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        float dz = d[u][j];
+        if (HAS_ACT) dz *= act_grad(fmaf(yv[u][j], sc[j], sh[j]), a ? av[u][j] : 0.f, g.act, g.slope);
+        d[u][j] = fmaf(k1[j], dz, fmaf(pp[j], yv[u][j], qq[j]));
+      }
+      Vec<T>::store(dy + k * V, d[u]);
+    }
   }
 }
 
@@ -556,8 +573,14 @@ int ew_bn_act_bwd_apply(const b200gan_view* da, const b200gan_view* y, const b20
       int64_t nbk = (d.nvec + 256 * 4 - 1) / (256 * 4);
       if (nbk > 16 * kNumSMs) nbk = 16 * kNumSMs;
       if (nbk < 1) nbk = 1;
-      if (y->dtype == B200GAN_F32) bn_act_bwd_apply_dense_kernel<float><<<(unsigned)nbk, 256, 0, st>>>(d);
-      else bn_act_bwd_apply_dense_kernel<__nv_bfloat16><<<(unsigned)nbk, 256, 0, st>>>(d);
+      const bool has_act = act != B200GAN_ACT_NONE;
+      if (y->dtype == B200GAN_F32) {
+        if (has_act) bn_act_bwd_apply_dense_kernel<float, true><<<(unsigned)nbk, 256, 0, st>>>(d);
+        else bn_act_bwd_apply_dense_kernel<float, false><<<(unsigned)nbk, 256, 0, st>>>(d);
+      } else {
+        if (has_act) bn_act_bwd_apply_dense_kernel<__nv_bfloat16, true><<<(unsigned)nbk, 256, 0, st>>>(d);
+        else bn_act_bwd_apply_dense_kernel<__nv_bfloat16, false><<<(unsigned)nbk, 256, 0, st>>>(d);
+      }
       B200_LAUNCH_CHECK("bn_act_bwd_apply(dense)");
       return 0;
     }

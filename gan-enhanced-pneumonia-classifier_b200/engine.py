@@ -131,6 +131,7 @@ class NetEngine:
         self.specs, self.transposed, self.dtype, self.algo = specs, transposed, dtype, algo
         self._conv = [L.Conv(sp.k, sp.stride, sp.pad, algo) for sp in specs]
         self.launches = 0     # C-ABI calls that launch kernels, made through this engine (bench.py's gpu_launches claim)
+        self._ws = None       # zeroed fp32 scratch for the split-K reduction of the tensor-core weight gradients
 
     # -- thin wrappers over the C ABI --------------------------------------------------------------
     def _tc_layer(self, i):
@@ -170,7 +171,14 @@ class NetEngine:
 
     def _wgrad(self, i, x: Act, dy: Act, dw, st, fuse=None):
         name = 'b200gan_convT2d_wgrad' if self.transposed else 'b200gan_conv2d_wgrad'
-        L.call(name, C.byref(self._conv[i]), C.byref(x.v), C.byref(dy.v), L.ptr(dw), C.byref(fuse) if fuse is not None else None, st)
+        ws = None
+        if self._tc_layer(i):
+            # all zero on entry, handed back all zero by the library: one buffer serves every layer
+            if self._ws is None or self._ws.numel() < dw.numel() or self._ws.device != dw.device:
+                self._ws = torch.zeros(max(dw.numel(), max(sp.cin * sp.cout * sp.k * sp.k for sp in self.specs)), device=dw.device,
+                                       dtype=torch.float32)
+            ws = self._ws
+        L.call(name, C.byref(self._conv[i]), C.byref(x.v), C.byref(dy.v), L.ptr(dw), L.ptr(ws), C.byref(fuse) if fuse is not None else None, st)
         self.launches += 1
 
     def out_hw(self, i, h, w):

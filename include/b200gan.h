@@ -115,13 +115,16 @@ int         b200gan_device_info(int device, char* name, int* cc_major, int* cc_m
 
 /* ---- nn.Conv2d: forward (dcgan.py:65-84), input gradient and weight gradient (autograd of it,
  *      reached from train_gan.py:129,137,148).  dw is fp32 (Cout,Cin,k,k) and is ACCUMULATED into
- *      (`+=`), matching autograd's accumulation over the real and fake passes (train_gan.py:129,137). */
+ *      (`+=`), matching autograd's accumulation over the real and fake passes (train_gan.py:129,137).
+ *      `workspace` (wgrad only): NULL, or numel(dweight) floats owned by the caller that are ALL ZERO on entry and are handed
+ *      back all zero: the tensor-core kernel reduces its split-K partial sums there in a layout that makes every atomic a
+ *      coalesced 128-byte transaction and then transposes into dweight; with NULL it adds into dweight directly (slower). */
 int b200gan_conv2d_fprop(const b200gan_conv* cv, const b200gan_view* x, const float* weight, const void* wpacked,
                          const b200gan_view* y, const b200gan_fuse* fuse, void* stream);
 int b200gan_conv2d_dgrad(const b200gan_conv* cv, const b200gan_view* dy, const float* weight, const void* wpacked,
                          const b200gan_view* dx, const b200gan_fuse* fuse, void* stream);
 int b200gan_conv2d_wgrad(const b200gan_conv* cv, const b200gan_view* x, const b200gan_view* dy, float* dweight,
-                         const b200gan_fuse* fuse, void* stream);
+                         float* workspace, const b200gan_fuse* fuse, void* stream);
 
 /* ---- nn.ConvTranspose2d: forward (dcgan.py:26-46), input gradient, weight gradient (Cin,Cout,k,k). */
 int b200gan_convT2d_fprop(const b200gan_conv* cv, const b200gan_view* x, const float* weight, const void* wpacked,
@@ -129,7 +132,7 @@ int b200gan_convT2d_fprop(const b200gan_conv* cv, const b200gan_view* x, const f
 int b200gan_convT2d_dgrad(const b200gan_conv* cv, const b200gan_view* dy, const float* weight, const void* wpacked,
                           const b200gan_view* dx, const b200gan_fuse* fuse, void* stream);
 int b200gan_convT2d_wgrad(const b200gan_conv* cv, const b200gan_view* x, const b200gan_view* dy, float* dweight,
-                          const b200gan_fuse* fuse, void* stream);
+                          float* workspace, const b200gan_fuse* fuse, void* stream);
 
 /* ---- bf16 repack of a k=4 conv weight for the tcgen05 implicit GEMM (`wpacked` above).  `weight` is the fp32
  *      master in conv geometry (Co,Ci,4,4) -- i.e. the Conv2d weight, or the ConvTranspose2d weight (Cin,Cout,4,4)

@@ -91,7 +91,7 @@ def test_image_side_layers_fused(nc, fine_kind, algo):
     f = L.fuse(dy_act=L.ACT_LRELU, dy_slope=SLOPE, dy_ref=a0_v)
     base = rnd((32, nc, 4, 4), 4)
     dw_t = torch.from_numpy(base.copy()).cuda()
-    L.call('b200gan_conv2d_wgrad', C.byref(cv), C.byref(x_v), C.byref(da0_v), L.ptr(dw_t), C.byref(f), st())
+    L.call('b200gan_conv2d_wgrad', C.byref(cv), C.byref(x_v), C.byref(da0_v), L.ptr(dw_t), None, C.byref(f), st())
     dw_ref = orc.conv2d_wgrad(fine, dy0, 4, 2, 1)
     close(dw_t.cpu().numpy() - base, dw_ref, rtol=1e-2, atol=1e-2 * np.abs(dw_ref).max(), what='D0 wgrad with fused LeakyReLU backward')
     dx_t, dx_v = mk_fine(np.zeros_like(fine))
@@ -115,7 +115,7 @@ def test_image_side_layers_fused(nc, fine_kind, algo):
     dy5 = dfake * (1 - fake * fake)
     f = L.fuse(dy_act=L.ACT_TANH, dy_ref=fake_v)
     dw_t = torch.from_numpy(base.copy()).cuda()
-    L.call('b200gan_convT2d_wgrad', C.byref(cv), C.byref(a4_v), C.byref(dfake_v), L.ptr(dw_t), C.byref(f), st())
+    L.call('b200gan_convT2d_wgrad', C.byref(cv), C.byref(a4_v), C.byref(dfake_v), L.ptr(dw_t), None, C.byref(f), st())
     dw_ref = orc.convT2d_wgrad(a4, dy5, 4, 2, 1)
     close(dw_t.cpu().numpy() - base, dw_ref, rtol=1e-2, atol=1e-2 * np.abs(dw_ref).max(), what='G5 wgrad with fused Tanh backward')
     da4_t = torch.empty((n, hc, wc, 32), device='cuda', dtype=torch.bfloat16)
@@ -144,7 +144,7 @@ def test_image_side_full_size_row_tiles():
         L.call('b200gan_conv2d_dgrad', C.byref(cv), C.byref(c_v), L.ptr(wd), None, C.byref(dx_v), None, st())
         close(dx_t.cpu().numpy(), orc.conv2d_dgrad(c, bf16_round(w), 2, 1, (2 * hc, 2 * wc)), rtol=1e-2, atol=2e-2, what=f'thin up {hc}x{wc}')
         dw_t = torch.zeros((32, nc, 4, 4), device='cuda')
-        L.call('b200gan_conv2d_wgrad', C.byref(cv), C.byref(x_v), C.byref(c_v), L.ptr(dw_t), None, st())
+        L.call('b200gan_conv2d_wgrad', C.byref(cv), C.byref(x_v), C.byref(c_v), L.ptr(dw_t), None, None, st())
         dw_ref = orc.conv2d_wgrad(bf16_round(fine), c, 4, 2, 1)
         close(dw_t.cpu().numpy(), dw_ref, rtol=5e-3, atol=5e-3 * np.abs(dw_ref).max(), what=f'thin wgrad {hc}x{wc}')
 
@@ -237,4 +237,4 @@ def test_fuse_argument_checking():
         L.call('b200gan_conv2d_dgrad', C.byref(cv), C.byref(L.view_nhwc(y)), L.ptr(w), None, C.byref(L.view_nhwc(x)), C.byref(f), st())
     with pytest.raises(L.B200GanError, match='extents differ'):
         f = L.fuse(dy_act=L.ACT_LRELU, dy_slope=0.2, dy_ref=L.view_nhwc(x))
-        L.call('b200gan_conv2d_wgrad', C.byref(cv), C.byref(L.view_nhwc(x)), C.byref(L.view_nhwc(y)), L.ptr(w), C.byref(f), st())
+        L.call('b200gan_conv2d_wgrad', C.byref(cv), C.byref(L.view_nhwc(x)), C.byref(L.view_nhwc(y)), L.ptr(w), None, C.byref(f), st())

@@ -71,7 +71,7 @@ def test_conv2d_fprop_dgrad_wgrad(case, mode):
     # wgrad accumulates: start from a non-zero buffer
     base = rng.randn(co, ci, k, k).astype(np.float32)
     dw = dev(base)
-    L.call('b200gan_conv2d_wgrad', C.byref(cv), C.byref(L.view_nhwc(xd)), C.byref(L.view_nhwc(dyd)), L.ptr(dw), None, st())
+    L.call('b200gan_conv2d_wgrad', C.byref(cv), C.byref(L.view_nhwc(xd)), C.byref(L.view_nhwc(dyd)), L.ptr(dw), None, None, st())
     ref = orc.conv2d_wgrad(x, dy, k, s, p)
     close(dw.cpu().numpy() - base, ref, rtol=1e-4, atol=1e-4 * max(1.0, np.abs(ref).max()), what='wgrad')
 
@@ -94,7 +94,7 @@ def test_convT2d_on_reference_nchw_views(mode):
     L.call('b200gan_convT2d_dgrad', C.byref(cv), C.byref(L.view_nchw(dyd)), L.ptr(wd), None, C.byref(L.view_nchw(dx)), None, st())
     close(dx.cpu().numpy(), orc.convT2d_dgrad(dy, wt, s, p), what='convT dgrad')
     dw = torch.zeros_like(wd)
-    L.call('b200gan_convT2d_wgrad', C.byref(cv), C.byref(L.view_nchw(xd)), C.byref(L.view_nchw(dyd)), L.ptr(dw), None, st())
+    L.call('b200gan_convT2d_wgrad', C.byref(cv), C.byref(L.view_nchw(xd)), C.byref(L.view_nchw(dyd)), L.ptr(dw), None, None, st())
     close(dw.cpu().numpy(), orc.convT2d_wgrad(x, dy, k, s, p), rtol=1e-4, atol=1e-4, what='convT wgrad')
     # G0: latent (N,nz,1,1) -> (N,C,7,7)
     z = rng.randn(3, 10, 1, 1).astype(np.float32)

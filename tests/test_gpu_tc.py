@@ -99,17 +99,23 @@ WGRAD = [(3, 32, 112, 112, 64), (5, 64, 56, 56, 128), (9, 128, 28, 28, 256), (70
          (3, 128, 12, 20, 192), (2, 512, 4, 4, 128)]
 
 
+@pytest.mark.parametrize('use_ws', [False, True])
 @pytest.mark.parametrize('case', WGRAD)
-def test_tc_wgrad_matches_simt(case):
+def test_tc_wgrad_matches_simt(case, use_ws):
+    """use_ws: the split-K partial sums go through the caller's zeroed workspace (coalesced atomics + transpose), which must
+    come back all zero; without it the kernel adds straight into dw."""
     n, ci, h, w_, co = case
     x = bf16_exact((n, h, w_, ci), 1.0, 4)
     dy = bf16_exact((n, h // 2, w_ // 2, co), 1.0, 5)
     base = torch.randn((co, ci, 4, 4), device='cuda')
     dw_tc, dw_ref = base.clone(), base.clone()
     cv_tc, cv_simt = L.Conv(4, 2, 1, L.ALGO_TCGEN05), L.Conv(4, 2, 1, L.ALGO_SIMT)
-    L.call('b200gan_conv2d_wgrad', C.byref(cv_tc), C.byref(L.view_nhwc(x)), C.byref(L.view_nhwc(dy)), L.ptr(dw_tc), None, st())
-    L.call('b200gan_conv2d_wgrad', C.byref(cv_simt), C.byref(L.view_nhwc(x)), C.byref(L.view_nhwc(dy)), L.ptr(dw_ref), None, st())
+    ws = torch.zeros(co * ci * 16, device='cuda') if use_ws else None
+    L.call('b200gan_conv2d_wgrad', C.byref(cv_tc), C.byref(L.view_nhwc(x)), C.byref(L.view_nhwc(dy)), L.ptr(dw_tc), L.ptr(ws), None, st())
+    L.call('b200gan_conv2d_wgrad', C.byref(cv_simt), C.byref(L.view_nhwc(x)), C.byref(L.view_nhwc(dy)), L.ptr(dw_ref), None, None, st())
     torch.cuda.synchronize()
+    if use_ws:
+        assert float(ws.abs().max()) == 0.0, 'workspace must be handed back zeroed'
     a, b = (dw_tc - base).cpu().numpy(), (dw_ref - base).cpu().numpy()
     print(f'wgrad {case}: max|diff|={np.abs(a - b).max():.4e} ref max={np.abs(b).max():.3e}')
     close(a, b, rtol=2e-3, atol=2e-3 * max(1.0, np.abs(b).max()), what=f'wgrad {case}')
@@ -121,6 +127,6 @@ def test_tc_wgrad_against_numpy_oracle():
     dy = bf16_exact((n, h // 2, h // 2, co), 1.0, 7)
     dw = torch.zeros((co, ci, 4, 4), device='cuda')
     cv = L.Conv(4, 2, 1, L.ALGO_TCGEN05)
-    L.call('b200gan_conv2d_wgrad', C.byref(cv), C.byref(L.view_nhwc(x)), C.byref(L.view_nhwc(dy)), L.ptr(dw), None, st())
+    L.call('b200gan_conv2d_wgrad', C.byref(cv), C.byref(L.view_nhwc(x)), C.byref(L.view_nhwc(dy)), L.ptr(dw), None, None, st())
     ref = orc.conv2d_wgrad(x.float().cpu().numpy().transpose(0, 3, 1, 2), dy.float().cpu().numpy().transpose(0, 3, 1, 2), 4, 2, 1)
     close(dw.cpu().numpy(), ref, rtol=1e-3, atol=1e-3, what='wgrad vs oracle')

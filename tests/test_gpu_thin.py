@@ -51,8 +51,8 @@ def test_thin_layers_match_generic(nc, fine_kind):
     # wgrad
     base = rnd((32, nc, 4, 4), 4)
     wa, wb = base.clone(), base.clone()
-    L.call('b200gan_conv2d_wgrad', C.byref(AUTO), C.byref(fview(fine)), C.byref(L.view_nhwc(coarse)), L.ptr(wa), None, st())
-    L.call('b200gan_conv2d_wgrad', C.byref(SIMT), C.byref(fview(fine)), C.byref(L.view_nhwc(coarse)), L.ptr(wb), None, st())
+    L.call('b200gan_conv2d_wgrad', C.byref(AUTO), C.byref(fview(fine)), C.byref(L.view_nhwc(coarse)), L.ptr(wa), None, None, st())
+    L.call('b200gan_conv2d_wgrad', C.byref(SIMT), C.byref(fview(fine)), C.byref(L.view_nhwc(coarse)), L.ptr(wb), None, None, st())
     ref = (wb - base).cpu().numpy()
     # the warp-MMA kernel stages the image as bf16 (the SIMT reference keeps fp32 image values): bf16 tolerance
     close((wa - base).cpu().numpy(), ref, rtol=5e-3, atol=5e-3 * np.abs(ref).max(), what='thin wgrad')
@@ -84,8 +84,8 @@ def test_window_gemv_matches_generic():
     close(da.float().cpu().numpy(), db.float().cpu().numpy(), rtol=1e-2, atol=1e-3, what='window dgrad')
     base = rnd((1, c, k, k), 4)
     wa, wb = base.clone(), base.clone()
-    L.call('b200gan_conv2d_wgrad', C.byref(cva), C.byref(L.view_nhwc(x)), C.byref(L.view_nhwc(dl)), L.ptr(wa), None, st())
-    L.call('b200gan_conv2d_wgrad', C.byref(cvs), C.byref(L.view_nhwc(x)), C.byref(L.view_nhwc(dl)), L.ptr(wb), None, st())
+    L.call('b200gan_conv2d_wgrad', C.byref(cva), C.byref(L.view_nhwc(x)), C.byref(L.view_nhwc(dl)), L.ptr(wa), None, None, st())
+    L.call('b200gan_conv2d_wgrad', C.byref(cvs), C.byref(L.view_nhwc(x)), C.byref(L.view_nhwc(dl)), L.ptr(wb), None, None, st())
     close((wa - base).cpu().numpy(), (wb - base).cpu().numpy(), rtol=1e-3, atol=1e-3, what='window wgrad')
 
 
@@ -102,7 +102,7 @@ def test_latent_gemm_matches_generic():
     dy = rnd((n, k, k, c), 3, torch.bfloat16)
     base = rnd((nz, c, k, k), 4)
     wa, wb = base.clone(), base.clone()
-    L.call('b200gan_convT2d_wgrad', C.byref(cva), C.byref(L.view_nchw(z)), C.byref(L.view_nhwc(dy)), L.ptr(wa), None, st())
-    L.call('b200gan_convT2d_wgrad', C.byref(cvs), C.byref(L.view_nchw(z)), C.byref(L.view_nhwc(dy)), L.ptr(wb), None, st())
+    L.call('b200gan_convT2d_wgrad', C.byref(cva), C.byref(L.view_nchw(z)), C.byref(L.view_nhwc(dy)), L.ptr(wa), None, None, st())
+    L.call('b200gan_convT2d_wgrad', C.byref(cvs), C.byref(L.view_nchw(z)), C.byref(L.view_nhwc(dy)), L.ptr(wb), None, None, st())
     ref = (wb - base).cpu().numpy()
     close((wa - base).cpu().numpy(), ref, rtol=1e-3, atol=1e-3 * np.abs(ref).max(), what='latent wgrad')

@@ -54,12 +54,13 @@ def main():
         y = torch.empty_like(dy)
         dx = torch.empty_like(x)
         dw = torch.zeros_like(w)
+        ws = torch.zeros_like(w)
         cv = L.Conv(4, 2, 1, algo)
         flops = 2.0 * B * (h // 2) ** 2 * co * 16 * ci
         for prim, fn in [
             ('down(fprop)', lambda: L.call('b200gan_conv2d_fprop', C.byref(cv), C.byref(L.view_nhwc(x)), L.ptr(w), L.ptr(wd), C.byref(L.view_nhwc(y)), None, st())),
             ('up(dgrad)', lambda: L.call('b200gan_conv2d_dgrad', C.byref(cv), C.byref(L.view_nhwc(dy)), L.ptr(w), L.ptr(wu), C.byref(L.view_nhwc(dx)), None, st())),
-            ('wgrad', lambda: L.call('b200gan_conv2d_wgrad', C.byref(cv), C.byref(L.view_nhwc(x)), C.byref(L.view_nhwc(dy)), L.ptr(dw), None, st())),
+            ('wgrad', lambda: L.call('b200gan_conv2d_wgrad', C.byref(cv), C.byref(L.view_nhwc(x)), C.byref(L.view_nhwc(dy)), L.ptr(dw), L.ptr(ws), None, st())),
         ]:
             ms = timeit(fn, flush)
             byt = (x.numel() + dy.numel()) * 2
