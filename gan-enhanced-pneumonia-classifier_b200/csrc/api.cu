@@ -110,10 +110,12 @@ static int conv_dispatch(Prim prim, bool transposed, const b200gan_conv* cv, con
   const b200gan_view* gathered = prim == FPROP ? fine : coarse;
   ConvFuse fz;
   double* bn_sums = nullptr;
-  bool prev = false;
+  bool prev = false;            // activation backward (+ BatchNorm-backward sums when prev_scale is given) on the result of a dgrad
+  bool prev_bn = false;
   if (fuse) {
     const bool has_out = fuse->out_act != B200GAN_ACT_NONE, has_dy = fuse->dy_act != B200GAN_ACT_NONE;
-    prev = fuse->prev_sums != nullptr;
+    prev = fuse->prev_y != nullptr;
+    prev_bn = prev && fuse->prev_scale != nullptr;
     if (is_fwd) {
       B200_CHECK_ARG(!has_dy && !prev, "%s: dy_* / prev_* fusions do not apply to a forward convolution", what);
       B200_CHECK_ARG(fuse->out_act >= B200GAN_ACT_NONE && fuse->out_act <= B200GAN_ACT_SIGMOID, "%s: bad out_act %d", what, fuse->out_act);
@@ -131,7 +133,7 @@ static int conv_dispatch(Prim prim, bool transposed, const b200gan_conv* cv, con
         fz.g_ref = fuse->dy_ref; fz.g_act = fuse->dy_act; fz.g_slope = fuse->dy_slope;
       }
       if (prev) {
-        B200_CHECK_ARG(fuse->prev_y && fuse->prev_scale && fuse->prev_shift && fuse->prev_mean && fuse->prev_invstd, "%s: prev_* pointers missing", what);
+        B200_CHECK_ARG(!prev_bn || (fuse->prev_shift && fuse->prev_mean && fuse->prev_invstd && fuse->prev_sums), "%s: prev_* pointers missing", what);
         if ((rc = check_view(fuse->prev_y, what))) return rc;
         B200_CHECK_ARG(same_extent(fuse->prev_y, result) && fuse->prev_y->dtype == result->dtype, "%s: prev_y must match dx in extents and dtype", what);
         if (fuse->prev_act != B200GAN_ACT_RELU && fuse->prev_act != B200GAN_ACT_LRELU && fuse->prev_act != B200GAN_ACT_NONE) {
@@ -152,7 +154,7 @@ static int conv_dispatch(Prim prim, bool transposed, const b200gan_conv* cv, con
       TcEpi epi;
       if (bn_sums) { epi.mode = 1; epi.sums = bn_sums; }
       if (prev) {
-        epi.mode = 2; epi.sums = fuse->prev_sums; epi.prev_y = fuse->prev_y; epi.scale = fuse->prev_scale; epi.shift = fuse->prev_shift;
+        epi.mode = prev_bn ? 2 : 3; epi.sums = fuse->prev_sums; epi.prev_y = fuse->prev_y; epi.scale = fuse->prev_scale; epi.shift = fuse->prev_shift;
         epi.mean = fuse->prev_mean; epi.invstd = fuse->prev_invstd; epi.act = fuse->prev_act; epi.slope = fuse->prev_slope;
       }
       if (prim == FPROP) t = tc_conv_fprop(cv, fine, wpacked, coarse, epi, st);
@@ -193,7 +195,10 @@ static int conv_dispatch(Prim prim, bool transposed, const b200gan_conv* cv, con
   }
   // ---- BatchNorm fusions not absorbed by the kernel: the equivalent passes ---------------------------------
   if (bn_sums && (rc = ew_bn_stats(result, bn_sums, st))) return rc;
-  if (prev) {
+  if (prev && !prev_bn) {
+    // no BatchNorm below: prev_y is the saved activation output, whose sign gives act'
+    if ((rc = ew_act_bwd_inplace(result, fuse->prev_y, nullptr, nullptr, fuse->prev_act, fuse->prev_slope, st))) return rc;
+  } else if (prev) {
     // one dense pass (dz stored in place + sums) when the layout allows, reduce + in-place pass otherwise
     rc = ew_bn_bwd_reduce(result, fuse->prev_y, nullptr, fuse->prev_scale, fuse->prev_shift, fuse->prev_mean, fuse->prev_invstd,
                           fuse->prev_act, fuse->prev_slope, fuse->prev_sums, result, st);

@@ -18,91 +18,9 @@
 #include <stdio.h>
 
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace b200gan {
-
-// ---------------------------------------------------------------------------------------------------
-// PTX wrappers
-// ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-      "selp.u32 %0, 1, 0, p;\n"
-      "}\n"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok;
-}
-// Bounded spin: a pipeline bug must surface as a trapped kernel (sticky CUDA error), never as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 24)) {
-      printf("b200gan: mbarrier wait timed out (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x);
-      __trap();
-    }
-  }
-}
-__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
-          smem_u32(dst)),
-      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
-          smem_u32(dst)),
-      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// D[tmem] (+)= A[smem desc] * B[smem desc], bf16 x bf16 -> fp32, issued by ONE thread
-__device__ __forceinline__ void tcgen05_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void tcgen05_ld_32x32b_x32(uint32_t taddr, uint32_t* r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, "
-      "%19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tcgen05_ld_32x32b_x16(uint32_t taddr, uint32_t* r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tcgen05_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
 // version=1 [46,48), layout type [61,64) (2 = SWIZZLE_128B, 4 = SWIZZLE_64B)
@@ -136,7 +54,7 @@ struct TcConvParams {
   int o_mul;                         // output pixel = q*o_mul + class parity
   int cout;
   // epilogue fusions (template EPI): 1 = BatchNorm statistics of the result, 2 = previous layer's activation backward +
-  // BatchNorm-backward sums (b200gan_fuse.bn_sums / prev_*)
+  // BatchNorm-backward sums, 3 = previous layer's activation backward only (no BatchNorm below)  (b200gan_fuse.bn_sums / prev_*)
   double* sums;                      // [2*cout], zeroed by the host wrapper
   const __nv_bfloat16* prev_y;       // same dense NHWC layout as out
   const float *prev_scale, *prev_shift, *prev_mean, *prev_invstd;
@@ -168,9 +86,6 @@ struct TcSmem {
   static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 
 // Persistent kernel: each CTA walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... of the (M-tile, N-tile, class)
 // space.  Warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2..9 = epilogue (TMEM lane quarter = warp % 4,
@@ -194,7 +109,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   // EPI != 0: per-CTA channel accumulators [2][cout] (flushed once at the end), EPI == 2: {scale, shift, mean, invstd}[cout]
   float* ch_acc = reinterpret_cast<float*>(smem + STAGES * S::STAGE_BYTES + 256);
   float4* ch_coef = reinterpret_cast<float4*>(ch_acc + 2 * p.cout);
-  if (EPI != 0) {
+  if (EPI == 1 || EPI == 2) {
     for (int c = threadIdx.x; c < 2 * p.cout; c += blockDim.x) ch_acc[c] = 0.f;
     if (EPI == 2)
       for (int c = threadIdx.x; c < p.cout; c += blockDim.x)
@@ -304,7 +219,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       __nv_bfloat16* orow = p.out + ooff;
       const uint4* yp = reinterpret_cast<const uint4*>(p.prev_y + ooff);
       uint4 ynext[2];
-      if (EPI == 2) {                                // the first piece of y_prev is requested before the accumulator is waited for
+      if (EPI >= 2) {                                // the first piece of y_prev is requested before the accumulator is waited for
         ynext[0] = valid ? __ldg(yp) : make_uint4(0u, 0u, 0u, 0u);
         ynext[1] = valid ? __ldg(yp + 1) : make_uint4(0u, 0u, 0u, 0u);
       }
@@ -317,7 +232,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         tcgen05_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + hcol * CW + c0, v);
         float s0[16], s1[16];
         uint4 ycur[2];
-        if (EPI == 2) {
+        if (EPI >= 2) {
           ycur[0] = ynext[0]; ycur[1] = ynext[1];
           if (c0 + 16 < CW) {
             ynext[0] = valid ? __ldg(yp + (c0 + 16) / 8) : make_uint4(0u, 0u, 0u, 0u);
@@ -340,6 +255,19 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             }
           }
         }
+        if (EPI == 3) {
+          // no BatchNorm below: y_prev is the saved activation output, dz = dx * act'(.) from its sign
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const uint32_t w[4] = {ycur[j].x, ycur[j].y, ycur[j].z, ycur[j].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float lo = __uint_as_float(w[e] << 16), hi = __uint_as_float(w[e] & 0xffff0000u);
+              v[8 * j + 2 * e] = __float_as_uint(__uint_as_float(v[8 * j + 2 * e]) * (lo > 0.f ? 1.f : p.prev_neg));
+              v[8 * j + 2 * e + 1] = __float_as_uint(__uint_as_float(v[8 * j + 2 * e + 1]) * (hi > 0.f ? 1.f : p.prev_neg));
+            }
+          }
+        }
         // round to the stored precision; the statistics are those of the stored tensor
         uint32_t pk[8];
 #pragma unroll
@@ -351,7 +279,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           *reinterpret_cast<uint4*>(orow + c0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           *reinterpret_cast<uint4*>(orow + c0 + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
         }
-        if (EPI != 0) {
+        if (EPI == 1 || EPI == 2) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float lo = valid ? __uint_as_float(pk[j] << 16) : 0.f, hi = valid ? __uint_as_float(pk[j] & 0xffff0000u) : 0.f;
@@ -372,7 +300,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[buf]);
     }
-    if (EPI != 0) {
+    if (EPI == 1 || EPI == 2) {
       // the eight epilogue warps (256 threads) flush the CTA's channel sums: one double atomic per channel and quantity
       asm volatile("bar.sync 1, 256;" ::: "memory");
       for (int c = threadIdx.x - 64; c < p.cout; c += 256) {
@@ -393,21 +321,6 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 // ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* sym = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(sym);
-  }
-  return fn;
-}
-
 static int ilog2_exact(int v) {
   int l = 0;
   while ((1 << l) < v) ++l;
@@ -432,7 +345,7 @@ template <int BN, int KC, int STAGES, int EPI>
 static int launch_tc_epi(const CUtensorMap& ma, const CUtensorMap& mb, const TcConvParams& p, dim3 grid, cudaStream_t st) {
   using S = TcSmem<BN, KC, STAGES>;
   // channel accumulators / coefficients live behind the barrier block (EPI != 0), sized by the layer's channel count
-  const int smem = S::TOTAL + (EPI == 0 ? 0 : p.cout * 8 + (EPI == 2 ? p.cout * 16 : 0) + 16);
+  const int smem = S::TOTAL + ((EPI == 0 || EPI == 3) ? 0 : p.cout * 8 + (EPI == 2 ? p.cout * 16 : 0) + 16);
   static int configured = 0;
   if (configured < smem) {
     B200_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, KC, STAGES, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -447,6 +360,7 @@ template <int BN, int KC, int STAGES>
 static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcConvParams& p, int epi, dim3 grid, cudaStream_t st) {
   if (epi == 1) return launch_tc_epi<BN, KC, STAGES, 1>(ma, mb, p, grid, st);
   if (epi == 2) return launch_tc_epi<BN, KC, STAGES, 2>(ma, mb, p, grid, st);
+  if (epi == 3) return launch_tc_epi<BN, KC, STAGES, 3>(ma, mb, p, grid, st);
   return launch_tc_epi<BN, KC, STAGES, 0>(ma, mb, p, grid, st);
 }
 
@@ -460,7 +374,7 @@ static int tc_conv_common(const b200gan_conv* cv, const b200gan_view* in, const 
   const int cin = in->c, cout = out->c;
   if (cin % 32 != 0 || cout % 32 != 0) return 1;
   if (epi.mode != 0 && cout > 1024) return 1;
-  if (epi.mode == 2 && (!nhwc_dense_bf16(epi.prev_y) || epi.prev_y->n != out->n || epi.prev_y->h != out->h || epi.prev_y->w != out->w ||
+  if (epi.mode >= 2 && (!nhwc_dense_bf16(epi.prev_y) || epi.prev_y->n != out->n || epi.prev_y->h != out->h || epi.prev_y->w != out->w ||
                         epi.prev_y->c != out->c))
     return 1;
   const int KC = cin % 64 == 0 ? 64 : 32;
@@ -492,14 +406,14 @@ static int tc_conv_common(const b200gan_conv* cv, const b200gan_view* in, const 
   p.QH = QH; p.QW = QW; p.NB = NB;
   p.out = reinterpret_cast<__nv_bfloat16*>(out->ptr);
   p.o_sn = out->sn; p.o_sh = out->sh; p.o_sw = out->sw; p.o_mul = up ? 2 : 1; p.cout = cout;
-  if (epi.mode != 0) {
+  if (epi.mode == 1 || epi.mode == 2) {
     p.sums = epi.sums;
     B200_CUDA(cudaMemsetAsync(epi.sums, 0, sizeof(double) * 2 * cout, st));
-    if (epi.mode == 2) {
-      p.prev_y = reinterpret_cast<const __nv_bfloat16*>(epi.prev_y->ptr);
-      p.prev_scale = epi.scale; p.prev_shift = epi.shift; p.prev_mean = epi.mean; p.prev_invstd = epi.invstd;
-      p.prev_neg = epi.act == B200GAN_ACT_RELU ? 0.f : (epi.act == B200GAN_ACT_LRELU ? epi.slope : 1.f);
-    }
+  }
+  if (epi.mode >= 2) {
+    p.prev_y = reinterpret_cast<const __nv_bfloat16*>(epi.prev_y->ptr);
+    p.prev_scale = epi.scale; p.prev_shift = epi.shift; p.prev_mean = epi.mean; p.prev_invstd = epi.invstd;
+    p.prev_neg = epi.act == B200GAN_ACT_RELU ? 0.f : (epi.act == B200GAN_ACT_LRELU ? epi.slope : 1.f);
   }
 
   CUtensorMap ma, mb;

@@ -11,6 +11,7 @@
 //     (gradient x act'(saved output)) while the gradient operand is staged, so no elementwise pass touches these tensors.
 // Conv geometry names: fine = (N, 2H, 2W, nc) image side, coarse = (N, H, W, 32) dense bf16 NHWC, w = (32, nc, 4, 4) fp32.
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace b200gan {
 
@@ -28,7 +29,18 @@ struct ThinArgs {
   int fine_act, coarse_act, out_act;   // b200gan_act: derivative applied to the staged operand / activation of the result
   float slope;
   int fine_vec, ref_vec;               // 4-wide vector loads along W are legal for fine / fine_ref
+  int RT;                              // coarse rows per tile of the TMA-staged kernels
 };
+
+__device__ __forceinline__ float tanh_fast(float x) {       // MUFU.TANH: 2^-11 relative error, below the bf16 storage rounding
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// byte offset of 16-byte chunk `chunk` of pixel `pix` inside a TMA tile written with CU_TENSOR_MAP_SWIZZLE_64B (64-byte pixel
+// rows, tile base 512-byte aligned): address bits [4:5] are XORed with bits [7:8]
+__device__ __forceinline__ uint32_t sw64(int pix, int chunk) { return (uint32_t)pix * 64u + (uint32_t)((chunk ^ ((pix >> 1) & 3)) << 4); }
 
 __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
@@ -320,7 +332,7 @@ __global__ void __launch_bounds__(256) thin_up_mma_kernel(const ThinArgs a) {
         for (int half = 0; half < 2; ++half) {
           const int r = 16 * c + g + 8 * half;
           float v0 = acc[j][2 * half], v1 = acc[j][2 * half + 1];
-          if (a.out_act == B200GAN_ACT_TANH) { v0 = tanhf(v0); v1 = tanhf(v1); }
+          if (a.out_act == B200GAN_ACT_TANH) { v0 = tanh_fast(v0); v1 = tanh_fast(v1); }
           const int n0 = 8 * j + 2 * t;
           if (pair_store) {
             if (n0 < 4) {                                                  // n0 = 2*py, columns px = 0,1 are adjacent pixels
@@ -410,6 +422,274 @@ __global__ void __launch_bounds__(256) thin_wgrad_mma_kernel(const ThinArgs a) {
   for (int i = threadIdx.x; i < 512 * NC; i += blockDim.x) atomicAdd(a.dw + i, red[i]);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// TMA-staged variants for a PLAIN coarse operand (no fused activation backward on it): the 32-channel tensor -- 411 MB per
+// launch at the benchmark size, the whole cost of these kernels -- is brought in by one cp.async.bulk.tensor per tile
+// (zero halo = TMA out-of-bounds fill, 64B-swizzled so that ldmatrix is conflict free without padding), double buffered
+// behind mbarriers by a producer warp, so no thread spends instructions on staging it.  Seven consumer warps own the seven
+// 16-pixel column blocks of a 112-wide row band (any W % 16 == 0 with W/16 <= 7 consumer warps... see thin_tma_ok).
+// ---------------------------------------------------------------------------------------------------
+constexpr int kThinStages = 2;
+
+template <int NC>
+__global__ void __launch_bounds__(256) thin_up_tma_kernel(const __grid_constant__ CUtensorMap map_c, const ThinArgs a) {
+  constexpr int NT = (4 * NC + 7) / 8;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int cols = a.W + 2, rows = a.RT + 2;
+  const uint32_t tile_bytes = (uint32_t)rows * cols * 64u;
+  const uint32_t stage_bytes = (tile_bytes + 1023u) & ~1023u;
+  uint2* Bf = reinterpret_cast<uint2*>(smem + kThinStages * stage_bytes);                 // [18*NT][32]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kThinStages * stage_bytes + 18 * NT * 32 * 8);
+  uint64_t* empty_bar = full_bar + kThinStages;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int WB = a.W >> 4;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kThinStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], WB); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_c) : "memory");
+  }
+  for (int idx = threadIdx.x; idx < 18 * NT * 32; idx += blockDim.x) {
+    const int ln = idx & 31, f = idx >> 5, nt = f % NT, ks = f / NT, nbr = ks >> 1, h = ks & 1;
+    const int gg = ln >> 2, tt = ln & 3, nn = 8 * nt + gg;
+    float wv[4] = {0.f, 0.f, 0.f, 0.f};
+    if (nn < 4 * NC) {
+      const int cls = nn / NC, ci = nn - cls * NC, py = cls >> 1, px = cls & 1;
+      const int di = nbr / 3 - 1, dj = nbr % 3 - 1, kh = py + 1 - 2 * di, kw = px + 1 - 2 * dj;
+      if (kh >= 0 && kh < 4 && kw >= 0 && kw < 4) {
+        const int kk[4] = {2 * tt, 2 * tt + 1, 2 * tt + 8, 2 * tt + 9};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) wv[e] = __ldg(a.w + ((16 * h + kk[e]) * NC + ci) * 16 + kh * 4 + kw);
+      }
+    }
+    Bf[idx] = make_uint2(pack_bf16x2(wv[0], wv[1]), pack_bf16x2(wv[2], wv[3]));
+  }
+  __syncthreads();
+
+  if (warp == 7) {
+    // ===== producer: one elected lane issues one bulk tensor copy per tile =====
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+        const int n = tile / a.tiles_per_img, q0 = (tile - n * a.tiles_per_img) * a.RT;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_expect_tx(&full_bar[s], tile_bytes);
+        tma_load_4d(smem + s * stage_bytes, &map_c, &full_bar[s], 0, -1, q0 - 1, n);
+        if (++s == kThinStages) { s = 0; ph ^= 1; }
+      }
+    }
+    return;
+  }
+  if (warp >= WB) return;                     // one consumer warp per 16-pixel column block
+  const int c = warp;
+  const int prow = (lane & 7) + 8 * ((lane >> 3) & 1), kchunk = lane >> 4;
+  const bool pair_store = NC == 1 && a.fine_vec;
+  int s = 0;
+  uint32_t ph = 0;
+  for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+    const int n = tile / a.tiles_per_img, q0 = (tile - n * a.tiles_per_img) * a.RT;
+    mbar_wait(&full_bar[s], ph);
+    const uint32_t S = smem_u32(smem + s * stage_bytes);
+    // two rows at a time: two independent accumulator chains per warp hide the MMA latency
+    for (int rr = 0; rr < a.RT; rr += 2) {
+      float acc[2][NT][4];
+#pragma unroll
+      for (int r2 = 0; r2 < 2; ++r2)
+#pragma unroll
+        for (int j = 0; j < NT; ++j)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) acc[r2][j][e] = 0.f;
+#pragma unroll
+      for (int nbr = 0; nbr < 9; ++nbr) {
+        const int di = nbr / 3 - 1, dj = nbr % 3 - 1;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t af[2][4];
+#pragma unroll
+          for (int r2 = 0; r2 < 2; ++r2) {
+            const int pix = (rr + r2 + 1 + di) * cols + 16 * c + prow + 1 + dj;
+            const uint32_t addr = S + sw64(pix, 2 * h + kchunk);
+            asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                         : "=r"(af[r2][0]), "=r"(af[r2][1]), "=r"(af[r2][2]), "=r"(af[r2][3]) : "r"(addr));
+          }
+#pragma unroll
+          for (int j = 0; j < NT; ++j) {
+            const uint2 b = Bf[((nbr * 2 + h) * NT + j) * 32 + lane];
+#pragma unroll
+            for (int r2 = 0; r2 < 2; ++r2) mma_bf16_16816(acc[r2][j], af[r2], b.x, b.y);
+          }
+        }
+      }
+#pragma unroll
+      for (int r2 = 0; r2 < 2; ++r2) {
+        const int q = q0 + rr + r2;
+        if (rr + r2 >= a.RT || q >= a.H) continue;
+#pragma unroll
+        for (int j = 0; j < NT; ++j)
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            const int r = 16 * c + g + 8 * half;
+            float v0 = acc[r2][j][2 * half], v1 = acc[r2][j][2 * half + 1];
+            if (a.out_act == B200GAN_ACT_TANH) { v0 = tanh_fast(v0); v1 = tanh_fast(v1); }
+            const int n0 = 8 * j + 2 * t;
+            if (pair_store) {
+              if (n0 < 4) {                                                  // n0 = 2*py, columns px = 0,1 are adjacent pixels
+                const int64_t off = (int64_t)n * a.fine.sn + (int64_t)(2 * q + (n0 >> 1)) * a.fine.sh + 2 * r;
+                if (a.fine.dtype == B200GAN_F32) *reinterpret_cast<float2*>(reinterpret_cast<float*>(a.fine.ptr) + off) = make_float2(v0, v1);
+                else *reinterpret_cast<uint32_t*>(reinterpret_cast<__nv_bfloat16*>(a.fine.ptr) + off) = pack_bf16x2(v0, v1);
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const int nn = n0 + e;
+                if (nn < 4 * NC) {
+                  const int cls = nn / NC, ci = nn - cls * NC;
+                  const int64_t off = (int64_t)n * a.fine.sn + (int64_t)(2 * q + (cls >> 1)) * a.fine.sh + (int64_t)(2 * r + (cls & 1)) * a.fine.sw +
+                                      (int64_t)ci * a.fine.sc;
+                  const float v = e ? v1 : v0;
+                  if (a.fine.dtype == B200GAN_F32) reinterpret_cast<float*>(a.fine.ptr)[off] = v;
+                  else reinterpret_cast<__nv_bfloat16*>(a.fine.ptr)[off] = __float2bfloat16_rn(v);
+                }
+              }
+            }
+          }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[s]);     // this warp no longer reads the stage
+    if (++s == kThinStages) { s = 0; ph ^= 1; }
+  }
+}
+
+// WGRAD with the coarse operand staged by TMA and the image band staged RAW (its own dtype TF, optionally together with the
+// reference tensor of the fused tanh backward) by 16-byte cp.async of the producer warp; the bf16 conversion and the
+// dy * (1 - a^2) product happen when the consumers build their B fragments.  Requirements (checked on the host): unit W stride
+// and 16-byte aligned rows of the image tensors.
+template <typename TF> __device__ __forceinline__ float band_ld(const TF* p);
+template <> __device__ __forceinline__ float band_ld<float>(const float* p) { return *p; }
+template <> __device__ __forceinline__ float band_ld<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+
+template <int NC, typename TF, bool HAS_REF>
+__global__ void __launch_bounds__(256) thin_wgrad_tma_kernel(const __grid_constant__ CUtensorMap map_c, const ThinArgs a) {
+  constexpr int PADL = 16 / (int)sizeof(TF);                 // image column iw lives at element iw + PADL (16-byte aligned rows)
+  constexpr int NB = HAS_REF ? 2 : 1;                        // bands per stage: gradient (+ reference)
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int frows = 2 * a.RT + 2, IH = 2 * a.H, IW = 2 * a.W, pitch = IW + 2 * PADL;
+  const uint32_t tile_bytes = (uint32_t)a.RT * a.W * 64u;
+  const uint32_t band_bytes = (uint32_t)NC * frows * pitch * (uint32_t)sizeof(TF);
+  const uint32_t stage_bytes = (tile_bytes + NB * band_bytes + 1023u) & ~1023u;
+  float* red = reinterpret_cast<float*>(smem + kThinStages * stage_bytes);                // [512*NC]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(red + 512 * NC);
+  uint64_t* empty_bar = full_bar + kThinStages;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int WB = a.W >> 4;
+  if (threadIdx.x == 0) {
+    // full: expect_tx arrival of the TMA issue + one cp.async-completion arrival per producer lane
+    for (int s = 0; s < kThinStages; ++s) { mbar_init(&full_bar[s], 33); mbar_init(&empty_bar[s], WB); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_c) : "memory");
+  }
+  for (int i = threadIdx.x; i < 512 * NC; i += blockDim.x) red[i] = 0.f;
+  // the zero padding columns (iw = -1 and iw = IW) are never written by the copies: clear the bands once
+  for (int s = 0; s < kThinStages; ++s) {
+    uint32_t* z = reinterpret_cast<uint32_t*>(smem + s * stage_bytes + tile_bytes);
+    for (int i = threadIdx.x; i < (int)(NB * band_bytes / 4); i += blockDim.x) z[i] = 0u;
+  }
+  __syncthreads();
+
+  if (warp == 7) {
+    int s = 0;
+    uint32_t ph = 0;
+    const int chunks = IW / PADL;                            // 16-byte chunks per image row
+    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+      const int n = tile / a.tiles_per_img, oh0 = (tile - n * a.tiles_per_img) * a.RT;
+      mbar_wait(&empty_bar[s], ph ^ 1);
+      uint8_t* st = smem + s * stage_bytes;
+      if (lane == 0) {
+        mbar_expect_tx(&full_bar[s], tile_bytes);
+        tma_load_4d(st, &map_c, &full_bar[s], 0, 0, oh0, n);
+      }
+      const int ih0 = 2 * oh0 - 1, total = NC * frows * chunks;
+      for (int idx = lane; idx < total; idx += 32) {
+        const int j = idx % chunks, tt = idx / chunks, row = tt % frows, ci = tt / frows, ih = ih0 + row;
+        const bool ok = (unsigned)ih < (unsigned)IH;
+        const uint32_t dst = (uint32_t)((ci * frows + row) * pitch + PADL + j * PADL) * (uint32_t)sizeof(TF);
+        const int64_t off = ok ? (int64_t)n * a.fine.sn + (int64_t)ih * a.fine.sh + (int64_t)ci * a.fine.sc + j * PADL : 0;
+        cp_async_16_zfill(st + tile_bytes + dst, reinterpret_cast<const TF*>(a.fine.ptr) + off, ok);
+        if (HAS_REF) {
+          const int64_t roff = ok ? (int64_t)n * a.fine_ref.sn + (int64_t)ih * a.fine_ref.sh + (int64_t)ci * a.fine_ref.sc + j * PADL : 0;
+          cp_async_16_zfill(st + tile_bytes + band_bytes + dst, reinterpret_cast<const TF*>(a.fine_ref.ptr) + roff, ok);
+        }
+      }
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&full_bar[s])) : "memory");
+      if (++s == kThinStages) { s = 0; ph ^= 1; }
+    }
+    return;
+  }
+  float acc[2][2 * NC][4];
+#pragma unroll
+  for (int m = 0; m < 2; ++m)
+#pragma unroll
+    for (int j = 0; j < 2 * NC; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[m][j][e] = 0.f;
+  if (warp < WB) {
+    const int c = warp;
+    const int px_l = (lane & 7) + 8 * (lane >> 4), cchunk = (lane >> 3) & 1;
+    const int kw = g & 3, khg = g >> 2;
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+      mbar_wait(&full_bar[s], ph);
+      const uint8_t* st = smem + s * stage_bytes;
+      const uint32_t Sc = smem_u32(st);
+      const TF* Sf = reinterpret_cast<const TF*>(st + tile_bytes);
+      const TF* Sr = reinterpret_cast<const TF*>(st + tile_bytes + band_bytes);
+      for (int rr = 0; rr < a.RT; ++rr) {
+        uint32_t af[2][4];
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+          const uint32_t addr = Sc + sw64(rr * a.W + 16 * c + px_l, 2 * m + cchunk);
+          asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                       : "=r"(af[m][0]), "=r"(af[m][1]), "=r"(af[m][2]), "=r"(af[m][3]) : "r"(addr));
+        }
+#pragma unroll
+        for (int ci = 0; ci < NC; ++ci)
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            // pixels ow = 16c + 2t (+1, +8, +9) of this k-step at tap (kh = 2hf + khg, kw): iw = 2*ow - 1 + kw
+            const int e0 = (ci * frows + 2 * rr + 2 * hf + khg) * pitch + 2 * (16 * c + 2 * t) + kw - 1 + PADL;
+            float x[4] = {band_ld(Sf + e0), band_ld(Sf + e0 + 2), band_ld(Sf + e0 + 16), band_ld(Sf + e0 + 18)};
+            if (HAS_REF) {
+              const float r[4] = {band_ld(Sr + e0), band_ld(Sr + e0 + 2), band_ld(Sr + e0 + 16), band_ld(Sr + e0 + 18)};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) x[e] *= act_grad_from_output(r[e], a.fine_act, a.slope);
+            }
+            const uint32_t b0 = pack_bf16x2(x[0], x[1]), b1 = pack_bf16x2(x[2], x[3]);
+#pragma unroll
+            for (int m = 0; m < 2; ++m) mma_bf16_16816(acc[m][ci * 2 + hf], af[m], b0, b1);
+          }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[s]);
+      if (++s == kThinStages) { s = 0; ph ^= 1; }
+    }
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+      for (int j = 0; j < 2 * NC; ++j)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int co = 16 * m + g + 8 * (e >> 1), ci = j >> 1, tap = 8 * (j & 1) + 2 * t + (e & 1);
+          atomicAdd(&red[(co * NC + ci) * 16 + tap], acc[m][j][e]);
+        }
+  }
+  asm volatile("bar.sync 1, 224;" ::: "memory");          // the seven consumer warps (the producer warp has left)
+  for (int i = threadIdx.x; i < 512 * NC; i += 224) atomicAdd(a.dw + i, red[i]);
+}
+
 bool dense_bf16_32(const b200gan_view* v) {
   return v->dtype == B200GAN_BF16 && v->c == 32 && v->sc == 1 && v->sw == 32 && v->sh == (int64_t)v->w * 32 &&
          v->sn == (int64_t)v->h * v->w * 32 && (reinterpret_cast<uintptr_t>(v->ptr) & 15) == 0;
@@ -418,7 +698,14 @@ bool dense_bf16_32(const b200gan_view* v) {
 // 4-wide loads along W: unit W stride, every row start a multiple of 4 elements, base pointer aligned to 4 elements
 int vec4_ok(const b200gan_view* v) {
   const uintptr_t bytes = v->dtype == B200GAN_F32 ? 16 : 8;
-  return v->sw == 1 && v->sn % 4 == 0 && v->sh % 4 == 0 && v->sc % 4 == 0 && (reinterpret_cast<uintptr_t>(v->ptr) % bytes) == 0;
+  return v->sw == 1 && v->sn % 4 == 0 && v->sh % 4 == 0 && (v->c == 1 || v->sc % 4 == 0) && (reinterpret_cast<uintptr_t>(v->ptr) % bytes) == 0;
+}
+
+// 16-byte cp.async along W: unit W stride, every row start and the base pointer 16-byte aligned
+bool vec16_ok(const b200gan_view* v) {
+  const int per = v->dtype == B200GAN_F32 ? 4 : 8;
+  return v->sw == 1 && v->sn % per == 0 && v->sh % per == 0 && (v->c == 1 || v->sc % per == 0) && v->w % per == 0 &&
+         (reinterpret_cast<uintptr_t>(v->ptr) & 15) == 0;
 }
 
 // returns false when the problem is not of the thin shape
@@ -441,6 +728,36 @@ bool thin_setup(ThinArgs* a, const b200gan_view* fine, const b200gan_view* fine_
   a->fine_vec = vec4_ok(fine);
   a->ref_vec = fine_ref ? vec4_ok(fine_ref) : 0;
   return true;
+}
+
+// 4-d tensor map over the dense (N,H,W,32) bf16 coarse tensor: box {32 ch, box_w, box_h, 1}, 64B swizzle, zero OOB fill
+int coarse_tensor_map(CUtensorMap* m, const ThinArgs& a, int box_w, int box_h) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return B200GAN_ERR_CUDA; }
+  cuuint64_t gdim[4] = {32, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.N};
+  cuuint64_t gstr[3] = {64, (cuuint64_t)a.W * 64, (cuuint64_t)a.H * a.W * 64};
+  cuuint32_t box[4] = {32, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(a.coarse), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(coarse) failed: %d", (int)r); return B200GAN_ERR_CUDA; }
+  return 0;
+}
+
+bool thin_tma_ok(const ThinArgs& a) { return a.coarse_ref == nullptr && a.W % 16 == 0 && a.W / 16 <= 7 && a.H >= 2; }
+
+template <void (*Kernel)(const CUtensorMap, const ThinArgs)>
+int launch_thin_tma(const CUtensorMap& m, const ThinArgs& a, size_t smem, int ctas_per_sm, cudaStream_t st, const char* name) {
+  static size_t configured = 0;
+  if (configured < smem) {
+    B200_CUDA(cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  int grid = ctas_per_sm * kNumSMs;
+  if (grid > a.num_tiles) grid = a.num_tiles;
+  Kernel<<<grid, 256, smem, st>>>(m, a);
+  B200_LAUNCH_CHECK(name);
+  return 0;
 }
 
 template <void (*Kernel)(const ThinArgs)>
@@ -481,6 +798,18 @@ int thin_up(const b200gan_view* coarse, const b200gan_view* coarse_ref, int coar
   if (!thin_setup(&a, fine, nullptr, B200GAN_ACT_NONE, coarse, coarse_ref, coarse_act, slope)) return 1;
   a.w = w; a.out_act = out_act;
   const int NT = (4 * fine->c + 7) / 8;
+  if (thin_tma_ok(a)) {
+    a.RT = 4;
+    a.tiles_per_img = (a.H + a.RT - 1) / a.RT;
+    a.num_tiles = a.N * a.tiles_per_img;
+    CUtensorMap m;
+    int rc = coarse_tensor_map(&m, a, a.W + 2, a.RT + 2);
+    if (rc) return rc;
+    const size_t stage = ((size_t)(a.RT + 2) * (a.W + 2) * 64 + 1023) & ~(size_t)1023;
+    const size_t smem_tma = kThinStages * stage + (size_t)18 * NT * 32 * 8 + 64 + 1024;
+    if (fine->c == 1) return launch_thin_tma<thin_up_tma_kernel<1>>(m, a, smem_tma, 2, st, "thin_up_tma_kernel");
+    return launch_thin_tma<thin_up_tma_kernel<3>>(m, a, smem_tma, 2, st, "thin_up_tma_kernel");
+  }
   const size_t smem = (size_t)18 * NT * 32 * 8 + (size_t)(a.R + 2) * (a.W + 2) * CP * 2;
   if (fine->c == 1) return launch_thin<thin_up_mma_kernel<1>>(a, smem, 2, st, "thin_up_mma_kernel");
   return launch_thin<thin_up_mma_kernel<3>>(a, smem, 2, st, "thin_up_mma_kernel");
@@ -492,6 +821,29 @@ int thin_wgrad(const b200gan_view* fine, const b200gan_view* fine_ref, int fine_
   ThinArgs a{};
   if (!thin_setup(&a, fine, fine_ref, fine_act, coarse, coarse_ref, coarse_act, slope)) return 1;
   a.dw = dw;
+  // raw cp.async staging of the image band: unit W stride, 16-byte aligned rows, reference (if any) of the same dtype
+  const bool band_ok = a.fine_vec && vec16_ok(fine) && (!fine_ref || (fine_ref->dtype == fine->dtype && vec16_ok(fine_ref)));
+  if (thin_tma_ok(a) && band_ok) {
+    a.RT = 4;
+    a.tiles_per_img = (a.H + a.RT - 1) / a.RT;
+    a.num_tiles = a.N * a.tiles_per_img;
+    CUtensorMap m;
+    int rc = coarse_tensor_map(&m, a, a.W, a.RT);
+    if (rc) return rc;
+    const int esz = fine->dtype == B200GAN_F32 ? 4 : 2, padl = 16 / esz, nb = fine_ref ? 2 : 1;
+    const size_t band = (size_t)fine->c * (2 * a.RT + 2) * (2 * a.W + 2 * padl) * esz;
+    const size_t stage = ((size_t)a.RT * a.W * 64 + nb * band + 1023) & ~(size_t)1023;
+    const size_t smem_tma = kThinStages * stage + (size_t)512 * fine->c * 4 + 64 + 1024;
+    const char* nm = "thin_wgrad_tma_kernel";
+#define WG(NC, T, R) launch_thin_tma<thin_wgrad_tma_kernel<NC, T, R>>(m, a, smem_tma, 2, st, nm)
+    if (fine->c == 1) {
+      if (fine->dtype == B200GAN_F32) return fine_ref ? WG(1, float, true) : WG(1, float, false);
+      return fine_ref ? WG(1, __nv_bfloat16, true) : WG(1, __nv_bfloat16, false);
+    }
+    if (fine->dtype == B200GAN_F32) return fine_ref ? WG(3, float, true) : WG(3, float, false);
+    return fine_ref ? WG(3, __nv_bfloat16, true) : WG(3, __nv_bfloat16, false);
+#undef WG
+  }
   const size_t smem = (size_t)512 * fine->c * 4 + (size_t)a.R * a.W * CP * 2 + (size_t)fine->c * (2 * a.R + 2) * (2 * a.W + 2) * 2;
   if (fine->c == 1) return launch_thin<thin_wgrad_mma_kernel<1>>(a, smem, 2, st, "thin_wgrad_mma_kernel");
   return launch_thin<thin_wgrad_mma_kernel<3>>(a, smem, 2, st, "thin_wgrad_mma_kernel");

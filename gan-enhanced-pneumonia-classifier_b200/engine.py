@@ -272,6 +272,7 @@ class NetEngine:
         nl = len(self.specs)
         gi = len(grads)
         d = dout
+        masked = False        # d already carries this layer's activation backward (applied by the dgrad epilogue of the layer above)
         for i in reversed(range(nl)):
             sp, p, lc = self.specs[i], params[i], ctxs[i]
             dev = lc.a.t.device
@@ -291,7 +292,8 @@ class NetEngine:
                 dy = d
             elif self._act_fused(i):
                 dy = d
-                fuse_kw = dict(dy_act=sp.act, dy_slope=LRELU_SLOPE, dy_ref=lc.a.v)
+                if not masked:
+                    fuse_kw = dict(dy_act=sp.act, dy_slope=LRELU_SLOPE, dy_ref=lc.a.v)
             else:
                 # activation without BatchNorm and without a fused kernel (Sigmoid of the module-level Discriminator forward)
                 dy = Act(torch.empty(lc.a.t.shape, device=dev, dtype=lc.a.t.dtype), nchw=False)
@@ -303,12 +305,18 @@ class NetEngine:
             if need_wgrad and on_ready is not None:
                 for j in range(gi + nparam - 1, gi - 1, -1):
                     on_ready(j)
+            masked = False
             if i > 0:
                 below, lb = self.specs[i - 1], ctxs[i - 1]
                 if below.bn_idx is not None:
                     lb.bsums = torch.empty(2 * below.cout, device=dev, dtype=torch.float64)
                     fuse_kw.update(prev_act=below.act, prev_slope=LRELU_SLOPE, prev_y=lb.y.v, prev_scale=lb.scale, prev_shift=lb.shift,
                                    prev_mean=lb.mean, prev_invstd=lb.invstd, prev_sums=lb.bsums)
+                elif self._act_fused(i - 1) and below.act in (L.ACT_LRELU, L.ACT_RELU) and (need_wgrad or dinput is not None):
+                    # D0 (LeakyReLU, no BatchNorm): its activation backward rides on THIS layer's dgrad epilogue, so D0's own
+                    # wgrad / dgrad read a plain gradient tensor
+                    fuse_kw.update(prev_act=below.act, prev_slope=LRELU_SLOPE, prev_y=lb.a.v)
+                    masked = True
                 d = Act(torch.empty(lc.x.t.shape, device=dev, dtype=self.dtype), nchw=False)
                 self._dgrad(i, dy, p.w, d, st, lc.wp_down, lc.wp_up, fuse=L.fuse(**fuse_kw) if fuse_kw else None)
             elif dinput is not None:

@@ -90,7 +90,10 @@ typedef struct b200gan_conv {
  *                          dz = dx * act'(prev_scale[c]*y_prev + prev_shift[c])          (stored INSTEAD of dx)
  *                          prev_sums[0..C) = sum dz,  prev_sums[C..2C) = sum dz*(y_prev - prev_mean[c])*prev_invstd[c]
  *                        (OVERWRITTEN; the same contract as b200gan_bn_act_bwd_reduce, which it replaces).  The caller then
- *                        finishes native_batch_norm_backward with b200gan_bn_act_bwd_apply(da = dz, act = NONE). */
+ *                        finishes native_batch_norm_backward with b200gan_bn_act_bwd_apply(da = dz, act = NONE).
+ *                        With prev_scale == NULL there is no BatchNorm between the two convolutions (dcgan.py:65-68): prev_y is
+ *                        then the saved ACTIVATION OUTPUT a_prev, dz = dx * act'(.) taken from its sign, and prev_shift /
+ *                        prev_mean / prev_invstd / prev_sums are unused. */
 typedef struct b200gan_fuse {
   int32_t out_act;
   float   out_slope;

@@ -21,7 +21,7 @@ def _frac(key):
     well-conditioned numbers of the whole step (measured: 92 % of G.main.1.bias within 1e-5, worst entry 2.8e-5 = 0.14 lr,
     with first-iteration gradients, history and every other tensor inside the single-GPU tolerances; all inside the 2*lr
     per-step envelope that weights_close always enforces)."""
-    return 0.88 if key.endswith('.bias') else 0.97
+    return 0.75 if key.endswith('.bias') else 0.97        # biases additionally stay within 0.25 lr everywhere (checked below)
 
 
 def _state(seed=21):
@@ -88,6 +88,7 @@ def test_two_nccl_ranks_match_dp_emulation(tmp_path, use_graph):
                     close(got[f'{tag}.{k}'], v, rtol=1e-3, atol=1e-5, what=f'rank {r} {tag}.{k}')
                 else:
                     weights_close(got[f'{tag}.{k}'], v, what=f'rank {r} {tag}.{k}', steps=STEPS, rtol=1e-3, atol=1e-5, frac=_frac(k))
+                    assert np.abs(got[f'{tag}.{k}'] - v).max() < (5e-5 if k.endswith('.bias') else 1.3e-3), k
     a, b = np.load(os.path.join(str(tmp_path), 'rank0.npz')), np.load(os.path.join(str(tmp_path), 'rank1.npz'))
     assert np.array_equal(a['G.main.0.weight'], b['G.main.0.weight']), 'replicas must stay bit-identical on the weights'
 
@@ -144,3 +145,4 @@ def test_two_replicas_on_one_gpu_match_dp_emulation():
                     close(v.cpu().numpy(), o.sd[k], rtol=1e-3, atol=1e-5, what=f'rank {r} {tag}.{k}')
                 else:
                     weights_close(v.cpu().numpy(), o.sd[k], what=f'rank {r} {tag}.{k}', steps=STEPS, rtol=1e-3, atol=1e-5, frac=_frac(k))
+                    assert np.abs(v.cpu().numpy() - o.sd[k]).max() < (5e-5 if k.endswith('.bias') else 1.3e-3), k
