@@ -59,6 +59,9 @@ struct TcConvParams {
   const __nv_bfloat16* prev_y;       // same dense NHWC layout as out
   const float *prev_scale, *prev_shift, *prev_mean, *prev_invstd;
   float prev_neg;                    // act'(z) for z <= 0: 0 (ReLU), slope (LeakyReLU), 1 (none)
+  // shared-memory plan (bytes from the 1024-aligned base): [stages][resident weights][barriers][channel accumulators]
+  int nstages, stage_stride, off_res, off_bar;
+  int resident;                      // 1: every weight tile of the layer stays in shared memory for the CTA's lifetime
 };
 
 
@@ -83,7 +86,7 @@ struct TcSmem {
   static constexpr int A_BYTES = 128 * KC * 2;
   static constexpr int B_BYTES = BN * KC * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int BAR_BYTES = 512;        // full[<=16] + empty[<=16] + acc_full[2] + acc_empty[2] + res + tmem slot
 };
 
 
@@ -101,13 +104,16 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   using S = TcSmem<BN, KC, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* acc_full = empty_bar + STAGES;     // [2]
+  const int NST = p.nstages;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.off_bar);
+  uint64_t* empty_bar = full_bar + 16;
+  uint64_t* acc_full = empty_bar + 16;         // [2]
   uint64_t* acc_empty = acc_full + 2;          // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* res_bar = acc_empty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 1);
+  uint8_t* smem_res = smem + p.off_res;
   // EPI != 0: per-CTA channel accumulators [2][cout] (flushed once at the end), EPI == 2: {scale, shift, mean, invstd}[cout]
-  float* ch_acc = reinterpret_cast<float*>(smem + STAGES * S::STAGE_BYTES + 256);
+  float* ch_acc = reinterpret_cast<float*>(smem + p.off_bar + S::BAR_BYTES);
   float4* ch_coef = reinterpret_cast<float4*>(ch_acc + 2 * p.cout);
   if (EPI == 1 || EPI == 2) {
     for (int c = threadIdx.x; c < 2 * p.cout; c += blockDim.x) ch_acc[c] = 0.f;
@@ -122,8 +128,9 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   const int num_tiles = p.num_tiles;
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < NST; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 8); }
+    mbar_init(res_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
@@ -140,6 +147,14 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   if (warp == 0) {
     // ===== TMA producer (one lane) =====
     if (lane == 0) {
+      if (p.resident) {
+        // all weight tiles [class][tap][chunk] once (n_tiles == 1): afterwards only activations stream through the ring
+        const int per_cls = p.taps * p.chunks;
+        mbar_expect_tx(res_bar, (uint32_t)(p.ncls * per_cls * S::B_BYTES));
+        for (int cls = 0; cls < p.ncls; ++cls)
+          for (int kb = 0; kb < per_cls; ++kb) tma_load_3d(smem_res + (cls * per_cls + kb) * S::B_BYTES, &map_b, res_bar, kb * KC, 0, cls);
+      }
+      const uint32_t stage_tx = p.resident ? S::A_BYTES : S::STAGE_BYTES;
       int s = 0;
       uint32_t ph = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
@@ -155,11 +170,11 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           const int cw = w0 + p.tap_dw[cls][tap], chh = h0 + p.tap_dh[cls][tap];
           for (int chunk = 0; chunk < p.chunks; ++chunk, kcol += KC) {
             mbar_wait(&empty_bar[s], ph ^ 1);
-            uint8_t* sa = smem + s * S::STAGE_BYTES;
-            mbar_expect_tx(&full_bar[s], S::STAGE_BYTES);
+            uint8_t* sa = smem + s * p.stage_stride;
+            mbar_expect_tx(&full_bar[s], stage_tx);
             tma_load_4d(sa, &map_a, &full_bar[s], chunk * KC, cw, chh, n0);
-            tma_load_3d(sa + S::A_BYTES, &map_b, &full_bar[s], kcol, cout0, cls);
-            if (++s == STAGES) { s = 0; ph ^= 1; }
+            if (!p.resident) tma_load_3d(sa + S::A_BYTES, &map_b, &full_bar[s], kcol, cout0, cls);
+            if (++s == NST) { s = 0; ph ^= 1; }
           }
         }
       }
@@ -175,15 +190,18 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       int s = 0;
       uint32_t ph = 0;
       int lt = 0;
+      if (p.resident) mbar_wait(res_bar, 0);
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++lt) {
         const int buf = lt & 1;
         mbar_wait(&acc_empty[buf], ((lt >> 1) & 1) ^ 1);   // epilogue has drained this accumulator
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + buf * BN;
+        const uint32_t res_cls = smem_u32(smem_res) + (uint32_t)((t % p.ncls) * num_kb * S::B_BYTES);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[s], ph);
           tcgen05_fence_after();
-          const uint32_t sa = smem_u32(smem + s * S::STAGE_BYTES), sb = sa + S::A_BYTES;
+          const uint32_t sa = smem_u32(smem + s * p.stage_stride);
+          const uint32_t sb = p.resident ? res_cls + (uint32_t)(kb * S::B_BYTES) : sa + S::A_BYTES;
 #pragma unroll
           for (int k = 0; k < KC / 16; ++k) {
             const uint64_t adesc = make_smem_desc(sa + k * 32, 16, SBO, LT);
@@ -191,7 +209,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             tcgen05_mma_f16(tmem_d, adesc, bdesc, idesc, (kb | k) != 0);
           }
           tcgen05_commit(&empty_bar[s]);                   // frees the smem stage when these MMAs retire
-          if (++s == STAGES) { s = 0; ph ^= 1; }
+          if (++s == NST) { s = 0; ph ^= 1; }
         }
         tcgen05_commit(&acc_full[buf]);                    // accumulator complete
       }
@@ -342,10 +360,26 @@ static bool nhwc_dense_bf16(const b200gan_view* v) {
 }
 
 template <int BN, int KC, int STAGES, int EPI>
-static int launch_tc_epi(const CUtensorMap& ma, const CUtensorMap& mb, const TcConvParams& p, dim3 grid, cudaStream_t st) {
+static int launch_tc_epi(const CUtensorMap& ma, const CUtensorMap& mb, TcConvParams p, dim3 grid, cudaStream_t st) {
   using S = TcSmem<BN, KC, STAGES>;
-  // channel accumulators / coefficients live behind the barrier block (EPI != 0), sized by the layer's channel count
-  const int smem = S::TOTAL + ((EPI == 0 || EPI == 3) ? 0 : p.cout * 8 + (EPI == 2 ? p.cout * 16 : 0) + 16);
+  // shared-memory plan.  Streaming weights: STAGES stages of (A + B), two CTAs per SM.  Resident weights (thin-K layers whose
+  // whole weight tensor is <= 64 KB): the weights once + a deeper ring of A-only stages, one CTA per SM.
+  int res_bytes = p.resident ? p.ncls * p.taps * p.chunks * S::B_BYTES : 0;
+  // two CTAs per SM must remain possible (one CTA per SM measured 30-100 % slower: a single TMA/MMA issue chain per SM does
+  // not keep the L2 request pipeline full), so resident mode needs >= 4 A-only stages next to the weights within ~110 KB
+  const int res_stages = (110 * 1024 - res_bytes) / S::A_BYTES;
+  if (p.resident && res_stages < 4) { p.resident = 0; res_bytes = 0; }
+  if (p.resident) {
+    p.stage_stride = S::A_BYTES;
+    p.nstages = res_stages > 16 ? 16 : res_stages;
+  } else {
+    p.stage_stride = S::STAGE_BYTES;
+    p.nstages = STAGES;
+  }
+  p.off_res = (p.nstages * p.stage_stride + 1023) & ~1023;
+  p.off_bar = p.off_res + res_bytes;
+  // channel accumulators / coefficients live behind the barrier block (EPI 1/2), sized by the layer's channel count
+  const int smem = 1024 + p.off_bar + S::BAR_BYTES + ((EPI == 0 || EPI == 3) ? 0 : p.cout * 8 + (EPI == 2 ? p.cout * 16 : 0) + 16);
   static int configured = 0;
   if (configured < smem) {
     B200_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, KC, STAGES, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -358,6 +392,7 @@ static int launch_tc_epi(const CUtensorMap& ma, const CUtensorMap& mb, const TcC
 
 template <int BN, int KC, int STAGES>
 static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcConvParams& p, int epi, dim3 grid, cudaStream_t st) {
+  static_assert(STAGES <= 16, "barrier block holds 16 stages");
   if (epi == 1) return launch_tc_epi<BN, KC, STAGES, 1>(ma, mb, p, grid, st);
   if (epi == 2) return launch_tc_epi<BN, KC, STAGES, 2>(ma, mb, p, grid, st);
   if (epi == 3) return launch_tc_epi<BN, KC, STAGES, 3>(ma, mb, p, grid, st);
@@ -442,6 +477,7 @@ static int tc_conv_common(const b200gan_conv* cv, const b200gan_view* in, const 
   p.n_tiles = cout / BN;
   p.ncls = up ? 4 : 1;
   p.num_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles * p.ncls;
+  p.resident = (p.n_tiles == 1 && (int64_t)p.ncls * p.taps * cin * BN * 2 <= 64 * 1024) ? 1 : 0;
   // persistent: two CTAs per SM (every configuration below fits 2 x (smem, 2*BN TMEM columns) per SM)
   const int ctas = p.num_tiles < 2 * kNumSMs ? p.num_tiles : 2 * kNumSMs;
   dim3 grid((unsigned)ctas, 1, 1);
