@@ -116,21 +116,8 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def time_dominant_kernel(pkg, torch, batch, peaks, iters=20):
-    """roofline: the D3 forward convolution (Conv2d 128->256, k4 s2 p1, 28x28 -> 14x14) timed alone."""
-    import ctypes as C
-    L = pkg._lib
-    n, ci, h, co, k = batch, 128, 28, 256, 4
-    x = torch.randn((n, h, h, ci), device='cuda').to(torch.bfloat16)
-    w = torch.randn((co, ci, k, k), device='cuda') * 0.02
-    y = torch.empty((n, h // 2, h // 2, co), device='cuda', dtype=torch.bfloat16)
-    cv = L.Conv(k, 2, 1, L.ALGO_TCGEN05)                                           # fails loudly if the tensor-core path is absent
-    wp = torch.empty(w.numel(), device='cuda', dtype=torch.bfloat16)
-    L.call('b200gan_pack_conv_weight', L.ptr(w), co, ci, k, 0, L.ptr(wp), L.stream_ptr())
-    flush = torch.empty(256 * 1024 * 1024, device='cuda', dtype=torch.uint8)      # > 126 MB L2
-
-    def launch():
-        L.call('b200gan_conv2d_fprop', C.byref(cv), C.byref(L.view_nhwc(x)), L.ptr(w), L.ptr(wp), C.byref(L.view_nhwc(y)), None, L.stream_ptr())
+def _time_launch(torch, launch, flush, iters):
+    """Average CUDA-event duration of one launch on the launching stream, L2 flushed (256 MB write) before every launch."""
     for _ in range(3):
         launch()
     torch.cuda.synchronize()
@@ -143,12 +130,67 @@ def time_dominant_kernel(pkg, torch, batch, peaks, iters=20):
         e1.record()
         torch.cuda.synchronize()
         tot += e0.elapsed_time(e1)
-    ms = tot / iters
+    return tot / iters
+
+
+def time_dominant_kernel(pkg, torch, batch, peaks, iters=20):
+    """roofline: the kernel class with the largest share of the step is conv_gemm_tc_kernel<128,64,3,*> (fprop / dgrad of
+    D2-D4 and G1-G3, 18 % of the iteration in profiles/); its representative launch, the D3 forward convolution
+    (Conv2d 128->256, k4 s2 p1, 28x28 -> 14x14, BatchNorm statistics fused in the epilogue exactly as the step runs it), is
+    timed alone.  `more` adds the other kernel families of the step, each against the roofline that bounds it."""
+    import ctypes as C
+    L = pkg._lib
+    bf = torch.bfloat16
+    flush = torch.empty(256 * 1024 * 1024, device='cuda', dtype=torch.uint8)      # > 126 MB L2
+    st = L.stream_ptr
+
+    def rnd(shape, dt=bf):
+        return torch.randn(shape, device='cuda').to(dt)
+    n, ci, h, co, k = batch, 128, 28, 256, 4
+    x, w, y = rnd((n, h, h, ci)), torch.randn((co, ci, k, k), device='cuda') * 0.02, torch.empty((n, h // 2, h // 2, co), device='cuda', dtype=bf)
+    cv = L.Conv(k, 2, 1, L.ALGO_TCGEN05)                                           # fails loudly if the tensor-core path is absent
+    wp = torch.empty(w.numel(), device='cuda', dtype=bf)
+    L.call('b200gan_pack_conv_weight', L.ptr(w), co, ci, k, 0, L.ptr(wp), st())
+    sums = torch.zeros(2 * co, device='cuda', dtype=torch.float64)
+    fz = L.fuse(bn_sums=sums)
+    ms = _time_launch(torch, lambda: L.call('b200gan_conv2d_fprop', C.byref(cv), C.byref(L.view_nhwc(x)), L.ptr(w), L.ptr(wp),
+                                            C.byref(L.view_nhwc(y)), C.byref(fz), st()), flush, iters)
     flops = 2.0 * n * (h // 2) ** 2 * co * (16 * ci)
     ach = flops / (ms * 1e-3) / 1e12
-    return {'bound': 'tensor', 'kernel': 'conv_gemm_tc_kernel: conv2d_fprop D3 (M=B*196, K=2048, N=256), bf16 tcgen05, timed alone, L2 flushed', 'achieved': ach,
-            'peak': peaks['tf_burst'], 'unit': 'TFLOP/s', 'frac': ach / peaks['tf_burst'], 'traffic': None, 'ms_per_launch': ms,
-            'peak_source': peaks['src'] + ' (burst: kernel timed alone)'}
+    more = []
+    # weight gradient of the same layer (tensor bound)
+    dy, dw, ws = rnd((n, h // 2, h // 2, co)), torch.zeros_like(w), torch.zeros_like(w)
+    m2 = _time_launch(torch, lambda: L.call('b200gan_conv2d_wgrad', C.byref(cv), C.byref(L.view_nhwc(x)), C.byref(L.view_nhwc(dy)), L.ptr(dw),
+                                            L.ptr(ws), None, st()), flush, iters)
+    more.append({'kernel': 'conv_wgrad_tc_kernel<128,256,2,4> + wgrad_finalize_kernel (D3 weight gradient)', 'bound': 'tensor',
+                 'achieved': flops / (m2 * 1e-3) / 1e12, 'peak': peaks['tf_burst'], 'unit': 'TFLOP/s', 'ms_per_launch': m2})
+    # BatchNorm backward apply on D1's tensor (HBM bound: read dz, read y, write dy)
+    yb, dz = rnd((n, 56, 56, 64)), rnd((n, 56, 56, 64))
+    vec = [torch.rand(64, device='cuda') + 0.5 for _ in range(5)]
+    bs = torch.zeros(128, device='cuda', dtype=torch.float64)
+    m3 = _time_launch(torch, lambda: L.call('b200gan_bn_act_bwd_apply', C.byref(L.view_nhwc(dz)), C.byref(L.view_nhwc(yb)), None, L.ptr(vec[0]),
+                                            L.ptr(vec[1]), L.ptr(vec[2]), L.ptr(vec[3]), L.ptr(vec[4]), L.ptr(bs), n * 56 * 56, L.ACT_NONE, 0.2,
+                                            C.byref(L.view_nhwc(dz)), None, None, st()), flush, iters)
+    byt = 3.0 * yb.numel() * 2
+    more.append({'kernel': 'bn_act_bwd_apply_dense_kernel (D1 tensor, 3 passes)', 'bound': 'hbm', 'achieved': byt / (m3 * 1e-3) / 1e9,
+                 'peak': peaks['hbm'], 'unit': 'GB/s', 'ms_per_launch': m3})
+    # image-side transposed convolution + Tanh (G5 forward; HBM bound: read the 32-channel tensor, write the image)
+    a4, w5, img = rnd((n, 112, 112, 32)), torch.randn((32, 1, 4, 4), device='cuda') * 0.02, torch.empty((n, 224, 224, 1), device='cuda', dtype=bf)
+    cva = L.Conv(4, 2, 1, L.ALGO_AUTO)
+    ft = L.fuse(out_act=L.ACT_TANH)
+    m4 = _time_launch(torch, lambda: L.call('b200gan_convT2d_fprop', C.byref(cva), C.byref(L.view_nhwc(a4)), L.ptr(w5), None,
+                                            C.byref(L.view_nhwc(img)), C.byref(ft), st()), flush, iters)
+    byt = (a4.numel() + img.numel()) * 2.0
+    more.append({'kernel': 'thin_up_tma_kernel<1> (G5 forward + Tanh)', 'bound': 'hbm', 'achieved': byt / (m4 * 1e-3) / 1e9, 'peak': peaks['hbm'],
+                 'unit': 'GB/s', 'ms_per_launch': m4})
+    for r in more:
+        r['frac'] = r['achieved'] / r['peak']
+    return {'bound': 'tensor', 'kernel': 'conv_gemm_tc_kernel<128,64,3,1>: conv2d_fprop D3 + BatchNorm statistics (M=B*196, K=2048, N=256), bf16 tcgen05, '
+                                         'timed alone with CUDA events on the launching stream, L2 flushed',
+            'achieved': ach, 'peak': peaks['tf_burst'], 'unit': 'TFLOP/s', 'frac': ach / peaks['tf_burst'],
+            'traffic': 124.8e6, 'traffic_source': 'dram__bytes_read.sum + dram__bytes_write.sum of this launch in profiles/r01_c_hot_kernels.md (ncu --set full); '
+                                                  'algorithmic bytes 154.1e6 (input 102.8e6 + output 51.4e6; part of the output is still in L2 when the kernel ends)',
+            'ms_per_launch': ms, 'peak_source': peaks['src'] + ' (burst: kernel timed alone)', 'more': more}
 
 
 def run_ours(args):
@@ -184,9 +226,12 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident timing ------------------------------------------------------------------
-    for _ in range(args.warmup):
-        tr.step(real, torch.randn((B, nz, 1, 1), device='cuda', generator=gen))
+    # ---- device-resident timing: inputs already in HBM (the trainer's static input buffers), fresh on-device noise per step
+    #      as in the reference (train_gan.py:132) -------------------------------------------------
+    in_real, in_noise = tr.input_buffers(real.shape, torch.float32, (B, nz, 1, 1))
+    in_real.copy_(real)
+    for _ in range(max(args.warmup, 3)):
+        tr.step(in_real, in_noise.normal_(generator=gen))
     barrier()
     l0 = tr.launches
     sampler = ClockSampler(local)
@@ -195,7 +240,7 @@ def run_ours(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        m = tr.step(real, torch.randn((B, nz, 1, 1), device='cuda', generator=gen))
+        m = tr.step(in_real, in_noise.normal_(generator=gen))
     e1.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -204,25 +249,52 @@ def run_ours(args):
     last = m.cpu().tolist()
 
     # ---- end to end: host buffers, H2D every step, D2H of the history scalars ----------------------
+    # The user-facing call is DCGANTrainer.step(real, noise).  Every step copies THAT step's real batch and noise from pinned
+    # host memory (on a copy stream, into one of two staging buffers, so the transfer of step i+1 overlaps the kernels of
+    # step i: plain double buffering, what a DataLoader with pin_memory + non_blocking copies gives) and reads the five
+    # history scalars back to pinned host memory.
     real_h = torch.empty((B, nc, 224, 224), dtype=torch.float32).pin_memory()
     real_h.copy_(real.cpu())
-    noise_h = torch.empty((B, nz, 1, 1), dtype=torch.float32).pin_memory()
+    noise_h = [torch.empty((B, nz, 1, 1), dtype=torch.float32).pin_memory() for _ in range(2)]
     hist_h = torch.empty(5, dtype=torch.float32).pin_memory()
-    real_d, noise_d = torch.empty_like(real), torch.empty((B, nz, 1, 1), device='cuda')
+    static_real, static_noise = tr.input_buffers(real.shape, torch.float32, (B, nz, 1, 1))
+    stage_r = [torch.empty_like(real) for _ in range(2)]
+    stage_n = [torch.empty((B, nz, 1, 1), device='cuda') for _ in range(2)]
+    copied = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+    copy_stream = torch.cuda.Stream()
 
-    def e2e_step():
-        noise_h.normal_()
-        real_d.copy_(real_h, non_blocking=True)
-        noise_d.copy_(noise_h, non_blocking=True)
-        hist_h.copy_(tr.step(real_d, noise_d), non_blocking=True)
-    for _ in range(2):
-        e2e_step()
+    def enqueue_copy(i):
+        k = i % 2
+        copied[k].synchronize()                            # host buffer k was last read by the copy issued two iterations ago
+        noise_h[k].normal_()
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[k])            # the staging buffer was read by the step two iterations ago
+            stage_r[k].copy_(real_h, non_blocking=True)
+            stage_n[k].copy_(noise_h[k], non_blocking=True)
+            copied[k].record(copy_stream)
+
+    def e2e_loop(n):
+        main = torch.cuda.current_stream()
+        for k in range(2):
+            consumed[k].record(main)
+        enqueue_copy(0)
+        for i in range(n):
+            k = i % 2
+            main.wait_event(copied[k])
+            static_real.copy_(stage_r[k])
+            static_noise.copy_(stage_n[k])
+            consumed[k].record(main)
+            if i + 1 < n:
+                enqueue_copy(i + 1)
+            hist_h.copy_(tr.step(static_real, static_noise), non_blocking=True)
+
+    e2e_loop(2)
     barrier()
     t0 = time.perf_counter()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
-    for _ in range(args.steps):
-        e2e_step()
+    e2e_loop(args.steps)
     f1.record()
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
@@ -253,7 +325,7 @@ def run_ours(args):
                        'algo': os.environ.get('B200GAN_ALGO', 'auto')},
             'model_flops_frac_of_peak': value / world * FLOP_PER_IMAGE / 1e12 / peaks['tf_sustained'],
             'roofline': roof, 'cpu_baseline': cpu,
-            'e2e': {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': real_h.numel() * 4 + noise_h.numel() * 4, 'd2h_bytes_per_step': 20,
+            'e2e': {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': real_h.numel() * 4 + noise_h[0].numel() * 4, 'd2h_bytes_per_step': 20,
                     'ms_per_step': ms_e2e / args.steps},
             'gpu_launches': launches, 'clocks': clocks, 'last_history': dict(zip(['errD', 'errG', 'D_x', 'D_G_z1', 'D_G_z2'], last)),
         }
