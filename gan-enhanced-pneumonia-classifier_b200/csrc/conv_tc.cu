@@ -16,6 +16,7 @@
 // the accumulator with tcgen05.ld and store bf16 NHWC rows.
 #include <cuda.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "ptx.cuh"
@@ -91,8 +92,10 @@ struct TcSmem {
 
 
 // Persistent kernel: each CTA walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... of the (M-tile, N-tile, class)
-// space.  Warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2..9 = epilogue (TMEM lane quarter = warp % 4,
-// column half = (warp - 2) / 4: eight warps keep enough global loads / stores in flight for the fused epilogues).  The accumulator is
+// space.  Warps 0..7 = epilogue (TMEM lane quarter = warp % 4, column half = warp / 4: eight warps keep enough global loads /
+// stores in flight for the fused epilogues), warp 8 = TMA producer, warp 9 = MMA issuer + TMEM owner.  The two single-thread
+// roles sit in the HIGHEST warp slots on purpose: the warp scheduler favours higher warp ids among eligible warps, and with
+// the roles in warps 0/1 the instruction-heavy fused epilogues delayed every TMA / MMA issue (measured +30 % kernel time).  The accumulator is
 // double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps the MMA stream of tile i+1, and the
 // smem ring keeps running across tile boundaries.  No integer division sits on the per-k-block path of the two
 // single-thread roles (a first version spent ~100 instructions per step there).
@@ -127,7 +130,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
   const int num_tiles = p.num_tiles;
 
-  if (warp == 0 && lane == 0) {
+  constexpr int kTmaWarp = 8, kMmaWarp = 9;
+  if (warp == kTmaWarp && lane == 0) {
     for (int s = 0; s < NST; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 8); }
     mbar_init(res_bar, 1);
@@ -135,7 +139,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
   }
-  if (warp == 1) {   // TMEM allocation by one full warp
+  if (warp == kMmaWarp) {   // TMEM allocation by one full warp
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
@@ -144,7 +148,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  if (warp == kTmaWarp) {
     // ===== TMA producer (one lane) =====
     if (lane == 0) {
       if (p.resident) {
@@ -180,7 +184,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       }
     }
     __syncwarp();
-  } else if (warp == 1) {
+  } else if (warp == kMmaWarp) {
     // ===== MMA issuer (one lane) =====
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
@@ -216,8 +220,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     }
     __syncwarp();
   } else {
-    // ===== epilogue: warps 2..9 =====
-    const int q = warp & 3, hcol = (warp - 2) >> 2;
+    // ===== epilogue: warps 0..7 =====
+    const int q = warp & 3, hcol = warp >> 2;
     constexpr int CW = BN / 2;                       // columns per warp
     const int row = q * 32 + lane;
     const int tw = row & (TW - 1), th = (row >> p.tw_log2) & (TH - 1), tn = row >> (p.tw_log2 + p.th_log2);
@@ -321,7 +325,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     if (EPI == 1 || EPI == 2) {
       // the eight epilogue warps (256 threads) flush the CTA's channel sums: one double atomic per channel and quantity
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      for (int c = threadIdx.x - 64; c < p.cout; c += 256) {
+      for (int c = threadIdx.x; c < p.cout; c += 256) {
         const float a0 = ch_acc[c], a1 = ch_acc[p.cout + c];
         if (a0 != 0.f) atomicAdd(p.sums + c, (double)a0);
         if (a1 != 0.f) atomicAdd(p.sums + p.cout + c, (double)a1 * (EPI == 2 ? (double)ch_coef[c].w : 1.0));
@@ -330,7 +334,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   }
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
   }
@@ -413,7 +417,10 @@ static int tc_conv_common(const b200gan_conv* cv, const b200gan_view* in, const 
                         epi.prev_y->c != out->c))
     return 1;
   const int KC = cin % 64 == 0 ? 64 : 32;
-  const int BN = cout % 128 == 0 ? 128 : (cout % 64 == 0 ? 64 : 32);
+  // 128 x 256 tiles for the wide layers (one CTA per SM, all 512 TMEM columns): a 128 x 128 tile needs 128 B/cycle/SM of
+  // operands at full MMA rate, more than the L2 delivers (the 128-wide kernel sits at ~55 % tensor-pipe with L2 at ~58 %)
+  static const bool wide = getenv("B200GAN_NO_BN256") == nullptr;
+  const int BN = (wide && cout % 256 == 0 && cin % 64 == 0) ? 256 : (cout % 128 == 0 ? 128 : (cout % 64 == 0 ? 64 : 32));
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return B200GAN_ERR_CUDA; }
   // GEMM-row pixel space: DOWN -> output pixels (OH,OW); UP -> input pixels (H,W) per parity class
@@ -479,10 +486,12 @@ static int tc_conv_common(const b200gan_conv* cv, const b200gan_view* in, const 
   p.num_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles * p.ncls;
   p.resident = (p.n_tiles == 1 && (int64_t)p.ncls * p.taps * cin * BN * 2 <= 64 * 1024) ? 1 : 0;
   // persistent: two CTAs per SM (every configuration below fits 2 x (smem, 2*BN TMEM columns) per SM)
-  const int ctas = p.num_tiles < 2 * kNumSMs ? p.num_tiles : 2 * kNumSMs;
+  const int per_sm = BN == 256 ? 1 : 2;
+  const int ctas = p.num_tiles < per_sm * kNumSMs ? p.num_tiles : per_sm * kNumSMs;
   dim3 grid((unsigned)ctas, 1, 1);
   const int e = epi.mode;
   if (KC == 64) {
+    if (BN == 256) return launch_tc<256, 64, 4>(ma, mb, p, e, grid, st);   // 4 x 48 KB, one CTA per SM
     if (BN == 128) return launch_tc<128, 64, 3>(ma, mb, p, e, grid, st);   // 3 x 32 KB
     if (BN == 64) return launch_tc<64, 64, 4>(ma, mb, p, e, grid, st);     // 4 x 24 KB
     return launch_tc<32, 64, 5>(ma, mb, p, e, grid, st);                   // 5 x 20 KB

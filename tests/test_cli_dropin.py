@@ -1,0 +1,55 @@
+"""Drop-in CLIs (CPU part): our train_gan.py / generate_synthetic.py expose exactly the reference's flags and defaults
+(src/train_gan.py:217-240, src/generate_synthetic.py:63-70; the lists below were read off the reference) plus additive flags only;
+a CPU round trip train -> generator_final.pth -> generate_synthetic writes the reference's artefacts."""
+import json
+import os
+
+import numpy as np
+import torch
+
+from gan_enhanced_pneumonia_classifier_b200 import generate_synthetic as gs
+from gan_enhanced_pneumonia_classifier_b200 import train_gan as tg
+
+REF_TRAIN_FLAGS = {
+    'data_dir': './data/processed', 'model_dir': './models', 'output_dir': './results', 'results_dir': './results/metrics',
+    'figures_dir': './results/figures', 'num_channels': 3, 'latent_dim': 100, 'feature_maps_g': 64, 'feature_maps_d': 64, 'epochs': 50,
+    'batch_size': 128, 'lr': 0.0002, 'beta1': 0.5, 'workers': 4, 'vis_batch_size': 64, 'save_interval': 500, 'checkpoint_interval': 10,
+    'cpu': False,
+}
+REF_SAMPLE_FLAGS = {'output_dir': './data/synthetic', 'num_images': 5000, 'latent_dim': 100, 'feature_maps_g': 64, 'batch_size': 64, 'cpu': False}
+
+
+def test_train_cli_keeps_reference_flags_and_defaults():
+    args = vars(tg.build_parser().parse_args([]))
+    for k, v in REF_TRAIN_FLAGS.items():
+        assert args[k] == v, k
+    assert set(args) - set(REF_TRAIN_FLAGS) == {'dtype', 'synthetic', 'max_iters', 'log_interval', 'seed'}        # additive only
+
+
+def test_sampler_cli_keeps_reference_flags_and_defaults():
+    args = vars(gs.build_parser().parse_args(['--model-path', 'x.pth']))
+    for k, v in REF_SAMPLE_FLAGS.items():
+        assert args[k] == v, k
+    assert set(args) - set(REF_SAMPLE_FLAGS) == {'model_path', 'num_channels', 'seed'}
+
+
+def test_cpu_round_trip_writes_reference_artefacts(tmp_path):
+    d = str(tmp_path)
+    argv = ['--cpu', '--synthetic', '4', '--batch-size', '2', '--epochs', '1', '--latent-dim', '8', '--feature-maps-g', '4', '--feature-maps-d', '4',
+            '--num-channels', '3', '--vis-batch-size', '2', '--model-dir', d + '/models', '--output-dir', d + '/results',
+            '--results-dir', d + '/results/metrics', '--figures-dir', d + '/results/figures', '--seed', '0', '--checkpoint-interval', '1']
+    hist = tg.main(tg.build_parser().parse_args(argv))
+    assert len(hist['G_losses_iter']) == 2 and len(hist['D_losses_epoch']) == 1
+    for f in ('models/gan/generator_final.pth', 'models/gan/discriminator_final.pth', 'models/gan/generator_epoch_001.pth',
+              'results/metrics/gan_training_history.json'):
+        assert os.path.exists(os.path.join(d, f)), f
+    assert any(n.startswith('fake_samples_epoch_001_iter_') for n in os.listdir(d + '/results/gan_images'))
+    saved = json.load(open(d + '/results/metrics/gan_training_history.json'))
+    assert set(saved) == set(tg.HISTORY_KEYS)
+    sd = torch.load(d + '/models/gan/generator_final.pth')
+    assert len(sd) == 31 and sd['main.0.weight'].shape == (8, 32, 7, 7) and sd['main.1.num_batches_tracked'].dtype == torch.int64
+    n = gs.generate_images(d + '/models/gan/generator_final.pth', d + '/synthetic', 3, 8, 4, 2, torch.device('cpu'))
+    assert n == 3 and sorted(os.listdir(d + '/synthetic')) == ['synthetic_00001.png', 'synthetic_00002.png', 'synthetic_00003.png']
+    from PIL import Image
+    img = np.asarray(Image.open(d + '/synthetic/synthetic_00001.png'))
+    assert img.shape == (224, 224, 3) and img.dtype == np.uint8

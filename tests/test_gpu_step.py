@@ -225,3 +225,29 @@ def test_fused_trainer_matches_oracle_over_three_iterations():
                 # BatchNorm biases (64 entries, sums of three ~lr-sized normalised updates) are the noisiest numbers of the step:
                 # two entries beyond 1e-5 already drop a 64-entry tensor below 0.97
                 weights_close(v.cpu().numpy(), o.sd[k], what=f'{tag}.{k}', steps=3, rtol=1e-3, atol=1e-5, frac=0.9 if k.endswith('.bias') else 0.97)
+
+
+def test_cli_train_then_sample_on_gpu(tmp_path):
+    """train_gan.py CLI (fused trainer, bf16, graph replay) -> generator_final.pth -> generate_synthetic.py on the GPU; the PNG
+    pixels must equal the oracle's eval-mode forward of the saved checkpoint on the same noise (reference generate_synthetic.py:34-54)."""
+    from PIL import Image
+    from gan_enhanced_pneumonia_classifier_b200 import generate_synthetic as gs
+    from gan_enhanced_pneumonia_classifier_b200 import train_gan as tg
+    d = str(tmp_path)
+    argv = ['--synthetic', '8', '--batch-size', '4', '--epochs', '2', '--latent-dim', '16', '--feature-maps-g', '8', '--feature-maps-d', '8',
+            '--num-channels', '3', '--vis-batch-size', '4', '--model-dir', d + '/models', '--output-dir', d + '/results',
+            '--results-dir', d + '/results/metrics', '--figures-dir', d + '/results/figures', '--seed', '0', '--dtype', 'fp32']
+    hist = tg.main(tg.build_parser().parse_args(argv))
+    assert len(hist['G_losses_iter']) == 4 and all(np.isfinite(hist['D_losses_iter']))
+    ckpt = d + '/models/gan/generator_final.pth'
+    torch.manual_seed(5)
+    gs.generate_images(ckpt, d + '/synthetic', 3, 16, 8, 2, torch.device('cuda'))
+    torch.manual_seed(5)
+    z = torch.cat([torch.randn(2, 16, 1, 1, device='cuda'), torch.randn(1, 16, 1, 1, device='cuda')]).cpu().numpy()
+    sd = {k: v.cpu().numpy() for k, v in torch.load(ckpt).items()}
+    ref, _ = orc.GeneratorOracle(16, 3, 8, sd).forward(z, train=False)
+    want = np.clip((ref * 0.5 + 0.5) * 255 + 0.5, 0, 255).astype(np.uint8).transpose(0, 2, 3, 1)
+    for i in range(3):
+        got = np.asarray(Image.open(f'{d}/synthetic/synthetic_{i + 1:05d}.png'))
+        assert got.shape == (224, 224, 3)
+        assert np.abs(got.astype(int) - want[i].astype(int)).max() <= 1, f'image {i}'       # fp32 path: at most one grey level
