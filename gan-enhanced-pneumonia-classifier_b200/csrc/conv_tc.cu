@@ -110,9 +110,12 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   const int NST = p.nstages;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.off_bar);
   uint64_t* empty_bar = full_bar + 16;
-  uint64_t* acc_full = empty_bar + 16;         // [2]
-  uint64_t* acc_empty = acc_full + 2;          // [2]
-  uint64_t* res_bar = acc_empty + 2;
+  // accumulator ring in TMEM: 4 buffers for the narrow tiles (their MMA time per tile is shorter than the epilogue's latency
+  // chain: barrier wake-up, tcgen05.ld, global stores), 2 for BN >= 128; two CTAs per SM share the 512 columns
+  constexpr int NACC = BN <= 64 ? 4 : 2;
+  uint64_t* acc_full = empty_bar + 16;         // [NACC]
+  uint64_t* acc_empty = acc_full + 4;          // [NACC]
+  uint64_t* res_bar = acc_empty + 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 1);
   uint8_t* smem_res = smem + p.off_res;
   // EPI != 0: per-CTA channel accumulators [2][cout] (flushed once at the end), EPI == 2: {scale, shift, mean, invstd}[cout]
@@ -127,13 +130,13 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int TW = 1 << p.tw_log2, TH = 1 << p.th_log2, TN = 128 >> (p.tw_log2 + p.th_log2);
-  constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+  constexpr uint32_t TMEM_COLS = NACC * BN < 32 ? 32 : NACC * BN;
   const int num_tiles = p.num_tiles;
 
   constexpr int kTmaWarp = 8, kMmaWarp = 9;
   if (warp == kTmaWarp && lane == 0) {
     for (int s = 0; s < NST; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 8); }
+    for (int b = 0; b < NACC; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 8); }
     mbar_init(res_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -195,23 +198,24 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       uint32_t ph = 0;
       int lt = 0;
       if (p.resident) mbar_wait(res_bar, 0);
+      const uint64_t adesc0 = make_smem_desc(smem_u32(smem), 16, SBO, LT);
+      const uint64_t bres0 = make_smem_desc(smem_u32(smem_res), 16, SBO, LT);
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++lt) {
-        const int buf = lt & 1;
-        mbar_wait(&acc_empty[buf], ((lt >> 1) & 1) ^ 1);   // epilogue has drained this accumulator
+        const int buf = lt % NACC;
+        mbar_wait(&acc_empty[buf], ((lt / NACC) & 1) ^ 1);   // epilogue has drained this accumulator
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + buf * BN;
-        const uint32_t res_cls = smem_u32(smem_res) + (uint32_t)((t % p.ncls) * num_kb * S::B_BYTES);
+        const uint32_t res_tile = (uint32_t)((t % p.ncls) * num_kb * S::B_BYTES);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[s], ph);
           tcgen05_fence_after();
-          const uint32_t sa = smem_u32(smem + s * p.stage_stride);
-          const uint32_t sb = p.resident ? res_cls + (uint32_t)(kb * S::B_BYTES) : sa + S::A_BYTES;
+          // base descriptors + 16-byte-unit offsets: two 64-bit adds per MMA instead of rebuilding both descriptors (the
+          // single issuing thread is the pacing resource for thin k-blocks)
+          const uint64_t adesc = adesc0 + (uint64_t)((uint32_t)(s * p.stage_stride) >> 4);
+          const uint64_t bdesc = p.resident ? bres0 + (uint64_t)((res_tile + (uint32_t)(kb * S::B_BYTES)) >> 4)
+                                            : adesc + (uint64_t)(S::A_BYTES >> 4);
 #pragma unroll
-          for (int k = 0; k < KC / 16; ++k) {
-            const uint64_t adesc = make_smem_desc(sa + k * 32, 16, SBO, LT);
-            const uint64_t bdesc = make_smem_desc(sb + k * 32, 16, SBO, LT);
-            tcgen05_mma_f16(tmem_d, adesc, bdesc, idesc, (kb | k) != 0);
-          }
+          for (int k = 0; k < KC / 16; ++k) tcgen05_mma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
           tcgen05_commit(&empty_bar[s]);                   // frees the smem stage when these MMAs retire
           if (++s == NST) { s = 0; ph ^= 1; }
         }
@@ -245,8 +249,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         ynext[0] = valid ? __ldg(yp) : make_uint4(0u, 0u, 0u, 0u);
         ynext[1] = valid ? __ldg(yp + 1) : make_uint4(0u, 0u, 0u, 0u);
       }
-      const int buf = lt & 1;
-      mbar_wait(&acc_full[buf], (lt >> 1) & 1);
+      const int buf = lt % NACC;
+      mbar_wait(&acc_full[buf], (lt / NACC) & 1);
       tcgen05_fence_after();
 #pragma unroll 1
       for (int c0 = 0; c0 < CW; c0 += 16) {
@@ -501,6 +505,327 @@ static int tc_conv_common(const b200gan_conv* cv, const b200gan_view* in, const 
   return launch_tc<32, 32, 8>(ma, mb, p, e, grid, st);                     // 8 x 10 KB
 }
 
+// ---------------------------------------------------------------------------------------------------
+// "Up" geometry for the thin layer (64 -> 32 channels: Conv2d(32->64) input gradient D1, ConvTranspose2d(64->32) forward G4):
+// all FOUR output-parity classes of a 128-pixel input tile in one CTA pass.  The generic kernel above treats every class as its
+// own tile and fetches 16 tap tiles + 16 weight tiles (320 KB) per 128 input pixels from L2; these layers are bound by exactly
+// that traffic (L2 at 60 %, tensor pipe < 20 %).  Here
+//   * ONE halo tile of the input (18 lines x 10 pixels x 64 channels = 23 KB for 16 x 8 input pixels) is fetched per tile; the nine
+//     3x3-neighbour operands are nine shifted windows into it: a K-major SWIZZLE_128B descriptor may start at any 128-byte row
+//     of a TMA-written tile and step between 8-row groups with any stride (the swizzle is a function of the shared-memory
+//     address; measured with tools/micro/desc_shift.cu), so "shift by one pixel / one line" is a start-address offset,
+//   * all weights (4 classes x 4 taps x 32 x 64 bf16 = 64 KB) stay in shared memory for the CTA's lifetime,
+//   * classes whose accumulators are adjacent in TMEM are merged into one MMA: the centre tile feeds all four classes with a
+//     single N = 128 instruction, three of the edge tiles with N = 64 (class order (0,0) (0,1) (1,1) (1,0) makes them adjacent):
+//     10 instead of 16 MMAs per 16 channels, and the 4 KB A tile is read from shared memory 10 instead of 16 times,
+//   * a warp writes both x-parities of a pixel: 128 contiguous bytes per input pixel and output row.
+// ---------------------------------------------------------------------------------------------------
+struct Up4Params {
+  int tiles_w, tiles_h, num_tiles;      // tiles of 8 (W) x 16 (H) input pixels of ONE image
+  int QH, QW, NB;
+  __nv_bfloat16* out;                 // (NB, 2QH, 2QW, 32) dense
+  double* sums;
+  const __nv_bfloat16* prev_y;
+  float prev_neg;
+  int nstages, off_res, off_bar;
+};
+
+// neighbour order: centre first (it initialises all four accumulators), then edges, then corners
+__constant__ int8_t kUp4Dh[9] = {0, -1, 1, 0, 0, -1, -1, 1, 1};
+__constant__ int8_t kUp4Dw[9] = {0, 0, 0, 1, -1, -1, 1, -1, 1};
+
+// the 40 MMAs of one tile, fully unrolled: neighbour windows and weight slots are compile-time offsets added to the two base
+// descriptors (the 14-bit start-address field cannot carry: every address stays below 256 KB)
+template <int NB, int GI>
+struct Up4Table {
+  static constexpr int dh[9] = {0, -1, 1, 0, 0, -1, -1, 1, 1};
+  static constexpr int dw[9] = {0, 0, 0, 1, -1, -1, 1, -1, 1};
+  static constexpr int first[9][2] = {{0, -1}, {0, -1}, {2, -1}, {1, -1}, {0, 3}, {0, -1}, {1, -1}, {3, -1}, {2, -1}};
+  static constexpr int count[9][2] = {{4, 0}, {2, 0}, {2, 0}, {2, 0}, {1, 1}, {1, 0}, {1, 0}, {1, 0}, {1, 0}};
+  __host__ __device__ static constexpr int slot_before(int nb, int gi) {
+    int sl = 0;
+    for (int i = 0; i < 9; ++i)
+      for (int g = 0; g < 2; ++g) {
+        if (i == nb && g == gi) return sl;
+        sl += count[i][g];
+      }
+    return sl;
+  }
+};
+
+template <int NB, int GI>
+__device__ __forceinline__ void up4_issue_group(uint32_t tmem_d, uint64_t adesc0, uint64_t bdesc0) {
+  using T = Up4Table<NB, GI>;
+  constexpr int cnt = T::count[NB][GI];
+  if constexpr (cnt > 0) {
+    constexpr uint32_t idesc = make_idesc_bf16(128, 32 * cnt, 0, 0);
+    constexpr int a_off = (1 + T::dh[NB]) * ((8 + 2) * 128) + (1 + T::dw[NB]) * 128;
+    constexpr int b_off = T::slot_before(NB, GI) * 4096;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      tcgen05_mma_f16(tmem_d + T::first[NB][GI] * 32, adesc0 + (uint64_t)((a_off + k * 32) >> 4), bdesc0 + (uint64_t)((b_off + k * 32) >> 4), idesc,
+                      (NB | k) != 0);
+  }
+}
+
+template <int NB>
+__device__ __forceinline__ void up4_issue_from(uint32_t tmem_d, uint64_t adesc0, uint64_t bdesc0) {
+  up4_issue_group<NB, 0>(tmem_d, adesc0, bdesc0);
+  up4_issue_group<NB, 1>(tmem_d, adesc0, bdesc0);
+  if constexpr (NB + 1 < 9) up4_issue_from<NB + 1>(tmem_d, adesc0, bdesc0);
+}
+
+__device__ __forceinline__ void up4_issue_tile(uint32_t tmem_d, uint64_t adesc0, uint64_t bdesc0) { up4_issue_from<0>(tmem_d, adesc0, bdesc0); }
+
+constexpr int kUp4TW = 8, kUp4TH = 16;                                  // 128 GEMM rows = 16 lines x 8 pixels of one image
+constexpr int kUp4Pitch = (kUp4TW + 2) * 128;                           // bytes between lines of the halo tile
+constexpr int kUp4TileBytes = (kUp4TH + 2) * kUp4Pitch;                 // 23040
+constexpr int kUp4Stage = (kUp4TileBytes + 1023) & ~1023;               // 23552
+
+template <int EPI>
+__global__ void __launch_bounds__(kTcThreads, 1)
+conv_up4_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Up4Params p) {
+  constexpr int WB_BYTES = 32 * 64 * 2;                              // one (class, tap) weight block
+  constexpr int NACC = 2;                                            // 2 x 128 accumulator columns
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int NST = p.nstages;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.off_bar);
+  uint64_t* empty_bar = full_bar + 16;
+  uint64_t* acc_full = empty_bar + 16;
+  uint64_t* acc_empty = acc_full + 4;
+  uint64_t* res_bar = acc_empty + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 1);
+  float* ch_acc = reinterpret_cast<float*>(smem + p.off_bar + 512);   // [2][32] (EPI 1)
+  uint8_t* smem_res = smem + p.off_res;                               // 16 weight blocks, see slot table below
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int kTmaWarp = 8, kMmaWarp = 9;
+  if (EPI == 1) for (int c = threadIdx.x; c < 64; c += blockDim.x) ch_acc[c] = 0.f;
+  if (warp == kTmaWarp && lane == 0) {
+    for (int s = 0; s < NST; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int b = 0; b < NACC; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 8); }
+    mbar_init(res_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+  }
+  if (warp == kMmaWarp) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(256));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int tiles_per_img = p.tiles_w * p.tiles_h;
+
+  // Column block b of the accumulator holds class kCls[b] = (py,px): (0,0) (0,1) (1,1) (1,0).  For neighbour (dh,dw) the
+  // classes with py in P(dh), px in P(dw) (P(-1) = {0}, P(0) = {0,1}, P(1) = {1}) take tap (jh,jw) = (py-dh, px-dw).
+  // Weight blocks are stored neighbour by neighbour in column-block order, so a run of adjacent blocks is one B operand.
+  if (warp == kTmaWarp) {
+    if (lane == 0) {
+      mbar_expect_tx(res_bar, 16 * WB_BYTES);
+      int slot = 0;
+      for (int nb = 0; nb < 9; ++nb) {
+        const int dh = kUp4Dh[nb], dw = kUp4Dw[nb];
+        for (int b = 0; b < 4; ++b) {
+          const int py = b >> 1, px = (b & 1) ^ py;                  // blocks 0..3 -> (0,0) (0,1) (1,1) (1,0)
+          const int jh = py - dh, jw = px - dw;
+          if (jh < 0 || jh > 1 || jw < 0 || jw > 1) continue;
+          tma_load_3d(smem_res + slot * WB_BYTES, &map_b, res_bar, (jh * 2 + jw) * 64, 0, py * 2 + px);
+          ++slot;
+        }
+      }
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+        const int n = t / tiles_per_img, r = t - n * tiles_per_img;
+        const int th_i = r / p.tiles_w, tw_i = r - th_i * p.tiles_w;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_expect_tx(&full_bar[s], kUp4TileBytes);
+        tma_load_4d(smem + s * kUp4Stage, &map_a, &full_bar[s], 0, tw_i * kUp4TW - 1, th_i * kUp4TH - 1, n);
+        if (++s == NST) { s = 0; ph ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == kMmaWarp) {
+    if (lane == 0) {
+      // per neighbour: up to two MMA groups (first column block, number of blocks); weight slots advance in the same order
+      // nb:            0 centre   1 (-1,0)   2 (1,0)    3 (0,1)    4 (0,-1)          5 (-1,-1) 6 (-1,1)  7 (1,-1)  8 (1,1)
+      // blocks:        0-3        0-1        2-3        1-2        0 and 3           0         1         3         2
+      // Everything below is unrolled with compile-time tables: the single issuing thread must not chase table loads or
+      // rebuild 64-bit descriptors per MMA (a first version with runtime tables took ~300 cycles per MMA instead of ~50).
+      const uint32_t res0 = smem_u32(smem_res);
+      const uint64_t bdesc0 = make_smem_desc(res0, 16, 8 * 128, 2u);
+      int s = 0;
+      uint32_t ph = 0;
+      int lt = 0;
+      mbar_wait(res_bar, 0);
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++lt) {
+        const int buf = lt % NACC;
+        mbar_wait(&acc_empty[buf], ((lt / NACC) & 1) ^ 1);
+        mbar_wait(&full_bar[s], ph);
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + buf * 128;
+        const uint64_t adesc0 = make_smem_desc(smem_u32(smem + s * kUp4Stage), 16, kUp4Pitch, 2u);
+        up4_issue_tile(tmem_d, adesc0, bdesc0);
+        tcgen05_commit(&empty_bar[s]);
+        tcgen05_commit(&acc_full[buf]);
+        if (++s == NST) { s = 0; ph ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===== epilogue: warps 0..7; TMEM lane quarter = warp % 4 (input pixel rows), half = warp / 4 = output row parity py =====
+    const int q = warp & 3, py = warp >> 2;
+    const int row = q * 32 + lane;
+    const int tw = row & (kUp4TW - 1), th = row >> 3;
+    const int64_t o_sh = (int64_t)2 * p.QW * 32, o_sn = (int64_t)2 * p.QH * o_sh;
+    int lt = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++lt) {
+      const int n = t / tiles_per_img, r = t - n * tiles_per_img;
+      const int th_i = r / p.tiles_w, tw_i = r - th_i * p.tiles_w;
+      const int iw = tw_i * kUp4TW + tw, ih = th_i * kUp4TH + th;
+      const bool valid = iw < p.QW && ih < p.QH;
+      // output pixels (2ih+py, 2iw) and (2ih+py, 2iw+1): 64 contiguous channels
+      const int64_t ooff = (int64_t)n * o_sn + (int64_t)(2 * ih + py) * o_sh + (int64_t)(2 * iw) * 32;
+      const uint4* yp = reinterpret_cast<const uint4*>(p.prev_y + ooff);
+      uint4 yv[8];
+      if (EPI == 3) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) yv[j] = valid ? __ldg(yp + j) : make_uint4(0u, 0u, 0u, 0u);
+      }
+      const int buf = lt % NACC;
+      mbar_wait(&acc_full[buf], (lt / NACC) & 1);
+      tcgen05_fence_after();
+      // this warp's two column blocks: py = 0 -> blocks 0,1 = px 0,1; py = 1 -> blocks 2,3 = px 1,0
+#pragma unroll
+      for (int bb = 0; bb < 2; ++bb) {
+        const int blk = 2 * py + bb, px = bb ^ py;
+        uint32_t v[32];
+        tcgen05_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * 128 + blk * 32, v);
+        tcgen05_wait_ld();
+        if (EPI == 3) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 y4 = yv[px * 4 + j];
+            const uint32_t w[4] = {y4.x, y4.y, y4.z, y4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float lo = __uint_as_float(w[e] << 16), hi = __uint_as_float(w[e] & 0xffff0000u);
+              v[8 * j + 2 * e] = __float_as_uint(__uint_as_float(v[8 * j + 2 * e]) * (lo > 0.f ? 1.f : p.prev_neg));
+              v[8 * j + 2 * e + 1] = __float_as_uint(__uint_as_float(v[8 * j + 2 * e + 1]) * (hi > 0.f ? 1.f : p.prev_neg));
+            }
+          }
+        }
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          __nv_bfloat162 b = __floats2bfloat162_rn(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+          pk[j] = *reinterpret_cast<uint32_t*>(&b);
+        }
+        if (valid) {
+          uint4* o = reinterpret_cast<uint4*>(p.out + ooff + px * 32);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) o[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+        }
+        if (EPI == 1) {
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            float s0[16], s1[16];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint32_t w = pk[8 * hh + j];
+              const float lo = valid ? __uint_as_float(w << 16) : 0.f, hi = valid ? __uint_as_float(w & 0xffff0000u) : 0.f;
+              s0[2 * j] = lo; s0[2 * j + 1] = hi; s1[2 * j] = lo * lo; s1[2 * j + 1] = hi * hi;
+            }
+            warp_column_sums(s0, lane);
+            warp_column_sums(s1, lane);
+            if (lane < 16) {
+              atomicAdd(&ch_acc[16 * hh + lane], s0[0]);
+              atomicAdd(&ch_acc[32 + 16 * hh + lane], s1[0]);
+            }
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+    }
+    if (EPI == 1) {
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (threadIdx.x < 64 && ch_acc[threadIdx.x] != 0.f) atomicAdd(p.sums + threadIdx.x, (double)ch_acc[threadIdx.x]);
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256));
+  }
+}
+
+template <int EPI>
+static int launch_up4(const CUtensorMap& ma, const CUtensorMap& mb, const Up4Params& p, int grid, int smem, cudaStream_t st) {
+  static int configured = 0;
+  if (configured < smem) {
+    B200_CUDA(cudaFuncSetAttribute(conv_up4_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = smem;
+  }
+  conv_up4_tc_kernel<EPI><<<grid, kTcThreads, smem, st>>>(ma, mb, p);
+  B200_LAUNCH_CHECK("conv_up4_tc_kernel");
+  return 0;
+}
+
+// returns 1 when the problem is not the 64 -> 32 channel "up" shape (or carries an epilogue this kernel does not have)
+static int tc_conv_up4(const b200gan_view* in, const void* wpacked, const b200gan_view* out, const TcEpi& epi, cudaStream_t st) {
+  static const bool enabled = getenv("B200GAN_NO_UP4") == nullptr;
+  if (!enabled || in->c != 64 || out->c != 32 || epi.mode == 2) return 1;
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return B200GAN_ERR_CUDA; }
+  if (in->h < 12 || in->w < 8) return 1;                               // small maps waste most of a 16 x 8 tile: generic kernel
+  Up4Params p{};
+  p.tiles_w = (in->w + kUp4TW - 1) / kUp4TW; p.tiles_h = (in->h + kUp4TH - 1) / kUp4TH;
+  p.num_tiles = p.tiles_w * p.tiles_h * in->n;
+  p.QH = in->h; p.QW = in->w; p.NB = in->n;
+  p.out = reinterpret_cast<__nv_bfloat16*>(out->ptr);
+  if (epi.mode == 1) {
+    p.sums = epi.sums;
+    B200_CUDA(cudaMemsetAsync(epi.sums, 0, sizeof(double) * 64, st));
+  }
+  if (epi.mode == 3) {
+    p.prev_y = reinterpret_cast<const __nv_bfloat16*>(epi.prev_y->ptr);
+    p.prev_neg = epi.act == B200GAN_ACT_RELU ? 0.f : (epi.act == B200GAN_ACT_LRELU ? epi.slope : 1.f);
+  }
+  CUtensorMap ma, mb;
+  {
+    cuuint64_t gdim[4] = {64, (cuuint64_t)in->w, (cuuint64_t)in->h, (cuuint64_t)in->n};
+    cuuint64_t gstr[3] = {128, (cuuint64_t)in->w * 128, (cuuint64_t)in->h * in->w * 128};
+    cuuint32_t box[4] = {64, kUp4TW + 2, kUp4TH + 2, 1};                // the halo tile
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&ma, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, in->ptr, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(A) failed: %d", (int)r); return B200GAN_ERR_CUDA; }
+  }
+  {
+    cuuint64_t gdim[3] = {256, 32, 4};                                 // wpacked "up" form: [class][32 rows][4 taps x 64]
+    cuuint64_t gstr[2] = {512, 512 * 32};
+    cuuint32_t box[3] = {64, 32, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&mb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(wpacked), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(B) failed: %d", (int)r); return B200GAN_ERR_CUDA; }
+  }
+  p.nstages = 6;                                                       // six halo tiles in flight
+  p.off_res = p.nstages * kUp4Stage;
+  p.off_bar = p.off_res + 16 * 4096;
+  const int smem = 1024 + p.off_bar + 512 + 256;
+  const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
+  if (epi.mode == 1) return launch_up4<1>(ma, mb, p, grid, smem, st);
+  if (epi.mode == 3) return launch_up4<3>(ma, mb, p, grid, smem, st);
+  return launch_up4<0>(ma, mb, p, grid, smem, st);
+}
+
 // `epi` describes an optional epilogue fusion (mode 0: none).  Both return 0 when the kernel ran (fusion included),
 // 1 when the problem does not qualify for the tensor-core path.
 int tc_conv_fprop(const b200gan_conv* cv, const b200gan_view* x, const void* wpacked, const b200gan_view* y, const TcEpi& epi,
@@ -509,6 +834,11 @@ int tc_conv_fprop(const b200gan_conv* cv, const b200gan_view* x, const void* wpa
 }
 int tc_conv_dgrad(const b200gan_conv* cv, const b200gan_view* dy, const void* wpacked, const b200gan_view* dx, const TcEpi& epi,
                   cudaStream_t st) {
+  if (cv->k == 4 && cv->stride == 2 && cv->pad == 1 && wpacked && nhwc_dense_bf16(dy) && nhwc_dense_bf16(dx) &&
+      (epi.mode < 2 || (nhwc_dense_bf16(epi.prev_y) && epi.prev_y->n == dx->n && epi.prev_y->h == dx->h && epi.prev_y->w == dx->w && epi.prev_y->c == dx->c))) {
+    const int t = tc_conv_up4(dy, wpacked, dx, epi, st);
+    if (t <= 0) return t;
+  }
   return tc_conv_common(cv, dy, wpacked, dx, /*up=*/true, epi, st);
 }
 
@@ -637,19 +967,21 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
       constexpr uint32_t idesc = make_idesc_bf16(128, NCO, 1, 1);       // both operands MN-major
       int s = 0, slot = 0;
       uint32_t ph = 0;
+      const uint64_t adesc0 = make_smem_desc(smem_u32(smem_a), A_BOX_BYTES, 8 * A_ROW, A_LT);
+      const uint64_t bdesc0 = make_smem_desc(smem_u32(smem_b), S::BK * 128, 8 * 128, 2u);
       for (int kbl = 0; kbl < nkb; ++kbl) {
-        const uint32_t sb = smem_u32(smem_b + slot * S::B_BYTES);
+        const uint64_t bdesc = bdesc0 + (uint64_t)((uint32_t)(slot * S::B_BYTES) >> 4);
 #pragma unroll 1
         for (int g = 0; g < G; ++g) {
           mbar_wait(&full_bar[s], ph);
           tcgen05_fence_after();
-          const uint32_t sa = smem_u32(smem_a + s * S::A_BYTES);
+          const uint64_t adesc = adesc0 + (uint64_t)((uint32_t)(s * S::A_BYTES) >> 4);
 #pragma unroll
           for (int k = 0; k < S::BK / 16; ++k) {
-            // MN-major canonical layout: LBO = distance between swizzle atoms along M/N (one TMA box), SBO = 8 pixel rows
-            const uint64_t adesc = make_smem_desc(sa + k * 16 * A_ROW, A_BOX_BYTES, 8 * A_ROW, A_LT);
-            const uint64_t bdesc = make_smem_desc(sb + k * 16 * 128, S::BK * 128, 8 * 128, 2u);
-            tcgen05_mma_f16(tmem_base + g * NCO, adesc, bdesc, idesc, (kbl | k) != 0);
+            // MN-major canonical layout: LBO = distance between swizzle atoms along M/N (one TMA box), SBO = 8 pixel rows;
+            // a k-step advances 16 pixel rows
+            tcgen05_mma_f16(tmem_base + g * NCO, adesc + (uint64_t)((k * 16 * A_ROW) >> 4), bdesc + (uint64_t)((k * 16 * 128) >> 4), idesc,
+                            (kbl | k) != 0);
           }
           tcgen05_commit(&empty_bar[s]);
           if (++s == STAGES) { s = 0; ph ^= 1; }

@@ -238,3 +238,29 @@ def test_fuse_argument_checking():
     with pytest.raises(L.B200GanError, match='extents differ'):
         f = L.fuse(dy_act=L.ACT_LRELU, dy_slope=0.2, dy_ref=L.view_nhwc(x))
         L.call('b200gan_conv2d_wgrad', C.byref(cv), C.byref(L.view_nhwc(x)), C.byref(L.view_nhwc(y)), L.ptr(w), None, C.byref(f), st())
+
+
+@pytest.mark.parametrize('case', [('bf16', 64, 32, 28), ('bf16', 64, 64, 12), ('bf16', 128, 96, 8), ('fp32', 24, 10, 6)])
+def test_dgrad_activation_only_epilogue(case):
+    """prev_* with prev_scale == NULL: the layer below has no BatchNorm (D0: Conv2d + LeakyReLU, dcgan.py:65-66); prev_y is its saved
+    activation output and the input-gradient convolution returns dx * act'(a_prev).  Cases: the fused 4-class "up" kernel
+    (64 -> 32 channels), the generic tcgen05 kernel, and the fp32 SIMT kernels."""
+    mode, co, ci, hc = case
+    dt = torch.float32 if mode == 'fp32' else torch.bfloat16
+    rt = (lambda a: a) if mode == 'fp32' else bf16_round
+    tol = dict(rtol=1e-4, atol=1e-5) if mode == 'fp32' else dict(rtol=2e-2, atol=2e-2)
+    n = 3
+    w = rt(rnd((co, ci, 4, 4), 1, 0.05))
+    wd = torch.from_numpy(w).cuda()
+    wp = torch.empty(w.size, device='cuda', dtype=torch.bfloat16)
+    L.call('b200gan_pack_conv_weight', L.ptr(wd), co, ci, 4, 1, L.ptr(wp), st())
+    dy = rt(rnd((n, co, hc, hc), 2))
+    a_prev = rt(rnd((n, ci, 2 * hc, 2 * hc), 3))
+    dy_t, dy_v = dev_nhwc(dy, dt)
+    ap_t, ap_v = dev_nhwc(a_prev, dt)
+    dz_t = torch.full((n, 2 * hc, 2 * hc, ci), float('nan'), device='cuda', dtype=dt)
+    cv = conv()
+    f = L.fuse(prev_act=L.ACT_LRELU, prev_slope=SLOPE, prev_y=ap_v)
+    L.call('b200gan_conv2d_dgrad', C.byref(cv), C.byref(dy_v), L.ptr(wd), L.ptr(wp), C.byref(L.view_nhwc(dz_t)), C.byref(f), st())
+    ref = orc.conv2d_dgrad(dy, w, 2, 1, (2 * hc, 2 * hc)) * np.where(a_prev > 0, 1.0, SLOPE).astype(np.float32)
+    close(back_nchw(dz_t, True), ref, what=f'dgrad + activation-only epilogue {case}', **tol)

@@ -1,0 +1,27 @@
+#!/usr/bin/env python
+"""Launch ONE convolution of the step a few times (for a single-kernel ncu capture). usage: one_kernel.py {d1_up|d1_down|d3_down} [B]"""
+import ctypes as C, os, sys
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import gan_enhanced_pneumonia_classifier_b200 as pkg
+L = pkg._lib
+which = sys.argv[1] if len(sys.argv) > 1 else 'd1_up'
+B = int(sys.argv[2]) if len(sys.argv) > 2 else 512
+st = L.stream_ptr
+bf = torch.bfloat16
+cfg = {'d1_up': (32, 112, 64), 'd1_down': (32, 112, 64), 'd3_down': (128, 28, 256), 'd2_up': (64, 56, 128)}[which]
+ci, h, co = cfg
+x = torch.randn((B, h, h, ci), device='cuda').to(bf); dy = torch.randn((B, h // 2, h // 2, co), device='cuda').to(bf)
+w = torch.randn((co, ci, 4, 4), device='cuda') * 0.02
+wd = torch.empty(w.numel(), device='cuda', dtype=bf); wu = torch.empty(w.numel(), device='cuda', dtype=bf)
+L.call('b200gan_pack_conv_weight', L.ptr(w), co, ci, 4, 0, L.ptr(wd), st()); L.call('b200gan_pack_conv_weight', L.ptr(w), co, ci, 4, 1, L.ptr(wu), st())
+y = torch.empty_like(dy); dx = torch.empty_like(x)
+cv = L.Conv(4, 2, 1, L.ALGO_TCGEN05)
+for _ in range(3):
+    if which.endswith('up'):
+        L.call('b200gan_conv2d_dgrad', C.byref(cv), C.byref(L.view_nhwc(dy)), L.ptr(w), L.ptr(wu), C.byref(L.view_nhwc(dx)), None, st())
+    else:
+        L.call('b200gan_conv2d_fprop', C.byref(cv), C.byref(L.view_nhwc(x)), L.ptr(w), L.ptr(wd), C.byref(L.view_nhwc(y)), None, st())
+torch.cuda.synchronize()
+print('done')
