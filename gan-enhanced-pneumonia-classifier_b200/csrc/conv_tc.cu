@@ -527,7 +527,7 @@ struct Up4Params {
   double* sums;
   const __nv_bfloat16* prev_y;
   float prev_neg;
-  int nstages, off_res, off_bar;
+  int nstages, off_res, off_bar, off_y;
 };
 
 // neighbour order: centre first (it initialises all four accumulators), then edges, then corners
@@ -563,8 +563,8 @@ __device__ __forceinline__ void up4_issue_group(uint32_t tmem_d, uint64_t adesc0
     constexpr int b_off = T::slot_before(NB, GI) * 4096;
 #pragma unroll
     for (int k = 0; k < 4; ++k)
-      tcgen05_mma_f16(tmem_d + T::first[NB][GI] * 32, adesc0 + (uint64_t)((a_off + k * 32) >> 4), bdesc0 + (uint64_t)((b_off + k * 32) >> 4), idesc,
-                      (NB | k) != 0);
+      tcgen05_mma_f16_elect(tmem_d + T::first[NB][GI] * 32, adesc0 + (uint64_t)((a_off + k * 32) >> 4), bdesc0 + (uint64_t)((b_off + k * 32) >> 4),
+                            idesc, (NB | k) != 0);
   }
 }
 
@@ -577,6 +577,9 @@ __device__ __forceinline__ void up4_issue_from(uint32_t tmem_d, uint64_t adesc0,
 
 __device__ __forceinline__ void up4_issue_tile(uint32_t tmem_d, uint64_t adesc0, uint64_t bdesc0) { up4_issue_from<0>(tmem_d, adesc0, bdesc0); }
 
+// byte offset of 16-byte chunk `chunk` of pixel `pix` in a tile of 64-byte pixel rows written / read with SWIZZLE_64B
+__device__ __forceinline__ uint32_t sw64(int pix, int chunk) { return (uint32_t)pix * 64u + (uint32_t)((chunk ^ ((pix >> 1) & 3)) << 4); }
+
 constexpr int kUp4TW = 8, kUp4TH = 16;                                  // 128 GEMM rows = 16 lines x 8 pixels of one image
 constexpr int kUp4Pitch = (kUp4TW + 2) * 128;                           // bytes between lines of the halo tile
 constexpr int kUp4TileBytes = (kUp4TH + 2) * kUp4Pitch;                 // 23040
@@ -584,9 +587,12 @@ constexpr int kUp4Stage = (kUp4TileBytes + 1023) & ~1023;               // 23552
 
 template <int EPI>
 __global__ void __launch_bounds__(kTcThreads, 1)
-conv_up4_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Up4Params p) {
+conv_up4_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_y,
+                   const __grid_constant__ CUtensorMap map_o, const Up4Params p) {
   constexpr int WB_BYTES = 32 * 64 * 2;                              // one (class, tap) weight block
-  constexpr int NACC = 2;                                            // 2 x 128 accumulator columns
+  constexpr int NACC = 4;                                            // 4 x 128 accumulator columns: all of TMEM (one CTA per SM)
+  constexpr int YST = 3, Y_BYTES = 32 * 16 * 64;                     // output tiles (32 lines x 16 pixels x 32 ch) staged for the TMA
+                                                                     // store; with EPI 3 the saved activation is TMA-loaded into them first
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int NST = p.nstages;
@@ -595,7 +601,10 @@ conv_up4_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   uint64_t* acc_full = empty_bar + 16;
   uint64_t* acc_empty = acc_full + 4;
   uint64_t* res_bar = acc_empty + 4;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 1);
+  uint64_t* y_full = res_bar + 1;              // [YST]
+  uint64_t* y_empty = y_full + 4;              // [YST]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(y_empty + 4);
+  uint8_t* smem_y = smem + p.off_y;
   float* ch_acc = reinterpret_cast<float*>(smem + p.off_bar + 512);   // [2][32] (EPI 1)
   uint8_t* smem_res = smem + p.off_res;                               // 16 weight blocks, see slot table below
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -605,12 +614,15 @@ conv_up4_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     for (int s = 0; s < NST; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int b = 0; b < NACC; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 8); }
     mbar_init(res_bar, 1);
+    for (int b = 0; b < YST; ++b) { mbar_init(&y_full[b], 1); mbar_init(&y_empty[b], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (EPI == 3) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_y) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_o) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
   }
   if (warp == kMmaWarp) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(256));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   tcgen05_fence_before();
@@ -636,8 +648,8 @@ conv_up4_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           ++slot;
         }
       }
-      int s = 0;
-      uint32_t ph = 0;
+      int s = 0, ys = 0;
+      uint32_t ph = 0, yph = 0;
       for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
         const int n = t / tiles_per_img, r = t - n * tiles_per_img;
         const int th_i = r / p.tiles_w, tw_i = r - th_i * p.tiles_w;
@@ -645,16 +657,26 @@ conv_up4_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         mbar_expect_tx(&full_bar[s], kUp4TileBytes);
         tma_load_4d(smem + s * kUp4Stage, &map_a, &full_bar[s], 0, tw_i * kUp4TW - 1, th_i * kUp4TH - 1, n);
         if (++s == NST) { s = 0; ph ^= 1; }
+        if (EPI == 3) {
+          // the saved activation under this tile's output (32 lines x 16 pixels), for the epilogue: staged by TMA because a
+          // per-thread global load of 128 bytes at a 128-byte lane stride costs 32 L1 wavefronts per instruction
+          mbar_wait(&y_empty[ys], yph ^ 1);
+          mbar_expect_tx(&y_full[ys], Y_BYTES);
+          tma_load_4d(smem_y + ys * Y_BYTES, &map_y, &y_full[ys], 0, 2 * tw_i * kUp4TW, 2 * th_i * kUp4TH, n);
+          if (++ys == YST) { ys = 0; yph ^= 1; }
+        }
       }
     }
     __syncwarp();
   } else if (warp == kMmaWarp) {
-    if (lane == 0) {
+    // ===== MMA issuer: the whole warp runs the loop (uniform control flow), one elected lane issues each instruction =====
+    {
       // per neighbour: up to two MMA groups (first column block, number of blocks); weight slots advance in the same order
       // nb:            0 centre   1 (-1,0)   2 (1,0)    3 (0,1)    4 (0,-1)          5 (-1,-1) 6 (-1,1)  7 (1,-1)  8 (1,1)
       // blocks:        0-3        0-1        2-3        1-2        0 and 3           0         1         3         2
-      // Everything below is unrolled with compile-time tables: the single issuing thread must not chase table loads or
-      // rebuild 64-bit descriptors per MMA (a first version with runtime tables took ~300 cycles per MMA instead of ~50).
+      // Everything is unrolled with compile-time tables (Up4Table): the issuing warp must not chase table loads or rebuild
+      // 64-bit descriptors per MMA (a first version with runtime tables took ~300 cycles per MMA instead of ~50).
+      const uint32_t tm0 = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint32_t res0 = smem_u32(smem_res);
       const uint64_t bdesc0 = make_smem_desc(res0, 16, 8 * 128, 2u);
       int s = 0;
@@ -666,11 +688,11 @@ conv_up4_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         mbar_wait(&acc_empty[buf], ((lt / NACC) & 1) ^ 1);
         mbar_wait(&full_bar[s], ph);
         tcgen05_fence_after();
-        const uint32_t tmem_d = tmem_base + buf * 128;
+        const uint32_t tmem_d = tm0 + buf * 128;
         const uint64_t adesc0 = make_smem_desc(smem_u32(smem + s * kUp4Stage), 16, kUp4Pitch, 2u);
         up4_issue_tile(tmem_d, adesc0, bdesc0);
-        tcgen05_commit(&empty_bar[s]);
-        tcgen05_commit(&acc_full[buf]);
+        tcgen05_commit_elect(&empty_bar[s]);
+        tcgen05_commit_elect(&acc_full[buf]);
         if (++s == NST) { s = 0; ph ^= 1; }
       }
     }
@@ -681,19 +703,30 @@ conv_up4_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     const int row = q * 32 + lane;
     const int tw = row & (kUp4TW - 1), th = row >> 3;
     const int64_t o_sh = (int64_t)2 * p.QW * 32, o_sn = (int64_t)2 * p.QH * o_sh;
-    int lt = 0;
-    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++lt) {
+    // (valid, output offset) of this thread's pixel pair in tile t
+    auto locate = [&](int t, bool& valid) -> int64_t {
       const int n = t / tiles_per_img, r = t - n * tiles_per_img;
       const int th_i = r / p.tiles_w, tw_i = r - th_i * p.tiles_w;
       const int iw = tw_i * kUp4TW + tw, ih = th_i * kUp4TH + th;
-      const bool valid = iw < p.QW && ih < p.QH;
+      valid = iw < p.QW && ih < p.QH && t < p.num_tiles;
       // output pixels (2ih+py, 2iw) and (2ih+py, 2iw+1): 64 contiguous channels
-      const int64_t ooff = (int64_t)n * o_sn + (int64_t)(2 * ih + py) * o_sh + (int64_t)(2 * iw) * 32;
-      const uint4* yp = reinterpret_cast<const uint4*>(p.prev_y + ooff);
+      return (int64_t)n * o_sn + (int64_t)(2 * ih + py) * o_sh + (int64_t)(2 * iw) * 32;
+    };
+    int lt = 0, ys = 0;
+    uint32_t yph = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++lt) {
+      bool valid;
+      (void)locate(t, valid);
+      uint8_t* yt = smem_y + ys * Y_BYTES;
+      // this thread's two output pixels (line 2th+py, pixels 2tw and 2tw+1) inside the 64B-swizzled 32 x 16 pixel tile
+      const int pix = (2 * th + py) * 16 + 2 * tw;
       uint4 yv[8];
       if (EPI == 3) {
+        mbar_wait(&y_full[ys], yph);                    // saved activation landed (the producer waited for the buffer)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) yv[j] = valid ? __ldg(yp + j) : make_uint4(0u, 0u, 0u, 0u);
+        for (int j = 0; j < 8; ++j) yv[j] = *reinterpret_cast<const uint4*>(yt + sw64(pix + (j >> 2), j & 3));
+      } else {
+        mbar_wait(&y_empty[ys], yph ^ 1);               // the TMA store that last used this buffer has read it
       }
       const int buf = lt % NACC;
       mbar_wait(&acc_full[buf], (lt / NACC) & 1);
@@ -724,11 +757,10 @@ conv_up4_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           __nv_bfloat162 b = __floats2bfloat162_rn(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
           pk[j] = *reinterpret_cast<uint32_t*>(&b);
         }
-        if (valid) {
-          uint4* o = reinterpret_cast<uint4*>(p.out + ooff + px * 32);
+        // into the staging tile (conflict-free thanks to the swizzle); rows outside the image are clipped by the TMA store
 #pragma unroll
-          for (int j = 0; j < 4; ++j) o[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-        }
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<uint4*>(yt + sw64(pix + px, j)) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
         if (EPI == 1) {
 #pragma unroll
           for (int hh = 0; hh < 2; ++hh) {
@@ -751,7 +783,23 @@ conv_up4_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      // one coalesced TMA store of the whole 32 KB tile instead of 16-byte stores at a 128-byte lane stride
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (threadIdx.x == 0) {
+        const int n = t / tiles_per_img, r = t - n * tiles_per_img;
+        const int th_i = r / p.tiles_w, tw_i = r - th_i * p.tiles_w;
+        asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(&map_o), "r"(smem_u32(yt)), "r"(0),
+                     "r"(2 * tw_i * kUp4TW), "r"(2 * th_i * kUp4TH), "r"(n)
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        // the store issued one tile ago has finished READING its buffer: hand that buffer back
+        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        if (lt > 0) mbar_arrive(&y_empty[(ys + YST - 1) % YST]);
+      }
+      if (++ys == YST) { ys = 0; yph ^= 1; }
     }
+    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // all stores complete before the CTA exits
     if (EPI == 1) {
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (threadIdx.x < 64 && ch_acc[threadIdx.x] != 0.f) atomicAdd(p.sums + threadIdx.x, (double)ch_acc[threadIdx.x]);
@@ -761,18 +809,19 @@ conv_up4_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   __syncthreads();
   if (warp == kMmaWarp) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
   }
 }
 
 template <int EPI>
-static int launch_up4(const CUtensorMap& ma, const CUtensorMap& mb, const Up4Params& p, int grid, int smem, cudaStream_t st) {
+static int launch_up4(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& my, const CUtensorMap& mo, const Up4Params& p, int grid, int smem,
+                      cudaStream_t st) {
   static int configured = 0;
   if (configured < smem) {
     B200_CUDA(cudaFuncSetAttribute(conv_up4_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = smem;
   }
-  conv_up4_tc_kernel<EPI><<<grid, kTcThreads, smem, st>>>(ma, mb, p);
+  conv_up4_tc_kernel<EPI><<<grid, kTcThreads, smem, st>>>(ma, mb, my, mo, p);
   B200_LAUNCH_CHECK("conv_up4_tc_kernel");
   return 0;
 }
@@ -816,14 +865,28 @@ static int tc_conv_up4(const b200gan_view* in, const void* wpacked, const b200ga
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(B) failed: %d", (int)r); return B200GAN_ERR_CUDA; }
   }
-  p.nstages = 6;                                                       // six halo tiles in flight
+  // output tile (and, for the mask epilogue, the saved activation under it): 32 lines x 16 pixels x 32 channels, 64B swizzle
+  CUtensorMap my, mo;
+  for (int which = 0; which < 2; ++which) {
+    void* base = which == 0 ? out->ptr : (epi.mode == 3 ? epi.prev_y->ptr : out->ptr);
+    cuuint64_t gdim[4] = {32, (cuuint64_t)out->w, (cuuint64_t)out->h, (cuuint64_t)out->n};
+    cuuint64_t gstr[3] = {64, (cuuint64_t)out->w * 64, (cuuint64_t)out->h * out->w * 64};
+    cuuint32_t box[4] = {32, 2 * kUp4TW, 2 * kUp4TH, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(which == 0 ? &mo : &my, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(out) failed: %d", (int)r); return B200GAN_ERR_CUDA; }
+  }
+  // One CTA per SM: two halo tiles in flight (23 KB each; the fill traffic is small) + all weights (64 KB) + three output staging tiles
+  p.nstages = 2;
   p.off_res = p.nstages * kUp4Stage;
-  p.off_bar = p.off_res + 16 * 4096;
+  p.off_y = p.off_res + 16 * 4096;
+  p.off_bar = p.off_y + 3 * 32 * 16 * 64;
   const int smem = 1024 + p.off_bar + 512 + 256;
   const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
-  if (epi.mode == 1) return launch_up4<1>(ma, mb, p, grid, smem, st);
-  if (epi.mode == 3) return launch_up4<3>(ma, mb, p, grid, smem, st);
-  return launch_up4<0>(ma, mb, p, grid, smem, st);
+  if (epi.mode == 1) return launch_up4<1>(ma, mb, my, mo, p, grid, smem, st);
+  if (epi.mode == 3) return launch_up4<3>(ma, mb, my, mo, p, grid, smem, st);
+  return launch_up4<0>(ma, mb, my, mo, p, grid, smem, st);
 }
 
 // `epi` describes an optional epilogue fusion (mode 0: none).  Both return 0 when the kernel ran (fusion included),

@@ -222,9 +222,13 @@ def test_fused_trainer_matches_oracle_over_three_iterations():
             elif 'running' in k:
                 close(v.cpu().numpy(), o.sd[k], rtol=1e-3, atol=1e-5, what=k)
             else:
-                # BatchNorm biases (64 entries, sums of three ~lr-sized normalised updates) are the noisiest numbers of the step:
-                # two entries beyond 1e-5 already drop a 64-entry tensor below 0.97
-                weights_close(v.cpu().numpy(), o.sd[k], what=f'{tag}.{k}', steps=3, rtol=1e-3, atol=1e-5, frac=0.9 if k.endswith('.bias') else 0.97)
+                if k.endswith('.bias'):
+                    # BatchNorm biases (8-64 entries, each the sum of three ~lr-sized normalised Adam updates of a near-cancelling
+                    # gradient) are the noisiest numbers of the step: fp32 atomics alone move single entries by ~2e-5 from run to
+                    # run, so a fraction-of-entries criterion is meaningless on them; every entry must stay within 0.25 lr
+                    assert np.abs(v.cpu().numpy() - o.sd[k]).max() < 5e-5, f'{tag}.{k}'
+                else:
+                    weights_close(v.cpu().numpy(), o.sd[k], what=f'{tag}.{k}', steps=3, rtol=1e-3, atol=1e-5, frac=0.97)
 
 
 def test_cli_train_then_sample_on_gpu(tmp_path):

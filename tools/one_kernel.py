@@ -18,9 +18,30 @@ wd = torch.empty(w.numel(), device='cuda', dtype=bf); wu = torch.empty(w.numel()
 L.call('b200gan_pack_conv_weight', L.ptr(w), co, ci, 4, 0, L.ptr(wd), st()); L.call('b200gan_pack_conv_weight', L.ptr(w), co, ci, 4, 1, L.ptr(wu), st())
 y = torch.empty_like(dy); dx = torch.empty_like(x)
 cv = L.Conv(4, 2, 1, L.ALGO_TCGEN05)
+epi = sys.argv[3] if len(sys.argv) > 3 else 'none'
+aprev = torch.randn((B, h, h, ci), device='cuda').to(bf)
+sums = torch.zeros(2 * ci, device='cuda', dtype=torch.float64)
+apv = L.view_nhwc(aprev)
+fz = None
+if epi == 'mask':
+    fz = L.fuse(prev_act=L.ACT_LRELU, prev_slope=0.2, prev_y=apv)
+flush = torch.empty(256 << 20, device='cuda', dtype=torch.uint8)
+def up():
+    if epi == 'stats':
+        f1 = L.fuse(bn_sums=sums)
+        L.call('b200gan_convT2d_fprop', C.byref(cv), C.byref(L.view_nhwc(dy)), L.ptr(w), L.ptr(wu), C.byref(L.view_nhwc(dx)), C.byref(f1), st())
+    else:
+        L.call('b200gan_conv2d_dgrad', C.byref(cv), C.byref(L.view_nhwc(dy)), L.ptr(w), L.ptr(wu), C.byref(L.view_nhwc(dx)), C.byref(fz) if fz is not None else None, st())
+if len(sys.argv) > 4:
+    for _ in range(3): up()
+    torch.cuda.synchronize(); tot = 0
+    for _ in range(10):
+        flush.zero_(); e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(); up(); e1.record(); torch.cuda.synchronize(); tot += e0.elapsed_time(e1)
+    print(which, epi, 'ms', tot / 10); sys.exit(0)
 for _ in range(3):
     if which.endswith('up'):
-        L.call('b200gan_conv2d_dgrad', C.byref(cv), C.byref(L.view_nhwc(dy)), L.ptr(w), L.ptr(wu), C.byref(L.view_nhwc(dx)), None, st())
+        up()
     else:
         L.call('b200gan_conv2d_fprop', C.byref(cv), C.byref(L.view_nhwc(x)), L.ptr(w), L.ptr(wd), C.byref(L.view_nhwc(y)), None, st())
 torch.cuda.synchronize()
