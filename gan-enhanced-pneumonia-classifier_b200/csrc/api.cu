@@ -34,7 +34,7 @@ int tc_conv_wgrad(const b200gan_conv*, const b200gan_view* x, const b200gan_view
 int tc_pack_weight(const float* w, int Co, int Ci, int k, int form, void* out, cudaStream_t);
 // image-side layers on warp-level MMAs (conv_thin_mma.cu): same return convention
 int thin_down(const b200gan_view* fine, const b200gan_view* fine_ref, int fine_act, const float* w, const b200gan_view* coarse, int out_act,
-              float slope, cudaStream_t);
+              float slope, const TcEpi& epi, cudaStream_t);
 int thin_up(const b200gan_view* coarse, const b200gan_view* coarse_ref, int coarse_act, float slope, const float* w, const b200gan_view* fine,
             int out_act, cudaStream_t);
 int thin_wgrad(const b200gan_view* fine, const b200gan_view* fine_ref, int fine_act, const b200gan_view* coarse, const b200gan_view* coarse_ref,
@@ -170,7 +170,16 @@ static int conv_dispatch(Prim prim, bool transposed, const b200gan_conv* cv, con
     // image-side layers (warp-level MMA, fused activations), the latent GEMM and the 7x7 GEMV
     const bool k4 = cv->k == 4 && cv->stride == 2 && cv->pad == 1;
     if (t > 0 && k4) {
-      if (prim == FPROP) t = thin_down(fine, fz.g_ref, fz.g_act, w, coarse, fz.out_act, fz.g_ref ? fz.g_slope : fz.out_slope, st);
+      if (prim == FPROP) {
+        TcEpi epi;                                   // the image-side "down" kernel absorbs the BatchNorm fusions too
+        if (bn_sums) { epi.mode = 1; epi.sums = bn_sums; }
+        if (prev_bn) {
+          epi.mode = 2; epi.sums = fuse->prev_sums; epi.prev_y = fuse->prev_y; epi.scale = fuse->prev_scale; epi.shift = fuse->prev_shift;
+          epi.mean = fuse->prev_mean; epi.invstd = fuse->prev_invstd; epi.act = fuse->prev_act; epi.slope = fuse->prev_slope;
+        }
+        t = (prev && !prev_bn) ? 1 : thin_down(fine, fz.g_ref, fz.g_act, w, coarse, fz.out_act, fz.g_ref ? fz.g_slope : fz.out_slope, epi, st);
+        if (t == 0) { bn_sums = nullptr; prev = false; }
+      }
       else if (prim == DGRAD) t = thin_up(coarse, fz.g_ref, fz.g_act, fz.g_slope, w, fine, fz.out_act, st);
       else t = thin_wgrad(fine, grad_is_coarse ? nullptr : fz.g_ref, fz.g_act, coarse, grad_is_coarse ? fz.g_ref : nullptr, fz.g_act, fz.g_slope, dw, st);
       if (t < 0) return t;

@@ -30,6 +30,13 @@ struct ThinArgs {
   float slope;
   int fine_vec, ref_vec;               // 4-wide vector loads along W are legal for fine / fine_ref
   int RT;                              // coarse rows per tile of the TMA-staged kernels
+  // down only: BatchNorm fusions on the 32-channel result (b200gan_fuse): epi 1 = statistics of the result (bn_sums),
+  // epi 2 = the result is the gradient w.r.t. act(BN(prev_y)): dz = dx * act'(scale*prev_y + shift), sums of dz and dz*xhat
+  int epi;
+  double* sums;
+  const __nv_bfloat16* prev_y;
+  const float *prev_scale, *prev_shift, *prev_mean, *prev_invstd;
+  float prev_neg;
 };
 
 __device__ __forceinline__ float tanh_fast(float x) {       // MUFU.TANH: 2^-11 relative error, below the bf16 storage rounding
@@ -198,7 +205,7 @@ __device__ __forceinline__ void stage_coarse(__nv_bfloat16* S, int rows, int col
 // MMA column n = 8j + g of n-tile j is mapped to channel 8*(g>>1) + 2j + (g&1), so that lane (g,t) ends up with the
 // eight consecutive channels 8t..8t+7 of its pixel: one 16-byte store per pixel row, fully coalesced across the warp.
 // ---------------------------------------------------------------------------------------------------
-template <int NC>
+template <int NC, int EPI>
 __global__ void __launch_bounds__(256) thin_down_mma_kernel(const ThinArgs a) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   __nv_bfloat16* S = reinterpret_cast<__nv_bfloat16*>(smem_raw);
@@ -216,6 +223,14 @@ __global__ void __launch_bounds__(256) thin_down_mma_kernel(const ThinArgs a) {
     }
   const int WB = a.W >> 4, mtiles = a.R * WB;
   const int kh_lo = t >> 1, kw0 = (t & 1) * 2;
+  float ssum[8], ssq[8], cf_scale[8], cf_shift[8], cf_mean[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    ssum[c] = 0.f; ssq[c] = 0.f;
+    cf_scale[c] = EPI == 2 ? a.prev_scale[8 * t + c] : 1.f;
+    cf_shift[c] = EPI == 2 ? a.prev_shift[8 * t + c] : 0.f;
+    cf_mean[c] = EPI == 2 ? a.prev_mean[8 * t + c] : 0.f;
+  }
   for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
     const int n = tile / a.tiles_per_img, oh0 = (tile - n * a.tiles_per_img) * a.R;
     __syncthreads();                       // previous tile fully consumed
@@ -253,14 +268,61 @@ __global__ void __launch_bounds__(256) thin_down_mma_kernel(const ThinArgs a) {
 #pragma unroll
           for (int e = 0; e < 4; ++e) acc[j][e] = fmaxf(acc[j][e], 0.f);
       }
-      __nv_bfloat16* o = a.coarse_out + (((int64_t)n * a.H + oh) * a.W + ow) * 32 + 8 * t;
+      const int64_t ooff = (((int64_t)n * a.H + oh) * a.W + ow) * 32 + 8 * t;
+      // lane (g,t) holds channels 8t..8t+7 of pixels ow and ow+8: value index c = 2j+e <-> acc[j][e] (row g), acc[j][2+e] (row g+8)
+      float yv[2][8];
+      if (EPI == 2) {
+        unpack8(__ldg(reinterpret_cast<const uint4*>(a.prev_y + ooff)), yv[0]);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(a.prev_y + ooff + 8 * 32)), yv[1]);
+#pragma unroll
+        for (int hrow = 0; hrow < 2; ++hrow)
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float z = fmaf(yv[hrow][c], cf_scale[c], cf_shift[c]);
+            acc[c >> 1][2 * hrow + (c & 1)] *= z > 0.f ? 1.f : a.prev_neg;
+          }
+      }
       uint4 lo, hi;
       lo.x = pack_bf16x2(acc[0][0], acc[0][1]); lo.y = pack_bf16x2(acc[1][0], acc[1][1]);
       lo.z = pack_bf16x2(acc[2][0], acc[2][1]); lo.w = pack_bf16x2(acc[3][0], acc[3][1]);
       hi.x = pack_bf16x2(acc[0][2], acc[0][3]); hi.y = pack_bf16x2(acc[1][2], acc[1][3]);
       hi.z = pack_bf16x2(acc[2][2], acc[2][3]); hi.w = pack_bf16x2(acc[3][2], acc[3][3]);
+      __nv_bfloat16* o = a.coarse_out + ooff;
       *reinterpret_cast<uint4*>(o) = lo;
       *reinterpret_cast<uint4*>(o + 8 * 32) = hi;
+      if (EPI != 0) {
+        // per-thread channel sums over every pixel this thread produces (the thread's eight channels never change);
+        // the statistics are those of the stored (bf16-rounded) values
+        float r0[8], r1[8];
+        unpack8(lo, r0);
+        unpack8(hi, r1);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          ssum[c] += r0[c] + r1[c];
+          if (EPI == 1) ssq[c] = fmaf(r0[c], r0[c], fmaf(r1[c], r1[c], ssq[c]));
+          else ssq[c] = fmaf(r0[c], yv[0][c] - cf_mean[c], fmaf(r1[c], yv[1][c] - cf_mean[c], ssq[c]));
+        }
+      }
+    }
+  }
+  if (EPI != 0) {
+    // reduce over the eight row lanes g (lane = 4g + t), then over the warps through shared memory, one fp64 atomic per channel
+    float* red = reinterpret_cast<float*>(smem_raw);           // [2][32], the staging tile is no longer needed
+    __syncthreads();
+    if (threadIdx.x < 64) red[threadIdx.x] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      float v0 = ssum[c], v1 = ssq[c];
+#pragma unroll
+      for (int off = 4; off < 32; off <<= 1) { v0 += __shfl_xor_sync(0xffffffffu, v0, off); v1 += __shfl_xor_sync(0xffffffffu, v1, off); }
+      if (g == 0) { atomicAdd(&red[8 * t + c], v0); atomicAdd(&red[32 + 8 * t + c], v1); }
+    }
+    __syncthreads();
+    if (threadIdx.x < 64) {
+      const int c = threadIdx.x & 31;
+      const double scale = (EPI == 2 && threadIdx.x >= 32) ? (double)a.prev_invstd[c] : 1.0;
+      atomicAdd(a.sums + threadIdx.x, (double)red[threadIdx.x] * scale);
     }
   }
 }
@@ -779,15 +841,35 @@ int launch_thin(const ThinArgs& a, size_t smem, int ctas_per_sm, cudaStream_t st
 // Each wrapper returns 1 when the problem is not of its shape (the dispatcher then uses the generic kernels).
 
 // fine (gathered; optionally multiplied by act'(fine_ref)) -> coarse = out_act(conv)
+// epi: optional BatchNorm fusion on the result (TcEpi modes 0 none, 1 statistics, 2 activation backward + BN-backward sums)
 int thin_down(const b200gan_view* fine, const b200gan_view* fine_ref, int fine_act, const float* w, const b200gan_view* coarse, int out_act,
-              float slope, cudaStream_t st) {
+              float slope, const TcEpi& epi, cudaStream_t st) {
   ThinArgs a{};
+  if (epi.mode == 3) return 1;
+  if (epi.mode == 2 && (!dense_bf16_32(epi.prev_y) || epi.prev_y->n != coarse->n || epi.prev_y->h != coarse->h || epi.prev_y->w != coarse->w)) return 1;
   if (out_act != B200GAN_ACT_NONE && out_act != B200GAN_ACT_LRELU && out_act != B200GAN_ACT_RELU) return 1;
   if (!thin_setup(&a, fine, fine_ref, fine_act, coarse, nullptr, B200GAN_ACT_NONE, slope)) return 1;
   a.w = w; a.out_act = out_act;
+  a.epi = epi.mode;
+  if (epi.mode != 0) {
+    a.sums = epi.sums;
+    B200_CUDA(cudaMemsetAsync(epi.sums, 0, sizeof(double) * 64, st));
+    if (epi.mode == 2) {
+      a.prev_y = reinterpret_cast<const __nv_bfloat16*>(epi.prev_y->ptr);
+      a.prev_scale = epi.scale; a.prev_shift = epi.shift; a.prev_mean = epi.mean; a.prev_invstd = epi.invstd;
+      a.prev_neg = epi.act == B200GAN_ACT_RELU ? 0.f : (epi.act == B200GAN_ACT_LRELU ? epi.slope : 1.f);
+    }
+  }
   const size_t smem = (size_t)fine->c * (2 * a.R + 2) * (2 * a.W + 2) * 2;
-  if (fine->c == 1) return launch_thin<thin_down_mma_kernel<1>>(a, smem, 6, st, "thin_down_mma_kernel");
-  return launch_thin<thin_down_mma_kernel<3>>(a, smem, 4, st, "thin_down_mma_kernel");
+  const char* nm = "thin_down_mma_kernel";
+  if (fine->c == 1) {
+    if (epi.mode == 0) return launch_thin<thin_down_mma_kernel<1, 0>>(a, smem, 6, st, nm);
+    if (epi.mode == 1) return launch_thin<thin_down_mma_kernel<1, 1>>(a, smem, 4, st, nm);
+    return launch_thin<thin_down_mma_kernel<1, 2>>(a, smem, 4, st, nm);
+  }
+  if (epi.mode == 0) return launch_thin<thin_down_mma_kernel<3, 0>>(a, smem, 4, st, nm);
+  if (epi.mode == 1) return launch_thin<thin_down_mma_kernel<3, 1>>(a, smem, 3, st, nm);
+  return launch_thin<thin_down_mma_kernel<3, 2>>(a, smem, 3, st, nm);
 }
 
 // coarse (gathered; optionally multiplied by act'(coarse_ref)) -> fine = out_act(transposed conv)

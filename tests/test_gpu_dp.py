@@ -85,7 +85,7 @@ def test_two_nccl_ranks_match_dp_emulation(tmp_path, use_graph):
                 if k.endswith('num_batches_tracked'):
                     assert int(got[f'{tag}.{k}']) == int(v)
                 elif 'running' in k:
-                    close(got[f'{tag}.{k}'], v, rtol=1e-3, atol=1e-5, what=f'rank {r} {tag}.{k}')
+                    close(got[f'{tag}.{k}'], v, rtol=2e-3, atol=1e-4, what=f'rank {r} {tag}.{k}')
                 else:
                     weights_close(got[f'{tag}.{k}'], v, what=f'rank {r} {tag}.{k}', steps=STEPS, rtol=1e-3, atol=1e-5, frac=_frac(k))
                     assert np.abs(got[f'{tag}.{k}'] - v).max() < (5e-5 if k.endswith('.bias') else 1.3e-3), k
@@ -142,7 +142,7 @@ def test_two_replicas_on_one_gpu_match_dp_emulation():
                 if k.endswith('num_batches_tracked'):
                     assert int(v) == int(o.sd[k])
                 elif 'running' in k:
-                    close(v.cpu().numpy(), o.sd[k], rtol=1e-3, atol=1e-5, what=f'rank {r} {tag}.{k}')
+                    close(v.cpu().numpy(), o.sd[k], rtol=2e-3, atol=1e-4, what=f'rank {r} {tag}.{k}')
                 else:
                     weights_close(v.cpu().numpy(), o.sd[k], what=f'rank {r} {tag}.{k}', steps=STEPS, rtol=1e-3, atol=1e-5, frac=_frac(k))
                     assert np.abs(v.cpu().numpy() - o.sd[k]).max() < (5e-5 if k.endswith('.bias') else 1.3e-3), k

@@ -264,3 +264,50 @@ def test_dgrad_activation_only_epilogue(case):
     L.call('b200gan_conv2d_dgrad', C.byref(cv), C.byref(dy_v), L.ptr(wd), L.ptr(wp), C.byref(L.view_nhwc(dz_t)), C.byref(f), st())
     ref = orc.conv2d_dgrad(dy, w, 2, 1, (2 * hc, 2 * hc)) * np.where(a_prev > 0, 1.0, SLOPE).astype(np.float32)
     close(back_nchw(dz_t, True), ref, what=f'dgrad + activation-only epilogue {case}', **tol)
+
+
+@pytest.mark.parametrize('nc', [1, 3])
+def test_image_side_down_kernel_batchnorm_epilogues(nc):
+    """G5's input gradient (ConvTranspose2d(32->nc) dgrad, the image-side "down" kernel) with BOTH fusions the generator step uses
+    at once: Tanh backward on the gradient operand (dy_act) and, in the epilogue, ReLU backward + BatchNorm-backward sums of the
+    layer below (prev_*); plus the forward-statistics epilogue (bn_sums) of the same kernel."""
+    n, hc, wc = 3, 12, 32
+    cv = conv()
+    w = rnd((32, nc, 4, 4), 1, 0.1)
+    wd = torch.from_numpy(w).cuda()
+    fake = bf16_round(np.tanh(rnd((n, nc, 2 * hc, 2 * wc), 2)))
+    dfake = bf16_round(rnd((n, nc, 2 * hc, 2 * wc), 3))
+    y4 = bf16_round(rnd((n, 32, hc, wc), 4))
+    scale, shift = rnd((32,), 5, 0.5) + 1.0, rnd((32,), 6, 0.3)
+    mean, invstd = rnd((32,), 7, 0.2), np.abs(rnd((32,), 8)) + 0.5
+    dvec = [torch.from_numpy(v).cuda() for v in (scale, shift, mean, invstd)]
+    fake_t, fake_v = dev_nhwc(fake, torch.bfloat16)
+    dfake_t, dfake_v = dev_nhwc(dfake, torch.bfloat16)
+    y4_t, y4_v = dev_nhwc(y4, torch.bfloat16)
+    dz_t = torch.full((n, hc, wc, 32), float('nan'), device='cuda', dtype=torch.bfloat16)
+    psums = torch.full((64,), -3.0, device='cuda', dtype=torch.float64)
+    f = L.fuse(dy_act=L.ACT_TANH, dy_ref=fake_v, prev_act=L.ACT_RELU, prev_y=y4_v, prev_scale=dvec[0], prev_shift=dvec[1], prev_mean=dvec[2],
+               prev_invstd=dvec[3], prev_sums=psums)
+    L.call('b200gan_convT2d_dgrad', C.byref(cv), C.byref(dfake_v), L.ptr(wd), None, C.byref(L.view_nhwc(dz_t)), C.byref(f), st())
+    dy5 = bf16_round(dfake * (1 - fake * fake))
+    da4 = orc.convT2d_dgrad(dy5, bf16_round(w), 2, 1)
+    z = y4 * scale[None, :, None, None] + shift[None, :, None, None]
+    dz_ref = da4 * (z > 0)
+    dz = back_nchw(dz_t, True)
+    safe = np.abs(z) > 1e-3
+    close(np.where(safe, dz, 0), np.where(safe, dz_ref, 0), rtol=2e-2, atol=2e-2, what='thin down + prev_*: dz')
+    xhat = (y4 - mean[None, :, None, None]) * invstd[None, :, None, None]
+    s = psums.cpu().numpy()
+    # the kernel's sums are those of the stored dz
+    close(s[:32], dz.astype(np.float64).sum(axis=(0, 2, 3)), rtol=1e-3, atol=1e-2, what='prev_sums: sum dz')
+    close(s[32:], (dz.astype(np.float64) * xhat).sum(axis=(0, 2, 3)), rtol=1e-3, atol=2e-2, what='prev_sums: sum dz*xhat')
+    # forward statistics epilogue of the same kernel (Conv2d(nc->32) forward with bn_sums)
+    x_t, x_v = dev_nhwc(dfake, torch.bfloat16)
+    y_t = torch.empty((n, hc, wc, 32), device='cuda', dtype=torch.bfloat16)
+    sums = torch.full((64,), 9.0, device='cuda', dtype=torch.float64)
+    f = L.fuse(bn_sums=sums)
+    L.call('b200gan_conv2d_fprop', C.byref(cv), C.byref(x_v), L.ptr(wd), None, C.byref(L.view_nhwc(y_t)), C.byref(f), st())
+    y = back_nchw(y_t, True).astype(np.float64)
+    close(y, orc.conv2d_fprop(dfake, bf16_round(w), 2, 1), rtol=2e-2, atol=2e-2, what='thin down + bn_sums: result')
+    close(sums.cpu().numpy()[:32], y.sum(axis=(0, 2, 3)), rtol=1e-4, atol=1e-2, what='bn_sums: sum')
+    close(sums.cpu().numpy()[32:], (y ** 2).sum(axis=(0, 2, 3)), rtol=1e-4, atol=1e-2, what='bn_sums: sum of squares')
