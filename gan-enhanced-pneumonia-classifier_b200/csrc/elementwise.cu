@@ -45,11 +45,21 @@ __device__ __forceinline__ int64_t pix_offset(const View& v, int64_t pix) {
 template <typename T> struct Vec;
 template <> struct Vec<float> {
   static constexpr int N = 4;
+  using Raw = float4;
+  __device__ static Raw load_raw(const float* p) { return *reinterpret_cast<const float4*>(p); }
+  __device__ static void unpack(const Raw& t, float* v) { v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
   __device__ static void load(const float* p, float* v) { const float4 t = *reinterpret_cast<const float4*>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
   __device__ static void store(float* p, const float* v) { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
 };
 template <> struct Vec<__nv_bfloat16> {
   static constexpr int N = 8;
+  using Raw = uint4;
+  __device__ static Raw load_raw(const __nv_bfloat16* p) { return *reinterpret_cast<const uint4*>(p); }
+  __device__ static void unpack(const Raw& t, float* v) {
+    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+  }
   __device__ static void load(const __nv_bfloat16* p, float* v) {
     const uint4 t = *reinterpret_cast<const uint4*>(p);
     const uint32_t w[4] = {t.x, t.y, t.z, t.w};
@@ -81,17 +91,28 @@ __global__ void __launch_bounds__(256) bn_act_fwd_dense_kernel(const T* __restri
   int c0 = (int)((i * V) % C);
 #pragma unroll
   for (int j = 0; j < V; ++j) { sc[j] = scale ? scale[c0 + j] : 1.f; sh[j] = scale ? shift[c0 + j] : 0.f; }
-  for (; i < nvec; i += stride) {
-    if (!hoist && scale) {
-      c0 = (int)((i * V) % C);
+  constexpr int U = 4;                   // four vectors in flight per thread (raw loads first): HBM streaming needs the depth
+  using Raw = typename Vec<T>::Raw;
+  for (; i < nvec; i += U * stride) {
+    Raw r[U];
 #pragma unroll
-      for (int j = 0; j < V; ++j) { sc[j] = scale[c0 + j]; sh[j] = shift[c0 + j]; }
+    for (int u = 0; u < U; ++u)
+      if (i + u * stride < nvec) r[u] = Vec<T>::load_raw(y + (i + u * stride) * V);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t k = i + u * stride;
+      if (k >= nvec) break;
+      if (!hoist && scale) {
+        c0 = (int)((k * V) % C);
+#pragma unroll
+        for (int j = 0; j < V; ++j) { sc[j] = scale[c0 + j]; sh[j] = shift[c0 + j]; }
+      }
+      float v[V];
+      Vec<T>::unpack(r[u], v);
+#pragma unroll
+      for (int j = 0; j < V; ++j) v[j] = act_fwd(fmaf(v[j], sc[j], sh[j]), act, slope);
+      Vec<T>::store(a + k * V, v);
     }
-    float v[V];
-    Vec<T>::load(y + i * V, v);
-#pragma unroll
-    for (int j = 0; j < V; ++j) v[j] = act_fwd(fmaf(v[j], sc[j], sh[j]), act, slope);
-    Vec<T>::store(a + i * V, v);
   }
 }
 
@@ -147,18 +168,20 @@ __global__ void __launch_bounds__(256, 3) bn_act_bwd_apply_dense_kernel(BwdDense
   const T* y = reinterpret_cast<const T*>(g.y);
   const T* a = reinterpret_cast<const T*>(g.a);
   T* dy = reinterpret_cast<T*>(g.dy);
-  // two vectors per thread and iteration, all loads issued before the first store: the pass is pure HBM streaming and
-  // needs ~40 KB in flight per SM (one vector pair at a time measured 49 % of the copy bandwidth)
-  constexpr int U = 2;
+  // U vectors per thread and iteration, all loads issued before the first store and kept RAW (packed) until they are used:
+  // the pass is pure HBM streaming and needs ~40 KB in flight per SM (one vector pair at a time measured 49 % of the copy
+  // bandwidth)
+  constexpr int U = HAS_ACT ? 2 : 4;
+  using Raw = typename Vec<T>::Raw;
   for (; i < g.nvec; i += U * stride) {
-    float d[U][V], yv[U][V], av[U][V];
+    Raw rd[U], ry[U], ra[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int64_t k = i + u * stride;
       if (k < g.nvec) {
-        Vec<T>::load(da + k * V, d[u]);
-        Vec<T>::load(y + k * V, yv[u]);
-        if (HAS_ACT && a) Vec<T>::load(a + k * V, av[u]);
+        rd[u] = Vec<T>::load_raw(da + k * V);
+        ry[u] = Vec<T>::load_raw(y + k * V);
+        if (HAS_ACT && a) ra[u] = Vec<T>::load_raw(a + k * V);
       }
     }
 #pragma unroll
@@ -166,13 +189,17 @@ __global__ void __launch_bounds__(256, 3) bn_act_bwd_apply_dense_kernel(BwdDense
       const int64_t k = i + u * stride;
       if (k >= g.nvec) break;
       if (!hoist) coeffs((int)((k * V) % C));
+      float d[V], yv[V], av[V];
+      Vec<T>::unpack(rd[u], d);
+      Vec<T>::unpack(ry[u], yv);
+      if (HAS_ACT && a) Vec<T>::unpack(ra[u], av);
 #pragma unroll
       for (int j = 0; j < V; ++j) {
-        float dz = d[u][j];
-        if (HAS_ACT) dz *= act_grad(fmaf(yv[u][j], sc[j], sh[j]), a ? av[u][j] : 0.f, g.act, g.slope);
-        d[u][j] = fmaf(k1[j], dz, fmaf(pp[j], yv[u][j], qq[j]));
+        float dz = d[j];
+        if (HAS_ACT) dz *= act_grad(fmaf(yv[j], sc[j], sh[j]), a ? av[j] : 0.f, g.act, g.slope);
+        d[j] = fmaf(k1[j], dz, fmaf(pp[j], yv[j], qq[j]));
       }
-      Vec<T>::store(dy + k * V, d[u]);
+      Vec<T>::store(dy + k * V, d);
     }
   }
 }
