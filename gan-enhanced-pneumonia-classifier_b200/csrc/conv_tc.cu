@@ -246,8 +246,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       const uint4* yp = reinterpret_cast<const uint4*>(p.prev_y + ooff);
       uint4 ynext[2];
       if (EPI >= 2) {                                // the first piece of y_prev is requested before the accumulator is waited for
-        ynext[0] = valid ? __ldg(yp) : make_uint4(0u, 0u, 0u, 0u);
-        ynext[1] = valid ? __ldg(yp + 1) : make_uint4(0u, 0u, 0u, 0u);
+        ynext[0] = ynext[1] = make_uint4(0u, 0u, 0u, 0u);
+        if (valid) ldg256_nc(yp, ynext[0], ynext[1]);
       }
       const int buf = lt % NACC;
       mbar_wait(&acc_full[buf], (lt / NACC) & 1);
@@ -261,8 +261,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         if (EPI >= 2) {
           ycur[0] = ynext[0]; ycur[1] = ynext[1];
           if (c0 + 16 < CW) {
-            ynext[0] = valid ? __ldg(yp + (c0 + 16) / 8) : make_uint4(0u, 0u, 0u, 0u);
-            ynext[1] = valid ? __ldg(yp + (c0 + 16) / 8 + 1) : make_uint4(0u, 0u, 0u, 0u);
+            ynext[0] = ynext[1] = make_uint4(0u, 0u, 0u, 0u);
+            if (valid) ldg256_nc(yp + (c0 + 16) / 8, ynext[0], ynext[1]);
           }
         }
         tcgen05_wait_ld();
@@ -301,10 +301,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           __nv_bfloat162 b = __floats2bfloat162_rn(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
           pk[j] = *reinterpret_cast<uint32_t*>(&b);
         }
-        if (valid) {
-          *reinterpret_cast<uint4*>(orow + c0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          *reinterpret_cast<uint4*>(orow + c0 + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-        }
+        if (valid) stg256(orow + c0, make_uint4(pk[0], pk[1], pk[2], pk[3]), make_uint4(pk[4], pk[5], pk[6], pk[7]));
         if (EPI == 1 || EPI == 2) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -364,7 +361,7 @@ static void pick_tile(int qh, int qw, int* tw, int* th) {
 
 static bool nhwc_dense_bf16(const b200gan_view* v) {
   return v->dtype == B200GAN_BF16 && v->sc == 1 && v->sw == v->c && v->sh == (int64_t)v->w * v->c &&
-         v->sn == (int64_t)v->h * v->w * v->c && (reinterpret_cast<uintptr_t>(v->ptr) & 15) == 0;
+         v->sn == (int64_t)v->h * v->w * v->c && (reinterpret_cast<uintptr_t>(v->ptr) & 31) == 0;      // 32 B: 256-bit epilogue accesses
 }
 
 template <int BN, int KC, int STAGES, int EPI>

@@ -69,6 +69,20 @@ __device__ __forceinline__ void tcgen05_mma_f16(uint32_t tmem_d, uint64_t adesc,
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// 256-bit global accesses (sm_100): one 32-byte sector per lane and instruction.  The epilogues read / write 32 bytes per
+// thread at a row stride, which costs one L1 wavefront per LANE per instruction whatever the width: 256-bit accesses halve the
+// number of instructions, i.e. the wavefronts.
+__device__ __forceinline__ void ldg256_nc(const void* p, uint4& a, uint4& b) {
+  asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+               : "l"(p));
+}
+__device__ __forceinline__ void stg256(void* p, const uint4& a, const uint4& b) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y),
+               "r"(b.z), "r"(b.w)
+               : "memory");
+}
+
 // Same, executed by ALL lanes of a converged warp: one elected lane issues.  Keeping the issuing warp's control flow uniform lets
 // the compiler hold descriptors in uniform registers; an `if (lane == 0)` region instead costs an ELECT / R2UR.BROADCAST / BRA loop
 // per operand of every MMA (measured: ~85 instead of ~50 cycles per MMA from the single issuing thread).
