@@ -264,7 +264,7 @@ int b200gan_convT2d_wgrad(const b200gan_conv* cv, const b200gan_view* x, const b
 }
 
 int b200gan_pack_conv_weight(const float* weight, int32_t co, int32_t ci, int32_t k, int32_t form, void* out, void* stream) {
-  B200_CHECK_ARG(weight && out && co > 0 && ci > 0 && (form == 0 || form == 1), "pack_conv_weight: bad argument");
+  B200_CHECK_ARG(weight && out && co > 0 && ci > 0 && form >= 0 && form <= 2, "pack_conv_weight: bad argument");
   return tc_pack_weight(weight, co, ci, k, form, out, (cudaStream_t)stream);
 }
 

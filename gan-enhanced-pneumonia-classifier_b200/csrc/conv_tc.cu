@@ -1193,9 +1193,12 @@ int tc_conv_wgrad(const b200gan_conv* cv, const b200gan_view* x, const b200gan_v
 // ---------------------------------------------------------------------------------------------------
 __global__ void pack_weight_kernel(const float* __restrict__ w, int Co, int Ci, int form, __nv_bfloat16* __restrict__ out) {
   const int64_t total = (int64_t)Co * Ci * 16;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+  const int64_t work = form == 2 ? 2 * total : total;                  // form 2: both forms back to back
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < work; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int f = form == 2 ? (idx >= total ? 1 : 0) : form;
+    const int64_t i = idx >= total ? idx - total : idx;
     float v;
-    if (form == 0) {
+    if (f == 0) {
       const int ci = (int)(i % Ci);
       const int tap = (int)((i / Ci) % 16);
       const int co = (int)(i / ((int64_t)Ci * 16));
@@ -1209,15 +1212,15 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int Co, int Ci, 
       const int kh = (py + 1) % 2 + 2 * jh, kw = (px + 1) % 2 + 2 * jw;
       v = w[((int64_t)co * Ci + ci) * 16 + kh * 4 + kw];
     }
-    out[i] = __float2bfloat16_rn(v);
+    out[idx] = __float2bfloat16_rn(v);
   }
 }
 
 int tc_pack_weight(const float* w, int Co, int Ci, int k, int form, void* out, cudaStream_t st) {
   if (k != 4) { set_error("pack_conv_weight: only k=4 (stride 2, pad 1) layers have a tensor-core path"); return B200GAN_ERR_UNSUPPORTED; }
-  const int64_t total = (int64_t)Co * Ci * 16;
+  const int64_t total = (int64_t)Co * Ci * 16 * (form == 2 ? 2 : 1);
   int64_t blocks = (total + 255) / 256;
-  if (blocks > 4 * kNumSMs) blocks = 4 * kNumSMs;
+  if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
   pack_weight_kernel<<<(unsigned)blocks, 256, 0, st>>>(w, Co, Ci, form, reinterpret_cast<__nv_bfloat16*>(out));
   B200_LAUNCH_CHECK("pack_weight_kernel");
   return 0;

@@ -132,6 +132,8 @@ class NetEngine:
         self._conv = [L.Conv(sp.k, sp.stride, sp.pad, algo) for sp in specs]
         self.launches = 0     # C-ABI calls that launch kernels, made through this engine (bench.py's gpu_launches claim)
         self._ws = None       # zeroed fp32 scratch for the split-K reduction of the tensor-core weight gradients
+        self.weights_version = None   # see _pack
+        self._packed = {}
 
     # -- thin wrappers over the C ABI --------------------------------------------------------------
     def _tc_layer(self, i):
@@ -147,16 +149,28 @@ class NetEngine:
         return sp.bn_idx is None and sp.k == 4 and sp.act in (L.ACT_LRELU, L.ACT_RELU, L.ACT_TANH)
 
     def _pack(self, i, w, st):
-        """bf16 GEMM-operand repacks of the fp32 master weight: ('down' form, 'up' form), see b200gan_pack_conv_weight."""
+        """bf16 GEMM-operand repacks of the fp32 master weight: ('down' form, 'up' form), see b200gan_pack_conv_weight.
+        One launch produces both.  While `weights_version` is not None the result is reused until the owner of the weights
+        bumps the version (DCGANTrainer does after each Adam update: the two Discriminator forwards of the D step share one
+        repack); with version None (module-level autograd path, weights may change behind our back) every forward repacks."""
         if not self._tc_layer(i):
             return None, None
-        co, ci = w.shape[0], w.shape[1]
-        down = torch.empty(w.numel(), device=w.device, dtype=torch.bfloat16)
-        up = torch.empty(w.numel(), device=w.device, dtype=torch.bfloat16)
-        L.call('b200gan_pack_conv_weight', L.ptr(w), co, ci, 4, 0, L.ptr(down), st)
-        L.call('b200gan_pack_conv_weight', L.ptr(w), co, ci, 4, 1, L.ptr(up), st)
-        self.launches += 2
-        return down, up
+        n = w.numel()
+        if self.weights_version is None:
+            both = torch.empty(2 * n, device=w.device, dtype=torch.bfloat16)
+        else:
+            # ONE persistent buffer per layer (fixed address): a captured CUDA graph may read, in its first Discriminator forward,
+            # the repack its own previous replay wrote after the Adam update
+            hit = self._packed.get(i)
+            if hit is None or hit[1].device != w.device or hit[1].numel() != 2 * n:
+                hit = self._packed[i] = [None, torch.empty(2 * n, device=w.device, dtype=torch.bfloat16)]
+            both = hit[1]
+            if hit[0] == self.weights_version:
+                return both[:n], both[n:]
+            hit[0] = self.weights_version
+        L.call('b200gan_pack_conv_weight', L.ptr(w), w.shape[0], w.shape[1], 4, 2, L.ptr(both), st)
+        self.launches += 1
+        return both[:n], both[n:]
 
     def _fprop(self, i, x: Act, w, y: Act, st, wp_down=None, wp_up=None, fuse=None):
         # ConvTranspose2d forward is the 'up' geometry, Conv2d forward the 'down' geometry

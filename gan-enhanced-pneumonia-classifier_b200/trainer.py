@@ -74,6 +74,7 @@ class DCGANTrainer:
         self.lr, self.beta1, self.beta2, self.eps = lr, beta1, beta2, eps
         self.engG = E.NetEngine(netG._specs(), True, dtype, algo)
         self.engD = E.NetEngine(netD._specs(), False, dtype, algo)
+        self.engG.weights_version = self.engD.weights_version = 0      # this trainer owns the weights: repack only after Adam
         self.arenaG = _Arena(self.engG.param_order(netG))
         self.arenaD = _Arena(self.engD.param_order(netD))
         self.dtype = dtype
@@ -239,6 +240,7 @@ class DCGANTrainer:
         del ctx_f
         yield 'D'
         self._adam(self.arenaD)
+        self.engD.weights_version += 1
         # (2) G step ------------------------------------------------------------- train_gan.py:144-150
         self.arenaG.grad.zero_()
         logit_g, ctx_d = self.engD.forward(fake, pD, True, True, last_act=False)
@@ -251,6 +253,7 @@ class DCGANTrainer:
         del ctx_g
         yield 'G'
         self._adam(self.arenaG)
+        self.engG.weights_version += 1
         # errD = errD_real + errD_fake (train_gan.py:140); D_x, D_G_z1, D_G_z2 are mean probabilities
         return torch.stack([m_real[0] + m_fake[0], m_g[0], m_real[1], m_fake[1], m_g[1]])
 

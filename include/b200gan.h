@@ -140,7 +140,8 @@ int b200gan_convT2d_wgrad(const b200gan_conv* cv, const b200gan_view* x, const b
 /* ---- bf16 repack of a k=4 conv weight for the tcgen05 implicit GEMM (`wpacked` above).  `weight` is the fp32
  *      master in conv geometry (Co,Ci,4,4) -- i.e. the Conv2d weight, or the ConvTranspose2d weight (Cin,Cout,4,4)
  *      read as (Co=Cin, Ci=Cout).  form 0 ("down": Conv2d fprop / ConvTranspose2d dgrad): [Co][(kh,kw,Ci)];
- *      form 1 ("up": ConvTranspose2d fprop / Conv2d dgrad): [parity class][Ci][(jh,jw,Co)].  out: Co*Ci*16 bf16. */
+ *      form 1 ("up": ConvTranspose2d fprop / Conv2d dgrad): [parity class][Ci][(jh,jw,Co)].  out: Co*Ci*16 bf16.
+ *      form 2: both in one launch, form 0 at out[0 .. Co*Ci*16), form 1 behind it (out: 2*Co*Ci*16 bf16). */
 int b200gan_pack_conv_weight(const float* weight, int32_t co, int32_t ci, int32_t k, int32_t form, void* out, void* stream);
 
 /* ---- nn.BatchNorm2d in training mode (dcgan.py:27,31,35,39,43,69,73,77,81) -------------------------

@@ -256,3 +256,36 @@ def test_cli_train_then_sample_on_gpu(tmp_path):
         got = np.asarray(Image.open(f'{d}/synthetic/synthetic_{i + 1:05d}.png'))
         assert got.shape == (224, 224, 3)
         assert np.abs(got.astype(int) - want[i].astype(int)).max() <= 1, f'image {i}'       # fp32 path: at most one grey level
+
+
+def test_packed_weight_cache_follows_the_weights_under_graph_replay():
+    """Full-size networks (ngf = ndf = 64: the tcgen05 layers and their bf16 weight repacks are active), batch 2, graph replay.
+    The repacks are cached per Adam update in persistent buffers that the captured graph reads across replays; after every step
+    each cached repack must equal a fresh repack of the current fp32 master weights bit for bit, and the history must stay finite
+    and close to the kernel-by-kernel run."""
+    import ctypes as C
+    from gan_enhanced_pneumonia_classifier_b200.trainer import DCGANTrainer
+    L = pkg._lib
+    m = dict(seed=5, nz=100, nc=1, fm=64)
+    real = torch.from_numpy(synthetic_real(7, 2, 1)).cuda()
+    noises = [torch.from_numpy(synthetic_noise(20 + i, 2, 100)).cuda() for i in range(4)]
+    hist = {}
+    for mode in (False, True):
+        G, D = build(m, torch.bfloat16)
+        tr = DCGANTrainer(G, D, dtype=torch.bfloat16, use_graph=mode)
+        rows = []
+        for z in noises:
+            rows.append(tr.step(real, z).cpu().numpy())
+            for eng, net in ((tr.engD, D), (tr.engG, G)):
+                for i, sp in enumerate(eng.specs):
+                    if not eng._tc_layer(i):
+                        continue
+                    w = net.main[sp.conv_idx].weight
+                    fresh = torch.empty(2 * w.numel(), device='cuda', dtype=torch.bfloat16)
+                    L.call('b200gan_pack_conv_weight', L.ptr(w), w.shape[0], w.shape[1], 4, 2, L.ptr(fresh), L.stream_ptr())
+                    ver, cached = eng._packed[i]
+                    if ver == eng.weights_version:          # a cache entry of the current version must be current
+                        assert torch.equal(cached, fresh), f'stale repack: graph={mode} layer {i}'
+        hist[mode] = np.stack(rows)
+        assert np.isfinite(hist[mode]).all()
+    close(hist[True][:2], hist[False][:2], rtol=5e-2, atol=5e-2, what='history, graph vs eager, full-size bf16')
