@@ -711,6 +711,7 @@ conv_up4_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     };
     int lt = 0, ys = 0;
     uint32_t yph = 0;
+    float st0 = 0.f, st1 = 0.f, st2 = 0.f, st3 = 0.f;
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++lt) {
       bool valid;
       (void)locate(t, valid);
@@ -758,24 +759,6 @@ conv_up4_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 #pragma unroll
         for (int j = 0; j < 4; ++j)
           *reinterpret_cast<uint4*>(yt + sw64(pix + px, j)) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-        if (EPI == 1) {
-#pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            float s0[16], s1[16];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const uint32_t w = pk[8 * hh + j];
-              const float lo = valid ? __uint_as_float(w << 16) : 0.f, hi = valid ? __uint_as_float(w & 0xffff0000u) : 0.f;
-              s0[2 * j] = lo; s0[2 * j + 1] = hi; s1[2 * j] = lo * lo; s1[2 * j + 1] = hi * hi;
-            }
-            warp_column_sums(s0, lane);
-            warp_column_sums(s1, lane);
-            if (lane < 16) {
-              atomicAdd(&ch_acc[16 * hh + lane], s0[0]);
-              atomicAdd(&ch_acc[32 + 16 * hh + lane], s1[0]);
-            }
-          }
-        }
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -794,10 +777,27 @@ conv_up4_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         if (lt > 0) mbar_arrive(&y_empty[(ys + YST - 1) % YST]);
       }
+      if (EPI == 1) {
+        // BatchNorm statistics from the staged (bf16-rounded) tile: warp w owns lines 4w..4w+3 (64 pixels), a half-warp one pixel,
+        // lane l the channel pair 2(l%16), +1 (conflict-free 4-byte shared loads), accumulated in registers over the CTA's tiles
+        const int n = t / tiles_per_img, r = t - n * tiles_per_img;
+        const int th_i = r / p.tiles_w, tw_i = r - th_i * p.tiles_w;
+#pragma unroll 4
+        for (int i = 0; i < 32; ++i) {
+          const int px = warp * 64 + 2 * i + (lane >> 4);
+          if (2 * tw_i * kUp4TW + (px & 15) < 2 * p.QW && 2 * th_i * kUp4TH + (px >> 4) < 2 * p.QH) {
+            const uint32_t w = *reinterpret_cast<const uint32_t*>(yt + sw64(px, (lane >> 2) & 3) + (lane & 3) * 4);
+            const float lo = __uint_as_float(w << 16), hi = __uint_as_float(w & 0xffff0000u);
+            st0 += lo; st1 += hi; st2 = fmaf(lo, lo, st2); st3 = fmaf(hi, hi, st3);
+          }
+        }
+      }
       if (++ys == YST) { ys = 0; yph ^= 1; }
     }
     if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // all stores complete before the CTA exits
     if (EPI == 1) {
+      atomicAdd(&ch_acc[2 * (lane & 15)], st0); atomicAdd(&ch_acc[2 * (lane & 15) + 1], st1);
+      atomicAdd(&ch_acc[32 + 2 * (lane & 15)], st2); atomicAdd(&ch_acc[32 + 2 * (lane & 15) + 1], st3);
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (threadIdx.x < 64 && ch_acc[threadIdx.x] != 0.f) atomicAdd(p.sums + threadIdx.x, (double)ch_acc[threadIdx.x]);
     }
@@ -886,10 +886,337 @@ static int tc_conv_up4(const b200gan_view* in, const void* wpacked, const b200ga
   return launch_up4<0>(ma, mb, my, mo, p, grid, smem, st);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// "Down" geometry for the thin layer (32 -> 64 channels: Conv2d(32->64) forward D1, ConvTranspose2d(64->32) input gradient G4),
+// the mirror image of conv_up4_tc_kernel: per 16 x 8 output pixels of one image the 34 x 18 input pixels are fetched ONCE as
+// four stride-2 parity planes (17 lines x 9 pixels x 32 channels each, TMA element strides {1,2,2,1}); tap (kh,kw) is the window
+// of plane (kh&1, kw&1) that starts at line kh>>1, pixel kw>>1 (SWIZZLE_64B descriptors are address based too:
+// tools/micro/desc_shift64.cu).  The generic kernel fetches 16 tap tiles of 8 KB per 128 pixels; this one 38 KB in total, and all
+// 64 KB of weights stay resident.  Epilogue: 1 = BatchNorm statistics, 2 = activation backward + BatchNorm-backward sums with the
+// saved conv output TMA-staged into the output staging tile; output by TMA store.
+// ---------------------------------------------------------------------------------------------------
+struct Down4Params {
+  int tiles_w, tiles_h, num_tiles;      // tiles of 8 (W) x 16 (H) OUTPUT pixels of one image
+  int OH, OW, NB;
+  double* sums;
+  const float *prev_scale, *prev_shift, *prev_mean, *prev_invstd;
+  float prev_neg;
+  int nstages, yst, off_res, off_io, off_bar;
+};
+
+constexpr int kDn4PlaneBytes = 17 * 9 * 64;                              // 9792
+constexpr int kDn4PlaneStride = (kDn4PlaneBytes + 1023) & ~1023;         // 10240
+constexpr int kDn4Stage = 4 * kDn4PlaneStride;                           // 40960
+constexpr int kDn4IoBytes = 128 * 128;                                   // 16 lines x 8 pixels x 64 channels
+
+template <int TAP>
+__device__ __forceinline__ void down4_issue_from(uint32_t tmem_d, uint64_t adesc0, uint64_t bdesc0) {
+  constexpr int kh = TAP >> 2, kw = TAP & 3;
+  constexpr int a_off = ((kh & 1) * 2 + (kw & 1)) * kDn4PlaneStride + ((kh >> 1) * 9 + (kw >> 1)) * 64;
+  constexpr uint32_t idesc = make_idesc_bf16(128, 64, 0, 0);
+#pragma unroll
+  for (int k = 0; k < 2; ++k)
+    tcgen05_mma_f16_elect(tmem_d, adesc0 + (uint64_t)((a_off + k * 32) >> 4), bdesc0 + (uint64_t)((TAP * 4096 + k * 32) >> 4), idesc, (TAP | k) != 0);
+  if constexpr (TAP + 1 < 16) down4_issue_from<TAP + 1>(tmem_d, adesc0, bdesc0);
+}
+
+// byte offset of 16-byte chunk `chunk` (0..7) of pixel `pix` in a tile of 128-byte pixel rows with SWIZZLE_128B
+__device__ __forceinline__ uint32_t sw128(int pix, int chunk) { return (uint32_t)pix * 128u + (uint32_t)((chunk ^ (pix & 7)) << 4); }
+
+template <int EPI>
+__global__ void __launch_bounds__(kTcThreads, 1)
+conv_down4_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_y,
+                     const __grid_constant__ CUtensorMap map_o, const Down4Params p) {
+  constexpr int NACC = 4;
+  const int YST = p.yst;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int NST = p.nstages;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.off_bar);
+  uint64_t* empty_bar = full_bar + 8;
+  uint64_t* acc_full = empty_bar + 8;
+  uint64_t* acc_empty = acc_full + 4;
+  uint64_t* res_bar = acc_empty + 4;
+  uint64_t* y_full = res_bar + 1;
+  uint64_t* y_empty = y_full + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(y_empty + 4);
+  float* ch_acc = reinterpret_cast<float*>(smem + p.off_bar + 512);      // [2][64]
+  float4* ch_coef = reinterpret_cast<float4*>(ch_acc + 128);             // [64] {scale, shift, mean, invstd}
+  uint8_t* smem_res = smem + p.off_res;
+  uint8_t* smem_io = smem + p.off_io;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int kTmaWarp = 8, kMmaWarp = 9;
+  if (EPI != 0) {
+    for (int c = threadIdx.x; c < 128; c += blockDim.x) ch_acc[c] = 0.f;
+    if (EPI == 2)
+      for (int c = threadIdx.x; c < 64; c += blockDim.x) ch_coef[c] = make_float4(p.prev_scale[c], p.prev_shift[c], p.prev_mean[c], p.prev_invstd[c]);
+  }
+  if (warp == kTmaWarp && lane == 0) {
+    for (int s = 0; s < NST; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int b = 0; b < NACC; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 8); }
+    mbar_init(res_bar, 1);
+    for (int b = 0; b < YST; ++b) { mbar_init(&y_full[b], 1); mbar_init(&y_empty[b], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_o) : "memory");
+    if (EPI == 2) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_y) : "memory");
+  }
+  if (warp == kMmaWarp) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(256));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int tiles_per_img = p.tiles_w * p.tiles_h;
+
+  if (warp == kTmaWarp) {
+    if (lane == 0) {
+      mbar_expect_tx(res_bar, 16 * 4096);
+      for (int tap = 0; tap < 16; ++tap) tma_load_3d(smem_res + tap * 4096, &map_b, res_bar, tap * 32, 0, 0);
+      int s = 0, ys = 0;
+      uint32_t ph = 0, yph = 0;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+        const int n = t / tiles_per_img, r = t - n * tiles_per_img;
+        const int th_i = r / p.tiles_w, tw_i = r - th_i * p.tiles_w;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_expect_tx(&full_bar[s], 4 * kDn4PlaneBytes);
+#pragma unroll
+        for (int pl = 0; pl < 4; ++pl)
+          tma_load_4d(smem + s * kDn4Stage + pl * kDn4PlaneStride, &map_a, &full_bar[s], 0, 16 * tw_i - 1 + (pl & 1), 32 * th_i - 1 + (pl >> 1), n);
+        if (++s == NST) { s = 0; ph ^= 1; }
+        if (EPI == 2) {
+          mbar_wait(&y_empty[ys], yph ^ 1);
+          mbar_expect_tx(&y_full[ys], kDn4IoBytes);
+          tma_load_4d(smem_io + ys * kDn4IoBytes, &map_y, &y_full[ys], 0, 8 * tw_i, 16 * th_i, n);
+          if (++ys == YST) { ys = 0; yph ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == kMmaWarp) {
+    const uint32_t tm0 = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint64_t bdesc0 = make_smem_desc(smem_u32(smem_res), 16, 8 * 64, 4u);
+    int s = 0;
+    uint32_t ph = 0;
+    int lt = 0;
+    mbar_wait(res_bar, 0);
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++lt) {
+      const int buf = lt % NACC;
+      mbar_wait(&acc_empty[buf], ((lt / NACC) & 1) ^ 1);
+      mbar_wait(&full_bar[s], ph);
+      tcgen05_fence_after();
+      const uint64_t adesc0 = make_smem_desc(smem_u32(smem + s * kDn4Stage), 16, 9 * 64, 4u);
+      down4_issue_from<0>(tm0 + buf * 64, adesc0, bdesc0);
+      tcgen05_commit_elect(&empty_bar[s]);
+      tcgen05_commit_elect(&acc_full[buf]);
+      if (++s == NST) { s = 0; ph ^= 1; }
+    }
+  } else {
+    // ===== epilogue: warps 0..7; TMEM lane quarter = warp % 4 (output pixel rows), column half = warp / 4 =====
+    const int q = warp & 3, hcol = warp >> 2;
+    const int row = q * 32 + lane;                 // = th * 8 + tw = pixel index inside the 16 x 8 tile
+    const int tw = row & 7, th = row >> 3;
+    int lt = 0, ys = 0;
+    uint32_t yph = 0;
+    float st0 = 0.f, st1 = 0.f, st2 = 0.f, st3 = 0.f;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++lt) {
+      const int n = t / tiles_per_img, r = t - n * tiles_per_img;
+      const int th_i = r / p.tiles_w, tw_i = r - th_i * p.tiles_w;
+      const bool valid = 8 * tw_i + tw < p.OW && 16 * th_i + th < p.OH;
+      uint8_t* io = smem_io + ys * kDn4IoBytes;
+      uint4 yv[4];
+      if (EPI == 2) {
+        mbar_wait(&y_full[ys], yph);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) yv[j] = *reinterpret_cast<const uint4*>(io + sw128(row, 4 * hcol + j));
+      } else {
+        mbar_wait(&y_empty[ys], yph ^ 1);
+      }
+      const int buf = lt % NACC;
+      mbar_wait(&acc_full[buf], (lt / NACC) & 1);
+      tcgen05_fence_after();
+      uint32_t v[32];
+      tcgen05_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * 64 + hcol * 32, v);
+      tcgen05_wait_ld();
+      float ym[32];
+      if (EPI == 2) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float y8[8];
+          unpack8(yv[j], y8);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float4 cf = ch_coef[32 * hcol + 8 * j + e];
+            const float z = fmaf(y8[e], cf.x, cf.y);
+            v[8 * j + e] = __float_as_uint(__uint_as_float(v[8 * j + e]) * (z > 0.f ? 1.f : p.prev_neg));
+            ym[8 * j + e] = y8[e] - cf.z;
+          }
+        }
+      }
+      uint32_t pk[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        __nv_bfloat162 b = __floats2bfloat162_rn(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+        pk[j] = *reinterpret_cast<uint32_t*>(&b);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(io + sw128(row, 4 * hcol + j)) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+      if (EPI == 2) {
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          float s0[16], s1[16];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t w = pk[8 * hh + j];
+            const float lo = valid ? __uint_as_float(w << 16) : 0.f, hi = valid ? __uint_as_float(w & 0xffff0000u) : 0.f;
+            s0[2 * j] = lo; s0[2 * j + 1] = hi;
+            s1[2 * j] = lo * ym[16 * hh + 2 * j]; s1[2 * j + 1] = hi * ym[16 * hh + 2 * j + 1];
+          }
+          warp_column_sums(s0, lane);
+          warp_column_sums(s1, lane);
+          if (lane < 16) {
+            atomicAdd(&ch_acc[32 * hcol + 16 * hh + lane], s0[0]);
+            atomicAdd(&ch_acc[64 + 32 * hcol + 16 * hh + lane], s1[0]);
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (threadIdx.x == 0) {
+        asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(&map_o), "r"(smem_u32(io)), "r"(0),
+                     "r"(8 * tw_i), "r"(16 * th_i), "r"(n)
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        if (lt > 0) mbar_arrive(&y_empty[(ys + YST - 1) % YST]);
+      }
+      if (EPI == 1) {
+        // BatchNorm statistics from the staged (bf16-rounded) tile: warp w owns pixels 16w..16w+15, lane l the channel pair 2l, 2l+1
+        // (one conflict-free 4-byte shared load per pixel), accumulated in registers over all tiles of the CTA
+#pragma unroll 4
+        for (int i = 0; i < 16; ++i) {
+          const int pix = warp * 16 + i;
+          if (8 * tw_i + (pix & 7) < p.OW && 16 * th_i + (pix >> 3) < p.OH) {
+            const uint32_t w = *reinterpret_cast<const uint32_t*>(io + sw128(pix, lane >> 2) + (lane & 3) * 4);
+            const float lo = __uint_as_float(w << 16), hi = __uint_as_float(w & 0xffff0000u);
+            st0 += lo; st1 += hi; st2 = fmaf(lo, lo, st2); st3 = fmaf(hi, hi, st3);
+          }
+        }
+      }
+      if (++ys == YST) { ys = 0; yph ^= 1; }
+    }
+    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (EPI == 1) {
+      atomicAdd(&ch_acc[2 * lane], st0); atomicAdd(&ch_acc[2 * lane + 1], st1);
+      atomicAdd(&ch_acc[64 + 2 * lane], st2); atomicAdd(&ch_acc[64 + 2 * lane + 1], st3);
+    }
+    if (EPI != 0) {
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (threadIdx.x < 128) {
+        const float a0 = ch_acc[threadIdx.x];
+        const double sc = (EPI == 2 && threadIdx.x >= 64) ? (double)ch_coef[threadIdx.x - 64].w : 1.0;
+        if (a0 != 0.f) atomicAdd(p.sums + threadIdx.x, (double)a0 * sc);
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256));
+  }
+}
+
+template <int EPI>
+static int launch_down4(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& my, const CUtensorMap& mo, const Down4Params& p, int grid,
+                        int smem, cudaStream_t st) {
+  static int configured = 0;
+  if (configured < smem) {
+    B200_CUDA(cudaFuncSetAttribute(conv_down4_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = smem;
+  }
+  conv_down4_tc_kernel<EPI><<<grid, kTcThreads, smem, st>>>(ma, mb, my, mo, p);
+  B200_LAUNCH_CHECK("conv_down4_tc_kernel");
+  return 0;
+}
+
+// returns 1 when the problem is not the 32 -> 64 channel "down" shape (or carries an epilogue this kernel does not have)
+static int tc_conv_down4(const b200gan_view* in, const void* wpacked, const b200gan_view* out, const TcEpi& epi, cudaStream_t st) {
+  static const bool enabled = getenv("B200GAN_NO_DOWN4") == nullptr;
+  if (!enabled || in->c != 32 || out->c != 64 || epi.mode == 3 || out->h < 12 || out->w < 8) return 1;
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return B200GAN_ERR_CUDA; }
+  Down4Params p{};
+  p.tiles_w = (out->w + 7) / 8; p.tiles_h = (out->h + 15) / 16;
+  p.num_tiles = p.tiles_w * p.tiles_h * out->n;
+  p.OH = out->h; p.OW = out->w; p.NB = out->n;
+  if (epi.mode != 0) {
+    p.sums = epi.sums;
+    B200_CUDA(cudaMemsetAsync(epi.sums, 0, sizeof(double) * 128, st));
+    if (epi.mode == 2) {
+      p.prev_scale = epi.scale; p.prev_shift = epi.shift; p.prev_mean = epi.mean; p.prev_invstd = epi.invstd;
+      p.prev_neg = epi.act == B200GAN_ACT_RELU ? 0.f : (epi.act == B200GAN_ACT_LRELU ? epi.slope : 1.f);
+    }
+  }
+  CUtensorMap ma, mb, my, mo;
+  {
+    cuuint64_t gdim[4] = {32, (cuuint64_t)in->w, (cuuint64_t)in->h, (cuuint64_t)in->n};
+    cuuint64_t gstr[3] = {64, (cuuint64_t)in->w * 64, (cuuint64_t)in->h * in->w * 64};
+    cuuint32_t box[4] = {32, 18, 34, 1};                                 // every second pixel: 9 x 17 land in shared memory
+    cuuint32_t estr[4] = {1, 2, 2, 1};
+    CUresult r = enc(&ma, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, in->ptr, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(A planes) failed: %d", (int)r); return B200GAN_ERR_CUDA; }
+  }
+  {
+    cuuint64_t gdim[3] = {512, 64, 1};                                   // wpacked "down" form: [64 rows][16 taps x 32]
+    cuuint64_t gstr[2] = {1024, 1024 * 64};
+    cuuint32_t box[3] = {32, 64, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&mb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(wpacked), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(B) failed: %d", (int)r); return B200GAN_ERR_CUDA; }
+  }
+  for (int which = 0; which < 2; ++which) {
+    void* base = which == 0 ? out->ptr : (epi.mode == 2 ? epi.prev_y->ptr : out->ptr);
+    cuuint64_t gdim[4] = {64, (cuuint64_t)out->w, (cuuint64_t)out->h, (cuuint64_t)out->n};
+    cuuint64_t gstr[3] = {128, (cuuint64_t)out->w * 128, (cuuint64_t)out->h * out->w * 128};
+    cuuint32_t box[4] = {64, 8, 16, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(which == 0 ? &mo : &my, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(out) failed: %d", (int)r); return B200GAN_ERR_CUDA; }
+  }
+  // 227 KB: 64 KB of weights + either 3 input stages and 2 staging tiles or 2 and 3 (the saved output of epilogue 2 is prefetched
+  // into the staging tiles, which then want the depth more than the input ring does)
+  static const int force_nst = getenv("B200GAN_DOWN4_NST") ? atoi(getenv("B200GAN_DOWN4_NST")) : 0;
+  p.nstages = force_nst ? force_nst : (epi.mode == 2 ? 2 : 3);
+  p.yst = p.nstages == 3 ? 2 : 3;
+  p.off_res = p.nstages * kDn4Stage;
+  p.off_io = p.off_res + 16 * 4096;
+  p.off_bar = p.off_io + p.yst * kDn4IoBytes;
+  const int smem = 1024 + p.off_bar + 512 + 512 + 1024 + 64;
+  const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
+  if (epi.mode == 1) return launch_down4<1>(ma, mb, my, mo, p, grid, smem, st);
+  if (epi.mode == 2) return launch_down4<2>(ma, mb, my, mo, p, grid, smem, st);
+  return launch_down4<0>(ma, mb, my, mo, p, grid, smem, st);
+}
+
 // `epi` describes an optional epilogue fusion (mode 0: none).  Both return 0 when the kernel ran (fusion included),
 // 1 when the problem does not qualify for the tensor-core path.
 int tc_conv_fprop(const b200gan_conv* cv, const b200gan_view* x, const void* wpacked, const b200gan_view* y, const TcEpi& epi,
                   cudaStream_t st) {
+  if (cv->k == 4 && cv->stride == 2 && cv->pad == 1 && wpacked && nhwc_dense_bf16(x) && nhwc_dense_bf16(y) &&
+      (epi.mode < 2 || (nhwc_dense_bf16(epi.prev_y) && epi.prev_y->n == y->n && epi.prev_y->h == y->h && epi.prev_y->w == y->w && epi.prev_y->c == y->c))) {
+    const int t = tc_conv_down4(x, wpacked, y, epi, st);
+    if (t <= 0) return t;
+  }
   return tc_conv_common(cv, x, wpacked, y, /*up=*/false, epi, st);
 }
 int tc_conv_dgrad(const b200gan_conv* cv, const b200gan_view* dy, const void* wpacked, const b200gan_view* dx, const TcEpi& epi,

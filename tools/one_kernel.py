@@ -32,6 +32,19 @@ def up():
         L.call('b200gan_convT2d_fprop', C.byref(cv), C.byref(L.view_nhwc(dy)), L.ptr(w), L.ptr(wu), C.byref(L.view_nhwc(dx)), C.byref(f1), st())
     else:
         L.call('b200gan_conv2d_dgrad', C.byref(cv), C.byref(L.view_nhwc(dy)), L.ptr(w), L.ptr(wu), C.byref(L.view_nhwc(dx)), C.byref(fz) if fz is not None else None, st())
+def down():
+    if epi == 'stats':
+        f1 = L.fuse(bn_sums=sums2)
+    elif epi == 'bnbwd':
+        f1 = L.fuse(prev_act=L.ACT_RELU, prev_y=L.view_nhwc(yprev), prev_scale=coef[0], prev_shift=coef[1], prev_mean=coef[2], prev_invstd=coef[3], prev_sums=sums2)
+    else:
+        f1 = None
+    L.call('b200gan_convT2d_dgrad' if epi == 'bnbwd' else 'b200gan_conv2d_fprop', C.byref(cv), C.byref(L.view_nhwc(x)), L.ptr(w), L.ptr(wd), C.byref(L.view_nhwc(y)), C.byref(f1) if f1 is not None else None, st())
+sums2 = torch.zeros(2 * co, device='cuda', dtype=torch.float64)
+yprev = torch.randn((B, h // 2, h // 2, co), device='cuda').to(bf)
+coef = torch.rand((4, co), device='cuda') + 0.5
+if which.endswith('down'):
+    up = down
 if len(sys.argv) > 4:
     for _ in range(3): up()
     torch.cuda.synchronize(); tot = 0
