@@ -45,6 +45,9 @@ int window_dgrad(const b200gan_conv*, const b200gan_view* dy, const float* w, co
 int window_wgrad(const b200gan_conv*, const b200gan_view* x, const b200gan_view* dy, float* dw, cudaStream_t);
 int latent_fprop(const b200gan_conv*, const b200gan_view* z, const float* w, const b200gan_view* y, cudaStream_t);
 int latent_wgrad(const b200gan_conv*, const b200gan_view* dy_fine, const b200gan_view* z, float* dw, cudaStream_t);
+// the same two as warp-level tensor-core GEMMs (latent_mma.cu)
+int latent_fprop_mma(const b200gan_conv*, const b200gan_view* z, const float* w, const b200gan_view* y, cudaStream_t);
+int latent_wgrad_mma(const b200gan_conv*, const b200gan_view* dy_fine, const b200gan_view* z, float* dw, cudaStream_t);
 // elementwise.cu
 int ew_bn_stats(const b200gan_view*, double*, cudaStream_t);
 int ew_bn_bwd_reduce(const b200gan_view*, const b200gan_view*, const b200gan_view*, const float*, const float*, const float*,
@@ -188,9 +191,11 @@ static int conv_dispatch(Prim prim, bool transposed, const b200gan_conv* cv, con
       if (prim == FPROP) t = window_fprop(cv, fine, w, coarse, st);
       else if (prim == DGRAD) {
         t = window_dgrad(cv, coarse, w, fine, st);
+        if (t > 0) t = latent_fprop_mma(cv, coarse, w, fine, st);
         if (t > 0) t = latent_fprop(cv, coarse, w, fine, st);
       } else {
         t = window_wgrad(cv, fine, coarse, dw, st);
+        if (t > 0) t = latent_wgrad_mma(cv, fine, coarse, dw, st);
         if (t > 0) t = latent_wgrad(cv, fine, coarse, dw, st);
       }
       if (t < 0) return t;

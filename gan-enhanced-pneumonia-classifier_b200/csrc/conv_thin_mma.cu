@@ -233,6 +233,18 @@ __global__ void __launch_bounds__(256) thin_down_mma_kernel(const ThinArgs a) {
   }
   for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
     const int n = tile / a.tiles_per_img, oh0 = (tile - n * a.tiles_per_img) * a.R;
+    // EPI 2: the saved forward output of this warp's NEXT m-tile is fetched one iteration ahead (the first one under the
+    // staging of the image band): loaded where it is used, its latency was exposed once per m-tile and tripled the kernel time
+    uint4 yq[2] = {make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u)};
+    auto fetch_y = [&](int mt) {
+      const int rr = mt / WB, c = mt - rr * WB;
+      if (mt < mtiles && oh0 + rr < a.H) {
+        const int64_t off = (((int64_t)n * a.H + oh0 + rr) * a.W + 16 * c + g) * 32 + 8 * t;
+        yq[0] = __ldg(reinterpret_cast<const uint4*>(a.prev_y + off));
+        yq[1] = __ldg(reinterpret_cast<const uint4*>(a.prev_y + off + 8 * 32));
+      }
+    };
+    if (EPI == 2) fetch_y(warp);
     __syncthreads();                       // previous tile fully consumed
     stage_fine<NC>(S, pitch, rows, a, n, 2 * oh0 - 1);
     __syncthreads();
@@ -240,6 +252,8 @@ __global__ void __launch_bounds__(256) thin_down_mma_kernel(const ThinArgs a) {
       const int rr = mt / WB, c = mt - rr * WB;
       const int oh = oh0 + rr;
       if (oh >= a.H) break;
+      const uint4 yc0 = yq[0], yc1 = yq[1];
+      if (EPI == 2) fetch_y(mt + 8);
       float acc[4][4];
 #pragma unroll
       for (int j = 0; j < 4; ++j)
@@ -272,8 +286,8 @@ __global__ void __launch_bounds__(256) thin_down_mma_kernel(const ThinArgs a) {
       // lane (g,t) holds channels 8t..8t+7 of pixels ow and ow+8: value index c = 2j+e <-> acc[j][e] (row g), acc[j][2+e] (row g+8)
       float yv[2][8];
       if (EPI == 2) {
-        unpack8(__ldg(reinterpret_cast<const uint4*>(a.prev_y + ooff)), yv[0]);
-        unpack8(__ldg(reinterpret_cast<const uint4*>(a.prev_y + ooff + 8 * 32)), yv[1]);
+        unpack8(yc0, yv[0]);
+        unpack8(yc1, yv[1]);
 #pragma unroll
         for (int hrow = 0; hrow < 2; ++hrow)
 #pragma unroll
