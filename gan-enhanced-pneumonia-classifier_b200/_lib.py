@@ -65,6 +65,7 @@ PROTOTYPES = {
     'b200gan_adam': [_vp, _vp, _vp, _vp, _i64, _f64, _f64, _f64, _f64, _i32, _vp, _f32, _vp],
     'b200gan_copy_view': [_VP, _VP, _vp],
     'b200gan_fill_f32': [_vp, _i64, _f32, _vp],
+    'b200gan_gather_augment': [_vp, _i64, _vp, _vp, C.POINTER(C.c_float), C.POINTER(C.c_float), _VP, _vp],
 }
 OTHER_SYMBOLS = ['b200gan_version', 'b200gan_last_error_string', 'b200gan_device_info']
 

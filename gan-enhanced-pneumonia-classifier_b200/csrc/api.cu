@@ -64,6 +64,7 @@ int ew_bce_sigmoid(const float*, int, float, float, float*, float*, float*, cuda
 int ew_adam(float*, const float*, float*, float*, int64_t, double, double, double, double, int, const int64_t*, float, cudaStream_t);
 int ew_copy_view(const b200gan_view*, const b200gan_view*, cudaStream_t);
 int ew_fill(float*, int64_t, float, cudaStream_t);
+int ew_gather_augment(const uint8_t*, int64_t, const int64_t*, const uint8_t*, const float*, const float*, const b200gan_view*, cudaStream_t);
 
 static int check_conv(const b200gan_conv* cv) {
   if (!cv) { set_error("null conv descriptor"); return B200GAN_ERR_BAD_ARG; }
@@ -355,6 +356,14 @@ int b200gan_copy_view(const b200gan_view* src, const b200gan_view* dst, void* st
 int b200gan_fill_f32(float* ptr, int64_t numel, float value, void* stream) {
   B200_CHECK_ARG(ptr || numel == 0, "fill_f32: null pointer");
   return ew_fill(ptr, numel, value, (cudaStream_t)stream);
+}
+
+int b200gan_gather_augment(const uint8_t* cache, int64_t num_images, const int64_t* index, const uint8_t* flip, const float* mean,
+                           const float* std, const b200gan_view* out, void* stream) {
+  int rc;
+  B200_CHECK_ARG(cache && index && num_images > 0, "gather_augment: null cache / index or empty cache");
+  if ((rc = check_view(out, "gather_augment"))) return rc;
+  return ew_gather_augment(cache, num_images, index, flip, mean, std, out, (cudaStream_t)stream);
 }
 
 }  // extern "C"

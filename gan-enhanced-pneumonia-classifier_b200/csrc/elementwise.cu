@@ -781,4 +781,65 @@ int ew_fill(float* p, int64_t n, float v, cudaStream_t st) {
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Input pipeline (reference: src/data_loader.py:17-23 'train' transform after Resize, consumed at src/train_gan.py:123):
+// out[b] = Normalize(ToTensor(hflip?(cache[index[b]]))) gathered from a device-resident uint8 cache (N, C, H, W).
+// One thread = four consecutive output pixels of one (b, c, h) row: a 4-byte read (mirrored rows read the mirrored group),
+// (v / 255 - mean) / std in fp32 with true divisions, exactly torchvision's ToTensor + Normalize.
+// ---------------------------------------------------------------------------------------------------
+struct AugCoef { float mean[4], stdv[4]; };
+
+template <typename TO>
+__global__ void __launch_bounds__(256) gather_augment_kernel(const uint8_t* __restrict__ cache, const int64_t* __restrict__ index,
+                                                             const uint8_t* __restrict__ flip, AugCoef cf, View out, int64_t num_images) {
+  const int W4 = (out.w + 3) >> 2;
+  const int64_t total = (int64_t)out.n * out.c * out.h * W4;
+  const bool vec_in = (out.w & 3) == 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int w4 = (int)(i % W4);
+    int64_t r = i / W4;
+    const int h = (int)(r % out.h); r /= out.h;
+    const int c = (int)(r % out.c);
+    const int b = (int)(r / out.c);
+    int64_t src = index[b];
+    src = src < 0 ? 0 : (src >= num_images ? num_images - 1 : src);
+    const bool mirror = flip && flip[b] != 0;
+    const uint8_t* row = cache + ((src * out.c + c) * out.h + h) * (int64_t)out.w;
+    const int w0 = 4 * w4;
+    uint8_t px[4];
+    if (vec_in) {
+      const uchar4 v = *reinterpret_cast<const uchar4*>(row + (mirror ? out.w - 4 - w0 : w0));
+      if (mirror) { px[0] = v.w; px[1] = v.z; px[2] = v.y; px[3] = v.x; }
+      else { px[0] = v.x; px[1] = v.y; px[2] = v.z; px[3] = v.w; }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) px[e] = w0 + e < out.w ? row[mirror ? out.w - 1 - (w0 + e) : w0 + e] : 0;
+    }
+    float o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) o[e] = __fdiv_rn(__fdiv_rn((float)px[e], 255.f) - cf.mean[c], cf.stdv[c]);
+    TO* dst = reinterpret_cast<TO*>(out.ptr) + (int64_t)b * out.sn + (int64_t)h * out.sh + (int64_t)w0 * out.sw + (int64_t)c * out.sc;
+    if (sizeof(TO) == 4 && out.sw == 1 && vec_in && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+      *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (w0 + e < out.w) st_from_float(dst + (int64_t)e * out.sw, o[e]);
+    }
+  }
+}
+
+int ew_gather_augment(const uint8_t* cache, int64_t num_images, const int64_t* index, const uint8_t* flip, const float* mean, const float* stdv,
+                      const b200gan_view* out, cudaStream_t st) {
+  B200_CHECK_ARG(out->c >= 1 && out->c <= 4, "gather_augment: 1..4 channels");
+  AugCoef cf;
+  for (int c = 0; c < 4; ++c) { cf.mean[c] = c < out->c && mean ? mean[c] : 0.f; cf.stdv[c] = c < out->c && stdv ? stdv[c] : 1.f; }
+  const int64_t total = (int64_t)out->n * out->c * out->h * ((out->w + 3) / 4);
+  if (total <= 0) return 0;
+  if (out->dtype == B200GAN_F32) gather_augment_kernel<float><<<ew_blocks(total), 256, 0, st>>>(cache, index, flip, cf, to_view(out), num_images);
+  else gather_augment_kernel<__nv_bfloat16><<<ew_blocks(total), 256, 0, st>>>(cache, index, flip, cf, to_view(out), num_images);
+  B200_LAUNCH_CHECK("gather_augment");
+  return 0;
+}
+
 }  // namespace b200gan

@@ -29,9 +29,11 @@ if __package__ in (None, ''):
     sys.path.insert(0, _HERE)
     from gan_enhanced_pneumonia_classifier_b200.dcgan import Discriminator, Generator, weights_init
     from gan_enhanced_pneumonia_classifier_b200.trainer import DCGANTrainer
+    from gan_enhanced_pneumonia_classifier_b200.data_cache import DeviceImageCache
 else:
     from .dcgan import Discriminator, Generator, weights_init
     from .trainer import DCGANTrainer
+    from .data_cache import DeviceImageCache
 
 HISTORY_KEYS = ('G_losses_iter', 'D_losses_iter', 'D_x_iter', 'D_G_z1_iter', 'D_G_z2_iter', 'G_losses_epoch', 'D_losses_epoch')
 
@@ -126,7 +128,40 @@ def main(args):
 
     # --- data ------------------------------------------------------------------------------------
     n_syn = getattr(args, 'synthetic', 0)
-    if n_syn:
+    cached = getattr(args, 'cache_dataset', False)
+    if cached and not use_cuda:
+        print('Error: --cache-dataset keeps the training images in GPU memory; it needs CUDA (drop the flag for --cpu runs).')
+        return
+    cache_dtype = {'bf16': torch.bfloat16, 'fp32': torch.float32}[getattr(args, 'dtype', 'bf16')]
+    if n_syn and cached:
+        g = torch.Generator().manual_seed(1 + rank)
+        u8 = torch.randint(0, 256, (n_syn, args.num_channels, 224, 224), dtype=torch.uint8, generator=g)
+        half = (0.5,) * args.num_channels
+        train_loader = DeviceImageCache(u8.to(device), batch_size=args.batch_size, mean=half, std=half, dtype=cache_dtype, seed=getattr(args, 'seed', None))
+        print(f'Loaded training data with {len(train_loader.dataset)} samples.' if is_main else '', end='\n' if is_main else '')
+    elif cached:
+        try:
+            import torchvision.transforms as T
+            from data_loader import RSNAPneumoniaDataset, check_dataset_availability     # the reference's src/data_loader.py:75,119
+            if not check_dataset_availability(args.data_dir):
+                raise FileNotFoundError(f'Dataset not available in {args.data_dir}. Please download using the provided script.')
+            ds = RSNAPneumoniaDataset(os.path.join(args.data_dir, 'Training', 'Images'), os.path.join(args.data_dir, 'stage2_train_metadata.csv'),
+                                      transform=T.Resize((224, 224)), is_test=False)
+            if world > 1:        # each rank caches and draws from its own slice of the images
+                ds = torch.utils.data.Subset(ds, range(rank, len(ds), world))
+            train_loader = DeviceImageCache.from_dataset(ds, device, num_workers=args.workers, batch_size=args.batch_size, dtype=cache_dtype,
+                                                         seed=getattr(args, 'seed', None))
+            if train_loader.images.shape[1] != args.num_channels:
+                print(f'Error: the dataset has {train_loader.images.shape[1]} channels, --num-channels is {args.num_channels}')
+                return
+            print(f'Loaded training data with {len(train_loader.dataset)} samples (device-resident cache, '
+                  f'{train_loader.images.numel() / 2**30:.2f} GiB).')
+        except FileNotFoundError as e:
+            print(f'Error: {e}')
+            print(f"Please ensure the dataset exists at '{args.data_dir}' and is structured correctly.")
+            print('Run `python src/download_dataset.py` first if needed.')
+            return
+    elif n_syn:
         train_loader = _synthetic_loader(n_syn, args.num_channels, args.batch_size, 1 + rank)
         print(f'Loaded training data with {len(train_loader.dataset)} samples.' if is_main else '', end='\n' if is_main else '')
     else:
@@ -287,6 +322,8 @@ def build_parser():
     # --- additive flags of the B200 build --- #
     parser.add_argument('--dtype', choices=['bf16', 'fp32'], default='bf16', help='B200 compute mode: bf16 tensor-core path or fp32 parity path')
     parser.add_argument('--synthetic', type=int, default=0, metavar='N', help='train on N synthetic uniform[-1,1] images instead of the RSNA loader')
+    parser.add_argument('--cache-dataset', action='store_true', help='decode the training images once into a device-resident uint8 cache; '
+                        'shuffle, horizontal flip and normalisation then run on the GPU (CUDA only)')
     parser.add_argument('--max-iters', type=int, default=0, help='stop after this many iterations (0 = run all epochs)')
     parser.add_argument('--log-interval', type=int, default=50, help='flush the device-side history scalars every N iterations')
     parser.add_argument('--seed', type=int, default=None, help='torch.manual_seed (the reference is unseeded)')

@@ -199,6 +199,15 @@ int b200gan_adam(float* param, const float* grad, float* exp_avg, float* exp_avg
 int b200gan_copy_view(const b200gan_view* src, const b200gan_view* dst, void* stream);
 int b200gan_fill_f32(float* ptr, int64_t numel, float value, void* stream);
 
+/* ---- input pipeline of the training loop (src/data_loader.py:17-23 'train' transform after Resize; the batch consumed at
+ *      src/train_gan.py:123): one batch gathered from a DEVICE-resident uint8 image cache instead of PNG decoding per epoch:
+ *        out[b] = Normalize(mean, std)(ToTensor(hflip_if(flip[b])(cache[index[b]])))
+ *      cache: (num_images, C, H, W) uint8 contiguous, C/H/W = out's extents;  index: int64[out->n] (device);  flip: uint8[out->n]
+ *      (device; non-zero mirrors along W; NULL = never);  mean/std: float[C] HOST arrays (NULL = 0 / 1);  out: f32 or bf16 view.
+ *      Arithmetic is torchvision's, (v / 255 - mean) / std in fp32 with true divisions: bit-exact for an f32 output. */
+int b200gan_gather_augment(const uint8_t* cache, int64_t num_images, const int64_t* index, const uint8_t* flip, const float* mean,
+                           const float* std, const b200gan_view* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

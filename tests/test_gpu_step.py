@@ -258,6 +258,20 @@ def test_cli_train_then_sample_on_gpu(tmp_path):
         assert np.abs(got.astype(int) - want[i].astype(int)).max() <= 1, f'image {i}'       # fp32 path: at most one grey level
 
 
+@pytest.mark.parametrize('dtype', ['fp32', 'bf16'])
+def test_cli_trains_from_the_device_resident_cache(tmp_path, dtype):
+    """train_gan.py --cache-dataset: batches come from DeviceImageCache (uint8 in HBM, gather / flip / normalise on the GPU)
+    instead of a host DataLoader; 10 images at batch 4 = 3 iterations per epoch, the last one ragged."""
+    from gan_enhanced_pneumonia_classifier_b200 import train_gan as tg
+    d = str(tmp_path)
+    argv = ['--synthetic', '10', '--cache-dataset', '--batch-size', '4', '--epochs', '2', '--latent-dim', '16', '--feature-maps-g', '8',
+            '--feature-maps-d', '8', '--num-channels', '3', '--vis-batch-size', '4', '--model-dir', d + '/models', '--output-dir', d + '/results',
+            '--results-dir', d + '/results/metrics', '--figures-dir', d + '/results/figures', '--seed', '0', '--dtype', dtype]
+    hist = tg.main(tg.build_parser().parse_args(argv))
+    assert len(hist['G_losses_iter']) == 6 and all(np.isfinite(hist['D_losses_iter'])) and all(np.isfinite(hist['G_losses_iter']))
+    assert os.path.exists(d + '/models/gan/generator_final.pth')
+
+
 def test_packed_weight_cache_follows_the_weights_under_graph_replay():
     """Full-size networks (ngf = ndf = 64: the tcgen05 layers and their bf16 weight repacks are active), batch 2, graph replay.
     The repacks are cached per Adam update in persistent buffers that the captured graph reads across replays; after every step
