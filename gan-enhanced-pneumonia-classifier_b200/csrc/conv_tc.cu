@@ -100,6 +100,7 @@ struct TcSmem {
 // smem ring keeps running across tile boundaries.  No integer division sits on the per-k-block path of the two
 // single-thread roles (a first version spent ~100 instructions per step there).
 constexpr int kTcThreads = 320;
+constexpr int kHaloThreads = 352;          // halo-tile kernels: + one warp that owns the TMA stores of the output tiles
 
 template <int BN, int KC, int STAGES, int EPI>
 __global__ void __launch_bounds__(kTcThreads, 2)
@@ -230,35 +231,64 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     const int row = q * 32 + lane;
     const int tw = row & (TW - 1), th = (row >> p.tw_log2) & (TH - 1), tn = row >> (p.tw_log2 + p.th_log2);
     int lt = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++lt) {
+    // (valid, output offset, first column) of this thread's row piece in tile t
+    auto locate = [&](int t, bool& valid, int& cout0) -> int64_t {
       int r = t;
       const int cls = r % p.ncls; r /= p.ncls;
       const int nt = r % p.n_tiles; r /= p.n_tiles;
       const int tw_i = r % p.tiles_w; r /= p.tiles_w;
       const int th_i = r % p.tiles_h;
       const int tn_i = r / p.tiles_h;
-      const int ow = tw_i * TW + tw, oh = th_i * TH + th, n = tn_i * TN + tn, cout0 = nt * BN + hcol * CW;
-      const bool valid = ow < p.QW && oh < p.QH && n < p.NB;
+      const int ow = tw_i * TW + tw, oh = th_i * TH + th, n = tn_i * TN + tn;
+      cout0 = nt * BN + hcol * CW;
+      valid = ow < p.QW && oh < p.QH && n < p.NB && t < num_tiles;
       const int py = cls >> 1, px = cls & 1;
-      const int64_t ooff = (int64_t)n * p.o_sn + (int64_t)(oh * p.o_mul + (p.o_mul > 1 ? py : 0)) * p.o_sh +
-                           (int64_t)(ow * p.o_mul + (p.o_mul > 1 ? px : 0)) * p.o_sw + cout0;
+      return (int64_t)n * p.o_sn + (int64_t)(oh * p.o_mul + (p.o_mul > 1 ? py : 0)) * p.o_sh +
+             (int64_t)(ow * p.o_mul + (p.o_mul > 1 ? px : 0)) * p.o_sw + cout0;
+    };
+    // Narrow tiles (<= 32 columns per warp): the whole row piece of y_prev for the NEXT tile is requested while this tile is
+    // processed.  Requested per 16-column chunk inside the tile, every chunk exposed one HBM latency (~1.5 us) to the eight
+    // epilogue warps, longer than the MMA stream of a whole tile.
+    constexpr bool PRE = EPI >= 2 && CW <= 32;
+    constexpr int NPRE = PRE ? CW / 8 : 1;
+    uint4 ypre[NPRE];
+    auto prefetch = [&](int t) {
+      bool v2; int c2;
+      const int64_t off = locate(t, v2, c2);
+#pragma unroll
+      for (int j = 0; j < NPRE; ++j) ypre[j] = make_uint4(0u, 0u, 0u, 0u);
+      if (v2) {
+#pragma unroll
+        for (int j = 0; j < NPRE; j += 2) ldg256_nc(reinterpret_cast<const uint4*>(p.prev_y + off) + j, ypre[j], ypre[j + 1]);
+      }
+    };
+    if (PRE) prefetch(blockIdx.x);
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++lt) {
+      bool valid; int cout0;
+      const int64_t ooff = locate(t, valid, cout0);
       __nv_bfloat16* orow = p.out + ooff;
       const uint4* yp = reinterpret_cast<const uint4*>(p.prev_y + ooff);
-      uint4 ynext[2];
-      if (EPI >= 2) {                                // the first piece of y_prev is requested before the accumulator is waited for
+      uint4 ynext[2], yall[NPRE];
+      if (PRE) {
+#pragma unroll
+        for (int j = 0; j < NPRE; ++j) yall[j] = ypre[j];
+        prefetch(t + gridDim.x);
+      } else if (EPI >= 2) {                         // the first piece of y_prev is requested before the accumulator is waited for
         ynext[0] = ynext[1] = make_uint4(0u, 0u, 0u, 0u);
         if (valid) ldg256_nc(yp, ynext[0], ynext[1]);
       }
       const int buf = lt % NACC;
       mbar_wait(&acc_full[buf], (lt / NACC) & 1);
       tcgen05_fence_after();
-#pragma unroll 1
+#pragma unroll (PRE ? 2 : 1)
       for (int c0 = 0; c0 < CW; c0 += 16) {
         uint32_t v[16];
         tcgen05_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + hcol * CW + c0, v);
         float s0[16], s1[16];
         uint4 ycur[2];
-        if (EPI >= 2) {
+        if (PRE) {
+          ycur[0] = yall[(c0 / 8) % NPRE]; ycur[1] = yall[(c0 / 8 + 1) % NPRE];
+        } else if (EPI >= 2) {
           ycur[0] = ynext[0]; ycur[1] = ynext[1];
           if (c0 + 16 < CW) {
             ynext[0] = ynext[1] = make_uint4(0u, 0u, 0u, 0u);
@@ -525,6 +555,7 @@ struct Up4Params {
   const __nv_bfloat16* prev_y;
   float prev_neg;
   int nstages, off_res, off_bar, off_y;
+  int yreg;                           // EPI 3: 1 = the saved activation is prefetched into registers one tile ahead, 0 = TMA-staged
 };
 
 // neighbour order: centre first (it initialises all four accumulators), then edges, then corners
@@ -583,7 +614,7 @@ constexpr int kUp4TileBytes = (kUp4TH + 2) * kUp4Pitch;                 // 23040
 constexpr int kUp4Stage = (kUp4TileBytes + 1023) & ~1023;               // 23552
 
 template <int EPI>
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__(kHaloThreads, 1)
 conv_up4_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_y,
                    const __grid_constant__ CUtensorMap map_o, const Up4Params p) {
   constexpr int WB_BYTES = 32 * 64 * 2;                              // one (class, tap) weight block
@@ -600,18 +631,19 @@ conv_up4_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   uint64_t* res_bar = acc_empty + 4;
   uint64_t* y_full = res_bar + 1;              // [YST]
   uint64_t* y_empty = y_full + 4;              // [YST]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(y_empty + 4);
+  uint64_t* staged = y_empty + 4;              // [YST] the eight epilogue warps have written their part of the output tile
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(staged + 4);
   uint8_t* smem_y = smem + p.off_y;
   float* ch_acc = reinterpret_cast<float*>(smem + p.off_bar + 512);   // [2][32] (EPI 1)
   uint8_t* smem_res = smem + p.off_res;                               // 16 weight blocks, see slot table below
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr int kTmaWarp = 8, kMmaWarp = 9;
+  constexpr int kTmaWarp = 8, kMmaWarp = 9, kStoreWarp = 10;
   if (EPI == 1) for (int c = threadIdx.x; c < 64; c += blockDim.x) ch_acc[c] = 0.f;
   if (warp == kTmaWarp && lane == 0) {
     for (int s = 0; s < NST; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int b = 0; b < NACC; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 8); }
     mbar_init(res_bar, 1);
-    for (int b = 0; b < YST; ++b) { mbar_init(&y_full[b], 1); mbar_init(&y_empty[b], 1); }
+    for (int b = 0; b < YST; ++b) { mbar_init(&y_full[b], 1); mbar_init(&y_empty[b], 1); mbar_init(&staged[b], 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     if (EPI == 3) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_y) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_o) : "memory");
@@ -654,7 +686,7 @@ conv_up4_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         mbar_expect_tx(&full_bar[s], kUp4TileBytes);
         tma_load_4d(smem + s * kUp4Stage, &map_a, &full_bar[s], 0, tw_i * kUp4TW - 1, th_i * kUp4TH - 1, n);
         if (++s == NST) { s = 0; ph ^= 1; }
-        if (EPI == 3) {
+        if (EPI == 3 && !p.yreg) {
           // the saved activation under this tile's output (32 lines x 16 pixels), for the epilogue: staged by TMA because a
           // per-thread global load of 128 bytes at a 128-byte lane stride costs 32 L1 wavefronts per instruction
           mbar_wait(&y_empty[ys], yph ^ 1);
@@ -694,6 +726,27 @@ conv_up4_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       }
     }
     __syncwarp();
+  } else if (warp == kStoreWarp) {
+    // ===== output stores: one thread turns every staged tile into ONE coalesced TMA store and hands the staging buffer back as
+    // soon as the store has read it.  A thread of its own may block on that read; the epilogue warps never meet at a CTA barrier.
+    if (lane == 0) {
+      int ys = 0;
+      uint32_t sph = 0;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+        const int n = t / tiles_per_img, r = t - n * tiles_per_img;
+        const int th_i = r / p.tiles_w, tw_i = r - th_i * p.tiles_w;
+        mbar_wait(&staged[ys], sph);
+        asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(&map_o),
+                     "r"(smem_u32(smem_y + ys * Y_BYTES)), "r"(0), "r"(2 * tw_i * kUp4TW), "r"(2 * th_i * kUp4TH), "r"(n)
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        mbar_arrive(&y_empty[ys]);
+        if (++ys == YST) { ys = 0; sph ^= 1; }
+      }
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");       // all stores complete before the CTA exits
+    }
+    __syncwarp();
   } else {
     // ===== epilogue: warps 0..7; TMEM lane quarter = warp % 4 (input pixel rows), half = warp / 4 = output row parity py =====
     const int q = warp & 3, py = warp >> 2;
@@ -712,6 +765,19 @@ conv_up4_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     int lt = 0, ys = 0;
     uint32_t yph = 0;
     float st0 = 0.f, st1 = 0.f, st2 = 0.f, st3 = 0.f;
+    uint4 ypre[EPI == 3 ? 8 : 1];
+    auto prefetch_y = [&](int t) {
+      if (EPI != 3) return;
+      bool v2;
+      const int64_t off = locate(t, v2);
+#pragma unroll
+      for (int j = 0; j < (EPI == 3 ? 8 : 1); ++j) ypre[j] = make_uint4(0u, 0u, 0u, 0u);
+      if (v2) {
+#pragma unroll
+        for (int j = 0; j < (EPI == 3 ? 8 : 0); j += 2) ldg256_nc(reinterpret_cast<const uint4*>(p.prev_y + off) + j, ypre[j], ypre[j + 1]);
+      }
+    };
+    if (EPI == 3 && p.yreg) prefetch_y(blockIdx.x);
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++lt) {
       bool valid;
       (void)locate(t, valid);
@@ -719,7 +785,12 @@ conv_up4_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       // this thread's two output pixels (line 2th+py, pixels 2tw and 2tw+1) inside the 64B-swizzled 32 x 16 pixel tile
       const int pix = (2 * th + py) * 16 + 2 * tw;
       uint4 yv[8];
-      if (EPI == 3) {
+      if (EPI == 3 && p.yreg) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) yv[j] = ypre[j];
+        prefetch_y(t + gridDim.x);
+        mbar_wait(&y_empty[ys], yph ^ 1);
+      } else if (EPI == 3) {
         mbar_wait(&y_full[ys], yph);                    // saved activation landed (the producer waited for the buffer)
 #pragma unroll
         for (int j = 0; j < 8; ++j) yv[j] = *reinterpret_cast<const uint4*>(yt + sw64(pix + (j >> 2), j & 3));
@@ -763,21 +834,12 @@ conv_up4_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[buf]);
-      // one coalesced TMA store of the whole 32 KB tile instead of 16-byte stores at a 128-byte lane stride
+      // publish this warp's part of the staged tile to the async proxy and to the store thread
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (threadIdx.x == 0) {
-        const int n = t / tiles_per_img, r = t - n * tiles_per_img;
-        const int th_i = r / p.tiles_w, tw_i = r - th_i * p.tiles_w;
-        asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(&map_o), "r"(smem_u32(yt)), "r"(0),
-                     "r"(2 * tw_i * kUp4TW), "r"(2 * th_i * kUp4TH), "r"(n)
-                     : "memory");
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        // the store issued one tile ago has finished READING its buffer: hand that buffer back
-        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-        if (lt > 0) mbar_arrive(&y_empty[(ys + YST - 1) % YST]);
-      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&staged[ys]);
       if (EPI == 1) {
+        mbar_wait(&staged[ys], yph);                   // all eight warps have written (the store thread reads it concurrently)
         // BatchNorm statistics from the staged (bf16-rounded) tile: warp w owns lines 4w..4w+3 (64 pixels), a half-warp one pixel,
         // lane l the channel pair 2(l%16), +1 (conflict-free 4-byte shared loads), accumulated in registers over the CTA's tiles
         const int n = t / tiles_per_img, r = t - n * tiles_per_img;
@@ -794,7 +856,6 @@ conv_up4_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       }
       if (++ys == YST) { ys = 0; yph ^= 1; }
     }
-    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // all stores complete before the CTA exits
     if (EPI == 1) {
       atomicAdd(&ch_acc[2 * (lane & 15)], st0); atomicAdd(&ch_acc[2 * (lane & 15) + 1], st1);
       atomicAdd(&ch_acc[32 + 2 * (lane & 15)], st2); atomicAdd(&ch_acc[32 + 2 * (lane & 15) + 1], st3);
@@ -818,7 +879,7 @@ static int launch_up4(const CUtensorMap& ma, const CUtensorMap& mb, const CUtens
     B200_CUDA(cudaFuncSetAttribute(conv_up4_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = smem;
   }
-  conv_up4_tc_kernel<EPI><<<grid, kTcThreads, smem, st>>>(ma, mb, my, mo, p);
+  conv_up4_tc_kernel<EPI><<<grid, kHaloThreads, smem, st>>>(ma, mb, my, mo, p);
   B200_LAUNCH_CHECK("conv_up4_tc_kernel");
   return 0;
 }
@@ -842,6 +903,10 @@ static int tc_conv_up4(const b200gan_view* in, const void* wpacked, const b200ga
   if (epi.mode == 3) {
     p.prev_y = reinterpret_cast<const __nv_bfloat16*>(epi.prev_y->ptr);
     p.prev_neg = epi.act == B200GAN_ACT_RELU ? 0.f : (epi.act == B200GAN_ACT_LRELU ? epi.slope : 1.f);
+    // measured at B=512 (tools/one_kernel.py d1_up 512 mask): TMA-staged 237 us, register prefetch one tile ahead 281 us (each
+    // 32-byte-per-lane load at a 128-byte lane stride costs 32 L1 wavefronts); the knob stays for re-measurement
+    static const int yreg = getenv("B200GAN_UP4_YREG") ? atoi(getenv("B200GAN_UP4_YREG")) : 0;
+    p.yreg = yreg;
   }
   CUtensorMap ma, mb;
   {
@@ -924,7 +989,7 @@ __device__ __forceinline__ void down4_issue_from(uint32_t tmem_d, uint64_t adesc
 __device__ __forceinline__ uint32_t sw128(int pix, int chunk) { return (uint32_t)pix * 128u + (uint32_t)((chunk ^ (pix & 7)) << 4); }
 
 template <int EPI>
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__(kHaloThreads, 1)
 conv_down4_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_y,
                      const __grid_constant__ CUtensorMap map_o, const Down4Params p) {
   constexpr int NACC = 4;
@@ -939,13 +1004,14 @@ conv_down4_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   uint64_t* res_bar = acc_empty + 4;
   uint64_t* y_full = res_bar + 1;
   uint64_t* y_empty = y_full + 4;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(y_empty + 4);
+  uint64_t* staged = y_empty + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(staged + 4);
   float* ch_acc = reinterpret_cast<float*>(smem + p.off_bar + 512);      // [2][64]
   float4* ch_coef = reinterpret_cast<float4*>(ch_acc + 128);             // [64] {scale, shift, mean, invstd}
   uint8_t* smem_res = smem + p.off_res;
   uint8_t* smem_io = smem + p.off_io;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr int kTmaWarp = 8, kMmaWarp = 9;
+  constexpr int kTmaWarp = 8, kMmaWarp = 9, kStoreWarp = 10;
   if (EPI != 0) {
     for (int c = threadIdx.x; c < 128; c += blockDim.x) ch_acc[c] = 0.f;
     if (EPI == 2)
@@ -955,7 +1021,7 @@ conv_down4_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     for (int s = 0; s < NST; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int b = 0; b < NACC; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 8); }
     mbar_init(res_bar, 1);
-    for (int b = 0; b < YST; ++b) { mbar_init(&y_full[b], 1); mbar_init(&y_empty[b], 1); }
+    for (int b = 0; b < YST; ++b) { mbar_init(&y_full[b], 1); mbar_init(&y_empty[b], 1); mbar_init(&staged[b], 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
@@ -1014,6 +1080,26 @@ conv_down4_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
       tcgen05_commit_elect(&acc_full[buf]);
       if (++s == NST) { s = 0; ph ^= 1; }
     }
+  } else if (warp == kStoreWarp) {
+    // ===== output stores (see conv_up4_tc_kernel): one thread, one TMA store per staged tile, buffer handed back once read =====
+    if (lane == 0) {
+      int ys = 0;
+      uint32_t sph = 0;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+        const int n = t / tiles_per_img, r = t - n * tiles_per_img;
+        const int th_i = r / p.tiles_w, tw_i = r - th_i * p.tiles_w;
+        mbar_wait(&staged[ys], sph);
+        asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(&map_o),
+                     "r"(smem_u32(smem_io + ys * kDn4IoBytes)), "r"(0), "r"(8 * tw_i), "r"(16 * th_i), "r"(n)
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        mbar_arrive(&y_empty[ys]);
+        if (++ys == YST) { ys = 0; sph ^= 1; }
+      }
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+    __syncwarp();
   } else {
     // ===== epilogue: warps 0..7; TMEM lane quarter = warp % 4 (output pixel rows), column half = warp / 4 =====
     const int q = warp & 3, hcol = warp >> 2;
@@ -1087,16 +1173,10 @@ conv_down4_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[buf]);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (threadIdx.x == 0) {
-        asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(&map_o), "r"(smem_u32(io)), "r"(0),
-                     "r"(8 * tw_i), "r"(16 * th_i), "r"(n)
-                     : "memory");
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-        if (lt > 0) mbar_arrive(&y_empty[(ys + YST - 1) % YST]);
-      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&staged[ys]);
       if (EPI == 1) {
+        mbar_wait(&staged[ys], yph);
         // BatchNorm statistics from the staged (bf16-rounded) tile: warp w owns pixels 16w..16w+15, lane l the channel pair 2l, 2l+1
         // (one conflict-free 4-byte shared load per pixel), accumulated in registers over all tiles of the CTA
 #pragma unroll 4
@@ -1111,7 +1191,6 @@ conv_down4_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
       }
       if (++ys == YST) { ys = 0; yph ^= 1; }
     }
-    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     if (EPI == 1) {
       atomicAdd(&ch_acc[2 * lane], st0); atomicAdd(&ch_acc[2 * lane + 1], st1);
       atomicAdd(&ch_acc[64 + 2 * lane], st2); atomicAdd(&ch_acc[64 + 2 * lane + 1], st3);
@@ -1141,7 +1220,7 @@ static int launch_down4(const CUtensorMap& ma, const CUtensorMap& mb, const CUte
     B200_CUDA(cudaFuncSetAttribute(conv_down4_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = smem;
   }
-  conv_down4_tc_kernel<EPI><<<grid, kTcThreads, smem, st>>>(ma, mb, my, mo, p);
+  conv_down4_tc_kernel<EPI><<<grid, kHaloThreads, smem, st>>>(ma, mb, my, mo, p);
   B200_LAUNCH_CHECK("conv_down4_tc_kernel");
   return 0;
 }

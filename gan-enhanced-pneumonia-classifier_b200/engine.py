@@ -328,7 +328,8 @@ class NetEngine:
                                    prev_mean=lb.mean, prev_invstd=lb.invstd, prev_sums=lb.bsums)
                 elif self._act_fused(i - 1) and below.act in (L.ACT_LRELU, L.ACT_RELU) and (need_wgrad or dinput is not None):
                     # D0 (LeakyReLU, no BatchNorm): its activation backward rides on THIS layer's dgrad epilogue, so D0's own
-                    # wgrad / dgrad read a plain gradient tensor
+                    # wgrad / dgrad read a plain gradient tensor (measured at B=512: the mask on D0's wgrad operand instead sends
+                    # that kernel down its register-staged variant, 299 us against 120 us, more than the epilogue costs here)
                     fuse_kw.update(prev_act=below.act, prev_slope=LRELU_SLOPE, prev_y=lb.a.v)
                     masked = True
                 d = Act(torch.empty(lc.x.t.shape, device=dev, dtype=self.dtype), nchw=False)

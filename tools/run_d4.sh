@@ -1,1 +1,2 @@
-timeout 600 python -m pytest tests/test_gpu_data_cache.py tests/test_gpu_step.py -x -q 2>&1 | tail -15
+B200GAN_UP4_YREG=0 timeout 60 python tools/one_kernel.py d1_up 512 mask time
+B200GAN_UP4_YREG=1 timeout 60 python tools/one_kernel.py d1_up 512 mask time
