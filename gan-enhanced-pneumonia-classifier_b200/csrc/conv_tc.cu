@@ -94,9 +94,9 @@ struct TcSmem {
 // Persistent kernel: each CTA walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... of the (M-tile, N-tile, class)
 // space.  Warps 0..7 = epilogue (TMEM lane quarter = warp % 4, column half = warp / 4: eight warps keep enough global loads /
 // stores in flight for the fused epilogues), warp 8 = TMA producer, warp 9 = MMA issuer + TMEM owner.  The two single-thread
-// roles sit in the HIGHEST warp slots on purpose: the warp scheduler favours higher warp ids among eligible warps, and with
-// the roles in warps 0/1 the instruction-heavy fused epilogues delayed every TMA / MMA issue (measured +30 % kernel time).  The accumulator is
-// double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps the MMA stream of tile i+1, and the
+// roles sit in the highest warp slots so that an epilogue warp's TMEM lane quarter and column half are warp % 4 and warp / 4
+// (roles in warps 0/1 instead measured the same within noise).  The accumulator is
+// multi-buffered in TMEM (2-4 x BN columns) so the epilogue of tile i overlaps the MMA stream of tile i+1, and the
 // smem ring keeps running across tile boundaries.  No integer division sits on the per-k-block path of the two
 // single-thread roles (a first version spent ~100 instructions per step there).
 constexpr int kTcThreads = 320;

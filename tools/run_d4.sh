@@ -1,2 +1,2 @@
-B200GAN_UP4_YREG=0 timeout 60 python tools/one_kernel.py d1_up 512 mask time
-B200GAN_UP4_YREG=1 timeout 60 python tools/one_kernel.py d1_up 512 mask time
+timeout 300 python -m pytest tests/test_gpu_fuse.py tests/test_gpu_thin.py -x -q 2>&1 | tail -3
+timeout 200 python tools/step_profile.py > gpurun_out/step_profile_l.txt 2>&1; grep -E "total|thin_down" gpurun_out/step_profile_l.txt
