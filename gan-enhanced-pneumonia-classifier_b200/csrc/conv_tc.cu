@@ -1493,21 +1493,30 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
   }
 }
 
-// dw[co][ci][tap] += ws[co][tap][ci]; ws = 0 (the workspace is handed back zeroed)
+// dw[co][ci][tap] += ws[co][tap][ci]; ws = 0 (the workspace is handed back zeroed).  One CTA per output channel: its 16 x Ci
+// slab (<= 32 KB) goes through shared memory with every thread's loads of a phase issued back to back (blocks of 512 floats with
+// one load per thread and phase were latency bound: 15 us per launch, twelve launches per iteration).  Ci % 4 == 0.
 __global__ void __launch_bounds__(256) wgrad_finalize_kernel(float* __restrict__ ws, float* __restrict__ dw, int Co, int Ci) {
-  __shared__ float t[16][33];
-  const int co = blockIdx.y, c0 = blockIdx.x * 32;
-  const int lane = threadIdx.x & 31, row = threadIdx.x >> 5;              // 8 rows of 32 lanes
-  for (int tap = row; tap < 16; tap += 8) {
-    float* src = ws + ((int64_t)co * 16 + tap) * Ci + c0 + lane;
-    t[tap][lane] = (c0 + lane < Ci) ? *src : 0.f;
-    if (c0 + lane < Ci) *src = 0.f;
+  extern __shared__ float fin_t[];                                         // [16][Ci + 1]
+  const int P = Ci + 1, n = 16 * Ci;
+  float* src = ws + (int64_t)blockIdx.x * n;
+  float* dst = dw + (int64_t)blockIdx.x * n;
+#pragma unroll 4
+  for (int i0 = threadIdx.x * 4; i0 < n; i0 += 1024) {
+    const float4 v = *reinterpret_cast<const float4*>(src + i0);           // tap = i0 / Ci, four consecutive ci
+    *reinterpret_cast<float4*>(src + i0) = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int tap = i0 / Ci, ci = i0 - tap * Ci;
+    float* t = fin_t + tap * P + ci;
+    t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w;
   }
   __syncthreads();
-  // 32 channels x 16 taps = 512 consecutive floats of dw
-  for (int i = threadIdx.x; i < 512; i += 256) {
-    const int cil = i >> 4, tap = i & 15;
-    if (c0 + cil < Ci) dw[((int64_t)co * Ci + c0 + cil) * 16 + tap] += t[tap][cil];
+#pragma unroll 4
+  for (int i0 = threadIdx.x * 4; i0 < n; i0 += 1024) {
+    const int ci = i0 >> 4, tap0 = i0 & 15;                                // four consecutive taps of one (co, ci)
+    float4 d = *reinterpret_cast<const float4*>(dst + i0);
+    const float* t = fin_t + tap0 * P + ci;
+    d.x += t[0]; d.y += t[P]; d.z += t[2 * P]; d.w += t[3 * P];
+    *reinterpret_cast<float4*>(dst + i0) = d;
   }
 }
 
@@ -1585,8 +1594,13 @@ int tc_conv_wgrad(const b200gan_conv* cv, const b200gan_view* x, const b200gan_v
   else rc = launch_wgrad<128, 64, 4, 4>(mx, mdy, p, grid, st);
   if (rc) return rc;
   if (workspace) {
-    dim3 fg((unsigned)((Ci + 31) / 32), (unsigned)Co);
-    wgrad_finalize_kernel<<<fg, 256, 0, st>>>(workspace, dw, Co, Ci);
+    const int fsmem = 16 * (Ci + 1) * (int)sizeof(float);
+    static int fin_configured = 0;
+    if (fsmem > 48 * 1024 && fin_configured < fsmem) {
+      B200_CUDA(cudaFuncSetAttribute(wgrad_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fsmem));
+      fin_configured = fsmem;
+    }
+    wgrad_finalize_kernel<<<(unsigned)Co, 256, fsmem, st>>>(workspace, dw, Co, Ci);
     B200_LAUNCH_CHECK("wgrad_finalize_kernel");
   }
   return 0;

@@ -1,2 +1,2 @@
-timeout 300 python -m pytest tests/test_gpu_fuse.py tests/test_gpu_thin.py -x -q 2>&1 | tail -3
-timeout 200 python tools/step_profile.py > gpurun_out/step_profile_l.txt 2>&1; grep -E "total|thin_down" gpurun_out/step_profile_l.txt
+for i in 1 2 3; do timeout 300 python bench.py --steps 30 --warmup 5 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['value'], d['e2e']['value'], d['clocks'])"; done
+nvidia-smi --query-gpu=name,power.limit,temperature.gpu --format=csv
