@@ -518,7 +518,7 @@ int ew_bn_act_fwd(const b200gan_view* y, const float* scale, const float* shift,
       const int64_t nvec = total / V;
       const int Cv = (y->c % V == 0) ? y->c : V;
       int64_t nbk = (nvec + 256 * 4 - 1) / (256 * 4);
-      if (nbk > 16 * kNumSMs) nbk = 16 * kNumSMs;
+      if (nbk > 4 * kNumSMs) nbk = 4 * kNumSMs;       // one resident wave (64 registers: 4 CTAs per SM), grid-stride inside
       if (nbk < 1) nbk = 1;
       if (y->dtype == B200GAN_F32)
         bn_act_fwd_dense_kernel<float><<<(unsigned)nbk, 256, 0, st>>>((const float*)y->ptr, (float*)a->ptr, nvec, Cv, scale, shift, act, slope);
@@ -598,7 +598,10 @@ int ew_bn_act_bwd_apply(const b200gan_view* da, const b200gan_view* y, const b20
       d.scale = scale; d.shift = shift; d.mean = mean; d.invstd = invstd; d.gamma = gamma; d.sums = sums; d.count = (double)count;
       d.act = act; d.slope = slope; d.dgamma = dgamma; d.dbeta = dbeta;
       int64_t nbk = (d.nvec + 256 * 4 - 1) / (256 * 4);
-      if (nbk > 16 * kNumSMs) nbk = 16 * kNumSMs;
+      // one resident wave (3 CTAs per SM at 80 registers): every thread derives its channel coefficients (fp64 divisions of the
+      // sums, five loads per channel) once; with 16 CTAs per SM queued that prologue was a third of the kernel's load traffic
+      const int64_t cap = 3 * kNumSMs;
+      if (nbk > cap) nbk = cap;
       if (nbk < 1) nbk = 1;
       const bool has_act = act != B200GAN_ACT_NONE;
       if (y->dtype == B200GAN_F32) {

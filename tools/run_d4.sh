@@ -1,2 +1,2 @@
-for i in 1 2 3; do timeout 300 python bench.py --steps 30 --warmup 5 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['value'], d['e2e']['value'], d['clocks'])"; done
-nvidia-smi --query-gpu=name,power.limit,temperature.gpu --format=csv
+timeout 600 python -m pytest tests/test_gpu_ops.py tests/test_gpu_step.py -x -q 2>&1 | tail -3
+timeout 200 python tools/step_profile.py > gpurun_out/step_profile_n.txt 2>&1; grep -E "total|bn_act" gpurun_out/step_profile_n.txt
