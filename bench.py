@@ -134,8 +134,8 @@ def _time_launch(torch, launch, flush, iters):
 
 
 def time_dominant_kernel(pkg, torch, batch, peaks, iters=20):
-    """roofline: the kernel class with the largest share of the step is conv_gemm_tc_kernel<128,64,3,*> (fprop / dgrad of
-    D2-D4 and G1-G3, 18 % of the iteration in profiles/); its representative launch, the D3 forward convolution
+    """roofline: the kernel class with the largest share of the step is conv_gemm_tc_kernel (fprop / dgrad of D2-D4 and G1-G3,
+    25 % of the iteration in profiles/r01_f_step_profile.txt); its representative launch, the D3 forward convolution
     (Conv2d 128->256, k4 s2 p1, 28x28 -> 14x14, BatchNorm statistics fused in the epilogue exactly as the step runs it), is
     timed alone.  `more` adds the other kernel families of the step, each against the roofline that bounds it."""
     import ctypes as C
@@ -183,12 +183,23 @@ def time_dominant_kernel(pkg, torch, batch, peaks, iters=20):
     byt = (a4.numel() + img.numel()) * 2.0
     more.append({'kernel': 'thin_up_tma_kernel<1> (G5 forward + Tanh)', 'bound': 'hbm', 'achieved': byt / (m4 * 1e-3) / 1e9, 'peak': peaks['hbm'],
                  'unit': 'GB/s', 'ms_per_launch': m4})
+    # the thin "down" layer D1 (32 -> 64 channels) forward with BatchNorm statistics: halo-tile tcgen05 kernel, HBM bound
+    # (read the 32-channel input once, write the 64-channel output once)
+    x1, w1 = rnd((n, 112, 112, 32)), torch.randn((64, 32, 4, 4), device='cuda') * 0.02
+    y1, wp1, s1 = torch.empty((n, 56, 56, 64), device='cuda', dtype=bf), torch.empty(64 * 32 * 16, device='cuda', dtype=bf), torch.zeros(128, device='cuda', dtype=torch.float64)
+    L.call('b200gan_pack_conv_weight', L.ptr(w1), 64, 32, 4, 0, L.ptr(wp1), st())
+    f1 = L.fuse(bn_sums=s1)
+    m5 = _time_launch(torch, lambda: L.call('b200gan_conv2d_fprop', C.byref(cv), C.byref(L.view_nhwc(x1)), L.ptr(w1), L.ptr(wp1),
+                                            C.byref(L.view_nhwc(y1)), C.byref(f1), st()), flush, iters)
+    byt = (x1.numel() + y1.numel()) * 2.0
+    more.append({'kernel': 'conv_down4_tc_kernel<1> (D1 forward + BatchNorm statistics)', 'bound': 'hbm', 'achieved': byt / (m5 * 1e-3) / 1e9,
+                 'peak': peaks['hbm'], 'unit': 'GB/s', 'ms_per_launch': m5})
     for r in more:
         r['frac'] = r['achieved'] / r['peak']
-    return {'bound': 'tensor', 'kernel': 'conv_gemm_tc_kernel<128,64,3,1>: conv2d_fprop D3 + BatchNorm statistics (M=B*196, K=2048, N=256), bf16 tcgen05, '
+    return {'bound': 'tensor', 'kernel': 'conv_gemm_tc_kernel<256,64,4,1>: conv2d_fprop D3 + BatchNorm statistics (M=B*196, K=2048, N=256), bf16 tcgen05, '
                                          'timed alone with CUDA events on the launching stream, L2 flushed',
             'achieved': ach, 'peak': peaks['tf_burst'], 'unit': 'TFLOP/s', 'frac': ach / peaks['tf_burst'],
-            'traffic': 124.8e6, 'traffic_source': 'dram__bytes_read.sum + dram__bytes_write.sum of this launch in profiles/r01_c_hot_kernels.md (ncu --set full); '
+            'traffic': 127.2e6, 'traffic_source': 'dram__bytes_read.sum + dram__bytes_write.sum of this launch in profiles/r01_g_hot_kernels.md (ncu --set full); '
                                                   'algorithmic bytes 154.1e6 (input 102.8e6 + output 51.4e6; part of the output is still in L2 when the kernel ends)',
             'ms_per_launch': ms, 'peak_source': peaks['src'] + ' (burst: kernel timed alone)', 'more': more}
 

@@ -44,6 +44,12 @@ if 'thin' in which:
     out32 = torch.empty_like(c32); outimg = torch.empty_like(img); dw0 = torch.zeros_like(w0)
 if 'd1' in which: d1 = mid(32, 112, 64)
 if 'd3' in which: d3 = mid(128, 28, 256)
+if 'lat' in which:
+    zl = torch.randn((B, 100, 1, 1), device='cuda'); wl = torch.randn((100, 512, 7, 7), device='cuda') * 0.02
+    yl = torch.empty((B, 7, 7, 512), device='cuda', dtype=bf); dyl = rnd((B, 7, 7, 512)); dwl = torch.zeros_like(wl)
+    cvl = L.Conv(7, 1, 0, L.ALGO_AUTO)
+if 'mask' in which:
+    dm = mid(32, 112, 64); a0m = rnd((B, 112, 112, 32))
 if 'ew' in which:
     yb = rnd((B, 56, 56, 64)); dab = rnd((B, 56, 56, 64)); ab = torch.empty_like(yb)
     sc, sh, mu, isd, gam = (torch.rand(64, device='cuda') + 0.5 for _ in range(5)); sums = torch.zeros(128, device='cuda', dtype=torch.float64)
@@ -57,6 +63,16 @@ for _ in range(reps):
         L.call('b200gan_conv2d_wgrad', C.byref(auto), C.byref(L.view_nchw(img32)), V(c32), L.ptr(dw0), None, C.byref(fz), st())
     if 'd1' in which: run_mid(d1)
     if 'd3' in which: run_mid(d3)
+    if 'lat' in which:
+        L.call('b200gan_convT2d_fprop', C.byref(cvl), C.byref(L.view_nchw(zl)), L.ptr(wl), None, V(yl), None, st())
+        L.call('b200gan_convT2d_wgrad', C.byref(cvl), C.byref(L.view_nchw(zl)), V(dyl), L.ptr(dwl), None, None, st())
+    if 'mask' in which:
+        fm = L.fuse(prev_act=L.ACT_LRELU, prev_slope=SL, prev_y=L.view_nhwc(a0m))
+        L.call('b200gan_conv2d_dgrad', C.byref(auto), V(dm['dy']), L.ptr(dm['w']), L.ptr(dm['wu']), V(dm['dx']), C.byref(fm), st())
+        yv2 = L.view_nhwc(dm['y'])
+        f2 = L.fuse(prev_act=L.ACT_RELU, prev_y=yv2, prev_scale=dm['coef_x'][0].repeat(2), prev_shift=dm['coef_x'][1].repeat(2), prev_mean=dm['coef_x'][2].repeat(2),
+                    prev_invstd=dm['coef_x'][3].repeat(2), prev_sums=dm['sums_y'])
+        L.call('b200gan_convT2d_dgrad', C.byref(auto), V(dm['x']), L.ptr(dm['w']), L.ptr(dm['wd']), V(dm['y'].clone()), C.byref(f2), st())
     if 'ew' in which:
         L.call('b200gan_bn_act_fwd', V(yb), L.ptr(sc), L.ptr(sh), L.ACT_LRELU, SL, V(ab), st())
         L.call('b200gan_bn_act_bwd_apply', V(dab), V(yb), None, L.ptr(sc), L.ptr(sh), L.ptr(mu), L.ptr(isd), L.ptr(gam), L.ptr(sums), B * 56 * 56, L.ACT_NONE, SL, V(dab), None, None, st())
