@@ -4,6 +4,7 @@
 // binary_cross_entropy and optim.Adam as called from dcgan.py:27-47,66-85 and train_gan.py:90-95,128-150.
 #include <math.h>
 
+#include <cstdlib>
 #include "common.cuh"
 
 namespace b200gan {
@@ -79,28 +80,27 @@ static bool dense_nhwc(const b200gan_view* v) {
          (reinterpret_cast<uintptr_t>(v->ptr) & 15) == 0;
 }
 
-template <typename T>
+template <typename T, int U = 4>
 __global__ void __launch_bounds__(256) bn_act_fwd_dense_kernel(const T* __restrict__ y, T* __restrict__ a, int64_t nvec, int C,
                                                                const float* __restrict__ scale, const float* __restrict__ shift,
                                                                int act, float slope) {
   constexpr int V = Vec<T>::N;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool hoist = (stride * V) % C == 0;
+  // chunks of 256*U consecutive vectors per CTA and iteration (see bn_act_bwd_apply_dense_kernel)
+  const bool hoist = (256 * V) % C == 0;
   float sc[V], sh[V];
-  int c0 = (int)((i * V) % C);
+  int c0 = (int)(((int64_t)threadIdx.x * V) % C);
 #pragma unroll
   for (int j = 0; j < V; ++j) { sc[j] = scale ? scale[c0 + j] : 1.f; sh[j] = scale ? shift[c0 + j] : 0.f; }
-  constexpr int U = 4;                   // four vectors in flight per thread (raw loads first): HBM streaming needs the depth
   using Raw = typename Vec<T>::Raw;
-  for (; i < nvec; i += U * stride) {
+  constexpr int64_t CH = 256 * U;
+  for (int64_t base = (int64_t)blockIdx.x * CH + threadIdx.x; base < nvec; base += (int64_t)gridDim.x * CH) {
     Raw r[U];
 #pragma unroll
     for (int u = 0; u < U; ++u)
-      if (i + u * stride < nvec) r[u] = Vec<T>::load_raw(y + (i + u * stride) * V);
+      if (base + u * 256 < nvec) r[u] = Vec<T>::load_raw(y + (base + u * 256) * V);
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int64_t k = i + u * stride;
+      const int64_t k = base + u * 256;
       if (k >= nvec) break;
       if (!hoist && scale) {
         c0 = (int)((k * V) % C);
@@ -142,9 +142,9 @@ __global__ void __launch_bounds__(256, 3) bn_act_bwd_apply_dense_kernel(BwdDense
       if (g.dgamma) g.dgamma[c] += (float)g.sums[C + c];
     }
   }
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool hoist = (stride * V) % C == 0;
+  // a CTA walks chunks of 256*U consecutive vectors (grid-stride over chunks): a warp's U loads of one tensor cover U consecutive
+  // 512-byte segments, and a thread keeps the same V channels as long as 256*V is a multiple of C
+  const bool hoist = (256 * V) % C == 0;
   float sc[V], sh[V], k1[V], pp[V], qq[V];
   auto coeffs = [&](int c0) {
 #pragma unroll
@@ -163,21 +163,21 @@ __global__ void __launch_bounds__(256, 3) bn_act_bwd_apply_dense_kernel(BwdDense
       }
     }
   };
-  coeffs((int)((i * V) % C));
+  coeffs((int)(((int64_t)threadIdx.x * V) % C));
   const T* da = reinterpret_cast<const T*>(g.da);
   const T* y = reinterpret_cast<const T*>(g.y);
   const T* a = reinterpret_cast<const T*>(g.a);
   T* dy = reinterpret_cast<T*>(g.dy);
-  // U vectors per thread and iteration, all loads issued before the first store and kept RAW (packed) until they are used:
-  // the pass is pure HBM streaming and needs ~40 KB in flight per SM (one vector pair at a time measured 49 % of the copy
-  // bandwidth)
-  constexpr int U = HAS_ACT ? 2 : 4;
+  // all loads of a chunk are issued before its first store and kept RAW (packed) until they are used.  Measured on D1's tensor
+  // (tools/ew_bench.py, one resident wave): U = 1 / 2 / 3 / 4 -> 126 / 110 / 114 / 123 us; U = 2 is 5.6 TB/s = 86 % of the copy peak
+  constexpr int U = 2;
   using Raw = typename Vec<T>::Raw;
-  for (; i < g.nvec; i += U * stride) {
+  constexpr int64_t CH = 256 * U;
+  for (int64_t base = (int64_t)blockIdx.x * CH + threadIdx.x; base < g.nvec; base += (int64_t)gridDim.x * CH) {
     Raw rd[U], ry[U], ra[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int64_t k = i + u * stride;
+      const int64_t k = base + u * 256;
       if (k < g.nvec) {
         rd[u] = Vec<T>::load_raw(da + k * V);
         ry[u] = Vec<T>::load_raw(y + k * V);
@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(256, 3) bn_act_bwd_apply_dense_kernel(BwdDense
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int64_t k = i + u * stride;
+      const int64_t k = base + u * 256;
       if (k >= g.nvec) break;
       if (!hoist) coeffs((int)((k * V) % C));
       float d[V], yv[V], av[V];

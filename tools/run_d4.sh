@@ -1,2 +1,2 @@
-timeout 300 python tools/ncu_target.py 512 1 d1,d3,lat,mask,ew > gpurun_out/ncu_target_plain.log 2>&1; echo plain rc=$?; tail -2 gpurun_out/ncu_target_plain.log
-timeout 1500 ncu --set full --clock-control none --import-source on -k regex:'conv_down4|conv_up4|latent|conv_gemm_tc|conv_wgrad_tc|bn_act|wgrad_finalize' -o gpurun_out/r01_g_hot python tools/ncu_target.py 512 1 d1,d3,lat,mask,ew > gpurun_out/ncu_g2.log 2>&1; echo ncu rc=$?; ls -la gpurun_out/r01_g_hot.ncu-rep
+timeout 600 python -m pytest tests/test_gpu_ops.py tests/test_gpu_fuse.py tests/test_gpu_step.py -x -q 2>&1 | tail -2
+timeout 200 python tools/step_profile.py > gpurun_out/step_profile_p.txt 2>&1; grep -E "total|bn_act" gpurun_out/step_profile_p.txt
