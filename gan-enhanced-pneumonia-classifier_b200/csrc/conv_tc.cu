@@ -1337,7 +1337,7 @@ struct TcWgradParams {
 template <int CIC, int NCO, int G, int STAGES>
 struct TcWgradSmem {
   static constexpr int BK = 64;                            // pixels per K-block
-  static constexpr int DY_SLOTS = 3;                       // safe while STAGES <= (DY_SLOTS - 1) * G
+  static constexpr int DY_SLOTS = (STAGES + G - 1) / G + 1 > 3 ? (STAGES + G - 1) / G + 1 : 3;   // safe while STAGES <= (DY_SLOTS - 1) * G
   static constexpr int A_BYTES = BK * 128 * 2;             // one group: 64 pixels x 128 (tap, ci) rows
   static constexpr int B_BYTES = BK * NCO * 2;
   static constexpr int TOTAL = STAGES * A_BYTES + DY_SLOTS * B_BYTES + 1024 + 256;
@@ -1540,7 +1540,9 @@ int tc_conv_wgrad(const b200gan_conv* cv, const b200gan_view* x, const b200gan_v
   const int Ci = x->c, Co = dy->c;
   if (Co % 64 != 0 || (Ci != 32 && Ci != 64 && Ci % 128 != 0)) return 1;
   const int CIC = Ci >= 128 ? 128 : Ci;
-  const int NCO = (CIC == 128 && Co % 256 == 0) ? 256 : ((CIC >= 64 && Co % 128 == 0) ? 128 : 64);
+  static const int force_nco = getenv("B200GAN_WGRAD_NCO") ? atoi(getenv("B200GAN_WGRAD_NCO")) : 0;      // measurement knob
+  const int NCO = (force_nco && CIC == 128 && Co % force_nco == 0) ? force_nco
+                                                                   : ((CIC == 128 && Co % 256 == 0) ? 256 : ((CIC >= 64 && Co % 128 == 0) ? 128 : 64));
   const int G = NCO == 256 ? 2 : 4, MT = 128 / CIC;
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return B200GAN_ERR_CUDA; }
@@ -1586,10 +1588,12 @@ int tc_conv_wgrad(const b200gan_conv* cv, const b200gan_view* x, const b200gan_v
   }
   dim3 grid((unsigned)units, 1, (unsigned)splits);
   int rc;
+  // deeper rings measured for the two thin configurations (<32,64,4,5>, <64,128,4,10>): no change, they are not latency bound
   if (CIC == 32) rc = launch_wgrad<32, 64, 4, 4>(mx, mdy, p, grid, st);                 // 4 x 16 KB + 3 x 8 KB: two CTAs per SM
   else if (CIC == 64 && NCO == 128) rc = launch_wgrad<64, 128, 4, 8>(mx, mdy, p, grid, st);
   else if (CIC == 64) rc = launch_wgrad<64, 64, 4, 4>(mx, mdy, p, grid, st);
-  else if (NCO == 256) rc = launch_wgrad<128, 256, 2, 4>(mx, mdy, p, grid, st);
+  // 6 x 16 KB of x stages + 4 x 32 KB of dy slots = 224 KB: three K-blocks in flight instead of two (D3 140 -> 127 us)
+  else if (NCO == 256) rc = launch_wgrad<128, 256, 2, 6>(mx, mdy, p, grid, st);
   else if (NCO == 128) rc = launch_wgrad<128, 128, 4, 8>(mx, mdy, p, grid, st);
   else rc = launch_wgrad<128, 64, 4, 4>(mx, mdy, p, grid, st);
   if (rc) return rc;

@@ -1,2 +1,2 @@
-timeout 600 python -m pytest tests/test_gpu_ops.py tests/test_gpu_fuse.py tests/test_gpu_step.py -x -q 2>&1 | tail -2
-timeout 200 python tools/step_profile.py > gpurun_out/step_profile_p.txt 2>&1; grep -E "total|bn_act" gpurun_out/step_profile_p.txt
+for d in 0 1; do echo DEEP=$d; B200GAN_WGRAD_DEEP=$d timeout 60 python tools/wgrad_bench.py; done
+B200GAN_WGRAD_DEEP=1 timeout 300 python -m pytest tests/test_gpu_tc.py -x -q -k wgrad 2>&1 | tail -2
