@@ -162,7 +162,7 @@ def time_dominant_kernel(pkg, torch, batch, peaks, iters=20):
     dy, dw, ws = rnd((n, h // 2, h // 2, co)), torch.zeros_like(w), torch.zeros_like(w)
     m2 = _time_launch(torch, lambda: L.call('b200gan_conv2d_wgrad', C.byref(cv), C.byref(L.view_nhwc(x)), C.byref(L.view_nhwc(dy)), L.ptr(dw),
                                             L.ptr(ws), None, st()), flush, iters)
-    more.append({'kernel': 'conv_wgrad_tc_kernel<128,256,2,4> + wgrad_finalize_kernel (D3 weight gradient)', 'bound': 'tensor',
+    more.append({'kernel': 'conv_wgrad_tc_kernel<128,256,2,6> + wgrad_finalize_kernel (D3 weight gradient)', 'bound': 'tensor',
                  'achieved': flops / (m2 * 1e-3) / 1e12, 'peak': peaks['tf_burst'], 'unit': 'TFLOP/s', 'ms_per_launch': m2})
     # BatchNorm backward apply on D1's tensor (HBM bound: read dz, read y, write dy)
     yb, dz = rnd((n, 56, 56, 64)), rnd((n, 56, 56, 64))
