@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define B200GAN_VERSION 200   /* major*10000 + minor*100 + patch */
+#define B200GAN_VERSION 300   /* major*10000 + minor*100 + patch */
 
 typedef enum b200gan_status {
   B200GAN_OK = 0,
