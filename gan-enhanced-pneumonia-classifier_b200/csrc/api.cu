@@ -41,7 +41,7 @@ int thin_wgrad(const b200gan_view* fine, const b200gan_view* fine_ref, int fine_
                int coarse_act, float slope, float* dw, cudaStream_t);
 // latent GEMM and 7x7 GEMV (conv_thin.cu): same return convention
 int window_fprop(const b200gan_conv*, const b200gan_view* x, const float* w, const b200gan_view* y, cudaStream_t);
-int window_dgrad(const b200gan_conv*, const b200gan_view* dy, const float* w, const b200gan_view* dx, cudaStream_t);
+int window_dgrad(const b200gan_conv*, const b200gan_view* dy, const float* w, const b200gan_view* dx, const TcEpi& epi, cudaStream_t);
 int window_wgrad(const b200gan_conv*, const b200gan_view* x, const b200gan_view* dy, float* dw, cudaStream_t);
 int latent_fprop(const b200gan_conv*, const b200gan_view* z, const float* w, const b200gan_view* y, cudaStream_t);
 int latent_wgrad(const b200gan_conv*, const b200gan_view* dy_fine, const b200gan_view* z, float* dw, cudaStream_t);
@@ -191,7 +191,13 @@ static int conv_dispatch(Prim prim, bool transposed, const b200gan_conv* cv, con
     if (t > 0 && plain) {
       if (prim == FPROP) t = window_fprop(cv, fine, w, coarse, st);
       else if (prim == DGRAD) {
-        t = window_dgrad(cv, coarse, w, fine, st);
+        TcEpi epi;                                   // the GEMV input gradient absorbs the BatchNorm-backward fusion of the layer below
+        if (prev_bn) {
+          epi.mode = 2; epi.sums = fuse->prev_sums; epi.prev_y = fuse->prev_y; epi.scale = fuse->prev_scale; epi.shift = fuse->prev_shift;
+          epi.mean = fuse->prev_mean; epi.invstd = fuse->prev_invstd; epi.act = fuse->prev_act; epi.slope = fuse->prev_slope;
+        }
+        t = (prev && !prev_bn) ? 1 : window_dgrad(cv, coarse, w, fine, epi, st);
+        if (t == 0) prev = false;
         if (t > 0) t = latent_fprop_mma(cv, coarse, w, fine, st);
         if (t > 0) t = latent_fprop(cv, coarse, w, fine, st);
       } else {

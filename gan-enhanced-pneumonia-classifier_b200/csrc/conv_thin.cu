@@ -71,6 +71,59 @@ __global__ void __launch_bounds__(256) window_dot_bwd_kernel(const __nv_bfloat16
   }
 }
 
+// dx[n][j] = dl[n] * w[j] followed by the activation backward and the BatchNorm-backward sums of the layer below (b200gan_fuse.prev_*
+// with BatchNorm): dz = dx * act'(scale*y + shift) stored, sums[c] += dz, sums[C+c] += dz * (y - mean) * invstd, from the stored
+// (bf16-rounded) dz.  A thread owns 8 channels of one position for 16 samples; four saved-output loads in flight.
+__global__ void __launch_bounds__(256) window_dgrad_bn_kernel(const float* __restrict__ w, const float* __restrict__ dl,
+                                                              const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ dx,
+                                                              const float* __restrict__ scale, const float* __restrict__ shift,
+                                                              const float* __restrict__ mean, const float* __restrict__ invstd, float neg,
+                                                              double* __restrict__ sums, int N, int J, int C, int HW, int n_per_block) {
+  extern __shared__ float wred[];                          // [2][C]
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) wred[i] = 0.f;
+  __syncthreads();
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v < J / 8) {
+    const int j = v * 8, hw = j / C, c = j - hw * C;
+    float wv[8], sc[8], sh[8], mu[8], s0[8], s1[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      wv[e] = __ldg(w + (int64_t)(c + e) * HW + hw);
+      sc[e] = scale[c + e]; sh[e] = shift[c + e]; mu[e] = mean[c + e];
+      s0[e] = 0.f; s1[e] = 0.f;
+    }
+    const int n0 = blockIdx.y * n_per_block, n1 = min(n0 + n_per_block, N);
+    for (int nb = n0; nb < n1; nb += 4) {
+      uint4 ry[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (nb + u < n1) ry[u] = __ldg(reinterpret_cast<const uint4*>(y + (int64_t)(nb + u) * J) + v);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int n = nb + u;
+        if (n >= n1) break;
+        const float d = __ldg(dl + n);
+        float yv[8], o[8];
+        unpack8(ry[u], yv);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = d * wv[e] * (fmaf(yv[e], sc[e], sh[e]) > 0.f ? 1.f : neg);
+        const uint4 packed = pack8(o);
+        reinterpret_cast<uint4*>(dx + (int64_t)n * J)[v] = packed;
+        unpack8(packed, o);                                // the sums are those of the stored values
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { s0[e] += o[e]; s1[e] = fmaf(o[e], yv[e] - mu[e], s1[e]); }
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { atomicAdd(&wred[c + e], s0[e]); atomicAdd(&wred[C + c + e], s1[e]); }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+    const float t = wred[i];
+    if (t != 0.f) atomicAdd(sums + i, (double)t * (i >= C ? (double)invstd[i - C] : 1.0));
+  }
+}
+
 static bool window_shape(const b200gan_conv* cv, const b200gan_view* fine, const b200gan_view* coarse) {
   return cv->stride == 1 && cv->pad == 0 && fine->h == cv->k && fine->w == cv->k && coarse->h == 1 && coarse->w == 1 &&
          coarse->c == 1 && dense_bf16_c(fine, fine->c) && fine->c % 8 == 0 && coarse->dtype == B200GAN_F32 && coarse->sn == 1;
@@ -94,9 +147,20 @@ static int window_bwd(const b200gan_conv* cv, const b200gan_view* x, const float
   B200_LAUNCH_CHECK("window_dot_bwd_kernel");
   return 0;
 }
-int window_dgrad(const b200gan_conv* cv, const b200gan_view* dy, const float* w, const b200gan_view* dx, cudaStream_t st) {
+// epi: mode 0 (none) or 2 (activation backward + BatchNorm-backward sums of the layer below); other modes return 1
+int window_dgrad(const b200gan_conv* cv, const b200gan_view* dy, const float* w, const b200gan_view* dx, const TcEpi& epi, cudaStream_t st) {
   if (!window_shape(cv, dx, dy)) return 1;
-  return window_bwd(cv, dx, w, dy, reinterpret_cast<__nv_bfloat16*>(dx->ptr), nullptr, st);
+  if (epi.mode == 0) return window_bwd(cv, dx, w, dy, reinterpret_cast<__nv_bfloat16*>(dx->ptr), nullptr, st);
+  if (epi.mode != 2 || !dense_bf16_c(epi.prev_y, dx->c) || epi.prev_y->n != dx->n || epi.prev_y->h != dx->h || epi.prev_y->w != dx->w || dx->c > 2048) return 1;
+  const int J = dx->h * dx->w * dx->c, npb = 16;
+  B200_CUDA(cudaMemsetAsync(epi.sums, 0, sizeof(double) * 2 * dx->c, st));
+  dim3 grid((J / 8 + 255) / 256, (dx->n + npb - 1) / npb);
+  const float neg = epi.act == B200GAN_ACT_RELU ? 0.f : (epi.act == B200GAN_ACT_LRELU ? epi.slope : 1.f);
+  window_dgrad_bn_kernel<<<grid, 256, 2 * dx->c * sizeof(float), st>>>(w, reinterpret_cast<const float*>(dy->ptr),
+      reinterpret_cast<const __nv_bfloat16*>(epi.prev_y->ptr), reinterpret_cast<__nv_bfloat16*>(dx->ptr), epi.scale, epi.shift, epi.mean, epi.invstd,
+      neg, epi.sums, dx->n, J, dx->c, dx->h * dx->w, npb);
+  B200_LAUNCH_CHECK("window_dgrad_bn_kernel");
+  return 0;
 }
 int window_wgrad(const b200gan_conv* cv, const b200gan_view* x, const b200gan_view* dy, float* dw, cudaStream_t st) {
   if (!window_shape(cv, x, dy)) return 1;

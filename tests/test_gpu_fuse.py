@@ -311,3 +311,37 @@ def test_image_side_down_kernel_batchnorm_epilogues(nc):
     close(y, orc.conv2d_fprop(dfake, bf16_round(w), 2, 1), rtol=2e-2, atol=2e-2, what='thin down + bn_sums: result')
     close(sums.cpu().numpy()[:32], y.sum(axis=(0, 2, 3)), rtol=1e-4, atol=1e-2, what='bn_sums: sum')
     close(sums.cpu().numpy()[32:], (y ** 2).sum(axis=(0, 2, 3)), rtol=1e-4, atol=1e-2, what='bn_sums: sum of squares')
+
+
+@pytest.mark.parametrize('n,c', [(37, 64), (512, 512), (5, 8)])
+def test_full_window_dgrad_batchnorm_epilogue(n, c):
+    """D5 = Conv2d(C->1, k7) on a 7x7 map (dcgan.py:84): its input gradient (an outer product) carries the LeakyReLU backward and the
+    BatchNorm-backward sums of D4 in the same kernel.  Checked against the unfused chain in float64 from the same bf16 inputs."""
+    k = 7
+    cv = L.Conv(k, 1, 0, L.ALGO_AUTO)
+    w = rnd((1, c, k, k), 1, 0.05)
+    dl = rnd((n, 1, 1, 1), 2)
+    y_prev = bf16_round(rnd((n, c, k, k), 3))
+    scale, shift = rnd((c,), 8, 0.5) + 1.0, rnd((c,), 9, 0.3)
+    mean, invstd = rnd((c,), 10, 0.2), np.abs(rnd((c,), 11)) + 0.5
+    wd, dld = torch.from_numpy(w).cuda(), torch.from_numpy(dl).cuda()
+    yp_t, yp_v = dev_nhwc(y_prev, torch.bfloat16)
+    dvec = [torch.from_numpy(v).cuda() for v in (scale, shift, mean, invstd)]
+    dz_t = torch.empty((n, k, k, c), device='cuda', dtype=torch.bfloat16)
+    psums = torch.full((2 * c,), -7.0, device='cuda', dtype=torch.float64)          # must be OVERWRITTEN
+    f = L.fuse(prev_act=L.ACT_LRELU, prev_slope=SLOPE, prev_y=yp_v, prev_scale=dvec[0], prev_shift=dvec[1], prev_mean=dvec[2], prev_invstd=dvec[3],
+               prev_sums=psums)
+    L.call('b200gan_conv2d_dgrad', C.byref(cv), C.byref(L.view_nchw(dld)), L.ptr(wd), None, C.byref(L.view_nhwc(dz_t)), C.byref(f), st())
+    dx = dl.astype(np.float64) * w.astype(np.float64)                                 # (n,1,1,1) * (1,c,7,7)
+    z = y_prev * scale[None, :, None, None] + shift[None, :, None, None]
+    dz_ref = dx * np.where(z > 0, 1.0, SLOPE)
+    dz = back_nchw(dz_t, True)
+    safe = np.abs(z) > 1e-3
+    close(np.where(safe, dz, 0), np.where(safe, dz_ref, 0), rtol=1e-2, atol=1e-6, what='k7 dgrad with prev_*: dz')
+    # the sums are those of the STORED (bf16) dz
+    xhat = (y_prev.astype(np.float64) - mean[None, :, None, None]) * invstd[None, :, None, None]
+    s = psums.cpu().numpy()
+    s0, s1 = dz.astype(np.float64).sum(axis=(0, 2, 3)), (dz.astype(np.float64) * xhat).sum(axis=(0, 2, 3))
+    assert np.all(np.abs(s[:c] - s0) <= 1e-4 * np.abs(dz).sum(axis=(0, 2, 3)) + 1e-6), 'prev_sums: sum dz'
+    assert np.all(np.abs(s[c:] - s1) <= 1e-4 * np.abs(dz * xhat).sum(axis=(0, 2, 3)) + 1e-6), 'prev_sums: sum dz*xhat'
+
