@@ -153,13 +153,17 @@ def test_image_side_full_size_row_tiles():
 # BatchNorm fusions of the middle layers: statistics in the forward epilogue, activation backward + BN-backward sums in the
 # input-gradient epilogue.  mode fp32 -> SIMT kernels, bf16 -> tcgen05 kernels (channels % 32 == 0).
 # ---------------------------------------------------------------------------------------------------
+# geometry (n, ci, co, hf, wf): fine (n,ci,hf,wf), coarse (n,co,hf/2,wf/2).  The second case is the thin 32<->64-channel layer at a size
+# the halo-tile tcgen05 kernels take (conv_down4_tc_kernel<1>, <2>, conv_up4_tc_kernel<1>), with ragged tiles in both directions
+# (24 = 16 + 8 output rows, 20 = 8 + 8 + 4 output columns)
+@pytest.mark.parametrize('geom', [(4, 32, 64, 16, 16), (3, 32, 64, 48, 40)])
 @pytest.mark.parametrize('mode', ['fp32', 'bf16'])
 @pytest.mark.parametrize('transposed', [False, True])
-def test_batchnorm_epilogue_fusions(mode, transposed):
+def test_batchnorm_epilogue_fusions(mode, transposed, geom):
     dt = torch.float32 if mode == 'fp32' else torch.bfloat16
     rt = (lambda a: a) if mode == 'fp32' else bf16_round
     tol = dict(rtol=1e-4, atol=1e-5) if mode == 'fp32' else dict(rtol=2e-2, atol=2e-2)
-    n, ci, co, hf, wf = 4, 32, 64, 16, 16           # conv geometry: fine (n,ci,16,16), coarse (n,co,8,8)
+    n, ci, co, hf, wf = geom
     cv = conv()
     w = rnd((co, ci, 4, 4), 1, 0.05)
     wd = torch.from_numpy(w).cuda()
