@@ -211,6 +211,7 @@ __global__ void __launch_bounds__(256) thin_down_mma_kernel(const ThinArgs a) {
   __nv_bfloat16* S = reinterpret_cast<__nv_bfloat16*>(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int rows = 2 * a.R + 2, pitch = 2 * a.W + 2;
+  uint8_t* Sy = smem_raw + ((NC * rows * pitch * 2 + 127) & ~127);      // EPI 2: the saved-output tile behind the image band
   uint32_t bw[NC][4][2];
 #pragma unroll
   for (int ci = 0; ci < NC; ++ci)
@@ -233,27 +234,31 @@ __global__ void __launch_bounds__(256) thin_down_mma_kernel(const ThinArgs a) {
   }
   for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
     const int n = tile / a.tiles_per_img, oh0 = (tile - n * a.tiles_per_img) * a.R;
-    // EPI 2: the saved forward output of this warp's NEXT m-tile is fetched one iteration ahead (the first one under the
-    // staging of the image band): loaded where it is used, its latency was exposed once per m-tile and tripled the kernel time
-    uint4 yq[2] = {make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u)};
-    auto fetch_y = [&](int mt) {
-      const int rr = mt / WB, c = mt - rr * WB;
-      if (mt < mtiles && oh0 + rr < a.H) {
-        const int64_t off = (((int64_t)n * a.H + oh0 + rr) * a.W + 16 * c + g) * 32 + 8 * t;
-        yq[0] = __ldg(reinterpret_cast<const uint4*>(a.prev_y + off));
-        yq[1] = __ldg(reinterpret_cast<const uint4*>(a.prev_y + off + 8 * 32));
-      }
-    };
-    if (EPI == 2) fetch_y(warp);
     __syncthreads();                       // previous tile fully consumed
+    if (EPI == 2) {
+      // the saved forward output under this tile (R rows x W pixels x 64 bytes) goes to shared memory by 16-byte cp.async, all of it
+      // in flight while the image band is staged: fetched from registers one m-tile ahead, each warp had 1 KB in flight and
+      // the stream ran at 1.6 TB/s
+      const int total = a.R * a.W * 4;
+      const __nv_bfloat16* src = a.prev_y + ((int64_t)n * a.H + oh0) * a.W * 32;
+      for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+        const int pl = idx >> 2, chunk = idx & 3;
+        cp_async_16_zfill(Sy + sw64(pl, chunk), src + (int64_t)pl * 32 + chunk * 8, oh0 + pl / a.W < a.H);
+      }
+    }
     stage_fine<NC>(S, pitch, rows, a, n, 2 * oh0 - 1);
+    if (EPI == 2) cp_async_wait_all();
     __syncthreads();
     for (int mt = warp; mt < mtiles; mt += 8) {
       const int rr = mt / WB, c = mt - rr * WB;
       const int oh = oh0 + rr;
       if (oh >= a.H) break;
-      const uint4 yc0 = yq[0], yc1 = yq[1];
-      if (EPI == 2) fetch_y(mt + 8);
+      uint4 yc0 = make_uint4(0u, 0u, 0u, 0u), yc1 = yc0;
+      if (EPI == 2) {
+        const int pl0 = rr * a.W + 16 * c + g;
+        yc0 = *reinterpret_cast<const uint4*>(Sy + sw64(pl0, t));
+        yc1 = *reinterpret_cast<const uint4*>(Sy + sw64(pl0 + 8, t));
+      }
       float acc[4][4];
 #pragma unroll
       for (int j = 0; j < 4; ++j)
@@ -874,7 +879,8 @@ int thin_down(const b200gan_view* fine, const b200gan_view* fine_ref, int fine_a
       a.prev_neg = epi.act == B200GAN_ACT_RELU ? 0.f : (epi.act == B200GAN_ACT_LRELU ? epi.slope : 1.f);
     }
   }
-  const size_t smem = (size_t)fine->c * (2 * a.R + 2) * (2 * a.W + 2) * 2;
+  size_t smem = (size_t)fine->c * (2 * a.R + 2) * (2 * a.W + 2) * 2;
+  if (epi.mode == 2) smem = ((smem + 127) & ~(size_t)127) + (size_t)a.R * a.W * 64;
   const char* nm = "thin_down_mma_kernel";
   if (fine->c == 1) {
     if (epi.mode == 0) return launch_thin<thin_down_mma_kernel<1, 0>>(a, smem, 6, st, nm);
