@@ -5,6 +5,7 @@ import json
 import os
 
 import numpy as np
+import pytest
 import torch
 
 from gan_enhanced_pneumonia_classifier_b200 import generate_synthetic as gs
@@ -53,3 +54,17 @@ def test_cpu_round_trip_writes_reference_artefacts(tmp_path):
     from PIL import Image
     img = np.asarray(Image.open(d + '/synthetic/synthetic_00001.png'))
     assert img.shape == (224, 224, 3) and img.dtype == np.uint8
+
+
+def test_device_cache_has_no_host_path(tmp_path, capsys):
+    """The device-resident image cache is CUDA only: a host tensor is rejected loudly, and `--cache-dataset --cpu` refuses to run
+    instead of quietly falling back to a host loader."""
+    from gan_enhanced_pneumonia_classifier_b200.data_cache import DeviceImageCache
+    with pytest.raises(RuntimeError, match='GPU memory'):
+        DeviceImageCache(torch.zeros((2, 3, 8, 8), dtype=torch.uint8))
+    d = str(tmp_path)
+    argv = ['--cpu', '--cache-dataset', '--synthetic', '4', '--batch-size', '2', '--epochs', '1', '--model-dir', d + '/models', '--output-dir', d + '/results',
+            '--results-dir', d + '/results/metrics', '--figures-dir', d + '/results/figures']
+    assert tg.main(tg.build_parser().parse_args(argv)) is None
+    assert '--cache-dataset keeps the training images in GPU memory' in capsys.readouterr().out
+    assert not os.path.exists(d + '/models/gan/generator_final.pth')
