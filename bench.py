@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the DCGAN adversarial training step (G+D iteration of train_gan.py:121-150) on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B] [--dtype bf16|fp32]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B] [--dtype bf16|fp32] [--nc 1|3]
 
 N>1 is launched by the driver as `python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...`
 (one rank per GPU, NCCL).  Rank 0 prints ONE JSON line.
@@ -33,7 +33,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = 'dcgan_train_images_per_sec'
 UNIT = 'images/s'
-FLOP_PER_IMAGE = 9.169e9          # algorithmic conv FLOPs per image per iteration, nc=1 (dead wgrad excluded)
+FLOP_PER_IMAGE = {1: 9.169e9, 3: 9.400e9}     # algorithmic conv FLOPs per image per iteration by nc (dead wgrad excluded)
 
 
 def load_peaks():
@@ -101,12 +101,12 @@ def run_reference(args):
     import torch
     import torch_cpu_port as port
     sample_batch = 64
-    r = port.time_cpu_steps(batch=sample_batch, steps=args.steps, warmup=args.warmup, nc=1)
+    r = port.time_cpu_steps(batch=sample_batch, steps=args.steps, warmup=args.warmup, nc=args.nc)
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': r['images_per_s'], 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': r['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'DCGAN train step nz=100 ngf=ndf=64 nc=1 224x224 (reference is hard-wired to 224x224, not 64x64)',
+        'config': {'workload': f'DCGAN train step nz=100 ngf=ndf=64 nc={args.nc} 224x224 (reference is hard-wired to 224x224, not 64x64)',
                    'per_gpu_batch': args.batch, 'sample': f'each step = one G+D iteration on a {sample_batch}-image sample of the batch'},
         'cpu_baseline': {'value': r['images_per_s'], 'unit': UNIT, 'cores': r['threads'], 'kind': 'port',
                          'sample': f'{args.steps} iterations x batch {sample_batch} (oracle/torch_cpu_port.py: stock torch.nn CPU path of dcgan.py/train_gan.py)'},
@@ -220,7 +220,7 @@ def run_ours(args):
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     peaks = load_peaks()
     dtype = torch.bfloat16 if args.dtype == 'bf16' else torch.float32
-    B, nz, nc = args.batch, 100, 1
+    B, nz, nc = args.batch, 100, args.nc
     torch.manual_seed(0)
     G, D = pkg.Generator(nz, nc, 64).cuda(), pkg.Discriminator(nc, 64).cuda()
     G.apply(pkg.weights_init)
@@ -330,11 +330,11 @@ def run_ours(args):
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': args.dtype, 'data': 'synthetic',
-            'config': {'workload': 'DCGAN train step nz=100 ngf=ndf=64 nc=1 224x224 (reference is hard-wired to 224x224, not 64x64)',
+            'config': {'workload': f'DCGAN train step nz=100 ngf=ndf=64 nc={nc} 224x224 (reference is hard-wired to 224x224, not 64x64)',
                        'per_gpu_batch': B, 'global_batch': B * world, 'parallelism': f'dp{world}', 'batchnorm': 'local (per-rank) statistics',
                        'l2': 'per-step working set (several GB of activations) far exceeds the 126 MB L2; no flush needed',
                        'algo': os.environ.get('B200GAN_ALGO', 'auto')},
-            'model_flops_frac_of_peak': value / world * FLOP_PER_IMAGE / 1e12 / peaks['tf_sustained'],
+            'model_flops_frac_of_peak': value / world * FLOP_PER_IMAGE[nc] / 1e12 / peaks['tf_sustained'],
             'roofline': roof, 'cpu_baseline': cpu,
             'e2e': {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': real_h.numel() * 4 + noise_h[0].numel() * 4, 'd2h_bytes_per_step': 20,
                     'ms_per_step': ms_e2e / args.steps},
@@ -353,6 +353,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=512, help='per-GPU batch')
     ap.add_argument('--dtype', default='bf16', choices=['bf16', 'fp32'])
+    ap.add_argument('--nc', type=int, default=1, choices=[1, 3], help='image channels: 1 = the benchmark workload (BASELINE.json), 3 = the CLI default')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':
