@@ -257,6 +257,19 @@ class DCGANTrainer:
         # errD = errD_real + errD_fake (train_gan.py:140); D_x, D_G_z1, D_G_z2 are mean probabilities
         return torch.stack([m_real[0] + m_fake[0], m_g[0], m_real[1], m_fake[1], m_g[1]])
 
+    def refresh_packed_weights(self):
+        """Re-derive the cached bf16 weight repacks from the fp32 masters.  Call after the weights were changed from OUTSIDE the
+        trainer (`load_state_dict`, manual edits): the repacks are otherwise only refreshed after the trainer's own Adam updates,
+        and a captured CUDA graph reads the persistent repack buffers its previous replay wrote."""
+        st = L.stream_ptr()
+        for eng, net in ((self.engD, self.netD), (self.engG, self.netG)):
+            for i, sp in enumerate(eng.specs):
+                hit = eng._packed.get(i)
+                if hit is None:
+                    continue
+                w = net.main[sp.conv_idx].weight
+                L.call('b200gan_pack_conv_weight', L.ptr(w), w.shape[0], w.shape[1], 4, 2, L.ptr(hit[1]), st)
+
     @torch.no_grad()
     def sample(self, noise: torch.Tensor) -> torch.Tensor:
         """The visualisation forward of train_gan.py:166-169 (train-mode under no_grad: BatchNorm buffers move)."""

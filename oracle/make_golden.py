@@ -21,6 +21,11 @@ Fixtures
   step_full_nc1.npz
       full-size nets (nz=100, ngf=ndf=64, nc=1), batch 2, 1 iteration; scalars, D probabilities, a
       strided sample of the fake image and per-tensor checksums of grads / post-step weights.
+  step_full_b32_nc1.npz / step_full_b32_nc3.npz
+      the configuration bench.py times, at a batch the CPU finishes in seconds: full-size nets, batch 32 (BatchNorm is well
+      conditioned: >= 1568 samples per channel), 2 iterations; as above, but every gradient / post-step tensor is kept as its
+      L2 norm plus a strided sample of up to 4096 entries (relative-L2 parity of the bf16 tensor-core path is measured on
+      those samples), small tensors (<= 4096 entries, incl. every BatchNorm vector) in full.
 """
 from __future__ import annotations
 
@@ -88,7 +93,7 @@ def reference_step(dcgan, netG, netD, optG, optD, real, noise):
                 grads_D=gradsD, grads_G=gradsG)
 
 
-def make_step_fixture(dcgan, name, nz, fm, nc, batch, iters, seed, full=False):
+def make_step_fixture(dcgan, name, nz, fm, nc, batch, iters, seed, full=False, sample=64, wsample=256, fake_stride=7):
     rng = np.random.RandomState(seed)
     sdG = orc.init_state(orc.generator_plan(nz, nc, fm), True, rng)
     sdD = orc.init_state(orc.discriminator_plan(nc, fm), False, rng)
@@ -98,7 +103,8 @@ def make_step_fixture(dcgan, name, nz, fm, nc, batch, iters, seed, full=False):
     optD = torch.optim.Adam(netD.parameters(), lr=2e-4, betas=(0.5, 0.999))
     optG = torch.optim.Adam(netG.parameters(), lr=2e-4, betas=(0.5, 0.999))
     out = dict(meta=json.dumps(dict(nz=nz, fm=fm, nc=nc, batch=batch, iters=iters, seed=seed, lr=2e-4, beta1=0.5,
-                                    real_seed=seed + 1, noise_seed=seed + 2, torch=torch.__version__)))
+                                    real_seed=seed + 1, noise_seed=seed + 2, torch=torch.__version__,
+                                    sample=sample, wsample=wsample, fake_stride=fake_stride)))
     real = synthetic_real(seed + 1, batch, nc)
     noises = synthetic_noise(seed + 2, batch * iters, nz).reshape(iters, batch, nz, 1, 1)
     for it in range(iters):
@@ -108,13 +114,13 @@ def make_step_fixture(dcgan, name, nz, fm, nc, batch, iters, seed, full=False):
         for k in ('p_real', 'p_fake', 'p_fake_for_G'):
             out[f'it{it}.{k}'] = r[k]
         if full:
-            out[f'it{it}.fake_sample'] = r['fake'][:, :, ::7, ::7].copy()
+            out[f'it{it}.fake_sample'] = r['fake'][:, :, ::fake_stride, ::fake_stride].copy()
             out[f'it{it}.fake_sum'] = np.float64(r['fake'].astype(np.float64).sum())
             out[f'it{it}.fake_sqsum'] = np.float64((r['fake'].astype(np.float64) ** 2).sum())
             for net in ('grads_D', 'grads_G'):
                 for k, v in r[net].items():
                     out[f'it{it}.{net}.{k}.l2'] = np.float64(np.sqrt((v.astype(np.float64) ** 2).sum()))
-                    out[f'it{it}.{net}.{k}.sample'] = v.reshape(-1)[::max(1, v.size // 64)][:64].copy()
+                    out[f'it{it}.{net}.{k}.sample'] = v.reshape(-1)[::max(1, v.size // sample)][:sample].copy()
         else:
             out[f'it{it}.fake'] = r['fake'][:, :, ::3, ::3].copy()     # strided sample keeps the fixture small
             if it == 0:
@@ -125,7 +131,7 @@ def make_step_fixture(dcgan, name, nz, fm, nc, batch, iters, seed, full=False):
         for k, v in to_np(net.state_dict()).items():
             if full and v.size > 4096:
                 out[f'final.{tag}.{k}.l2'] = np.float64(np.sqrt((v.astype(np.float64) ** 2).sum()))
-                out[f'final.{tag}.{k}.sample'] = v.reshape(-1)[::max(1, v.size // 256)][:256].copy()
+                out[f'final.{tag}.{k}.sample'] = v.reshape(-1)[::max(1, v.size // wsample)][:wsample].copy()
             else:
                 out[f'final.{tag}.{k}'] = v
     path = os.path.join(GOLDEN_DIR, name)
@@ -211,6 +217,7 @@ def make_main_fixture(ref_src, name):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--ref', default='/root/reference')
+    ap.add_argument('--only', default=None, help='substring filter on the fixture names (default: regenerate all)')
     a = ap.parse_args()
     ref_src = os.path.join(a.ref, 'src')
     sys.path.insert(0, ref_src)
@@ -218,10 +225,21 @@ def main():
     assert os.path.abspath(dcgan.__file__).startswith(os.path.abspath(a.ref)), dcgan.__file__
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     torch.manual_seed(0)
-    make_step_fixture(dcgan, 'step_small_nc1.npz', nz=16, fm=8, nc=1, batch=3, iters=2, seed=100)
-    make_step_fixture(dcgan, 'step_small_nc3.npz', nz=16, fm=8, nc=3, batch=3, iters=2, seed=200)
-    make_step_fixture(dcgan, 'step_full_nc1.npz', nz=100, fm=64, nc=1, batch=2, iters=1, seed=300, full=True)
-    make_main_fixture(ref_src, 'main_small_nc3.npz')
+    want = lambda n: a.only is None or a.only in n
+    if want('step_small_nc1.npz'):
+        make_step_fixture(dcgan, 'step_small_nc1.npz', nz=16, fm=8, nc=1, batch=3, iters=2, seed=100)
+    if want('step_small_nc3.npz'):
+        make_step_fixture(dcgan, 'step_small_nc3.npz', nz=16, fm=8, nc=3, batch=3, iters=2, seed=200)
+    if want('step_full_nc1.npz'):
+        make_step_fixture(dcgan, 'step_full_nc1.npz', nz=100, fm=64, nc=1, batch=2, iters=1, seed=300, full=True)
+    if want('step_full_b32_nc1.npz'):
+        make_step_fixture(dcgan, 'step_full_b32_nc1.npz', nz=100, fm=64, nc=1, batch=32, iters=2, seed=500, full=True, sample=4096, wsample=4096,
+                          fake_stride=13)
+    if want('step_full_b32_nc3.npz'):
+        make_step_fixture(dcgan, 'step_full_b32_nc3.npz', nz=100, fm=64, nc=3, batch=32, iters=2, seed=600, full=True, sample=4096, wsample=4096,
+                          fake_stride=13)
+    if want('main_small_nc3.npz'):
+        make_main_fixture(ref_src, 'main_small_nc3.npz')
 
 
 if __name__ == '__main__':
