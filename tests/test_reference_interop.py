@@ -50,8 +50,7 @@ def test_unmodified_reference_sampler_loads_our_checkpoint(tmp_path):
     tg.main(tg.build_parser().parse_args(argv))
     ckpt = d + '/models/gan/generator_final.pth'
     ref_gs = _load_reference('generate_synthetic')
-    import inspect
-    assert inspect.getsourcefile(ref_gs.generate_images).startswith(REF_SRC) and inspect.getsourcefile(ref_gs.Generator).startswith(REF_SRC)
+    assert ref_gs.__file__.startswith(REF_SRC) and ref_gs.Generator.__init__.__code__.co_filename.startswith(REF_SRC)   # the reference's own classes
     # the call the reference's __main__ makes (generate_synthetic.py:82-90); any load error there ends in sys.exit(1)
     torch.manual_seed(3)
     ref_gs.generate_images(ckpt, d + '/ref_synthetic', 3, 8, 4, 2, torch.device('cpu'))
