@@ -66,8 +66,14 @@ PROTOTYPES = {
     'b200gan_copy_view': [_VP, _VP, _vp],
     'b200gan_fill_f32': [_vp, _i64, _f32, _vp],
     'b200gan_gather_augment': [_vp, _i64, _vp, _vp, C.POINTER(C.c_float), C.POINTER(C.c_float), _VP, _vp],
+    'b200gan_dp_unique_id': [_vp],
+    'b200gan_dp_init': [_vp, _i32, _i32, C.POINTER(_vp)],
+    'b200gan_dp_allreduce_bucket': [_vp, _vp, _i64, _vp],
+    'b200gan_dp_sync': [_vp, _vp],
+    'b200gan_dp_destroy': [_vp],
 }
-OTHER_SYMBOLS = ['b200gan_version', 'b200gan_last_error_string', 'b200gan_device_info']
+OTHER_SYMBOLS = ['b200gan_version', 'b200gan_last_error_string', 'b200gan_device_info', 'b200gan_dp_collectives']
+DP_ID_BYTES = 128
 
 _lib = None
 
@@ -94,6 +100,8 @@ def load():
     lib.b200gan_last_error_string.restype = C.c_char_p
     lib.b200gan_device_info.argtypes = [C.c_int, C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.b200gan_device_info.restype = C.c_int
+    lib.b200gan_dp_collectives.argtypes = [_vp]
+    lib.b200gan_dp_collectives.restype = C.c_int64
     _lib = lib
     return lib
 

@@ -6,20 +6,66 @@ arena (trainer._Arena); `GradBuckets` cuts that arena into contiguous buckets in
 NCCL traffic over NVLink overlaps the rest of the backward pass.  The 1/world scaling is folded into the Adam kernel
 (`b200gan_adam(grad_scale=1/world)`), so the collective is a plain sum.  BatchNorm statistics stay local to each rank.
 
-The class only touches torch tensors and `torch.distributed`, so the same code runs on CPU tensors over gloo (that is how
-tests/test_dp_gloo.py covers it without GPUs) and on CUDA tensors over NCCL (also inside CUDA-graph capture: the communication
-stream forks from and joins the capturing stream through events).
+Transport: for CUDA arenas the collectives go through the library's own communicator (`DPComm` = b200gan_dp_* of
+include/b200gan.h: ncclCommInitRank from a broadcast unique id, a dedicated communication stream, event fork / join against the
+compute stream, capturable into the iteration's CUDA graph); `torch.distributed` only carries the 128-byte id.  For CPU arenas
+(tests/test_dp_gloo.py, world_size 2 over gloo, no GPU) the same bucket plan runs over `torch.distributed.all_reduce`.
 """
 from __future__ import annotations
 
 from typing import List, Optional, Sequence, Tuple
 
+import ctypes as C
+
 import torch
 import torch.distributed as dist
 
+from . import _lib as L
+
+
+class DPComm:
+    """The library's NCCL communicator for this process' GPU (b200gan_dp_init): rank 0 draws the unique id, `torch.distributed`
+    (any backend; `group` optional) broadcasts its 128 bytes, every rank joins.  Create AFTER torch.cuda.set_device."""
+
+    def __init__(self, group=None):
+        if not (dist.is_available() and dist.is_initialized()):
+            raise L.B200GanError('DPComm needs an initialised torch.distributed process group to exchange the NCCL unique id')
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        buf = (C.c_ubyte * L.DP_ID_BYTES)()
+        if self.rank == 0:
+            L.call('b200gan_dp_unique_id', C.cast(buf, C.c_void_p))
+        dev = torch.device('cuda', torch.cuda.current_device()) if dist.get_backend(group) == 'nccl' else torch.device('cpu')
+        t = torch.tensor(list(bytes(buf)), dtype=torch.uint8, device=dev)
+        dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        ident = (C.c_ubyte * L.DP_ID_BYTES)(*t.cpu().tolist())
+        self._h = C.c_void_p()
+        L.call('b200gan_dp_init', C.cast(ident, C.c_void_p), self.world, self.rank, C.byref(self._h))
+
+    def allreduce_bucket(self, view: torch.Tensor):
+        L.call('b200gan_dp_allreduce_bucket', self._h, L.ptr(view), view.numel(), L.stream_ptr())
+
+    def sync(self):
+        L.call('b200gan_dp_sync', self._h, L.stream_ptr())
+
+    @property
+    def collectives(self) -> int:
+        return int(L.load().b200gan_dp_collectives(self._h)) if self._h else 0
+
+    def close(self):
+        if self._h:
+            h, self._h = self._h, C.c_void_p()
+            L.call('b200gan_dp_destroy', h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:      # noqa: BLE001  (interpreter shutdown)
+            pass
+
 
 class GradBuckets:
-    def __init__(self, grad_arena: torch.Tensor, slices: Sequence[Tuple[int, int]], group=None, bucket_numel: int = 1 << 20):
+    def __init__(self, grad_arena: torch.Tensor, slices: Sequence[Tuple[int, int]], group=None, bucket_numel: int = 1 << 20,
+                 comm: Optional[DPComm] = None):
         """grad_arena: flat tensor holding every gradient; slices[i] = (start, end) of parameter i in `param_order()`
         (layer 0 first).  Buckets are built from the END of the arena (the last layer's gradients are final first)."""
         self.arena, self.group = grad_arena, group
@@ -38,7 +84,9 @@ class GradBuckets:
                 self._bucket_of[i] = b
         self._pending = [set(idx) for (_, _, idx) in self.buckets]
         self._launched = [False] * len(self.buckets)
-        self._comm: Optional[torch.cuda.Stream] = torch.cuda.Stream() if grad_arena.is_cuda else None
+        self.comm = comm                 # CUDA arenas: the library's communicator; None: torch.distributed (CPU / gloo tests)
+        if grad_arena.is_cuda and self.world > 1 and comm is None:
+            raise L.B200GanError('GradBuckets over a CUDA arena needs a DPComm (the library owns the NCCL communicator)')
         self.collectives = 0
 
     def begin(self):
@@ -60,14 +108,10 @@ class GradBuckets:
         self._launched[b] = True
         self.collectives += 1
         view = self.arena[lo:hi]
-        if self._comm is None:
+        if self.comm is None:
             dist.all_reduce(view, group=self.group)
-            return
-        ev = torch.cuda.Event()
-        ev.record(torch.cuda.current_stream())
-        with torch.cuda.stream(self._comm):
-            self._comm.wait_event(ev)
-            dist.all_reduce(view, group=self.group)
+        else:
+            self.comm.allreduce_bucket(view)         # asynchronous, on the library's communication stream
 
     def finish(self):
         """Launch whatever has not gone out yet and make the current stream wait for every bucket (call before Adam)."""
@@ -76,5 +120,5 @@ class GradBuckets:
         for b in range(len(self.buckets)):
             if not self._launched[b]:
                 self._launch(b)
-        if self._comm is not None:
-            torch.cuda.current_stream().wait_stream(self._comm)
+        if self.comm is not None:
+            self.comm.sync()

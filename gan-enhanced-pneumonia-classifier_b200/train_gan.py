@@ -75,6 +75,18 @@ def _synthetic_loader(n_images, nc, batch_size, seed):
     return torch.utils.data.DataLoader(ds, batch_size=batch_size, shuffle=False, pin_memory=torch.cuda.is_available())
 
 
+_DATA_LOADER_HINT = ("The RSNA loaders are the reference's own src/data_loader.py (not shipped here): put the reference's src/ directory on "
+                     'PYTHONPATH (see INTEGRATION.md), or train on synthetic images with --synthetic N.')
+
+
+def _shard_loader(loader, world, rank, batch_size, workers, seed):
+    """Data parallel over the reference's DataLoader (data_loader.py:189-192): the same dataset behind a DistributedSampler
+    (shuffle, equal shard sizes), so that each rank walks 1/world of the images per epoch."""
+    sampler = torch.utils.data.distributed.DistributedSampler(loader.dataset, num_replicas=world, rank=rank, shuffle=True, seed=seed,
+                                                              drop_last=True)
+    return torch.utils.data.DataLoader(loader.dataset, batch_size=batch_size, sampler=sampler, num_workers=workers, pin_memory=True)
+
+
 def _save_image_grid(t, path):
     import torchvision.utils as vutils
     vutils.save_image(t, path, normalize=True, nrow=8)
@@ -117,8 +129,9 @@ def main(args):
     is_main = rank == 0
     if is_main:
         print(f'Using device: {device}' + (f' (data parallel over {world} ranks)' if world > 1 else ''))
-    if getattr(args, 'seed', None) is not None:
-        torch.manual_seed(args.seed)
+    seed = getattr(args, 'seed', None)
+    if seed is not None:
+        torch.manual_seed(seed)          # common stream: weight initialisation and fixed_noise are the same on every rank
 
     gan_model_dir = os.path.join(args.model_dir, 'gan')
     gan_output_dir = os.path.join(args.output_dir, 'gan_images')
@@ -137,7 +150,8 @@ def main(args):
         g = torch.Generator().manual_seed(1 + rank)
         u8 = torch.randint(0, 256, (n_syn, args.num_channels, 224, 224), dtype=torch.uint8, generator=g)
         half = (0.5,) * args.num_channels
-        train_loader = DeviceImageCache(u8.to(device), batch_size=args.batch_size, mean=half, std=half, dtype=cache_dtype, seed=getattr(args, 'seed', None))
+        train_loader = DeviceImageCache(u8.to(device), batch_size=args.batch_size, mean=half, std=half, dtype=cache_dtype,
+                                        seed=None if seed is None else seed + rank)
         print(f'Loaded training data with {len(train_loader.dataset)} samples.' if is_main else '', end='\n' if is_main else '')
     elif cached:
         try:
@@ -147,15 +161,19 @@ def main(args):
                 raise FileNotFoundError(f'Dataset not available in {args.data_dir}. Please download using the provided script.')
             ds = RSNAPneumoniaDataset(os.path.join(args.data_dir, 'Training', 'Images'), os.path.join(args.data_dir, 'stage2_train_metadata.csv'),
                                       transform=T.Resize((224, 224)), is_test=False)
-            if world > 1:        # each rank caches and draws from its own slice of the images
-                ds = torch.utils.data.Subset(ds, range(rank, len(ds), world))
+            if world > 1:        # each rank caches and draws from its own slice of the images; equal slices, so that every rank
+                ds = torch.utils.data.Subset(ds, range(rank, len(ds) // world * world, world))   # issues the same collectives
             train_loader = DeviceImageCache.from_dataset(ds, device, num_workers=args.workers, batch_size=args.batch_size, dtype=cache_dtype,
-                                                         seed=getattr(args, 'seed', None))
+                                                         seed=None if seed is None else seed + rank)
             if train_loader.images.shape[1] != args.num_channels:
                 print(f'Error: the dataset has {train_loader.images.shape[1]} channels, --num-channels is {args.num_channels}')
                 return
             print(f'Loaded training data with {len(train_loader.dataset)} samples (device-resident cache, '
                   f'{train_loader.images.numel() / 2**30:.2f} GiB).')
+        except ImportError as e:
+            print(f'Error: {e}')
+            print(_DATA_LOADER_HINT)
+            return
         except FileNotFoundError as e:
             print(f'Error: {e}')
             print(f"Please ensure the dataset exists at '{args.data_dir}' and is structured correctly.")
@@ -168,7 +186,13 @@ def main(args):
         try:
             from data_loader import get_dataloaders          # the reference's src/data_loader.py:158
             train_loader, _ = get_dataloaders(data_dir=args.data_dir, batch_size=args.batch_size, num_workers=args.workers)
+            if world > 1:
+                train_loader = _shard_loader(train_loader, world, rank, args.batch_size, args.workers, seed or 0)
             print(f'Loaded training data with {len(train_loader.dataset)} samples.')
+        except ImportError as e:
+            print(f'Error: {e}')
+            print(_DATA_LOADER_HINT)
+            return
         except FileNotFoundError as e:
             print(f'Error: {e}')
             print(f"Please ensure the dataset exists at '{args.data_dir}' and is structured correctly.")
@@ -177,6 +201,14 @@ def main(args):
         except Exception as e:   # noqa: BLE001  (reference :75-77)
             print(f'Error loading data: {e}')
             return
+
+    if world > 1:
+        # every rank must issue the same number of gradient exchanges per epoch, on the same batch shapes
+        nb = torch.tensor([len(train_loader), -len(train_loader)], device=device, dtype=torch.int64)
+        torch.distributed.all_reduce(nb, op=torch.distributed.ReduceOp.MAX)
+        if int(nb[0]) != -int(nb[1]):
+            raise RuntimeError(f'data-parallel ranks disagree on the number of batches per epoch ({-int(nb[1])}..{int(nb[0])}): '
+                               'shard the dataset into equal parts')
 
     # --- networks (reference :80-84) ----------------------------------------------------------------
     netG = Generator(args.latent_dim, args.num_channels, args.feature_maps_g).to(device)
@@ -191,9 +223,12 @@ def main(args):
         print('Discriminator Architecture Initialized.')
 
     fixed_noise = torch.randn(args.vis_batch_size, args.latent_dim, 1, 1, device=device)
+    if seed is not None and world > 1:
+        torch.manual_seed(seed + rank)   # from here on (per-step noise, train_gan.py:132) every rank draws its own stream
     trainer = None
     if use_cuda:
         dtype = {'bf16': torch.bfloat16, 'fp32': torch.float32}[getattr(args, 'dtype', 'bf16')]
+        netG.compute_dtype = netD.compute_dtype = dtype      # the module-level forwards (visualisation, train_gan.py:166-169) too
         trainer = DCGANTrainer(netG, netD, lr=args.lr, beta1=args.beta1, dtype=dtype)
     else:
         criterion = nn.BCELoss()
@@ -218,6 +253,8 @@ def main(args):
         pending = []                      # device-side (5,) tensors, not yet synchronised
         epoch_rows = []
         num_batches = len(train_loader)
+        if hasattr(getattr(train_loader, 'sampler', None), 'set_epoch'):
+            train_loader.sampler.set_epoch(epoch)
         it = enumerate(train_loader)
         bar = tqdm(it, total=num_batches, desc=f'Epoch {epoch + 1}/{args.epochs}', leave=True) if (tqdm and is_main) else it
 

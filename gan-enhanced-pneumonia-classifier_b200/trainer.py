@@ -27,7 +27,7 @@ import torch
 
 from . import _lib as L
 from . import engine as E
-from .dp import GradBuckets
+from .dp import DPComm, GradBuckets
 
 REAL_LABEL = 0.9      # train_gan.py:92
 FAKE_LABEL = 0.0      # train_gan.py:93
@@ -83,8 +83,13 @@ class DCGANTrainer:
         if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
             self.world = torch.distributed.get_world_size(process_group)
         self.extra_launches = 0
-        self.bucketsD = GradBuckets(self.arenaD.grad, self.arenaD.slices, process_group)
-        self.bucketsG = GradBuckets(self.arenaG.grad, self.arenaG.slices, process_group)
+        # data parallel: the library's own NCCL communicator (b200gan_dp_*); torch.distributed only carried its unique id
+        self.comm = DPComm(process_group) if self.world > 1 else None
+        self.bucketsD = GradBuckets(self.arenaD.grad, self.arenaD.slices, process_group, comm=self.comm)
+        self.bucketsG = GradBuckets(self.arenaG.grad, self.arenaG.slices, process_group, comm=self.comm)
+        # B200GAN_DP_SEGMENTED=1: keep the collectives out of the capture (three graphs cut at the two exchanges, every bucket
+        # issued between the replays) -- a diagnostic switch; the default captures the bucket all-reduces with the iteration
+        self.segmented = os.environ.get('B200GAN_DP_SEGMENTED', '0') == '1'
         if use_graph is None:
             use_graph = os.environ.get('B200GAN_GRAPH', '1') != '0'
         self.use_graph = use_graph
@@ -146,7 +151,7 @@ class DCGANTrainer:
         for graph, exchange in cap.graph:
             graph.replay()
             if exchange is not None:
-                self._exchange(exchange, overlap=False)
+                self._exchange(exchange, overlapped=False)
         self._replayed_launches += cap.launches
         return cap.out.clone()
 
@@ -161,23 +166,23 @@ class DCGANTrainer:
                          None if noise_shape is None else torch.zeros(noise_shape, device=dev, dtype=torch.float32))
         return bufs[key]
 
-    def _exchange(self, which: str, overlap: bool):
+    def _exchange(self, which: str, overlapped: bool = True):
         """Gradient exchange between ranks before the Adam update of network `which` ('D' or 'G'): sum over ranks (the 1/world
-        factor is applied inside the Adam kernel).  overlap=True: buckets were launched on the communication stream while
-        the backward pass ran (dp.GradBuckets), only the stragglers and the stream join remain; overlap=False (between
-        graph replays): one all-reduce of the whole arena on the current stream."""
-        if self.world == 1:
+        factor is applied inside the Adam kernel).  The buckets were launched on the library's communication stream while the
+        backward pass ran (dp.GradBuckets.ready); what remains is the last bucket and the stream join.  overlapped=False
+        (segmented diagnostic mode, between graph replays): every bucket goes out now."""
+        if self.comm is None:
             return
-        arena, buckets = (self.arenaD, self.bucketsD) if which == 'D' else (self.arenaG, self.bucketsG)
-        if overlap:
-            buckets.finish()
-        else:
-            torch.distributed.all_reduce(arena.grad, group=self.pg)
+        buckets = self.bucketsD if which == 'D' else self.bucketsG
+        if not overlapped:
+            buckets.begin()
+        buckets.finish()
 
     def _capture(self, real, noise, key):
-        """Single GPU: the whole iteration is ONE graph.  Data parallel: the iteration is cut at the two gradient exchanges into
-        three graphs sharing one memory pool, and the NCCL all-reduces run between the replays (collectives are kept out of
-        the captures: capturing them together with the side-stream fork/join deadlocked NCCL 2.28 on this stack)."""
+        """The whole iteration is ONE graph, data parallel included: the bucket all-reduces are captured with it (the library forks
+        its communication stream from the capturing stream per bucket and joins it before each Adam update), so a replayed
+        iteration overlaps NCCL traffic with the backward pass exactly like the kernel-by-kernel one.  The communicator was
+        warmed up by the eager first iteration (NCCL sets up its channels on first use, which must not happen under capture)."""
         cap = _Captured()
         cap.real, cap.noise = self.input_buffers(real.shape, real.dtype, None if noise is None else noise.shape)
         cap.real.copy_(real)
@@ -185,22 +190,25 @@ class DCGANTrainer:
             cap.noise.copy_(noise)
         l0 = self.engG.launches + self.engD.launches + self.extra_launches
         torch.cuda.synchronize()
-        gen = self._segments(cap.real, cap.noise, overlap=False)
+        gen = self._segments(cap.real, cap.noise, overlap=not self.segmented)
         cap.graph = []
         pool = torch.cuda.graph_pool_handle()
         done = False
         while not done:
             g = torch.cuda.CUDAGraph()
             exchange = None
-            with torch.cuda.graph(g, pool=pool):
+            # thread_local: NCCL's proxy / torch's watchdog threads may touch the CUDA API while this thread captures
+            with torch.cuda.graph(g, pool=pool, capture_error_mode='thread_local' if self.world > 1 else 'global'):
                 while True:
                     try:
                         exchange = next(gen)
                     except StopIteration as e:
                         cap.out, done, exchange = e.value, True, None
                         break
-                    if self.world > 1:
+                    if self.comm is not None and self.segmented:
                         break                    # cut the graph here; the exchange runs between replays
+                    self._exchange(exchange)     # captured: last bucket + join of the communication stream
+                    exchange = None
             cap.graph.append((g, exchange))
         cap.launches = self.engG.launches + self.engD.launches + self.extra_launches - l0
         # capture records, it does not execute: take the recorded launches back out of the eager counters
@@ -212,7 +220,7 @@ class DCGANTrainer:
         gen = self._segments(real, noise, overlap=True)
         while True:
             try:
-                self._exchange(next(gen), overlap=True)
+                self._exchange(next(gen))
             except StopIteration as e:
                 return e.value
 
@@ -224,8 +232,8 @@ class DCGANTrainer:
             noise = torch.randn((real.shape[0], self.engG.specs[0].cin, 1, 1), device=real.device, dtype=torch.float32)
         pG = E.params_from_module(netG, self.engG.specs)
         pD = E.params_from_module(netD, self.engD.specs)
-        readyD = self.bucketsD.ready if (overlap and self.world > 1) else None
-        readyG = self.bucketsG.ready if (overlap and self.world > 1) else None
+        readyD = self.bucketsD.ready if (overlap and self.comm is not None) else None
+        readyG = self.bucketsG.ready if (overlap and self.comm is not None) else None
         # (1) D step ------------------------------------------------------------- train_gan.py:122-141
         self.arenaD.grad.zero_()
         logit_r, ctx_r = self.engD.forward(self._as_input(real), pD, True, True, last_act=False)

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define B200GAN_VERSION 300   /* major*10000 + minor*100 + patch */
+#define B200GAN_VERSION 400   /* major*10000 + minor*100 + patch */
 
 typedef enum b200gan_status {
   B200GAN_OK = 0,
@@ -207,6 +207,30 @@ int b200gan_fill_f32(float* ptr, int64_t numel, float value, void* stream);
  *      Arithmetic is torchvision's, (v / 255 - mean) / std in fp32 with true divisions: bit-exact for an f32 output. */
 int b200gan_gather_augment(const uint8_t* cache, int64_t num_images, const int64_t* index, const uint8_t* flip, const float* mean,
                            const float* std, const b200gan_view* out, void* stream);
+
+/* ---- data-parallel gradient-bucket layer (new functionality: the reference is single-device, src/train_gan.py:49; semantics in
+ *      SURVEY.md section 8e).  One process per GPU; weights and Adam state replicated; every optimizer update (train_gan.py:141,150)
+ *      is preceded by a SUM of the per-rank gradients, issued bucket by bucket while the backward pass is still running:
+ *        dp_unique_id         rank 0 obtains the 128-byte NCCL unique id; the host side broadcasts it to the other ranks
+ *                             (torch.distributed store / broadcast -- plumbing only);
+ *        dp_init              ncclCommInitRank on the CURRENT device + a dedicated communication stream; returns an opaque handle
+ *                             (the only persistent state the library ever owns; released by dp_destroy);
+ *        dp_allreduce_bucket  in-place sum over ranks of `grad[0..numel)` (fp32, device).  Asynchronous: forks the communication
+ *                             stream from `stream` (everything launched on `stream` so far precedes the collective) and
+ *                             returns; `stream` itself continues with the backward pass.  Capturable into a CUDA graph;
+ *        dp_sync              joins: `stream` waits for every bucket issued so far (call before b200gan_adam, whose grad_scale
+ *                             carries the 1/world factor);
+ *        dp_collectives       number of bucket all-reduces issued through the handle (launch accounting / tests).
+ *      Errors: B200GAN_ERR_NCCL with the NCCL message in b200gan_last_error_string().  NCCL is bound at run time from the
+ *      libnccl.so.2 already loaded in the process (torch's), so single-GPU users never need it. */
+#define B200GAN_DP_ID_BYTES 128
+typedef struct b200gan_dp b200gan_dp;
+int     b200gan_dp_unique_id(void* id_out);
+int     b200gan_dp_init(const void* id, int32_t world, int32_t rank, b200gan_dp** out);
+int     b200gan_dp_allreduce_bucket(b200gan_dp* dp, float* grad, int64_t numel, void* stream);
+int     b200gan_dp_sync(b200gan_dp* dp, void* stream);
+int64_t b200gan_dp_collectives(const b200gan_dp* dp);
+int     b200gan_dp_destroy(b200gan_dp* dp);
 
 #ifdef __cplusplus
 }

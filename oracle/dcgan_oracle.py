@@ -239,11 +239,29 @@ def param_keys(plan):
     return keys
 
 
-class Net:
-    """Common forward/backward driver over a plan and a state dict (numpy arrays, updated in place)."""
+def bf16_round(x):
+    """Round-to-nearest-even to bfloat16 precision, returned as float32 (what storing a tensor in bf16 and reading it back does)."""
+    u = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32)
+    r = ((u >> np.uint32(16)) & np.uint32(1)) + np.uint32(0x7FFF)
+    return ((u + r) & np.uint32(0xFFFF0000)).view(np.float32)
 
-    def __init__(self, plan, transposed, state):
+
+class Net:
+    """Common forward/backward driver over a plan and a state dict (numpy arrays, updated in place).
+
+    `storage`: None (the reference's fp32 arithmetic), or a rounding function (e.g. `bf16_round`) applied wherever the B200
+    build's bf16 mode STORES a tensor: network input as read by the first convolution, the multiplicand copy of every conv
+    weight (the fp32 masters stay exact; layers in `fp32_weight_layers` multiply by the fp32 weights), every convolution
+    output, every activation output, every activation-backward result dz, every BatchNorm-backward result dy, and the
+    gradient handed out of the network.  Accumulation stays wide, statistics are those of the STORED tensors.  This is the
+    model the bf16 tensor-core path is held to tightly (tests/test_gpu_fullsize.py); how far that model sits from the fp32
+    reference is a property of bf16 storage, not of the kernels."""
+    fp32_weight_layers = ()
+    fp32_output_layers = ()
+
+    def __init__(self, plan, transposed, state, storage=None):
         self.plan, self.transposed, self.sd = plan, transposed, state
+        self.q = storage if storage is not None else (lambda t: t)
 
     # activation after layer i
     def _act(self, i, z):
@@ -254,10 +272,13 @@ class Net:
 
     def forward(self, x, train=True):
         cache = []
-        a = x
+        q = self.q
+        a = q(x)
         for i, (conv_i, bn_i, cin, cout, k, s, p) in enumerate(self.plan):
             w = self.sd[f'main.{conv_i}.weight']
+            w = w if i in self.fp32_weight_layers else q(w)
             y = convT2d_fprop(a, w, s, p) if self.transposed else conv2d_fprop(a, w, s, p)
+            y = y if i in self.fp32_output_layers else q(y)
             xhat = invstd = None
             if bn_i is not None:
                 g, b = self.sd[f'main.{bn_i}.weight'], self.sd[f'main.{bn_i}.bias']
@@ -269,6 +290,7 @@ class Net:
             else:
                 z = y
             out = self._act(i, z)
+            out = out if i in self.fp32_output_layers else q(out)
             cache.append((a, z, out, xhat, invstd))
             a = out
         return a, cache
@@ -276,31 +298,35 @@ class Net:
     def backward(self, cache, dout, need_input_grad=True):
         """Returns (grads dict over parameter keys, dinput or None)."""
         grads = {}
+        q = self.q
         d = dout
         for i in reversed(range(len(self.plan))):
             conv_i, bn_i, cin, cout, k, s, p = self.plan[i]
             a_in, z, out, xhat, invstd = cache[i]
             dz = self._act_bwd(i, d, z, out)
+            dz = dz if i in self.fp32_output_layers else q(dz)
             if bn_i is not None:
                 dy, dg, db = bn_train_bwd(dz, xhat, self.sd[f'main.{bn_i}.weight'], invstd)
+                dy = q(dy)
                 grads[f'main.{bn_i}.weight'], grads[f'main.{bn_i}.bias'] = dg, db
             else:
                 dy = dz
             w = self.sd[f'main.{conv_i}.weight']
+            w = w if i in self.fp32_weight_layers else q(w)
             if self.transposed:
                 grads[f'main.{conv_i}.weight'] = convT2d_wgrad(a_in, dy, k, s, p)
                 d = convT2d_dgrad(dy, w, s, p) if (i > 0 or need_input_grad) else None
             else:
                 grads[f'main.{conv_i}.weight'] = conv2d_wgrad(a_in, dy, k, s, p)
                 d = conv2d_dgrad(dy, w, s, p, a_in.shape[2:]) if (i > 0 or need_input_grad) else None
-        return grads, d
+        return grads, (q(d) if d is not None else None)
 
 
 class GeneratorOracle(Net):
     """dcgan.py:14-52: ConvT -> BN -> ReLU (x5), ConvT -> Tanh."""
 
-    def __init__(self, latent_dim, nc, ngf, state):
-        super().__init__(generator_plan(latent_dim, nc, ngf), True, state)
+    def __init__(self, latent_dim, nc, ngf, state, storage=None):
+        super().__init__(generator_plan(latent_dim, nc, ngf), True, state, storage)
 
     def _act(self, i, z):
         return np.tanh(z) if i == 5 else np.maximum(z, 0)
@@ -314,8 +340,11 @@ class GeneratorOracle(Net):
 class DiscriminatorOracle(Net):
     """dcgan.py:54-90: Conv -> LeakyReLU, (Conv -> BN -> LeakyReLU) x4, Conv -> Sigmoid, flattened to (N,)."""
 
-    def __init__(self, nc, ndf, state):
-        super().__init__(discriminator_plan(nc, ndf), False, state)
+    fp32_weight_layers = (5,)      # the 7x7 GEMV multiplies bf16 activations by the fp32 master weights
+    fp32_output_layers = (5,)      # logits, probabilities and the loss gradient stay fp32
+
+    def __init__(self, nc, ndf, state, storage=None):
+        super().__init__(discriminator_plan(nc, ndf), False, state, storage)
 
     def _act(self, i, z):
         if i == 5:

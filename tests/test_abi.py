@@ -23,11 +23,11 @@ def test_library_exports_every_declared_symbol():
     assert os.path.exists(L.LIB_PATH), 'run __graft_entry__.build() first'
     lib = ctypes.CDLL(L.LIB_PATH)
     names = header_functions()
-    assert len(names) >= 19
+    assert len(names) >= 27
     for n in names:
         assert hasattr(lib, n), f'{n} declared in include/b200gan.h but not exported'
     assert sorted(list(L.PROTOTYPES) + L.OTHER_SYMBOLS) == names, 'ctypes prototypes and header differ'
-    assert lib.b200gan_version() == 300        # 0.3.0: + b200gan_gather_augment
+    assert lib.b200gan_version() == 400        # 0.4.0: + b200gan_dp_* (gradient-bucket layer on the library's own NCCL communicator)
 
 
 def test_bad_arguments_fail_loudly_without_a_gpu():

@@ -26,6 +26,8 @@ pytestmark = pytest.mark.gpu
 # with `pytest -s`; the first-layer tensors are the worst: their gradients passed through every bf16-stored activation)
 GRAD_REL_L2 = 6e-2
 GRAD_NORM_RTOL = 3e-2
+WEIGHT_TIGHT_FRAC = 0.9
+EMU_GRAD_REL_L2 = 2e-2
 
 
 def _sample(v, n):
@@ -33,7 +35,7 @@ def _sample(v, n):
     return v[::max(1, v.size // n)][:n]
 
 
-def _build(m):
+def _build(m, dtype):
     rng = np.random.RandomState(m['seed'])
     sdG = orc.init_state(orc.generator_plan(m['nz'], m['nc'], m['fm']), True, rng)
     sdD = orc.init_state(orc.discriminator_plan(m['nc'], m['fm']), False, rng)
@@ -41,7 +43,7 @@ def _build(m):
     G.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in sdG.items()})
     D.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in sdD.items()})
     G, D = G.cuda(), D.cuda()
-    G.compute_dtype = D.compute_dtype = torch.bfloat16
+    G.compute_dtype = D.compute_dtype = dtype
     return G, D
 
 
@@ -74,11 +76,60 @@ class _Snapshot:
 @pytest.mark.parametrize('mode', ['eager', 'graph'])
 @pytest.mark.parametrize('nc', [1, 3])
 def test_bf16_full_width_trainer_matches_reference_fixture(nc, mode, capsys):
+    _run(nc, mode, torch.bfloat16, capsys, rtol=2e-2, atol=2e-3, grad_rel=GRAD_REL_L2, grad_norm=GRAD_NORM_RTOL, tight=WEIGHT_TIGHT_FRAC)
+
+
+def test_fp32_full_width_trainer_matches_reference_fixture(capsys):
+    """The same comparison in the fp32 parity mode (SIMT kernels): separates wiring from bf16 precision.  north_star: fp32 rtol 1e-4
+    on outputs / losses; gradients by relative L2."""
+    _run(1, 'eager', torch.float32, capsys, rtol=1e-4, atol=1e-6, grad_rel=1e-3, grad_norm=1e-3, tight=0.97, it1_rtol=2e-3)
+
+
+@pytest.mark.parametrize('nc', [1, 3])
+def test_bf16_full_width_step_matches_the_bf16_storage_oracle(nc, capsys):
+    """The tight half of the bf16 parity statement.  Against the fp32 reference the bf16 path can only be as close as bf16 STORAGE
+    allows, and with hard ReLU / LeakyReLU branches that is not 2^-9: a pre-activation within rounding distance of zero takes the
+    other branch, which perturbs the gradients by ~sqrt(fraction of flipped elements) (measured above: 0.1-0.25 relative L2, the
+    same in kernel-by-kernel and graph mode, and 1e-3..2e-2 even between two fp32 implementations).  Here the oracle rounds to
+    bf16 at exactly the points where the kernels store bf16 (dcgan_oracle.Net(storage=bf16_round)): what remains is summation
+    order, tanh.approx and one-ulp rounding differences, so every gradient tensor must agree tightly."""
+    from gan_enhanced_pneumonia_classifier_b200.trainer import DCGANTrainer
+    m = dict(seed=700 + nc, nz=100, nc=nc, fm=64, batch=8, lr=2e-4, beta1=0.5)
+    G, D = _build(m, torch.bfloat16)
+    tr = DCGANTrainer(G, D, lr=m['lr'], beta1=m['beta1'], dtype=torch.bfloat16, use_graph=False)
+    real, noise = synthetic_real(m['seed'] + 1, m['batch'], nc), synthetic_noise(m['seed'] + 2, m['batch'], m['nz'])
+    got = tr.step(torch.from_numpy(real).cuda(), torch.from_numpy(noise).cuda()).cpu().numpy()
+    rng = np.random.RandomState(m['seed'])
+    sdG = orc.init_state(orc.generator_plan(m['nz'], nc, m['fm']), True, rng)
+    sdD = orc.init_state(orc.discriminator_plan(nc, m['fm']), False, rng)
+    oG = orc.GeneratorOracle(m['nz'], nc, m['fm'], sdG, storage=orc.bf16_round)
+    oD = orc.DiscriminatorOracle(nc, m['fm'], sdD, storage=orc.bf16_round)
+    r = orc.train_iteration(oG, oD, orc.AdamOracle(orc.param_keys(oG.plan), m['lr'], m['beta1']),
+                            orc.AdamOracle(orc.param_keys(oD.plan), m['lr'], m['beta1']), real, noise)
+    want = np.array([r[k] for k in ('errD', 'errG', 'D_x', 'D_G_z1', 'D_G_z2')])
+    report, fails = [f'history got {got} want {want}'], []
+    if not (np.abs(got - want) <= 1e-4 + 5e-3 * np.abs(want)).all():
+        fails.append(f'history scalars: got {got} want {want}')
+    for arena, tag in ((tr.arenaD, 'grads_D'), (tr.arenaG, 'grads_G')):
+        keys = orc.param_keys(oD.plan if tag == 'grads_D' else oG.plan)
+        for k, (lo, hi) in zip(keys, arena.slices):
+            v = arena.grad[lo:hi].float().cpu().numpy().astype(np.float64)
+            ref = r[tag][k].astype(np.float64).reshape(-1)
+            rel = float(np.linalg.norm(v - ref) / max(np.linalg.norm(ref), 1e-30))
+            report.append(f'{tag}.{k:16s} relL2 vs bf16-storage oracle {rel:.3e}')
+            if rel >= EMU_GRAD_REL_L2:
+                fails.append(f'{tag}.{k}: relative L2 {rel:.3e} against the bf16-storage oracle (bound {EMU_GRAD_REL_L2})')
+    with capsys.disabled():
+        print(f'\n[full-width bf16 step vs bf16-storage oracle nc={nc}]\n  ' + '\n  '.join(report))
+    assert not fails, '\n'.join(fails)
+
+
+def _run(nc, mode, dtype, capsys, rtol, atol, grad_rel, grad_norm, tight, it1_rtol=None):
     from gan_enhanced_pneumonia_classifier_b200.trainer import DCGANTrainer
     g = np.load(os.path.join(GOLDEN, f'step_full_b32_nc{nc}.npz'))
     m = json.loads(str(g['meta']))
-    G, D = _build(m)
-    tr = DCGANTrainer(G, D, lr=m['lr'], beta1=m['beta1'], dtype=torch.bfloat16, use_graph=(mode == 'graph'))
+    G, D = _build(m, dtype)
+    tr = DCGANTrainer(G, D, lr=m['lr'], beta1=m['beta1'], dtype=dtype, use_graph=(mode == 'graph'))
     snap = _Snapshot(tr)
     real = torch.from_numpy(synthetic_real(m['real_seed'], m['batch'], nc)).cuda()
     noises = synthetic_noise(m['noise_seed'], m['batch'] * m['iters'], m['nz']).reshape(m['iters'], m['batch'], m['nz'], 1, 1)
@@ -95,15 +146,17 @@ def test_bf16_full_width_trainer_matches_reference_fixture(nc, mode, capsys):
         fake = G(noises[0]).cpu().numpy()
     snap.restore(buffers_only=True)
     fs = m['fake_stride']
-    close(fake[:, :, ::fs, ::fs], g['it0.fake_sample'], rtol=2e-2, atol=2e-2, what='generator output')
-    report = []
+    close(fake[:, :, ::fs, ::fs], g['it0.fake_sample'], rtol=rtol, atol=max(atol, 1e-5) * 10, what='generator output')
+    report, fails = [], []
     keysD, keysG = orc.param_keys(orc.discriminator_plan(nc, m['fm'])), orc.param_keys(orc.generator_plan(m['nz'], nc, m['fm']))
     for it in range(m['iters']):
         got = tr.step(real, noises[it]).cpu().numpy()
         want = np.array([g[f'it{it}.{k}'] for k in ('errD', 'errG', 'D_x', 'D_G_z1', 'D_G_z2')])
         report.append(f'it{it} history got {got} want {want}')
         # north star: bf16 rtol 2e-2 against the fp32 reference (losses, mean probabilities)
-        close(got, want, rtol=2e-2, atol=2e-3, what=f'history scalars it{it}')
+        rt = rtol if it == 0 or it1_rtol is None else it1_rtol          # later iterations carry the first Adam step's sign-flip noise
+        if not (np.abs(got - want) <= atol + rt * np.abs(want)).all():
+            fails.append(f'history scalars it{it}: got {got} want {want}')
         if mode == 'graph':
             assert len(tr._graphs) == 1, 'the compared iterations must be graph replays'
         # ---- every gradient tensor of this iteration, relative L2 on the fixture's strided sample + the tensor's norm
@@ -117,8 +170,10 @@ def test_bf16_full_width_trainer_matches_reference_fixture(nc, mode, capsys):
                 nrm = float(np.sqrt((v ** 2).sum()) / g[f'it{it}.{tag}.{k}.l2'])
                 report.append(f'it{it} {tag}.{k:16s} relL2 {rel:.3e}  norm ratio {nrm:.4f}')
                 worst = max(worst, rel)
-                assert rel < GRAD_REL_L2, f'it{it} {tag}.{k}: relative L2 {rel:.3e} (bound {GRAD_REL_L2})'
-                assert abs(nrm - 1) < GRAD_NORM_RTOL, f'it{it} {tag}.{k}: norm ratio {nrm:.4f}'
+                if rel >= grad_rel:
+                    fails.append(f'it{it} {tag}.{k}: relative L2 {rel:.3e} (bound {grad_rel})')
+                if abs(nrm - 1) >= grad_norm:
+                    fails.append(f'it{it} {tag}.{k}: norm ratio {nrm:.4f}')
         report.append(f'it{it} worst gradient relL2 {worst:.3e}')
     # ---- post-step state: weights inside the sign-flip envelope and mostly tight; BatchNorm buffers; counters exact
     for tag, net in (('G', G), ('D', D)):
@@ -131,11 +186,15 @@ def test_bf16_full_width_trainer_matches_reference_fixture(nc, mode, capsys):
             a = v if ref.shape == v.shape else _sample(v, m['wsample'])
             d = np.abs(a.astype(np.float64) - ref)
             if 'running' in k:
-                close(a, ref, rtol=2e-2, atol=2e-3, what=f'{tag}.{k}')
+                if not (d <= max(atol, 1e-5) + max(rtol, 2e-3) * np.abs(ref)).all():
+                    fails.append(f'{tag}.{k}: max diff {d.max():.3e} (ref max {np.abs(ref).max():.3e})')
             else:
-                assert d.max() <= 2.05 * m['lr'] * m['iters'] + 1e-6, f'{tag}.{k}: max diff {d.max():.3e} exceeds the sign-flip envelope'
-                tight = float((d <= 0.25 * m['lr'] * m['iters']).mean())
-                report.append(f'final {tag}.{k:16s} max diff {d.max():.2e}  within 0.25*lr*iters: {tight:.4f}')
-                assert tight >= 0.9, f'{tag}.{k}: only {tight:.3f} of the entries within 0.25 lr per step'
+                frac = float((d <= 0.25 * m['lr'] * m['iters']).mean())
+                report.append(f'final {tag}.{k:16s} max diff {d.max():.2e}  within 0.25*lr*iters: {frac:.4f}')
+                if d.max() > 2.05 * m['lr'] * m['iters'] + 1e-6:
+                    fails.append(f'{tag}.{k}: max diff {d.max():.3e} exceeds the sign-flip envelope')
+                if frac < tight:
+                    fails.append(f'{tag}.{k}: only {frac:.3f} of the entries within 0.25 lr per step')
     with capsys.disabled():
-        print(f'\n[full-width bf16 parity nc={nc} {mode}]\n  ' + '\n  '.join(report))
+        print(f'\n[full-width {dtype} parity nc={nc} {mode}]\n  ' + '\n  '.join(report))
+    assert not fails, '\n'.join(fails)
