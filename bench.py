@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Benchmark of the DCGAN adversarial training step (G+D iteration of train_gan.py:121-150) on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B] [--dtype bf16|fp32] [--nc 1|3]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B | --global-batch G] [--dtype bf16|fp32]
+                    [--nc 1|3] [--check]
 
 N>1 is launched by the driver as `python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...`
 (one rank per GPU, NCCL).  Rank 0 prints ONE JSON line.
@@ -10,11 +11,16 @@ Workload (BASELINE.json configs[1]): DCGAN nz=100, ngf=ndf=64, nc=1, batch 512 p
 accumulate, synthetic uniform[-1,1] images.  NOTE: BASELINE.json says "64x64"; the reference architecture is
 hard-wired to 224x224 (dcgan.py:26,84; a 64x64 input raises in Discriminator), so every number is at 224x224.
 
-metric  = training images/s over all ranks (weak scaling: per-GPU batch fixed).
+metric  = training images/s over all ranks.  Default: weak scaling, per-GPU batch fixed at 512 (configs[1] per GPU).
+          --global-batch G (BASELINE.json configs[2] uses 4096): strong scaling, per-GPU batch G / N, `"scaling": "strong"`.
+--check = before timing, every rank verifies the data-parallel invariants (replicas bit-identical after the steps, gradients
+          equal to the sum over ranks) and the line carries `"dp_check": "ok"`; a violation aborts the run.
 value   = device-timed (CUDA events, max over ranks), inputs resident in HBM.
 e2e     = same metric through DCGANTrainer.step with HOST inputs: every step copies the real batch and the noise
           from pinned host memory and reads the 5 history scalars back.
-roofline= the dominant kernel (the D3 conv forward, M=B*196 K=2048 N=256) timed alone with CUDA events.
+roofline= the dominant kernel class (conv_gemm_tc_kernel): best case (the D3 conv forward, M=B*196 K=2048 N=256, timed alone with
+          CUDA events, L2 flushed) and `class_frac`: the class's 24 launches weighted by their in-step durations (CUPTI pass after
+          the timed region; never inside it).
 cpu_baseline / --impl reference = the reference's CPU path (oracle/torch_cpu_port.py, stock torch.nn on all host
           threads) on a bounded sample (batch 64 per step) of the same workload.
 """
@@ -100,8 +106,11 @@ def run_reference(args):
     sys.path.insert(0, os.path.join(ROOT, 'oracle'))
     import torch
     import torch_cpu_port as port
-    sample_batch = 64
-    r = port.time_cpu_steps(batch=sample_batch, steps=args.steps, warmup=args.warmup, nc=args.nc)
+    # each step = one G+D iteration on a bounded sample of the batch (64 images: BASELINE configs[0]; ~0.7 s on 16 cores), smaller
+    # when many steps are asked for, so that the whole run stays within a few minutes
+    sample_batch = 64 if args.steps <= 100 else 16
+    steps = args.steps
+    r = port.time_cpu_steps(batch=sample_batch, steps=steps, warmup=min(args.warmup, 2), nc=args.nc, threads=port.host_threads())
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': r['images_per_s'], 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': r['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
@@ -109,7 +118,8 @@ def run_reference(args):
         'config': {'workload': f'DCGAN train step nz=100 ngf=ndf=64 nc={args.nc} 224x224 (reference is hard-wired to 224x224, not 64x64)',
                    'per_gpu_batch': args.batch, 'sample': f'each step = one G+D iteration on a {sample_batch}-image sample of the batch'},
         'cpu_baseline': {'value': r['images_per_s'], 'unit': UNIT, 'cores': r['threads'], 'kind': 'port',
-                         'sample': f'{args.steps} iterations x batch {sample_batch} (oracle/torch_cpu_port.py: stock torch.nn CPU path of dcgan.py/train_gan.py)'},
+                         'sample': f'{steps} iterations x batch {sample_batch} after {min(args.warmup, 2)} warm-up (oracle/torch_cpu_port.py: stock torch.nn CPU '
+                                   'path of dcgan.py/train_gan.py; a PORT, /root/reference does not exist on the GPU box)'},
         'e2e': {'value': r['images_per_s'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0, 'host': {'nproc': os.cpu_count(), 'torch_threads': torch.get_num_threads()},
     }
@@ -199,9 +209,108 @@ def time_dominant_kernel(pkg, torch, batch, peaks, iters=20):
     return {'bound': 'tensor', 'kernel': 'conv_gemm_tc_kernel<256,64,4,1>: conv2d_fprop D3 + BatchNorm statistics (M=B*196, K=2048, N=256), bf16 tcgen05, '
                                          'timed alone with CUDA events on the launching stream, L2 flushed',
             'achieved': ach, 'peak': peaks['tf_burst'], 'unit': 'TFLOP/s', 'frac': ach / peaks['tf_burst'],
-            'traffic': 127.2e6, 'traffic_source': 'dram__bytes_read.sum + dram__bytes_write.sum of this launch in profiles/r01_g_hot_kernels.md (ncu --set full); '
-                                                  'algorithmic bytes 154.1e6 (input 102.8e6 + output 51.4e6; part of the output is still in L2 when the kernel ends)',
+            'traffic': None, 'traffic_note': 'not measurable inside this run (needs ncu); the ncu --set full capture of this launch is in profiles/ '
+                                             '(dram__bytes_read.sum + dram__bytes_write.sum per launch); algorithmic bytes 154.1e6 (input 102.8e6 + output 51.4e6)',
             'ms_per_launch': ms, 'peak_source': peaks['src'] + ' (burst: kernel timed alone)', 'more': more}
+
+
+def kernel_breakdown(torch, step_fn, steps=2):
+    """Per-kernel GPU time of `steps` replayed iterations through CUPTI (torch.profiler), run AFTER the timed region.
+    Returns {kernel name: (launches per step, microseconds per step)}."""
+    import collections
+    import re
+    from torch.profiler import ProfilerActivity, profile
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for _ in range(steps):
+            step_fn()
+        torch.cuda.synchronize()
+    agg = collections.defaultdict(lambda: [0, 0.0])
+    for e in prof.events():
+        if e.device_type == torch.autograd.DeviceType.CUDA:
+            name = re.sub(r'\(.*', '', e.name.replace('(anonymous namespace)::', '')).replace('void b200gan::', '').replace('b200gan::', '')
+            agg[name[:96]][0] += 1
+            agg[name[:96]][1] += e.device_time if hasattr(e, 'device_time') else e.cuda_time
+    return {k: (n / steps, t / steps) for k, (n, t) in agg.items()}
+
+
+# 2*MAC of one k4 s2 p1 layer-operation of D1-D4 / G1-G4 per image (SURVEY.md 8a: 102.76 MMAC each)
+LAYER_OP_FLOP = 2 * 102.76e6
+# launches per iteration of each tcgen05 kernel family (DESIGN.md section 4): the generic kernel serves D2-D4 fprop (x3 passes) and
+# dgrad (x3), G1-G3 fprop and dgrad; the halo-tile kernels D1 fprop (x3) / dgrad (x3), G4 fprop / dgrad; wgrad D1-D4 (x2) + G1-G4
+TC_CLASS_LAUNCHES = {'conv_gemm_tc_kernel': 24, 'conv_up4_tc_kernel': 4, 'conv_down4_tc_kernel': 4, 'conv_wgrad_tc_kernel': 12}
+
+
+def class_fractions(breakdown, batch, peaks):
+    """Tensor-core kernel classes weighted over ALL their launches in the step: FLOPs of the class / its summed in-step duration,
+    against the sustained bf16 peak (the kernels run back to back inside a long step)."""
+    out = {}
+    for cls, launches in TC_CLASS_LAUNCHES.items():
+        rows = [(k, v) for k, v in breakdown.items() if k.startswith(cls)]
+        n = sum(v[0] for _, v in rows)
+        us = sum(v[1] for _, v in rows)
+        if not rows or us <= 0:
+            continue
+        tf = launches * LAYER_OP_FLOP * batch / (us * 1e-6) / 1e12
+        out[cls] = {'launches_per_step': n, 'expected_launches': launches, 'us_per_step': us, 'tflops': tf,
+                    'frac_of_sustained_peak': tf / peaks['tf_sustained'], 'frac_of_burst_peak': tf / peaks['tf_burst']}
+    return out
+
+
+def dp_check(torch, dist, tr, world, rank, B, nz, nc):
+    """Data-parallel invariants, asserted on every rank before the timed region (driver-visible multi-GPU correctness):
+      1. after the exchange, every rank holds the SAME gradient arena, and it equals the sum over ranks of the local gradients
+         (the local ones are recomputed with the exchange disabled and summed with torch.distributed as an independent path);
+      2. after two full steps (kernel by kernel, then graph replay) the weights and Adam moments are bit-identical on all ranks."""
+    import gan_enhanced_pneumonia_classifier_b200.trainer as T
+    gen = torch.Generator(device='cuda').manual_seed(1234 + rank)
+    real = torch.rand((B, nc, 224, 224), device='cuda', generator=gen) * 2 - 1
+    noise = torch.randn((B, nz, 1, 1), device='cuda', generator=gen)
+    snap = [t.clone() for a in (tr.arenaG, tr.arenaD) for t in (a.param, a.exp_avg, a.exp_avg_sq)]
+    bufs = [(b, b.clone()) for net in (tr.netG, tr.netD) for b in net.buffers()]
+
+    def rewind():
+        with torch.no_grad():
+            for a, k in ((tr.arenaG, 0), (tr.arenaD, 3)):
+                a.param.copy_(snap[k]); a.exp_avg.copy_(snap[k + 1]); a.exp_avg_sq.copy_(snap[k + 2])
+                a.step_dev.zero_(); a.step = 0
+            for b, v in bufs:
+                b.copy_(v)
+        tr.refresh_packed_weights()
+
+    # (1) local D gradients without any exchange, summed through torch.distributed
+    comm, tr.comm = tr.comm, None
+    g = tr._segments(real, noise, overlap=False)
+    assert next(g) == 'D'
+    local = tr.arenaD.grad.clone()
+    g.close()
+    tr.comm = comm
+    rewind()
+    want = local.clone()
+    dist.all_reduce(want)
+    g = tr._segments(real, noise, overlap=True)
+    assert next(g) == 'D'
+    tr._exchange('D')
+    torch.cuda.synchronize()
+    got = tr.arenaD.grad.clone()
+    g.close()
+    rewind()
+    err = float((got - want).abs().max() / want.abs().max().clamp_min(1e-30))
+    assert err < 1e-5, f'rank {rank}: exchanged D gradients differ from the sum over ranks (max rel {err:.3e})'
+    ref = got.clone()
+    dist.broadcast(ref, 0)
+    assert torch.equal(ref, got), f'rank {rank}: gradient arena differs from rank 0 after the exchange'
+    # (2) replicas stay bit-identical over steps
+    for _ in range(3):
+        tr.step(real, noise)
+    torch.cuda.synchronize()
+    for a in (tr.arenaG, tr.arenaD):
+        for t in (a.param, a.exp_avg, a.exp_avg_sq):
+            r0 = t.clone()
+            dist.broadcast(r0, 0)
+            assert torch.equal(r0, t), f'rank {rank}: replica state diverged from rank 0'
+    rewind()
+    return 'ok'
 
 
 def run_ours(args):
@@ -220,15 +329,23 @@ def run_ours(args):
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     peaks = load_peaks()
     dtype = torch.bfloat16 if args.dtype == 'bf16' else torch.float32
-    B, nz, nc = args.batch, 100, args.nc
-    torch.manual_seed(0)
-    G, D = pkg.Generator(nz, nc, 64).cuda(), pkg.Discriminator(nc, 64).cuda()
-    G.apply(pkg.weights_init)
-    D.apply(pkg.weights_init)
-    if world > 1:      # replicas start from rank 0's weights, as DDP would
-        for t in list(G.state_dict().values()) + list(D.state_dict().values()):
-            dist.broadcast(t, 0)
-    tr = DCGANTrainer(G, D, lr=2e-4, beta1=0.5, dtype=dtype)
+    nz, nc = 100, args.nc
+    strong = args.global_batch is not None
+    if strong and args.global_batch % world:
+        raise SystemExit(f'--global-batch {args.global_batch} is not divisible by {world} ranks')
+    B = args.global_batch // world if strong else args.batch
+
+    def make_trainer(nc_):
+        torch.manual_seed(0)
+        G, D = pkg.Generator(nz, nc_, 64).cuda(), pkg.Discriminator(nc_, 64).cuda()
+        G.apply(pkg.weights_init)
+        D.apply(pkg.weights_init)
+        if world > 1:      # replicas start from rank 0's weights, as DDP would
+            for t in list(G.state_dict().values()) + list(D.state_dict().values()):
+                dist.broadcast(t, 0)
+        return DCGANTrainer(G, D, lr=2e-4, beta1=0.5, dtype=dtype)
+
+    tr = make_trainer(nc)
     gen = torch.Generator(device='cuda').manual_seed(1 + rank)
     real = torch.rand((B, nc, 224, 224), device='cuda', generator=gen) * 2 - 1
 
@@ -236,6 +353,8 @@ def run_ours(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    check = dp_check(torch, dist, tr, world, rank, min(B, 64), nz, nc) if (args.check and world > 1) else None
 
     # ---- device-resident timing: inputs already in HBM (the trainer's static input buffers), fresh on-device noise per step
     #      as in the reference (train_gan.py:132) -------------------------------------------------
@@ -263,13 +382,16 @@ def run_ours(args):
     # The user-facing call is DCGANTrainer.step(real, noise).  Every step copies THAT step's real batch and noise from pinned
     # host memory (on a copy stream, into one of two staging buffers, so the transfer of step i+1 overlaps the kernels of
     # step i: plain double buffering, what a DataLoader with pin_memory + non_blocking copies gives) and reads the five
-    # history scalars back to pinned host memory.
-    real_h = torch.empty((B, nc, 224, 224), dtype=torch.float32).pin_memory()
+    # history scalars back to pinned host memory.  The host batch is bf16: the first convolution rounds the image to bf16
+    # for its tensor-core operand anyway (bit-identical results, test_gpu_step.py), so shipping fp32 only doubles the PCIe /
+    # host-memory traffic that eight ranks share.
+    e2e_dt = torch.bfloat16 if dtype == torch.bfloat16 else torch.float32
+    real_h = torch.empty((B, nc, 224, 224), dtype=e2e_dt).pin_memory()
     real_h.copy_(real.cpu())
     noise_h = [torch.empty((B, nz, 1, 1), dtype=torch.float32).pin_memory() for _ in range(2)]
     hist_h = torch.empty(5, dtype=torch.float32).pin_memory()
-    static_real, static_noise = tr.input_buffers(real.shape, torch.float32, (B, nz, 1, 1))
-    stage_r = [torch.empty_like(real) for _ in range(2)]
+    static_real, static_noise = tr.input_buffers(real.shape, e2e_dt, (B, nz, 1, 1))
+    stage_r = [torch.empty((B, nc, 224, 224), device='cuda', dtype=e2e_dt) for _ in range(2)]
     stage_n = [torch.empty((B, nz, 1, 1), device='cuda') for _ in range(2)]
     copied = [torch.cuda.Event() for _ in range(2)]
     consumed = [torch.cuda.Event() for _ in range(2)]
@@ -300,12 +422,13 @@ def run_ours(args):
                 enqueue_copy(i + 1)
             hist_h.copy_(tr.step(static_real, static_noise), non_blocking=True)
 
-    e2e_loop(2)
+    e2e_loop(3)                     # first call for this input dtype runs kernel by kernel, second captures, third replays
     barrier()
+    e2e_steps = args.steps
     t0 = time.perf_counter()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
-    e2e_loop(args.steps)
+    e2e_loop(e2e_steps)
     f1.record()
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
@@ -315,31 +438,72 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = t.tolist()
 
+    # ---- after the timed regions (never inside): per-kernel breakdown of replayed steps, the RGB configuration, the CPU baseline
+    breakdown = kernel_breakdown(torch, lambda: tr.step(in_real, in_noise.normal_(generator=gen))) if rank == 0 else None
+    barrier()
+    rgb = None
+    if nc == 1 and not args.no_rgb and not strong:
+        del tr, stage_r, static_real
+        torch.cuda.empty_cache()
+        tr3 = make_trainer(3)
+        real3 = torch.rand((B, 3, 224, 224), device='cuda', generator=gen) * 2 - 1
+        n3 = torch.empty((B, nz, 1, 1), device='cuda')
+        for _ in range(3):
+            tr3.step(real3, n3.normal_(generator=gen))
+        barrier()
+        k3 = max(5, min(args.steps, 30))
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(k3):
+            tr3.step(real3, n3.normal_(generator=gen))
+        g1.record()
+        barrier()
+        t3 = torch.tensor([g0.elapsed_time(g1)], device='cuda', dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t3, op=dist.ReduceOp.MAX)
+        rgb = {'nc': 3, 'note': 'the CLI default (train_gan.py --num-channels 3), the only configuration generate_synthetic.py loads',
+               'value': B * world * k3 / (t3.item() * 1e-3), 'unit': UNIT, 'ms_per_step': t3.item() / k3, 'steps': k3}
+
     if rank == 0:
         value = B * world * args.steps / (ms * 1e-3)
-        e2e = B * world * args.steps / (ms_e2e * 1e-3)
+        e2e = B * world * e2e_steps / (ms_e2e * 1e-3)
         roof = time_dominant_kernel(pkg, torch, B, peaks)
+        cls = class_fractions(breakdown, B, peaks)
+        if 'conv_gemm_tc_kernel' in cls:
+            roof['class_frac'] = cls['conv_gemm_tc_kernel']['frac_of_sustained_peak']
+            roof['class_note'] = ('conv_gemm_tc_kernel over all its launches of one iteration (fused epilogues included), FLOPs / summed in-step '
+                                  'durations (CUPTI, after the timed region) against the SUSTAINED bf16 peak; `frac` above is the best single launch')
+        sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+        import torch_cpu_port as port
         cpu = None
-        if world == 1 and not args.no_cpu_baseline:
-            sys.path.insert(0, os.path.join(ROOT, 'oracle'))
-            import torch_cpu_port as port
-            r = port.time_cpu_steps(batch=64, steps=3, warmup=1, nc=nc)
+        if not args.no_cpu_baseline:
+            r = port.time_cpu_steps(batch=64, steps=3, warmup=1, nc=nc, threads=port.host_threads())
             cpu = {'value': r['images_per_s'], 'unit': UNIT, 'cores': r['threads'], 'kind': 'port',
-                   'sample': '3 iterations x batch 64 after 1 warm-up (oracle/torch_cpu_port.py: stock torch.nn CPU path of dcgan.py/train_gan.py)'}
+                   'sample': '3 iterations x batch 64 after 1 warm-up (oracle/torch_cpu_port.py: stock torch.nn CPU path of dcgan.py/train_gan.py; '
+                             'a PORT: /root/reference does not exist on the GPU box)'}
+        top = sorted(breakdown.items(), key=lambda kv: -kv[1][1])[:12]
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
-            'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'strong' if strong else 'weak', 'vs_baseline': None,
             'dtype': args.dtype, 'data': 'synthetic',
             'config': {'workload': f'DCGAN train step nz=100 ngf=ndf=64 nc={nc} 224x224 (reference is hard-wired to 224x224, not 64x64)',
                        'per_gpu_batch': B, 'global_batch': B * world, 'parallelism': f'dp{world}', 'batchnorm': 'local (per-rank) statistics',
+                       'gradient_exchange': 'none (1 GPU)' if world == 1 else 'bucketed NCCL all-reduce on the library\'s communicator, captured in '
+                                                                              'the iteration graph, overlapped with the backward pass',
                        'l2': 'per-step working set (several GB of activations) far exceeds the 126 MB L2; no flush needed',
                        'algo': os.environ.get('B200GAN_ALGO', 'auto')},
             'model_flops_frac_of_peak': value / world * FLOP_PER_IMAGE[nc] / 1e12 / peaks['tf_sustained'],
-            'roofline': roof, 'cpu_baseline': cpu,
-            'e2e': {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': real_h.numel() * 4 + noise_h[0].numel() * 4, 'd2h_bytes_per_step': 20,
-                    'ms_per_step': ms_e2e / args.steps},
+            'roofline': roof, 'tensor_core_classes': cls, 'cpu_baseline': cpu,
+            'e2e': {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': real_h.numel() * real_h.element_size() + noise_h[0].numel() * 4,
+                    'd2h_bytes_per_step': 20, 'ms_per_step': ms_e2e / e2e_steps, 'host_dtype': str(e2e_dt).replace('torch.', '')},
             'gpu_launches': launches, 'clocks': clocks, 'last_history': dict(zip(['errD', 'errG', 'D_x', 'D_G_z1', 'D_G_z2'], last)),
+            'kernel_time_ms_per_step': sum(v[1] for v in breakdown.values()) / 1e3,
+            'top_kernels': [{'kernel': k, 'launches_per_step': v[0], 'us_per_step': round(v[1], 1)} for k, v in top],
         }
+        if rgb is not None:
+            line['more_configs'] = [rgb]
+        if check is not None:
+            line['dp_check'] = check
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -348,12 +512,15 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=10)
-    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--steps', type=int, default=200, help='timed iterations (default: ~2 s of work, so that the clocks line shows the power-capped steady state)')
+    ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=512, help='per-GPU batch')
     ap.add_argument('--dtype', default='bf16', choices=['bf16', 'fp32'])
     ap.add_argument('--nc', type=int, default=1, choices=[1, 3], help='image channels: 1 = the benchmark workload (BASELINE.json), 3 = the CLI default')
+    ap.add_argument('--global-batch', type=int, default=None, help='strong scaling: total batch over all ranks (BASELINE configs[2]: 4096)')
+    ap.add_argument('--check', action='store_true', help='N>1: assert the data-parallel invariants on every rank before timing')
+    ap.add_argument('--no-rgb', action='store_true', help='skip the additional nc=3 measurement (more_configs)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':

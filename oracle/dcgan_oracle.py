@@ -252,7 +252,7 @@ class Net:
     `storage`: None (the reference's fp32 arithmetic), or a rounding function (e.g. `bf16_round`) applied wherever the B200
     build's bf16 mode STORES a tensor: network input as read by the first convolution, the multiplicand copy of every conv
     weight (the fp32 masters stay exact; layers in `fp32_weight_layers` multiply by the fp32 weights), every convolution
-    output, every activation output, every activation-backward result dz, every BatchNorm-backward result dy, and the
+    output that feeds a BatchNorm, every activation output, every activation-backward result dz, every BatchNorm-backward result dy, and the
     gradient handed out of the network.  Accumulation stays wide, statistics are those of the STORED tensors.  This is the
     model the bf16 tensor-core path is held to tightly (tests/test_gpu_fullsize.py); how far that model sits from the fp32
     reference is a property of bf16 storage, not of the kernels."""
@@ -278,7 +278,9 @@ class Net:
             w = self.sd[f'main.{conv_i}.weight']
             w = w if i in self.fp32_weight_layers else q(w)
             y = convT2d_fprop(a, w, s, p) if self.transposed else conv2d_fprop(a, w, s, p)
-            y = y if i in self.fp32_output_layers else q(y)
+            # a convolution output is stored (rounded) only where BatchNorm needs its statistics; without BatchNorm the activation
+            # rides on the convolution's epilogue and only the activation output is stored
+            y = q(y) if bn_i is not None else y
             xhat = invstd = None
             if bn_i is not None:
                 g, b = self.sd[f'main.{bn_i}.weight'], self.sd[f'main.{bn_i}.bias']

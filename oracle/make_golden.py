@@ -25,7 +25,9 @@ Fixtures
       the configuration bench.py times, at a batch the CPU finishes in seconds: full-size nets, batch 32 (BatchNorm is well
       conditioned: >= 1568 samples per channel), 2 iterations; as above, but every gradient / post-step tensor is kept as its
       L2 norm plus a strided sample of up to 4096 entries (relative-L2 parity of the bf16 tensor-core path is measured on
-      those samples), small tensors (<= 4096 entries, incl. every BatchNorm vector) in full.
+      those samples), small tensors (<= 4096 entries, incl. every BatchNorm vector) in full.  `bf16_model.*`: the same first
+      iteration by the numpy oracle with bf16 STORAGE rounding (dcgan_oracle.Net(storage=bf16_round)): its history scalars and
+      the relative L2 distance of each of its gradient tensors from the reference's -- what bf16 storage costs by itself.
 """
 from __future__ import annotations
 
@@ -93,7 +95,7 @@ def reference_step(dcgan, netG, netD, optG, optD, real, noise):
                 grads_D=gradsD, grads_G=gradsG)
 
 
-def make_step_fixture(dcgan, name, nz, fm, nc, batch, iters, seed, full=False, sample=64, wsample=256, fake_stride=7):
+def make_step_fixture(dcgan, name, nz, fm, nc, batch, iters, seed, full=False, sample=64, wsample=256, fake_stride=7, bf16_model=False):
     rng = np.random.RandomState(seed)
     sdG = orc.init_state(orc.generator_plan(nz, nc, fm), True, rng)
     sdD = orc.init_state(orc.discriminator_plan(nc, fm), False, rng)
@@ -127,6 +129,23 @@ def make_step_fixture(dcgan, name, nz, fm, nc, batch, iters, seed, full=False, s
                 for net in ('grads_D', 'grads_G'):
                     for k, v in r[net].items():
                         out[f'it{it}.{net}.{k}'] = v
+    if bf16_model:
+        # Calibration of the bf16 comparison: how far does IDEAL bf16 storage (the numpy oracle rounding to bf16 wherever the CUDA path
+        # stores bf16, wide accumulation everywhere) sit from the reference's fp32 gradients of the first iteration?  With hard ReLU /
+        # LeakyReLU branches that distance is not 2^-9: pre-activations within rounding distance of zero change branch.  The CUDA bf16
+        # path is held to a small multiple of these per-tensor numbers (tests/test_gpu_fullsize.py).
+        rng2 = np.random.RandomState(seed)
+        oG = orc.GeneratorOracle(nz, nc, fm, orc.init_state(orc.generator_plan(nz, nc, fm), True, rng2), storage=orc.bf16_round)
+        oD = orc.DiscriminatorOracle(nc, fm, orc.init_state(orc.discriminator_plan(nc, fm), False, rng2), storage=orc.bf16_round)
+        r = orc.train_iteration(oG, oD, orc.AdamOracle(orc.param_keys(oG.plan), 2e-4, 0.5), orc.AdamOracle(orc.param_keys(oD.plan), 2e-4, 0.5),
+                                real, noises[0])
+        for k in ('errG', 'errD', 'D_x', 'D_G_z1', 'D_G_z2'):
+            out[f'bf16_model.it0.{k}'] = np.float64(r[k])
+        for net in ('grads_D', 'grads_G'):
+            for k, v in r[net].items():
+                a = v.reshape(-1)[::max(1, v.size // sample)][:sample].astype(np.float64)
+                ref = out[f'it0.{net}.{k}.sample'].astype(np.float64)
+                out[f'bf16_model.it0.{net}.{k}.rel_l2'] = np.float64(np.linalg.norm(a - ref) / np.linalg.norm(ref))
     for tag, net in (('G', netG), ('D', netD)):
         for k, v in to_np(net.state_dict()).items():
             if full and v.size > 4096:
@@ -234,10 +253,10 @@ def main():
         make_step_fixture(dcgan, 'step_full_nc1.npz', nz=100, fm=64, nc=1, batch=2, iters=1, seed=300, full=True)
     if want('step_full_b32_nc1.npz'):
         make_step_fixture(dcgan, 'step_full_b32_nc1.npz', nz=100, fm=64, nc=1, batch=32, iters=2, seed=500, full=True, sample=4096, wsample=4096,
-                          fake_stride=13)
+                          fake_stride=13, bf16_model=True)
     if want('step_full_b32_nc3.npz'):
         make_step_fixture(dcgan, 'step_full_b32_nc3.npz', nz=100, fm=64, nc=3, batch=32, iters=2, seed=600, full=True, sample=4096, wsample=4096,
-                          fake_stride=13)
+                          fake_stride=13, bf16_model=True)
     if want('main_small_nc3.npz'):
         make_main_fixture(ref_src, 'main_small_nc3.npz')
 

@@ -99,8 +99,19 @@ class CpuStepper:
         return errD.item(), errG.item(), D_x, D_G_z1, D_G_z2
 
 
-def time_cpu_steps(batch=64, steps=3, warmup=1, nc=1, seed=1):
-    """images/s of the CPU path on all host threads: `steps` timed iterations at `batch` images."""
+def host_threads():
+    """The host threads this process may use (its CPU affinity mask; os.cpu_count() where affinity is not available)."""
+    import os
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def time_cpu_steps(batch=64, steps=3, warmup=1, nc=1, seed=1, threads=None):
+    """images/s of the CPU path on all host threads: `steps` timed iterations at `batch` images.  The thread count is set
+    explicitly (torchrun exports OMP_NUM_THREADS=1, which would otherwise leave the CPU arm on one thread)."""
+    torch.set_num_threads(threads or host_threads())
     torch.manual_seed(0)
     st = CpuStepper(nc=nc)
     g = torch.Generator().manual_seed(seed)

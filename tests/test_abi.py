@@ -39,6 +39,19 @@ def test_bad_arguments_fail_loudly_without_a_gpu():
         L.call('b200gan_bn_stats', ctypes.byref(v), None, None)
 
 
+def test_dp_entry_points_validate_arguments_without_a_gpu():
+    ident = (ctypes.c_ubyte * L.DP_ID_BYTES)()
+    h = ctypes.c_void_p()
+    with pytest.raises(L.B200GanError, match='bad argument'):
+        L.call('b200gan_dp_init', ctypes.cast(ident, ctypes.c_void_p), 2, 5, ctypes.byref(h))         # rank outside the world
+    with pytest.raises(L.B200GanError, match='bad argument'):
+        L.call('b200gan_dp_allreduce_bucket', None, None, 0, None)
+    with pytest.raises(L.B200GanError, match='null handle'):
+        L.call('b200gan_dp_sync', None, None)
+    L.call('b200gan_dp_destroy', None)                                                               # destroying nothing is fine
+    assert L.load().b200gan_dp_collectives(None) == 0
+
+
 def test_cuda_tensors_never_fall_back(monkeypatch):
     monkeypatch.setattr(L, '_lib', None)
     monkeypatch.setattr(L, 'LIB_PATH', '/nonexistent/libb200gan.so')

@@ -1,5 +1,8 @@
 """tcgen05 implicit-GEMM convolutions (forced with ALGO_TCGEN05, so a silent SIMT fallback cannot pass) against
-the numpy oracle (small shapes) and the fp32-accumulating SIMT kernels (every layer shape of the DCGAN)."""
+the numpy oracle AND the fp32-accumulating SIMT kernels, on every layer shape of the DCGAN (small / ragged batches).
+
+Oracle tolerance: operands are bf16-exact, the oracle accumulates in float64; the kernel accumulates in fp32 and rounds the
+result to bf16 once, so it must sit within ONE bf16 ulp (2^-8 relative) of the oracle plus the fp32 accumulation error."""
 import ctypes as C
 
 import numpy as np
@@ -53,6 +56,19 @@ def run_pair(n, ci, h, w_, co, direction):
     return dy, wt, dx_tc, dx_ref
 
 
+BF16_ULP = 2.0 ** -8
+
+
+def oracle_close(got_nhwc, ref_nchw, what):
+    """bf16 result against the float64-accumulated oracle: one bf16 ulp + fp32 accumulation noise."""
+    ref = np.ascontiguousarray(ref_nchw.transpose(0, 2, 3, 1))
+    close(got_nhwc.float().cpu().numpy(), ref, rtol=1.05 * BF16_ULP, atol=2e-5 * max(1.0, float(np.abs(ref).max())), what=what + ' vs numpy oracle')
+
+
+def nchw(t):
+    return t.float().cpu().numpy().transpose(0, 3, 1, 2)
+
+
 def report(tag, got, ref):
     g, r = got.float(), ref.float()
     err = (g - r).abs().max().item()
@@ -74,6 +90,7 @@ def test_tc_down_conv_matches_simt(case):
     report(f'down {case}', y_tc, y_ref)
     assert not torch.isnan(y_tc.float()).any()
     close(y_tc.float().cpu().numpy(), y_ref.float().cpu().numpy(), rtol=1.6e-2, atol=2e-2, what=f'down {case}')
+    oracle_close(y_tc, orc.conv2d_fprop(nchw(x), wt.cpu().numpy(), 2, 1), f'down {case}')
 
 
 @pytest.mark.parametrize('case', UP)
@@ -83,6 +100,7 @@ def test_tc_up_conv_matches_simt(case):
     report(f'up {case}', dx_tc, dx_ref)
     assert not torch.isnan(dx_tc.float()).any()
     close(dx_tc.float().cpu().numpy(), dx_ref.float().cpu().numpy(), rtol=1.6e-2, atol=2e-2, what=f'up {case}')
+    oracle_close(dx_tc, orc.conv2d_dgrad(nchw(dy), wt.cpu().numpy(), 2, 1, (2 * h, 2 * w_)), f'up {case}')
 
 
 def test_tc_against_numpy_oracle():
@@ -119,6 +137,9 @@ def test_tc_wgrad_matches_simt(case, use_ws):
     a, b = (dw_tc - base).cpu().numpy(), (dw_ref - base).cpu().numpy()
     print(f'wgrad {case}: max|diff|={np.abs(a - b).max():.4e} ref max={np.abs(b).max():.3e}')
     close(a, b, rtol=2e-3, atol=2e-3 * max(1.0, np.abs(b).max()), what=f'wgrad {case}')
+    # fp32 result (fp32 accumulation over up to n*OH*OW = 9408 terms, then `base + .` in fp32) against the float64 oracle
+    ref = orc.conv2d_wgrad(nchw(x), nchw(dy), 4, 2, 1)
+    close(a, ref, rtol=1e-4, atol=3e-5 * max(1.0, np.abs(ref).max()), what=f'wgrad {case} vs numpy oracle')
 
 
 def test_tc_wgrad_against_numpy_oracle():
