@@ -27,6 +27,7 @@ struct NcclApi {
   int (*CommInitRank)(NcclComm*, int, NcclUniqueId, int) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
   int (*CommDestroy)(NcclComm) = nullptr;
+  int (*CommAbort)(NcclComm) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
   int (*GetVersion)(int*) = nullptr;
   bool ok = false;
@@ -42,6 +43,7 @@ const NcclApi& nccl() {
     a.CommInitRank = reinterpret_cast<decltype(a.CommInitRank)>(dlsym(h, "ncclCommInitRank"));
     a.AllReduce = reinterpret_cast<decltype(a.AllReduce)>(dlsym(h, "ncclAllReduce"));
     a.CommDestroy = reinterpret_cast<decltype(a.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
+    a.CommAbort = reinterpret_cast<decltype(a.CommAbort)>(dlsym(h, "ncclCommAbort"));
     a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
     a.GetVersion = reinterpret_cast<decltype(a.GetVersion)>(dlsym(h, "ncclGetVersion"));
     a.ok = a.GetUniqueId && a.CommInitRank && a.AllReduce && a.CommDestroy && a.GetErrorString;
@@ -128,8 +130,11 @@ int b200gan_dp_destroy(b200gan_dp* dp) {
   if (dp->comm_stream) cudaStreamSynchronize(dp->comm_stream);
   int rc = 0;
   if (dp->comm && nccl().ok) {
-    const int r = nccl().CommDestroy(dp->comm);
-    if (r != kNcclSuccess) rc = nccl_fail(r, "ncclCommDestroy");
+    // ncclCommAbort, not ncclCommDestroy: destroy is collective-flavoured (it waits for the peers and for every CUDA graph that
+    // captured the communicator to be released first; measured: a rank whose captured iteration graph is still alive hangs
+    // there at interpreter exit).  All work was drained above, so aborting only frees the resources, in any order across ranks.
+    const int r = nccl().CommAbort ? nccl().CommAbort(dp->comm) : nccl().CommDestroy(dp->comm);
+    if (r != kNcclSuccess) rc = nccl_fail(r, "ncclCommAbort");
   }
   if (dp->fork) cudaEventDestroy(dp->fork);
   if (dp->join) cudaEventDestroy(dp->join);

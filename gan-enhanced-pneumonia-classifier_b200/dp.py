@@ -52,15 +52,11 @@ class DPComm:
         return int(L.load().b200gan_dp_collectives(self._h)) if self._h else 0
 
     def close(self):
+        """Release the communicator (after the CUDA graphs that captured it: DCGANTrainer.close does both in order).  Not called
+        from __del__: at interpreter shutdown the CUDA context may already be gone, and process exit releases everything anyway."""
         if self._h:
             h, self._h = self._h, C.c_void_p()
             L.call('b200gan_dp_destroy', h)
-
-    def __del__(self):
-        try:
-            self.close()
-        except Exception:      # noqa: BLE001  (interpreter shutdown)
-            pass
 
 
 class GradBuckets:

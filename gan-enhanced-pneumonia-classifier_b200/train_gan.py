@@ -323,6 +323,8 @@ def main(args):
             print(f'Error saving training history to {history_filename}: {e}')
         plot_gan_losses(history, os.path.join(args.figures_dir, 'gan_loss_curve.png'))
     if world > 1:
+        if trainer is not None:
+            trainer.close()
         torch.distributed.destroy_process_group()
     return history
 

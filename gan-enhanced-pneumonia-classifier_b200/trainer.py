@@ -265,6 +265,15 @@ class DCGANTrainer:
         # errD = errD_real + errD_fake (train_gan.py:140); D_x, D_G_z1, D_G_z2 are mean probabilities
         return torch.stack([m_real[0] + m_fake[0], m_g[0], m_real[1], m_fake[1], m_g[1]])
 
+    def close(self):
+        """Data parallel: drop the captured graphs (they hold the communicator's captured collectives), drain the device, release the
+        library's NCCL communicator.  Call before torch.distributed.destroy_process_group(); a no-op on one GPU."""
+        self._graphs.clear()
+        if self.comm is not None:
+            torch.cuda.synchronize()
+            self.comm.close()
+            self.comm = self.bucketsD.comm = self.bucketsG.comm = None
+
     def refresh_packed_weights(self):
         """Re-derive the cached bf16 weight repacks from the fp32 masters.  Call after the weights were changed from OUTSIDE the
         trainer (`load_state_dict`, manual edits): the repacks are otherwise only refreshed after the trainer's own Adam updates,

@@ -52,6 +52,7 @@ def _worker(rank, port, out_dir, use_graph):
             hist.append(tr.step(torch.from_numpy(real).cuda(), torch.from_numpy(noise).cuda()).cpu().numpy())
         np.savez(os.path.join(out_dir, f'rank{rank}.npz'), hist=np.stack(hist), collectives=tr.bucketsD.collectives + tr.bucketsG.collectives,
                  **{f'G.{k}': v.cpu().numpy() for k, v in G.state_dict().items()}, **{f'D.{k}': v.cpu().numpy() for k, v in D.state_dict().items()})
+        tr.close()
     finally:
         dist.destroy_process_group()
 
