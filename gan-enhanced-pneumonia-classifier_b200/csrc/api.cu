@@ -17,6 +17,18 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+int num_sms() {
+  static std::atomic<int> cached[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  int v = cached[dev].load(std::memory_order_relaxed);
+  if (v == 0) {
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    cached[dev].store(v, std::memory_order_relaxed);
+  }
+  return v;
+}
+
 int cuda_fail(cudaError_t e, const char* what) {
   set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
   return B200GAN_ERR_CUDA;

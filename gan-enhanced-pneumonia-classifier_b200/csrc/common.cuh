@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "../../include/b200gan.h"
 
 namespace b200gan {
@@ -74,7 +76,28 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-constexpr int kNumSMs = 148;   // B200
+// SM count of the CURRENT device (B200: 148), read from the driver once per device
+int num_sms();
+#define kNumSMs (::b200gan::num_sms())
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device, per-function attribute: raise it at most once per (device, kernel,
+// size), from any host thread (the C ABI promises re-entrancy per device; a plain `static int` guard was neither).
+template <auto Kernel>                                       // the kernel FUNCTION is the template argument: one guard array per kernel
+static inline cudaError_t ensure_dynamic_smem(int smem) {
+  constexpr int kMaxDevices = 64;
+  static std::atomic<int> configured[kMaxDevices];          // zero-initialised
+  const auto kernel = Kernel;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= kMaxDevices) return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (configured[dev].load(std::memory_order_acquire) >= smem) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);      // idempotent: a race only repeats the call
+  if (e != cudaSuccess) return e;
+  int cur = configured[dev].load(std::memory_order_relaxed);
+  while (cur < smem && !configured[dev].compare_exchange_weak(cur, smem, std::memory_order_release)) {}
+  return cudaSuccess;
+}
 
 // 8 bf16 <-> 8 floats through one 16-byte vector
 __device__ __forceinline__ void unpack8(const uint4& t, float* v) {

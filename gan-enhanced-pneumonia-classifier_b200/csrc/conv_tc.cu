@@ -19,29 +19,6 @@
 namespace b200gan {
 
 // ---------------------------------------------------------------------------------------------------
-struct TcConvParams {
-  int tiles_w, tiles_h, tiles_n;     // tiles of the GEMM-row pixel space (TW x TH x TN pixels each, product 128)
-  int tw_log2, th_log2;              // log2(TW), log2(TH)
-  int a_mul;                         // input coordinate = tile origin * a_mul + tap offset
-  int taps;                          // 16 (DOWN) or 4 (UP)
-  int chunks;                        // Cin / KC
-  int n_tiles, ncls, num_tiles;      // Cout tiles, parity classes (1 or 4), total tiles = spatial * n_tiles * ncls
-  int8_t tap_dh[4][16], tap_dw[4][16];   // [class][tap]
-  int QH, QW, NB;                    // valid extent of the pixel space (rows beyond are discarded)
-  __nv_bfloat16* out;
-  int64_t o_sn, o_sh, o_sw;
-  int o_mul;                         // output pixel = q*o_mul + class parity
-  int cout;
-  // epilogue fusions (template EPI): 1 = BatchNorm statistics of the result, 2 = previous layer's activation backward +
-  // BatchNorm-backward sums, 3 = previous layer's activation backward only (no BatchNorm below)  (b200gan_fuse.bn_sums / prev_*)
-  double* sums;                      // [2*cout], zeroed by the host wrapper
-  const __nv_bfloat16* prev_y;       // same dense NHWC layout as out
-  const float *prev_scale, *prev_shift, *prev_mean, *prev_invstd;
-  float prev_neg;                    // act'(z) for z <= 0: 0 (ReLU), slope (LeakyReLU), 1 (none)
-  // shared-memory plan (bytes from the 1024-aligned base): [stages][resident weights][barriers][channel accumulators]
-  int nstages, stage_stride, off_res, off_bar;
-  int resident;                      // 1: every weight tile of the layer stays in shared memory for the CTA's lifetime
-};
 
 
 template <int BN, int KC, int STAGES>
@@ -365,11 +342,7 @@ static int launch_tc_epi(const CUtensorMap& ma, const CUtensorMap& mb, TcConvPar
   p.off_bar = p.off_res + res_bytes;
   // channel accumulators / coefficients live behind the barrier block (EPI 1/2), sized by the layer's channel count
   const int smem = 1024 + p.off_bar + S::BAR_BYTES + ((EPI == 0 || EPI == 3) ? 0 : p.cout * 8 + (EPI == 2 ? p.cout * 16 : 0) + 16);
-  static int configured = 0;
-  if (configured < smem) {
-    B200_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, KC, STAGES, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = smem;
-  }
+  B200_CUDA((ensure_dynamic_smem<conv_gemm_tc_kernel<BN, KC, STAGES, EPI>>(smem)));
   conv_gemm_tc_kernel<BN, KC, STAGES, EPI><<<grid, kTcThreads, smem, st>>>(ma, mb, p);
   B200_LAUNCH_CHECK("conv_gemm_tc_kernel");
   return 0;
@@ -471,6 +444,21 @@ static int tc_conv_common(const b200gan_conv* cv, const b200gan_view* in, const 
   const int ctas = p.num_tiles < per_sm * kNumSMs ? p.num_tiles : per_sm * kNumSMs;
   dim3 grid((unsigned)ctas, 1, 1);
   const int e = epi.mode;
+  // wide layers: a CTA pair per 256 x 256 tile (tcgen05 cta_group::2, conv_tc_pair.cu) -- each CTA stages half of the weight tile
+  static const bool pair_ok = getenv("B200GAN_NO_PAIR") == nullptr;
+  if (pair_ok && KC == 64 && BN == 256 && p.tiles_w * p.tiles_h * p.tiles_n >= 2) {
+    CUtensorMap mbh;
+    const int ktot = p.taps * cin;
+    cuuint64_t gdim[3] = {(cuuint64_t)ktot, (cuuint64_t)cout, (cuuint64_t)p.ncls};
+    cuuint64_t gstr[2] = {(cuuint64_t)ktot * 2, (cuuint64_t)ktot * cout * 2};
+    cuuint32_t box[3] = {64, 128, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&mbh, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(wpacked), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(B half) failed: %d", (int)r); return B200GAN_ERR_CUDA; }
+    const int t = launch_tc_pair(ma, mbh, p, e, st);
+    if (t <= 0) return t;
+  }
   if (KC == 64) {
     if (BN == 256) return launch_tc<256, 64, 4>(ma, mb, p, e, grid, st);   // 4 x 48 KB, one CTA per SM
     if (BN == 128) return launch_tc<128, 64, 3>(ma, mb, p, e, grid, st);   // 3 x 32 KB

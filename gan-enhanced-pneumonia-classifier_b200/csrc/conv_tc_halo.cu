@@ -347,11 +347,7 @@ conv_up4_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 template <int EPI>
 static int launch_up4(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& my, const CUtensorMap& mo, const Up4Params& p, int grid, int smem,
                       cudaStream_t st) {
-  static int configured = 0;
-  if (configured < smem) {
-    B200_CUDA(cudaFuncSetAttribute(conv_up4_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = smem;
-  }
+  B200_CUDA((ensure_dynamic_smem<conv_up4_tc_kernel<EPI>>(smem)));
   conv_up4_tc_kernel<EPI><<<grid, kHaloThreads, smem, st>>>(ma, mb, my, mo, p);
   B200_LAUNCH_CHECK("conv_up4_tc_kernel");
   return 0;
@@ -688,11 +684,7 @@ conv_down4_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
 template <int EPI>
 static int launch_down4(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& my, const CUtensorMap& mo, const Down4Params& p, int grid,
                         int smem, cudaStream_t st) {
-  static int configured = 0;
-  if (configured < smem) {
-    B200_CUDA(cudaFuncSetAttribute(conv_down4_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = smem;
-  }
+  B200_CUDA((ensure_dynamic_smem<conv_down4_tc_kernel<EPI>>(smem)));
   conv_down4_tc_kernel<EPI><<<grid, kHaloThreads, smem, st>>>(ma, mb, my, mo, p);
   B200_LAUNCH_CHECK("conv_down4_tc_kernel");
   return 0;

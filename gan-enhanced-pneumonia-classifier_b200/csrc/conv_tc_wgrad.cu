@@ -218,11 +218,7 @@ __global__ void __launch_bounds__(256) wgrad_finalize_kernel(float* __restrict__
 template <int CIC, int NCO, int G, int STAGES>
 static int launch_wgrad(const CUtensorMap& mx, const CUtensorMap& mdy, const TcWgradParams& p, dim3 grid, cudaStream_t st) {
   using S = TcWgradSmem<CIC, NCO, G, STAGES>;
-  static bool configured = false;
-  if (!configured) {
-    B200_CUDA(cudaFuncSetAttribute(conv_wgrad_tc_kernel<CIC, NCO, G, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
-    configured = true;
-  }
+  B200_CUDA((ensure_dynamic_smem<conv_wgrad_tc_kernel<CIC, NCO, G, STAGES>>(S::TOTAL)));
   conv_wgrad_tc_kernel<CIC, NCO, G, STAGES><<<grid, 192, S::TOTAL, st>>>(mx, mdy, p);
   B200_LAUNCH_CHECK("conv_wgrad_tc_kernel");
   return 0;
@@ -294,11 +290,7 @@ int tc_conv_wgrad(const b200gan_conv* cv, const b200gan_view* x, const b200gan_v
   if (rc) return rc;
   if (workspace) {
     const int fsmem = 16 * (Ci + 1) * (int)sizeof(float);
-    static int fin_configured = 0;
-    if (fsmem > 48 * 1024 && fin_configured < fsmem) {
-      B200_CUDA(cudaFuncSetAttribute(wgrad_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fsmem));
-      fin_configured = fsmem;
-    }
+    if (fsmem > 48 * 1024) B200_CUDA((ensure_dynamic_smem<wgrad_finalize_kernel>(fsmem)));
     wgrad_finalize_kernel<<<(unsigned)Co, 256, fsmem, st>>>(workspace, dw, Co, Ci);
     B200_LAUNCH_CHECK("wgrad_finalize_kernel");
   }

@@ -829,11 +829,7 @@ bool thin_tma_ok(const ThinArgs& a) { return a.coarse_ref == nullptr && a.W % 16
 
 template <void (*Kernel)(const CUtensorMap, const ThinArgs)>
 int launch_thin_tma(const CUtensorMap& m, const ThinArgs& a, size_t smem, int ctas_per_sm, cudaStream_t st, const char* name) {
-  static size_t configured = 0;
-  if (configured < smem) {
-    B200_CUDA(cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  B200_CUDA((ensure_dynamic_smem<Kernel>((int)smem)));
   int grid = ctas_per_sm * kNumSMs;
   if (grid > a.num_tiles) grid = a.num_tiles;
   Kernel<<<grid, 256, smem, st>>>(m, a);
@@ -843,11 +839,7 @@ int launch_thin_tma(const CUtensorMap& m, const ThinArgs& a, size_t smem, int ct
 
 template <void (*Kernel)(const ThinArgs)>
 int launch_thin(const ThinArgs& a, size_t smem, int ctas_per_sm, cudaStream_t st, const char* name) {
-  static size_t configured = 0;            // one instance per kernel (the kernel is a template argument)
-  if (configured < smem) {
-    B200_CUDA(cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  B200_CUDA((ensure_dynamic_smem<Kernel>((int)smem)));
   int grid = ctas_per_sm * kNumSMs;
   if (grid > a.num_tiles) grid = a.num_tiles;
   Kernel<<<grid, 256, smem, st>>>(a);

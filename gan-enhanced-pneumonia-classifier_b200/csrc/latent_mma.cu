@@ -243,12 +243,10 @@ int latent_fprop_mma(const b200gan_conv* cv, const b200gan_view* z, const float*
   const int smem = KP * kCols * 2 + 64 * (KP + kZP) * 2;
   dim3 grid((z->n + 63) / 64, y->c / kCB);
   const View zv = to_view(z);
-  static int configured[2] = {0, 0};
   const int which = z->dtype == B200GAN_F32 ? 0 : 1;
-  if (configured[which] < smem) {
-    if (which == 0) B200_CUDA(cudaFuncSetAttribute(latent_fprop_mma_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    else B200_CUDA(cudaFuncSetAttribute(latent_fprop_mma_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured[which] = smem;
+  {
+    if (which == 0) B200_CUDA((ensure_dynamic_smem<latent_fprop_mma_kernel<float>>(smem)));
+    else B200_CUDA((ensure_dynamic_smem<latent_fprop_mma_kernel<__nv_bfloat16>>(smem)));
   }
   if (which == 0)
     latent_fprop_mma_kernel<float><<<grid, kLatThreads, smem, st>>>(zv, w, reinterpret_cast<__nv_bfloat16*>(y->ptr), z->n, z->c, KP, y->c);
@@ -263,12 +261,10 @@ int latent_wgrad_mma(const b200gan_conv* cv, const b200gan_view* dy, const b200g
   const int smem = 64 * kCols * 2 + 64 * (32 + kZP) * 2;
   dim3 grid(dy->c / kCB, (z->c + 31) / 32);
   const View zv = to_view(z);
-  static int configured[2] = {0, 0};
   const int which = z->dtype == B200GAN_F32 ? 0 : 1;
-  if (configured[which] < smem) {
-    if (which == 0) B200_CUDA(cudaFuncSetAttribute(latent_wgrad_mma_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    else B200_CUDA(cudaFuncSetAttribute(latent_wgrad_mma_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured[which] = smem;
+  {
+    if (which == 0) B200_CUDA((ensure_dynamic_smem<latent_wgrad_mma_kernel<float>>(smem)));
+    else B200_CUDA((ensure_dynamic_smem<latent_wgrad_mma_kernel<__nv_bfloat16>>(smem)));
   }
   if (which == 0)
     latent_wgrad_mma_kernel<float><<<grid, kLatThreads, smem, st>>>(zv, reinterpret_cast<const __nv_bfloat16*>(dy->ptr), dw, z->n, z->c, dy->c);

@@ -58,6 +58,34 @@ static inline bool nhwc_dense_bf16(const b200gan_view* v) {
          v->sn == (int64_t)v->h * v->w * v->c && (reinterpret_cast<uintptr_t>(v->ptr) & 31) == 0;      // 32 B: 256-bit epilogue accesses
 }
 
+// parameters of the generic implicit-GEMM kernels (conv_tc.cu: one CTA per tile; conv_tc_pair.cu: a CTA pair per 256-row tile)
+struct TcConvParams {
+  int tiles_w, tiles_h, tiles_n;     // tiles of the GEMM-row pixel space (TW x TH x TN pixels each, product 128)
+  int tw_log2, th_log2;              // log2(TW), log2(TH)
+  int a_mul;                         // input coordinate = tile origin * a_mul + tap offset
+  int taps;                          // 16 (DOWN) or 4 (UP)
+  int chunks;                        // Cin / KC
+  int n_tiles, ncls, num_tiles;      // Cout tiles, parity classes (1 or 4), total tiles = spatial * n_tiles * ncls
+  int8_t tap_dh[4][16], tap_dw[4][16];   // [class][tap]
+  int QH, QW, NB;                    // valid extent of the pixel space (rows beyond are discarded)
+  __nv_bfloat16* out;
+  int64_t o_sn, o_sh, o_sw;
+  int o_mul;                         // output pixel = q*o_mul + class parity
+  int cout;
+  // epilogue fusions (template EPI): 1 = BatchNorm statistics of the result, 2 = previous layer's activation backward +
+  // BatchNorm-backward sums, 3 = previous layer's activation backward only (no BatchNorm below)  (b200gan_fuse.bn_sums / prev_*)
+  double* sums;                      // [2*cout], zeroed by the host wrapper
+  const __nv_bfloat16* prev_y;       // same dense NHWC layout as out
+  const float *prev_scale, *prev_shift, *prev_mean, *prev_invstd;
+  float prev_neg;                    // act'(z) for z <= 0: 0 (ReLU), slope (LeakyReLU), 1 (none)
+  // shared-memory plan (bytes from the 1024-aligned base): [stages][resident weights][barriers][channel accumulators]
+  int nstages, stage_stride, off_res, off_bar;
+  int resident;                      // 1: every weight tile of the layer stays in shared memory for the CTA's lifetime
+};
+
+// CTA-pair kernel (conv_tc_pair.cu): 256 x 256 tiles on tcgen05.mma.cta_group::2.  `mb_half` is the weight map with a 128-row box.
+int launch_tc_pair(const CUtensorMap& ma, const CUtensorMap& mb_half, TcConvParams p, int epi, cudaStream_t st);
+
 // halo-tile kernels (conv_tc_halo.cu): return 1 when the problem is not of their shape / fusion
 int tc_conv_up4(const b200gan_view* in, const void* wpacked, const b200gan_view* out, const TcEpi& epi, cudaStream_t st);
 int tc_conv_down4(const b200gan_view* in, const void* wpacked, const b200gan_view* out, const TcEpi& epi, cudaStream_t st);

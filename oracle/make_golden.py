@@ -18,6 +18,10 @@ Fixtures
       in-memory dataset of 10 images -> batches 4,4,2; save_interval=2 so the train-mode visualisation
       forward of train_gan.py:166-169 runs 3 times).  Initial weights (torch RNG), fixed noise and
       per-iteration noise are recorded from the run; history JSON and final state dicts are the outputs.
+  wgan_small_nc1.npz / wgan_small_nc3.npz
+      the reference's WGAN-GP iteration (src/wggan.py modules and its unmodified `gradient_penalty`, op sequence of
+      src/train_wggan.py:70-92): nz=16, ngf=ndf=8, two critic updates + one generator update; recorded noise / alpha, losses,
+      gradient penalties, critic scores, every gradient and the final state dicts.
   step_full_nc1.npz
       full-size nets (nz=100, ngf=ndf=64, nc=1), batch 2, 1 iteration; scalars, D probabilities, a
       strided sample of the fake image and per-tensor checksums of grads / post-step weights.
@@ -233,6 +237,68 @@ def make_main_fixture(ref_src, name):
     print('wrote', path, os.path.getsize(path) // 1024, 'KiB', 'history:', {k: v[:3] for k, v in hist.items()})
 
 
+def make_wgan_fixture(wggan, name, nz, fm, nc, batch, critic_iters, seed, lambda_gp=10.0):
+    """The reference's WGAN-GP iteration (train_wggan.py:70-92) with its own modules and its own, unmodified `gradient_penalty`
+    (torch.autograd does the double backward); noise and the interpolation draw `alpha` (wggan.py:76) are recorded from the run."""
+    import wgan_oracle as wo
+    rng = np.random.RandomState(seed)
+    sdG = orc.init_state(wo.wgan_generator_plan(nz, nc, fm), True, rng)
+    sdD = orc.init_state(wo.critic_plan(nc, fm), False, rng)
+    netG, netD = wggan.Generator(nz, nc, fm), wggan.Discriminator(nc, fm)
+    load_state(netG, sdG)
+    load_state(netD, sdD)
+    optG = torch.optim.Adam(netG.parameters(), lr=2e-4, betas=(0.5, 0.9))
+    optD = torch.optim.Adam(netD.parameters(), lr=2e-4, betas=(0.5, 0.9))
+    real = torch.from_numpy(synthetic_real(seed + 1, batch, nc))
+    noises = synthetic_noise(seed + 2, batch * (critic_iters + 1), nz).reshape(critic_iters + 1, batch, nz, 1, 1)
+    out = dict(meta=json.dumps(dict(nz=nz, fm=fm, nc=nc, batch=batch, critic_iters=critic_iters, seed=seed, lr=2e-4, beta1=0.5, beta2=0.9,
+                                    lambda_gp=lambda_gp, real_seed=seed + 1, noise_seed=seed + 2, torch=torch.__version__)))
+    real_rand = torch.rand
+    alphas = []
+
+    def rec_rand(*a, **k):
+        t = real_rand(*a, **k)
+        alphas.append(t.detach().numpy().copy())
+        return t
+
+    for it in range(critic_iters):                       # train_wggan.py:70-85
+        netD.zero_grad()
+        d_real = netD(real)
+        d_real_loss = -d_real.mean()
+        fake = netG(torch.from_numpy(noises[it]))
+        d_fake = netD(fake.detach())
+        d_fake_loss = d_fake.mean()
+        torch.rand = rec_rand
+        try:
+            gp = wggan.gradient_penalty(netD, real.data, fake.data, torch.device('cpu'), lambda_gp=lambda_gp)
+        finally:
+            torch.rand = real_rand
+        d_loss = d_real_loss + d_fake_loss + gp
+        d_loss.backward()
+        out[f'c{it}.d_loss'], out[f'c{it}.gp'] = np.float64(d_loss.item()), np.float64(gp.item())
+        out[f'c{it}.alpha'] = alphas[-1]
+        out[f'c{it}.d_real'], out[f'c{it}.d_fake'] = d_real.detach().numpy().copy(), d_fake.detach().numpy().copy()
+        if it == 0:
+            for k, p in netD.named_parameters():
+                out[f'c{it}.grads_D.{k}'] = p.grad.detach().numpy().copy()
+        optD.step()
+    netG.zero_grad()                                     # train_wggan.py:87-92
+    fake = netG(torch.from_numpy(noises[critic_iters]))
+    g_loss = -netD(fake).mean()
+    g_loss.backward()
+    out['g_loss'] = np.float64(g_loss.item())
+    out['fake'] = fake.detach().numpy()[:, :, ::3, ::3].copy()
+    for k, p in netG.named_parameters():
+        out[f'grads_G.{k}'] = p.grad.detach().numpy().copy()
+    optG.step()
+    for tag, net in (('G', netG), ('D', netD)):
+        for k, v in to_np(net.state_dict()).items():
+            out[f'final.{tag}.{k}'] = v
+    path = os.path.join(GOLDEN_DIR, name)
+    np.savez_compressed(path, **out)
+    print('wrote', path, os.path.getsize(path) // 1024, 'KiB', 'd_loss', [float(out[f'c{i}.d_loss']) for i in range(critic_iters)], 'g_loss', float(out['g_loss']))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--ref', default='/root/reference')
@@ -259,6 +325,12 @@ def main():
                           fake_stride=13, bf16_model=True)
     if want('main_small_nc3.npz'):
         make_main_fixture(ref_src, 'main_small_nc3.npz')
+    import wggan  # the reference's file, unmodified
+    assert os.path.abspath(wggan.__file__).startswith(os.path.abspath(a.ref)), wggan.__file__
+    if want('wgan_small_nc1.npz'):
+        make_wgan_fixture(wggan, 'wgan_small_nc1.npz', nz=16, fm=8, nc=1, batch=3, critic_iters=2, seed=800)
+    if want('wgan_small_nc3.npz'):
+        make_wgan_fixture(wggan, 'wgan_small_nc3.npz', nz=16, fm=8, nc=3, batch=4, critic_iters=2, seed=900)
 
 
 if __name__ == '__main__':

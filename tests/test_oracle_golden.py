@@ -127,3 +127,42 @@ def test_torch_port_matches_fixture():
         errD, errG, D_x, z1, z2 = st.step(real, torch.from_numpy(noises[it]))
         for k, v in (('errD', errD), ('errG', errG), ('D_x', D_x), ('D_G_z1', z1), ('D_G_z2', z2)):
             close(v, g[f'it{it}.{k}'], rtol=1e-6, atol=1e-7, what=f'it{it}.{k}')
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# WGAN-GP: the numpy oracle with its hand-written double backward against the reference's
+# wggan.py + torch.autograd (fixtures from oracle/make_golden.py)
+# ---------------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('name', ['wgan_small_nc1.npz', 'wgan_small_nc3.npz'])
+def test_wgan_oracle_matches_reference_fixture(name):
+    import wgan_oracle as wo
+    g = np.load(os.path.join(GOLDEN, name))
+    m = json.loads(str(g['meta']))
+    rng = np.random.RandomState(m['seed'])
+    sdG = orc.init_state(wo.wgan_generator_plan(m['nz'], m['nc'], m['fm']), True, rng)
+    sdD = orc.init_state(wo.critic_plan(m['nc'], m['fm']), False, rng)
+    G, D = wo.WGANGenerator(m['nz'], m['nc'], m['fm'], sdG), wo.Critic(m['nc'], m['fm'], sdD)
+    optG = orc.AdamOracle(orc.param_keys(G.plan), m['lr'], m['beta1'], beta2=m['beta2'])
+    optD = orc.AdamOracle(orc.param_keys(D.plan), m['lr'], m['beta1'], beta2=m['beta2'])
+    real = synthetic_real(m['real_seed'], m['batch'], m['nc'])
+    noises = synthetic_noise(m['noise_seed'], m['batch'] * (m['critic_iters'] + 1), m['nz']).reshape(m['critic_iters'] + 1, m['batch'], m['nz'], 1, 1)
+    for it in range(m['critic_iters']):
+        r = wo.critic_iteration(G, D, optD, real, noises[it], g[f'c{it}.alpha'], m['lambda_gp'])
+        tol = dict(rtol=1e-4, atol=1e-6) if it == 0 else dict(rtol=2e-3, atol=1e-5)
+        close(r['d_loss'], g[f'c{it}.d_loss'], what=f'c{it}.d_loss', **tol)
+        close(r['gp'], g[f'c{it}.gp'], what=f'c{it}.gp', **tol)
+        if it == 0:
+            for k, v in r['grads_D'].items():
+                grad_close(v, g[f'c0.grads_D.{k}'], f'critic gradient {k} (incl. the gradient penalty\'s double backward)', bulk=2e-4)
+    r = wo.generator_iteration(G, D, optG, noises[m['critic_iters']])
+    close(r['g_loss'], g['g_loss'], rtol=2e-3, atol=1e-5, what='g_loss')
+    close(r['fake'][:, :, ::3, ::3], g['fake'], rtol=2e-3, atol=1e-4, what='fake')
+    for tag, net in (('G', G), ('D', D)):
+        for k, v in net.sd.items():
+            ref = g[f'final.{tag}.{k}']
+            if k.endswith('num_batches_tracked'):
+                assert int(v) == int(ref), k
+            elif 'running' in k:
+                close(v, ref, rtol=1e-3, atol=1e-5, what=k)
+            else:
+                weights_close(v, ref, what=f'final.{tag}.{k}', steps=m['critic_iters'] if tag == 'D' else 1, rtol=1e-3, atol=1e-5, frac=0.97)
