@@ -66,6 +66,11 @@ PROTOTYPES = {
     'b200gan_copy_view': [_VP, _VP, _vp],
     'b200gan_fill_f32': [_vp, _i64, _f32, _vp],
     'b200gan_gather_augment': [_vp, _i64, _vp, _vp, C.POINTER(C.c_float), C.POINTER(C.c_float), _VP, _vp],
+    'b200gan_sample_sumsq': [_VP, _vp, _vp],
+    'b200gan_gp_from_norms': [_vp, _i32, _f32, _vp, _vp, _vp],
+    'b200gan_sample_axpby': [_VP, _vp, _VP, _vp, _VP, _vp],
+    'b200gan_bn_bwd_bwd': [_VP, _VP, _VP, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _VP, _VP, _vp, _vp, _vp],
+    'b200gan_mean_f32': [_vp, _i64, _f32, _vp, _vp],
     'b200gan_dp_unique_id': [_vp],
     'b200gan_dp_init': [_vp, _i32, _i32, C.POINTER(_vp)],
     'b200gan_dp_allreduce_bucket': [_vp, _vp, _i64, _vp],

@@ -78,6 +78,15 @@ int ew_copy_view(const b200gan_view*, const b200gan_view*, cudaStream_t);
 int ew_fill(float*, int64_t, float, cudaStream_t);
 int ew_gather_augment(const uint8_t*, int64_t, const int64_t*, const uint8_t*, const float*, const float*, const b200gan_view*, cudaStream_t);
 
+// wgan_gp.cu
+int gp_bn_bwd_bwd(const b200gan_view* r, const b200gan_view* y, const b200gan_view* dz, const float* scale, const float* shift, const float* mean,
+                  const float* invstd, const float* gamma, const double* dz_sums, int64_t count, int act, float slope, const b200gan_view* u,
+                  const b200gan_view* inj, float* dgamma, double* sums3, cudaStream_t st);
+int gp_sample_sumsq(const b200gan_view* x, double* out, cudaStream_t st);
+int gp_from_norms(const double* sumsq, int n, float lambda, float* gp, float* coeff, cudaStream_t st);
+int gp_sample_axpby(const b200gan_view* x, const float* a, const b200gan_view* y, const float* b, const b200gan_view* out, cudaStream_t st);
+int gp_mean_f32(const float* x, int64_t n, float scale, float* out, cudaStream_t st);
+
 static int check_conv(const b200gan_conv* cv) {
   if (!cv) { set_error("null conv descriptor"); return B200GAN_ERR_BAD_ARG; }
   if (cv->k <= 0 || cv->stride <= 0 || cv->pad < 0 || cv->k > 16) { set_error("bad conv geometry k=%d s=%d p=%d", cv->k, cv->stride, cv->pad); return B200GAN_ERR_BAD_ARG; }
@@ -374,6 +383,45 @@ int b200gan_copy_view(const b200gan_view* src, const b200gan_view* dst, void* st
 int b200gan_fill_f32(float* ptr, int64_t numel, float value, void* stream) {
   B200_CHECK_ARG(ptr || numel == 0, "fill_f32: null pointer");
   return ew_fill(ptr, numel, value, (cudaStream_t)stream);
+}
+
+int b200gan_sample_sumsq(const b200gan_view* x, double* sumsq, void* stream) {
+  int rc;
+  if ((rc = check_view(x, "sample_sumsq"))) return rc;
+  B200_CHECK_ARG(sumsq, "sample_sumsq: null output");
+  return gp_sample_sumsq(x, sumsq, (cudaStream_t)stream);
+}
+
+int b200gan_gp_from_norms(const double* sumsq, int32_t batch, float lambda_gp, float* gp, float* coeff, void* stream) {
+  B200_CHECK_ARG(sumsq && gp && coeff && batch > 0, "gp_from_norms: bad argument");
+  return gp_from_norms(sumsq, batch, lambda_gp, gp, coeff, (cudaStream_t)stream);
+}
+
+int b200gan_sample_axpby(const b200gan_view* x, const float* a, const b200gan_view* y, const float* b, const b200gan_view* out, void* stream) {
+  int rc;
+  if ((rc = check_view(x, "sample_axpby"))) return rc;
+  if ((rc = check_view(out, "sample_axpby"))) return rc;
+  if (y && (rc = check_view(y, "sample_axpby"))) return rc;
+  return gp_sample_axpby(x, a, y, b, out, (cudaStream_t)stream);
+}
+
+int b200gan_bn_bwd_bwd(const b200gan_view* r, const b200gan_view* y, const b200gan_view* dz, const float* scale, const float* shift,
+                       const float* save_mean, const float* save_invstd, const float* gamma, const double* dz_sums, int64_t count, int32_t act,
+                       float slope, const b200gan_view* u, const b200gan_view* inj, float* dgamma, double* workspace, void* stream) {
+  int rc;
+  if ((rc = check_view(r, "bn_bwd_bwd"))) return rc;
+  if ((rc = check_view(y, "bn_bwd_bwd"))) return rc;
+  if ((rc = check_view(dz, "bn_bwd_bwd"))) return rc;
+  if ((rc = check_view(u, "bn_bwd_bwd"))) return rc;
+  if ((rc = check_view(inj, "bn_bwd_bwd"))) return rc;
+  B200_CHECK_ARG(scale && shift && save_mean && save_invstd && gamma && dz_sums && workspace && count > 0, "bn_bwd_bwd: null pointer");
+  B200_CHECK_ARG(act == B200GAN_ACT_NONE || act == B200GAN_ACT_RELU || act == B200GAN_ACT_LRELU, "bn_bwd_bwd: activation must be NONE, RELU or LRELU");
+  return gp_bn_bwd_bwd(r, y, dz, scale, shift, save_mean, save_invstd, gamma, dz_sums, count, act, slope, u, inj, dgamma, workspace, (cudaStream_t)stream);
+}
+
+int b200gan_mean_f32(const float* x, int64_t n, float scale, float* out, void* stream) {
+  B200_CHECK_ARG(x && out && n > 0, "mean_f32: bad argument");
+  return gp_mean_f32(x, n, scale, out, (cudaStream_t)stream);
 }
 
 int b200gan_gather_augment(const uint8_t* cache, int64_t num_images, const int64_t* index, const uint8_t* flip, const float* mean,

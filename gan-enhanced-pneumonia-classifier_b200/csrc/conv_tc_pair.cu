@@ -7,6 +7,15 @@
 // M = 256 MMA issued by the leader reads the other half from the peer's shared memory.  Fill per CTA and k-block drops from 48 KB
 // to 32 KB (62 B/cycle at full rate), six stages fit instead of four, and one thread issues the MMAs of two SMs.
 //
+// MEASURED (round 2, B=512, D3 forward alone, L2 flushed): correct (tests/test_gpu_tc.py against the numpy oracle), but 179 us against
+// 90 us for the one-CTA kernel, independent of the stage count (2..6) and of the epilogue (a drain-only epilogue: 172 us).  The MMA
+// itself is not the problem (tools/micro/mma_rate_pair.cu: M=256 N=256 K=16 retires every 128 cycles for both SMs, with or without a
+// multicast commit per k-block); a cycle trace of the leader shows ~1870 cycles per k-block, of which 400 waiting for its own TMA
+// bytes and 830 for the peer's, with both producers starved of free stages: each SM takes in 32 KB (TMA) + 16 KB (the peer's weight
+// half, re-read over the SM-to-SM network by every MMA) per k-block, i.e. the same 48 KB as the one-CTA kernel, at a third of its
+// rate.  Signalling the leader through a relay thread instead of remote complete_tx measured the same (205 us).  The kernel is
+// therefore OPT-IN (B200GAN_PAIR=1) and carries no performance claim; the dispatch default stays the one-CTA kernel.
+//
 // Protocol (see ptx.cuh): "full" barriers live in the leader and count both CTAs' bytes; tcgen05.commit multicasts the stage
 // release and the accumulator-ready arrival to both CTAs; the peer's epilogue warps arrive remotely on the leader's
 // accumulator-drained barriers.  Each CTA's epilogue reads its own 128 TMEM lanes exactly like the one-CTA kernel.
@@ -268,7 +277,24 @@ static int launch_pair_epi(const CUtensorMap& ma, const CUtensorMap& mb, TcConvP
   // pair tiles replace the one-CTA tile count: ceil(M tiles / 2) x N tiles x classes
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
   p.num_tiles = ((m_tiles + 1) / 2) * p.n_tiles * p.ncls;
-  const int pairs = kNumSMs / 2;
+  // Persistent schedule: exactly as many CTA pairs as can be CO-RESIDENT (a pair needs both SMs of one TPC; the driver knows how many
+  // fit with this kernel's shared-memory size: 74 on the pool's B200s).
+  static std::atomic<int> resident[64];
+  int dev = 0;
+  B200_CUDA(cudaGetDevice(&dev));
+  int pairs = (dev >= 0 && dev < 64) ? resident[dev].load(std::memory_order_relaxed) : 0;
+  if (pairs <= 0) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * (kNumSMs / 2)); cfg.blockDim = dim3(kTcThreads); cfg.dynamicSmemBytes = (size_t)smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, conv_gemm_tc_pair_kernel<EPI>, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = kNumSMs / 2; }
+    pairs = n < kNumSMs / 2 ? n : kNumSMs / 2;
+    if (dev >= 0 && dev < 64) resident[dev].store(pairs, std::memory_order_relaxed);
+  }
   const int clusters = p.num_tiles < pairs ? p.num_tiles : pairs;
   conv_gemm_tc_pair_kernel<EPI><<<2 * clusters, kTcThreads, smem, st>>>(ma, mb, p);      // __cluster_dims__(2,1,1)
   B200_LAUNCH_CHECK("conv_gemm_tc_pair_kernel");

@@ -208,6 +208,32 @@ int b200gan_fill_f32(float* ptr, int64_t numel, float value, void* stream);
 int b200gan_gather_augment(const uint8_t* cache, int64_t num_images, const int64_t* index, const uint8_t* flip, const float* mean,
                            const float* std, const b200gan_view* out, void* stream);
 
+/* ---- WGAN-GP critic update (src/wggan.py:72-89 `gradient_penalty`, src/train_wggan.py:70-85).  The reference
+ *      leaves the penalty's double backward to torch.autograd (`create_graph=True`); here it is launched explicitly.  Its convolutions are
+ *      plain b200gan_conv2d_{fprop,dgrad,wgrad} calls (the reverse of an input-gradient convolution is a forward convolution of the
+ *      adjoint); these entry points are the rest:
+ *        sample_sumsq     sumsq[n] = sum over (h,w,c) of x(n,.)^2                    (`gradients.view(B,-1).norm(2, dim=1)`, wggan.py:87-88)
+ *        gp_from_norms    gp[0] = lambda * mean_n (sqrt(sumsq[n]) - 1)^2  and  coeff[n] = lambda * (2/B) (||g_n|| - 1) / ||g_n||,
+ *                         so that d gp / d g(n,.) = coeff[n] * g(n,.)
+ *        sample_axpby     out(n,.) = a[n] x(n,.) + b[n] y(n,.)   (y NULL: first term only; a / b NULL: 1) -- the interpolation
+ *                         `alpha*real + (1-alpha)*fake` (wggan.py:77), the scaling by coeff[n], and `dst += src` (out == x)
+ *        bn_bwd_bwd       second-order terms of training-mode BatchNorm.  With xhat = (y-mean) invstd, P(v) = v - mean(v) - xhat mean(v xhat),
+ *                         the first backward computed dy = gamma invstd P(dz); given r = adjoint of dy:
+ *                           u   = gamma invstd P(r) * act'(scale*y + shift)      adjoint of the activation gradient above this BatchNorm
+ *                           inj = -gamma invstd^2 [xhat mean(r P(dz)) + mean(dz xhat) P(r) + mean(r xhat) P(dz)]   adjoint of the conv output y
+ *                           dgamma[c] += invstd[c] * sum r P(dz)
+ *                         dz_sums: [0..C) = sum dz, [C..2C) = sum dz*xhat of the first backward (b200gan_fuse.prev_sums' contract);
+ *                         workspace: 3*C doubles.  (native_batch_norm_backward's own backward in torch.autograd.)
+ *        mean_f32         out[0] = scale * sum x[0..n)   (critic scores -> loss terms, train_wggan.py:74,79) */
+int b200gan_sample_sumsq(const b200gan_view* x, double* sumsq, void* stream);
+int b200gan_gp_from_norms(const double* sumsq, int32_t batch, float lambda_gp, float* gp, float* coeff, void* stream);
+int b200gan_sample_axpby(const b200gan_view* x, const float* a, const b200gan_view* y, const float* b, const b200gan_view* out, void* stream);
+int b200gan_bn_bwd_bwd(const b200gan_view* r, const b200gan_view* y, const b200gan_view* dz, const float* scale, const float* shift,
+                       const float* save_mean, const float* save_invstd, const float* gamma, const double* dz_sums, int64_t count,
+                       int32_t act, float slope, const b200gan_view* u, const b200gan_view* inj, float* dgamma, double* workspace,
+                       void* stream);
+int b200gan_mean_f32(const float* x, int64_t n, float scale, float* out, void* stream);
+
 /* ---- data-parallel gradient-bucket layer (new functionality: the reference is single-device, src/train_gan.py:49; semantics in
  *      SURVEY.md section 8e).  One process per GPU; weights and Adam state replicated; every optimizer update (train_gan.py:141,150)
  *      is preceded by a SUM of the per-rank gradients, issued bucket by bucket while the backward pass is still running:
