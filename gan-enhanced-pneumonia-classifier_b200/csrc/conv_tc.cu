@@ -446,7 +446,8 @@ static int tc_conv_common(const b200gan_conv* cv, const b200gan_view* in, const 
   const int e = epi.mode;
   // wide layers, opt-in (B200GAN_PAIR=1): a CTA pair per 256 x 256 tile (tcgen05 cta_group::2, conv_tc_pair.cu).  Correct, but measured
   // 2x slower than the one-CTA kernel on this workload (see the header of conv_tc_pair.cu), so it is not the default.
-  static const bool pair_ok = getenv("B200GAN_PAIR") != nullptr && atoi(getenv("B200GAN_PAIR")) != 0;
+  const char* pair_env = getenv("B200GAN_PAIR");             // read per call: tests switch it inside one process
+  const bool pair_ok = pair_env != nullptr && atoi(pair_env) != 0;
   if (pair_ok && KC == 64 && BN == 256 && p.tiles_w * p.tiles_h * p.tiles_n >= 2) {
     CUtensorMap mbh;
     const int ktot = p.taps * cin;

@@ -83,10 +83,11 @@ def discriminator_specs(nc: int, ndf: int) -> List[LayerSpec]:
 
 class Act:
     """A device tensor plus the b200gan_view describing it as logical (N,H,W,C)."""
-    __slots__ = ('t', 'v')
+    __slots__ = ('t', 'v', 'nchw')
 
     def __init__(self, t: torch.Tensor, nchw: bool):
         self.t = t
+        self.nchw = nchw
         self.v = L.view_nchw(t) if nchw else L.view_nhwc(t)
 
     @property
@@ -121,7 +122,7 @@ def _check_f32(t, what):
 class LayerCtx:
     """What the forward pass keeps per layer: input x, conv output y (BatchNorm layers only), activation output a,
     BatchNorm coefficients, packed weights, and (filled during backward) the BatchNorm-backward sums."""
-    __slots__ = ('x', 'y', 'a', 'scale', 'shift', 'mean', 'invstd', 'wp_down', 'wp_up', 'bsums')
+    __slots__ = ('x', 'y', 'a', 'scale', 'shift', 'mean', 'invstd', 'wp_down', 'wp_up', 'bsums', 'bsums2')
 
 
 class NetEngine:
@@ -310,7 +311,7 @@ class NetEngine:
                     fuse_kw = dict(dy_act=sp.act, dy_slope=LRELU_SLOPE, dy_ref=lc.a.v)
             else:
                 # activation without BatchNorm and without a fused kernel (Sigmoid of the module-level Discriminator forward)
-                dy = Act(torch.empty(lc.a.t.shape, device=dev, dtype=lc.a.t.dtype), nchw=False)
+                dy = Act(torch.empty_like(lc.a.t), nchw=lc.a.nchw)          # same layout as the saved output (NCHW at the network edge)
                 L.call('b200gan_bn_act_bwd_apply', C.byref(d.v), C.byref(lc.a.v), C.byref(lc.a.v), None, None, None, None, None, None, 0,
                        sp.act, LRELU_SLOPE, C.byref(dy.v), None, None, st)
                 self.launches += 1

@@ -112,6 +112,28 @@ def test_tc_against_numpy_oracle():
     close(dx_tc.float().cpu().numpy().transpose(0, 3, 1, 2), ref, rtol=1e-2, atol=1e-2, what='up vs oracle')
 
 
+@pytest.mark.parametrize('case,direction', [((9, 128, 28, 28, 256), 'down'), ((130, 256, 14, 14, 512), 'down'), ((5, 64, 28, 28, 256), 'down'),
+                                            ((130, 512, 7, 7, 256), 'up')])
+def test_cta_pair_kernel_matches_oracle(case, direction, monkeypatch):
+    """The opt-in CTA-pair kernel (tcgen05.mma.cta_group::2, 256 x 256 tiles, conv_tc_pair.cu; B200GAN_PAIR=1) on the wide layers, odd
+    M-tile counts included (the last pair's second tile is empty), against the numpy oracle and the one-CTA kernel."""
+    monkeypatch.setenv('B200GAN_PAIR', '1')
+    if direction == 'down':
+        n, ci, h, w_, co = case
+        x, wt, y_pair, _ = run_pair(n, ci, h, w_, co, 'down')
+        oracle_close(y_pair, orc.conv2d_fprop(nchw(x), wt.cpu().numpy(), 2, 1), f'pair down {case}')
+        monkeypatch.setenv('B200GAN_PAIR', '0')
+        _, _, y_one, _ = run_pair(n, ci, h, w_, co, 'down')
+    else:
+        n, co, h, w_, ci = case
+        dy, wt, y_pair, _ = run_pair(n, ci, h, w_, co, 'up')
+        oracle_close(y_pair, orc.conv2d_dgrad(nchw(dy), wt.cpu().numpy(), 2, 1, (2 * h, 2 * w_)), f'pair up {case}')
+        monkeypatch.setenv('B200GAN_PAIR', '0')
+        _, _, y_one, _ = run_pair(n, ci, h, w_, co, 'up')
+    # same operands, same fp32 accumulation order per output element up to the MMA's internal order: one bf16 ulp at most
+    close(y_pair.float().cpu().numpy(), y_one.float().cpu().numpy(), rtol=1.05 * BF16_ULP, atol=1e-4, what='pair vs one-CTA kernel')
+
+
 # (n, Ci, H, W, Co): x is (n,H,W,Ci), dy is (n,H/2,W/2,Co) -- the four tensor-core layer geometries + odd sizes
 WGRAD = [(3, 32, 112, 112, 64), (5, 64, 56, 56, 128), (9, 128, 28, 28, 256), (70, 256, 14, 14, 512), (2, 64, 8, 24, 64),
          (3, 128, 12, 20, 192), (2, 512, 4, 4, 128)]

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Development aid: the D3 forward convolution (Conv2d 128->256, 28x28 -> 14x14, B=512) alone on the CTA-pair kernel at several cluster
-counts (B200GAN_PAIR_CLUSTERS), CUDA events, L2 flushed.  Run with B200GAN_NO_PAIR=1 for the one-CTA kernel."""
+counts (B200GAN_PAIR_CLUSTERS), CUDA events, L2 flushed.  Needs B200GAN_PAIR=1 (the pair kernel is opt-in); without it the one-CTA kernel is timed."""
 import ctypes as C, os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
