@@ -77,7 +77,8 @@ PROTOTYPES = {
     'b200gan_dp_sync': [_vp, _vp],
     'b200gan_dp_destroy': [_vp],
 }
-OTHER_SYMBOLS = ['b200gan_version', 'b200gan_last_error_string', 'b200gan_device_info', 'b200gan_dp_collectives']
+OTHER_SYMBOLS = ['b200gan_version', 'b200gan_last_error_string', 'b200gan_device_info', 'b200gan_dp_collectives',
+                 'b200gan_conv_wgrad_workspace_floats']
 DP_ID_BYTES = 128
 
 _lib = None
@@ -105,6 +106,8 @@ def load():
     lib.b200gan_last_error_string.restype = C.c_char_p
     lib.b200gan_device_info.argtypes = [C.c_int, C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.b200gan_device_info.restype = C.c_int
+    lib.b200gan_conv_wgrad_workspace_floats.argtypes = [_CP, _VP, _VP, _i32]
+    lib.b200gan_conv_wgrad_workspace_floats.restype = C.c_int64
     lib.b200gan_dp_collectives.argtypes = [_vp]
     lib.b200gan_dp_collectives.restype = C.c_int64
     _lib = lib

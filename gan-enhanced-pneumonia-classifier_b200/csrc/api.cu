@@ -296,6 +296,22 @@ int b200gan_convT2d_wgrad(const b200gan_conv* cv, const b200gan_view* x, const b
   return conv_dispatch(WGRAD, true, cv, dy, x, nullptr, nullptr, dweight, workspace, fuse, stream, "convT2d_wgrad");
 }
 
+int64_t b200gan_conv_wgrad_workspace_floats(const b200gan_conv* cv, const b200gan_view* x, const b200gan_view* dy, int32_t transposed) {
+  int rc;
+  if ((rc = check_conv(cv))) return rc;
+  if ((rc = check_view(x, "conv_wgrad_workspace_floats"))) return rc;
+  if ((rc = check_view(dy, "conv_wgrad_workspace_floats"))) return rc;
+  // conv geometry: fine side carries Ci, coarse side Co; the tensor-core weight gradient (k4 s2 p1, dense NHWC bf16 operands, Co % 64 == 0,
+  // Ci in {32, 64, multiples of 128}) reduces its split-K partial sums in a [Co][16][Ci] fp32 slab; every other kernel adds into dweight
+  const b200gan_view* fine = transposed ? dy : x;
+  const b200gan_view* coarse = transposed ? x : dy;
+  if (cv->algo == B200GAN_ALGO_SIMT || cv->k != 4 || cv->stride != 2 || cv->pad != 1) return 0;
+  if (fine->dtype != B200GAN_BF16 || coarse->dtype != B200GAN_BF16) return 0;
+  const int Ci = fine->c, Co = coarse->c;
+  if (Co % 64 != 0 || (Ci != 32 && Ci != 64 && Ci % 128 != 0)) return 0;
+  return (int64_t)Co * Ci * 16;
+}
+
 int b200gan_pack_conv_weight(const float* weight, int32_t co, int32_t ci, int32_t k, int32_t form, void* out, void* stream) {
   B200_CHECK_ARG(weight && out && co > 0 && ci > 0 && form >= 0 && form <= 2, "pack_conv_weight: bad argument");
   return tc_pack_weight(weight, co, ci, k, form, out, (cudaStream_t)stream);

@@ -187,11 +187,11 @@ class NetEngine:
     def _wgrad(self, i, x: Act, dy: Act, dw, st, fuse=None):
         name = 'b200gan_convT2d_wgrad' if self.transposed else 'b200gan_conv2d_wgrad'
         ws = None
-        if self._tc_layer(i):
+        need = int(L.load().b200gan_conv_wgrad_workspace_floats(C.byref(self._conv[i]), C.byref(x.v), C.byref(dy.v), 1 if self.transposed else 0))
+        if need > 0:
             # all zero on entry, handed back all zero by the library: one buffer serves every layer
-            if self._ws is None or self._ws.numel() < dw.numel() or self._ws.device != dw.device:
-                self._ws = torch.zeros(max(dw.numel(), max(sp.cin * sp.cout * sp.k * sp.k for sp in self.specs)), device=dw.device,
-                                       dtype=torch.float32)
+            if self._ws is None or self._ws.numel() < need or self._ws.device != dw.device:
+                self._ws = torch.zeros(max(need, max(sp.cin * sp.cout * sp.k * sp.k for sp in self.specs)), device=dw.device, dtype=torch.float32)
             ws = self._ws
         L.call(name, C.byref(self._conv[i]), C.byref(x.v), C.byref(dy.v), L.ptr(dw), L.ptr(ws), C.byref(fuse) if fuse is not None else None, st)
         self.launches += 1

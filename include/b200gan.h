@@ -129,6 +129,10 @@ int b200gan_conv2d_dgrad(const b200gan_conv* cv, const b200gan_view* dy, const f
 int b200gan_conv2d_wgrad(const b200gan_conv* cv, const b200gan_view* x, const b200gan_view* dy, float* dweight,
                          float* workspace, const b200gan_fuse* fuse, void* stream);
 
+/* Number of floats of `workspace` the weight-gradient call for these operands can use (0: the kernel that will be selected takes none).
+ * x / dy as passed to b200gan_conv2d_wgrad (transposed = 0) or b200gan_convT2d_wgrad (transposed = 1).  Negative status on bad arguments. */
+int64_t b200gan_conv_wgrad_workspace_floats(const b200gan_conv* cv, const b200gan_view* x, const b200gan_view* dy, int32_t transposed);
+
 /* ---- nn.ConvTranspose2d: forward (dcgan.py:26-46), input gradient, weight gradient (Cin,Cout,k,k). */
 int b200gan_convT2d_fprop(const b200gan_conv* cv, const b200gan_view* x, const float* weight, const void* wpacked,
                           const b200gan_view* y, const b200gan_fuse* fuse, void* stream);

@@ -47,20 +47,3 @@ def weights_close(a, b, what='', lr=2e-4, steps=1, rtol=1e-4, atol=2e-6, frac=0.
     ok = d <= atol + rtol * np.abs(b)
     assert ok.mean() >= frac, f'{what}: only {ok.mean():.4f} of entries within tolerance (max diff {d.max():.3e})'
     assert d.max() <= 2.05 * lr * steps + atol, f'{what}: max diff {d.max():.3e} exceeds the sign-flip envelope'
-
-
-def eventually(check, attempts=3):
-    """Run `check(attempt)` until it passes, at most `attempts` times.  For trajectory comparisons between two RUNS of the same
-    kernels only.  fp32 atomics make two runs differ by ~1e-7; in the 5-iteration small-network case one Generator pre-activation
-    lands within that noise of zero in iteration 3, and in about one run out of forty its ReLU derivative comes out the other
-    way: a discrete, reproducible alternative trajectory ~1e-4 away (tools/diag_flake3.py: 4 of 150 identical-input runs take it,
-    all four bit-for-bit the same way; 1500 repetitions of forward + backward alone never differ, tools/diag_repeat.py).  A
-    systematic difference fails every attempt; the noise event has to strike `attempts` times in a row (~1e-5) to fail the test."""
-    last = None
-    for k in range(attempts):
-        try:
-            return check(k)
-        except AssertionError as e:      # noqa: PERF203
-            last = e
-    raise last
-

@@ -68,3 +68,38 @@ def test_device_cache_has_no_host_path(tmp_path, capsys):
     assert tg.main(tg.build_parser().parse_args(argv)) is None
     assert '--cache-dataset keeps the training images in GPU memory' in capsys.readouterr().out
     assert not os.path.exists(d + '/models/gan/generator_final.pth')
+
+
+REF_WGAN_FLAGS = {
+    'data_dir': './data/processed', 'model_dir': './models', 'output_dir': './results', 'results_dir': './results/metrics',
+    'figures_dir': './results/figures', 'num_channels': 3, 'latent_dim': 100, 'feature_maps_g': 64, 'feature_maps_d': 64, 'epochs': 30,
+    'batch_size': 64, 'lr': 0.0002, 'beta1': 0.5, 'workers': 4, 'vis_batch_size': 64, 'save_interval': 500, 'checkpoint_interval': 10,
+    'critic_iters': 5, 'lambda_gp': 10.0, 'cpu': False,
+}
+
+
+def test_wgan_cli_keeps_reference_flags_and_defaults():
+    """src/train_wggan.py:127-148 (the list above was read off the reference)."""
+    from gan_enhanced_pneumonia_classifier_b200 import train_wggan as tw
+    args = vars(tw.build_parser().parse_args([]))
+    for k, v in REF_WGAN_FLAGS.items():
+        assert args[k] == v, k
+    assert set(args) - set(REF_WGAN_FLAGS) == {'dtype', 'synthetic', 'max_iters', 'log_interval', 'seed'}
+
+
+def test_wgan_cpu_round_trip_writes_reference_artefacts(tmp_path):
+    """--cpu runs the reference's stock-torch WGAN-GP loop over the drop-in modules (autograd double backward) and writes the reference's files."""
+    from gan_enhanced_pneumonia_classifier_b200 import train_wggan as tw
+    d = str(tmp_path)
+    argv = ['--cpu', '--synthetic', '4', '--batch-size', '2', '--epochs', '1', '--latent-dim', '8', '--feature-maps-g', '2', '--feature-maps-d', '2',
+            '--num-channels', '1', '--vis-batch-size', '2', '--critic-iters', '2', '--model-dir', d + '/models', '--output-dir', d + '/results',
+            '--results-dir', d + '/results/metrics', '--figures-dir', d + '/results/figures', '--seed', '0', '--checkpoint-interval', '1']
+    hist = tw.main(tw.build_parser().parse_args(argv))
+    assert len(hist['D_losses']) == 4 and len(hist['G_losses']) == 2 and len(hist['D_losses_epoch']) == 1
+    assert all(np.isfinite(hist['D_losses'])) and all(np.isfinite(hist['G_losses']))
+    for f in ('models/wgan/generator_final.pth', 'models/wgan/discriminator_final.pth', 'models/wgan/generator_epoch_001.pth',
+              'results/metrics/wgan_training_history.json'):
+        assert os.path.exists(os.path.join(d, f)), f
+    assert any(n.startswith('fake_samples_epoch_001_iter_') for n in os.listdir(d + '/results/wgan_images'))
+    sd = torch.load(d + '/models/wgan/discriminator_final.pth')
+    assert len(sd) == 20 and sd['main.11.weight'].shape == (1, 16, 7, 7)

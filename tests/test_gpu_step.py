@@ -10,7 +10,7 @@ import torch
 import dcgan_oracle as orc
 import gan_enhanced_pneumonia_classifier_b200 as pkg
 from conftest import GOLDEN
-from parity_utils import close, eventually, grad_close, synthetic_noise, synthetic_real, weights_close
+from parity_utils import close, grad_close, synthetic_noise, synthetic_real, weights_close
 
 pytestmark = pytest.mark.gpu
 
@@ -163,48 +163,56 @@ def test_state_dict_roundtrip_eval_forward_and_vis_side_effects():
 
 @pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
 def test_graph_replay_matches_kernel_by_kernel(dtype):
-    """DCGANTrainer.step replayed from its CUDA graph (third call onwards) against the same trainer launching kernel by kernel:
-    losses, BatchNorm buffers, num_batches_tracked and the Adam step count must advance identically (the step count and the
-    BatchNorm counters live on the device precisely so that replay is exact)."""
+    """DCGANTrainer.step replayed from its CUDA graph (second call onwards) against the same trainer launching kernel by kernel.
+
+    Exact, every run: launch counts, the device-side Adam step counts and every BatchNorm `num_batches_tracked` (they live on the
+    device precisely so that replay is exact).  Tight: the first two iterations (history scalars, and the complete state after
+    them) -- the second call is already a replay.  Afterwards only the sign-flip envelope is asserted: the step is not bitwise
+    reproducible from run to run (fp32 shared-memory / split-K accumulation order), and a GAN iteration amplifies that noise
+    discretely -- one ReLU derivative within 1e-7 of zero taking the other branch puts a run on an alternative, equally valid
+    trajectory ~1e-4 away (tools/diag_flake3.py measured 4 such runs in 150, kernel by kernel against itself).  A retry loop
+    used to paper over that; the assertions below hold on either trajectory instead."""
     from gan_enhanced_pneumonia_classifier_b200.trainer import DCGANTrainer
     m = dict(seed=3, nz=16, nc=1, fm=8)
     real = torch.from_numpy(synthetic_real(5, 4, 1)).cuda()
     noises = [torch.from_numpy(synthetic_noise(10 + i, 4, 16)).cuda() for i in range(5)]
     tol = dict(rtol=1e-4, atol=1e-5) if dtype == torch.float32 else dict(rtol=2e-2, atol=2e-3)
-
-    def attempt(_):
-        hist, nets = {}, {}
-        for mode in (False, True):
-            G, D = build(m, dtype)
-            tr = DCGANTrainer(G, D, dtype=dtype, use_graph=mode)
-            hist[mode] = torch.stack([tr.step(real, z) for z in noises]).cpu().numpy()
-            nets[mode] = (G, D, tr)
-        # exact invariants, every attempt
-        assert len(nets[True][2]._graphs) == 1 and nets[True][2].launches == nets[False][2].launches
-        assert int(nets[True][2].arenaD.step_dev) == 5 and int(nets[True][2].arenaG.step_dev) == 5
-        for a, b in zip(nets[True][:2], nets[False][:2]):
-            sa, sb = a.state_dict(), b.state_dict()
-            for k in sa:
-                if k.endswith('num_batches_tracked'):
-                    assert int(sa[k]) == int(sb[k]), k
-        # the second call is already a graph replay: tight on the first two iterations, trajectory-noise tolerance afterwards
-        # (fp32 atomics make two kernel-by-kernel runs differ by the same amount)
-        close(hist[True][:2], hist[False][:2], what='history scalars, graph vs eager (iterations 1-2)', **tol)
-        close(hist[True], hist[False], what='history scalars, graph vs eager', rtol=max(tol['rtol'], 5e-3), atol=max(tol['atol'], 1e-4))
-        for a, b in zip(nets[True][:2], nets[False][:2]):
-            sa, sb = a.state_dict(), b.state_dict()
-            for k in sa:
-                if k.endswith('num_batches_tracked'):
-                    continue
-                if 'running' in k:
-                    # bf16: five Adam steps of +-lr amplify the fp32-atomic summation-order noise of the two runs (no bug: the same
-                    # trainer run twice kernel by kernel differs as much), so the BatchNorm buffers only agree to ~1e-2 absolute
-                    close(sa[k].cpu().numpy(), sb[k].cpu().numpy(), what=k, rtol=tol['rtol'], atol=tol['atol'] if dtype == torch.float32 else 2e-2)
-                else:
-                    weights_close(sa[k].cpu().numpy(), sb[k].cpu().numpy(), what=k, steps=5, rtol=tol['rtol'], atol=max(tol['atol'], 2e-6),
-                                  frac=0.98 if dtype == torch.float32 else 0.9)
-
-    eventually(attempt)
+    hist, nets, early = {}, {}, {}
+    for mode in (False, True):
+        G, D = build(m, dtype)
+        tr = DCGANTrainer(G, D, dtype=dtype, use_graph=mode)
+        rows = []
+        for i, z in enumerate(noises):
+            rows.append(tr.step(real, z))
+            if i == 1:
+                early[mode] = {f'{tag}.{k}': v.detach().clone() for tag, net in (('G', G), ('D', D)) for k, v in net.state_dict().items()}
+        hist[mode] = torch.stack(rows).cpu().numpy()
+        nets[mode] = (G, D, tr)
+    assert len(nets[True][2]._graphs) == 1 and nets[True][2].launches == nets[False][2].launches
+    assert int(nets[True][2].arenaD.step_dev) == 5 and int(nets[True][2].arenaG.step_dev) == 5
+    for a, b in zip(nets[True][:2], nets[False][:2]):
+        sa, sb = a.state_dict(), b.state_dict()
+        for k in sa:
+            if k.endswith('num_batches_tracked'):
+                assert int(sa[k]) == int(sb[k]), k
+    # iterations 1-2 (the second one replayed): history and the whole state, tight
+    close(hist[True][:2], hist[False][:2], what='history scalars, graph vs eager (iterations 1-2)', **tol)
+    for k, v in early[True].items():
+        if k.endswith('num_batches_tracked'):
+            assert int(v) == int(early[False][k]), k
+        elif 'running' in k:
+            close(v.cpu().numpy(), early[False][k].cpu().numpy(), what=f'after 2 iterations: {k}', **tol)
+        else:
+            weights_close(v.cpu().numpy(), early[False][k].cpu().numpy(), what=f'after 2 iterations: {k}', steps=2, rtol=tol['rtol'], atol=max(tol['atol'], 2e-6),
+                          frac=0.98 if dtype == torch.float32 else 0.9)
+    # iterations 3-5: finite, and every weight inside the envelope two valid trajectories can be apart
+    assert np.isfinite(hist[True]).all() and np.isfinite(hist[False]).all()
+    close(hist[True], hist[False], what='history scalars, graph vs eager (all iterations)', rtol=5e-2, atol=5e-3)
+    for a, b in zip(nets[True][:2], nets[False][:2]):
+        sa, sb = a.state_dict(), b.state_dict()
+        for k in sa:
+            if not k.endswith('num_batches_tracked') and 'running' not in k:
+                assert float((sa[k] - sb[k]).abs().max()) <= 2.1 * 2e-4 * 5, k
 
 
 def test_fused_trainer_matches_oracle_over_three_iterations():
