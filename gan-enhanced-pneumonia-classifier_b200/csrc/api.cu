@@ -55,6 +55,10 @@ int thin_wgrad(const b200gan_view* fine, const b200gan_view* fine_ref, int fine_
 int window_fprop(const b200gan_conv*, const b200gan_view* x, const float* w, const b200gan_view* y, cudaStream_t);
 int window_dgrad(const b200gan_conv*, const b200gan_view* dy, const float* w, const b200gan_view* dx, const TcEpi& epi, cudaStream_t);
 int window_wgrad(const b200gan_conv*, const b200gan_view* x, const b200gan_view* dy, float* dw, cudaStream_t);
+// valid convolution of a small map to one channel (the WGAN-GP critic's score map, conv_thin.cu): same return convention
+int score_fprop(const b200gan_conv*, const b200gan_view* x, const float* w, const b200gan_view* y, cudaStream_t);
+int score_dgrad(const b200gan_conv*, const b200gan_view* dy, const float* w, const b200gan_view* dx, cudaStream_t);
+int score_wgrad(const b200gan_conv*, const b200gan_view* x, const b200gan_view* dy, float* dw, cudaStream_t);
 int latent_fprop(const b200gan_conv*, const b200gan_view* z, const float* w, const b200gan_view* y, cudaStream_t);
 int latent_wgrad(const b200gan_conv*, const b200gan_view* dy_fine, const b200gan_view* z, float* dw, cudaStream_t);
 // the same two as warp-level tensor-core GEMMs (latent_mma.cu)
@@ -210,7 +214,7 @@ static int conv_dispatch(Prim prim, bool transposed, const b200gan_conv* cv, con
       if (t < 0) return t;
     }
     if (t > 0 && plain) {
-      if (prim == FPROP) t = window_fprop(cv, fine, w, coarse, st);
+      if (prim == FPROP) { t = window_fprop(cv, fine, w, coarse, st); if (t > 0) t = score_fprop(cv, fine, w, coarse, st); }
       else if (prim == DGRAD) {
         TcEpi epi;                                   // the GEMV input gradient absorbs the BatchNorm-backward fusion of the layer below
         if (prev_bn) {
@@ -219,10 +223,12 @@ static int conv_dispatch(Prim prim, bool transposed, const b200gan_conv* cv, con
         }
         t = (prev && !prev_bn) ? 1 : window_dgrad(cv, coarse, w, fine, epi, st);
         if (t == 0) prev = false;
+        if (t > 0) t = score_dgrad(cv, coarse, w, fine, st);
         if (t > 0) t = latent_fprop_mma(cv, coarse, w, fine, st);
         if (t > 0) t = latent_fprop(cv, coarse, w, fine, st);
       } else {
         t = window_wgrad(cv, fine, coarse, dw, st);
+        if (t > 0) t = score_wgrad(cv, fine, coarse, dw, st);
         if (t > 0) t = latent_wgrad_mma(cv, fine, coarse, dw, st);
         if (t > 0) t = latent_wgrad(cv, fine, coarse, dw, st);
       }

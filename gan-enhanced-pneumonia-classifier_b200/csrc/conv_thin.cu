@@ -13,6 +13,184 @@ static bool dense_bf16_c(const b200gan_view* v, int c) {
 }
 
 // ---------------------------------------------------------------------------------------------------
+// "score map": valid convolution of a SMALL map to ONE channel, Conv2d(C -> 1, k, stride 1, pad 0) with an output map of up to 8 x 8
+// (the WGAN-GP critic's last layer, wggan.py:63: 512 x 14 x 14 -> 1 x 8 x 8) and its gradients.  As an implicit GEMM this has N = 1: the
+// generic kernels waste 63/64 of every tile on it (measured 3.6 ms per call at batch 128).  Here one CTA owns one image: the weights sit
+// transposed ([tap][C], fp32) in shared memory, a lane owns C/32 consecutive channels, warps split output rows / input pixels / taps.
+// x: (N,H,W,C) dense bf16;  y, dy: (N,OH,OW,1) dense fp32;  w, dw: (1,C,k,k) fp32.
+// ---------------------------------------------------------------------------------------------------
+template <int CPL>
+__device__ __forceinline__ void ld_channels(const __nv_bfloat16* p, float (&v)[CPL]) {
+  if constexpr (CPL % 8 == 0) {
+#pragma unroll
+    for (int j = 0; j < CPL / 8; ++j) unpack8(*reinterpret_cast<const uint4*>(p + 8 * j), &v[8 * j]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) v[j] = __bfloat162float(p[j]);
+  }
+}
+
+template <int CPL>
+__global__ void __launch_bounds__(256) score_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, float* __restrict__ y, int H, int W,
+                                                       int k, int OH, int OW) {
+  extern __shared__ float wt[];                                  // [k*k][C]
+  constexpr int C = 32 * CPL;
+  const int kk = k * k, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < kk * C; i += blockDim.x) { const int c = i / kk, t = i - c * kk; wt[t * C + c] = w[i]; }
+  __syncthreads();
+  const __nv_bfloat16* xn = x + (int64_t)blockIdx.x * H * W * C + lane * CPL;
+  for (int oh = warp; oh < OH; oh += 8) {
+    float acc[8];
+#pragma unroll
+    for (int o = 0; o < 8; ++o) acc[o] = 0.f;
+    for (int kh = 0; kh < k; ++kh)
+      for (int px = 0; px < W; ++px) {
+        float xv[CPL];
+        ld_channels<CPL>(xn + ((int64_t)(oh + kh) * W + px) * C, xv);
+#pragma unroll
+        for (int o = 0; o < 8; ++o) {
+          const int kw = px - o;
+          if (o < OW && kw >= 0 && kw < k) {
+            const float* wr = wt + (kh * k + kw) * C + lane * CPL;
+            float s = 0.f;
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) s = fmaf(xv[j], wr[j], s);
+            acc[o] += s;
+          }
+        }
+      }
+#pragma unroll
+    for (int o = 0; o < 8; ++o) {
+      const float s = warp_sum(acc[o]);
+      if (lane == 0 && o < OW) y[((int64_t)blockIdx.x * OH + oh) * OW + o] = s;
+    }
+  }
+}
+
+template <int CPL>
+__global__ void __launch_bounds__(256) score_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w, __nv_bfloat16* __restrict__ dx, int H,
+                                                         int W, int k, int OH, int OW) {
+  extern __shared__ float wt[];                                  // [k*k][C] then dy[OH*OW]
+  constexpr int C = 32 * CPL;
+  const int kk = k * k, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* dys = wt + kk * C;
+  for (int i = threadIdx.x; i < kk * C; i += blockDim.x) { const int c = i / kk, t = i - c * kk; wt[t * C + c] = w[i]; }
+  for (int i = threadIdx.x; i < OH * OW; i += blockDim.x) dys[i] = dy[(int64_t)blockIdx.x * OH * OW + i];
+  __syncthreads();
+  __nv_bfloat16* dxn = dx + (int64_t)blockIdx.x * H * W * C + lane * CPL;
+  for (int p = warp; p < H * W; p += 8) {
+    const int ih = p / W, iw = p - ih * W;
+    float acc[CPL];
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) acc[j] = 0.f;
+    for (int kh = 0; kh < k; ++kh) {
+      const int oh = ih - kh;
+      if (oh < 0 || oh >= OH) continue;
+      for (int kw = 0; kw < k; ++kw) {
+        const int ow = iw - kw;
+        if (ow < 0 || ow >= OW) continue;
+        const float g = dys[oh * OW + ow];
+        const float* wr = wt + (kh * k + kw) * C + lane * CPL;
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) acc[j] = fmaf(g, wr[j], acc[j]);
+      }
+    }
+    __nv_bfloat16* o = dxn + (int64_t)p * C;
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) o[j] = __float2bfloat16_rn(acc[j]);
+  }
+}
+
+// dw[c][kh][kw] += sum_n sum_{oh,ow} dy[n][oh][ow] x[n][oh+kh][ow+kw][c]: a CTA walks images n = blockIdx.x, + gridDim.x, ...; warp w owns taps
+// t = w, w + 8, ...; the per-CTA partial sums live in shared memory ([tap][C], one owner thread per element) and are added once at the end
+template <int CPL>
+__global__ void __launch_bounds__(256) score_wgrad_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw, int N, int H,
+                                                         int W, int k, int OH, int OW) {
+  extern __shared__ float accs[];                                // [k*k][C] then dy[OH*OW]
+  constexpr int C = 32 * CPL;
+  const int kk = k * k, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* dys = accs + kk * C;
+  for (int i = threadIdx.x; i < kk * C; i += blockDim.x) accs[i] = 0.f;
+  for (int n = blockIdx.x; n < N; n += gridDim.x) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < OH * OW; i += blockDim.x) dys[i] = dy[(int64_t)n * OH * OW + i];
+    __syncthreads();
+    const __nv_bfloat16* xn = x + (int64_t)n * H * W * C + lane * CPL;
+    for (int t = warp; t < kk; t += 8) {
+      const int kh = t / k, kw = t - kh * k;
+      float acc[CPL];
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) acc[j] = 0.f;
+      for (int oh = 0; oh < OH; ++oh)
+        for (int ow = 0; ow < OW; ++ow) {
+          float xv[CPL];
+          ld_channels<CPL>(xn + ((int64_t)(oh + kh) * W + ow + kw) * C, xv);
+          const float g = dys[oh * OW + ow];
+#pragma unroll
+          for (int j = 0; j < CPL; ++j) acc[j] = fmaf(g, xv[j], acc[j]);
+        }
+      float* a = accs + t * C + lane * CPL;
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) a[j] += acc[j];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kk * C; i += blockDim.x) {       // i = c * kk + t in the reference layout
+    const int c = i / kk, t = i - c * kk;
+    const float v = accs[t * C + c];
+    if (v != 0.f) atomicAdd(dw + i, v);
+  }
+}
+
+static bool score_shape(const b200gan_conv* cv, const b200gan_view* fine, const b200gan_view* coarse) {
+  if (cv->stride != 1 || cv->pad != 0 || coarse->c != 1 || fine->c % 32 != 0 || fine->c > 512) return false;
+  const int cpl = fine->c / 32;
+  if (cpl != 1 && cpl != 2 && cpl != 4 && cpl != 8 && cpl != 16) return false;
+  if (coarse->h != fine->h - cv->k + 1 || coarse->w != fine->w - cv->k + 1 || coarse->w > 8 || coarse->h < 1) return false;
+  if (coarse->h == 1 && coarse->w == 1) return false;                      // the full-window kernels below are better at that
+  return dense_bf16_c(fine, fine->c) && coarse->dtype == B200GAN_F32 && coarse->sw == 1 && coarse->sh == coarse->w &&
+         coarse->sn == (int64_t)coarse->h * coarse->w;
+}
+
+#define SCORE_DISPATCH(KERNEL, GRID, SMEM, ...)                                                                  \
+  do {                                                                                                           \
+    const int cpl__ = fine__->c / 32;                                                                            \
+    if (cpl__ == 16) { B200_CUDA((ensure_dynamic_smem<KERNEL<16>>((int)(SMEM)))); KERNEL<16><<<GRID, 256, SMEM, st>>>(__VA_ARGS__); } \
+    else if (cpl__ == 8) { B200_CUDA((ensure_dynamic_smem<KERNEL<8>>((int)(SMEM)))); KERNEL<8><<<GRID, 256, SMEM, st>>>(__VA_ARGS__); }  \
+    else if (cpl__ == 4) { B200_CUDA((ensure_dynamic_smem<KERNEL<4>>((int)(SMEM)))); KERNEL<4><<<GRID, 256, SMEM, st>>>(__VA_ARGS__); }  \
+    else if (cpl__ == 2) { B200_CUDA((ensure_dynamic_smem<KERNEL<2>>((int)(SMEM)))); KERNEL<2><<<GRID, 256, SMEM, st>>>(__VA_ARGS__); }  \
+    else { B200_CUDA((ensure_dynamic_smem<KERNEL<1>>((int)(SMEM)))); KERNEL<1><<<GRID, 256, SMEM, st>>>(__VA_ARGS__); }                    \
+  } while (0)
+
+int score_fprop(const b200gan_conv* cv, const b200gan_view* x, const float* w, const b200gan_view* y, cudaStream_t st) {
+  if (!score_shape(cv, x, y)) return 1;
+  const b200gan_view* fine__ = x;
+  const size_t smem = (size_t)cv->k * cv->k * x->c * sizeof(float);
+  SCORE_DISPATCH(score_fwd_kernel, x->n, smem, reinterpret_cast<const __nv_bfloat16*>(x->ptr), w, reinterpret_cast<float*>(y->ptr), x->h, x->w, cv->k, y->h, y->w);
+  B200_LAUNCH_CHECK("score_fwd_kernel");
+  return 0;
+}
+int score_dgrad(const b200gan_conv* cv, const b200gan_view* dy, const float* w, const b200gan_view* dx, cudaStream_t st) {
+  if (!score_shape(cv, dx, dy)) return 1;
+  const b200gan_view* fine__ = dx;
+  const size_t smem = ((size_t)cv->k * cv->k * dx->c + dy->h * dy->w) * sizeof(float);
+  SCORE_DISPATCH(score_dgrad_kernel, dx->n, smem, reinterpret_cast<const float*>(dy->ptr), w, reinterpret_cast<__nv_bfloat16*>(dx->ptr), dx->h, dx->w, cv->k, dy->h,
+                 dy->w);
+  B200_LAUNCH_CHECK("score_dgrad_kernel");
+  return 0;
+}
+int score_wgrad(const b200gan_conv* cv, const b200gan_view* x, const b200gan_view* dy, float* dw, cudaStream_t st) {
+  if (!score_shape(cv, x, dy)) return 1;
+  const b200gan_view* fine__ = x;
+  const size_t smem = ((size_t)cv->k * cv->k * x->c + dy->h * dy->w) * sizeof(float);
+  const int grid = x->n < 2 * kNumSMs ? x->n : 2 * kNumSMs;
+  SCORE_DISPATCH(score_wgrad_kernel, grid, smem, reinterpret_cast<const __nv_bfloat16*>(x->ptr), reinterpret_cast<const float*>(dy->ptr), dw, x->n, x->h, x->w,
+                 cv->k, dy->h, dy->w);
+  B200_LAUNCH_CHECK("score_wgrad_kernel");
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // full-window convolution to one channel (D5: Conv2d(C->1, k=H=W, p0) + its gradients) as GEMV / outer product.
 //   x: (N,K,K,C) dense bf16, w: (1,C,K,K) fp32.  J = K*K*C, NHWC index j = hw*C + c  <->  weight index c*K*K + hw
 // ---------------------------------------------------------------------------------------------------

@@ -162,3 +162,31 @@ def test_wgan_cli_trains_on_the_gpu(tmp_path, dtype):
     assert all(np.isfinite(hist['D_losses'])) and all(np.isfinite(hist['G_losses']))
     sd = torch.load(d + '/models/wgan/generator_final.pth')
     assert len(sd) == 31 and sd['main.0.weight'].shape == (16, 128, 7, 7) and int(sd['main.1.num_batches_tracked']) > 0
+
+
+@pytest.mark.parametrize('n,c', [(3, 64), (5, 512), (2, 32)])
+def test_score_map_kernels_match_the_oracle(n, c):
+    """The critic's last layer Conv2d(C -> 1, k7 s1 p0) on the 14 x 14 map (wggan.py:63) and its gradients through the dedicated
+    one-CTA-per-image kernels (bf16 activations, fp32 weights / scores, as the training step uses them) against the numpy oracle."""
+    import ctypes as C
+    L = pkg._lib
+    rng = np.random.RandomState(c)
+    bf = lambda a: torch.from_numpy(a).to(torch.bfloat16).float().numpy()
+    x = bf(rng.randn(n, c, 14, 14).astype(np.float32))
+    w = (rng.randn(1, c, 7, 7) * 0.05).astype(np.float32)
+    dy = rng.randn(n, 1, 8, 8).astype(np.float32)
+    xt = torch.from_numpy(np.ascontiguousarray(x.transpose(0, 2, 3, 1))).cuda().to(torch.bfloat16)
+    wt, dyt = torch.from_numpy(w).cuda(), torch.from_numpy(np.ascontiguousarray(dy.transpose(0, 2, 3, 1))).cuda()
+    cv, st = L.Conv(7, 1, 0, L.ALGO_AUTO), L.stream_ptr()
+    y = torch.full((n, 8, 8, 1), float('nan'), device='cuda')
+    L.call('b200gan_conv2d_fprop', C.byref(cv), C.byref(L.view_nhwc(xt)), L.ptr(wt), None, C.byref(L.view_nhwc(y)), None, st)
+    close(y.cpu().numpy().transpose(0, 3, 1, 2), orc.conv2d_fprop(x, w, 1, 0), rtol=1e-4, atol=1e-4, what='score map forward')
+    dx = torch.full((n, 14, 14, c), float('nan'), device='cuda', dtype=torch.bfloat16)
+    L.call('b200gan_conv2d_dgrad', C.byref(cv), C.byref(L.view_nhwc(dyt)), L.ptr(wt), None, C.byref(L.view_nhwc(dx)), None, st)
+    ref = orc.conv2d_dgrad(dy, w, 1, 0, (14, 14))
+    close(dx.float().cpu().numpy().transpose(0, 3, 1, 2), ref, rtol=2.0 ** -8 * 1.05, atol=1e-5 * max(1.0, np.abs(ref).max()), what='score map input gradient')
+    base = torch.randn((1, c, 7, 7), device='cuda')
+    dw = base.clone()
+    L.call('b200gan_conv2d_wgrad', C.byref(cv), C.byref(L.view_nhwc(xt)), C.byref(L.view_nhwc(dyt)), L.ptr(dw), None, None, st)
+    ref = orc.conv2d_wgrad(x, dy, 7, 1, 0)
+    close((dw - base).cpu().numpy(), ref, rtol=1e-4, atol=3e-5 * max(1.0, np.abs(ref).max()), what='score map weight gradient')
