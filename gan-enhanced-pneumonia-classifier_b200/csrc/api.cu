@@ -51,6 +51,13 @@ int thin_up(const b200gan_view* coarse, const b200gan_view* coarse_ref, int coar
             int out_act, cudaStream_t);
 int thin_wgrad(const b200gan_view* fine, const b200gan_view* fine_ref, int fine_act, const b200gan_view* coarse, const b200gan_view* coarse_ref,
                int coarse_act, float slope, float* dw, cudaStream_t);
+// image-side layers whose feature side is not 32 channels wide (conv_edge.cu: the WGAN-GP 64-channel edge layers): same return convention
+int edge_down(const b200gan_view* fine, const b200gan_view* fine_ref, int fine_act, const float* w, const b200gan_view* coarse, int out_act, float slope,
+              cudaStream_t);
+int edge_up(const b200gan_view* coarse, const b200gan_view* coarse_ref, int coarse_act, float slope, const float* w, const b200gan_view* fine, int out_act,
+            cudaStream_t);
+int edge_wgrad(const b200gan_view* fine, const b200gan_view* fine_ref, int fine_act, const b200gan_view* coarse, const b200gan_view* coarse_ref,
+               int coarse_act, float slope, float* dw, cudaStream_t);
 // latent GEMM and 7x7 GEMV (conv_thin.cu): same return convention
 int window_fprop(const b200gan_conv*, const b200gan_view* x, const float* w, const b200gan_view* y, cudaStream_t);
 int window_dgrad(const b200gan_conv*, const b200gan_view* dy, const float* w, const b200gan_view* dx, const TcEpi& epi, cudaStream_t);
@@ -212,6 +219,12 @@ static int conv_dispatch(Prim prim, bool transposed, const b200gan_conv* cv, con
       else if (prim == DGRAD) t = thin_up(coarse, fz.g_ref, fz.g_act, fz.g_slope, w, fine, fz.out_act, st);
       else t = thin_wgrad(fine, grad_is_coarse ? nullptr : fz.g_ref, fz.g_act, coarse, grad_is_coarse ? fz.g_ref : nullptr, fz.g_act, fz.g_slope, dw, st);
       if (t < 0) return t;
+      if (t > 0) {                                   // other feature widths (they absorb no BatchNorm fusion: the passes below run)
+        if (prim == FPROP) t = edge_down(fine, fz.g_ref, fz.g_act, w, coarse, fz.out_act, fz.g_ref ? fz.g_slope : fz.out_slope, st);
+        else if (prim == DGRAD) t = edge_up(coarse, fz.g_ref, fz.g_act, fz.g_slope, w, fine, fz.out_act, st);
+        else t = edge_wgrad(fine, grad_is_coarse ? nullptr : fz.g_ref, fz.g_act, coarse, grad_is_coarse ? fz.g_ref : nullptr, fz.g_act, fz.g_slope, dw, st);
+        if (t < 0) return t;
+      }
     }
     if (t > 0 && plain) {
       if (prim == FPROP) { t = window_fprop(cv, fine, w, coarse, st); if (t > 0) t = score_fprop(cv, fine, w, coarse, st); }

@@ -18,43 +18,47 @@ namespace b200gan {
 
 namespace {
 
-__device__ __forceinline__ void decode(const View& v, int64_t idx, int& c, int64_t& off) {
-  c = (int)(idx % v.c);
-  int64_t pix = idx / v.c;
-  const int w = (int)(pix % v.w); pix /= v.w;
-  const int h = (int)(pix % v.h);
-  const int64_t n = pix / v.h;
-  off = n * v.sn + (int64_t)h * v.sh + (int64_t)w * v.sw + (int64_t)c * v.sc;
-}
-__device__ __forceinline__ int64_t offset_like(const View& v, int64_t idx) {
-  int c; int64_t off;
-  decode(v, idx, c, off);
-  return off;
-}
 __device__ __forceinline__ void st_rt(void* base, int dtype, int64_t off, float x) {
   if (dtype == B200GAN_F32) reinterpret_cast<float*>(base)[off] = x;
   else reinterpret_cast<__nv_bfloat16*>(base)[off] = __float2bfloat16_rn(x);
 }
 
-// sums[0..C) = sum r, [C..2C) = sum r xhat, [2C..3C) = sum r dz.  One CTA = a contiguous chunk of elements; per-channel partial sums in
-// shared memory (fp32), one fp64 atomic per channel, quantity and CTA.
+// Row-based indexing for the strided views: a CTA row (blockIdx.y) is one (n, h) line of W*C elements, a thread walks elements e = tid, tid + 256,
+// ... of the line, so the per-element index arithmetic is one 32-bit division by C (no 64-bit div / mod chains).
+struct RowBase { int64_t r, y, dz, u, inj; };
+__device__ __forceinline__ int64_t row_off(const View& v, int n, int h) { return (int64_t)n * v.sn + (int64_t)h * v.sh; }
+
+// sums[0..C) = sum r, [C..2C) = sum r xhat, [2C..3C) = sum r dz.  256 % C == 0 or C % 256 == 0 (every channel count of the critic): a thread
+// only ever meets channels tid % C (+ 256, ...), so it accumulates in registers (up to four channel slots) and touches shared memory once.
 __global__ void __launch_bounds__(256) bn_bwd_bwd_reduce_kernel(View r, View y, View dz, const float* __restrict__ mean, const float* __restrict__ invstd,
-                                                               double* __restrict__ sums, int64_t total, int64_t chunk) {
+                                                               double* __restrict__ sums, int rows_per_cta) {
   extern __shared__ float acc[];                 // [3][C]
-  const int C = r.c;
+  const int C = r.c, WC = r.w * C;
   for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) acc[i] = 0.f;
   __syncthreads();
-  const int64_t lo = (int64_t)blockIdx.x * chunk, hi = min(total, lo + chunk);
-  for (int64_t idx = lo + threadIdx.x; idx < hi; idx += blockDim.x) {
-    int c; int64_t off;
-    decode(r, idx, c, off);
-    const float rv = ld_rt(r.ptr, r.dtype, off);
-    const float yv = ld_rt(y.ptr, y.dtype, offset_like(y, idx));
-    const float dv = ld_rt(dz.ptr, dz.dtype, offset_like(dz, idx));
-    const float xh = (yv - mean[c]) * invstd[c];
-    atomicAdd(&acc[c], rv);
-    atomicAdd(&acc[C + c], rv * xh);
-    atomicAdd(&acc[2 * C + c], rv * dv);
+  const int nslots = C > 256 ? C / 256 : 1;
+  float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+  float mu[4], is[4];
+  for (int k = 0; k < 4; ++k) { const int c = (threadIdx.x + 256 * k) % C; mu[k] = mean[c]; is[k] = invstd[c]; }
+  const int row0 = blockIdx.x * rows_per_cta, nrows = r.n * r.h;
+  for (int row = row0; row < row0 + rows_per_cta && row < nrows; ++row) {
+    const int n = row / r.h, h = row - n * r.h;
+    const int64_t br = row_off(r, n, h), by = row_off(y, n, h), bd = row_off(dz, n, h);
+    int k = 0;
+    for (int e = threadIdx.x; e < WC; e += 256) {
+      const int w = e / C, c = e - w * C;
+      const float rv = ld_rt(r.ptr, r.dtype, br + (int64_t)w * r.sw + (int64_t)c * r.sc);
+      const float yv = ld_rt(y.ptr, y.dtype, by + (int64_t)w * y.sw + (int64_t)c * y.sc);
+      const float dv = ld_rt(dz.ptr, dz.dtype, bd + (int64_t)w * dz.sw + (int64_t)c * dz.sc);
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (q == k) { s0[q] += rv; s1[q] = fmaf(rv, (yv - mu[q]) * is[q], s1[q]); s2[q] = fmaf(rv, dv, s2[q]); }
+      if (++k == nslots) k = 0;
+    }
+  }
+  for (int k = 0; k < nslots; ++k) {
+    const int c = (threadIdx.x + 256 * k) % C;
+    atomicAdd(&acc[c], s0[k]); atomicAdd(&acc[C + c], s1[k]); atomicAdd(&acc[2 * C + c], s2[k]);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 3 * C; i += blockDim.x)
@@ -67,9 +71,9 @@ __global__ void __launch_bounds__(256) bn_bwd_bwd_apply_kernel(View r, View y, V
                                                               const float* __restrict__ mean, const float* __restrict__ invstd,
                                                               const float* __restrict__ gamma, const double* __restrict__ dzs,
                                                               const double* __restrict__ sums, double count, int act, float slope, View u, View inj,
-                                                              float* __restrict__ dgamma, int64_t total) {
-  extern __shared__ float coef[];                // [8][C]: mr, mrx, mrp, m1, m2, gamma*invstd, invstd, mean
-  const int C = r.c;
+                                                              float* __restrict__ dgamma, int rows_per_cta) {
+  extern __shared__ float coef[];                // [10][C]: mr, mrx, mrp, m1, m2, gamma*invstd, invstd, mean, scale, shift
+  const int C = r.c, WC = r.w * C;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const double sr = sums[c], srx = sums[C + c], srd = sums[2 * C + c];
     const double m1 = dzs[c] / count, m2 = dzs[C + c] / count;
@@ -77,23 +81,28 @@ __global__ void __launch_bounds__(256) bn_bwd_bwd_apply_kernel(View r, View y, V
     coef[c] = (float)(sr / count); coef[C + c] = (float)(srx / count); coef[2 * C + c] = (float)(srp / count);
     coef[3 * C + c] = (float)m1; coef[4 * C + c] = (float)m2;
     coef[5 * C + c] = gamma[c] * invstd[c]; coef[6 * C + c] = invstd[c]; coef[7 * C + c] = mean[c];
+    coef[8 * C + c] = scale[c]; coef[9 * C + c] = shift[c];
     if (blockIdx.x == 0 && dgamma) dgamma[c] += (float)((double)invstd[c] * srp);
   }
   __syncthreads();
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-    int c; int64_t off;
-    decode(r, idx, c, off);
-    const float rv = ld_rt(r.ptr, r.dtype, off);
-    const float yv = ld_rt(y.ptr, y.dtype, offset_like(y, idx));
-    const float dv = ld_rt(dz.ptr, dz.dtype, offset_like(dz, idx));
-    const float is = coef[6 * C + c], gs = coef[5 * C + c];
-    const float xh = (yv - coef[7 * C + c]) * is;
-    const float pr = rv - coef[c] - xh * coef[C + c];
-    const float pdz = dv - coef[3 * C + c] - xh * coef[4 * C + c];
-    const float z = fmaf(yv, scale[c], shift[c]);
-    const float d = act == B200GAN_ACT_RELU ? (z > 0.f ? 1.f : 0.f) : (act == B200GAN_ACT_LRELU ? (z > 0.f ? 1.f : slope) : 1.f);
-    st_rt(u.ptr, u.dtype, offset_like(u, idx), gs * pr * d);
-    st_rt(inj.ptr, inj.dtype, offset_like(inj, idx), -(gs * is) * (xh * coef[2 * C + c] + coef[4 * C + c] * pr + coef[C + c] * pdz));
+  const int row0 = blockIdx.x * rows_per_cta, nrows = r.n * r.h;
+  for (int row = row0; row < row0 + rows_per_cta && row < nrows; ++row) {
+    const int n = row / r.h, h = row - n * r.h;
+    const int64_t br = row_off(r, n, h), by = row_off(y, n, h), bd = row_off(dz, n, h), bu = row_off(u, n, h), bi = row_off(inj, n, h);
+    for (int e = threadIdx.x; e < WC; e += 256) {
+      const int w = e / C, c = e - w * C;
+      const float rv = ld_rt(r.ptr, r.dtype, br + (int64_t)w * r.sw + (int64_t)c * r.sc);
+      const float yv = ld_rt(y.ptr, y.dtype, by + (int64_t)w * y.sw + (int64_t)c * y.sc);
+      const float dv = ld_rt(dz.ptr, dz.dtype, bd + (int64_t)w * dz.sw + (int64_t)c * dz.sc);
+      const float is = coef[6 * C + c], gs = coef[5 * C + c];
+      const float xh = (yv - coef[7 * C + c]) * is;
+      const float pr = rv - coef[c] - xh * coef[C + c];
+      const float pdz = dv - coef[3 * C + c] - xh * coef[4 * C + c];
+      const float z = fmaf(yv, coef[8 * C + c], coef[9 * C + c]);
+      const float d = act == B200GAN_ACT_RELU ? (z > 0.f ? 1.f : 0.f) : (act == B200GAN_ACT_LRELU ? (z > 0.f ? 1.f : slope) : 1.f);
+      st_rt(u.ptr, u.dtype, bu + (int64_t)w * u.sw + (int64_t)c * u.sc, gs * pr * d);
+      st_rt(inj.ptr, inj.dtype, bi + (int64_t)w * inj.sw + (int64_t)c * inj.sc, -(gs * is) * (xh * coef[2 * C + c] + coef[4 * C + c] * pr + coef[C + c] * pdz));
+    }
   }
 }
 
@@ -139,16 +148,21 @@ __global__ void gp_from_norms_kernel(const double* __restrict__ sumsq, int n, fl
   if (threadIdx.x == 0) gp[0] = (float)((double)lambda * part[0] / n);
 }
 
-// out(n,.) = a[n] x(n,.) + b[n] y(n,.)   (y == nullptr: no second term).  a / b may be nullptr (= 1).
+// out(n,.) = a[n] x(n,.) + b[n] y(n,.)   (y == nullptr: no second term).  a / b may be nullptr (= 1).  One (n, h) line per blockIdx.y step.
 __global__ void __launch_bounds__(256) sample_axpby_kernel(View x, const float* __restrict__ a, View y, bool has_y, const float* __restrict__ b, View out,
-                                                          int64_t total) {
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-    int c; int64_t off;
-    decode(x, idx, c, off);
-    const int64_t n = idx / ((int64_t)x.h * x.w * x.c);
-    float v = (a ? a[n] : 1.f) * ld_rt(x.ptr, x.dtype, off);
-    if (has_y) v = fmaf(b ? b[n] : 1.f, ld_rt(y.ptr, y.dtype, offset_like(y, idx)), v);
-    st_rt(out.ptr, out.dtype, offset_like(out, idx), v);
+                                                          int rows_per_cta) {
+  const int C = x.c, WC = x.w * C, nrows = x.n * x.h;
+  const int row0 = blockIdx.x * rows_per_cta;
+  for (int row = row0; row < row0 + rows_per_cta && row < nrows; ++row) {
+    const int n = row / x.h, h = row - n * x.h;
+    const float an = a ? a[n] : 1.f, bn = b ? b[n] : 1.f;
+    const int64_t bx = row_off(x, n, h), by = row_off(y, n, h), bo = row_off(out, n, h);
+    for (int e = threadIdx.x; e < WC; e += 256) {
+      const int w = e / C, c = e - w * C;
+      float v = an * ld_rt(x.ptr, x.dtype, bx + (int64_t)w * x.sw + (int64_t)c * x.sc);
+      if (has_y) v = fmaf(bn, ld_rt(y.ptr, y.dtype, by + (int64_t)w * y.sw + (int64_t)c * y.sc), v);
+      st_rt(out.ptr, out.dtype, bo + (int64_t)w * out.sw + (int64_t)c * out.sc, v);
+    }
   }
 }
 
@@ -175,17 +189,16 @@ int gp_bn_bwd_bwd(const b200gan_view* r, const b200gan_view* y, const b200gan_vi
                   const b200gan_view* inj, float* dgamma, double* sums3, cudaStream_t st) {
   B200_CHECK_ARG(same_extent(r, y) && same_extent(r, dz) && same_extent(r, u) && same_extent(r, inj), "bn_bwd_bwd: views differ in extent");
   const int C = r->c;
-  B200_CHECK_ARG(C <= 1024, "bn_bwd_bwd: at most 1024 channels (got %d)", C);
-  const int64_t total = (int64_t)r->n * r->h * r->w * C;
+  B200_CHECK_ARG(C <= 1024 && (256 % C == 0 || C % 256 == 0), "bn_bwd_bwd: channel count must divide 256 or be a multiple of it, at most 1024 (got %d)", C);
   B200_CUDA(cudaMemsetAsync(sums3, 0, sizeof(double) * 3 * C, st));
-  int64_t blocks = (total + 256 * 64 - 1) / (256 * 64);
-  if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
-  if (blocks < 1) blocks = 1;
-  const int64_t chunk = (total + blocks - 1) / blocks;
-  bn_bwd_bwd_reduce_kernel<<<(unsigned)blocks, 256, 3 * C * sizeof(float), st>>>(to_view(r), to_view(y), to_view(dz), mean, invstd, sums3, total, chunk);
+  const int nrows = r->n * r->h;
+  int rows_per_cta = (nrows + 8 * kNumSMs - 1) / (8 * kNumSMs);
+  if (rows_per_cta < 1) rows_per_cta = 1;
+  const unsigned blocks = (unsigned)((nrows + rows_per_cta - 1) / rows_per_cta);
+  bn_bwd_bwd_reduce_kernel<<<blocks, 256, 3 * C * sizeof(float), st>>>(to_view(r), to_view(y), to_view(dz), mean, invstd, sums3, rows_per_cta);
   B200_LAUNCH_CHECK("bn_bwd_bwd_reduce_kernel");
-  bn_bwd_bwd_apply_kernel<<<(unsigned)blocks, 256, 8 * C * sizeof(float), st>>>(to_view(r), to_view(y), to_view(dz), scale, shift, mean, invstd, gamma, dz_sums,
-                                                                               sums3, (double)count, act, slope, to_view(u), to_view(inj), dgamma, total);
+  bn_bwd_bwd_apply_kernel<<<blocks, 256, 10 * C * sizeof(float), st>>>(to_view(r), to_view(y), to_view(dz), scale, shift, mean, invstd, gamma, dz_sums, sums3,
+                                                                     (double)count, act, slope, to_view(u), to_view(inj), dgamma, rows_per_cta);
   B200_LAUNCH_CHECK("bn_bwd_bwd_apply_kernel");
   return 0;
 }
@@ -209,11 +222,11 @@ int gp_from_norms(const double* sumsq, int n, float lambda, float* gp, float* co
 
 int gp_sample_axpby(const b200gan_view* x, const float* a, const b200gan_view* y, const float* b, const b200gan_view* out, cudaStream_t st) {
   B200_CHECK_ARG(same_extent(x, out) && (!y || same_extent(x, y)), "sample_axpby: views differ in extent");
-  const int64_t total = (int64_t)x->n * x->h * x->w * x->c;
-  int64_t blocks = (total + 256 * 8 - 1) / (256 * 8);
-  if (blocks > 16 * kNumSMs) blocks = 16 * kNumSMs;
-  if (blocks < 1) blocks = 1;
-  sample_axpby_kernel<<<(unsigned)blocks, 256, 0, st>>>(to_view(x), a, y ? to_view(y) : to_view(x), y != nullptr, b, to_view(out), total);
+  const int nrows = x->n * x->h;
+  int rows_per_cta = (nrows + 16 * kNumSMs - 1) / (16 * kNumSMs);
+  if (rows_per_cta < 1) rows_per_cta = 1;
+  const unsigned blocks = (unsigned)((nrows + rows_per_cta - 1) / rows_per_cta);
+  sample_axpby_kernel<<<blocks, 256, 0, st>>>(to_view(x), a, y ? to_view(y) : to_view(x), y != nullptr, b, to_view(out), rows_per_cta);
   B200_LAUNCH_CHECK("sample_axpby_kernel");
   return 0;
 }

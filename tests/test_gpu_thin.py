@@ -133,3 +133,53 @@ def test_latent_gemm_shapes(n, nz, c):
     L.call('b200gan_convT2d_wgrad', C.byref(cv), C.byref(L.view_nchw(z)), C.byref(L.view_nhwc(dy)), L.ptr(dw), None, None, st())
     dw_ref = torch.einsum('nk,nsc->kcs', zb, dy.float().reshape(n, k * k, c)).reshape(nz, c, k, k).cpu().numpy()
     close((dw - base).cpu().numpy(), dw_ref, rtol=2e-4, atol=2e-4 * np.abs(dw_ref).max(), what='latent wgrad')
+
+
+@pytest.mark.parametrize('nc,c,fine_kind', [(1, 64, 'nchw_f32'), (3, 64, 'nchw_f32'), (1, 64, 'nhwc_bf16'), (3, 16, 'nhwc_bf16'), (2, 128, 'nchw_f32')])
+def test_edge_layers_match_oracle_and_generic(nc, c, fine_kind):
+    """The image-side layers whose feature side is not 32 channels wide (conv_edge.cu: the WGAN-GP critic's Conv2d(nc -> 64) and
+    generator's ConvTranspose2d(64 -> nc)), forward / input gradient / weight gradient with the fused activations the training step
+    uses, against the numpy oracle and the generic SIMT kernels."""
+    n, h = 3, 12
+    w = rnd((c, nc, 4, 4), 1, scale=0.1)
+    if fine_kind == 'nchw_f32':
+        fine = rnd((n, nc, 2 * h, 2 * h), 2)
+        fview, to_nchw = L.view_nchw, lambda t: t.float().cpu().numpy()
+    else:
+        fine = rnd((n, 2 * h, 2 * h, nc), 2, torch.bfloat16)
+        fview, to_nchw = L.view_nhwc, lambda t: t.float().cpu().numpy().transpose(0, 3, 1, 2)
+    coarse = rnd((n, h, h, c), 3, torch.bfloat16)
+    cn = coarse.float().cpu().numpy().transpose(0, 3, 1, 2)
+    fnp, wnp = to_nchw(fine), w.cpu().numpy()
+    # down + LeakyReLU on the way out (the critic's first layer, wggan.py:52-53)
+    ya, yb = torch.empty_like(coarse), torch.empty_like(coarse)
+    fz = L.fuse(out_act=L.ACT_LRELU, out_slope=0.2)
+    L.call('b200gan_conv2d_fprop', C.byref(AUTO), C.byref(fview(fine)), L.ptr(w), None, C.byref(L.view_nhwc(ya)), C.byref(fz), st())
+    L.call('b200gan_conv2d_fprop', C.byref(SIMT), C.byref(fview(fine)), L.ptr(w), None, C.byref(L.view_nhwc(yb)), C.byref(fz), st())
+    ref = orc.conv2d_fprop(fnp, wnp, 2, 1)
+    ref = np.where(ref > 0, ref, 0.2 * ref)
+    close(ya.float().cpu().numpy().transpose(0, 3, 1, 2), ref, rtol=2.0 ** -8 * 1.05, atol=1e-5, what='edge down + LeakyReLU vs oracle')
+    close(ya.float().cpu().numpy(), yb.float().cpu().numpy(), rtol=2.0 ** -7 * 1.05, atol=1e-5, what='edge down vs generic (one bf16 ulp)')
+    # up + Tanh on the way out (the generator's last layer, wggan.py:41-42)
+    da, db = torch.empty_like(fine), torch.empty_like(fine)
+    ft = L.fuse(out_act=L.ACT_TANH)
+    L.call('b200gan_convT2d_fprop', C.byref(AUTO), C.byref(L.view_nhwc(coarse)), L.ptr(w), None, C.byref(fview(da)), C.byref(ft), st())
+    L.call('b200gan_convT2d_fprop', C.byref(SIMT), C.byref(L.view_nhwc(coarse)), L.ptr(w), None, C.byref(fview(db)), C.byref(ft), st())
+    ref = np.tanh(orc.conv2d_dgrad(cn, wnp, 2, 1, (2 * h, 2 * h)))
+    tol = dict(rtol=1e-5, atol=1e-5) if fine_kind == 'nchw_f32' else dict(rtol=2.0 ** -8 * 1.05, atol=1e-5)
+    close(to_nchw(da), ref, what='edge up + Tanh vs oracle', **tol)
+    close(to_nchw(da), to_nchw(db), what='edge up vs generic', **tol)
+    # up with the LeakyReLU backward on the gradient operand (the critic's first-layer input gradient: dy * act'(a0))
+    a0 = rnd((n, h, h, c), 5, torch.bfloat16)
+    fm = L.fuse(dy_act=L.ACT_LRELU, dy_slope=0.2, dy_ref=L.view_nhwc(a0))
+    L.call('b200gan_conv2d_dgrad', C.byref(AUTO), C.byref(L.view_nhwc(coarse)), L.ptr(w), None, C.byref(fview(da)), C.byref(fm), st())
+    mask = np.where(a0.float().cpu().numpy().transpose(0, 3, 1, 2) > 0, 1.0, 0.2).astype(np.float32)
+    ref = orc.conv2d_dgrad(cn * mask, wnp, 2, 1, (2 * h, 2 * h))
+    close(to_nchw(da), ref, what='edge up with activation backward vs oracle', **(dict(rtol=1e-5, atol=1e-5) if fine_kind == 'nchw_f32' else dict(rtol=2.0 ** -8 * 1.05, atol=1e-4)))
+    # weight gradient, plain and with the mask on the gradient operand
+    for fuse, g in ((None, cn), (fm, cn * mask)):
+        base = rnd((c, nc, 4, 4), 4)
+        dw = base.clone()
+        L.call('b200gan_conv2d_wgrad', C.byref(AUTO), C.byref(fview(fine)), C.byref(L.view_nhwc(coarse)), L.ptr(dw), None, C.byref(fuse) if fuse is not None else None, st())
+        ref = orc.conv2d_wgrad(fnp, g, 4, 2, 1)
+        close((dw - base).cpu().numpy(), ref, rtol=1e-4, atol=2e-5 * max(1.0, np.abs(ref).max()), what='edge wgrad vs oracle')

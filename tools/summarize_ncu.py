@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Table of the key metrics of an `ncu --set full` report.  usage: summarize_ncu.py <report.ncu-rep> > table.md  (and writes the raw
+"""Table of the key metrics of an `ncu --set full` report (per launch; `tensor busy %` = hmma sub-pipe active cycles / 4 / elapsed SM cycles).  usage: summarize_ncu.py <report.ncu-rep> > table.md  (and writes the raw
 CSV of the selected columns next to it when a second argument is given)."""
 import csv
 import io
@@ -15,7 +15,7 @@ idx = {n: i for i, n in enumerate(h)}
 COLS = [('time us', 'gpu__time_duration.sum'), ('dram rd MB', 'dram__bytes_read.sum'), ('dram wr MB', 'dram__bytes_write.sum'),
         ('dram %', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed'), ('L2 %', 'lts__throughput.avg.pct_of_peak_sustained_elapsed'),
         ('L2->SM GB', 'lts__t_sectors_srcunit_tex_op_read.sum'),
-        ('tensor pipe %', 'sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed'),
+        ('tensor busy %', '__tensor_busy__'),
         ('tc smem wavefronts %', 'l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed'),
         ('issue %', 'sm__inst_issued.avg.pct_of_peak_sustained_active'), ('warps active %', 'sm__warps_active.avg.pct_of_peak_sustained_active'),
         ('regs', 'launch__registers_per_thread'), ('smem KB', 'launch__shared_mem_per_block_dynamic')]
@@ -25,6 +25,13 @@ def find(name):
         if k.endswith(name): return idx[k]
     return None
 def val(row, name):
+    if name == '__tensor_busy__':
+        # UTCHMMA keeps the four tensor sub-pipes of an SM busy: busy fraction = hmma sub-pipe active cycles / 4 / elapsed SM cycles
+        # (sm__pipe_tensor_cycles_active_realtime.pct, which round 1 printed, under-reports tcgen05 work by ~3x)
+        a, b = find('sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg'), find('sm__cycles_elapsed.avg')
+        if a is None or b is None or row[a] in ('', 'no data', 'n/a') or row[b] in ('', 'no data', 'n/a'):
+            return ''
+        return f"{100.0 * float(row[a].replace(',', '')) / 4.0 / float(row[b].replace(',', '')):.1f}"
     i = find(name)
     if i is None or row[i] in ('', 'no data', 'n/a'): return ''
     v = float(row[i].replace(',', ''))
