@@ -479,6 +479,39 @@ def run_ours(args):
         rgb = {'nc': 3, 'note': 'the CLI default (train_gan.py --num-channels 3), the only configuration generate_synthetic.py loads',
                'value': B * world * k3 / (t3.item() * 1e-3), 'unit': UNIT, 'ms_per_step': t3.item() / k3, 'steps': k3}
 
+    # BASELINE.json configs[4]: WGAN-GP (wggan.py / train_wggan.py), critic with gradient-penalty double backward, n_critic = 5, batch 512 per GPU.
+    # A parity-test configuration (tests/test_gpu_wgan.py), measured here for the record: one iteration = 5 critic updates + 1 generator update
+    # on one batch of real images; images/s counts the real images consumed.  Kernel by kernel (no CUDA graph yet), local BatchNorm statistics.
+    wgan = None
+    log('wgan-gp configuration')
+    if nc == 1 and not args.no_wgan and not strong and world == 1:
+        for name in ('tr3', 'tr'):
+            if name in locals() and locals()[name] is not None:
+                locals()[name].close()
+        tr = tr3 = None
+        torch.cuda.empty_cache()
+        from gan_enhanced_pneumonia_classifier_b200 import wggan
+        from gan_enhanced_pneumonia_classifier_b200.wgan_trainer import WGANGPTrainer
+        torch.manual_seed(0)
+        wG, wD = wggan.Generator(nz, 1, 64).cuda(), wggan.Discriminator(1, 64).cuda()
+        wtr = WGANGPTrainer(wG, wD, critic_iters=5, dtype=dtype)
+        wreal = torch.rand((B, 1, 224, 224), device='cuda', generator=gen) * 2 - 1
+        wtr.step(wreal)
+        torch.cuda.synchronize()
+        kw = 3
+        w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        wl0 = wtr.launches
+        w0.record()
+        for _ in range(kw):
+            wout = wtr.step(wreal)
+        w1.record()
+        torch.cuda.synchronize()
+        wms = w0.elapsed_time(w1) / kw
+        wgan = {'model': 'WGAN-GP (wggan.py, train_wggan.py:66-93): 5 critic updates with gradient penalty (double backward) + 1 generator update per iteration',
+                'nc': 1, 'per_gpu_batch': B, 'value': B / (wms * 1e-3), 'unit': 'real images/s', 'ms_per_iteration': wms, 'steps': kw,
+                'gpu_launches_per_iteration': (wtr.launches - wl0) // kw, 'last_losses': [float(v) for v in wout.tolist()]}
+        del wtr, wG, wD
+        torch.cuda.empty_cache()
     log('roofline kernels, cpu baseline')
     if rank == 0:
         value = B * world * args.steps / (ms * 1e-3)
@@ -516,8 +549,9 @@ def run_ours(args):
             'kernel_time_ms_per_step': sum(v[1] for v in breakdown.values()) / 1e3,
             'top_kernels': [{'kernel': k, 'launches_per_step': v[0], 'us_per_step': round(v[1], 1)} for k, v in top],
         }
-        if rgb is not None:
-            line['more_configs'] = [rgb]
+        more = [c for c in (rgb, wgan) if c is not None]
+        if more:
+            line['more_configs'] = more
         if check is not None:
             line['dp_check'] = check
         print(json.dumps(line), flush=True)
@@ -539,6 +573,7 @@ def main():
     ap.add_argument('--global-batch', type=int, default=None, help='strong scaling: total batch over all ranks (BASELINE configs[2]: 4096)')
     ap.add_argument('--check', action='store_true', help='N>1: assert the data-parallel invariants on every rank before timing')
     ap.add_argument('--no-rgb', action='store_true', help='skip the additional nc=3 measurement (more_configs)')
+    ap.add_argument('--no-wgan', action='store_true', help='skip the additional WGAN-GP measurement (more_configs, 1 GPU only)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':
