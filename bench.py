@@ -2,7 +2,7 @@
 """Benchmark of the DCGAN adversarial training step (G+D iteration of train_gan.py:121-150) on B200.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B | --global-batch G] [--dtype bf16|fp32]
-                    [--nc 1|3] [--check]
+                    [--nc 1|3] [--no-check] [--no-rgb] [--no-wgan]
 
 N>1 is launched by the driver as `python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...`
 (one rank per GPU, NCCL).  Rank 0 prints ONE JSON line.
@@ -13,7 +13,7 @@ hard-wired to 224x224 (dcgan.py:26,84; a 64x64 input raises in Discriminator), s
 
 metric  = training images/s over all ranks.  Default: weak scaling, per-GPU batch fixed at 512 (configs[1] per GPU).
           --global-batch G (BASELINE.json configs[2] uses 4096): strong scaling, per-GPU batch G / N, `"scaling": "strong"`.
---check = before timing, every rank verifies the data-parallel invariants (replicas bit-identical after the steps, gradients
+--check = (default at N>1; --no-check skips it) before timing, every rank verifies the data-parallel invariants (replicas bit-identical after the steps, gradients
           equal to the sum over ranks) and the line carries `"dp_check": "ok"`; a violation aborts the run.
 value   = device-timed (CUDA events, max over ranks), inputs resident in HBM.
 e2e     = same metric through DCGANTrainer.step with HOST inputs: every step copies the real batch and the noise
@@ -571,7 +571,9 @@ def main():
     ap.add_argument('--dtype', default='bf16', choices=['bf16', 'fp32'])
     ap.add_argument('--nc', type=int, default=1, choices=[1, 3], help='image channels: 1 = the benchmark workload (BASELINE.json), 3 = the CLI default')
     ap.add_argument('--global-batch', type=int, default=None, help='strong scaling: total batch over all ranks (BASELINE configs[2]: 4096)')
-    ap.add_argument('--check', action='store_true', help='N>1: assert the data-parallel invariants on every rank before timing')
+    ap.add_argument('--check', dest='check', action='store_true', default=True,
+                    help='N>1 (default on): assert the data-parallel invariants on every rank before timing; the line carries "dp_check": "ok"')
+    ap.add_argument('--no-check', dest='check', action='store_false', help='skip the data-parallel invariants check')
     ap.add_argument('--no-rgb', action='store_true', help='skip the additional nc=3 measurement (more_configs)')
     ap.add_argument('--no-wgan', action='store_true', help='skip the additional WGAN-GP measurement (more_configs, 1 GPU only)')
     ap.add_argument('--no-cpu-baseline', action='store_true')

@@ -147,3 +147,42 @@ def test_two_replicas_on_one_gpu_match_dp_emulation():
                 else:
                     weights_close(v.cpu().numpy(), o.sd[k], what=f'rank {r} {tag}.{k}', steps=STEPS, rtol=1e-3, atol=1e-5, frac=_frac(k))
                     assert np.abs(v.cpu().numpy() - o.sd[k]).max() < (5e-5 if k.endswith('.bias') else 1.3e-3), k
+
+
+def _wgan_worker(rank, port, out_dir):
+    import torch.distributed as dist
+    from gan_enhanced_pneumonia_classifier_b200 import wggan
+    from gan_enhanced_pneumonia_classifier_b200.wgan_trainer import WGANGPTrainer
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=WORLD, device_id=torch.device('cuda', rank))
+    try:
+        torch.manual_seed(7)                                   # same initial weights on both ranks
+        G, D = wggan.Generator(NZ, NC, FM).cuda(), wggan.Discriminator(NC, FM).cuda()
+        tr = WGANGPTrainer(G, D, critic_iters=2, dtype=torch.float32)
+        torch.manual_seed(100 + rank)                          # different shards / noise / interpolation draws per rank
+        real = torch.rand(B, NC, 224, 224, device='cuda') * 2 - 1
+        hist = torch.stack([tr.step(real) for _ in range(2)]).cpu().numpy()
+        np.savez(os.path.join(out_dir, f'wgan{rank}.npz'), hist=hist, **{f'G.{k}': v.cpu().numpy() for k, v in G.state_dict().items()},
+                 **{f'D.{k}': v.cpu().numpy() for k, v in D.state_dict().items()})
+        tr.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs')
+def test_two_nccl_ranks_wgan_gp_replicas_stay_identical(tmp_path):
+    """WGANGPTrainer under data parallelism: both ranks see different data, so their losses and BatchNorm buffers differ, but every weight
+    (critic and generator, after 4 critic + 2 generator updates on summed gradients) must stay bit-identical across the replicas."""
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        port = s.getsockname()[1]
+    mp.start_processes(_wgan_worker, args=(port, str(tmp_path)), nprocs=WORLD, join=True, start_method='spawn')
+    a, b = np.load(os.path.join(str(tmp_path), 'wgan0.npz')), np.load(os.path.join(str(tmp_path), 'wgan1.npz'))
+    assert np.isfinite(a['hist']).all() and np.isfinite(b['hist']).all() and not np.array_equal(a['hist'], b['hist'])
+    for k in a.files:
+        if k == 'hist' or 'running' in k or k.endswith('num_batches_tracked'):
+            continue
+        assert np.array_equal(a[k], b[k]), f'replicas diverged on {k}'
+    assert not np.array_equal(a['D.main.3.running_mean'], b['D.main.3.running_mean'])
