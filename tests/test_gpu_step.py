@@ -100,11 +100,10 @@ def test_bf16_mode_within_tolerance_of_fp32_reference():
     for k in ('errG', 'errD', 'D_x', 'D_G_z1', 'D_G_z2', 'p_real', 'p_fake', 'p_fake_for_G'):
         close(r[k], g[f'it0.{k}'], rtol=2e-2, atol=2e-3, what=k)
     close(r['fake'][:, :, ::3, ::3], g['it0.fake'], rtol=2e-2, atol=2e-2, what='fake')
-    # Gradients: bf16 storage noise (2^-9 per stored tensor) is amplified by the BatchNorm backward, which at this
-    # fixture's batch of 3 normalises over as few as 147 samples (measured: relative L2 1e-2 at D's last layer
-    # growing to ~0.2 at the first layers, identical for the SIMT and the tcgen05 kernels; fp32 mode: 1e-6).
-    # The per-kernel bf16 parity is pinned tightly in test_gpu_tc.py / test_gpu_ops.py; here the wiring is checked
-    # through direction (cosine) and magnitude of every gradient tensor.
+    # Gradients of the bf16 path are compared where BatchNorm is well conditioned: full width, batch 32, against the reference fixture with
+    # bounds calibrated by the bf16-storage oracle (tests/test_gpu_fullsize.py).  At this fixture's batch of 3 a BatchNorm layer normalises over
+    # as few as 147 samples and bf16 storage noise alone moves the gradients by 0.2 relative L2 (SIMT and tcgen05 kernels alike), so only their
+    # wiring is checked here: direction and magnitude of every gradient tensor.
     for net in ('grads_D', 'grads_G'):
         for k, v in r[net].items():
             ref = g[f'it0.{net}.{k}'].astype(np.float64).reshape(-1)
