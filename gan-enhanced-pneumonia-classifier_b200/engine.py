@@ -133,6 +133,11 @@ class NetEngine:
         self._conv = [L.Conv(sp.k, sp.stride, sp.pad, algo) for sp in specs]
         self.launches = 0     # C-ABI calls that launch kernels, made through this engine (bench.py's gpu_launches claim)
         self._ws = None       # zeroed fp32 scratch for the split-K reduction of the tensor-core weight gradients
+        # Optional second stream for the weight-gradient launches (set by the fused trainer): nothing on the way down depends on
+        # them (the next layer needs only the input gradient), so they leave the backward pass's critical path and co-run with its
+        # HBM-bound BatchNorm passes.  `join_wgrads()` is the point where the compute stream waits for them.
+        self.wgrad_stream = None
+        self._side_keep = []  # operands of weight gradients still in flight on wgrad_stream (kept from the caching allocator)
         self.weights_version = None   # see _pack
         self._packed = {}
 
@@ -315,11 +320,21 @@ class NetEngine:
                 L.call('b200gan_bn_act_bwd_apply', C.byref(d.v), C.byref(lc.a.v), C.byref(lc.a.v), None, None, None, None, None, None, 0,
                        sp.act, LRELU_SLOPE, C.byref(dy.v), None, None, st)
                 self.launches += 1
-            if need_wgrad and grads[gi] is not None:
-                self._wgrad(i, lc.x, dy, grads[gi], st, fuse=L.fuse(**fuse_kw) if fuse_kw else None)
-            if need_wgrad and on_ready is not None:
-                for j in range(gi + nparam - 1, gi - 1, -1):
-                    on_ready(j)
+            side = self.wgrad_stream if (need_wgrad and grads[gi] is not None) else None
+            if side is not None:
+                side.wait_stream(torch.cuda.current_stream())      # dy (and dgamma / dbeta of this layer) are final
+                with torch.cuda.stream(side):
+                    self._wgrad(i, lc.x, dy, grads[gi], L.stream_ptr(), fuse=L.fuse(**fuse_kw) if fuse_kw else None)
+                    if on_ready is not None:                       # the bucket's all-reduce forks from the stream the gradient is on
+                        for j in range(gi + nparam - 1, gi - 1, -1):
+                            on_ready(j)
+                self._side_keep.append((lc, dy))
+            else:
+                if need_wgrad and grads[gi] is not None:
+                    self._wgrad(i, lc.x, dy, grads[gi], st, fuse=L.fuse(**fuse_kw) if fuse_kw else None)
+                if need_wgrad and on_ready is not None:
+                    for j in range(gi + nparam - 1, gi - 1, -1):
+                        on_ready(j)
             masked = False
             if i > 0:
                 below, lb = self.specs[i - 1], ctxs[i - 1]
@@ -338,6 +353,12 @@ class NetEngine:
             elif dinput is not None:
                 self._dgrad(i, dy, p.w, dinput, st, lc.wp_down, lc.wp_up, fuse=L.fuse(**fuse_kw) if fuse_kw else None)
         return dinput
+
+    def join_wgrads(self):
+        """Make the current stream wait for the weight gradients launched on `wgrad_stream` (call before the gradients are read)."""
+        if self.wgrad_stream is not None:
+            torch.cuda.current_stream().wait_stream(self.wgrad_stream)
+        self._side_keep.clear()
 
     def param_order(self, module):
         """The parameters in `module.parameters()` order: conv weight, then BN weight, bias per layer."""

@@ -75,6 +75,12 @@ class DCGANTrainer:
         self.engG = E.NetEngine(netG._specs(), True, dtype, algo)
         self.engD = E.NetEngine(netD._specs(), False, dtype, algo)
         self.engG.weights_version = self.engD.weights_version = 0      # this trainer owns the weights: repack only after Adam
+        dev = next(netD.parameters()).device
+        if os.environ.get('B200GAN_WGRAD_STREAM', '1') != '0' and dev.type == 'cuda':
+            # weight gradients off the backward pass's critical path (engine.NetEngine.wgrad_stream); B200GAN_WGRAD_STREAM=0 is the
+            # single-stream order, kept for A/B timing
+            self.engG.wgrad_stream = self.engD.wgrad_stream = torch.cuda.Stream(device=dev)
+        self.gfwd_stream = torch.cuda.Stream(device=dev) if (os.environ.get('B200GAN_GFWD_STREAM', '1') != '0' and dev.type == 'cuda') else None
         self.arenaG = _Arena(self.engG.param_order(netG))
         self.arenaD = _Arena(self.engD.param_order(netD))
         self.dtype = dtype
@@ -236,16 +242,25 @@ class DCGANTrainer:
         readyG = self.bucketsG.ready if (overlap and self.comm is not None) else None
         # (1) D step ------------------------------------------------------------- train_gan.py:122-141
         self.arenaD.grad.zero_()
+        if self.gfwd_stream is not None:
+            # the Generator's forward does not depend on the real half of the D step: it runs beside it on its own stream
+            self.gfwd_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.gfwd_stream):
+                fake, ctx_g = self.engG.forward(self._as_input(noise), pG, True, True)
         logit_r, ctx_r = self.engD.forward(self._as_input(real), pD, True, True, last_act=False)
         m_real, dl = self._bce(logit_r, REAL_LABEL)
         self.engD.backward(ctx_r, pD, None, self.arenaD.grads, dlogit=dl)
         del ctx_r
-        fake, ctx_g = self.engG.forward(self._as_input(noise), pG, True, True)
+        if self.gfwd_stream is not None:
+            torch.cuda.current_stream().wait_stream(self.gfwd_stream)
+        else:
+            fake, ctx_g = self.engG.forward(self._as_input(noise), pG, True, True)
         logit_f, ctx_f = self.engD.forward(fake, pD, True, True, last_act=False)
         m_fake, dl = self._bce(logit_f, FAKE_LABEL)
         self.bucketsD.begin()                    # real + fake gradients have both accumulated once this backward has written them
         self.engD.backward(ctx_f, pD, None, self.arenaD.grads, dlogit=dl, on_ready=readyD)
         del ctx_f
+        self.engD.join_wgrads()
         yield 'D'
         self._adam(self.arenaD)
         self.engD.weights_version += 1
@@ -259,6 +274,7 @@ class DCGANTrainer:
         self.bucketsG.begin()
         self.engG.backward(ctx_g, pG, dfake, self.arenaG.grads, on_ready=readyG)
         del ctx_g
+        self.engG.join_wgrads()
         yield 'G'
         self._adam(self.arenaG)
         self.engG.weights_version += 1
