@@ -71,6 +71,12 @@ PROTOTYPES = {
     'b200gan_sample_axpby': [_VP, _vp, _VP, _vp, _VP, _vp],
     'b200gan_bn_bwd_bwd': [_VP, _VP, _VP, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _VP, _VP, _vp, _vp, _vp],
     'b200gan_mean_f32': [_vp, _i64, _f32, _vp, _vp],
+    'b200gan_embed_add': [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp],
+    'b200gan_embed_bwd': [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp],
+    'b200gan_upconv3_fold': [_vp, _i32, _i32, _vp, _vp],
+    'b200gan_upconv3_unfold': [_vp, _i32, _i32, _vp, _vp],
+    'b200gan_class_proj_fwd': [_VP, _vp, _vp, _vp, _vp],
+    'b200gan_class_proj_bwd': [_VP, _vp, _vp, _vp, _VP, _i32, _vp, _vp],
     'b200gan_dp_unique_id': [_vp],
     'b200gan_dp_init': [_vp, _i32, _i32, C.POINTER(_vp)],
     'b200gan_dp_allreduce_bucket': [_vp, _vp, _i64, _vp],

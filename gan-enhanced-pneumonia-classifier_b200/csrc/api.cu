@@ -98,6 +98,15 @@ int gp_from_norms(const double* sumsq, int n, float lambda, float* gp, float* co
 int gp_sample_axpby(const b200gan_view* x, const float* a, const b200gan_view* y, const float* b, const b200gan_view* out, cudaStream_t st);
 int gp_mean_f32(const float* x, int64_t n, float scale, float* out, cudaStream_t st);
 
+// cgan_ops.cu
+int cgan_embed_add(const float* table, const int64_t* labels, const float* z, int batch, int dim, int tail, float* out, cudaStream_t st);
+int cgan_embed_bwd(const float* dx, const int64_t* labels, int batch, int dim, int stride, int classes, float* dtable, cudaStream_t st);
+int cgan_upconv3_fold(const float* w3, int co, int ci, float* w4, cudaStream_t st);
+int cgan_upconv3_unfold(const float* dw4, int co, int ci, float* dw3, cudaStream_t st);
+int cgan_class_proj_fwd(const b200gan_view* x, const float* table, const int64_t* labels, float* out, cudaStream_t st);
+int cgan_class_proj_bwd(const b200gan_view* x, const float* table, const int64_t* labels, const float* dout, const b200gan_view* dx, int classes,
+                        float* dtable, cudaStream_t st);
+
 static int check_conv(const b200gan_conv* cv) {
   if (!cv) { set_error("null conv descriptor"); return B200GAN_ERR_BAD_ARG; }
   if (cv->k <= 0 || cv->stride <= 0 || cv->pad < 0 || cv->k > 16) { set_error("bad conv geometry k=%d s=%d p=%d", cv->k, cv->stride, cv->pad); return B200GAN_ERR_BAD_ARG; }
@@ -457,6 +466,44 @@ int b200gan_bn_bwd_bwd(const b200gan_view* r, const b200gan_view* y, const b200g
 int b200gan_mean_f32(const float* x, int64_t n, float scale, float* out, void* stream) {
   B200_CHECK_ARG(x && out && n > 0, "mean_f32: bad argument");
   return gp_mean_f32(x, n, scale, out, (cudaStream_t)stream);
+}
+
+int b200gan_embed_add(const float* table, const int64_t* labels, const float* z, int32_t batch, int32_t dim, int32_t tail, float* out, void* stream) {
+  B200_CHECK_ARG(table && labels && out && batch > 0 && dim > 0 && tail >= 0, "embed_add: bad argument");
+  return cgan_embed_add(table, labels, z, batch, dim, tail, out, (cudaStream_t)stream);
+}
+
+int b200gan_embed_bwd(const float* dx, const int64_t* labels, int32_t batch, int32_t dim, int32_t stride, int32_t num_classes, float* dtable,
+                      void* stream) {
+  B200_CHECK_ARG(dx && labels && dtable && batch > 0 && dim > 0 && stride >= dim && num_classes > 0, "embed_bwd: bad argument");
+  return cgan_embed_bwd(dx, labels, batch, dim, stride, num_classes, dtable, (cudaStream_t)stream);
+}
+
+int b200gan_upconv3_fold(const float* w3, int32_t co, int32_t ci, float* w4, void* stream) {
+  B200_CHECK_ARG(w3 && w4 && co > 0 && ci > 0, "upconv3_fold: bad argument");
+  return cgan_upconv3_fold(w3, co, ci, w4, (cudaStream_t)stream);
+}
+
+int b200gan_upconv3_unfold(const float* dw4, int32_t co, int32_t ci, float* dw3, void* stream) {
+  B200_CHECK_ARG(dw4 && dw3 && co > 0 && ci > 0, "upconv3_unfold: bad argument");
+  return cgan_upconv3_unfold(dw4, co, ci, dw3, (cudaStream_t)stream);
+}
+
+int b200gan_class_proj_fwd(const b200gan_view* x, const float* table, const int64_t* labels, float* out, void* stream) {
+  int rc;
+  if ((rc = check_view(x, "class_proj_fwd"))) return rc;
+  B200_CHECK_ARG(table && labels && out, "class_proj_fwd: null pointer");
+  return cgan_class_proj_fwd(x, table, labels, out, (cudaStream_t)stream);
+}
+
+int b200gan_class_proj_bwd(const b200gan_view* x, const float* table, const int64_t* labels, const float* dout, const b200gan_view* dx,
+                           int32_t num_classes, float* dtable, void* stream) {
+  int rc;
+  if ((rc = check_view(x, "class_proj_bwd"))) return rc;
+  if (dx && (rc = check_view(dx, "class_proj_bwd"))) return rc;
+  B200_CHECK_ARG(table && labels && dout && num_classes > 0, "class_proj_bwd: bad argument");
+  B200_CHECK_ARG(!dx || (dx->n == x->n && dx->h == x->h && dx->w == x->w && dx->c == x->c), "class_proj_bwd: dx and x differ in extent");
+  return cgan_class_proj_bwd(x, table, labels, dout, dx, num_classes, dtable, (cudaStream_t)stream);
 }
 
 int b200gan_gather_augment(const uint8_t* cache, int64_t num_images, const int64_t* index, const uint8_t* flip, const float* mean,

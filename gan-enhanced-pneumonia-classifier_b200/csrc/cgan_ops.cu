@@ -1,0 +1,173 @@
+// Kernels specific to the conditional GAN (reference src/cgan.py) -- the pieces around its convolutions:
+//   * label conditioning of the Generator (cgan.py:22,55-56): x = z + label_emb[labels], written with a trailing column of ones so that the
+//     Linear layer's bias (cgan.py:24,57) rides as one more input feature of the latent GEMM (and its gradient falls out of that GEMM's
+//     weight gradient);
+//   * nearest Upsample(2) + Conv2d(3, 1, 1) (cgan.py:28-29,33-34,38-39,43-44,48-49) as ONE stride-2 transposed convolution: an output pixel
+//     2i+a reads upsampled pixels 2i+a-1 .. 2i+a+1, i.e. source pixels {i-1, i, i} (a = 0) or {i, i, i+1} (a = 1), so per dimension the three
+//     taps fold into the two taps a ConvTranspose2d(4, 2, 1) applies to the same sources (zero padding of the upsampled border = source index
+//     out of range in both forms):   W4[kh] = sum_a A[kh][a] w3[a],  A = [[0,0,1],[0,1,1],[1,1,0],[1,0,0]]  (kh = 0..3), both dimensions,
+//     and (Cout,Cin) -> (Cin,Cout).  The folded weight feeds the ConvTranspose2d kernels (tcgen05 for the wide layers); the weight
+//     gradient folds back with the adjoint map.  4/9 of the multiply-adds of the upsample-then-convolve form, no upsampled tensor in HBM;
+//   * the projection term of the Discriminator (cgan.py:103): out[n] += <label_emb[labels[n]], features[n] in (C,H,W) order>, and its backward.
+// All fp32 arithmetic; activations f32 or bf16 through strided views.  Batch-order loops instead of atomics: results are run-to-run identical.
+#include "common.cuh"
+
+namespace b200gan {
+
+namespace {
+
+__global__ void embed_add_kernel(const float* __restrict__ table, const int64_t* __restrict__ labels, const float* __restrict__ z, int batch,
+                                 int dim, int tail, float* __restrict__ out) {
+  const int row = dim + tail;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < (int64_t)batch * row; i += (int64_t)gridDim.x * blockDim.x) {
+    const int n = (int)(i / row), d = (int)(i - (int64_t)n * row);
+    out[i] = d < dim ? table[labels[n] * dim + d] + (z ? z[(int64_t)n * dim + d] : 0.f) : 1.f;
+  }
+}
+
+// dtable[cls][d] += sum over the samples of class cls of dx[n][d]   (rows of dx are `stride` floats apart)
+__global__ void embed_bwd_kernel(const float* __restrict__ dx, const int64_t* __restrict__ labels, int batch, int dim, int stride, int classes,
+                                 float* __restrict__ dtable) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < classes * dim; i += gridDim.x * blockDim.x) {
+    const int cls = i / dim, d = i - cls * dim;
+    float s = 0.f;
+    for (int n = 0; n < batch; ++n)
+      if (labels[n] == cls) s += dx[(int64_t)n * stride + d];
+    dtable[i] += s;
+  }
+}
+
+__device__ __forceinline__ float fold_coeff(int k4, int a) {      // A[k4][a]
+  return (k4 == 0 && a == 2) || (k4 == 1 && a >= 1) || (k4 == 2 && a <= 1) || (k4 == 3 && a == 0) ? 1.f : 0.f;
+}
+
+// w4[(ci, co, kh, kw)] = sum_{a,b} A[kh][a] A[kw][b] w3[(co, ci, a, b)]
+__global__ void upconv3_fold_kernel(const float* __restrict__ w3, int co, int ci, float* __restrict__ w4) {
+  const int total = ci * co * 16;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int kw = i & 3, kh = (i >> 2) & 3, o = (i >> 4) % co, c = (i >> 4) / co;
+    const float* src = w3 + ((int64_t)o * ci + c) * 9;
+    float s = 0.f;
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b) s += fold_coeff(kh, a) * fold_coeff(kw, b) * src[a * 3 + b];
+    w4[i] = s;
+  }
+}
+
+// dw3[(co, ci, a, b)] += sum_{kh,kw} A[kh][a] A[kw][b] dw4[(ci, co, kh, kw)]
+__global__ void upconv3_unfold_kernel(const float* __restrict__ dw4, int co, int ci, float* __restrict__ dw3) {
+  const int total = co * ci * 9;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int b = i % 3, a = (i / 3) % 3, c = (i / 9) % ci, o = (i / 9) / ci;
+    const float* src = dw4 + ((int64_t)c * co + o) * 16;
+    float s = 0.f;
+#pragma unroll
+    for (int kh = 0; kh < 4; ++kh)
+#pragma unroll
+      for (int kw = 0; kw < 4; ++kw) s += fold_coeff(kh, a) * fold_coeff(kw, b) * src[kh * 4 + kw];
+    dw3[i] += s;
+  }
+}
+
+__device__ __forceinline__ int64_t feat_off(const View& v, int n, int j) {     // j = (c, h, w) flattened, the order of x.view(N, -1) on NCHW
+  const int hw = v.h * v.w, c = j / hw, r = j - c * hw, h = r / v.w, w = r - h * v.w;
+  return (int64_t)n * v.sn + (int64_t)h * v.sh + (int64_t)w * v.sw + (int64_t)c * v.sc;
+}
+
+// one CTA per sample: out[n] += <table[labels[n]], x[n]>
+__global__ void __launch_bounds__(256) class_proj_fwd_kernel(View x, const float* __restrict__ table, const int64_t* __restrict__ labels,
+                                                            float* __restrict__ out) {
+  __shared__ float part[256];
+  const int n = blockIdx.x, F = x.h * x.w * x.c;
+  const float* row = table + labels[n] * F;
+  float s = 0.f;
+  for (int j = threadIdx.x; j < F; j += 256) s = fmaf(row[j], ld_rt(x.ptr, x.dtype, feat_off(x, n, j)), s);
+  part[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) part[threadIdx.x] += part[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[n] += part[0];
+}
+
+__device__ __forceinline__ void st_any(void* base, int dtype, int64_t off, float x) {
+  if (dtype == B200GAN_F32) reinterpret_cast<float*>(base)[off] = x;
+  else reinterpret_cast<__nv_bfloat16*>(base)[off] = __float2bfloat16_rn(x);
+}
+
+// dx[n] += dout[n] * table[labels[n]]
+__global__ void class_proj_bwd_x_kernel(View dx, const float* __restrict__ table, const int64_t* __restrict__ labels, const float* __restrict__ dout) {
+  const int n = blockIdx.y, F = dx.h * dx.w * dx.c;
+  const float g = dout[n];
+  const float* row = table + labels[n] * F;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < F; j += gridDim.x * blockDim.x) {
+    const int64_t off = feat_off(dx, n, j);
+    st_any(dx.ptr, dx.dtype, off, fmaf(g, row[j], ld_rt(dx.ptr, dx.dtype, off)));
+  }
+}
+
+// dtable[cls][j] += sum over the samples of class cls of dout[n] * x[n][j]
+__global__ void class_proj_bwd_table_kernel(View x, const int64_t* __restrict__ labels, const float* __restrict__ dout, int classes,
+                                            float* __restrict__ dtable) {
+  const int F = x.h * x.w * x.c;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < classes * F; i += gridDim.x * blockDim.x) {
+    const int cls = i / F, j = i - cls * F;
+    float s = 0.f;
+    for (int n = 0; n < x.n; ++n)
+      if (labels[n] == cls) s = fmaf(dout[n], ld_rt(x.ptr, x.dtype, feat_off(x, n, j)), s);
+    dtable[i] += s;
+  }
+}
+
+int grid_for(int64_t total) { return (int)((total + 255) / 256 < 8 * kNumSMs ? (total + 255) / 256 : 8 * kNumSMs); }
+
+}  // namespace
+
+int cgan_embed_add(const float* table, const int64_t* labels, const float* z, int batch, int dim, int tail, float* out, cudaStream_t st) {
+  embed_add_kernel<<<grid_for((int64_t)batch * (dim + tail)), 256, 0, st>>>(table, labels, z, batch, dim, tail, out);
+  B200_LAUNCH_CHECK("embed_add_kernel");
+  return 0;
+}
+
+int cgan_embed_bwd(const float* dx, const int64_t* labels, int batch, int dim, int stride, int classes, float* dtable, cudaStream_t st) {
+  embed_bwd_kernel<<<grid_for((int64_t)classes * dim), 256, 0, st>>>(dx, labels, batch, dim, stride, classes, dtable);
+  B200_LAUNCH_CHECK("embed_bwd_kernel");
+  return 0;
+}
+
+int cgan_upconv3_fold(const float* w3, int co, int ci, float* w4, cudaStream_t st) {
+  upconv3_fold_kernel<<<grid_for((int64_t)co * ci * 16), 256, 0, st>>>(w3, co, ci, w4);
+  B200_LAUNCH_CHECK("upconv3_fold_kernel");
+  return 0;
+}
+
+int cgan_upconv3_unfold(const float* dw4, int co, int ci, float* dw3, cudaStream_t st) {
+  upconv3_unfold_kernel<<<grid_for((int64_t)co * ci * 9), 256, 0, st>>>(dw4, co, ci, dw3);
+  B200_LAUNCH_CHECK("upconv3_unfold_kernel");
+  return 0;
+}
+
+int cgan_class_proj_fwd(const b200gan_view* x, const float* table, const int64_t* labels, float* out, cudaStream_t st) {
+  class_proj_fwd_kernel<<<x->n, 256, 0, st>>>(to_view(x), table, labels, out);
+  B200_LAUNCH_CHECK("class_proj_fwd_kernel");
+  return 0;
+}
+
+int cgan_class_proj_bwd(const b200gan_view* x, const float* table, const int64_t* labels, const float* dout, const b200gan_view* dx, int classes,
+                        float* dtable, cudaStream_t st) {
+  const int F = x->h * x->w * x->c;
+  if (dx) {
+    class_proj_bwd_x_kernel<<<dim3((F + 255) / 256, x->n), 256, 0, st>>>(to_view(dx), table, labels, dout);
+    B200_LAUNCH_CHECK("class_proj_bwd_x_kernel");
+  }
+  if (dtable) {
+    class_proj_bwd_table_kernel<<<grid_for((int64_t)classes * F), 256, 0, st>>>(to_view(x), labels, dout, classes, dtable);
+    B200_LAUNCH_CHECK("class_proj_bwd_table_kernel");
+  }
+  return 0;
+}
+
+}  // namespace b200gan

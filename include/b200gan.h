@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define B200GAN_VERSION 400   /* major*10000 + minor*100 + patch */
+#define B200GAN_VERSION 410   /* major*10000 + minor*100 + patch */
 
 typedef enum b200gan_status {
   B200GAN_OK = 0,
@@ -237,6 +237,27 @@ int b200gan_bn_bwd_bwd(const b200gan_view* r, const b200gan_view* y, const b200g
                        int32_t act, float slope, const b200gan_view* u, const b200gan_view* inj, float* dgamma, double* workspace,
                        void* stream);
 int b200gan_mean_f32(const float* x, int64_t n, float scale, float* out, void* stream);
+
+/* ---- conditional GAN (src/cgan.py): what surrounds its convolutions.
+ *        embed_add        out[n][0..dim) = table[labels[n]] + z[n] (z NULL: lookup only), out[n][dim..dim+tail) = 1.
+ *                         Generator conditioning `z + label_emb(labels)` (cgan.py:22,55-56); tail = 1 appends the constant feature through
+ *                         which the bias of `fc` (cgan.py:24,57) rides in the latent GEMM (b200gan_convT2d_* with k=7 on the 1x1 input).
+ *        embed_bwd        dtable[c] += sum over {n : labels[n] == c} of dx[n][0..dim)   (rows of dx `stride` floats apart; nn.Embedding backward)
+ *        upconv3_fold     nearest Upsample(2) + Conv2d(3,1,1) (cgan.py:28-29 ... 48-49) == ConvTranspose2d(4,2,1) with
+ *                         w4[ci][co][kh][kw] = sum_ab A[kh][a] A[kw][b] w3[co][ci][a][b], A = [[0,0,1],[0,1,1],[1,1,0],[1,0,0]]:
+ *                         the folded weight feeds b200gan_convT2d_{fprop,dgrad,wgrad} (no upsampled tensor, 4/9 of the multiply-adds);
+ *        upconv3_unfold   the adjoint: dw3 += A^T dw4 A  (weight gradient back in the Conv2d(3) layout)
+ *        class_proj_fwd   out[n] += < table[labels[n]], x(n) flattened in (c,h,w) order >     (projection term, cgan.py:103)
+ *        class_proj_bwd   dx(n) += dout[n] table[labels[n]] (dx NULL: skipped);  dtable[c] += sum over {n : labels[n] == c} of dout[n] x(n)
+ *                         (dtable NULL: skipped).  labels: int64 on the device.  Batch-order loops, no atomics: run-to-run identical. */
+int b200gan_embed_add(const float* table, const int64_t* labels, const float* z, int32_t batch, int32_t dim, int32_t tail, float* out, void* stream);
+int b200gan_embed_bwd(const float* dx, const int64_t* labels, int32_t batch, int32_t dim, int32_t stride, int32_t num_classes, float* dtable,
+                      void* stream);
+int b200gan_upconv3_fold(const float* w3, int32_t co, int32_t ci, float* w4, void* stream);
+int b200gan_upconv3_unfold(const float* dw4, int32_t co, int32_t ci, float* dw3, void* stream);
+int b200gan_class_proj_fwd(const b200gan_view* x, const float* table, const int64_t* labels, float* out, void* stream);
+int b200gan_class_proj_bwd(const b200gan_view* x, const float* table, const int64_t* labels, const float* dout, const b200gan_view* dx,
+                           int32_t num_classes, float* dtable, void* stream);
 
 /* ---- data-parallel gradient-bucket layer (new functionality: the reference is single-device, src/train_gan.py:49; semantics in
  *      SURVEY.md section 8e).  One process per GPU; weights and Adam state replicated; every optimizer update (train_gan.py:141,150)

@@ -22,6 +22,13 @@ Fixtures
       the reference's WGAN-GP iteration (src/wggan.py modules and its unmodified `gradient_penalty`, op sequence of
       src/train_wggan.py:70-92): nz=16, ngf=ndf=8, two critic updates + one generator update; recorded noise / alpha, losses,
       gradient penalties, critic scores, every gradient and the final state dicts.
+  cgan_step_nc1.npz / cgan_step_nc3.npz
+      the reference's conditional-GAN modules (src/cgan.py) through the op sequence of src/train_cgan.py:150-193 minus the VGG16 perceptual term
+      (ImageNet weights cannot be downloaded offline): nz=16, nf=8, two iterations; recorded labels / smoothing / noise, logits, sampled fake
+      image, every gradient of both networks, history rows, initial and final state dicts.
+  cgan_main_nc3.npz
+      the UNMODIFIED `train_cgan.main(args)` (matplotlib stubbed, dataset class -> seeded in-memory dataset, PerceptualLoss -> 0), 6 epochs x 2
+      batches of 4: every torch.rand / randn / randint draw in order, the optimizers' initial parameters, history JSON, final state dicts.
   step_full_nc1.npz
       full-size nets (nz=100, ngf=ndf=64, nc=1), batch 2, 1 iteration; scalars, D probabilities, a
       strided sample of the fake image and per-tensor checksums of grads / post-step weights.
@@ -299,6 +306,174 @@ def make_wgan_fixture(wggan, name, nz, fm, nc, batch, critic_iters, seed, lambda
     print('wrote', path, os.path.getsize(path) // 1024, 'KiB', 'd_loss', [float(out[f'c{i}.d_loss']) for i in range(critic_iters)], 'g_loss', float(out['g_loss']))
 
 
+def _stub_matplotlib():
+    """matplotlib is not installed in the image: stub it before importing the reference's training scripts."""
+    mpl = types.ModuleType('matplotlib')
+    mpl.use = lambda *a, **k: None
+    plt = types.ModuleType('matplotlib.pyplot')
+    for fn in ('figure', 'plot', 'title', 'xlabel', 'ylabel', 'legend', 'grid', 'tight_layout', 'savefig', 'close', 'subplot'):
+        setattr(plt, fn, lambda *a, **k: None)
+    mpl.pyplot = plt
+    sys.modules.setdefault('matplotlib', mpl)
+    sys.modules.setdefault('matplotlib.pyplot', plt)
+
+
+def make_cgan_step_fixture(cgan, name, nz, nf, nc, batch, iters, seed):
+    """The reference's conditional-GAN modules (src/cgan.py, unmodified) driven by the op sequence of train_cgan.py:150-193 WITHOUT the VGG16
+    perceptual term (its ImageNet weights cannot be downloaded here): adversarial BCEWithLogits + 5 x feature matching.  Inputs that torch's RNG
+    would draw (noise, labels, label smoothing) come from numpy and are stored; initial weights are the modules' own (torch RNG), stored."""
+    torch.manual_seed(seed)
+    netG, netD = cgan.Generator(nz, 2, nc, nf), cgan.Discriminator(2, nc, nf)
+    rng = np.random.RandomState(seed)
+    # the reference zero-initialises nothing but BatchNorm biases; give every bias / embedding a visible value so that their paths are exercised
+    with torch.no_grad():
+        for net in (netG, netD):
+            for k, p in net.named_parameters():
+                if k.endswith('bias') and p.abs().max() == 0:
+                    p.copy_(torch.from_numpy((rng.randn(*p.shape) * 0.05).astype(np.float32)))
+    out = dict(meta=json.dumps(dict(nz=nz, nf=nf, nc=nc, batch=batch, iters=iters, seed=seed, lr=2e-4, beta1=0.5, fm_weight=5.0, torch=torch.__version__)))
+    for tag, net in (('G', netG), ('D', netD)):
+        for k, v in to_np(net.state_dict()).items():
+            out[f'init.{tag}.{k}'] = v
+    optD = torch.optim.Adam(netD.parameters(), lr=2e-4, betas=(0.5, 0.999))
+    optG = torch.optim.Adam(netG.parameters(), lr=2e-4, betas=(0.5, 0.999))
+    crit = torch.nn.BCEWithLogitsLoss()
+    hist = []
+    for it in range(iters):
+        real = torch.from_numpy(synthetic_real(seed + 10 + it, batch, nc))
+        real_labels = torch.from_numpy(rng.randint(0, 2, batch).astype(np.int64))
+        fake_labels = torch.from_numpy(rng.randint(0, 2, batch).astype(np.int64))
+        smooth_real = torch.from_numpy((0.9 - 0.1 * rng.rand(batch)).astype(np.float32))
+        smooth_fake = torch.from_numpy((0.1 + 0.1 * rng.rand(batch)).astype(np.float32))
+        noise = torch.from_numpy(rng.randn(batch, nz).astype(np.float32))
+        for k, v in (('real_labels', real_labels), ('fake_labels', fake_labels), ('smooth_real', smooth_real), ('smooth_fake', smooth_fake), ('noise', noise)):
+            out[f'it{it}.{k}'] = v.numpy().copy()
+        netD.zero_grad()
+        output_real = netD(real, real_labels, 1.0)
+        D_x = torch.sigmoid(output_real).mean().item()
+        errD_real = crit(output_real, smooth_real)
+        fake_images = netG(noise, fake_labels, 1.0)
+        output_fake = netD(fake_images.detach(), fake_labels, 1.0)
+        D_G_z1 = torch.sigmoid(output_fake).mean().item()
+        errD = errD_real + crit(output_fake, smooth_fake)
+        errD.backward()
+        out[f'it{it}.out_real'], out[f'it{it}.out_fake'] = output_real.detach().numpy().copy(), output_fake.detach().numpy().copy()
+        out[f'it{it}.fake'] = fake_images.detach().numpy()[:, :, ::5, ::5].copy()
+        for k, p in netD.named_parameters():
+            out[f'it{it}.grads_D.{k}'] = p.grad.detach().numpy().copy()
+        optD.step()
+        netG.zero_grad()
+        output_fake = netD(fake_images, fake_labels, 1.0)
+        D_G_z2 = torch.sigmoid(output_fake).mean().item()
+        errG_adv = crit(output_fake, smooth_real)
+        feats_real = netD.get_intermediate_features(real, real_labels, 1.0)
+        feats_fake = netD.get_intermediate_features(fake_images, fake_labels, 1.0)
+        errG_fm = sum(torch.mean((a - b) ** 2) for a, b in zip(feats_real, feats_fake))
+        errG = errG_adv + 5.0 * errG_fm
+        errG.backward()
+        out[f'it{it}.feat_fake_l2'] = np.array([np.sqrt((f.detach().numpy().astype(np.float64) ** 2).sum()) for f in feats_fake])
+        for k, p in netG.named_parameters():
+            out[f'it{it}.grads_G.{k}'] = p.grad.detach().numpy().copy()
+        optG.step()
+        hist.append([errD.item(), errG.item(), D_x, D_G_z1, D_G_z2, errG_fm.item()])
+    out['history'] = np.array(hist, dtype=np.float64)
+    for tag, net in (('G', netG), ('D', netD)):
+        for k, v in to_np(net.state_dict()).items():
+            out[f'final.{tag}.{k}'] = v
+    path = os.path.join(GOLDEN_DIR, name)
+    np.savez_compressed(path, **out)
+    print('wrote', path, os.path.getsize(path) // 1024, 'KiB', 'history', hist)
+
+
+def make_cgan_main_fixture(name):
+    """The reference's UNMODIFIED `train_cgan.main(args)` on CPU.  Stubs, none of which touch the reference's files: matplotlib (absent); the dataset
+    class -> a seeded in-memory dataset; `PerceptualLoss` -> a module returning 0 (VGG16's ImageNet weights cannot be downloaded offline; the term
+    is the one part of train_cgan.py this fixture does not pin).  Every torch.rand / randn / randint draw of the run is recorded in order."""
+    _stub_matplotlib()
+    import train_cgan  # the reference's file, unmodified
+
+    nz, nf, nc, bs, n_img, data_seed, epochs = 16, 8, 3, 4, 8, 4242, 6
+    real = synthetic_real(data_seed, n_img, nc)
+    labels = np.random.RandomState(data_seed + 1).randint(0, 2, n_img).astype(np.int64)
+
+    class MemoryDataset(torch.utils.data.Dataset):
+        def __init__(self, *a, **k):
+            pass
+
+        def __len__(self):
+            return n_img
+
+        def __getitem__(self, i):
+            return torch.from_numpy(real[i]), torch.tensor(labels[i])
+
+    class NoPerceptual(torch.nn.Module):
+        def forward(self, x, y):
+            return torch.zeros(())
+
+    class OrderedLoader(torch.utils.data.DataLoader):          # the reference asks for shuffle=True: keep the order replayable
+        def __init__(self, ds, batch_size, shuffle, num_workers):
+            super().__init__(ds, batch_size=batch_size, shuffle=False, num_workers=0)
+
+    rec = dict(draws=[], init=[])
+    originals = dict(rand=torch.rand, randn=torch.randn, randint=torch.randint)
+
+    def recorder(kind):
+        def fn(*a, **k):
+            t = originals[kind](*a, **k)
+            rec['draws'].append((kind, t.detach().cpu().numpy().copy()))
+            return t
+        return fn
+
+    real_adam = torch.optim.Adam
+
+    def rec_adam(params, *a, **k):
+        params = list(params)
+        rec['init'].append([p.detach().cpu().numpy().copy() for p in params])
+        return real_adam(params, *a, **k)
+
+    train_cgan.RSNAPneumoniaDataset = MemoryDataset
+    train_cgan.DataLoader = OrderedLoader
+    train_cgan.PerceptualLoss = NoPerceptual
+    train_cgan.optim.Adam = rec_adam
+    tmp = tempfile.mkdtemp(prefix='golden_cgan_')
+    args = argparse.Namespace(
+        data_dir=tmp, model_dir=os.path.join(tmp, 'models'), output_dir=os.path.join(tmp, 'results'),
+        results_dir=os.path.join(tmp, 'results', 'metrics'), figures_dir=os.path.join(tmp, 'results', 'figures'),
+        num_channels=nc, latent_dim=nz, feature_maps_g=nf, feature_maps_d=nf, epochs=epochs, batch_size=bs, lr=2e-4, beta1=0.5, workers=0,
+        vis_batch_size=5, save_interval=5, checkpoint_interval=100, cpu=True)
+    torch.manual_seed(4321)
+    for kind in originals:
+        setattr(torch, kind, recorder(kind))
+    try:
+        train_cgan.main(args)
+    finally:
+        for kind, fn in originals.items():
+            setattr(torch, kind, fn)
+        train_cgan.optim.Adam = real_adam
+    hist = json.load(open(os.path.join(args.results_dir, 'gan_training_history.json')))
+    sdG = to_np(torch.load(os.path.join(args.model_dir, 'gan', 'generator_final.pth')))
+    sdD = to_np(torch.load(os.path.join(args.model_dir, 'gan', 'discriminator_final.pth')))
+    out = dict(meta=json.dumps(dict(nz=nz, nf=nf, nc=nc, batch=bs, n_img=n_img, data_seed=data_seed, epochs=epochs, lr=2e-4, beta1=0.5, save_interval=5,
+                                    vis_batch=5, torch=torch.__version__, draw_kinds=[k for k, _ in rec['draws']],
+                                    files=sorted(os.listdir(os.path.join(args.output_dir, 'gan_images'))))),
+               history=json.dumps(hist))
+    for i, (_, v) in enumerate(rec['draws']):
+        out[f'draw{i}'] = v
+    netG = train_cgan.Generator(nz, 2, nc, nf)
+    netD = train_cgan.Discriminator(2, nc, nf)
+    for (k, _), v in zip(netD.named_parameters(), rec['init'][0]):      # optimizerD is created first (train_cgan.py:124)
+        out[f'init.D.{k}'] = v
+    for (k, _), v in zip(netG.named_parameters(), rec['init'][1]):
+        out[f'init.G.{k}'] = v
+    for k, v in sdG.items():
+        out[f'final.G.{k}'] = v
+    for k, v in sdD.items():
+        out[f'final.D.{k}'] = v
+    path = os.path.join(GOLDEN_DIR, name)
+    np.savez_compressed(path, **out)
+    print('wrote', path, os.path.getsize(path) // 1024, 'KiB', 'draws', len(rec['draws']), 'history:', {k: v[:3] for k, v in hist.items()})
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--ref', default='/root/reference')
@@ -331,6 +506,14 @@ def main():
         make_wgan_fixture(wggan, 'wgan_small_nc1.npz', nz=16, fm=8, nc=1, batch=3, critic_iters=2, seed=800)
     if want('wgan_small_nc3.npz'):
         make_wgan_fixture(wggan, 'wgan_small_nc3.npz', nz=16, fm=8, nc=3, batch=4, critic_iters=2, seed=900)
+    import cgan  # the reference's file, unmodified
+    assert os.path.abspath(cgan.__file__).startswith(os.path.abspath(a.ref)), cgan.__file__
+    if want('cgan_step_nc1.npz'):
+        make_cgan_step_fixture(cgan, 'cgan_step_nc1.npz', nz=16, nf=8, nc=1, batch=3, iters=2, seed=1100)
+    if want('cgan_step_nc3.npz'):
+        make_cgan_step_fixture(cgan, 'cgan_step_nc3.npz', nz=16, nf=8, nc=3, batch=4, iters=2, seed=1200)
+    if want('cgan_main_nc3.npz'):
+        make_cgan_main_fixture('cgan_main_nc3.npz')
 
 
 if __name__ == '__main__':

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f'{n} declared in include/b200gan.h but not exported'
     assert sorted(list(L.PROTOTYPES) + L.OTHER_SYMBOLS) == names, 'ctypes prototypes and header differ'
-    assert lib.b200gan_version() == 400        # 0.4.0: + b200gan_dp_* (gradient-bucket layer on the library's own NCCL communicator)
+    assert lib.b200gan_version() == 410        # 0.4.1: + conditional-GAN entry points (embed_*, upconv3_*, class_proj_*)
 
 
 def test_bad_arguments_fail_loudly_without_a_gpu():
