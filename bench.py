@@ -512,6 +512,36 @@ def run_ours(args):
                 'gpu_launches_per_iteration': (wtr.launches - wl0) // kw, 'last_losses': [float(v) for v in wout.tolist()]}
         del wtr, wG, wD
         torch.cuda.empty_cache()
+
+    # BASELINE.json configs[3]: CGAN (cgan.py / train_cgan.py), CLI-default widths (feature_maps 32, nc=3), batch 1024 per GPU.  A parity-test
+    # configuration (tests/test_gpu_cgan.py), measured for the record: one iteration of train_cgan.py:150-193 WITHOUT the VGG16 perceptual term
+    # (not implemented: its ImageNet checkpoint cannot be obtained offline).  Kernel by kernel, unfused bias / BatchNorm passes, no CUDA graph.
+    cg = None
+    log('cgan configuration')
+    if nc == 1 and not args.no_cgan and not strong and world == 1:
+        from gan_enhanced_pneumonia_classifier_b200 import cgan as cgan_mod
+        from gan_enhanced_pneumonia_classifier_b200.cgan_trainer import CGANTrainer
+        torch.manual_seed(0)
+        cB = 1024
+        cG, cD = cgan_mod.Generator(nz, 2, 3, 32).cuda(), cgan_mod.Discriminator(2, 3, 32).cuda()
+        ctr = CGANTrainer(cG, cD, dtype=dtype)
+        creal = torch.rand((cB, 3, 224, 224), device='cuda', generator=gen) * 2 - 1
+        clab = torch.randint(0, 2, (cB,), device='cuda', generator=gen)
+        ctr.step(creal, clab)
+        torch.cuda.synchronize()
+        kc = 5
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(kc):
+            cout = ctr.step(creal, clab)
+        c1.record()
+        torch.cuda.synchronize()
+        cms = c0.elapsed_time(c1) / kc
+        cg = {'model': 'CGAN (cgan.py, train_cgan.py:150-193 minus the VGG16 perceptual term): feature_maps 32, projection discriminator, '
+                       'adversarial + feature-matching generator loss', 'nc': 3, 'per_gpu_batch': cB, 'value': cB / (cms * 1e-3), 'unit': UNIT,
+              'ms_per_iteration': cms, 'steps': kc, 'last_history': [float(v) for v in cout.tolist()]}
+        del ctr, cG, cD
+        torch.cuda.empty_cache()
     log('roofline kernels, cpu baseline')
     if rank == 0:
         value = B * world * args.steps / (ms * 1e-3)
@@ -549,7 +579,7 @@ def run_ours(args):
             'kernel_time_ms_per_step': sum(v[1] for v in breakdown.values()) / 1e3,
             'top_kernels': [{'kernel': k, 'launches_per_step': v[0], 'us_per_step': round(v[1], 1)} for k, v in top],
         }
-        more = [c for c in (rgb, wgan) if c is not None]
+        more = [c for c in (rgb, wgan, cg) if c is not None]
         if more:
             line['more_configs'] = more
         if check is not None:
@@ -576,6 +606,7 @@ def main():
     ap.add_argument('--no-check', dest='check', action='store_false', help='skip the data-parallel invariants check')
     ap.add_argument('--no-rgb', action='store_true', help='skip the additional nc=3 measurement (more_configs)')
     ap.add_argument('--no-wgan', action='store_true', help='skip the additional WGAN-GP measurement (more_configs, 1 GPU only)')
+    ap.add_argument('--no-cgan', action='store_true', help='skip the additional CGAN measurement (more_configs, 1 GPU only)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':

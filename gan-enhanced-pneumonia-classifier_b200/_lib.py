@@ -71,6 +71,9 @@ PROTOTYPES = {
     'b200gan_sample_axpby': [_VP, _vp, _VP, _vp, _VP, _vp],
     'b200gan_bn_bwd_bwd': [_VP, _VP, _VP, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _VP, _VP, _vp, _vp, _vp],
     'b200gan_mean_f32': [_vp, _i64, _f32, _vp, _vp],
+    'b200gan_bce_logits': [_vp, _vp, _i32, _f32, _vp, _vp, _vp],
+    'b200gan_fm_pair': [_VP, _VP, _VP, _f32, _i32, _vp, _vp],
+    'b200gan_accumulate_2d': [_vp, _vp, _i32, _i32, _i32, _i64, _i64, _vp],
     'b200gan_embed_add': [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp],
     'b200gan_embed_bwd': [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp],
     'b200gan_upconv3_fold': [_vp, _i32, _i32, _vp, _vp],

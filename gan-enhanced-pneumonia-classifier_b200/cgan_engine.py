@@ -62,6 +62,21 @@ class _ConvOp:
 
     def wgrad(self, x: Act, dy: Act, dw):
         """dw += (accumulating, like autograd)."""
+        coarse = x if self.transposed else dy
+        if self.tc and coarse.v.c == 32:
+            # The tensor-core weight-gradient kernel tiles the coarse side's channels by 64.  A 32-channel coarse operand is copied into the
+            # lower half of a zeroed 64-channel tensor (one elementwise pass) instead of dropping to the generic SIMT kernel (measured at batch
+            # 1024: 13.7 ms per call on that kernel); the coarse channels are dimension 0 of dw in both geometries, so the real block of the
+            # padded gradient is its leading half.
+            wide = _nhwc(coarse.v.n, coarse.v.h, coarse.v.w, 64, coarse.t.device, coarse.t.dtype, zero=True)
+            L.call('b200gan_copy_view', C.byref(coarse.v), C.byref(Act(wide.t[..., :32], nchw=False).v), _st())
+            dwp = torch.zeros((64,) + tuple(dw.shape[1:]), device=dw.device, dtype=torch.float32)
+            self._wgrad_call(wide if self.transposed else x, dy if self.transposed else wide, dwp)
+            L.call('b200gan_accumulate_2d', L.ptr(dw), L.ptr(dwp), 0, 1, dw.numel(), 0, 1, _st())
+            return
+        self._wgrad_call(x, dy, dw)
+
+    def _wgrad_call(self, x: Act, dy: Act, dw):
         name = 'b200gan_convT2d_wgrad' if self.transposed else 'b200gan_conv2d_wgrad'
         need = int(L.load().b200gan_conv_wgrad_workspace_floats(C.byref(self.desc), C.byref(x.v), C.byref(dy.v), 1 if self.transposed else 0))
         ws = None
@@ -73,25 +88,27 @@ class _ConvOp:
 
 
 class _BNState:
-    __slots__ = ('scale', 'shift', 'mean', 'invstd')
+    __slots__ = ('scale', 'shift', 'mean', 'invstd', 'sums')
 
 
 def _bn_forward(y: Act, bn, act, out: Act, training: bool) -> _BNState:
-    """BatchNorm2d + activation (training: batch statistics, running-stat side effects; eval: running statistics)."""
-    dev, c = y.t.device, y.v.c
+    """BatchNorm2d + activation (training: batch statistics, running-stat side effects; eval: running statistics).  y / out may be stored
+    wider than the BatchNorm (zero-padded channels, see _padded): the statistics pass runs over the stored width, the finalize step over the
+    real channels, and the padded channels get scale = shift = 0, so they stay exactly zero through the dense apply pass."""
+    dev, p, c = y.t.device, y.v.c, bn.weight.shape[0]
     s = _BNState()
-    s.scale = torch.empty(c, device=dev, dtype=torch.float32)
-    s.shift = torch.empty(c, device=dev, dtype=torch.float32)
-    s.mean = s.invstd = None
+    coef = torch.zeros(4 * p, device=dev, dtype=torch.float32) if p != c else torch.empty(4 * c, device=dev, dtype=torch.float32)
+    s.scale, s.shift, s.mean, s.invstd = coef[:p], coef[p:2 * p], coef[2 * p:3 * p], coef[3 * p:]
+    s.sums = None
     if training:
-        sums = torch.empty(2 * c, device=dev, dtype=torch.float64)
-        s.mean = torch.empty(c, device=dev, dtype=torch.float32)
-        s.invstd = torch.empty(c, device=dev, dtype=torch.float32)
+        sums = torch.empty(2 * p, device=dev, dtype=torch.float64)
         L.call('b200gan_bn_stats', C.byref(y.v), L.ptr(sums), _st())
-        L.call('b200gan_bn_finalize', L.ptr(sums), c, y.v.n * y.v.h * y.v.w, L.ptr(bn.weight), L.ptr(bn.bias), L.ptr(bn.running_mean),
+        s.sums = sums if p == c else torch.cat([sums[:c], sums[p:p + c]])
+        L.call('b200gan_bn_finalize', L.ptr(s.sums), c, y.v.n * y.v.h * y.v.w, L.ptr(bn.weight), L.ptr(bn.bias), L.ptr(bn.running_mean),
                L.ptr(bn.running_var), L.ptr(bn.num_batches_tracked), BN_MOMENTUM, BN_EPS, L.ptr(s.scale), L.ptr(s.shift), L.ptr(s.mean),
                L.ptr(s.invstd), _st())
     else:
+        s.mean = s.invstd = None
         L.call('b200gan_bn_eval_coeffs', c, L.ptr(bn.weight), L.ptr(bn.bias), L.ptr(bn.running_mean), L.ptr(bn.running_var), BN_EPS,
                L.ptr(s.scale), L.ptr(s.shift), _st())
     L.call('b200gan_bn_act_fwd', C.byref(y.v), L.ptr(s.scale), L.ptr(s.shift), act, LRELU_SLOPE, C.byref(out.v), _st())
@@ -99,13 +116,33 @@ def _bn_forward(y: Act, bn, act, out: Act, training: bool) -> _BNState:
 
 
 def _bn_backward(da: Act, y: Act, s: _BNState, bn, act, dy: Act, dgamma, dbeta):
-    """native_batch_norm_backward behind the activation backward: dy (may alias da), dgamma += , dbeta +=."""
-    c = y.v.c
-    sums = torch.empty(2 * c, device=y.t.device, dtype=torch.float64)
+    """native_batch_norm_backward behind the activation backward: dy (may alias da), dgamma += , dbeta +=.  Padded channels (see _bn_forward):
+    gamma = invstd = 0 there, so dy stays exactly zero; their dgamma / dbeta land in scratch."""
+    p, c = y.v.c, bn.weight.shape[0]
+    dev = y.t.device
+    sums = torch.empty(2 * p, device=dev, dtype=torch.float64)
+    gamma, dg, db = bn.weight, dgamma, dbeta
+    if p != c:
+        gamma = _pad_vec(bn.weight.detach(), p)
+        scratch = torch.zeros(2 * p, device=dev, dtype=torch.float32)
+        dg, db = (scratch[:p], scratch[p:]) if dgamma is not None else (None, None)
     L.call('b200gan_bn_act_bwd_reduce', C.byref(da.v), C.byref(y.v), None, L.ptr(s.scale), L.ptr(s.shift), L.ptr(s.mean), L.ptr(s.invstd), act,
            LRELU_SLOPE, L.ptr(sums), _st())
     L.call('b200gan_bn_act_bwd_apply', C.byref(da.v), C.byref(y.v), None, L.ptr(s.scale), L.ptr(s.shift), L.ptr(s.mean), L.ptr(s.invstd),
-           L.ptr(bn.weight), L.ptr(sums), y.v.n * y.v.h * y.v.w, act, LRELU_SLOPE, C.byref(dy.v), L.ptr(dgamma), L.ptr(dbeta), _st())
+           L.ptr(gamma), L.ptr(sums), y.v.n * y.v.h * y.v.w, act, LRELU_SLOPE, C.byref(dy.v), L.ptr(dg), L.ptr(db), _st())
+    if p != c and dgamma is not None:
+        L.call('b200gan_accumulate_2d', L.ptr(dgamma), L.ptr(dg), 0, 1, c, 0, 1, _st())
+        L.call('b200gan_accumulate_2d', L.ptr(dbeta), L.ptr(db), 0, 1, c, 0, 1, _st())
+
+
+def _bn_again(s: _BNState, y: Act, bn):
+    """The running-statistics side effect of one more training-mode forward over the same batch with the same weights (its outputs would be
+    identical): the finalize step once more on the saved sums."""
+    c = bn.weight.shape[0]
+    scratch = torch.empty(4 * c, device=y.t.device, dtype=torch.float32)
+    L.call('b200gan_bn_finalize', L.ptr(s.sums), c, y.v.n * y.v.h * y.v.w, L.ptr(bn.weight), L.ptr(bn.bias), L.ptr(bn.running_mean),
+           L.ptr(bn.running_var), L.ptr(bn.num_batches_tracked), BN_MOMENTUM, BN_EPS, L.ptr(scratch[:c]), L.ptr(scratch[c:2 * c]),
+           L.ptr(scratch[2 * c:3 * c]), L.ptr(scratch[3 * c:]), _st())
 
 
 _ones_cache = {}
@@ -129,11 +166,18 @@ def _act_backward(da: Act, a: Act, act, dz: Act):
            C.byref(dz.v), None, None, _st())
 
 
-def _channel_sum(dy: Act) -> torch.Tensor:
-    """Gradient of a per-channel bias: sum of dy over (N,H,W), fp64 accumulation, returned as fp32."""
+def _add_channel_sum(dst: torch.Tensor, dy: Act, c: Optional[int] = None):
+    """Gradient of a per-channel bias: dst += sum of dy over (N,H,W) (fp64 accumulation); c: only the first c channels (padded tensors)."""
     sums = torch.empty(2 * dy.v.c, device=dy.t.device, dtype=torch.float64)
     L.call('b200gan_bn_stats', C.byref(dy.v), L.ptr(sums), _st())
-    return sums[:dy.v.c].float()
+    L.call('b200gan_accumulate_2d', L.ptr(dst), L.ptr(sums), 1, 1, dy.v.c if c is None else c, 0, 1, _st())
+
+
+def _buf(grads: dict, into: Optional[dict], p) -> torch.Tensor:
+    """The fp32 buffer the gradient of parameter `p` is accumulated into: the caller's (`into`, e.g. a trainer's arena) or a fresh zero one."""
+    if p not in grads:
+        grads[p] = into[p] if into is not None else torch.zeros_like(p, dtype=torch.float32)
+    return grads[p]
 
 
 def _accumulate(dst: Act, src: Act):
@@ -141,8 +185,39 @@ def _accumulate(dst: Act, src: Act):
     L.call('b200gan_sample_axpby', C.byref(dst.v), None, C.byref(src.v), None, C.byref(dst.v), _st())
 
 
-def _nhwc(n, h, w, c, dev, dtype) -> Act:
-    return Act(torch.empty((n, h, w, c), device=dev, dtype=dtype), nchw=False)
+def _nhwc(n, h, w, c, dev, dtype, zero=False) -> Act:
+    return Act((torch.zeros if zero else torch.empty)((n, h, w, c), device=dev, dtype=dtype), nchw=False)
+
+
+# Channel padding.  The tcgen05 / warp-MMA convolution kernels want channel counts that are multiples of 32; the CLI-default widths have one
+# 16-channel tensor per network (feature_maps // 2).  In the tensor-core mode such a tensor is STORED 32 channels wide, the upper half exactly
+# zero (zero-padded weight blocks produce it, zero-padded weight blocks consume it), which doubles the multiply-adds of the two layers that touch
+# it and moves them from the generic SIMT kernels onto the tensor cores (measured at batch 1024: 161 -> see DESIGN.md ms per iteration).
+# Bias and BatchNorm passes run densely over the stored width with zero-padded coefficients (the padding stays exactly zero); what must see the
+# REAL channels only (feature matching, the features handed to autograd) goes through a strided view.
+def _padded(c: int, enable: bool) -> int:
+    return (c + 31) // 32 * 32 if (enable and c >= 16 and c % 32) else c
+
+
+def _real(act: Act, c: int) -> Act:
+    return act if act.v.c == c else Act(act.t[..., :c], nchw=False)
+
+
+def _pad_block(w: torch.Tensor, d0: int, d1: int) -> torch.Tensor:
+    """w (a, b, k, k) -> (d0, d1, k, k), zero outside the original block (a copy only when something is padded)."""
+    if w.shape[0] == d0 and w.shape[1] == d1:
+        return w
+    out = torch.zeros((d0, d1) + tuple(w.shape[2:]), device=w.device, dtype=w.dtype)
+    out[:w.shape[0], :w.shape[1]] = w
+    return out
+
+
+def _pad_vec(v: torch.Tensor, d: int) -> torch.Tensor:
+    if v.shape[0] == d:
+        return v
+    out = torch.zeros(d, device=v.device, dtype=v.dtype)
+    out[:v.shape[0]] = v
+    return out
 
 
 def _f32(t, what):
@@ -170,8 +245,10 @@ class GeneratorEngine:
         self.algo = default_algo() if algo is None else algo
         self.nz, self.classes, self.nc, self.nf = latent_dim, num_classes, nc, nf
         self.ch = [nf * 8, nf * 4, nf * 2, nf, nf // 2, nc]
+        pad = self.dtype == torch.bfloat16 and self.algo != L.ALGO_SIMT
+        self.pch = [_padded(c, pad) for c in self.ch[:5]] + [nc]          # stored widths (see _padded)
         self.fc = _ConvOp(INIT_SIZE, 1, 0, True, latent_dim + 1, self.ch[0], self.dtype, self.algo)
-        self.up = [_ConvOp(4, 2, 1, True, self.ch[i], self.ch[i + 1], self.dtype, self.algo) for i in range(5)]
+        self.up = [_ConvOp(4, 2, 1, True, self.pch[i], self.pch[i + 1], self.dtype, self.algo) for i in range(5)]
 
     @staticmethod
     def conv_of(mod, i):          # i = 1..5: main[3], [7], [11], [15], [19]
@@ -186,7 +263,9 @@ class GeneratorEngine:
         w = torch.cat([mod.fc.weight.detach().t(), mod.fc.bias.detach()[None]], 0).contiguous()
         return w.view(self.nz + 1, self.ch[0], INIT_SIZE, INIT_SIZE)
 
-    def forward(self, mod, z, labels, save: bool):
+    def forward(self, mod, z, labels, save: bool, internal: bool = False):
+        """Returns (image, tape): the image as the reference's (N, nc, 224, 224) fp32 tensor, or with internal=True as an Act in the engine's own
+        layout and compute dtype (what the fused trainer hands straight to the Discriminator)."""
         training = mod.training
         if save and not training:
             raise L.B200GanError('backward through an eval-mode network is not on the training path and is not implemented')
@@ -203,6 +282,8 @@ class GeneratorEngine:
         # layer 0: fc (+bias) as the k7 transposed convolution of the 1x1 input, then main[0] BatchNorm + main[1] ReLU
         l0 = _GLayer()
         l0.x, l0.w4, l0.packs = Act(xa, nchw=False), self.fc_weight(mod), (None, None)
+        if self.pch[0] != self.ch[0]:
+            raise L.B200GanError(f'feature_maps_g = {self.nf}: the first generator width must be a multiple of 32 or below 16 in the bf16 mode')
         l0.y = _nhwc(n, INIT_SIZE, INIT_SIZE, self.ch[0], dev, self.dtype)
         self.fc.fprop(l0.x, l0.w4, l0.y, l0.packs)
         l0.a = _nhwc(n, INIT_SIZE, INIT_SIZE, self.ch[0], dev, self.dtype)
@@ -214,17 +295,23 @@ class GeneratorEngine:
             conv, op = self.conv_of(mod, i), self.up[i - 1]
             lay = _GLayer()
             lay.x = cur
-            lay.w4 = torch.empty((op.cin, op.cout, 4, 4), device=dev, dtype=torch.float32)
+            cin, cout = self.ch[i - 1], self.ch[i]                    # real widths; op.cin / op.cout are the stored ones
+            folded = torch.empty((cin, cout, 4, 4), device=dev, dtype=torch.float32)
             w3 = _f32(conv.weight.detach(), 'conv weight')
-            L.call('b200gan_upconv3_fold', L.ptr(w3), op.cout, op.cin, L.ptr(lay.w4), _st())
+            L.call('b200gan_upconv3_fold', L.ptr(w3), cout, cin, L.ptr(folded), _st())
+            lay.w4 = _pad_block(folded, op.cin, op.cout)
             lay.packs = op.pack(lay.w4)
             h = cur.v.h * 2
             lay.y = _nhwc(n, h, h, op.cout, dev, self.dtype)
             op.fprop(cur, lay.w4, lay.y, lay.packs)
             if i < 5:
-                _bias_act(lay.y, conv.bias.detach(), L.ACT_NONE, lay.y)
+                _bias_act(lay.y, _pad_vec(conv.bias.detach(), op.cout), L.ACT_NONE, lay.y)
                 lay.a = _nhwc(n, h, h, op.cout, dev, self.dtype)
                 lay.bn = _bn_forward(lay.y, self.bn_of(mod, i), L.ACT_RELU, lay.a, training)
+            elif internal:
+                lay.a, lay.bn = lay.y, None
+                _bias_act(lay.y, conv.bias.detach(), L.ACT_TANH, lay.a)                          # in place
+                lay.y = None
             else:
                 out_t = torch.empty((n, self.nc, h, h), device=dev, dtype=torch.float32)        # the reference's NCHW fp32 image
                 lay.a, lay.bn = Act(out_t, nchw=True), None
@@ -232,52 +319,50 @@ class GeneratorEngine:
                 lay.y = None
             tape.append(lay)
             cur = lay.a
-        return out_t, (tape, labels)
+        return (cur if internal else out_t), (tape, labels)
 
-    def backward(self, mod, saved, dout, need_dz: bool):
-        """Returns (dz or None, {parameter: gradient}) for one upstream gradient `dout` (N, nc, 224, 224)."""
+    def backward(self, mod, saved, dout, need_dz: bool, into: Optional[dict] = None):
+        """Returns (dz or None, {parameter: gradient}) for one upstream gradient `dout`: an (N, nc, 224, 224) fp32 tensor or an Act.  With `into`
+        ({parameter: fp32 buffer}) the gradients are accumulated there instead of into fresh tensors."""
         tape, labels = saved
-        dev = dout.device
-        n = dout.shape[0]
         grads = {}
-        d = Act(_f32(dout, 'grad_output'), nchw=True)
+        d = dout if isinstance(dout, Act) else Act(_f32(dout, 'grad_output'), nchw=True)
+        dev = d.t.device
+        n = d.v.n
         for i in range(5, 0, -1):
             lay, conv, op = tape[i], self.conv_of(mod, i), self.up[i - 1]
+            cin, cout = self.ch[i - 1], self.ch[i]
             dy = _nhwc(n, lay.a.v.h, lay.a.v.w, op.cout, dev, self.dtype)
             if lay.bn is None:
                 _act_backward(d, lay.a, L.ACT_TANH, dy)
             else:
                 bn = self.bn_of(mod, i)
-                grads[bn.weight] = torch.zeros_like(bn.weight)
-                grads[bn.bias] = torch.zeros_like(bn.bias)
-                _bn_backward(d, lay.y, lay.bn, bn, L.ACT_RELU, dy, grads[bn.weight], grads[bn.bias])
-            grads[conv.bias] = _channel_sum(dy)
+                _bn_backward(d, lay.y, lay.bn, bn, L.ACT_RELU, dy, _buf(grads, into, bn.weight), _buf(grads, into, bn.bias))
+            _add_channel_sum(_buf(grads, into, conv.bias), dy, cout)
             dw4 = torch.zeros_like(lay.w4)
             op.wgrad(lay.x, dy, dw4)
-            grads[conv.weight] = torch.zeros_like(conv.weight)
-            L.call('b200gan_upconv3_unfold', L.ptr(dw4), op.cout, op.cin, L.ptr(grads[conv.weight]), _st())
+            if dw4.shape[0] != cin or dw4.shape[1] != cout:
+                dw4 = dw4[:cin, :cout].contiguous()                 # the real block of the padded weight gradient
+            L.call('b200gan_upconv3_unfold', L.ptr(dw4), cout, cin, L.ptr(_buf(grads, into, conv.weight)), _st())
             d = _nhwc(n, lay.x.v.h, lay.x.v.w, op.cin, dev, self.dtype)
             op.dgrad(dy, lay.w4, d, lay.packs)
         l0, bn = tape[0], self.bn_of(mod, 0)
-        grads[bn.weight] = torch.zeros_like(bn.weight)
-        grads[bn.bias] = torch.zeros_like(bn.bias)
-        _bn_backward(d, l0.y, l0.bn, bn, L.ACT_RELU, d, grads[bn.weight], grads[bn.bias])
+        _bn_backward(d, l0.y, l0.bn, bn, L.ACT_RELU, d, _buf(grads, into, bn.weight), _buf(grads, into, bn.bias))
         dwa = torch.zeros_like(l0.w4)
         self.fc.wgrad(l0.x, d, dwa)
-        flat = dwa.view(self.nz + 1, -1)
-        grads[mod.fc.weight] = flat[:self.nz].t()             # back in the Linear's (out, in) layout
-        grads[mod.fc.bias] = flat[self.nz]
+        m = dwa.numel() // (self.nz + 1)                      # back in the Linear's layout: weight (out, in) from the GEMM's (in, out), bias = last row
+        L.call('b200gan_accumulate_2d', L.ptr(_buf(grads, into, mod.fc.weight)), L.ptr(dwa), 0, m, self.nz, 1, m, _st())
+        L.call('b200gan_accumulate_2d', L.ptr(_buf(grads, into, mod.fc.bias)), L.ptr(dwa.view(-1)[self.nz * m:]), 0, 1, m, 0, 1, _st())
         dxa = torch.empty((n, 1, 1, self.nz + 1), device=dev, dtype=torch.float32)
         self.fc.dgrad(d, l0.w4, Act(dxa, nchw=False), l0.packs)
-        grads[mod.label_emb.weight] = torch.zeros_like(mod.label_emb.weight)
-        L.call('b200gan_embed_bwd', L.ptr(dxa), L.ptr(labels), n, self.nz, self.nz + 1, self.classes, L.ptr(grads[mod.label_emb.weight]), _st())
+        L.call('b200gan_embed_bwd', L.ptr(dxa), L.ptr(labels), n, self.nz, self.nz + 1, self.classes, L.ptr(_buf(grads, into, mod.label_emb.weight)), _st())
         dz = dxa.view(n, self.nz + 1)[:, :self.nz].contiguous() if need_dz else None
         return dz, grads
 
 
 # ------------------------------------------------------------------------------------------------ Discriminator
 class _DLayer:
-    __slots__ = ('x', 'y', 'a', 'bn', 'packs')
+    __slots__ = ('x', 'y', 'a', 'bn', 'packs', 'w')
 
 
 class DiscriminatorEngine:
@@ -290,7 +375,9 @@ class DiscriminatorEngine:
         self.algo = default_algo() if algo is None else algo
         self.classes, self.nc, self.nf = num_classes, nc, nf
         self.ch = [nc, nf // 2, nf, nf * 2, nf * 4, nf * 8]
-        self.down = [_ConvOp(4, 2, 1, False, self.ch[i], self.ch[i + 1], self.dtype, self.algo) for i in range(5)]
+        self.pch = list(self.ch)                                          # stored widths: the first layer's output may be padded (see _padded)
+        self.pch[1] = _padded(self.ch[1], self.dtype == torch.bfloat16 and self.algo != L.ALGO_SIMT)
+        self.down = [_ConvOp(4, 2, 1, False, self.pch[i], self.pch[i + 1], self.dtype, self.algo) for i in range(5)]
         self.head = _ConvOp(INIT_SIZE, 1, 0, False, self.ch[5], 1, self.dtype, self.algo)
 
     def conv_of(self, mod, i):
@@ -304,26 +391,31 @@ class DiscriminatorEngine:
         training = mod.training
         if save and not training:
             raise L.B200GanError('backward through an eval-mode network is not on the training path and is not implemented')
-        dev = x.device
-        n = x.shape[0]
-        if x.dim() != 4 or x.shape[1] != self.nc or x.shape[2] != 32 * INIT_SIZE or x.shape[3] != 32 * INIT_SIZE:
-            raise L.B200GanError(f'expected images of shape (N,{self.nc},{32 * INIT_SIZE},{32 * INIT_SIZE}), got {tuple(x.shape)}')
-        xin = x.detach()
-        if xin.dtype != torch.float32:
-            xin = xin.float()
+        if isinstance(x, Act):                      # already in the engine's layout (the fused trainer's fake batch)
+            cur = x
+        else:
+            if x.dim() != 4:
+                raise L.B200GanError(f'expected images of shape (N,{self.nc},{32 * INIT_SIZE},{32 * INIT_SIZE}), got {tuple(x.shape)}')
+            xin = x.detach()
+            if xin.dtype not in (torch.float32, torch.bfloat16):
+                xin = xin.float()
+            cur = Act(xin, nchw=True)
+        dev, n = cur.t.device, cur.v.n
+        if cur.v.c != self.nc or cur.v.h != 32 * INIT_SIZE or cur.v.w != 32 * INIT_SIZE:
+            raise L.B200GanError(f'expected images of shape (N,{self.nc},{32 * INIT_SIZE},{32 * INIT_SIZE}), got (N,{cur.v.c},{cur.v.h},{cur.v.w})')
         labels = _labels(labels, n, self.classes, dev)
         tape: List[_DLayer] = []
-        cur = Act(xin, nchw=True)
         for i in range(5):
             conv, op = self.conv_of(mod, i), self.down[i]
             lay = _DLayer()
-            lay.x, lay.packs = cur, op.pack(_f32(conv.weight.detach(), 'conv weight'))
+            lay.w = _pad_block(_f32(conv.weight.detach(), 'conv weight'), op.cout, op.cin)
+            lay.x, lay.packs = cur, op.pack(lay.w)
             h = cur.v.h // 2
             lay.y = _nhwc(n, h, h, op.cout, dev, self.dtype)
-            op.fprop(cur, conv.weight.detach(), lay.y, lay.packs)
+            op.fprop(cur, lay.w, lay.y, lay.packs)
             if i == 0:
                 lay.a, lay.bn = lay.y, None
-                _bias_act(lay.y, conv.bias.detach(), L.ACT_LRELU, lay.a)           # in place, as the reference's inplace LeakyReLU
+                _bias_act(lay.y, _pad_vec(conv.bias.detach(), op.cout), L.ACT_LRELU, lay.a)      # in place, as the reference's inplace LeakyReLU
             else:
                 _bias_act(lay.y, conv.bias.detach(), L.ACT_NONE, lay.y)
                 lay.a = _nhwc(n, h, h, op.cout, dev, self.dtype)
@@ -345,15 +437,32 @@ class DiscriminatorEngine:
     def feature_tensors(self, tape) -> List[torch.Tensor]:
         """The distinct intermediates of main[:-1] as NCHW fp32 tensors, in order [a0, y1, a1, y2, a2, y3, a3, y4, a4]."""
         outs = []
-        for i, lay in enumerate(tape):
-            for src in ([lay.a] if i == 0 else [lay.y, lay.a]):
-                t = torch.empty((src.v.n, src.v.c, src.v.h, src.v.w), device=src.t.device, dtype=torch.float32)
-                L.call('b200gan_copy_view', C.byref(src.v), C.byref(Act(t, nchw=True).v), _st())
-                outs.append(t)
+        for _, src in self.feature_acts(tape):
+            t = torch.empty((src.v.n, src.v.c, src.v.h, src.v.w), device=src.t.device, dtype=torch.float32)
+            L.call('b200gan_copy_view', C.byref(src.v), C.byref(Act(t, nchw=True).v), _st())
+            outs.append(t)
         return outs
 
-    def backward(self, mod, saved, dlogits: Optional[torch.Tensor], dfeats: Optional[List[Optional[torch.Tensor]]], need_dx: bool, need_dw: bool):
-        """Gradients for the upstream gradient of the logits (N,) and / or of the nine feature tensors.  Returns (dx or None, {param: grad})."""
+    def feature_acts(self, tape):
+        """[(stored Act, the same restricted to its real channels)] for [a0, y1, a1, y2, a2, y3, a3, y4, a4]."""
+        out = []
+        for i, lay in enumerate(tape):
+            for src in ([lay.a] if i == 0 else [lay.y, lay.a]):
+                out.append((src, _real(src, self.ch[i + 1])))
+        return out
+
+    def replay_running_stats(self, mod, saved):
+        """What one more training-mode forward over the same batch would do to the BatchNorm buffers (train_cgan.py:181 and :188 run the
+        Discriminator twice on the same fake batch with the same weights; the second pass's outputs are the first's)."""
+        for i, lay in enumerate(saved[0]):
+            if lay.bn is not None:
+                _bn_again(lay.bn, lay.y, self.bn_of(mod, i))
+
+    def backward(self, mod, saved, dlogits: Optional[torch.Tensor], dfeats: Optional[list], need_dx: bool, need_dw: bool, into: Optional[dict] = None,
+                 dx_out: Optional[Act] = None):
+        """Gradients for the upstream gradient of the logits (N,) and / or of the nine feature tensors [a0, y1, a1, ..., y4, a4] (NCHW fp32
+        tensors or Acts in any layout; entries may be None).  Returns (dx or None, {param: grad}); `into`: see GeneratorEngine.backward;
+        `dx_out`: where the input gradient goes (default: a fresh NCHW fp32 tensor)."""
         tape, labels = saved
         dev = tape[0].x.t.device
         n = tape[0].x.v.n
@@ -370,49 +479,50 @@ class DiscriminatorEngine:
             table = _f32(mod.label_emb.weight.detach(), 'label_emb.weight')
             dtable = None
             if need_dw:
-                grads[conv.weight] = torch.zeros_like(conv.weight)
-                self.head.wgrad(top.a, dla, grads[conv.weight])
-                grads[conv.bias] = _channel_sum(dla)
-                dtable = grads[mod.label_emb.weight] = torch.zeros_like(mod.label_emb.weight)
+                self.head.wgrad(top.a, dla, _buf(grads, into, conv.weight))
+                _add_channel_sum(_buf(grads, into, conv.bias), dla)
+                dtable = _buf(grads, into, mod.label_emb.weight)
             L.call('b200gan_class_proj_bwd', C.byref(top.a.v), L.ptr(table), L.ptr(labels), L.ptr(dl), C.byref(d.v), self.classes, L.ptr(dtable), _st())
 
         def feat(j):
-            return None if dfeats is None or dfeats[j] is None else Act(_f32(dfeats[j], 'grad of features'), nchw=True)
+            if dfeats is None or dfeats[j] is None:
+                return None
+            return dfeats[j] if isinstance(dfeats[j], Act) else Act(_f32(dfeats[j], 'grad of features'), nchw=True)
 
         for i in range(4, -1, -1):
             lay, conv, op = tape[i], self.conv_of(mod, i), self.down[i]
             ga = feat(2 * i)                  # a_i sits at position 2i of [a0, y1, a1, ..., y4, a4]
-            if ga is not None:
-                if have_d:
-                    _accumulate(d, ga)
-                else:
-                    L.call('b200gan_copy_view', C.byref(ga.v), C.byref(d.v), _st())
-                    have_d = True
             if not have_d:
                 d.t.zero_()                   # no gradient reaches this depth from above (memset)
                 have_d = True
+            if ga is not None:
+                _accumulate(_real(d, ga.v.c), ga)        # (a gradient over the real channels of a padded tensor lands on its real channels)
             if lay.bn is None:
                 _act_backward(d, lay.a, L.ACT_LRELU, d)
             else:
                 bn = self.bn_of(mod, i)
-                dg = db = None
-                if need_dw:
-                    dg = grads[bn.weight] = torch.zeros_like(bn.weight)
-                    db = grads[bn.bias] = torch.zeros_like(bn.bias)
+                dg = _buf(grads, into, bn.weight) if need_dw else None
+                db = _buf(grads, into, bn.bias) if need_dw else None
                 _bn_backward(d, lay.y, lay.bn, bn, L.ACT_LRELU, d, dg, db)
                 gy = feat(2 * i - 1)
                 if gy is not None:
                     _accumulate(d, gy)
             if need_dw:
-                grads[conv.bias] = _channel_sum(d)
-                grads[conv.weight] = torch.zeros_like(conv.weight)
-                op.wgrad(lay.x, d, grads[conv.weight])
+                cin, cout = self.ch[i], self.ch[i + 1]
+                _add_channel_sum(_buf(grads, into, conv.bias), d, cout)
+                if op.cin == cin and op.cout == cout:
+                    op.wgrad(lay.x, d, _buf(grads, into, conv.weight))
+                else:                         # padded layer: the real block of the padded weight gradient
+                    dwp = torch.zeros_like(lay.w)
+                    op.wgrad(lay.x, d, dwp)
+                    L.call('b200gan_accumulate_2d', L.ptr(_buf(grads, into, conv.weight)), L.ptr(dwp), 0, cout, cin * 16, op.cin * 16, 1, _st())
             if i > 0:
                 nd = _nhwc(n, lay.x.v.h, lay.x.v.w, op.cin, dev, self.dtype)
-                op.dgrad(d, conv.weight.detach(), nd, lay.packs)
+                op.dgrad(d, lay.w, nd, lay.packs)
                 d = nd
             elif need_dx:
-                dx = torch.empty((n, self.nc, lay.x.v.h, lay.x.v.w), device=dev, dtype=torch.float32)
-                op.dgrad(d, conv.weight.detach(), Act(dx, nchw=True), lay.packs)
-                return dx, grads
+                if dx_out is None:
+                    dx_out = Act(torch.empty((n, self.nc, lay.x.v.h, lay.x.v.w), device=dev, dtype=torch.float32), nchw=True)
+                op.dgrad(d, lay.w, dx_out, lay.packs)
+                return dx_out.t, grads
         return None, grads

@@ -107,6 +107,10 @@ int cgan_class_proj_fwd(const b200gan_view* x, const float* table, const int64_t
 int cgan_class_proj_bwd(const b200gan_view* x, const float* table, const int64_t* labels, const float* dout, const b200gan_view* dx, int classes,
                         float* dtable, cudaStream_t st);
 
+int cgan_bce_logits(const float* x, const float* t, int batch, float grad_scale, float* out2, float* dlogit, cudaStream_t st);
+int cgan_fm_pair(const b200gan_view* r, const b200gan_view* f, const b200gan_view* d, float coeff, int add, double* sum, cudaStream_t st);
+int cgan_accumulate_2d(float* dst, const void* src, int f64, int rows, int cols, int64_t srs, int64_t scs, cudaStream_t st);
+
 static int check_conv(const b200gan_conv* cv) {
   if (!cv) { set_error("null conv descriptor"); return B200GAN_ERR_BAD_ARG; }
   if (cv->k <= 0 || cv->stride <= 0 || cv->pad < 0 || cv->k > 16) { set_error("bad conv geometry k=%d s=%d p=%d", cv->k, cv->stride, cv->pad); return B200GAN_ERR_BAD_ARG; }
@@ -466,6 +470,27 @@ int b200gan_bn_bwd_bwd(const b200gan_view* r, const b200gan_view* y, const b200g
 int b200gan_mean_f32(const float* x, int64_t n, float scale, float* out, void* stream) {
   B200_CHECK_ARG(x && out && n > 0, "mean_f32: bad argument");
   return gp_mean_f32(x, n, scale, out, (cudaStream_t)stream);
+}
+
+int b200gan_bce_logits(const float* logit, const float* target, int32_t batch, float grad_scale, float* out2, float* dlogit, void* stream) {
+  B200_CHECK_ARG(logit && target && out2 && batch > 0, "bce_logits: bad argument");
+  return cgan_bce_logits(logit, target, batch, grad_scale, out2, dlogit, (cudaStream_t)stream);
+}
+
+int b200gan_fm_pair(const b200gan_view* real, const b200gan_view* fake, const b200gan_view* dfake, float coeff, int32_t add, double* sum, void* stream) {
+  int rc;
+  if ((rc = check_view(real, "fm_pair"))) return rc;
+  if ((rc = check_view(fake, "fm_pair"))) return rc;
+  if (dfake && (rc = check_view(dfake, "fm_pair"))) return rc;
+  B200_CHECK_ARG(sum, "fm_pair: null sum");
+  B200_CHECK_ARG(same_extent(real, fake) && (!dfake || same_extent(dfake, fake)), "fm_pair: views differ in extent");
+  return cgan_fm_pair(real, fake, dfake, coeff, add, sum, (cudaStream_t)stream);
+}
+
+int b200gan_accumulate_2d(float* dst, const void* src, int32_t src_f64, int32_t rows, int32_t cols, int64_t src_row_stride, int64_t src_col_stride,
+                          void* stream) {
+  B200_CHECK_ARG(dst && src && rows > 0 && cols > 0, "accumulate_2d: bad argument");
+  return cgan_accumulate_2d(dst, src, src_f64, rows, cols, src_row_stride, src_col_stride, (cudaStream_t)stream);
 }
 
 int b200gan_embed_add(const float* table, const int64_t* labels, const float* z, int32_t batch, int32_t dim, int32_t tail, float* out, void* stream) {

@@ -16,6 +16,11 @@ namespace b200gan {
 
 namespace {
 
+__device__ __forceinline__ void st_any(void* base, int dtype, int64_t off, float x) {
+  if (dtype == B200GAN_F32) reinterpret_cast<float*>(base)[off] = x;
+  else reinterpret_cast<__nv_bfloat16*>(base)[off] = __float2bfloat16_rn(x);
+}
+
 __global__ void embed_add_kernel(const float* __restrict__ table, const int64_t* __restrict__ labels, const float* __restrict__ z, int batch,
                                  int dim, int tail, float* __restrict__ out) {
   const int row = dim + tail;
@@ -93,11 +98,6 @@ __global__ void __launch_bounds__(256) class_proj_fwd_kernel(View x, const float
   if (threadIdx.x == 0) out[n] += part[0];
 }
 
-__device__ __forceinline__ void st_any(void* base, int dtype, int64_t off, float x) {
-  if (dtype == B200GAN_F32) reinterpret_cast<float*>(base)[off] = x;
-  else reinterpret_cast<__nv_bfloat16*>(base)[off] = __float2bfloat16_rn(x);
-}
-
 // dx[n] += dout[n] * table[labels[n]]
 __global__ void class_proj_bwd_x_kernel(View dx, const float* __restrict__ table, const int64_t* __restrict__ labels, const float* __restrict__ dout) {
   const int n = blockIdx.y, F = dx.h * dx.w * dx.c;
@@ -119,6 +119,67 @@ __global__ void class_proj_bwd_table_kernel(View x, const int64_t* __restrict__ 
     for (int n = 0; n < x.n; ++n)
       if (labels[n] == cls) s = fmaf(dout[n], ld_rt(x.ptr, x.dtype, feat_off(x, n, j)), s);
     dtable[i] += s;
+  }
+}
+
+// BCEWithLogitsLoss(mean) against per-sample targets, its gradient and the mean probability, one CTA:
+//   out2[0] = mean_i max(x,0) - x t + log1p(exp(-|x|)),  out2[1] = mean_i sigmoid(x),  dlogit[i] = grad_scale (sigmoid(x) - t) / B
+__global__ void __launch_bounds__(256) bce_logits_kernel(const float* __restrict__ x, const float* __restrict__ t, int batch, float grad_scale,
+                                                        float* __restrict__ out2, float* __restrict__ dlogit) {
+  __shared__ double part[2][256];
+  double loss = 0.0, prob = 0.0;
+  for (int i = threadIdx.x; i < batch; i += 256) {
+    const float xi = x[i], ti = t[i];
+    const float p = 1.f / (1.f + expf(-xi));
+    loss += (double)(fmaxf(xi, 0.f) - xi * ti + log1pf(expf(-fabsf(xi))));
+    prob += (double)p;
+    if (dlogit) dlogit[i] = grad_scale * (p - ti) / (float)batch;
+  }
+  part[0][threadIdx.x] = loss; part[1][threadIdx.x] = prob;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) { part[0][threadIdx.x] += part[0][threadIdx.x + o]; part[1][threadIdx.x] += part[1][threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { out2[0] = (float)(part[0][0] / batch); out2[1] = (float)(part[1][0] / batch); }
+}
+
+// Feature matching on one pair of equally shaped tensors (train_cgan.py:75-76): sum += sum (r - f)^2 (fp64), dfake = coeff (r - f)
+// (coeff = -2 weight multiplicity / numel; overwrites dfake or adds to it).  Element order follows the fake view (dense NHWC in practice).
+__global__ void __launch_bounds__(256) fm_pair_kernel(View r, View f, View d, float coeff, int add, double* __restrict__ sum) {
+  __shared__ double part[256];
+  const int64_t total = (int64_t)f.n * f.h * f.w * f.c;
+  double s = 0.0;
+  for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+    const int c = (int)(i % f.c);
+    int64_t q = i / f.c;
+    const int w = (int)(q % f.w); q /= f.w;
+    const int h = (int)(q % f.h);
+    const int n = (int)(q / f.h);
+    const float rv = ld_rt(r.ptr, r.dtype, (int64_t)n * r.sn + (int64_t)h * r.sh + (int64_t)w * r.sw + (int64_t)c * r.sc);
+    const float fv = ld_rt(f.ptr, f.dtype, (int64_t)n * f.sn + (int64_t)h * f.sh + (int64_t)w * f.sw + (int64_t)c * f.sc);
+    const float diff = rv - fv;
+    s += (double)diff * diff;
+    if (d.ptr) {
+      const int64_t off = (int64_t)n * d.sn + (int64_t)h * d.sh + (int64_t)w * d.sw + (int64_t)c * d.sc;
+      st_any(d.ptr, d.dtype, off, add ? fmaf(coeff, diff, ld_rt(d.ptr, d.dtype, off)) : coeff * diff);
+    }
+  }
+  part[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) part[threadIdx.x] += part[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) atomicAdd(sum, part[0]);
+}
+
+// dst[r][c] += src[r * srs + c * scs]   (src float or double): bias gradients out of fp64 channel sums, the Linear's gradient out of the
+// latent GEMM's transposed layout
+__global__ void accumulate_2d_kernel(float* __restrict__ dst, const void* __restrict__ src, int f64, int rows, int cols, int64_t srs, int64_t scs) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < (int64_t)rows * cols; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cols, c = i - r * cols, j = r * srs + c * scs;
+    dst[i] += f64 ? (float)reinterpret_cast<const double*>(src)[j] : reinterpret_cast<const float*>(src)[j];
   }
 }
 
@@ -167,6 +228,27 @@ int cgan_class_proj_bwd(const b200gan_view* x, const float* table, const int64_t
     class_proj_bwd_table_kernel<<<grid_for((int64_t)classes * F), 256, 0, st>>>(to_view(x), labels, dout, classes, dtable);
     B200_LAUNCH_CHECK("class_proj_bwd_table_kernel");
   }
+  return 0;
+}
+
+int cgan_bce_logits(const float* x, const float* t, int batch, float grad_scale, float* out2, float* dlogit, cudaStream_t st) {
+  bce_logits_kernel<<<1, 256, 0, st>>>(x, t, batch, grad_scale, out2, dlogit);
+  B200_LAUNCH_CHECK("bce_logits_kernel");
+  return 0;
+}
+
+int cgan_fm_pair(const b200gan_view* r, const b200gan_view* f, const b200gan_view* d, float coeff, int add, double* sum, cudaStream_t st) {
+  View dv;
+  if (d) dv = to_view(d); else dv.ptr = nullptr;
+  const int64_t total = (int64_t)f->n * f->h * f->w * f->c;
+  fm_pair_kernel<<<grid_for(total), 256, 0, st>>>(to_view(r), to_view(f), dv, coeff, add, sum);
+  B200_LAUNCH_CHECK("fm_pair_kernel");
+  return 0;
+}
+
+int cgan_accumulate_2d(float* dst, const void* src, int f64, int rows, int cols, int64_t srs, int64_t scs, cudaStream_t st) {
+  accumulate_2d_kernel<<<grid_for((int64_t)rows * cols), 256, 0, st>>>(dst, src, f64, rows, cols, srs, scs);
+  B200_LAUNCH_CHECK("accumulate_2d_kernel");
   return 0;
 }
 

@@ -1,0 +1,271 @@
+"""Drop-in for the reference's `src/train_cgan.py` (conditional GAN): same CLI flags and defaults (reference
+:249-267), same artefacts (`<model-dir>/gan/generator_epoch_%03d.pth`, `discriminator_epoch_%03d.pth`, `generator_final.pth`,
+`discriminator_final.pth`, `<output-dir>/gan_images/fake_samples_epoch_%03d_iter_%06d.png`, `<results-dir>/gan_training_history.json` with the
+nine history lists of reference :127-128 -- the five per-iteration ones stay empty there too --, `<figures-dir>/gan_loss_curve.png`), same training
+semantics (reference :150-193: randomly smoothed BCEWithLogits targets, the D-step skip rule from epoch 5 on, adversarial + feature-matching
+Generator loss, Adam betas (beta1, 0.999)).
+
+One deliberate difference, stated instead of hidden: the reference adds 10 x a VGG16 perceptual loss (:57-73,186) whose ImageNet checkpoint is
+downloaded at start-up.  That term is not implemented on the B200 path (no checkpoint offline, nothing to pin it against): on a CUDA device this
+CLI REFUSES to run unless `--no-perceptual` says the term may be dropped.  `--cpu` keeps the reference's stock-torch loop, perceptual term included
+when torchvision can load the checkpoint.
+Additive flags only: --no-perceptual, --dtype {bf16,fp32}, --synthetic N, --max-iters, --log-interval, --seed.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.optim as optim
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+if __package__ in (None, ''):
+    sys.path.insert(0, os.path.dirname(_HERE))
+    sys.path.insert(0, _HERE)
+    from gan_enhanced_pneumonia_classifier_b200.cgan import Discriminator, Generator, weights_init
+    from gan_enhanced_pneumonia_classifier_b200.cgan_trainer import CGANTrainer
+    from gan_enhanced_pneumonia_classifier_b200.train_gan import _DATA_LOADER_HINT, _save_image_grid, _save_state
+else:
+    from .cgan import Discriminator, Generator, weights_init
+    from .cgan_trainer import CGANTrainer
+    from .train_gan import _DATA_LOADER_HINT, _save_image_grid, _save_state
+
+HISTORY_KEYS = ('G_losses_iter', 'D_losses_iter', 'D_x_iter', 'D_G_z1_iter', 'D_G_z2_iter', 'G_losses_epoch', 'D_losses_epoch', 'perceptual_losses',
+                'feature_matching_losses')
+NUM_CLASSES = 2          # reference :106
+
+
+def plot_gan_losses(history, out_path):
+    """reference :19-55 (two panels: adversarial losses, additional loss components); matplotlib is optional here."""
+    try:
+        import matplotlib
+        matplotlib.use('Agg')
+        import matplotlib.pyplot as plt
+    except ImportError:
+        print(f'matplotlib is not installed: skipping {out_path}')
+        return
+    epochs = range(1, len(history['G_losses_epoch']) + 1)
+    plt.figure(figsize=(12, 6))
+    for panel, keys in ((1, (('G_losses_epoch', 'Generator Loss'), ('D_losses_epoch', 'Discriminator Loss'))),
+                        (2, (('perceptual_losses', 'Perceptual Loss'), ('feature_matching_losses', 'Feature Matching Loss')))):
+        plt.subplot(2, 1, panel)
+        for key, label in keys:
+            plt.plot(epochs, history[key], label=label, alpha=0.8)
+        plt.xlabel('Epochs')
+        plt.ylabel('Loss')
+        plt.legend()
+        plt.grid(True, linestyle='--', alpha=0.6)
+    plt.tight_layout()
+    plt.savefig(out_path)
+    plt.close()
+
+
+def _synthetic_labelled_loader(n_images, nc, batch_size, seed):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.rand(n_images, nc, 224, 224, generator=g) * 2 - 1
+    y = torch.randint(0, NUM_CLASSES, (n_images,), generator=g)
+    return torch.utils.data.DataLoader(torch.utils.data.TensorDataset(x, y), batch_size=batch_size, shuffle=True, generator=g,
+                                       pin_memory=torch.cuda.is_available())
+
+
+def _reference_cpu_iteration(netG, netD, optG, optD, criterion, perceptual, real, real_labels, epoch, latent_dim):
+    """The reference's stock-torch iteration (:150-193), used for --cpu.  Returns the seven history values."""
+    b, device = real.size(0), real.device
+    smooth_real = torch.full((b,), 0.9, device=device) - 0.1 * torch.rand(b, device=device)
+    smooth_fake = torch.full((b,), 0.1, device=device) + 0.1 * torch.rand(b, device=device)
+    netD.zero_grad()
+    out_real = netD(real, real_labels, 1.0)
+    d_x = torch.sigmoid(out_real).mean().item()
+    err_real = criterion(out_real, smooth_real)
+    noise = torch.randn(b, latent_dim, device=device)
+    fake_labels = torch.randint(0, NUM_CLASSES, (b,), device=device)
+    fake = netG(noise, fake_labels, 1.0)
+    out_fake = netD(fake.detach(), fake_labels, 1.0)
+    d_g_z1 = torch.sigmoid(out_fake).mean().item()
+    err_d = err_real + criterion(out_fake, smooth_fake)
+    if d_x < 0.8 or d_g_z1 > 0.2 or epoch < 5:
+        err_d.backward()
+        optD.step()
+    netG.zero_grad()
+    out_g = netD(fake, fake_labels, 1.0)
+    d_g_z2 = torch.sigmoid(out_g).mean().item()
+    err_p = perceptual(fake, real) if perceptual is not None else torch.zeros((), device=device)
+    err_fm = sum(torch.mean((r - f) ** 2) for r, f in zip(netD.get_intermediate_features(real, real_labels, 1.0),
+                                                         netD.get_intermediate_features(fake, fake_labels, 1.0)))
+    err_g = criterion(out_g, smooth_real) + 10.0 * err_p + 5.0 * err_fm
+    err_g.backward()
+    optG.step()
+    return torch.tensor([err_d.item(), err_g.item(), d_x, d_g_z1, d_g_z2, float(err_p), err_fm.item()])
+
+
+class _VGGPerceptual(nn.Module):
+    """reference :57-73 (CPU path only): MSE between VGG16 feature maps after relu1_2, relu2_2, relu3_3."""
+
+    def __init__(self):
+        super().__init__()
+        import torchvision.models as models
+        vgg = models.vgg16(weights=models.VGG16_Weights.IMAGENET1K_V1).features
+        self.blocks = nn.ModuleList([vgg[:4], vgg[4:9], vgg[9:16]]).eval()
+        for p in self.parameters():
+            p.requires_grad = False
+
+    def forward(self, x, y):
+        total = 0.0
+        for block in self.blocks:
+            x, y = block(x), block(y)
+            total = total + torch.mean((x - y) ** 2)
+        return total
+
+
+def main(args):
+    use_cuda = torch.cuda.is_available() and not args.cpu
+    device = torch.device('cuda' if use_cuda else 'cpu')
+    print(f'Using device: {device}')
+    no_perceptual = getattr(args, 'no_perceptual', False)
+    if use_cuda and not no_perceptual:
+        print('Error: the VGG16 perceptual term of the reference (train_cgan.py:57-73,186) is not implemented on the B200 path. '
+              'Pass --no-perceptual to train with the adversarial and feature-matching terms only, or --cpu for the stock-torch loop.')
+        return None
+    if getattr(args, 'seed', None) is not None:
+        torch.manual_seed(args.seed)
+    model_dir = os.path.join(args.model_dir, 'gan')
+    image_dir = os.path.join(args.output_dir, 'gan_images')
+    for d in (model_dir, image_dir, args.results_dir, args.figures_dir):
+        os.makedirs(d, exist_ok=True)
+
+    n_syn = getattr(args, 'synthetic', 0)
+    if n_syn:
+        dataloader = _synthetic_labelled_loader(n_syn, args.num_channels, args.batch_size, 1)
+    else:
+        try:
+            from data_loader import RSNAPneumoniaDataset, data_transforms          # the reference's src/data_loader.py
+        except ImportError as e:
+            print(f'Error loading data: {e}')
+            print(_DATA_LOADER_HINT)
+            return None
+        try:
+            dataset = RSNAPneumoniaDataset(data_dir=os.path.join(args.data_dir, 'Training', 'Images'),
+                                           metadata_file=os.path.join(args.data_dir, 'stage2_train_metadata.csv'),
+                                           transform=data_transforms['train'], is_test=False)
+            dataloader = torch.utils.data.DataLoader(dataset, batch_size=args.batch_size, shuffle=True, num_workers=args.workers)
+        except Exception as e:                                                      # reference :101-103
+            print(f'Error loading data: {e}')
+            return None
+    print(f'Loaded training data with {len(dataloader.dataset)} samples.')
+
+    netG = Generator(args.latent_dim, NUM_CLASSES, args.num_channels, args.feature_maps_g).to(device)
+    netD = Discriminator(NUM_CLASSES, args.num_channels, args.feature_maps_d).to(device)
+    netG.apply(weights_init)
+    netD.apply(weights_init)
+    fixed_noise = torch.randn(args.vis_batch_size, args.latent_dim, device=device)
+    fixed_labels = torch.tensor(np.tile(np.arange(NUM_CLASSES), args.vis_batch_size // NUM_CLASSES + 1)[:args.vis_batch_size], dtype=torch.long,
+                                device=device)
+    trainer = None
+    if use_cuda:
+        dtype = {'bf16': torch.bfloat16, 'fp32': torch.float32}[getattr(args, 'dtype', 'bf16')]
+        trainer = CGANTrainer(netG, netD, lr=args.lr, beta1=args.beta1, dtype=dtype)
+    else:
+        criterion = nn.BCEWithLogitsLoss()
+        perceptual = None if no_perceptual else _VGGPerceptual().to(device)
+        optimizerD = optim.Adam(netD.parameters(), lr=args.lr, betas=(args.beta1, 0.999))
+        optimizerG = optim.Adam(netG.parameters(), lr=args.lr, betas=(args.beta1, 0.999))
+
+    history = {k: [] for k in HISTORY_KEYS}
+    log_interval = max(1, getattr(args, 'log_interval', 50))
+    max_iters = getattr(args, 'max_iters', 0) or 0
+    iters, stop = 0, False
+    start = time.time()
+    for epoch in range(args.epochs):
+        epoch_start = time.time()
+        pending, rows = [], []
+
+        def flush():
+            if pending:
+                rows.extend(torch.stack(pending).float().cpu().tolist())          # ONE sync for log_interval iterations
+                pending.clear()
+
+        n_batches = len(dataloader)
+        for i, (real_images, real_labels) in enumerate(dataloader):
+            real_images = real_images.to(device, non_blocking=True)
+            real_labels = real_labels.to(device, non_blocking=True)
+            if trainer is not None:
+                pending.append(trainer.step(real_images, real_labels, epoch=epoch))
+            else:
+                pending.append(_reference_cpu_iteration(netG, netD, optimizerG, optimizerD, criterion, perceptual, real_images, real_labels, epoch,
+                                                        args.latent_dim))
+            last = (epoch == args.epochs - 1 and i == n_batches - 1) or (max_iters and iters + 1 >= max_iters)
+            if (iters % args.save_interval == 0) or last:
+                with torch.no_grad():                      # the networks stay in training mode, as in the reference (:208-210)
+                    fake_vis = netG(fixed_noise, fixed_labels, 1.0).detach().float().cpu()
+                _save_image_grid(fake_vis, f'{image_dir}/fake_samples_epoch_{epoch + 1:03d}_iter_{iters:06d}.png')
+            iters += 1
+            if len(pending) >= log_interval:
+                flush()
+            if max_iters and iters >= max_iters:
+                stop = True
+                break
+        flush()
+        r = np.array(rows) if rows else np.full((1, 7), np.nan)
+        history['D_losses_epoch'].append(float(r[:, 0].mean()))
+        history['G_losses_epoch'].append(float(r[:, 1].mean()))
+        history['perceptual_losses'].append(float(r[:, 5].mean()))
+        history['feature_matching_losses'].append(float(r[:, 6].mean()))
+        print(f"Epoch {epoch + 1}/{args.epochs} Summary - Time: {time.time() - epoch_start:.2f}s, Avg Loss_D: {history['D_losses_epoch'][-1]:.4f}, "
+              f"Avg Loss_G: {history['G_losses_epoch'][-1]:.4f}, D(x): {r[:, 2].mean():.3f}, D(G(z)): {r[:, 4].mean():.3f}")
+        if (epoch + 1) % args.checkpoint_interval == 0 or (epoch + 1) == args.epochs:
+            _save_state(netG, os.path.join(model_dir, f'generator_epoch_{epoch + 1:03d}.pth'))
+            _save_state(netD, os.path.join(model_dir, f'discriminator_epoch_{epoch + 1:03d}.pth'))
+            print(f'Saved checkpoints for epoch {epoch + 1} to {model_dir}')
+        if stop:
+            break
+    print(f'Training finished in {time.time() - start:.2f} seconds.')
+    _save_state(netG, os.path.join(model_dir, 'generator_final.pth'))
+    _save_state(netD, os.path.join(model_dir, 'discriminator_final.pth'))
+    print(f'Saved final models to {model_dir}')
+    with open(os.path.join(args.results_dir, 'gan_training_history.json'), 'w') as f:
+        json.dump(history, f, indent=4)
+    plot_gan_losses(history, os.path.join(args.figures_dir, 'gan_loss_curve.png'))
+    return history
+
+
+def build_parser():
+    parser = argparse.ArgumentParser(description='Train cDCGAN on RSNA Pneumonia Dataset with Enhanced Logging')
+    parser.add_argument('--data-dir', type=str, default='./data/processed')
+    parser.add_argument('--model-dir', type=str, default='./models')
+    parser.add_argument('--output-dir', type=str, default='./results')
+    parser.add_argument('--results-dir', type=str, default='./results/metrics')
+    parser.add_argument('--figures-dir', type=str, default='./results/figures')
+    parser.add_argument('--num-channels', type=int, default=3)
+    parser.add_argument('--latent-dim', type=int, default=100)
+    parser.add_argument('--feature-maps-g', type=int, default=32)
+    parser.add_argument('--feature-maps-d', type=int, default=32)
+    parser.add_argument('--epochs', type=int, default=50)
+    parser.add_argument('--batch-size', type=int, default=32)
+    parser.add_argument('--lr', type=float, default=0.0002)
+    parser.add_argument('--beta1', type=float, default=0.5)
+    parser.add_argument('--workers', type=int, default=4)
+    parser.add_argument('--vis-batch-size', type=int, default=32)
+    parser.add_argument('--save-interval', type=int, default=1000)
+    parser.add_argument('--checkpoint-interval', type=int, default=5)
+    parser.add_argument('--cpu', action='store_true')
+    # --- additive (not in the reference) --- #
+    parser.add_argument('--no-perceptual', action='store_true', help='drop the VGG16 perceptual term (required on CUDA: not implemented there)')
+    parser.add_argument('--dtype', choices=['bf16', 'fp32'], default='bf16', help='compute dtype of the B200 kernels')
+    parser.add_argument('--synthetic', type=int, default=0, help='train on N synthetic uniform[-1,1] images with random labels instead of the RSNA set')
+    parser.add_argument('--max-iters', type=int, default=0, help='stop after this many iterations (0 = all epochs)')
+    parser.add_argument('--log-interval', type=int, default=50, help='iterations between host synchronisations of the loss history')
+    parser.add_argument('--seed', type=int, default=None)
+    return parser
+
+
+if __name__ == '__main__':
+    a = build_parser().parse_args()
+    print('--- Training Arguments ---')
+    for k, v in vars(a).items():
+        print(f'  {k}: {v}')
+    print('-------------------------')
+    main(a)

@@ -249,7 +249,18 @@ int b200gan_mean_f32(const float* x, int64_t n, float scale, float* out, void* s
  *        upconv3_unfold   the adjoint: dw3 += A^T dw4 A  (weight gradient back in the Conv2d(3) layout)
  *        class_proj_fwd   out[n] += < table[labels[n]], x(n) flattened in (c,h,w) order >     (projection term, cgan.py:103)
  *        class_proj_bwd   dx(n) += dout[n] table[labels[n]] (dx NULL: skipped);  dtable[c] += sum over {n : labels[n] == c} of dout[n] x(n)
- *                         (dtable NULL: skipped).  labels: int64 on the device.  Batch-order loops, no atomics: run-to-run identical. */
+ *                         (dtable NULL: skipped).  labels: int64 on the device.  Batch-order loops, no atomics: run-to-run identical.
+ *        bce_logits       nn.BCEWithLogitsLoss(mean) against PER-SAMPLE targets (train_cgan.py:111,156-160) with its backward and the mean probability
+ *                         (`torch.sigmoid(out).mean()`, :163,170,182):  out2[0] = mean_i max(x,0) - x t + log1p(exp(-|x|)),
+ *                         out2[1] = mean_i sigmoid(x_i),  dlogit[i] = grad_scale (sigmoid(x_i) - t_i) / B   (dlogit may be NULL)
+ *        fm_pair          feature matching on one pair of intermediates (train_cgan.py:75-76): sum[0] += sum (real - fake)^2 (fp64, the caller
+ *                         divides by numel), dfake = coeff (real - fake) written (add = 0) or added (add = 1); dfake may be NULL
+ *        accumulate_2d    dst[r][c] += src[r*src_row_stride + c*src_col_stride], src float (src_f64 = 0) or double: bias gradients out of the
+ *                         fp64 channel sums of b200gan_bn_stats, the Linear's (out,in) gradient out of the latent GEMM's (in,out) one */
+int b200gan_bce_logits(const float* logit, const float* target, int32_t batch, float grad_scale, float* out2, float* dlogit, void* stream);
+int b200gan_fm_pair(const b200gan_view* real, const b200gan_view* fake, const b200gan_view* dfake, float coeff, int32_t add, double* sum, void* stream);
+int b200gan_accumulate_2d(float* dst, const void* src, int32_t src_f64, int32_t rows, int32_t cols, int64_t src_row_stride, int64_t src_col_stride,
+                          void* stream);
 int b200gan_embed_add(const float* table, const int64_t* labels, const float* z, int32_t batch, int32_t dim, int32_t tail, float* out, void* stream);
 int b200gan_embed_bwd(const float* dx, const int64_t* labels, int32_t batch, int32_t dim, int32_t stride, int32_t num_classes, float* dtable,
                       void* stream);

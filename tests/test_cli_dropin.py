@@ -103,3 +103,37 @@ def test_wgan_cpu_round_trip_writes_reference_artefacts(tmp_path):
     assert any(n.startswith('fake_samples_epoch_001_iter_') for n in os.listdir(d + '/results/wgan_images'))
     sd = torch.load(d + '/models/wgan/discriminator_final.pth')
     assert len(sd) == 20 and sd['main.11.weight'].shape == (1, 16, 7, 7)
+
+
+# ---- conditional GAN CLI ---------------------------------------------------------------------------------
+REF_CGAN_FLAGS = dict(data_dir='./data/processed', model_dir='./models', output_dir='./results', results_dir='./results/metrics',
+                      figures_dir='./results/figures', num_channels=3, latent_dim=100, feature_maps_g=32, feature_maps_d=32, epochs=50, batch_size=32,
+                      lr=0.0002, beta1=0.5, workers=4, vis_batch_size=32, save_interval=1000, checkpoint_interval=5, cpu=False)
+
+
+def test_cgan_cli_keeps_reference_flags_and_defaults():
+    """src/train_cgan.py:249-267 (the list above was read off the reference)."""
+    from gan_enhanced_pneumonia_classifier_b200 import train_cgan as tc
+    args = vars(tc.build_parser().parse_args([]))
+    for k, v in REF_CGAN_FLAGS.items():
+        assert args[k] == v, k
+    assert set(args) - set(REF_CGAN_FLAGS) == {'no_perceptual', 'dtype', 'synthetic', 'max_iters', 'log_interval', 'seed'}
+
+
+def test_cgan_cpu_round_trip_writes_reference_artefacts(tmp_path):
+    """--cpu --no-perceptual runs the reference's stock-torch loop (minus the VGG16 term) over the drop-in modules and writes the reference's files."""
+    from gan_enhanced_pneumonia_classifier_b200 import train_cgan as tc
+    d = str(tmp_path)
+    argv = ['--cpu', '--no-perceptual', '--synthetic', '4', '--batch-size', '2', '--epochs', '1', '--latent-dim', '8', '--feature-maps-g', '2',
+            '--feature-maps-d', '2', '--num-channels', '1', '--vis-batch-size', '3', '--model-dir', d + '/models', '--output-dir', d + '/results',
+            '--results-dir', d + '/results/metrics', '--figures-dir', d + '/results/figures', '--seed', '0', '--checkpoint-interval', '1']
+    hist = tc.main(tc.build_parser().parse_args(argv))
+    assert set(hist) == set(tc.HISTORY_KEYS)
+    assert len(hist['G_losses_epoch']) == 1 and np.isfinite(hist['G_losses_epoch'][0]) and np.isfinite(hist['feature_matching_losses'][0])
+    assert hist['perceptual_losses'] == [0.0] and hist['G_losses_iter'] == []        # the reference never fills the per-iteration lists either
+    for f in ('models/gan/generator_final.pth', 'models/gan/discriminator_final.pth', 'models/gan/generator_epoch_001.pth',
+              'results/metrics/gan_training_history.json'):
+        assert os.path.exists(os.path.join(d, f)), f
+    assert any(n.startswith('fake_samples_epoch_001_iter_') for n in os.listdir(d + '/results/gan_images'))
+    sd = torch.load(d + '/models/gan/generator_final.pth')
+    assert sd['label_emb.weight'].shape == (2, 8) and sd['fc.weight'].shape == (16 * 49, 8) and sd['main.19.weight'].shape == (1, 1, 3, 3)
