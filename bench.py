@@ -338,7 +338,7 @@ def run_ours(args):
         if world > 1:      # replicas start from rank 0's weights, as DDP would
             for t in list(G.state_dict().values()) + list(D.state_dict().values()):
                 dist.broadcast(t, 0)
-        return DCGANTrainer(G, D, lr=2e-4, beta1=0.5, dtype=dtype)
+        return DCGANTrainer(G, D, lr=2e-4, beta1=0.5, dtype=dtype, sync_bn=args.sync_bn)
 
     tr = make_trainer(nc)
     gen = torch.Generator(device='cuda').manual_seed(1 + rank)
@@ -566,7 +566,7 @@ def run_ours(args):
             'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'strong' if strong else 'weak', 'vs_baseline': None,
             'dtype': args.dtype, 'data': 'synthetic',
             'config': {'workload': f'DCGAN train step nz=100 ngf=ndf=64 nc={nc} 224x224 (reference is hard-wired to 224x224, not 64x64)',
-                       'per_gpu_batch': B, 'global_batch': B * world, 'parallelism': f'dp{world}', 'batchnorm': 'local (per-rank) statistics',
+                       'per_gpu_batch': B, 'global_batch': B * world, 'parallelism': f'dp{world}', 'batchnorm': 'synchronised over ranks (--sync-bn)' if (args.sync_bn and world > 1) else 'local (per-rank) statistics',
                        'gradient_exchange': 'none (1 GPU)' if world == 1 else 'bucketed NCCL all-reduce on the library\'s communicator, captured in '
                                                                               'the iteration graph, overlapped with the backward pass',
                        'l2': 'per-step working set (several GB of activations) far exceeds the 126 MB L2; no flush needed',
@@ -606,6 +606,7 @@ def main():
     ap.add_argument('--no-check', dest='check', action='store_false', help='skip the data-parallel invariants check')
     ap.add_argument('--no-rgb', action='store_true', help='skip the additional nc=3 measurement (more_configs)')
     ap.add_argument('--no-wgan', action='store_true', help='skip the additional WGAN-GP measurement (more_configs, 1 GPU only)')
+    ap.add_argument('--sync-bn', action='store_true', help='N>1: synchronised BatchNorm statistics (default: local to each rank)')
     ap.add_argument('--no-cgan', action='store_true', help='skip the additional CGAN measurement (more_configs, 1 GPU only)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()

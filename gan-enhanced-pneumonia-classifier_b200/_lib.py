@@ -83,6 +83,7 @@ PROTOTYPES = {
     'b200gan_dp_unique_id': [_vp],
     'b200gan_dp_init': [_vp, _i32, _i32, C.POINTER(_vp)],
     'b200gan_dp_allreduce_bucket': [_vp, _vp, _i64, _vp],
+    'b200gan_dp_allreduce_f64': [_vp, _vp, _i64, _vp],
     'b200gan_dp_sync': [_vp, _vp],
     'b200gan_dp_destroy': [_vp],
 }

@@ -20,7 +20,7 @@ namespace {
 
 struct NcclUniqueId { char internal[128]; };           // ncclUniqueId (NCCL_UNIQUE_ID_BYTES = 128)
 typedef void* NcclComm;
-enum { kNcclSuccess = 0, kNcclFloat32 = 7, kNcclSum = 0 };
+enum { kNcclSuccess = 0, kNcclFloat32 = 7, kNcclFloat64 = 8, kNcclSum = 0 };
 
 struct NcclApi {
   int (*GetUniqueId)(NcclUniqueId*) = nullptr;
@@ -111,6 +111,20 @@ int b200gan_dp_allreduce_bucket(b200gan_dp* dp, float* grad, int64_t numel, void
   B200_CUDA(cudaEventRecord(dp->fork, st));
   B200_CUDA(cudaStreamWaitEvent(dp->comm_stream, dp->fork, 0));
   B200_NCCL(nccl().AllReduce(grad, grad, (size_t)numel, kNcclFloat32, kNcclSum, dp->comm, dp->comm_stream));
+  dp->collectives++;
+  return 0;
+}
+
+int b200gan_dp_allreduce_f64(b200gan_dp* dp, double* buf, int64_t numel, void* stream) {
+  B200_CHECK_ARG(dp && dp->comm && buf && numel > 0, "dp_allreduce_f64: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  // synchronised BatchNorm: the per-channel sums of one layer, needed by the very next kernel.  Issued on the communication stream like the
+  // gradient buckets (ONE stream per communicator keeps NCCL's issue order trivially identical on all ranks), fenced on both sides.
+  B200_CUDA(cudaEventRecord(dp->fork, st));
+  B200_CUDA(cudaStreamWaitEvent(dp->comm_stream, dp->fork, 0));
+  B200_NCCL(nccl().AllReduce(buf, buf, (size_t)numel, kNcclFloat64, kNcclSum, dp->comm, dp->comm_stream));
+  B200_CUDA(cudaEventRecord(dp->join, dp->comm_stream));
+  B200_CUDA(cudaStreamWaitEvent(st, dp->join, 0));
   dp->collectives++;
   return 0;
 }

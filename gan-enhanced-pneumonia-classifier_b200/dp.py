@@ -44,6 +44,10 @@ class DPComm:
     def allreduce_bucket(self, view: torch.Tensor):
         L.call('b200gan_dp_allreduce_bucket', self._h, L.ptr(view), view.numel(), L.stream_ptr())
 
+    def allreduce_f64(self, sums: torch.Tensor):
+        """Synchronised BatchNorm: sum the per-channel fp64 sums of one layer over the ranks, in stream order."""
+        L.call('b200gan_dp_allreduce_f64', self._h, L.ptr(sums), sums.numel(), L.stream_ptr())
+
     def sync(self):
         L.call('b200gan_dp_sync', self._h, L.stream_ptr())
 

@@ -137,6 +137,10 @@ class NetEngine:
         # them (the next layer needs only the input gradient), so they leave the backward pass's critical path and co-run with its
         # HBM-bound BatchNorm passes.  `join_wgrads()` is the point where the compute stream waits for them.
         self.wgrad_stream = None
+        # Synchronised BatchNorm (data parallel, --sync-bn): a dp.DPComm; the per-channel sums of every BatchNorm (forward statistics and
+        # backward reductions) are summed over the ranks before they are used, and the sample count becomes the global one -- exactly the
+        # arithmetic of one process on the concatenated batch.  None: statistics are local to the rank.
+        self.sync_bn = None
         self._side_keep = []  # operands of weight gradients still in flight on wgrad_stream (kept from the caching allocator)
         self.weights_version = None   # see _pack
         self._packed = {}
@@ -242,7 +246,11 @@ class NetEngine:
                     mean = torch.empty(cch, device=dev, dtype=torch.float32)
                     invstd = torch.empty(cch, device=dev, dtype=torch.float32)
                     self._fprop(i, cur, p.w, y, st, wp_down, wp_up, fuse=L.fuse(bn_sums=sums))
-                    L.call('b200gan_bn_finalize', L.ptr(sums), cch, cur.v.n * oh * ow, L.ptr(p.gamma), L.ptr(p.beta),
+                    ranks = 1
+                    if self.sync_bn is not None:
+                        self.sync_bn.allreduce_f64(sums)
+                        ranks = self.sync_bn.world
+                    L.call('b200gan_bn_finalize', L.ptr(sums), cch, cur.v.n * oh * ow * ranks, L.ptr(p.gamma), L.ptr(p.beta),
                            L.ptr(p.rm), L.ptr(p.rv), L.ptr(p.nbt), BN_MOMENTUM, BN_EPS, L.ptr(scale), L.ptr(shift),
                            L.ptr(mean), L.ptr(invstd), st)
                     if save:
@@ -305,6 +313,17 @@ class NetEngine:
                 cnt = lc.y.v.n * lc.y.v.h * lc.y.v.w
                 dg = grads[gi + 1] if need_wgrad else None
                 db = grads[gi + 2] if need_wgrad else None
+                if self.sync_bn is not None:
+                    # the input gradient needs the GLOBAL sums; dgamma / dbeta stay this rank's share (the gradient exchange sums them)
+                    local = lc.bsums.clone()
+                    self.sync_bn.allreduce_f64(lc.bsums)
+                    cnt *= self.sync_bn.world
+                    cch = sp.cout
+                    if dg is not None:
+                        L.call('b200gan_accumulate_2d', L.ptr(dg), L.ptr(local[cch:]), 1, 1, cch, 0, 1, st)
+                        L.call('b200gan_accumulate_2d', L.ptr(db), L.ptr(local), 1, 1, cch, 0, 1, st)
+                        self.launches += 2
+                    dg = db = None
                 L.call('b200gan_bn_act_bwd_apply', C.byref(d.v), C.byref(lc.y.v), None, L.ptr(lc.scale), L.ptr(lc.shift),
                        L.ptr(lc.mean), L.ptr(lc.invstd), L.ptr(p.gamma), L.ptr(lc.bsums), cnt, L.ACT_NONE, LRELU_SLOPE,
                        C.byref(d.v), L.ptr(dg), L.ptr(db), st)

@@ -229,7 +229,7 @@ def main(args):
     if use_cuda:
         dtype = {'bf16': torch.bfloat16, 'fp32': torch.float32}[getattr(args, 'dtype', 'bf16')]
         netG.compute_dtype = netD.compute_dtype = dtype      # the module-level forwards (visualisation, train_gan.py:166-169) too
-        trainer = DCGANTrainer(netG, netD, lr=args.lr, beta1=args.beta1, dtype=dtype)
+        trainer = DCGANTrainer(netG, netD, lr=args.lr, beta1=args.beta1, dtype=dtype, sync_bn=getattr(args, 'sync_bn', False))
     else:
         criterion = nn.BCELoss()
         optimizerD = optim.Adam(netD.parameters(), lr=args.lr, betas=(args.beta1, 0.999))
@@ -366,6 +366,8 @@ def build_parser():
     parser.add_argument('--max-iters', type=int, default=0, help='stop after this many iterations (0 = run all epochs)')
     parser.add_argument('--log-interval', type=int, default=50, help='flush the device-side history scalars every N iterations')
     parser.add_argument('--seed', type=int, default=None, help='torch.manual_seed (the reference is unseeded)')
+    parser.add_argument('--sync-bn', action='store_true', help='data parallel only: BatchNorm statistics over the global batch (one small all-reduce per '
+                        'BatchNorm pass) instead of per rank; the iteration then equals one process on the concatenated batch')
     return parser
 
 

@@ -67,7 +67,8 @@ class _Captured:
 
 class DCGANTrainer:
     def __init__(self, netG, netD, lr: float = 2e-4, beta1: float = 0.5, beta2: float = 0.999, eps: float = 1e-8,
-                 dtype: Optional[torch.dtype] = None, algo: Optional[int] = None, process_group=None, use_graph: Optional[bool] = None):
+                 dtype: Optional[torch.dtype] = None, algo: Optional[int] = None, process_group=None, use_graph: Optional[bool] = None,
+                 sync_bn: bool = False):
         dtype = dtype or E.default_compute_dtype()
         algo = E.default_algo() if algo is None else algo
         self.netG, self.netD = netG, netD
@@ -91,6 +92,12 @@ class DCGANTrainer:
         self.extra_launches = 0
         # data parallel: the library's own NCCL communicator (b200gan_dp_*); torch.distributed only carried its unique id
         self.comm = DPComm(process_group) if self.world > 1 else None
+        # --sync-bn: BatchNorm statistics (and the BatchNorm-backward reductions) over the GLOBAL batch instead of the rank's shard: one small
+        # fp64 all-reduce per BatchNorm pass on the library's communicator (optional).  The iteration then equals a
+        # single process on the concatenated batch.
+        self.sync_bn = bool(sync_bn) and self.comm is not None
+        if self.sync_bn:
+            self.engG.sync_bn = self.engD.sync_bn = self.comm
         self.bucketsD = GradBuckets(self.arenaD.grad, self.arenaD.slices, process_group, comm=self.comm)
         self.bucketsG = GradBuckets(self.arenaG.grad, self.arenaG.slices, process_group, comm=self.comm)
         # B200GAN_DP_SEGMENTED=1: keep the collectives out of the capture (three graphs cut at the two exchanges, every bucket
@@ -289,6 +296,7 @@ class DCGANTrainer:
             torch.cuda.synchronize()
             self.comm.close()
             self.comm = self.bucketsD.comm = self.bucketsG.comm = None
+            self.engG.sync_bn = self.engD.sync_bn = None
 
     def refresh_packed_weights(self):
         """Re-derive the cached bf16 weight repacks from the fp32 masters.  Call after the weights were changed from OUTSIDE the

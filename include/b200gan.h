@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define B200GAN_VERSION 410   /* major*10000 + minor*100 + patch */
+#define B200GAN_VERSION 420   /* major*10000 + minor*100 + patch */
 
 typedef enum b200gan_status {
   B200GAN_OK = 0,
@@ -282,7 +282,11 @@ int b200gan_class_proj_bwd(const b200gan_view* x, const float* table, const int6
  *                             returns; `stream` itself continues with the backward pass.  Capturable into a CUDA graph;
  *        dp_sync              joins: `stream` waits for every bucket issued so far (call before b200gan_adam, whose grad_scale
  *                             carries the 1/world factor);
- *        dp_collectives       number of bucket all-reduces issued through the handle (launch accounting / tests).
+ *        dp_allreduce_f64     in-place sum over ranks of `buf[0..numel)` (fp64, device), COMPLETE for `stream` on return of the stream order:
+ *                             forks to the communication stream and joins back.  Synchronised BatchNorm (`--sync-bn`): the per-channel
+ *                             sums of b200gan_bn_stats / b200gan_fuse.bn_sums / prev_sums are summed over ranks between the reduction and
+ *                             b200gan_bn_finalize / b200gan_bn_act_bwd_apply, whose `count` then is the GLOBAL sample count;
+ *        dp_collectives       number of all-reduces issued through the handle (launch accounting / tests).
  *      Errors: B200GAN_ERR_NCCL with the NCCL message in b200gan_last_error_string().  NCCL is bound at run time from the
  *      libnccl.so.2 already loaded in the process (torch's), so single-GPU users never need it. */
 #define B200GAN_DP_ID_BYTES 128
@@ -290,6 +294,7 @@ typedef struct b200gan_dp b200gan_dp;
 int     b200gan_dp_unique_id(void* id_out);
 int     b200gan_dp_init(const void* id, int32_t world, int32_t rank, b200gan_dp** out);
 int     b200gan_dp_allreduce_bucket(b200gan_dp* dp, float* grad, int64_t numel, void* stream);
+int     b200gan_dp_allreduce_f64(b200gan_dp* dp, double* buf, int64_t numel, void* stream);
 int     b200gan_dp_sync(b200gan_dp* dp, void* stream);
 int64_t b200gan_dp_collectives(const b200gan_dp* dp);
 int     b200gan_dp_destroy(b200gan_dp* dp);

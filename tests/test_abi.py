@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f'{n} declared in include/b200gan.h but not exported'
     assert sorted(list(L.PROTOTYPES) + L.OTHER_SYMBOLS) == names, 'ctypes prototypes and header differ'
-    assert lib.b200gan_version() == 410        # 0.4.1: + conditional-GAN entry points (embed_*, upconv3_*, class_proj_*)
+    assert lib.b200gan_version() == 420        # 0.4.2: + conditional-GAN entry points, b200gan_dp_allreduce_f64 (synchronised BatchNorm)
 
 
 def test_bad_arguments_fail_loudly_without_a_gpu():

@@ -24,7 +24,7 @@ def test_train_cli_keeps_reference_flags_and_defaults():
     args = vars(tg.build_parser().parse_args([]))
     for k, v in REF_TRAIN_FLAGS.items():
         assert args[k] == v, k
-    assert set(args) - set(REF_TRAIN_FLAGS) == {'dtype', 'synthetic', 'max_iters', 'log_interval', 'seed', 'cache_dataset'}        # additive only
+    assert set(args) - set(REF_TRAIN_FLAGS) == {'dtype', 'synthetic', 'max_iters', 'log_interval', 'seed', 'cache_dataset', 'sync_bn'}        # additive only
 
 
 def test_sampler_cli_keeps_reference_flags_and_defaults():

@@ -33,7 +33,7 @@ def _shard(rank, it):
     return synthetic_real(300 + 10 * it + rank, B, NC), synthetic_noise(400 + 10 * it + rank, B, NZ)
 
 
-def _worker(rank, port, out_dir, use_graph):
+def _worker(rank, port, out_dir, use_graph, sync_bn=False):
     import torch.distributed as dist
     import gan_enhanced_pneumonia_classifier_b200 as pkg
     from gan_enhanced_pneumonia_classifier_b200.trainer import DCGANTrainer
@@ -45,7 +45,7 @@ def _worker(rank, port, out_dir, use_graph):
         G, D = pkg.Generator(NZ, NC, FM), pkg.Discriminator(NC, FM)
         G.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in sdG.items()})
         D.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in sdD.items()})
-        tr = DCGANTrainer(G.cuda(), D.cuda(), dtype=torch.float32, use_graph=use_graph)
+        tr = DCGANTrainer(G.cuda(), D.cuda(), dtype=torch.float32, use_graph=use_graph, sync_bn=sync_bn)
         hist = []
         for it in range(STEPS):
             real, noise = _shard(rank, it)
@@ -92,6 +92,43 @@ def test_two_nccl_ranks_match_dp_emulation(tmp_path, use_graph):
                     assert np.abs(got[f'{tag}.{k}'] - v).max() < (5e-5 if k.endswith('.bias') else 1.3e-3), k
     a, b = np.load(os.path.join(str(tmp_path), 'rank0.npz')), np.load(os.path.join(str(tmp_path), 'rank1.npz'))
     assert np.array_equal(a['G.main.0.weight'], b['G.main.0.weight']), 'replicas must stay bit-identical on the weights'
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs')
+@pytest.mark.parametrize('use_graph', [False, True])
+def test_two_nccl_ranks_with_synchronised_batchnorm_equal_one_process_on_the_concatenated_batch(tmp_path, use_graph):
+    """--sync-bn (optional): BatchNorm statistics and BatchNorm-backward reductions summed over the ranks on the library's
+    communicator.  Two ranks of batch B then ARE the single-process iteration on the 2B batch -- the plain oracle, no DP emulation: the mean of the
+    ranks' loss rows is the oracle's row, the weights and the running statistics (global mean / unbiased global variance) are the oracle's."""
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        port = s.getsockname()[1]
+    mp.start_processes(_worker, args=(port, str(tmp_path), use_graph, True), nprocs=WORLD, join=True, start_method='spawn')
+    sdG, sdD = _state()
+    G = orc.GeneratorOracle(NZ, NC, FM, {k: v.copy() for k, v in sdG.items()})
+    D = orc.DiscriminatorOracle(NC, FM, {k: v.copy() for k, v in sdD.items()})
+    oG, oD = orc.AdamOracle(orc.param_keys(G.plan), 2e-4, 0.5), orc.AdamOracle(orc.param_keys(D.plan), 2e-4, 0.5)
+    ref = []
+    for it in range(STEPS):
+        shards = [_shard(r, it) for r in range(WORLD)]
+        out = orc.train_iteration(G, D, oG, oD, np.concatenate([s[0] for s in shards]), np.concatenate([s[1] for s in shards]))
+        ref.append([out[k] for k in ('errD', 'errG', 'D_x', 'D_G_z1', 'D_G_z2')])
+    got = [np.load(os.path.join(str(tmp_path), f'rank{r}.npz')) for r in range(WORLD)]
+    mean_hist = np.mean([g['hist'] for g in got], axis=0)
+    close(mean_hist[0], np.array(ref[0]), rtol=1e-4, atol=1e-6, what='first-iteration history (mean over ranks)')
+    close(mean_hist, np.array(ref), rtol=5e-3, atol=1e-4, what='history (mean over ranks)')
+    for tag, net in (('G', G), ('D', D)):
+        for k, v in net.sd.items():
+            if k.endswith('num_batches_tracked'):
+                assert int(got[0][f'{tag}.{k}']) == int(v)
+            elif 'running' in k:
+                close(got[0][f'{tag}.{k}'], v, rtol=2e-3, atol=1e-4, what=f'{tag}.{k}')
+            else:
+                weights_close(got[0][f'{tag}.{k}'], v, what=f'{tag}.{k}', steps=STEPS, rtol=1e-3, atol=1e-5, frac=_frac(k))
+    for k in got[0].files:
+        if k[:2] in ('G.', 'D.'):
+            assert np.array_equal(got[0][k], got[1][k]), f'{k}: with synchronised BatchNorm the replicas agree on every tensor, buffers included'
 
 
 def test_two_replicas_on_one_gpu_match_dp_emulation():
