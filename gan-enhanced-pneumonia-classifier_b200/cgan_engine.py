@@ -461,7 +461,7 @@ class DiscriminatorEngine:
     def backward(self, mod, saved, dlogits: Optional[torch.Tensor], dfeats: Optional[list], need_dx: bool, need_dw: bool, into: Optional[dict] = None,
                  dx_out: Optional[Act] = None):
         """Gradients for the upstream gradient of the logits (N,) and / or of the nine feature tensors [a0, y1, a1, ..., y4, a4] (NCHW fp32
-        tensors or Acts in any layout; entries may be None).  Returns (dx or None, {param: grad}); `into`: see GeneratorEngine.backward;
+        tensors, Acts in any layout, or callables `g(target_act)` that add their gradient into the target themselves; entries may be None).  Returns (dx or None, {param: grad}); `into`: see GeneratorEngine.backward;
         `dx_out`: where the input gradient goes (default: a fresh NCHW fp32 tensor)."""
         tape, labels = saved
         dev = tape[0].x.t.device
@@ -484,19 +484,24 @@ class DiscriminatorEngine:
                 dtable = _buf(grads, into, mod.label_emb.weight)
             L.call('b200gan_class_proj_bwd', C.byref(top.a.v), L.ptr(table), L.ptr(labels), L.ptr(dl), C.byref(d.v), self.classes, L.ptr(dtable), _st())
 
-        def feat(j):
-            if dfeats is None or dfeats[j] is None:
-                return None
-            return dfeats[j] if isinstance(dfeats[j], Act) else Act(_f32(dfeats[j], 'grad of features'), nchw=True)
+        def add_feat(j, i, d):
+            """d += gradient of feature j (an intermediate of layer i): a tensor / Act to accumulate, or a callable that adds it itself
+            (the fused trainer's feature-matching kernel writes straight into d: no gradient tensor, no accumulate pass)."""
+            g = None if dfeats is None else dfeats[j]
+            if g is None:
+                return
+            tgt = _real(d, self.ch[i + 1])
+            if callable(g):
+                g(tgt)
+            else:
+                _accumulate(tgt, g if isinstance(g, Act) else Act(_f32(g, 'grad of features'), nchw=True))
 
         for i in range(4, -1, -1):
             lay, conv, op = tape[i], self.conv_of(mod, i), self.down[i]
-            ga = feat(2 * i)                  # a_i sits at position 2i of [a0, y1, a1, ..., y4, a4]
             if not have_d:
                 d.t.zero_()                   # no gradient reaches this depth from above (memset)
                 have_d = True
-            if ga is not None:
-                _accumulate(_real(d, ga.v.c), ga)        # (a gradient over the real channels of a padded tensor lands on its real channels)
+            add_feat(2 * i, i, d)             # a_i sits at position 2i of [a0, y1, a1, ..., y4, a4]
             if lay.bn is None:
                 _act_backward(d, lay.a, L.ACT_LRELU, d)
             else:
@@ -504,9 +509,7 @@ class DiscriminatorEngine:
                 dg = _buf(grads, into, bn.weight) if need_dw else None
                 db = _buf(grads, into, bn.bias) if need_dw else None
                 _bn_backward(d, lay.y, lay.bn, bn, L.ACT_LRELU, d, dg, db)
-                gy = feat(2 * i - 1)
-                if gy is not None:
-                    _accumulate(d, gy)
+                add_feat(2 * i - 1, i, d)
             if need_dw:
                 cin, cout = self.ch[i], self.ch[i + 1]
                 _add_channel_sum(_buf(grads, into, conv.bias), d, cout)

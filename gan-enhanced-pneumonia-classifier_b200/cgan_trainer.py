@@ -23,6 +23,7 @@ import torch
 
 from . import _lib as L
 from . import cgan_engine as CE
+from .dp import DPComm, GradBuckets
 from .engine import Act
 from .trainer import _Arena
 
@@ -32,7 +33,7 @@ FEATURE_MULTIPLICITY = [2, 1, 2, 1, 2, 1, 2, 1, 2]      # of [a0, y1, a1, ..., y
 
 class CGANTrainer:
     def __init__(self, netG, netD, lr: float = 2e-4, beta1: float = 0.5, beta2: float = 0.999, eps: float = 1e-8, fm_weight: float = 5.0,
-                 perceptual_weight: float = 0.0, dtype: Optional[torch.dtype] = None):
+                 perceptual_weight: float = 0.0, dtype: Optional[torch.dtype] = None, process_group=None):
         if perceptual_weight != 0.0:
             raise L.B200GanError('the VGG16 perceptual term of train_cgan.py:57-73 is not implemented (its ImageNet weights cannot be obtained '
                                  'offline); pass perceptual_weight=0 to train with the adversarial and feature-matching terms only')
@@ -47,12 +48,33 @@ class CGANTrainer:
         self.intoD = dict(zip(self.pD, self.arenaD.grads))
         self.d_steps = 0
         self._fm_scale = None
+        # data parallel (one process per GPU, the batch sharded): both gradient arenas are summed over the ranks on the library's NCCL communicator
+        # before their Adam updates (1/world folded into the Adam kernel); BatchNorm statistics stay per rank; the D-step skip rule is evaluated
+        # on the rank-averaged D(x) / D(G(z)) so that every rank takes the same branch (and issues the same collectives)
+        self.world = 1
+        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(process_group)
+        self.comm = DPComm(process_group) if self.world > 1 else None
+        self.bucketsD = GradBuckets(self.arenaD.grad, self.arenaD.slices, process_group, comm=self.comm)
+        self.bucketsG = GradBuckets(self.arenaG.grad, self.arenaG.slices, process_group, comm=self.comm)
 
     # -- pieces ---------------------------------------------------------------------------------------------------------------------
     def _adam(self, arena):
         arena.step_dev.add_(1)
         L.call('b200gan_adam', L.ptr(arena.param), L.ptr(arena.grad), L.ptr(arena.exp_avg), L.ptr(arena.exp_avg_sq), arena.numel, self.lr,
-               self.beta1, self.beta2, self.eps, 0, L.ptr(arena.step_dev), 1.0, L.stream_ptr())
+               self.beta1, self.beta2, self.eps, 0, L.ptr(arena.step_dev), 1.0 / self.world, L.stream_ptr())
+
+    def _exchange(self, buckets):
+        if self.comm is not None:
+            buckets.begin()
+            buckets.finish()
+
+    def close(self):
+        """Data parallel: release the library's NCCL communicator (call before torch.distributed.destroy_process_group(); a no-op on one GPU)."""
+        if self.comm is not None:
+            torch.cuda.synchronize()
+            self.comm.close()
+            self.comm = self.bucketsD.comm = self.bucketsG.comm = None
 
     @staticmethod
     def _bce(logits, target, want_grad=True):
@@ -62,23 +84,24 @@ class CGANTrainer:
         return out2, dl
 
     def _feature_matching(self, tape_real, tape_fake):
-        """Returns (the loss as the reference sums it over the 14 aliased entries, gradients w.r.t. the nine distinct fake intermediates)."""
+        """Returns (loss, adders): the loss as the reference sums it over the 14 aliased entries -- a device scalar that is complete once every
+        adder has run -- and, per distinct fake intermediate, a callable that ADDS that term's gradient into the tensor the Discriminator's
+        backward pass hands it (`b200gan_fm_pair` computes the sum and the gradient in the same pass over the pair)."""
         real_acts, fake_acts = self.engD.feature_acts(tape_real), self.engD.feature_acts(tape_fake)
         dev = fake_acts[0][0].t.device
         sums = torch.zeros(len(fake_acts), device=dev, dtype=torch.float64)
         key = tuple(f.t.numel() for _, f in fake_acts)                            # real (unpadded) element counts
         if self._fm_scale is None or self._fm_scale[0] != key:                   # multiplicity / numel per pair, built once per batch shape
             self._fm_scale = (key, torch.tensor([mult / nel for mult, nel in zip(FEATURE_MULTIPLICITY, key)], device=dev, dtype=torch.float64))
-        dfeats = []
-        for j, ((_, r), (stored, f)) in enumerate(zip(real_acts, fake_acts)):
-            padded = stored.v.c != f.v.c
-            d = Act((torch.zeros_like if padded else torch.empty_like)(stored.t), nchw=False)       # in the stored (possibly padded) layout
-            d_real = Act(d.t[..., :f.v.c], nchw=False) if padded else d
-            L.call('b200gan_fm_pair', C.byref(r.v), C.byref(f.v), C.byref(d_real.v), -2.0 * self.fm_weight * FEATURE_MULTIPLICITY[j] / key[j], 0,
-                   C.c_void_p(sums.data_ptr() + 8 * j), L.stream_ptr())
-            dfeats.append(d)
-        loss = torch.dot(sums, self._fm_scale[1]).float()                         # nine scalars
-        return loss, dfeats
+
+        def adder(j, r, f):
+            def add(target: Act):
+                L.call('b200gan_fm_pair', C.byref(r.v), C.byref(f.v), C.byref(target.v), -2.0 * self.fm_weight * FEATURE_MULTIPLICITY[j] / key[j], 1,
+                       C.c_void_p(sums.data_ptr() + 8 * j), L.stream_ptr())
+            return add
+
+        adders = [adder(j, r, f) for j, ((_, r), (_, f)) in enumerate(zip(real_acts, fake_acts))]
+        return (lambda: torch.dot(sums, self._fm_scale[1]).float()), adders
 
     # -- one iteration ------------------------------------------------------------------------------------------------------------------
     def step(self, real: torch.Tensor, real_labels: torch.Tensor, epoch: int = 0, noise: Optional[torch.Tensor] = None,
@@ -107,12 +130,16 @@ class CGANTrainer:
         m_fake, dl_f = self._bce(logit_f, smooth_fake)
         stepped = True
         if epoch >= 5:                                        # train_cgan.py:176: `if D_x < 0.8 or D_G_z1 > 0.2 or epoch < 5`
-            d_x, d_g_z1 = float(m_real[1]), float(m_fake[1])
+            probs = torch.stack([m_real[1], m_fake[1]]).double()
+            if self.comm is not None:
+                self.comm.allreduce_f64(probs)
+            d_x, d_g_z1 = (probs / self.world).tolist()
             stepped = d_x < 0.8 or d_g_z1 > 0.2
         if stepped:
             self.arenaD.grad.zero_()
             self.engD.backward(netD, tape_r, dl_r, None, need_dx=False, need_dw=True, into=self.intoD)
             self.engD.backward(netD, tape_f, dl_f, None, need_dx=False, need_dw=True, into=self.intoD)
+            self._exchange(self.bucketsD)
             self._adam(self.arenaD)
             self.d_steps += 1
         del tape_r, tape_f
@@ -121,11 +148,13 @@ class CGANTrainer:
         m_adv, dl_g = self._bce(logit_g, smooth_real)
         _, tape_fr = self.engD.forward(netD, real, real_labels, save=True, head=False)
         self.engD.replay_running_stats(netD, tape_a)          # the reference's features pass over the fake batch
-        l_fm, dfeats = self._feature_matching(tape_fr[0], tape_a[0])
+        fm_loss, adders = self._feature_matching(tape_fr[0], tape_a[0])
         dfake = Act(torch.empty_like(fake.t), nchw=False)
-        self.engD.backward(netD, tape_a, dl_g, dfeats, need_dx=True, need_dw=False, dx_out=dfake)
+        self.engD.backward(netD, tape_a, dl_g, adders, need_dx=True, need_dw=False, dx_out=dfake)
+        l_fm = fm_loss()                                      # every pair has been visited by the backward pass
         self.arenaG.grad.zero_()
         self.engG.backward(netG, tape_g, dfake, need_dz=False, into=self.intoG)
+        self._exchange(self.bucketsG)
         self._adam(self.arenaG)
         zero = torch.zeros((), device=dev)
         return torch.stack([m_real[0] + m_fake[0], m_adv[0] + self.fm_weight * l_fm, m_real[1], m_fake[1], m_adv[1], zero, l_fm])

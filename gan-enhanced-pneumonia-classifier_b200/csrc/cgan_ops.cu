@@ -174,6 +174,47 @@ __global__ void __launch_bounds__(256) fm_pair_kernel(View r, View f, View d, fl
   if (threadIdx.x == 0) atomicAdd(sum, part[0]);
 }
 
+// the same for three dense bf16 tensors of one layout (every pair but the padded one): 16-byte accesses, eight elements per thread and trip
+__global__ void __launch_bounds__(256) fm_pair_dense_kernel(const uint4* __restrict__ r, const uint4* __restrict__ f, uint4* __restrict__ d, int64_t vecs,
+                                                           float coeff, int add, double* __restrict__ sum) {
+  __shared__ double part[256];
+  float s = 0.f;
+  double acc = 0.0;
+  int trips = 0;
+  for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < vecs; i += (int64_t)gridDim.x * 256) {
+    const uint4 rv = r[i], fv = f[i];
+    uint4 dv = (d && add) ? d[i] : make_uint4(0u, 0u, 0u, 0u);
+    const __nv_bfloat162* rp = reinterpret_cast<const __nv_bfloat162*>(&rv);
+    const __nv_bfloat162* fp = reinterpret_cast<const __nv_bfloat162*>(&fv);
+    __nv_bfloat162* dp = reinterpret_cast<__nv_bfloat162*>(&dv);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 a = __bfloat1622float2(rp[k]), b = __bfloat1622float2(fp[k]);
+      const float d0 = a.x - b.x, d1 = a.y - b.y;
+      s = fmaf(d0, d0, fmaf(d1, d1, s));
+      if (d) {
+        const float2 o = __bfloat1622float2(dp[k]);
+        dp[k] = __floats2bfloat162_rn(fmaf(coeff, d0, o.x), fmaf(coeff, d1, o.y));
+      }
+    }
+    if (d) d[i] = dv;
+    if (++trips == 16) { acc += (double)s; s = 0.f; trips = 0; }          // bound the fp32 partial sums
+  }
+  part[threadIdx.x] = acc + (double)s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) part[threadIdx.x] += part[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) atomicAdd(sum, part[0]);
+}
+
+bool dense_bf16_same(const b200gan_view* a, const b200gan_view* b) {
+  return a->dtype == B200GAN_BF16 && b->dtype == B200GAN_BF16 && a->sc == 1 && a->sw == a->c && a->sh == (int64_t)a->w * a->c &&
+         a->sn == (int64_t)a->h * a->w * a->c && b->sc == 1 && b->sw == a->sw && b->sh == a->sh && b->sn == a->sn &&
+         ((reinterpret_cast<uintptr_t>(a->ptr) | reinterpret_cast<uintptr_t>(b->ptr)) & 15) == 0;
+}
+
 // dst[r][c] += src[r * srs + c * scs]   (src float or double): bias gradients out of fp64 channel sums, the Linear's gradient out of the
 // latent GEMM's transposed layout
 __global__ void accumulate_2d_kernel(float* __restrict__ dst, const void* __restrict__ src, int f64, int rows, int cols, int64_t srs, int64_t scs) {
@@ -241,6 +282,12 @@ int cgan_fm_pair(const b200gan_view* r, const b200gan_view* f, const b200gan_vie
   View dv;
   if (d) dv = to_view(d); else dv.ptr = nullptr;
   const int64_t total = (int64_t)f->n * f->h * f->w * f->c;
+  if (total % 8 == 0 && dense_bf16_same(f, r) && (!d || dense_bf16_same(f, d))) {
+    fm_pair_dense_kernel<<<grid_for(total / 8), 256, 0, st>>>(reinterpret_cast<const uint4*>(r->ptr), reinterpret_cast<const uint4*>(f->ptr),
+                                                             d ? reinterpret_cast<uint4*>(d->ptr) : nullptr, total / 8, coeff, add, sum);
+    B200_LAUNCH_CHECK("fm_pair_dense_kernel");
+    return 0;
+  }
   fm_pair_kernel<<<grid_for(total), 256, 0, st>>>(to_view(r), to_view(f), dv, coeff, add, sum);
   B200_LAUNCH_CHECK("fm_pair_kernel");
   return 0;

@@ -10,6 +10,9 @@ downloaded at start-up.  That term is not implemented on the B200 path (no check
 CLI REFUSES to run unless `--no-perceptual` says the term may be dropped.  `--cpu` keeps the reference's stock-torch loop, perceptual term included
 when torchvision can load the checkpoint.
 Additive flags only: --no-perceptual, --dtype {bf16,fp32}, --synthetic N, --max-iters, --log-interval, --seed.
+Under `torchrun` (CUDA) the run is data parallel like train_gan.py's: one process per GPU, every rank trains on its own shard (DistributedSampler /
+its own synthetic images and random draws), weights start from rank 0's initialisation, `CGANTrainer` sums the gradient arenas over the ranks on the
+library's NCCL communicator and evaluates the D-step skip rule on rank-averaged probabilities; rank 0 writes the artefacts.
 """
 import argparse
 import json
@@ -123,15 +126,27 @@ class _VGGPerceptual(nn.Module):
 
 def main(args):
     use_cuda = torch.cuda.is_available() and not args.cpu
-    device = torch.device('cuda' if use_cuda else 'cpu')
-    print(f'Using device: {device}')
+    world, rank, local_rank = (int(os.environ.get(k, d)) for k, d in (('WORLD_SIZE', '1'), ('RANK', '0'), ('LOCAL_RANK', '0')))
+    if world > 1 and not use_cuda:
+        print('Error: data-parallel training (torchrun) needs CUDA devices.')
+        return None
+    device = torch.device('cuda', local_rank) if use_cuda else torch.device('cpu')
+    is_main = rank == 0
+    if is_main:
+        print(f'Using device: {device}' + (f' (data parallel over {world} ranks)' if world > 1 else ''))
     no_perceptual = getattr(args, 'no_perceptual', False)
     if use_cuda and not no_perceptual:
-        print('Error: the VGG16 perceptual term of the reference (train_cgan.py:57-73,186) is not implemented on the B200 path. '
-              'Pass --no-perceptual to train with the adversarial and feature-matching terms only, or --cpu for the stock-torch loop.')
+        if is_main:
+            print('Error: the VGG16 perceptual term of the reference (train_cgan.py:57-73,186) is not implemented on the B200 path. '
+                  'Pass --no-perceptual to train with the adversarial and feature-matching terms only, or --cpu for the stock-torch loop.')
         return None
-    if getattr(args, 'seed', None) is not None:
-        torch.manual_seed(args.seed)
+    if use_cuda:
+        torch.cuda.set_device(device)
+    if world > 1:
+        torch.distributed.init_process_group('nccl')
+    seed = getattr(args, 'seed', None)
+    if seed is not None:
+        torch.manual_seed(seed)          # common stream: weight initialisation and the fixed visualisation noise are the same on every rank
     model_dir = os.path.join(args.model_dir, 'gan')
     image_dir = os.path.join(args.output_dir, 'gan_images')
     for d in (model_dir, image_dir, args.results_dir, args.figures_dir):
@@ -139,7 +154,7 @@ def main(args):
 
     n_syn = getattr(args, 'synthetic', 0)
     if n_syn:
-        dataloader = _synthetic_labelled_loader(n_syn, args.num_channels, args.batch_size, 1)
+        dataloader = _synthetic_labelled_loader(n_syn, args.num_channels, args.batch_size, 1 + rank)
     else:
         try:
             from data_loader import RSNAPneumoniaDataset, data_transforms          # the reference's src/data_loader.py
@@ -151,19 +166,34 @@ def main(args):
             dataset = RSNAPneumoniaDataset(data_dir=os.path.join(args.data_dir, 'Training', 'Images'),
                                            metadata_file=os.path.join(args.data_dir, 'stage2_train_metadata.csv'),
                                            transform=data_transforms['train'], is_test=False)
-            dataloader = torch.utils.data.DataLoader(dataset, batch_size=args.batch_size, shuffle=True, num_workers=args.workers)
+            if world > 1:
+                sampler = torch.utils.data.distributed.DistributedSampler(dataset, num_replicas=world, rank=rank, shuffle=True, seed=seed or 0, drop_last=True)
+                dataloader = torch.utils.data.DataLoader(dataset, batch_size=args.batch_size, sampler=sampler, num_workers=args.workers, drop_last=True)
+            else:
+                dataloader = torch.utils.data.DataLoader(dataset, batch_size=args.batch_size, shuffle=True, num_workers=args.workers)
         except Exception as e:                                                      # reference :101-103
             print(f'Error loading data: {e}')
             return None
-    print(f'Loaded training data with {len(dataloader.dataset)} samples.')
+    if is_main:
+        print(f'Loaded training data with {len(dataloader.dataset)} samples.')
+    if world > 1:                        # every rank must issue the same number of gradient exchanges per epoch
+        nb = torch.tensor([len(dataloader), -len(dataloader)], device=device, dtype=torch.int64)
+        torch.distributed.all_reduce(nb, op=torch.distributed.ReduceOp.MAX)
+        if int(nb[0]) != -int(nb[1]):
+            raise RuntimeError(f'data-parallel ranks disagree on the number of batches per epoch ({-int(nb[1])}..{int(nb[0])})')
 
     netG = Generator(args.latent_dim, NUM_CLASSES, args.num_channels, args.feature_maps_g).to(device)
     netD = Discriminator(NUM_CLASSES, args.num_channels, args.feature_maps_d).to(device)
     netG.apply(weights_init)
     netD.apply(weights_init)
+    if world > 1:                        # all replicas start from rank 0's initialisation
+        for t in list(netG.state_dict().values()) + list(netD.state_dict().values()):
+            torch.distributed.broadcast(t, 0)
     fixed_noise = torch.randn(args.vis_batch_size, args.latent_dim, device=device)
     fixed_labels = torch.tensor(np.tile(np.arange(NUM_CLASSES), args.vis_batch_size // NUM_CLASSES + 1)[:args.vis_batch_size], dtype=torch.long,
                                 device=device)
+    if seed is not None and world > 1:
+        torch.manual_seed(seed + rank)   # from here on (noise, fake labels, label smoothing) every rank draws its own stream
     trainer = None
     if use_cuda:
         dtype = {'bf16': torch.bfloat16, 'fp32': torch.float32}[getattr(args, 'dtype', 'bf16')]
@@ -189,6 +219,8 @@ def main(args):
                 pending.clear()
 
         n_batches = len(dataloader)
+        if world > 1 and hasattr(getattr(dataloader, 'sampler', None), 'set_epoch'):
+            dataloader.sampler.set_epoch(epoch)
         for i, (real_images, real_labels) in enumerate(dataloader):
             real_images = real_images.to(device, non_blocking=True)
             real_labels = real_labels.to(device, non_blocking=True)
@@ -199,9 +231,10 @@ def main(args):
                                                         args.latent_dim))
             last = (epoch == args.epochs - 1 and i == n_batches - 1) or (max_iters and iters + 1 >= max_iters)
             if (iters % args.save_interval == 0) or last:
-                with torch.no_grad():                      # the networks stay in training mode, as in the reference (:208-210)
-                    fake_vis = netG(fixed_noise, fixed_labels, 1.0).detach().float().cpu()
-                _save_image_grid(fake_vis, f'{image_dir}/fake_samples_epoch_{epoch + 1:03d}_iter_{iters:06d}.png')
+                with torch.no_grad():                      # the networks stay in training mode, as in the reference (:208-210); every rank
+                    fake_vis = netG(fixed_noise, fixed_labels, 1.0).detach().float().cpu()        # runs it: the BatchNorm buffers move
+                if is_main:
+                    _save_image_grid(fake_vis, f'{image_dir}/fake_samples_epoch_{epoch + 1:03d}_iter_{iters:06d}.png')
             iters += 1
             if len(pending) >= log_interval:
                 flush()
@@ -214,21 +247,27 @@ def main(args):
         history['G_losses_epoch'].append(float(r[:, 1].mean()))
         history['perceptual_losses'].append(float(r[:, 5].mean()))
         history['feature_matching_losses'].append(float(r[:, 6].mean()))
-        print(f"Epoch {epoch + 1}/{args.epochs} Summary - Time: {time.time() - epoch_start:.2f}s, Avg Loss_D: {history['D_losses_epoch'][-1]:.4f}, "
-              f"Avg Loss_G: {history['G_losses_epoch'][-1]:.4f}, D(x): {r[:, 2].mean():.3f}, D(G(z)): {r[:, 4].mean():.3f}")
-        if (epoch + 1) % args.checkpoint_interval == 0 or (epoch + 1) == args.epochs:
+        if is_main:
+            print(f"Epoch {epoch + 1}/{args.epochs} Summary - Time: {time.time() - epoch_start:.2f}s, Avg Loss_D: {history['D_losses_epoch'][-1]:.4f}, "
+                  f"Avg Loss_G: {history['G_losses_epoch'][-1]:.4f}, D(x): {r[:, 2].mean():.3f}, D(G(z)): {r[:, 4].mean():.3f}")
+        if is_main and ((epoch + 1) % args.checkpoint_interval == 0 or (epoch + 1) == args.epochs):
             _save_state(netG, os.path.join(model_dir, f'generator_epoch_{epoch + 1:03d}.pth'))
             _save_state(netD, os.path.join(model_dir, f'discriminator_epoch_{epoch + 1:03d}.pth'))
             print(f'Saved checkpoints for epoch {epoch + 1} to {model_dir}')
         if stop:
             break
-    print(f'Training finished in {time.time() - start:.2f} seconds.')
-    _save_state(netG, os.path.join(model_dir, 'generator_final.pth'))
-    _save_state(netD, os.path.join(model_dir, 'discriminator_final.pth'))
-    print(f'Saved final models to {model_dir}')
-    with open(os.path.join(args.results_dir, 'gan_training_history.json'), 'w') as f:
-        json.dump(history, f, indent=4)
-    plot_gan_losses(history, os.path.join(args.figures_dir, 'gan_loss_curve.png'))
+    if is_main:
+        print(f'Training finished in {time.time() - start:.2f} seconds.')
+        _save_state(netG, os.path.join(model_dir, 'generator_final.pth'))
+        _save_state(netD, os.path.join(model_dir, 'discriminator_final.pth'))
+        print(f'Saved final models to {model_dir}')
+        with open(os.path.join(args.results_dir, 'gan_training_history.json'), 'w') as f:
+            json.dump(history, f, indent=4)
+        plot_gan_losses(history, os.path.join(args.figures_dir, 'gan_loss_curve.png'))
+    if world > 1:
+        if trainer is not None:
+            trainer.close()
+        torch.distributed.destroy_process_group()
     return history
 
 

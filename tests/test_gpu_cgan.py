@@ -367,6 +367,15 @@ def test_loss_kernels_match_numpy():
     L.call('b200gan_fm_pair', C.byref(ra.v), C.byref(fa.v), C.byref(d.v), -0.5, 1, L.ptr(s), st())
     close(s.item(), ((r.astype(np.float64) - f) ** 2).sum(), rtol=1e-6, what='feature-matching sum')
     close(d.t.permute(0, 3, 1, 2).cpu().numpy(), 1.0 - 0.5 * (r - f), rtol=1e-6, atol=1e-6, what='feature-matching gradient (accumulating)')
+    # the dense bf16 fast path (three NHWC tensors of one layout), accumulating and overwriting
+    rb, fb = dev(rng.randn(4, 6, 6, 32).astype(np.float32), torch.bfloat16), dev(rng.randn(4, 6, 6, 32).astype(np.float32), torch.bfloat16)
+    for add in (1, 0):
+        db = torch.full((4, 6, 6, 32), 0.5, device='cuda', dtype=torch.bfloat16)
+        s.zero_()
+        L.call('b200gan_fm_pair', C.byref(Act(rb, nchw=False).v), C.byref(Act(fb, nchw=False).v), C.byref(Act(db, nchw=False).v), 0.25, add, L.ptr(s), st())
+        diff = rb.double() - fb.double()
+        close(s.item(), (diff ** 2).sum().item(), rtol=1e-6, what='feature-matching sum, dense bf16')
+        close(db.float().cpu().numpy(), ((0.5 if add else 0.0) + 0.25 * diff).float().cpu().numpy(), rtol=8e-3, atol=4e-3, what='feature-matching gradient, dense bf16')
     src = rng.randn(4, 6)
     dst = torch.full((6, 4), 2.0, device='cuda')
     src_d = dev(src)

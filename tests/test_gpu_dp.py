@@ -223,3 +223,54 @@ def test_two_nccl_ranks_wgan_gp_replicas_stay_identical(tmp_path):
             continue
         assert np.array_equal(a[k], b[k]), f'replicas diverged on {k}'
     assert not np.array_equal(a['D.main.3.running_mean'], b['D.main.3.running_mean'])
+
+
+def _cgan_worker(rank, port, out_dir):
+    import json
+    import torch.distributed as dist
+    from conftest import GOLDEN
+    from gan_enhanced_pneumonia_classifier_b200 import cgan
+    from gan_enhanced_pneumonia_classifier_b200.cgan_trainer import CGANTrainer
+    from test_oracle_golden import cgan_state
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=WORLD, device_id=torch.device('cuda', rank))
+    try:
+        g = np.load(os.path.join(GOLDEN, 'cgan_step_nc3.npz'))
+        m = json.loads(str(g['meta']))
+        G, D = cgan.Generator(m['nz'], 2, m['nc'], m['nf']), cgan.Discriminator(2, m['nc'], m['nf'])
+        G.load_state_dict({k: torch.from_numpy(v) for k, v in cgan_state(g, 'G').items()})
+        D.load_state_dict({k: torch.from_numpy(v) for k, v in cgan_state(g, 'D').items()})
+        tr = CGANTrainer(G.cuda(), D.cuda(), dtype=torch.float32)
+        torch.manual_seed(100 + rank)                          # each rank its own images, labels and random draws
+        rows, stepped = [], []
+        for it, epoch in enumerate((0, 5, 5)):                 # epoch 5: the D-step skip rule is live (rank-averaged probabilities decide)
+            real = torch.rand(3, m['nc'], 224, 224, device='cuda') * 2 - 1
+            labels = torch.randint(0, 2, (3,), device='cuda')
+            before = tr.d_steps
+            rows.append(tr.step(real, labels, epoch=epoch).cpu().numpy())
+            stepped.append(tr.d_steps - before)
+        np.savez(os.path.join(out_dir, f'cgan{rank}.npz'), rows=np.stack(rows), stepped=np.array(stepped), collectives=tr.comm.collectives,
+                 **{f'G.{k}': v.cpu().numpy() for k, v in G.state_dict().items() if 'running' not in k and 'num_batches' not in k},
+                 **{f'D.{k}': v.cpu().numpy() for k, v in D.state_dict().items() if 'running' not in k and 'num_batches' not in k})
+        tr.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs')
+def test_two_nccl_ranks_cgan_replicas_stay_identical_and_agree_on_the_skip_rule(tmp_path):
+    """CGANTrainer under data parallelism: different shards and random draws per rank, gradient arenas summed on the library's communicator, the
+    D-step skip rule decided on rank-averaged probabilities -- so the replicas take the same branch, issue the same collectives and hold
+    bit-identical weights afterwards (per-rank BatchNorm buffers excluded: statistics are local)."""
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        port = s.getsockname()[1]
+    mp.start_processes(_cgan_worker, args=(port, str(tmp_path)), nprocs=WORLD, join=True, start_method='spawn')
+    a, b = (np.load(os.path.join(str(tmp_path), f'cgan{r}.npz')) for r in range(WORLD))
+    assert np.array_equal(a['stepped'], b['stepped']) and int(a['collectives']) == int(b['collectives']) > 0
+    assert np.isfinite(a['rows']).all() and np.isfinite(b['rows']).all() and not np.array_equal(a['rows'], b['rows'])
+    for k in a.files:
+        if k[:2] in ('G.', 'D.'):
+            assert np.array_equal(a[k], b[k]), f'{k} differs between the replicas'
