@@ -514,8 +514,8 @@ def run_ours(args):
         torch.cuda.empty_cache()
 
     # BASELINE.json configs[3]: CGAN (cgan.py / train_cgan.py), CLI-default widths (feature_maps 32, nc=3), batch 1024 per GPU.  A parity-test
-    # configuration (tests/test_gpu_cgan.py), measured for the record: one iteration of train_cgan.py:150-193 WITHOUT the VGG16 perceptual term
-    # (not implemented: its ImageNet checkpoint cannot be obtained offline).  Kernel by kernel, unfused bias / BatchNorm passes, no CUDA graph.
+    # configuration (tests/test_gpu_cgan.py, tests/test_gpu_perceptual.py), measured for the record: one iteration of train_cgan.py:150-193 without
+    # and with the VGG16 perceptual term (random VGG16 weights).  Kernel by kernel, unfused bias / BatchNorm passes, no CUDA graph.
     cg = None
     log('cgan configuration')
     if nc == 1 and not args.no_cgan and not strong and world == 1:
@@ -524,7 +524,7 @@ def run_ours(args):
         torch.manual_seed(0)
         cB = 1024
         cG, cD = cgan_mod.Generator(nz, 2, 3, 32).cuda(), cgan_mod.Discriminator(2, 3, 32).cuda()
-        ctr = CGANTrainer(cG, cD, dtype=dtype)
+        ctr = CGANTrainer(cG, cD, perceptual_weight=0.0, dtype=dtype)
         creal = torch.rand((cB, 3, 224, 224), device='cuda', generator=gen) * 2 - 1
         clab = torch.randint(0, 2, (cB,), device='cuda', generator=gen)
         ctr.step(creal, clab)
@@ -537,10 +537,26 @@ def run_ours(args):
         c1.record()
         torch.cuda.synchronize()
         cms = c0.elapsed_time(c1) / kc
-        cg = {'model': 'CGAN (cgan.py, train_cgan.py:150-193 minus the VGG16 perceptual term): feature_maps 32, projection discriminator, '
-                       'adversarial + feature-matching generator loss', 'nc': 3, 'per_gpu_batch': cB, 'value': cB / (cms * 1e-3), 'unit': UNIT,
-              'ms_per_iteration': cms, 'steps': kc, 'last_history': [float(v) for v in cout.tolist()]}
-        del ctr, cG, cD
+        cg = {'model': 'CGAN (cgan.py, train_cgan.py:150-193): feature_maps 32, projection discriminator; generator loss = adversarial + '
+                       '5 x feature matching (`value`: --no-perceptual) and + 10 x VGG16 perceptual (`with_perceptual`: the full loss of train_cgan.py:191, '
+                       'VGG16 on RANDOM weights -- the ImageNet checkpoint cannot be obtained offline; the arithmetic does not depend on the values)',
+              'nc': 3, 'per_gpu_batch': cB, 'value': cB / (cms * 1e-3), 'unit': UNIT, 'ms_per_iteration': cms, 'steps': kc,
+              'last_history': [float(v) for v in cout.tolist()]}
+        del ctr
+        torch.cuda.empty_cache()
+        from gan_enhanced_pneumonia_classifier_b200.perceptual import PerceptualLoss
+        vgg = PerceptualLoss('random').cuda()
+        ctr = CGANTrainer(cG, cD, perceptual=vgg, perceptual_weight=10.0, dtype=dtype)
+        ctr.step(creal, clab)
+        torch.cuda.synchronize()
+        c0.record()
+        for _ in range(kc):
+            cout = ctr.step(creal, clab)
+        c1.record()
+        torch.cuda.synchronize()
+        pms = c0.elapsed_time(c1) / kc
+        cg['with_perceptual'] = {'value': cB / (pms * 1e-3), 'unit': UNIT, 'ms_per_iteration': pms, 'steps': kc, 'last_history': [float(v) for v in cout.tolist()]}
+        del ctr, cG, cD, vgg
         torch.cuda.empty_cache()
     log('roofline kernels, cpu baseline')
     if rank == 0:

@@ -74,6 +74,11 @@ PROTOTYPES = {
     'b200gan_bce_logits': [_vp, _vp, _i32, _f32, _vp, _vp, _vp],
     'b200gan_fm_pair': [_VP, _VP, _VP, _f32, _i32, _vp, _vp],
     'b200gan_accumulate_2d': [_vp, _vp, _i32, _i32, _i32, _i64, _i64, _vp],
+    'b200gan_conv3x3_fold': [_vp, _i32, _i32, _i32, _vp, _vp],
+    'b200gan_bias_relu_d2s': [_VP, _vp, _VP, _vp],
+    'b200gan_relu_bwd_s2d': [_VP, _VP, _VP, _vp],
+    'b200gan_maxpool2_fwd': [_VP, _VP, _vp],
+    'b200gan_maxpool2_bwd': [_VP, _VP, _VP, _i32, _vp],
     'b200gan_embed_add': [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp],
     'b200gan_embed_bwd': [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp],
     'b200gan_upconv3_fold': [_vp, _i32, _i32, _vp, _vp],

@@ -9,9 +9,10 @@ What one `step` does, in the reference's order:
                        targets, ONE backward through the Discriminator carrying both the logit gradient and the gradients of all intermediate
                        features (the reference's second features pass over the same fake batch is bit-for-bit the first: only its BatchNorm
                        running-statistics side effect is replayed), the Generator's backward + Adam.
-The VGG16 perceptual term (:57-73,186; weight 10) is NOT implemented: it needs torchvision's ImageNet checkpoint, which neither the reference nor
-this library can obtain offline, so there is nothing to check it against.  `CGANTrainer(perceptual_weight != 0)` raises instead of silently
-dropping the term.
+The VGG16 perceptual term (:57-73,186; weight 10) is `perceptual.PerceptualLoss` handed to the constructor: its gradient w.r.t. the fake batch is added to
+the one coming back through the Discriminator before the Generator's backward.  The ImageNet checkpoint the reference downloads cannot be obtained
+offline, so the CALLER supplies the VGG16 (checkpoint path, torchvision's cache, or random weights for benchmarks); without one the term is dropped
+only on an explicit `perceptual_weight=0`, never silently.
 """
 from __future__ import annotations
 
@@ -33,10 +34,13 @@ FEATURE_MULTIPLICITY = [2, 1, 2, 1, 2, 1, 2, 1, 2]      # of [a0, y1, a1, ..., y
 
 class CGANTrainer:
     def __init__(self, netG, netD, lr: float = 2e-4, beta1: float = 0.5, beta2: float = 0.999, eps: float = 1e-8, fm_weight: float = 5.0,
-                 perceptual_weight: float = 0.0, dtype: Optional[torch.dtype] = None, process_group=None):
-        if perceptual_weight != 0.0:
-            raise L.B200GanError('the VGG16 perceptual term of train_cgan.py:57-73 is not implemented (its ImageNet weights cannot be obtained '
-                                 'offline); pass perceptual_weight=0 to train with the adversarial and feature-matching terms only')
+                 perceptual=None, perceptual_weight: float = 10.0, dtype: Optional[torch.dtype] = None, process_group=None):
+        """perceptual: a `perceptual.PerceptualLoss` (VGG16 with whatever weights the caller could obtain) or None; with None the term is only
+        dropped when perceptual_weight is explicitly 0 -- asking for the reference's loss (weight 10) without a VGG16 raises."""
+        if perceptual is None and perceptual_weight != 0.0:
+            raise L.B200GanError('the generator loss of train_cgan.py:191 includes 10 x a VGG16 perceptual term: pass perceptual=PerceptualLoss(...) '
+                                 '(perceptual.py), or perceptual_weight=0 to train with the adversarial and feature-matching terms only')
+        self.perceptual, self.perceptual_weight = perceptual, (perceptual_weight if perceptual is not None else 0.0)
         self.netG, self.netD = netG, netD
         self.lr, self.beta1, self.beta2, self.eps, self.fm_weight = lr, beta1, beta2, eps, fm_weight
         if dtype is not None:
@@ -107,7 +111,7 @@ class CGANTrainer:
     def step(self, real: torch.Tensor, real_labels: torch.Tensor, epoch: int = 0, noise: Optional[torch.Tensor] = None,
              fake_labels: Optional[torch.Tensor] = None, smooth_real: Optional[torch.Tensor] = None, smooth_fake: Optional[torch.Tensor] = None):
         """real: (N, nc, 224, 224) CUDA tensor; real_labels: (N,) int64.  The random draws of the reference (train_cgan.py:156-160,166-167) are
-        made here unless given.  Returns a (7,) CUDA tensor [errD, errG, D_x, D_G_z1, D_G_z2, perceptual (0), feature matching] -- no host
+        made here unless given.  Returns a (7,) CUDA tensor [errD, errG, D_x, D_G_z1, D_G_z2, perceptual, feature matching] -- no host
         synchronisation before epoch 5."""
         netG, netD = self.netG, self.netD
         if not (netG.training and netD.training):
@@ -152,9 +156,12 @@ class CGANTrainer:
         dfake = Act(torch.empty_like(fake.t), nchw=False)
         self.engD.backward(netD, tape_a, dl_g, adders, need_dx=True, need_dw=False, dx_out=dfake)
         l_fm = fm_loss()                                      # every pair has been visited by the backward pass
+        l_p = torch.zeros((), device=dev)
+        if self.perceptual is not None and self.perceptual_weight != 0.0:      # 10 x perceptual(fake, real), train_cgan.py:186,191: its gradient joins dfake
+            self.perceptual.compute_dtype = self.engG.dtype
+            l_p = self.perceptual._engine_for().loss_and_grad(fake, real, self.perceptual_weight, dx_into=dfake)
         self.arenaG.grad.zero_()
         self.engG.backward(netG, tape_g, dfake, need_dz=False, into=self.intoG)
         self._exchange(self.bucketsG)
         self._adam(self.arenaG)
-        zero = torch.zeros((), device=dev)
-        return torch.stack([m_real[0] + m_fake[0], m_adv[0] + self.fm_weight * l_fm, m_real[1], m_fake[1], m_adv[1], zero, l_fm])
+        return torch.stack([m_real[0] + m_fake[0], m_adv[0] + self.perceptual_weight * l_p + self.fm_weight * l_fm, m_real[1], m_fake[1], m_adv[1], l_p, l_fm])

@@ -111,6 +111,13 @@ int cgan_bce_logits(const float* x, const float* t, int batch, float grad_scale,
 int cgan_fm_pair(const b200gan_view* r, const b200gan_view* f, const b200gan_view* d, float coeff, int add, double* sum, cudaStream_t st);
 int cgan_accumulate_2d(float* dst, const void* src, int f64, int rows, int cols, int64_t srs, int64_t scs, cudaStream_t st);
 
+// vgg_ops.cu
+int vgg_conv3x3_fold(const float* w3, int co, int ci, int ci_pad, float* w4, cudaStream_t st);
+int vgg_bias_relu_d2s(const b200gan_view* t, const float* bias, const b200gan_view* a, cudaStream_t st);
+int vgg_relu_bwd_s2d(const b200gan_view* da, const b200gan_view* a, const b200gan_view* dt, cudaStream_t st);
+int vgg_maxpool2_fwd(const b200gan_view* a, const b200gan_view* p, cudaStream_t st);
+int vgg_maxpool2_bwd(const b200gan_view* a, const b200gan_view* dp, const b200gan_view* da, int add, cudaStream_t st);
+
 static int check_conv(const b200gan_conv* cv) {
   if (!cv) { set_error("null conv descriptor"); return B200GAN_ERR_BAD_ARG; }
   if (cv->k <= 0 || cv->stride <= 0 || cv->pad < 0 || cv->k > 16) { set_error("bad conv geometry k=%d s=%d p=%d", cv->k, cv->stride, cv->pad); return B200GAN_ERR_BAD_ARG; }
@@ -529,6 +536,42 @@ int b200gan_class_proj_bwd(const b200gan_view* x, const float* table, const int6
   B200_CHECK_ARG(table && labels && dout && num_classes > 0, "class_proj_bwd: bad argument");
   B200_CHECK_ARG(!dx || (dx->n == x->n && dx->h == x->h && dx->w == x->w && dx->c == x->c), "class_proj_bwd: dx and x differ in extent");
   return cgan_class_proj_bwd(x, table, labels, dout, dx, num_classes, dtable, (cudaStream_t)stream);
+}
+
+int b200gan_conv3x3_fold(const float* w3, int32_t co, int32_t ci, int32_t ci_pad, float* w4, void* stream) {
+  B200_CHECK_ARG(w3 && w4 && co > 0 && ci > 0 && ci_pad >= ci, "conv3x3_fold: bad argument");
+  return vgg_conv3x3_fold(w3, co, ci, ci_pad, w4, (cudaStream_t)stream);
+}
+
+int b200gan_bias_relu_d2s(const b200gan_view* t, const float* bias, const b200gan_view* a, void* stream) {
+  int rc;
+  if ((rc = check_view(t, "bias_relu_d2s"))) return rc;
+  if ((rc = check_view(a, "bias_relu_d2s"))) return rc;
+  B200_CHECK_ARG(bias, "bias_relu_d2s: null bias");
+  return vgg_bias_relu_d2s(t, bias, a, (cudaStream_t)stream);
+}
+
+int b200gan_relu_bwd_s2d(const b200gan_view* da, const b200gan_view* a, const b200gan_view* dt, void* stream) {
+  int rc;
+  if ((rc = check_view(da, "relu_bwd_s2d"))) return rc;
+  if ((rc = check_view(a, "relu_bwd_s2d"))) return rc;
+  if ((rc = check_view(dt, "relu_bwd_s2d"))) return rc;
+  return vgg_relu_bwd_s2d(da, a, dt, (cudaStream_t)stream);
+}
+
+int b200gan_maxpool2_fwd(const b200gan_view* a, const b200gan_view* p, void* stream) {
+  int rc;
+  if ((rc = check_view(a, "maxpool2_fwd"))) return rc;
+  if ((rc = check_view(p, "maxpool2_fwd"))) return rc;
+  return vgg_maxpool2_fwd(a, p, (cudaStream_t)stream);
+}
+
+int b200gan_maxpool2_bwd(const b200gan_view* a, const b200gan_view* dp, const b200gan_view* da, int32_t add, void* stream) {
+  int rc;
+  if ((rc = check_view(a, "maxpool2_bwd"))) return rc;
+  if ((rc = check_view(dp, "maxpool2_bwd"))) return rc;
+  if ((rc = check_view(da, "maxpool2_bwd"))) return rc;
+  return vgg_maxpool2_bwd(a, dp, da, add, (cudaStream_t)stream);
 }
 
 int b200gan_gather_augment(const uint8_t* cache, int64_t num_images, const int64_t* index, const uint8_t* flip, const float* mean,

@@ -5,11 +5,12 @@ nine history lists of reference :127-128 -- the five per-iteration ones stay emp
 semantics (reference :150-193: randomly smoothed BCEWithLogits targets, the D-step skip rule from epoch 5 on, adversarial + feature-matching
 Generator loss, Adam betas (beta1, 0.999)).
 
-One deliberate difference, stated instead of hidden: the reference adds 10 x a VGG16 perceptual loss (:57-73,186) whose ImageNet checkpoint is
-downloaded at start-up.  That term is not implemented on the B200 path (no checkpoint offline, nothing to pin it against): on a CUDA device this
-CLI REFUSES to run unless `--no-perceptual` says the term may be dropped.  `--cpu` keeps the reference's stock-torch loop, perceptual term included
-when torchvision can load the checkpoint.
-Additive flags only: --no-perceptual, --dtype {bf16,fp32}, --synthetic N, --max-iters, --log-interval, --seed.
+The VGG16 perceptual loss (:57-73, 10 x in the Generator loss :186,191) is `perceptual.PerceptualLoss` (same `blocks`, frozen, B200 kernels on CUDA).
+Like the reference it asks torchvision for the ImageNet checkpoint at start-up (`--vgg-weights imagenet`, the default): where that cannot be had
+(offline, no cache) the CLI stops with a message instead of training something else -- give it a vgg16 state_dict file (`--vgg-weights FILE`), or say
+explicitly that the term may be dropped (`--no-perceptual`) or run on random weights (`--vgg-weights random`, benchmarks only).
+`--cpu` keeps the reference's stock-torch loop.
+Additive flags only: --no-perceptual, --vgg-weights, --dtype {bf16,fp32}, --synthetic N, --max-iters, --log-interval, --seed.
 Under `torchrun` (CUDA) the run is data parallel like train_gan.py's: one process per GPU, every rank trains on its own shard (DistributedSampler /
 its own synthetic images and random draws), weights start from rank 0's initialisation, `CGANTrainer` sums the gradient arenas over the ranks on the
 library's NCCL communicator and evaluates the D-step skip rule on rank-averaged probabilities; rank 0 writes the artefacts.
@@ -31,10 +32,12 @@ if __package__ in (None, ''):
     sys.path.insert(0, _HERE)
     from gan_enhanced_pneumonia_classifier_b200.cgan import Discriminator, Generator, weights_init
     from gan_enhanced_pneumonia_classifier_b200.cgan_trainer import CGANTrainer
+    from gan_enhanced_pneumonia_classifier_b200.perceptual import PerceptualLoss
     from gan_enhanced_pneumonia_classifier_b200.train_gan import _DATA_LOADER_HINT, _save_image_grid, _save_state
 else:
     from .cgan import Discriminator, Generator, weights_init
     from .cgan_trainer import CGANTrainer
+    from .perceptual import PerceptualLoss
     from .train_gan import _DATA_LOADER_HINT, _save_image_grid, _save_state
 
 HISTORY_KEYS = ('G_losses_iter', 'D_losses_iter', 'D_x_iter', 'D_G_z1_iter', 'D_G_z2_iter', 'G_losses_epoch', 'D_losses_epoch', 'perceptual_losses',
@@ -105,25 +108,6 @@ def _reference_cpu_iteration(netG, netD, optG, optD, criterion, perceptual, real
     return torch.tensor([err_d.item(), err_g.item(), d_x, d_g_z1, d_g_z2, float(err_p), err_fm.item()])
 
 
-class _VGGPerceptual(nn.Module):
-    """reference :57-73 (CPU path only): MSE between VGG16 feature maps after relu1_2, relu2_2, relu3_3."""
-
-    def __init__(self):
-        super().__init__()
-        import torchvision.models as models
-        vgg = models.vgg16(weights=models.VGG16_Weights.IMAGENET1K_V1).features
-        self.blocks = nn.ModuleList([vgg[:4], vgg[4:9], vgg[9:16]]).eval()
-        for p in self.parameters():
-            p.requires_grad = False
-
-    def forward(self, x, y):
-        total = 0.0
-        for block in self.blocks:
-            x, y = block(x), block(y)
-            total = total + torch.mean((x - y) ** 2)
-        return total
-
-
 def main(args):
     use_cuda = torch.cuda.is_available() and not args.cpu
     world, rank, local_rank = (int(os.environ.get(k, d)) for k, d in (('WORLD_SIZE', '1'), ('RANK', '0'), ('LOCAL_RANK', '0')))
@@ -135,11 +119,17 @@ def main(args):
     if is_main:
         print(f'Using device: {device}' + (f' (data parallel over {world} ranks)' if world > 1 else ''))
     no_perceptual = getattr(args, 'no_perceptual', False)
-    if use_cuda and not no_perceptual:
-        if is_main:
-            print('Error: the VGG16 perceptual term of the reference (train_cgan.py:57-73,186) is not implemented on the B200 path. '
-                  'Pass --no-perceptual to train with the adversarial and feature-matching terms only, or --cpu for the stock-torch loop.')
-        return None
+    perceptual = None
+    if not no_perceptual:
+        source = getattr(args, 'vgg_weights', 'imagenet')
+        try:
+            perceptual = PerceptualLoss(source)               # reference :60,112: downloads torchvision's ImageNet checkpoint unless cached
+        except Exception as e:   # noqa: BLE001
+            if is_main:
+                print(f'Error: cannot obtain the VGG16 weights of the perceptual loss ({source}): {e}')
+                print('Pass --vgg-weights FILE (a torchvision vgg16 state_dict), --vgg-weights random (architecture only), or --no-perceptual to train '
+                      'with the adversarial and feature-matching terms only.')
+            return None
     if use_cuda:
         torch.cuda.set_device(device)
     if world > 1:
@@ -197,10 +187,12 @@ def main(args):
     trainer = None
     if use_cuda:
         dtype = {'bf16': torch.bfloat16, 'fp32': torch.float32}[getattr(args, 'dtype', 'bf16')]
-        trainer = CGANTrainer(netG, netD, lr=args.lr, beta1=args.beta1, dtype=dtype)
+        if perceptual is not None:
+            perceptual = perceptual.to(device)
+        trainer = CGANTrainer(netG, netD, lr=args.lr, beta1=args.beta1, perceptual=perceptual, perceptual_weight=10.0 if perceptual is not None else 0.0,
+                              dtype=dtype)
     else:
         criterion = nn.BCEWithLogitsLoss()
-        perceptual = None if no_perceptual else _VGGPerceptual().to(device)
         optimizerD = optim.Adam(netD.parameters(), lr=args.lr, betas=(args.beta1, 0.999))
         optimizerG = optim.Adam(netG.parameters(), lr=args.lr, betas=(args.beta1, 0.999))
 
@@ -292,7 +284,9 @@ def build_parser():
     parser.add_argument('--checkpoint-interval', type=int, default=5)
     parser.add_argument('--cpu', action='store_true')
     # --- additive (not in the reference) --- #
-    parser.add_argument('--no-perceptual', action='store_true', help='drop the VGG16 perceptual term (required on CUDA: not implemented there)')
+    parser.add_argument('--no-perceptual', action='store_true', help='drop the VGG16 perceptual term of the Generator loss')
+    parser.add_argument('--vgg-weights', type=str, default='imagenet', help="VGG16 weights of the perceptual loss: 'imagenet' (torchvision's checkpoint, "
+                        "as the reference), a path to a vgg16 state_dict, or 'random' (architecture only)")
     parser.add_argument('--dtype', choices=['bf16', 'fp32'], default='bf16', help='compute dtype of the B200 kernels')
     parser.add_argument('--synthetic', type=int, default=0, help='train on N synthetic uniform[-1,1] images with random labels instead of the RSNA set')
     parser.add_argument('--max-iters', type=int, default=0, help='stop after this many iterations (0 = all epochs)')

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define B200GAN_VERSION 420   /* major*10000 + minor*100 + patch */
+#define B200GAN_VERSION 430   /* major*10000 + minor*100 + patch */
 
 typedef enum b200gan_status {
   B200GAN_OK = 0,
@@ -269,6 +269,23 @@ int b200gan_upconv3_unfold(const float* dw4, int32_t co, int32_t ci, float* dw3,
 int b200gan_class_proj_fwd(const b200gan_view* x, const float* table, const int64_t* labels, float* out, void* stream);
 int b200gan_class_proj_bwd(const b200gan_view* x, const float* table, const int64_t* labels, const float* dout, const b200gan_view* dx,
                            int32_t num_classes, float* dtable, void* stream);
+
+/* ---- VGG16 perceptual loss of the conditional GAN (src/train_cgan.py:57-73,186: MSE between torchvision vgg16.features[:4], [4:9], [9:16] of the
+ *      fake and the real batch; the network is frozen, only the gradient w.r.t. the fake image is needed).  Its Conv2d(3,1,1) layers run on the
+ *      stride-2 4x4 convolution kernels: T[n,i,j,(a,b,co)] = conv_k4s2p1(X, W4) with W4[(a,b,co),ci,kh,kw] = w3[co,ci,kh-a,kw-b] (zero outside
+ *      0..2) holds output pixel (2i+a, 2j+b) of the 3x3 convolution in channel block (a,b) -- all four output parities as 4*Co channels of one call
+ *      of b200gan_conv2d_fprop / b200gan_conv2d_dgrad (16/9 of the multiply-adds, tensor-core speed).  The entry points around it:
+ *        conv3x3_fold    w4 (4*Co, ci_pad, 4, 4) from w3 (Co, Ci, 3, 3); input channels Ci..ci_pad-1 are zero (the 3-channel image is stored 32 wide)
+ *        bias_relu_d2s   a[n,2i+a,2j+b,co] = relu(t[n,i,j,(a,b,co)] + bias[co])                 bias + ReLU + depth-to-space, one pass
+ *        relu_bwd_s2d    dt[n,i,j,(a,b,co)] = da[n,2i+a,2j+b,co] * (a[n,2i+a,2j+b,co] > 0)      ReLU backward + space-to-depth, one pass
+ *        maxpool2_fwd    nn.MaxPool2d(2,2)
+ *        maxpool2_bwd    da (+)= dp routed to the FIRST maximum of each window in (row, column) order (ATen's choice); add = 1 accumulates
+ *      Operands: dense NHWC views of one dtype (f32 / bf16), channels a multiple of 4 / 8.  The MSE itself is b200gan_fm_pair. */
+int b200gan_conv3x3_fold(const float* w3, int32_t co, int32_t ci, int32_t ci_pad, float* w4, void* stream);
+int b200gan_bias_relu_d2s(const b200gan_view* t, const float* bias, const b200gan_view* a, void* stream);
+int b200gan_relu_bwd_s2d(const b200gan_view* da, const b200gan_view* a, const b200gan_view* dt, void* stream);
+int b200gan_maxpool2_fwd(const b200gan_view* a, const b200gan_view* p, void* stream);
+int b200gan_maxpool2_bwd(const b200gan_view* a, const b200gan_view* dp, const b200gan_view* da, int32_t add, void* stream);
 
 /* ---- data-parallel gradient-bucket layer (new functionality: the reference is single-device, src/train_gan.py:49; semantics in
  *      SURVEY.md section 8e).  One process per GPU; weights and Adam state replicated; every optimizer update (train_gan.py:141,150)

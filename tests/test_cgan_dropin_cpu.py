@@ -72,3 +72,23 @@ def test_checkpoints_round_trip_with_the_reference_modules():
     x = torch.randn(3, 3, 224, 224)
     assert torch.equal(mine_g(z, labels), ref_g(z, labels))
     assert torch.allclose(mine_d(x, labels), ref_d(x, labels), rtol=1e-5, atol=1e-5)
+
+
+def test_perceptual_loss_dropin_cpu_path_is_the_reference_formula():
+    """perceptual.PerceptualLoss on CPU tensors: torchvision's vgg16.features[:4], [4:9], [9:16], chained, MSE summed (train_cgan.py:57-73), frozen
+    parameters -- checked against the numpy oracle on the same random weights."""
+    import vgg_oracle as vo
+    from gan_enhanced_pneumonia_classifier_b200.perceptual import PerceptualLoss
+    sd = vo.init_weights(np.random.RandomState(2))
+    mod = PerceptualLoss('random')
+    assert len(mod.blocks) == 3 and [len(b) for b in mod.blocks] == [4, 5, 7] and not mod.blocks.training
+    assert all(not p.requires_grad for p in mod.parameters())
+    torch.nn.Sequential(*[m for blk in mod.blocks for m in blk]).load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    rng = np.random.RandomState(3)
+    x, y = rng.rand(1, 3, 16, 16).astype(np.float32), rng.rand(1, 3, 16, 16).astype(np.float32)
+    xt = torch.from_numpy(x).requires_grad_(True)
+    loss = mod(xt, torch.from_numpy(y))
+    loss.backward()
+    ref, dx = vo.perceptual(x, y, sd)
+    close(loss.item(), ref, rtol=1e-5, what='perceptual loss')
+    close(xt.grad.numpy(), dx, rtol=1e-3, atol=1e-7, what='d perceptual / d x')

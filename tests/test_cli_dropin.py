@@ -117,7 +117,7 @@ def test_cgan_cli_keeps_reference_flags_and_defaults():
     args = vars(tc.build_parser().parse_args([]))
     for k, v in REF_CGAN_FLAGS.items():
         assert args[k] == v, k
-    assert set(args) - set(REF_CGAN_FLAGS) == {'no_perceptual', 'dtype', 'synthetic', 'max_iters', 'log_interval', 'seed'}
+    assert set(args) - set(REF_CGAN_FLAGS) == {'no_perceptual', 'vgg_weights', 'dtype', 'synthetic', 'max_iters', 'log_interval', 'seed'}
 
 
 def test_cgan_cpu_round_trip_writes_reference_artefacts(tmp_path):

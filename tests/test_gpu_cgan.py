@@ -393,7 +393,7 @@ def test_fused_trainer_matches_reference_fixture_and_the_module_loop(name):
     m = json.loads(str(g['meta']))
     G, D = build(g, m, torch.float32)
     G2, D2 = build(g, m, torch.float32)
-    tr = CGANTrainer(G, D, lr=m['lr'], beta1=m['beta1'], dtype=torch.float32)
+    tr = CGANTrainer(G, D, lr=m['lr'], beta1=m['beta1'], perceptual_weight=0.0, dtype=torch.float32)
     optD = torch.optim.Adam(D2.parameters(), lr=m['lr'], betas=(m['beta1'], 0.999))
     optG = torch.optim.Adam(G2.parameters(), lr=m['lr'], betas=(m['beta1'], 0.999))
     for it in range(m['iters']):
@@ -444,7 +444,7 @@ def test_fused_trainer_skips_the_d_step_by_the_reference_rule():
             D.main[14].bias.zero_()
             D.label_emb.weight[0] = 8.0 * a_real / a_real.dot(a_real)
             D.label_emb.weight[1] = -8.0 * a_fake / a_fake.dot(a_fake)
-        tr = CGANTrainer(G, D, lr=m['lr'], beta1=m['beta1'], dtype=torch.float32)
+        tr = CGANTrainer(G, D, lr=m['lr'], beta1=m['beta1'], perceptual_weight=0.0, dtype=torch.float32)
         before = tr.arenaD.param.clone()
         row = tr.step(real, real_labels, epoch=epoch, noise=draws[2], fake_labels=fake_labels, smooth_real=draws[0], smooth_fake=draws[1]).cpu().numpy()
         assert row[2] >= 0.8 and row[3] <= 0.2, row
@@ -456,9 +456,9 @@ def test_fused_trainer_bf16_full_width_runs_and_learns_finite():
     from gan_enhanced_pneumonia_classifier_b200.cgan_trainer import CGANTrainer
     torch.manual_seed(5)
     G, D = cgan.Generator(100, 2, 3, 32).cuda(), cgan.Discriminator(2, 3, 32).cuda()
-    tr = CGANTrainer(G, D, dtype=torch.bfloat16)
+    tr = CGANTrainer(G, D, perceptual_weight=0.0, dtype=torch.bfloat16)
     with pytest.raises(L.B200GanError):
-        CGANTrainer(G, D, perceptual_weight=10.0)
+        CGANTrainer(G, D)                                  # the reference's loss (perceptual weight 10) without a VGG16: refused, not dropped
     real = dev(synthetic_real(1, 16, 3))
     labels = dev(np.random.RandomState(2).randint(0, 2, 16).astype(np.int64))
     rows = torch.stack([tr.step(real, labels, epoch=e) for e in range(3)]).cpu().numpy()
@@ -473,8 +473,11 @@ def test_cgan_cli_on_gpu(tmp_path):
     d = str(tmp_path)
     base = ['--synthetic', '8', '--batch-size', '4', '--epochs', '1', '--vis-batch-size', '4', '--model-dir', d + '/models', '--output-dir', d + '/results',
             '--results-dir', d + '/results/metrics', '--figures-dir', d + '/results/figures', '--seed', '0', '--checkpoint-interval', '1']
-    assert tc.main(tc.build_parser().parse_args(base)) is None                       # refuses without --no-perceptual
+    # the reference's default needs torchvision's ImageNet checkpoint: offline (and uncached) the CLI stops instead of training something else
+    assert tc.main(tc.build_parser().parse_args(base + ['--vgg-weights', os.path.join(d, 'no_such_checkpoint.pth')])) is None
     hist = tc.main(tc.build_parser().parse_args(base + ['--no-perceptual']))
     assert len(hist['G_losses_epoch']) == 1 and np.isfinite(hist['G_losses_epoch'][0]) and hist['perceptual_losses'] == [0.0]
+    hist = tc.main(tc.build_parser().parse_args(base + ['--vgg-weights', 'random']))                 # the full generator loss of train_cgan.py:191
+    assert np.isfinite(hist['G_losses_epoch'][0]) and hist['perceptual_losses'][0] > 0
     sd = torch.load(d + '/models/gan/generator_final.pth')
     assert sd['fc.weight'].shape == (256 * 49, 100) and sd['fc.weight'].device.type == 'cpu'

@@ -241,7 +241,7 @@ def _cgan_worker(rank, port, out_dir):
         G, D = cgan.Generator(m['nz'], 2, m['nc'], m['nf']), cgan.Discriminator(2, m['nc'], m['nf'])
         G.load_state_dict({k: torch.from_numpy(v) for k, v in cgan_state(g, 'G').items()})
         D.load_state_dict({k: torch.from_numpy(v) for k, v in cgan_state(g, 'D').items()})
-        tr = CGANTrainer(G.cuda(), D.cuda(), dtype=torch.float32)
+        tr = CGANTrainer(G.cuda(), D.cuda(), perceptual_weight=0.0, dtype=torch.float32)
         torch.manual_seed(100 + rank)                          # each rank its own images, labels and random draws
         rows, stepped = [], []
         for it, epoch in enumerate((0, 5, 5)):                 # epoch 5: the D-step skip rule is live (rank-averaged probabilities decide)

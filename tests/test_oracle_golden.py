@@ -346,3 +346,34 @@ def test_cgan_oracle_d_step_skip_rule():
         assert moved == stepped
         seen.add(stepped)
     assert True in seen
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# VGG16 perceptual loss (train_cgan.py:57-73): the numpy oracle against torchvision's own vgg16.features[:16] with the same random weights
+# ---------------------------------------------------------------------------------------------------------------------------
+def test_vgg_oracle_matches_torchvision():
+    import torch
+    import torchvision.models as models
+    import vgg_oracle as vo
+    rng = np.random.RandomState(5)
+    sd = vo.init_weights(rng)
+    vgg = models.vgg16(weights=None).features[:16]
+    vgg.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    blocks = [vgg[:4], vgg[4:9], vgg[9:16]]                      # train_cgan.py:61-63
+    x = (rng.rand(2, 3, 32, 32).astype(np.float32) * 2 - 1)
+    y = (rng.rand(2, 3, 32, 32).astype(np.float32) * 2 - 1)
+    xt, yt = torch.from_numpy(x).requires_grad_(True), torch.from_numpy(y)
+    a, b, total = xt, yt, 0.0
+    for blk in blocks:                                           # train_cgan.py:66-73
+        a, b = blk(a), blk(b)
+        total = total + torch.mean((a - b) ** 2)
+    total.backward()
+    loss, dx = vo.perceptual(x, y, sd)
+    close(loss, total.item(), rtol=1e-5, what='perceptual loss')
+    grad_close(dx, xt.grad.numpy(), 'd perceptual / d x', bulk=1e-5, l2=1e-3, worst=2e-2)
+    # the max-pool tie rule: a window of equal values sends its gradient to the first element
+    a4 = np.zeros((1, 1, 2, 2), np.float32)
+    assert np.array_equal(vo.maxpool2_bwd(a4, np.ones((1, 1, 1, 1), np.float32)), np.array([[[[1, 0], [0, 0]]]], np.float32))
+    at = torch.zeros(1, 1, 2, 2, requires_grad=True)
+    torch.nn.functional.max_pool2d(at, 2).sum().backward()
+    assert np.array_equal(at.grad.numpy(), np.array([[[[1, 0], [0, 0]]]], np.float32))
