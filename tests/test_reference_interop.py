@@ -28,7 +28,7 @@ def _load_reference(name):
     """Import /root/reference/src/<name>.py under a private module name, with the reference directory first on sys.path so that its
     own `from dcgan import Generator` / `from utils import check_create_dir` resolve to the reference's files."""
     sys.path.insert(0, REF_SRC)
-    saved = {k: sys.modules.pop(k) for k in ('dcgan', 'utils') if k in sys.modules}
+    saved = {k: sys.modules.pop(k) for k in ('dcgan', 'cgan', 'wggan', 'utils') if k in sys.modules}
     try:
         spec = importlib.util.spec_from_file_location(f'_reference_{name}', os.path.join(REF_SRC, f'{name}.py'))
         mod = importlib.util.module_from_spec(spec)
@@ -36,7 +36,7 @@ def _load_reference(name):
         return mod
     finally:
         sys.path.remove(REF_SRC)
-        for k in ('dcgan', 'utils'):
+        for k in ('dcgan', 'cgan', 'wggan', 'utils'):
             sys.modules.pop(k, None)
         sys.modules.update(saved)
 
@@ -89,3 +89,28 @@ def test_our_modules_load_the_reference_produced_checkpoints():
     with torch.no_grad():
         out = G(torch.from_numpy(z)).numpy()
     np.testing.assert_allclose(out, ref, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF_SRC, 'generate_synthetic_cgan.py')), reason='/root/reference is only present in the build container')
+def test_unmodified_reference_cgan_and_wgan_samplers_load_our_checkpoints(tmp_path):
+    """generate_synthetic_cgan.py / generate_synthetic_wgan.py of the reference (their own Generator classes, strict load_state_dict, eval-mode forward,
+    PNG output) accept the `generator_final.pth` files written by OUR train_cgan.py / train_wggan.py."""
+    from gan_enhanced_pneumonia_classifier_b200 import train_cgan as tc
+    from gan_enhanced_pneumonia_classifier_b200 import train_wggan as tw
+    d = str(tmp_path)
+    common = ['--cpu', '--synthetic', '4', '--batch-size', '2', '--epochs', '1', '--latent-dim', '8', '--feature-maps-g', '2', '--feature-maps-d', '2',
+              '--num-channels', '3', '--vis-batch-size', '2', '--seed', '0']
+
+    def dirs(tag):
+        return ['--model-dir', f'{d}/{tag}/models', '--output-dir', f'{d}/{tag}/results', '--results-dir', f'{d}/{tag}/results/metrics',
+                '--figures-dir', f'{d}/{tag}/results/figures']
+
+    tc.main(tc.build_parser().parse_args(common + dirs('cgan') + ['--no-perceptual']))
+    tw.main(tw.build_parser().parse_args(common + dirs('wgan') + ['--critic-iters', '1']))
+    for name, ckpt, out in (('generate_synthetic_cgan', f'{d}/cgan/models/gan/generator_final.pth', f'{d}/ref_cgan'),
+                            ('generate_synthetic_wgan', f'{d}/wgan/models/wgan/generator_final.pth', f'{d}/ref_wgan')):
+        ref = _load_reference(name)
+        assert ref.__file__.startswith(REF_SRC) and ref.Generator.__init__.__code__.co_filename.startswith(REF_SRC)      # the reference's own classes
+        torch.manual_seed(4)
+        ref.generate_images(ckpt, out, 3, 8, 2, 2, torch.device('cpu'))          # any load error there ends in sys.exit(1)
+        assert sorted(os.listdir(out)) == ['synthetic_00001.png', 'synthetic_00002.png', 'synthetic_00003.png']
