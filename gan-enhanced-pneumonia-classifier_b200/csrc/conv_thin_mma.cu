@@ -30,6 +30,8 @@ struct ThinArgs {
   float slope;
   int fine_vec, ref_vec;               // 4-wide vector loads along W are legal for fine / fine_ref
   int RT;                              // coarse rows per tile of the TMA-staged kernels
+  int cpitch;                          // elements between consecutive coarse pixels: 32 (dense) or the width of the tensor a 32-channel slice is cut
+                                       // from (only the TMA-staged kernels take slices: their tensor map carries the strides)
   // down only: BatchNorm fusions on the 32-channel result (b200gan_fuse): epi 1 = statistics of the result (bn_sums),
   // epi 2 = the result is the gradient w.r.t. act(BN(prev_y)): dz = dx * act'(scale*prev_y + shift), sums of dz and dz*xhat
   int epi;
@@ -287,7 +289,7 @@ __global__ void __launch_bounds__(256) thin_down_mma_kernel(const ThinArgs a) {
 #pragma unroll
           for (int e = 0; e < 4; ++e) acc[j][e] = fmaxf(acc[j][e], 0.f);
       }
-      const int64_t ooff = (((int64_t)n * a.H + oh) * a.W + ow) * 32 + 8 * t;
+      const int64_t ooff = (((int64_t)n * a.H + oh) * a.W + ow) * a.cpitch + 8 * t;
       // lane (g,t) holds channels 8t..8t+7 of pixels ow and ow+8: value index c = 2j+e <-> acc[j][e] (row g), acc[j][2+e] (row g+8)
       float yv[2][8];
       if (EPI == 2) {
@@ -308,7 +310,7 @@ __global__ void __launch_bounds__(256) thin_down_mma_kernel(const ThinArgs a) {
       hi.z = pack_bf16x2(acc[2][2], acc[2][3]); hi.w = pack_bf16x2(acc[3][2], acc[3][3]);
       __nv_bfloat16* o = a.coarse_out + ooff;
       *reinterpret_cast<uint4*>(o) = lo;
-      *reinterpret_cast<uint4*>(o + 8 * 32) = hi;
+      *reinterpret_cast<uint4*>(o + 8 * a.cpitch) = hi;
       if (EPI != 0) {
         // per-thread channel sums over every pixel this thread produces (the thread's eight channels never change);
         // the statistics are those of the stored (bf16-rounded) values
@@ -789,10 +791,17 @@ bool vec16_ok(const b200gan_view* v) {
          (reinterpret_cast<uintptr_t>(v->ptr) & 15) == 0;
 }
 
+// a 32-channel slice of a dense wider NHWC bf16 tensor (pixel pitch a multiple of 8 elements = 16 bytes), or the dense tensor itself
+bool slice_bf16_32(const b200gan_view* v) {
+  return v->dtype == B200GAN_BF16 && v->c == 32 && v->sc == 1 && v->sw >= 32 && v->sw % 8 == 0 && v->sh == (int64_t)v->w * v->sw &&
+         v->sn == (int64_t)v->h * v->w * v->sw && (reinterpret_cast<uintptr_t>(v->ptr) & 15) == 0;
+}
+
 // returns false when the problem is not of the thin shape
 bool thin_setup(ThinArgs* a, const b200gan_view* fine, const b200gan_view* fine_ref, int fine_act, const b200gan_view* coarse,
                 const b200gan_view* coarse_ref, int coarse_act, float slope) {
-  if (!dense_bf16_32(coarse) || (fine->c != 1 && fine->c != 3)) return false;
+  if (!slice_bf16_32(coarse) || (fine->c != 1 && fine->c != 3)) return false;
+  if (coarse->sw != 32 && coarse_ref) return false;
   if (coarse->w % 16 != 0 || coarse->w > 128 || fine->h != 2 * coarse->h || fine->w != 2 * coarse->w || fine->n != coarse->n) return false;
   if (coarse_ref && (!dense_bf16_32(coarse_ref) || coarse_ref->n != coarse->n || coarse_ref->h != coarse->h || coarse_ref->w != coarse->w)) return false;
   if (fine_ref && (fine_ref->n != fine->n || fine_ref->h != fine->h || fine_ref->w != fine->w || fine_ref->c != fine->c)) return false;
@@ -802,6 +811,7 @@ bool thin_setup(ThinArgs* a, const b200gan_view* fine, const b200gan_view* fine_
   a->coarse_out = reinterpret_cast<__nv_bfloat16*>(coarse->ptr);
   a->coarse_ref = coarse_ref ? reinterpret_cast<const __nv_bfloat16*>(coarse_ref->ptr) : nullptr;
   a->N = coarse->n; a->H = coarse->h; a->W = coarse->w;
+  a->cpitch = (int)coarse->sw;
   a->R = coarse->h < 8 ? coarse->h : 8;
   a->tiles_per_img = (a->H + a->R - 1) / a->R;
   a->num_tiles = a->N * a->tiles_per_img;
@@ -811,12 +821,14 @@ bool thin_setup(ThinArgs* a, const b200gan_view* fine, const b200gan_view* fine_
   return true;
 }
 
-// 4-d tensor map over the dense (N,H,W,32) bf16 coarse tensor: box {32 ch, box_w, box_h, 1}, 64B swizzle, zero OOB fill
+// 4-d tensor map over the (N,H,W,32) bf16 coarse tensor (dense, or a channel slice: pixel pitch a.cpitch): box {32 ch, box_w, box_h, 1}, 64B swizzle,
+// zero OOB fill
 int coarse_tensor_map(CUtensorMap* m, const ThinArgs& a, int box_w, int box_h) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return B200GAN_ERR_CUDA; }
   cuuint64_t gdim[4] = {32, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.N};
-  cuuint64_t gstr[3] = {64, (cuuint64_t)a.W * 64, (cuuint64_t)a.H * a.W * 64};
+  const cuuint64_t pix = (cuuint64_t)a.cpitch * 2;              // bytes between pixels
+  cuuint64_t gstr[3] = {pix, (cuuint64_t)a.W * pix, (cuuint64_t)a.H * a.W * pix};
   cuuint32_t box[4] = {32, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(a.coarse), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -860,6 +872,7 @@ int thin_down(const b200gan_view* fine, const b200gan_view* fine_ref, int fine_a
   if (epi.mode == 2 && (!dense_bf16_32(epi.prev_y) || epi.prev_y->n != coarse->n || epi.prev_y->h != coarse->h || epi.prev_y->w != coarse->w)) return 1;
   if (out_act != B200GAN_ACT_NONE && out_act != B200GAN_ACT_LRELU && out_act != B200GAN_ACT_RELU) return 1;
   if (!thin_setup(&a, fine, fine_ref, fine_act, coarse, nullptr, B200GAN_ACT_NONE, slope)) return 1;
+  if (a.cpitch != 32 && epi.mode != 0) return 1;                // a 32-channel slice as the result: plain / activation epilogue only
   a.w = w; a.out_act = out_act;
   a.epi = epi.mode;
   if (epi.mode != 0) {
@@ -904,6 +917,7 @@ int thin_up(const b200gan_view* coarse, const b200gan_view* coarse_ref, int coar
     if (fine->c == 1) return launch_thin_tma<thin_up_tma_kernel<1>>(m, a, smem_tma, 2, st, "thin_up_tma_kernel");
     return launch_thin_tma<thin_up_tma_kernel<3>>(m, a, smem_tma, 2, st, "thin_up_tma_kernel");
   }
+  if (a.cpitch != 32) return 1;                                 // the cp.async-staged kernel indexes the coarse tensor densely
   const size_t smem = (size_t)18 * NT * 32 * 8 + (size_t)(a.R + 2) * (a.W + 2) * CP * 2;
   if (fine->c == 1) return launch_thin<thin_up_mma_kernel<1>>(a, smem, 2, st, "thin_up_mma_kernel");
   return launch_thin<thin_up_mma_kernel<3>>(a, smem, 2, st, "thin_up_mma_kernel");
@@ -938,6 +952,7 @@ int thin_wgrad(const b200gan_view* fine, const b200gan_view* fine_ref, int fine_
     return fine_ref ? WG(3, __nv_bfloat16, true) : WG(3, __nv_bfloat16, false);
 #undef WG
   }
+  if (a.cpitch != 32) return 1;
   const size_t smem = (size_t)512 * fine->c * 4 + (size_t)a.R * a.W * CP * 2 + (size_t)fine->c * (2 * a.R + 2) * (2 * a.W + 2) * 2;
   if (fine->c == 1) return launch_thin<thin_wgrad_mma_kernel<1>>(a, smem, 2, st, "thin_wgrad_mma_kernel");
   return launch_thin<thin_wgrad_mma_kernel<3>>(a, smem, 2, st, "thin_wgrad_mma_kernel");

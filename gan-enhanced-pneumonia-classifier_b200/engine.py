@@ -182,19 +182,63 @@ class NetEngine:
         self.launches += 1
         return both[:n], both[n:]
 
+    # -- 64-channel image-side layers (the WGAN-GP critic's Conv2d(nc -> 64) and generator's ConvTranspose2d(64 -> nc)) ---------------
+    # The warp-MMA kernels of the image-side layers are built for a 32-channel feature side.  A 64-channel one is served as two 32-channel
+    # SLICES of the same tensor (the TMA-staged kernels take the slice's strides in their tensor map): the "up" direction sums two fp32 partial
+    # images before the activation, the weight gradient writes the two halves of dw directly.  Measured at batch 512: 3.2 ms -> 0.4 ms ("up"),
+    # 1.15 ms -> 0.3 ms (weight gradient) against the fp32-FMA kernels of conv_edge.cu, which remain the path for fused gradient masks.
+    def _split64(self, coarse: Act, fine: Act, fuse_has_coarse_ref: bool) -> bool:
+        sp_ok = self.dtype == torch.bfloat16 and self.algo != L.ALGO_SIMT
+        return (sp_ok and coarse.v.c == 64 and fine.v.c in (1, 3) and not fuse_has_coarse_ref and not coarse.nchw and coarse.t.dtype == torch.bfloat16
+                and coarse.t.is_contiguous() and coarse.v.w % 16 == 0 and coarse.v.w <= 112 and fine.v.h == 2 * coarse.v.h)
+
+    def _up64(self, name, i, coarse: Act, w, fine: Act, st, out_act):
+        """fine = out_act(up(coarse[..., :32], w[:32]) + up(coarse[..., 32:], w[32:]))."""
+        parts = []
+        for h in range(2):
+            t = Act(torch.empty((fine.v.n, fine.v.h, fine.v.w, fine.v.c), device=coarse.t.device, dtype=torch.float32), nchw=False)
+            cs, ws = Act(coarse.t[..., 32 * h:32 * h + 32], nchw=False), w[32 * h:32 * h + 32]
+            L.call(name, C.byref(self._conv[i]), C.byref(cs.v), L.ptr(ws), None, C.byref(t.v), None, st)
+            parts.append(t)
+        L.call('b200gan_sample_axpby', C.byref(parts[0].v), None, C.byref(parts[1].v), None, C.byref(parts[0].v), st)
+        L.call('b200gan_bn_act_fwd', C.byref(parts[0].v), None, None, out_act, LRELU_SLOPE, C.byref(fine.v), st)
+        self.launches += 4
+
     def _fprop(self, i, x: Act, w, y: Act, st, wp_down=None, wp_up=None, fuse=None):
         # ConvTranspose2d forward is the 'up' geometry, Conv2d forward the 'down' geometry
         name, wp = ('b200gan_convT2d_fprop', wp_up) if self.transposed else ('b200gan_conv2d_fprop', wp_down)
+        if self.transposed and (fuse is None or not fuse.bn_sums) and self._conv[i].k == 4 and self._split64(x, y, False):
+            return self._up64(name, i, x, w, y, st, fuse.out_act if fuse is not None else L.ACT_NONE)
+        if not self.transposed and (fuse is None or not fuse.bn_sums) and self._conv[i].k == 4 and self._split64(y, x, False):
+            for h in range(2):                       # "down" into the two 32-channel halves of the result (activation epilogue included)
+                ys = Act(y.t[..., 32 * h:32 * h + 32], nchw=False)
+                L.call(name, C.byref(self._conv[i]), C.byref(x.v), L.ptr(w[32 * h:32 * h + 32]), None, C.byref(ys.v), C.byref(fuse) if fuse is not None else None, st)
+            self.launches += 2
+            return
         L.call(name, C.byref(self._conv[i]), C.byref(x.v), L.ptr(w), L.ptr(wp), C.byref(y.v), C.byref(fuse) if fuse is not None else None, st)
         self.launches += 1
 
     def _dgrad(self, i, dy: Act, w, dx: Act, st, wp_down=None, wp_up=None, fuse=None):
         name, wp = ('b200gan_convT2d_dgrad', wp_down) if self.transposed else ('b200gan_conv2d_dgrad', wp_up)
+        if not self.transposed and fuse is None and self._conv[i].k == 4 and self._split64(dy, dx, False):
+            return self._up64(name, i, dy, w, dx, st, L.ACT_NONE)
         L.call(name, C.byref(self._conv[i]), C.byref(dy.v), L.ptr(w), L.ptr(wp), C.byref(dx.v), C.byref(fuse) if fuse is not None else None, st)
         self.launches += 1
 
     def _wgrad(self, i, x: Act, dy: Act, dw, st, fuse=None):
         name = 'b200gan_convT2d_wgrad' if self.transposed else 'b200gan_conv2d_wgrad'
+        coarse, fine = (x, dy) if self.transposed else (dy, x)
+        # a fused activation backward on the COARSE gradient (the critic's first layer) keeps the one-call path; on the fine side (tanh of the
+        # generator's last layer) it rides along with the slices
+        coarse_ref = fuse is not None and bool(fuse.dy_ref) and not self.transposed
+        if self._conv[i].k == 4 and self._split64(coarse, fine, coarse_ref):
+            for h in range(2):
+                cs = Act(coarse.t[..., 32 * h:32 * h + 32], nchw=False)
+                xa, da = (cs, dy) if self.transposed else (x, cs)
+                L.call(name, C.byref(self._conv[i]), C.byref(xa.v), C.byref(da.v), L.ptr(dw[32 * h:32 * h + 32]), None,
+                       C.byref(fuse) if fuse is not None else None, st)
+            self.launches += 2
+            return
         ws = None
         need = int(L.load().b200gan_conv_wgrad_workspace_floats(C.byref(self._conv[i]), C.byref(x.v), C.byref(dy.v), 1 if self.transposed else 0))
         if need > 0:
