@@ -180,6 +180,117 @@ __global__ void mean_f32_kernel(const float* __restrict__ x, int64_t n, float sc
   if (threadIdx.x == 0) out[0] = (float)(part[0] * (double)scale);
 }
 
+
+// ---- dense bf16 fast paths: every operand a dense NHWC bf16 tensor of one shape, C a power of two in [8, 1024].  A thread owns ONE group of eight
+//      consecutive channels for its whole life (the grid stride is a multiple of C / 8 vectors), so the per-channel coefficients / partial sums live in
+//      registers and every access is 16 bytes.  Same arithmetic as the generic kernels above.
+__device__ __forceinline__ void unpack8v(const uint4& v, float* f) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { const float2 t = __bfloat1622float2(h[k]); f[2 * k] = t.x; f[2 * k + 1] = t.y; }
+}
+__device__ __forceinline__ uint4 pack8v(const float* f) {
+  uint4 v;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) h[k] = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
+  return v;
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_bwd_reduce_dense_kernel(const uint4* __restrict__ r, const uint4* __restrict__ y, const uint4* __restrict__ dz,
+                                                                     const float* __restrict__ mean, const float* __restrict__ invstd, double* __restrict__ sums,
+                                                                     int C, int64_t vecs) {
+  extern __shared__ float acc[];                 // [3][C]
+  for (int i = threadIdx.x; i < 3 * C; i += 256) acc[i] = 0.f;
+  __syncthreads();
+  const int64_t first = blockIdx.x * 256ll + threadIdx.x;
+  const int c0 = (int)(first % (C / 8)) * 8;
+  float mu[8], is[8], s0[8], s1[8], s2[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { mu[k] = mean[c0 + k]; is[k] = invstd[c0 + k]; s0[k] = s1[k] = s2[k] = 0.f; }
+  for (int64_t i = first; i < vecs; i += (int64_t)gridDim.x * 256) {
+    float rv[8], yv[8], dv[8];
+    unpack8v(r[i], rv); unpack8v(y[i], yv); unpack8v(dz[i], dv);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { s0[k] += rv[k]; s1[k] = fmaf(rv[k], (yv[k] - mu[k]) * is[k], s1[k]); s2[k] = fmaf(rv[k], dv[k], s2[k]); }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { atomicAdd(&acc[c0 + k], s0[k]); atomicAdd(&acc[C + c0 + k], s1[k]); atomicAdd(&acc[2 * C + c0 + k], s2[k]); }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 3 * C; i += 256)
+    if (acc[i] != 0.f) atomicAdd(sums + i, (double)acc[i]);
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_bwd_apply_dense_kernel(const uint4* __restrict__ r, const uint4* __restrict__ y, const uint4* __restrict__ dz,
+                                                                    const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
+                                                                    const float* __restrict__ invstd, const float* __restrict__ gamma, const double* __restrict__ dzs,
+                                                                    const double* __restrict__ sums, double count, int act, float slope, uint4* __restrict__ u,
+                                                                    uint4* __restrict__ inj, float* __restrict__ dgamma, int C, int64_t vecs) {
+  const int64_t first = blockIdx.x * 256ll + threadIdx.x;
+  const int c0 = (int)(first % (C / 8)) * 8;
+  float mr[8], mrx[8], mrp[8], m1[8], m2[8], gs[8], is[8], mu[8], sc[8], sh[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int c = c0 + k;
+    const double sr = sums[c], srx = sums[C + c], srd = sums[2 * C + c];
+    const double a1 = dzs[c] / count, a2 = dzs[C + c] / count;
+    const double srp = srd - a1 * sr - a2 * srx;             // sum r P(dz)
+    mr[k] = (float)(sr / count); mrx[k] = (float)(srx / count); mrp[k] = (float)(srp / count);
+    m1[k] = (float)a1; m2[k] = (float)a2;
+    gs[k] = gamma[c] * invstd[c]; is[k] = invstd[c]; mu[k] = mean[c]; sc[k] = scale[c]; sh[k] = shift[c];
+    if (first < C / 8 && dgamma) dgamma[c] += (float)((double)invstd[c] * srp);         // the first C/8 threads of the grid: one per channel group
+  }
+  for (int64_t i = first; i < vecs; i += (int64_t)gridDim.x * 256) {
+    float rv[8], yv[8], dv[8], uo[8], io[8];
+    unpack8v(r[i], rv); unpack8v(y[i], yv); unpack8v(dz[i], dv);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float xh = (yv[k] - mu[k]) * is[k];
+      const float pr = rv[k] - mr[k] - xh * mrx[k];
+      const float pdz = dv[k] - m1[k] - xh * m2[k];
+      const float z = fmaf(yv[k], sc[k], sh[k]);
+      const float d = act == B200GAN_ACT_RELU ? (z > 0.f ? 1.f : 0.f) : (act == B200GAN_ACT_LRELU ? (z > 0.f ? 1.f : slope) : 1.f);
+      uo[k] = gs[k] * pr * d;
+      io[k] = -(gs[k] * is[k]) * (xh * mrp[k] + m2[k] * pr + mrx[k] * pdz);
+    }
+    u[i] = pack8v(uo);
+    inj[i] = pack8v(io);
+  }
+}
+
+// out = a[n] x + b[n] y, dense tensors of one dtype (T = float: 4 per access, bf16: 8), `per` accesses per sample
+template <typename T>
+__global__ void __launch_bounds__(256) sample_axpby_dense_kernel(const uint4* __restrict__ x, const float* __restrict__ a, const uint4* __restrict__ y,
+                                                                const float* __restrict__ b, uint4* __restrict__ out, int64_t vecs, int64_t per) {
+  constexpr int V = sizeof(T) == 4 ? 4 : 8;
+  for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < vecs; i += (int64_t)gridDim.x * 256) {
+    const int n = (int)(i / per);
+    const float an = a ? a[n] : 1.f, bn = b ? b[n] : 1.f;
+    float xv[V], yv[V];
+    const uint4 xr = x[i];
+    if (sizeof(T) == 4) { const float* p = reinterpret_cast<const float*>(&xr); for (int k = 0; k < V; ++k) xv[k] = p[k]; }
+    else unpack8v(xr, xv);
+    if (y) {
+      const uint4 yr = y[i];
+      if (sizeof(T) == 4) { const float* p = reinterpret_cast<const float*>(&yr); for (int k = 0; k < V; ++k) yv[k] = p[k]; }
+      else unpack8v(yr, yv);
+#pragma unroll
+      for (int k = 0; k < V; ++k) xv[k] = fmaf(bn, yv[k], an * xv[k]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < V; ++k) xv[k] *= an;
+    }
+    uint4 o;
+    if (sizeof(T) == 4) { float* p = reinterpret_cast<float*>(&o); for (int k = 0; k < V; ++k) p[k] = xv[k]; }
+    else o = pack8v(xv);
+    out[i] = o;
+  }
+}
+
+bool dense_view(const b200gan_view* v) {
+  return v->sc == 1 && v->sw == v->c && v->sh == (int64_t)v->w * v->c && v->sn == (int64_t)v->h * v->w * v->c && (reinterpret_cast<uintptr_t>(v->ptr) & 15) == 0;
+}
+
 bool same_extent(const b200gan_view* a, const b200gan_view* b) { return a->n == b->n && a->h == b->h && a->w == b->w && a->c == b->c; }
 
 }  // namespace
@@ -191,6 +302,21 @@ int gp_bn_bwd_bwd(const b200gan_view* r, const b200gan_view* y, const b200gan_vi
   const int C = r->c;
   B200_CHECK_ARG(C <= 1024 && (256 % C == 0 || C % 256 == 0), "bn_bwd_bwd: channel count must divide 256 or be a multiple of it, at most 1024 (got %d)", C);
   B200_CUDA(cudaMemsetAsync(sums3, 0, sizeof(double) * 3 * C, st));
+  const b200gan_view* all[5] = {r, y, dz, u, inj};
+  bool fast = C >= 8 && (C & (C - 1)) == 0;
+  for (const b200gan_view* v : all) fast = fast && v->dtype == B200GAN_BF16 && dense_view(v);
+  if (fast) {
+    const int64_t vecs = (int64_t)r->n * r->h * r->w * C / 8;
+    int64_t blocks = (vecs + 255) / 256;
+    if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;              // any grid keeps a thread on one channel group: 256 % (C / 8) == 0
+    bn_bwd_bwd_reduce_dense_kernel<<<(unsigned)blocks, 256, 3 * C * sizeof(float), st>>>((const uint4*)r->ptr, (const uint4*)y->ptr, (const uint4*)dz->ptr, mean, invstd,
+                                                                                        sums3, C, vecs);
+    B200_LAUNCH_CHECK("bn_bwd_bwd_reduce_dense_kernel");
+    bn_bwd_bwd_apply_dense_kernel<<<(unsigned)blocks, 256, 0, st>>>((const uint4*)r->ptr, (const uint4*)y->ptr, (const uint4*)dz->ptr, scale, shift, mean, invstd, gamma,
+                                                                   dz_sums, sums3, (double)count, act, slope, (uint4*)u->ptr, (uint4*)inj->ptr, dgamma, C, vecs);
+    B200_LAUNCH_CHECK("bn_bwd_bwd_apply_dense_kernel");
+    return 0;
+  }
   const int nrows = r->n * r->h;
   int rows_per_cta = (nrows + 8 * kNumSMs - 1) / (8 * kNumSMs);
   if (rows_per_cta < 1) rows_per_cta = 1;
@@ -222,6 +348,23 @@ int gp_from_norms(const double* sumsq, int n, float lambda, float* gp, float* co
 
 int gp_sample_axpby(const b200gan_view* x, const float* a, const b200gan_view* y, const float* b, const b200gan_view* out, cudaStream_t st) {
   B200_CHECK_ARG(same_extent(x, out) && (!y || same_extent(x, y)), "sample_axpby: views differ in extent");
+  {
+    const int per_vec = x->dtype == B200GAN_F32 ? 4 : 8;
+    const int64_t per = (int64_t)x->h * x->w * x->c;
+    bool fast = per % per_vec == 0 && dense_view(x) && dense_view(out) && out->dtype == x->dtype && (!y || (dense_view(y) && y->dtype == x->dtype));
+    if (fast) {
+      const int64_t vecs = (int64_t)x->n * per / per_vec;
+      int64_t blocks = (vecs + 255) / 256;
+      if (blocks > 16 * kNumSMs) blocks = 16 * kNumSMs;
+      if (x->dtype == B200GAN_F32)
+        sample_axpby_dense_kernel<float><<<(unsigned)blocks, 256, 0, st>>>((const uint4*)x->ptr, a, y ? (const uint4*)y->ptr : nullptr, b, (uint4*)out->ptr, vecs, per / per_vec);
+      else
+        sample_axpby_dense_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>((const uint4*)x->ptr, a, y ? (const uint4*)y->ptr : nullptr, b, (uint4*)out->ptr, vecs,
+                                                                                  per / per_vec);
+      B200_LAUNCH_CHECK("sample_axpby_dense_kernel");
+      return 0;
+    }
+  }
   const int nrows = x->n * x->h;
   int rows_per_cta = (nrows + 16 * kNumSMs - 1) / (16 * kNumSMs);
   if (rows_per_cta < 1) rows_per_cta = 1;
