@@ -491,7 +491,23 @@ def run_ours(args):
     # on one batch of real images; images/s counts the real images consumed.  Kernel by kernel (no CUDA graph yet), local BatchNorm statistics.
     wgan = None
     log('wgan-gp configuration')
-    if nc == 1 and not args.no_wgan and not strong and world == 1:
+    extras = world == 1 or args.extras_dp        # the two widened configurations: on one GPU by default, data parallel with --extras-dp
+
+    def timed_ms(fn, k):
+        """k calls of fn between two events, barriers on both sides, max over ranks."""
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            out = fn()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1) / k], device='cuda', dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item(), out
+
+    if nc == 1 and not args.no_wgan and not strong and extras:
         for name in ('tr3', 'tr'):
             if name in locals() and locals()[name] is not None:
                 locals()[name].close()
@@ -506,17 +522,12 @@ def run_ours(args):
         wtr.step(wreal)
         torch.cuda.synchronize()
         kw = 3
-        w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         wl0 = wtr.launches
-        w0.record()
-        for _ in range(kw):
-            wout = wtr.step(wreal)
-        w1.record()
-        torch.cuda.synchronize()
-        wms = w0.elapsed_time(w1) / kw
+        wms, wout = timed_ms(lambda: wtr.step(wreal), kw)
         wgan = {'model': 'WGAN-GP (wggan.py, train_wggan.py:66-93): 5 critic updates with gradient penalty (double backward) + 1 generator update per iteration',
-                'nc': 1, 'per_gpu_batch': B, 'value': B / (wms * 1e-3), 'unit': 'real images/s', 'ms_per_iteration': wms, 'steps': kw,
+                'nc': 1, 'per_gpu_batch': B, 'n_gpus': world, 'value': B * world / (wms * 1e-3), 'unit': 'real images/s', 'ms_per_iteration': wms, 'steps': kw,
                 'gpu_launches_per_iteration': (wtr.launches - wl0) // kw, 'last_losses': [float(v) for v in wout.tolist()]}
+        wtr.close()
         del wtr, wG, wD
         torch.cuda.empty_cache()
 
@@ -525,7 +536,7 @@ def run_ours(args):
     # and with the VGG16 perceptual term (random VGG16 weights).  Kernel by kernel, unfused bias / BatchNorm passes, no CUDA graph.
     cg = None
     log('cgan configuration')
-    if nc == 1 and not args.no_cgan and not strong and world == 1:
+    if nc == 1 and not args.no_cgan and not strong and extras:
         from gan_enhanced_pneumonia_classifier_b200 import cgan as cgan_mod
         from gan_enhanced_pneumonia_classifier_b200.cgan_trainer import CGANTrainer
         torch.manual_seed(0)
@@ -537,18 +548,13 @@ def run_ours(args):
         ctr.step(creal, clab)
         torch.cuda.synchronize()
         kc = 5
-        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        c0.record()
-        for _ in range(kc):
-            cout = ctr.step(creal, clab)
-        c1.record()
-        torch.cuda.synchronize()
-        cms = c0.elapsed_time(c1) / kc
+        cms, cout = timed_ms(lambda: ctr.step(creal, clab), kc)
         cg = {'model': 'CGAN (cgan.py, train_cgan.py:150-193): feature_maps 32, projection discriminator; generator loss = adversarial + '
                        '5 x feature matching (`value`: --no-perceptual) and + 10 x VGG16 perceptual (`with_perceptual`: the full loss of train_cgan.py:191, '
                        'VGG16 on RANDOM weights -- the ImageNet checkpoint cannot be obtained offline; the arithmetic does not depend on the values)',
-              'nc': 3, 'per_gpu_batch': cB, 'value': cB / (cms * 1e-3), 'unit': UNIT, 'ms_per_iteration': cms, 'steps': kc,
+              'nc': 3, 'per_gpu_batch': cB, 'n_gpus': world, 'value': cB * world / (cms * 1e-3), 'unit': UNIT, 'ms_per_iteration': cms, 'steps': kc,
               'last_history': [float(v) for v in cout.tolist()]}
+        ctr.close()
         del ctr
         torch.cuda.empty_cache()
         from gan_enhanced_pneumonia_classifier_b200.perceptual import PerceptualLoss
@@ -556,13 +562,9 @@ def run_ours(args):
         ctr = CGANTrainer(cG, cD, perceptual=vgg, perceptual_weight=10.0, dtype=dtype)
         ctr.step(creal, clab)
         torch.cuda.synchronize()
-        c0.record()
-        for _ in range(kc):
-            cout = ctr.step(creal, clab)
-        c1.record()
-        torch.cuda.synchronize()
-        pms = c0.elapsed_time(c1) / kc
-        cg['with_perceptual'] = {'value': cB / (pms * 1e-3), 'unit': UNIT, 'ms_per_iteration': pms, 'steps': kc, 'last_history': [float(v) for v in cout.tolist()]}
+        pms, cout = timed_ms(lambda: ctr.step(creal, clab), kc)
+        cg['with_perceptual'] = {'value': cB * world / (pms * 1e-3), 'unit': UNIT, 'ms_per_iteration': pms, 'steps': kc, 'last_history': [float(v) for v in cout.tolist()]}
+        ctr.close()
         del ctr, cG, cD, vgg
         torch.cuda.empty_cache()
     log('roofline kernels, cpu baseline')
@@ -631,6 +633,7 @@ def main():
     ap.add_argument('--no-rgb', action='store_true', help='skip the additional nc=3 measurement (more_configs)')
     ap.add_argument('--no-wgan', action='store_true', help='skip the additional WGAN-GP measurement (more_configs, 1 GPU only)')
     ap.add_argument('--sync-bn', action='store_true', help='N>1: synchronised BatchNorm statistics (default: local to each rank)')
+    ap.add_argument('--extras-dp', action='store_true', help='N>1: also run the WGAN-GP and CGAN measurements (more_configs) data parallel; default: one GPU only')
     ap.add_argument('--no-cgan', action='store_true', help='skip the additional CGAN measurement (more_configs, 1 GPU only)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
