@@ -207,6 +207,9 @@ __device__ __forceinline__ void stage_coarse(__nv_bfloat16* S, int rows, int col
 // MMA column n = 8j + g of n-tile j is mapped to channel 8*(g>>1) + 2j + (g&1), so that lane (g,t) ends up with the
 // eight consecutive channels 8t..8t+7 of its pixel: one 16-byte store per pixel row, fully coalesced across the warp.
 // ---------------------------------------------------------------------------------------------------
+// (Measured, round 2: at NC = 3 this kernel holds 106-123 registers = two resident CTAs per SM and reaches 0.30-0.42 of the copy bandwidth.  Capping it at
+//  80 registers for three CTAs made it SLOWER (259 -> 307 us): ncu puts the issue slots at 57 % busy with 24 % of the warp slots filled -- the staging loop's
+//  per-element index arithmetic and its three odd-aligned shared-memory stores per four pixels are what it spends its time on, not latency.)
 template <int NC, int EPI>
 __global__ void __launch_bounds__(256) thin_down_mma_kernel(const ThinArgs a) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -932,7 +935,9 @@ int thin_wgrad(const b200gan_view* fine, const b200gan_view* fine_ref, int fine_
   // raw cp.async staging of the image band: unit W stride, 16-byte aligned rows, reference (if any) of the same dtype
   const bool band_ok = a.fine_vec && vec16_ok(fine) && (!fine_ref || (fine_ref->dtype == fine->dtype && vec16_ok(fine_ref)));
   if (thin_tma_ok(a) && band_ok) {
-    a.RT = 4;
+    // rows of the coarse tensor per tile: the raw image band beside it is 3x as large at nc = 3 (6x in fp32), and at 4 rows one stage pair took
+    // 113-170 KB = ONE resident CTA per SM (ncu: 12 % of the warp slots, 0.19 of the copy bandwidth); 2 rows keep two CTAs resident
+    a.RT = fine->c == 3 ? 2 : 4;
     a.tiles_per_img = (a.H + a.RT - 1) / a.RT;
     a.num_tiles = a.N * a.tiles_per_img;
     CUtensorMap m;
