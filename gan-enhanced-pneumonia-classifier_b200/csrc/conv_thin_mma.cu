@@ -94,12 +94,131 @@ __device__ __forceinline__ void load4_rt(const View& v, int64_t off, int vec, fl
   }
 }
 
+// ---- row-per-warp staging (same shared-memory layout as stage_fine below) --------------------------------------------------------------------------
+// ncu on the per-element loop of stage_fine (round 2, nc = 3): 154 M warp instructions per launch of the first Discriminator layer, ~2/3 of them the
+// staging loop's index arithmetic (two divisions per four pixels) and its three odd-aligned 2+4+2-byte shared-memory stores; issue slots 57 % busy at 24 %
+// occupancy.  Here a warp owns a whole image row: a lane loads EIGHT consecutive pixels with 16-byte accesses, packs them to bf16 pairs, takes its left
+// neighbour's last pixel by one shuffle (the layout puts pixel iw at element iw+1, so the aligned 4-byte words hold the pairs (iw odd, iw+1)) and writes
+// four aligned words.  No division per element, one shuffle and four 4-byte stores per eight pixels.  Two layouts qualify: channel-planar rows with unit
+// W stride (the reference's NCHW tensors, f32 or bf16; any tensor at nc = 1) and the dense interleaved 3-channel bf16 image the fused trainer keeps
+// between the networks; a reference tensor for the fused activation backward must have the same layout.  IW % 8 == 0, IW <= 256.
+__device__ __forceinline__ void row_words_store(uint32_t* Srow32, int lane, int groups, uint32_t q0, uint32_t q1, uint32_t q2, uint32_t q3) {
+  // q_i = bf16 pair (pixel 2i low, pixel 2i+1 high) of this lane's eight pixels; lanes >= groups hold zeros
+  uint32_t prev = __shfl_up_sync(0xffffffffu, q3, 1);
+  if (lane == 0) prev = 0u;                                        // iw = -1: the left zero padding
+  if (lane < groups) {
+    uint32_t* d = Srow32 + 4 * lane;
+    d[0] = __funnelshift_l(prev, q0, 16);                          // (iw = 8 lane - 1, 8 lane)
+    d[1] = __funnelshift_l(q0, q1, 16);
+    d[2] = __funnelshift_l(q1, q2, 16);
+    d[3] = __funnelshift_l(q2, q3, 16);
+    if (lane == groups - 1) d[4] = q3 >> 16;                       // (iw = IW - 1, the right zero padding)
+  }
+}
+
+__device__ __forceinline__ void load8_planar(const View& v, int64_t off, float (&o)[8]) {       // eight pixels consecutive along W, unit stride
+  if (v.dtype == B200GAN_F32) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(v.ptr) + off));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(v.ptr) + off + 4));
+    o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+  } else {
+    const uint4 t = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(v.ptr) + off));
+    o[0] = __uint_as_float(t.x << 16); o[1] = __uint_as_float(t.x & 0xffff0000u); o[2] = __uint_as_float(t.y << 16); o[3] = __uint_as_float(t.y & 0xffff0000u);
+    o[4] = __uint_as_float(t.z << 16); o[5] = __uint_as_float(t.z & 0xffff0000u); o[6] = __uint_as_float(t.w << 16); o[7] = __uint_as_float(t.w & 0xffff0000u);
+  }
+}
+
+__device__ __forceinline__ bool rows_planar_ok(const View& v, int IW) {
+  const int per = v.dtype == B200GAN_F32 ? 4 : 8;                  // elements per 16 bytes
+  return v.sw == 1 && v.sn % per == 0 && v.sh % per == 0 && (v.c == 1 || v.sc % per == 0) &&
+         (reinterpret_cast<uintptr_t>(v.ptr) & 15) == 0 && IW % 8 == 0 && IW <= 256;
+}
+__device__ __forceinline__ bool rows_rgb_ok(const View& v, int IW) {                           // dense interleaved (N,H,W,3) bf16
+  return v.dtype == B200GAN_BF16 && v.c == 3 && v.sc == 1 && v.sw == 3 && v.sh == (int64_t)3 * v.w && v.sn == (int64_t)3 * v.w * v.h &&
+         (reinterpret_cast<uintptr_t>(v.ptr) & 15) == 0 && IW % 8 == 0 && IW <= 256;
+}
+
+// channel c of eight interleaved RGB pixels held as twelve 32-bit words (24 bf16): the four pixel pairs
+template <int CH>
+__device__ __forceinline__ void rgb_pairs(const uint32_t (&w)[12], uint32_t (&q)[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int ka = 3 * (2 * i) + CH, kb = ka + 3;                  // element indices of pixels 2i and 2i+1
+    const uint32_t sel = ((ka & 1) ? 0x32u : 0x10u) | (((kb & 1) ? 0x76u : 0x54u) << 8);
+    q[i] = __byte_perm(w[ka >> 1], w[kb >> 1], sel);
+  }
+}
+
+template <int NC>
+__device__ __forceinline__ bool stage_fine_rows(__nv_bfloat16* S, int pitch, int rows, const ThinArgs& a, int n, int ih0) {
+  const int IH = 2 * a.H, IW = 2 * a.W, groups = IW >> 3;
+  const bool has_ref = a.fine_ref.ptr != nullptr;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  uint32_t* S32 = reinterpret_cast<uint32_t*>(S);
+  if (rows_planar_ok(a.fine, IW) && (!has_ref || rows_planar_ok(a.fine_ref, IW))) {
+    // (one row per trip: issuing two rows' loads before converting either was measured -- it pushes these kernels past 128 registers, one resident CTA
+    //  per SM, and every consumer of this routine lost 25-60 %)
+    for (int r = warp; r < NC * rows; r += nwarps) {
+      const int ci = r / rows, row = r - ci * rows, ih = ih0 + row;
+      uint32_t q[4] = {0u, 0u, 0u, 0u};
+      if (lane < groups && (unsigned)ih < (unsigned)IH) {
+        float v[8];
+        load8_planar(a.fine, (int64_t)n * a.fine.sn + (int64_t)ih * a.fine.sh + (int64_t)ci * a.fine.sc + 8 * lane, v);
+        if (has_ref) {
+          float rf[8];
+          load8_planar(a.fine_ref, (int64_t)n * a.fine_ref.sn + (int64_t)ih * a.fine_ref.sh + (int64_t)ci * a.fine_ref.sc + 8 * lane, rf);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] *= act_grad_from_output(rf[e], a.fine_act, a.slope);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) q[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+      }
+      row_words_store(S32 + ((ci * rows + row) * pitch >> 1), lane, groups, q[0], q[1], q[2], q[3]);
+    }
+    return true;
+  }
+  if (NC == 3 && rows_rgb_ok(a.fine, IW) && (!has_ref || rows_rgb_ok(a.fine_ref, IW))) {
+    for (int row = warp; row < rows; row += nwarps) {
+      const int ih = ih0 + row;
+      uint32_t w[12];
+#pragma unroll
+      for (int k = 0; k < 12; ++k) w[k] = 0u;
+      if (lane < groups && (unsigned)ih < (unsigned)IH) {
+        const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(a.fine.ptr) + (int64_t)n * a.fine.sn + (int64_t)ih * a.fine.sh + 24 * lane);
+        const uint4 t0 = __ldg(src), t1 = __ldg(src + 1), t2 = __ldg(src + 2);
+        w[0] = t0.x; w[1] = t0.y; w[2] = t0.z; w[3] = t0.w; w[4] = t1.x; w[5] = t1.y; w[6] = t1.z; w[7] = t1.w; w[8] = t2.x; w[9] = t2.y; w[10] = t2.z; w[11] = t2.w;
+        if (has_ref) {
+          const uint4* rs = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(a.fine_ref.ptr) + (int64_t)n * a.fine_ref.sn + (int64_t)ih * a.fine_ref.sh + 24 * lane);
+          const uint4 r0 = __ldg(rs), r1 = __ldg(rs + 1), r2 = __ldg(rs + 2);
+          const uint32_t rw[12] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w};
+#pragma unroll
+          for (int k = 0; k < 12; ++k) {
+            const float lo = __uint_as_float(w[k] << 16) * act_grad_from_output(__uint_as_float(rw[k] << 16), a.fine_act, a.slope);
+            const float hi = __uint_as_float(w[k] & 0xffff0000u) * act_grad_from_output(__uint_as_float(rw[k] & 0xffff0000u), a.fine_act, a.slope);
+            w[k] = pack_bf16x2(lo, hi);
+          }
+        }
+      }
+      uint32_t q[4];
+      rgb_pairs<0>(w, q);
+      row_words_store(S32 + ((0 * rows + row) * pitch >> 1), lane, groups, q[0], q[1], q[2], q[3]);
+      rgb_pairs<1>(w, q);
+      row_words_store(S32 + ((1 * rows + row) * pitch >> 1), lane, groups, q[0], q[1], q[2], q[3]);
+      rgb_pairs<2>(w, q);
+      row_words_store(S32 + ((2 * rows + row) * pitch >> 1), lane, groups, q[0], q[1], q[2], q[3]);
+    }
+    return true;
+  }
+  return false;
+}
+
 // Stage fine rows [ih0, ih0+rows) of image n as bf16: S[(ci*rows + row)*pitch + s], s = iw + 1 in [0, IW+1]; s = 0 and
 // s = IW+1 (iw = -1, IW) and rows outside the image are the zero padding of the convolution.  IW % 4 == 0.
 // Loads are issued four deep per thread before anything is stored: the staging loops are what keeps HBM busy here
 // (each SM needs ~40 KB in flight), a one-load-at-a-time loop runs at a fifth of the bandwidth.
 template <int NC>
 __device__ __forceinline__ void stage_fine(__nv_bfloat16* S, int pitch, int rows, const ThinArgs& a, int n, int ih0) {
+  if (stage_fine_rows<NC>(S, pitch, rows, a, n, ih0)) return;      // (uniform across the CTA: it depends on the views only)
   const int IH = 2 * a.H, IW = 2 * a.W, IW4 = IW >> 2;
   const int total = NC * rows * IW4;
   constexpr int U = 4;
@@ -207,9 +326,9 @@ __device__ __forceinline__ void stage_coarse(__nv_bfloat16* S, int rows, int col
 // MMA column n = 8j + g of n-tile j is mapped to channel 8*(g>>1) + 2j + (g&1), so that lane (g,t) ends up with the
 // eight consecutive channels 8t..8t+7 of its pixel: one 16-byte store per pixel row, fully coalesced across the warp.
 // ---------------------------------------------------------------------------------------------------
-// (Measured, round 2: at NC = 3 this kernel holds 106-123 registers = two resident CTAs per SM and reaches 0.30-0.42 of the copy bandwidth.  Capping it at
-//  80 registers for three CTAs made it SLOWER (259 -> 307 us): ncu puts the issue slots at 57 % busy with 24 % of the warp slots filled -- the staging loop's
-//  per-element index arithmetic and its three odd-aligned shared-memory stores per four pixels are what it spends its time on, not latency.)
+// (Measured, round 2: at NC = 3 this kernel holds 106-128 registers = two resident CTAs per SM.  Capping it at 80 registers for three CTAs is SLOWER, before
+//  and after the row-per-warp staging (same-box A/B: 247 -> 261 us on the fp32 batch, 171 -> 193 us on the bf16 one): what it spends its time on is
+//  instruction issue, not latency -- ncu put the issue slots at 57 % busy with 24 % of the warp slots filled, most of it the old staging loop.)
 template <int NC, int EPI>
 __global__ void __launch_bounds__(256) thin_down_mma_kernel(const ThinArgs a) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -571,6 +690,12 @@ __global__ void __launch_bounds__(256) thin_up_tma_kernel(const __grid_constant_
   const int c = warp;
   const int prow = (lane & 7) + 8 * ((lane >> 3) & 1), kchunk = lane >> 4;
   const bool pair_store = NC == 1 && a.fine_vec;
+  // Dense interleaved RGB bf16 result (the image the fused trainer keeps between the networks): the warp's 2 x 32 pixels x 3 channels are gathered in a
+  // 384-byte shared-memory scratch and leave as 24 16-byte stores.  (ncu, round 2: the per-element path issued 3.2 M two-byte store requests per launch
+  // for 154 MB; the kernel sat at 0.28 of the copy bandwidth with the LSU as its busiest unit.)
+  const bool rgb_store = NC == 3 && a.fine.dtype == B200GAN_BF16 && a.fine.sc == 1 && a.fine.sw == 3 && a.fine.sh == (int64_t)6 * a.W &&
+                         a.fine.sn % 8 == 0 && (reinterpret_cast<uintptr_t>(a.fine.ptr) & 15) == 0;
+  __nv_bfloat16* scratch = reinterpret_cast<__nv_bfloat16*>(smem + kThinStages * stage_bytes + 18 * NT * 32 * 8 + 64) + warp * 192;
   int s = 0;
   uint32_t ph = 0;
   for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
@@ -611,6 +736,31 @@ __global__ void __launch_bounds__(256) thin_up_tma_kernel(const __grid_constant_
       for (int r2 = 0; r2 < 2; ++r2) {
         const int q = q0 + rr + r2;
         if (rr + r2 >= a.RT || q >= a.H) continue;
+        if (NC == 3 && rgb_store) {
+#pragma unroll
+          for (int j = 0; j < NT; ++j)
+#pragma unroll
+            for (int half = 0; half < 2; ++half)
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const int nn = 8 * j + 2 * t + e;
+                if (nn < 12) {
+                  float v = acc[r2][j][2 * half + e];
+                  if (a.out_act == B200GAN_ACT_TANH) v = tanh_fast(v);
+                  const int cls = nn / 3, ci = nn - cls * 3;
+                  scratch[(cls >> 1) * 96 + (2 * (g + 8 * half) + (cls & 1)) * 3 + ci] = __float2bfloat16_rn(v);
+                }
+              }
+          __syncwarp();
+          if (lane < 24) {
+            const int row = lane / 12, chunk = lane - row * 12;
+            const uint4 v = *reinterpret_cast<const uint4*>(scratch + row * 96 + chunk * 8);
+            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(a.fine.ptr) + (int64_t)n * a.fine.sn + (int64_t)(2 * q + row) * a.fine.sh + 96 * c + chunk * 8;
+            *reinterpret_cast<uint4*>(dst) = v;
+          }
+          __syncwarp();
+          continue;
+        }
 #pragma unroll
         for (int j = 0; j < NT; ++j)
 #pragma unroll
@@ -916,7 +1066,7 @@ int thin_up(const b200gan_view* coarse, const b200gan_view* coarse_ref, int coar
     int rc = coarse_tensor_map(&m, a, a.W + 2, a.RT + 2);
     if (rc) return rc;
     const size_t stage = ((size_t)(a.RT + 2) * (a.W + 2) * 64 + 1023) & ~(size_t)1023;
-    const size_t smem_tma = kThinStages * stage + (size_t)18 * NT * 32 * 8 + 64 + 1024;
+    const size_t smem_tma = kThinStages * stage + (size_t)18 * NT * 32 * 8 + 64 + 8 * 384 + 1024;      // + the per-warp RGB store scratch
     if (fine->c == 1) return launch_thin_tma<thin_up_tma_kernel<1>>(m, a, smem_tma, 2, st, "thin_up_tma_kernel");
     return launch_thin_tma<thin_up_tma_kernel<3>>(m, a, smem_tma, 2, st, "thin_up_tma_kernel");
   }
@@ -934,7 +1084,9 @@ int thin_wgrad(const b200gan_view* fine, const b200gan_view* fine_ref, int fine_
   a.dw = dw;
   // raw cp.async staging of the image band: unit W stride, 16-byte aligned rows, reference (if any) of the same dtype
   const bool band_ok = a.fine_vec && vec16_ok(fine) && (!fine_ref || (fine_ref->dtype == fine->dtype && vec16_ok(fine_ref)));
-  if (thin_tma_ok(a) && band_ok) {
+  // nc = 3: the cp.async-staged kernel below with the row-per-warp image staging beats the TMA-staged one (fp32 real batch: 433 -> 268 us); its raw
+  // image band is 3-6x as large and left one or two resident CTAs per SM
+  if (thin_tma_ok(a) && band_ok && fine->c != 3) {
     // rows of the coarse tensor per tile: the raw image band beside it is 3x as large at nc = 3 (6x in fp32), and at 4 rows one stage pair took
     // 113-170 KB = ONE resident CTA per SM (ncu: 12 % of the warp slots, 0.19 of the copy bandwidth); 2 rows keep two CTAs resident
     a.RT = fine->c == 3 ? 2 : 4;
