@@ -691,9 +691,10 @@ __global__ void __launch_bounds__(256) thin_up_tma_kernel(const __grid_constant_
   const int prow = (lane & 7) + 8 * ((lane >> 3) & 1), kchunk = lane >> 4;
   const bool pair_store = NC == 1 && a.fine_vec;
   // Dense interleaved RGB bf16 result (the image the fused trainer keeps between the networks): the warp's 2 x 32 pixels x 3 channels are gathered in a
-  // 384-byte shared-memory scratch and leave as 24 16-byte stores.  (ncu, round 2: the per-element path issued 3.2 M two-byte store requests per launch
+  // 384-byte shared-memory scratch and leave as 24 16-byte stores.  (At nc = 1 the paired 4-byte stores are already one 128-byte line per instruction:
+  // the staged form measured 168 us against 154 us.)  (ncu, round 2: the per-element path issued 3.2 M two-byte store requests per launch
   // for 154 MB; the kernel sat at 0.28 of the copy bandwidth with the LSU as its busiest unit.)
-  const bool rgb_store = NC == 3 && a.fine.dtype == B200GAN_BF16 && a.fine.sc == 1 && a.fine.sw == 3 && a.fine.sh == (int64_t)6 * a.W &&
+  const bool rgb_store = NC == 3 && a.fine.dtype == B200GAN_BF16 && a.fine.sc == 1 && a.fine.sw == NC && a.fine.sh == (int64_t)2 * NC * a.W &&
                          a.fine.sn % 8 == 0 && (reinterpret_cast<uintptr_t>(a.fine.ptr) & 15) == 0;
   __nv_bfloat16* scratch = reinterpret_cast<__nv_bfloat16*>(smem + kThinStages * stage_bytes + 18 * NT * 32 * 8 + 64) + warp * 192;
   int s = 0;
@@ -736,7 +737,7 @@ __global__ void __launch_bounds__(256) thin_up_tma_kernel(const __grid_constant_
       for (int r2 = 0; r2 < 2; ++r2) {
         const int q = q0 + rr + r2;
         if (rr + r2 >= a.RT || q >= a.H) continue;
-        if (NC == 3 && rgb_store) {
+        if (rgb_store) {
 #pragma unroll
           for (int j = 0; j < NT; ++j)
 #pragma unroll
@@ -744,18 +745,18 @@ __global__ void __launch_bounds__(256) thin_up_tma_kernel(const __grid_constant_
 #pragma unroll
               for (int e = 0; e < 2; ++e) {
                 const int nn = 8 * j + 2 * t + e;
-                if (nn < 12) {
+                if (nn < 4 * NC) {
                   float v = acc[r2][j][2 * half + e];
                   if (a.out_act == B200GAN_ACT_TANH) v = tanh_fast(v);
-                  const int cls = nn / 3, ci = nn - cls * 3;
-                  scratch[(cls >> 1) * 96 + (2 * (g + 8 * half) + (cls & 1)) * 3 + ci] = __float2bfloat16_rn(v);
+                  const int cls = nn / NC, ci = nn - cls * NC;
+                  scratch[(cls >> 1) * 32 * NC + (2 * (g + 8 * half) + (cls & 1)) * NC + ci] = __float2bfloat16_rn(v);
                 }
               }
           __syncwarp();
-          if (lane < 24) {
-            const int row = lane / 12, chunk = lane - row * 12;
-            const uint4 v = *reinterpret_cast<const uint4*>(scratch + row * 96 + chunk * 8);
-            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(a.fine.ptr) + (int64_t)n * a.fine.sn + (int64_t)(2 * q + row) * a.fine.sh + 96 * c + chunk * 8;
+          if (lane < 8 * NC) {                                     // two fine rows of 32 pixels x NC channels: 4 NC 16-byte chunks each
+            const int row = lane / (4 * NC), chunk = lane - row * 4 * NC;
+            const uint4 v = *reinterpret_cast<const uint4*>(scratch + row * 32 * NC + chunk * 8);
+            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(a.fine.ptr) + (int64_t)n * a.fine.sn + (int64_t)(2 * q + row) * a.fine.sh + 32 * NC * c + chunk * 8;
             *reinterpret_cast<uint4*>(dst) = v;
           }
           __syncwarp();
