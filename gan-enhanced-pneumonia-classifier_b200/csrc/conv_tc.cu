@@ -40,11 +40,11 @@ struct TcSmem {
 // single-thread roles (a first version spent ~100 instructions per step there).
 
 template <int BN, int KC, int STAGES, int EPI>
-__global__ void __launch_bounds__(kTcThreads, 2)
+__global__ void __launch_bounds__(kTcThreads, BN == 256 ? 1 : 2)     // the 256-wide tile owns all of TMEM: one CTA per SM anyway
 conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcConvParams p) {
   using S = TcSmem<BN, KC, STAGES>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = align_smem_1024(smem_raw);
   const int NST = p.nstages;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.off_bar);
   uint64_t* empty_bar = full_bar + 16;
@@ -186,6 +186,26 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     // Narrow tiles (<= 32 columns per warp): the whole row piece of y_prev for the NEXT tile is requested while this tile is
     // processed.  Requested per 16-column chunk inside the tile, every chunk exposed one HBM latency (~1.5 us) to the eight
     // epilogue warps, longer than the MMA stream of a whole tile.
+    // BatchNorm sums: lanes j and j+16 hold column j of a 16-column chunk after warp_column_sums; they stay in registers (one pair per
+    // chunk of this warp's CW columns) for as long as the CTA's tiles keep the same channel tile, and reach shared memory when it changes
+    // and at the end (a shared-memory float atomicAdd is a compare-and-swap loop: two per chunk and tile were a visible part of the fused
+    // epilogues' cost)
+    constexpr int NCH = CW / 16 > 0 ? CW / 16 : 1;
+    float ra0[NCH], ra1[NCH];
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) ra0[i] = ra1[i] = 0.f;
+    int acc_cout0 = -1;
+    auto flush_sums = [&]() {
+      if (lane < 16) {
+#pragma unroll
+        for (int i = 0; i < NCH; ++i) {
+          if (ra0[i] != 0.f) atomicAdd(&ch_acc[acc_cout0 + 16 * i + lane], ra0[i]);
+          if (ra1[i] != 0.f) atomicAdd(&ch_acc[p.cout + acc_cout0 + 16 * i + lane], ra1[i]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < NCH; ++i) ra0[i] = ra1[i] = 0.f;
+    };
     constexpr bool PRE = EPI >= 2 && CW <= 32;
     constexpr int NPRE = PRE ? CW / 8 : 1;
     uint4 ypre[NPRE];
@@ -203,6 +223,10 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++lt) {
       bool valid; int cout0;
       const int64_t ooff = locate(t, valid, cout0);
+      if ((EPI == 1 || EPI == 2) && cout0 != acc_cout0) {
+        if (acc_cout0 >= 0) flush_sums();
+        acc_cout0 = cout0;
+      }
       __nv_bfloat16* orow = p.out + ooff;
       const uint4* yp = reinterpret_cast<const uint4*>(p.prev_y + ooff);
       uint4 ynext[2], yall[NPRE];
@@ -279,9 +303,11 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           }
           warp_column_sums(s0, lane);
           warp_column_sums(s1, lane);
-          if (lane < 16) {
-            atomicAdd(&ch_acc[cout0 + c0 + lane], s0[0]);
-            atomicAdd(&ch_acc[p.cout + cout0 + c0 + lane], s1[0]);
+#pragma unroll
+          for (int i = 0; i < NCH; ++i) {                  // compile-time register indices whether or not the chunk loop is unrolled
+            const bool mine = i == (c0 >> 4);
+            ra0[i] += mine ? s0[0] : 0.f;
+            ra1[i] += mine ? s1[0] : 0.f;
           }
         }
       }
@@ -291,6 +317,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       if (lane == 0) mbar_arrive(&acc_empty[buf]);
     }
     if (EPI == 1 || EPI == 2) {
+      if (acc_cout0 >= 0) flush_sums();
       // the eight epilogue warps (256 threads) flush the CTA's channel sums: one double atomic per channel and quantity
       asm volatile("bar.sync 1, 256;" ::: "memory");
       for (int c = threadIdx.x; c < p.cout; c += 256) {
@@ -487,7 +514,9 @@ int tc_conv_dgrad(const b200gan_conv* cv, const b200gan_view* dy, const void* wp
                   cudaStream_t st) {
   if (cv->k == 4 && cv->stride == 2 && cv->pad == 1 && wpacked && nhwc_dense_bf16(dy) && nhwc_dense_bf16(dx) &&
       (epi.mode < 2 || (nhwc_dense_bf16(epi.prev_y) && epi.prev_y->n == dx->n && epi.prev_y->h == dx->h && epi.prev_y->w == dx->w && epi.prev_y->c == dx->c))) {
-    const int t = tc_conv_up4(dy, wpacked, dx, epi, st);
+    int t = tc_conv_up4(dy, wpacked, dx, epi, st);
+    if (t <= 0) return t;
+    t = tc_conv_up4w(dy, wpacked, dx, epi, st);
     if (t <= 0) return t;
   }
   return tc_conv_common(cv, dy, wpacked, dx, /*up=*/true, epi, st);

@@ -36,7 +36,7 @@ template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
 conv_gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcConvParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = align_smem_1024(smem_raw);
   const int NST = p.nstages;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.off_bar);      // used in the leader only
   uint64_t* empty_bar = full_bar + 16;                                     // one set per CTA, released by multicast commits

@@ -52,7 +52,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
   constexpr int B_NBOX = NCO / 64;
   constexpr uint32_t TMEM_COLS = G * NCO <= 256 ? 256 : 512;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = align_smem_1024(smem_raw);
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * S::A_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + S::DY_SLOTS * S::B_BYTES);

@@ -640,7 +640,7 @@ template <int NC>
 __global__ void __launch_bounds__(256) thin_up_tma_kernel(const __grid_constant__ CUtensorMap map_c, const ThinArgs a) {
   constexpr int NT = (4 * NC + 7) / 8;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = align_smem_1024(smem_raw);
   const int cols = a.W + 2, rows = a.RT + 2;
   const uint32_t tile_bytes = (uint32_t)rows * cols * 64u;
   const uint32_t stage_bytes = (tile_bytes + 1023u) & ~1023u;
@@ -812,7 +812,7 @@ __global__ void __launch_bounds__(256) thin_wgrad_tma_kernel(const __grid_consta
   constexpr int PADL = 16 / (int)sizeof(TF);                 // image column iw lives at element iw + PADL (16-byte aligned rows)
   constexpr int NB = HAS_REF ? 2 : 1;                        // bands per stage: gradient (+ reference)
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = align_smem_1024(smem_raw);
   const int frows = 2 * a.RT + 2, IH = 2 * a.H, IW = 2 * a.W, pitch = IW + 2 * PADL;
   const uint32_t tile_bytes = (uint32_t)a.RT * a.W * 64u;
   const uint32_t band_bytes = (uint32_t)NC * frows * pitch * (uint32_t)sizeof(TF);

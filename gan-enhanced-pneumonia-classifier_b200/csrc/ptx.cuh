@@ -10,6 +10,11 @@ namespace b200gan {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// 1024-byte alignment of the dynamic shared memory (SWIZZLE_128B tiles) as POINTER arithmetic on the __shared__ array: rounding through
+// uintptr_t hands the compiler a generic pointer, and every access behind it becomes a generic LD / ST -- and every float atomicAdd a
+// generic ATOM attempt + QSPC + compare-and-swap loop (found in the SASS of the fused epilogues, round 2)
+__device__ __forceinline__ uint8_t* align_smem_1024(uint8_t* smem_raw) { return smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u); }
+
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }

@@ -89,5 +89,7 @@ int launch_tc_pair(const CUtensorMap& ma, const CUtensorMap& mb_half, TcConvPara
 // halo-tile kernels (conv_tc_halo.cu): return 1 when the problem is not of their shape / fusion
 int tc_conv_up4(const b200gan_view* in, const void* wpacked, const b200gan_view* out, const TcEpi& epi, cudaStream_t st);
 int tc_conv_down4(const b200gan_view* in, const void* wpacked, const b200gan_view* out, const TcEpi& epi, cudaStream_t st);
+// conv_tc_halo_wide.cu: the 128 -> 64 channel "up" layer
+int tc_conv_up4w(const b200gan_view* in, const void* wpacked, const b200gan_view* out, const TcEpi& epi, cudaStream_t st);
 
 }  // namespace b200gan

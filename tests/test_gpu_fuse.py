@@ -155,8 +155,9 @@ def test_image_side_full_size_row_tiles():
 # ---------------------------------------------------------------------------------------------------
 # geometry (n, ci, co, hf, wf): fine (n,ci,hf,wf), coarse (n,co,hf/2,wf/2).  The second case is the thin 32<->64-channel layer at a size
 # the halo-tile tcgen05 kernels take (conv_down4_tc_kernel<1>, <2>, conv_up4_tc_kernel<1>), with ragged tiles in both directions
-# (24 = 16 + 8 output rows, 20 = 8 + 8 + 4 output columns)
-@pytest.mark.parametrize('geom', [(4, 32, 64, 16, 16), (3, 32, 64, 48, 40)])
+# (24 = 16 + 8 output rows, 20 = 8 + 8 + 4 output columns); the last two are the 64<->128-channel layer: its "up" direction runs on
+# conv_up4w_tc_kernel<1> (ConvTranspose2d forward + statistics) and <2> (Conv2d input gradient + BatchNorm backward), ragged and full tiles
+@pytest.mark.parametrize('geom', [(4, 32, 64, 16, 16), (3, 32, 64, 48, 40), (3, 64, 128, 48, 40), (5, 64, 128, 56, 56)])
 @pytest.mark.parametrize('mode', ['fp32', 'bf16'])
 @pytest.mark.parametrize('transposed', [False, True])
 def test_batchnorm_epilogue_fusions(mode, transposed, geom):

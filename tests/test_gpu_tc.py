@@ -80,7 +80,7 @@ def report(tag, got, ref):
 DOWN = [(2, 64, 16, 16, 128), (3, 32, 112, 112, 64), (5, 64, 56, 56, 128), (9, 128, 28, 28, 256), (130, 256, 14, 14, 512),
         (2, 32, 8, 24, 32), (3, 64, 12, 20, 64)]
 UP = [(2, 128, 8, 8, 64), (130, 512, 7, 7, 256), (9, 256, 14, 14, 128), (5, 128, 28, 28, 64), (3, 64, 56, 56, 32),
-      (2, 32, 4, 12, 32), (3, 64, 6, 10, 64)]
+      (2, 32, 4, 12, 32), (3, 64, 6, 10, 64), (3, 128, 24, 20, 64), (150, 128, 12, 8, 64)]
 
 
 @pytest.mark.parametrize('case', DOWN)

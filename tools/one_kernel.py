@@ -25,9 +25,13 @@ apv = L.view_nhwc(aprev)
 fz = None
 if epi == 'mask':
     fz = L.fuse(prev_act=L.ACT_LRELU, prev_slope=0.2, prev_y=apv)
+coef_u = torch.rand((4, ci), device='cuda') + 0.5
 flush = torch.empty(256 << 20, device='cuda', dtype=torch.uint8)
 def up():
-    if epi == 'stats':
+    if epi == 'bnbwd':
+        f1 = L.fuse(prev_act=L.ACT_LRELU, prev_slope=0.2, prev_y=apv, prev_scale=coef_u[0], prev_shift=coef_u[1], prev_mean=coef_u[2], prev_invstd=coef_u[3], prev_sums=sums)
+        L.call('b200gan_conv2d_dgrad', C.byref(cv), C.byref(L.view_nhwc(dy)), L.ptr(w), L.ptr(wu), C.byref(L.view_nhwc(dx)), C.byref(f1), st())
+    elif epi == 'stats':
         f1 = L.fuse(bn_sums=sums)
         L.call('b200gan_convT2d_fprop', C.byref(cv), C.byref(L.view_nhwc(dy)), L.ptr(w), L.ptr(wu), C.byref(L.view_nhwc(dx)), C.byref(f1), st())
     else:
