@@ -138,6 +138,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       if (p.resident) mbar_wait(res_bar, 0);
       const uint64_t adesc0 = make_smem_desc(smem_u32(smem), 16, SBO, LT);
       const uint64_t bres0 = make_smem_desc(smem_u32(smem_res), 16, SBO, LT);
+      const uint32_t dhi = (uint32_t)(adesc0 >> 32);     // SBO, version, layout type: the same for both operands
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++lt) {
         const int buf = lt % NACC;
         mbar_wait(&acc_empty[buf], ((lt / NACC) & 1) ^ 1);   // epilogue has drained this accumulator
@@ -149,11 +150,11 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           tcgen05_fence_after();
           // base descriptors + 16-byte-unit offsets: two 64-bit adds per MMA instead of rebuilding both descriptors (the
           // single issuing thread is the pacing resource for thin k-blocks)
-          const uint64_t adesc = adesc0 + (uint64_t)((uint32_t)(s * p.stage_stride) >> 4);
-          const uint64_t bdesc = p.resident ? bres0 + (uint64_t)((res_tile + (uint32_t)(kb * S::B_BYTES)) >> 4)
-                                            : adesc + (uint64_t)(S::A_BYTES >> 4);
+          // 32-bit arithmetic on the descriptors' low words (the start-address field cannot carry), see tcgen05_mma_f16_elect32
+          const uint32_t alo = (uint32_t)adesc0 + ((uint32_t)(s * p.stage_stride) >> 4);
+          const uint32_t blo = p.resident ? (uint32_t)bres0 + ((res_tile + (uint32_t)(kb * S::B_BYTES)) >> 4) : alo + (uint32_t)(S::A_BYTES >> 4);
 #pragma unroll
-          for (int k = 0; k < KC / 16; ++k) tcgen05_mma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          for (int k = 0; k < KC / 16; ++k) tcgen05_mma_f16_lohi(tmem_d, alo + 2 * k, dhi, blo + 2 * k, dhi, idesc, (kb | k) != 0);
           tcgen05_commit(&empty_bar[s]);                   // frees the smem stage when these MMAs retire
           if (++s == NST) { s = 0; ph ^= 1; }
         }

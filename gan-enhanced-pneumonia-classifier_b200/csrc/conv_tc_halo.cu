@@ -64,8 +64,8 @@ __device__ __forceinline__ void up4_issue_group(uint32_t tmem_d, uint64_t adesc0
     constexpr int b_off = T::slot_before(NB, GI) * 4096;
 #pragma unroll
     for (int k = 0; k < 4; ++k)
-      tcgen05_mma_f16_elect(tmem_d + T::first[NB][GI] * 32, adesc0 + (uint64_t)((a_off + k * 32) >> 4), bdesc0 + (uint64_t)((b_off + k * 32) >> 4),
-                            idesc, (NB | k) != 0);
+      tcgen05_mma_f16_elect32(tmem_d + T::first[NB][GI] * 32, (uint32_t)adesc0 + (uint32_t)((a_off + k * 32) >> 4), (uint32_t)(adesc0 >> 32),
+                              (uint32_t)bdesc0 + (uint32_t)((b_off + k * 32) >> 4), (uint32_t)(bdesc0 >> 32), idesc, (NB | k) != 0);
   }
 }
 
@@ -452,7 +452,8 @@ __device__ __forceinline__ void down4_issue_from(uint32_t tmem_d, uint64_t adesc
   constexpr uint32_t idesc = make_idesc_bf16(128, 64, 0, 0);
 #pragma unroll
   for (int k = 0; k < 2; ++k)
-    tcgen05_mma_f16_elect(tmem_d, adesc0 + (uint64_t)((a_off + k * 32) >> 4), bdesc0 + (uint64_t)((TAP * 4096 + k * 32) >> 4), idesc, (TAP | k) != 0);
+    tcgen05_mma_f16_elect32(tmem_d, (uint32_t)adesc0 + (uint32_t)((a_off + k * 32) >> 4), (uint32_t)(adesc0 >> 32),
+                            (uint32_t)bdesc0 + (uint32_t)((TAP * 4096 + k * 32) >> 4), (uint32_t)(bdesc0 >> 32), idesc, (TAP | k) != 0);
   if constexpr (TAP + 1 < 16) down4_issue_from<TAP + 1>(tmem_d, adesc0, bdesc0);
 }
 

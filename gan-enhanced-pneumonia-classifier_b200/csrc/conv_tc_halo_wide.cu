@@ -63,26 +63,6 @@ __device__ __forceinline__ uint32_t upw_sw128(int pix, int chunk) { return (uint
 // The 24 MMAs of one 64-channel chunk.  Row neighbour dh in {0, DH1} (DH1 = -1 for py = 0, +1 for py = 1; tap jh = py - dh), column
 // neighbour dw in {0, -1, +1}.  Weight slots per chunk and row neighbour: [px0 jw0 | px1 jw1] (dw = 0, one N = 128 operand),
 // [px0 jw1] (dw = -1), [px1 jw0] (dw = +1).  `first`: this chunk's first MMA initialises the accumulator.
-// One MMA from the descriptors' 32-bit halves: the offsets of the shifted windows / weight slots only touch the low word (the 14-bit
-// start-address field cannot carry: every address stays below 256 KB), so a window is ONE 32-bit add instead of a 64-bit add per operand
-__device__ __forceinline__ void upw_mma(uint32_t tmem_d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p, e;\n"
-      ".reg .b64 da, db;\n"
-      "mov.b64 da, {%1, %2};\n"
-      "mov.b64 db, {%3, %4};\n"
-      "elect.sync _|e, 0xffffffff;\n"
-      "setp.ne.b32 p, %6, 0;\n"
-      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n"
-      "}\n" ::"r"(tmem_d),
-      "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-
-// The 24 MMAs of one 64-channel chunk.  Row neighbour dh in {0, DH1} (DH1 = -1 for py = 0, +1 for py = 1; tap jh = py - dh), column
-// neighbour dw in {0, -1, +1}.  Weight slots per chunk and row neighbour: [px0 jw0 | px1 jw1] (dw = 0, one N = 128 operand),
-// [px0 jw1] (dw = -1), [px1 jw0] (dw = +1).  `first`: this chunk's first MMA initialises the accumulator.
 template <int DH1>
 __device__ __forceinline__ void upw_issue_chunk(uint32_t tmem_d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, bool first) {
   constexpr uint32_t idesc128 = make_idesc_bf16(128, 128, 0, 0), idesc64 = make_idesc_bf16(128, 64, 0, 0);
@@ -93,14 +73,14 @@ __device__ __forceinline__ void upw_issue_chunk(uint32_t tmem_d, uint32_t alo, u
     const int b_off = dhi * 4 * kUpwWB;
 #pragma unroll
     for (int k = 0; k < 4; ++k)      // dw = 0: both column classes
-      upw_mma(tmem_d, alo + (uint32_t)((row_off + 128 + k * 32) >> 4), ahi, blo + (uint32_t)((b_off + k * 32) >> 4), bhi, idesc128,
+      tcgen05_mma_f16_elect32(tmem_d, alo + (uint32_t)((row_off + 128 + k * 32) >> 4), ahi, blo + (uint32_t)((b_off + k * 32) >> 4), bhi, idesc128,
               (first && dhi == 0 && k == 0) ? 0u : 1u);
 #pragma unroll
     for (int k = 0; k < 4; ++k)      // dw = -1: px = 0 takes tap jw = 1
-      upw_mma(tmem_d, alo + (uint32_t)((row_off + 0 + k * 32) >> 4), ahi, blo + (uint32_t)((b_off + 2 * kUpwWB + k * 32) >> 4), bhi, idesc64, 1u);
+      tcgen05_mma_f16_elect32(tmem_d, alo + (uint32_t)((row_off + 0 + k * 32) >> 4), ahi, blo + (uint32_t)((b_off + 2 * kUpwWB + k * 32) >> 4), bhi, idesc64, 1u);
 #pragma unroll
     for (int k = 0; k < 4; ++k)      // dw = +1: px = 1 takes tap jw = 0
-      upw_mma(tmem_d + 64, alo + (uint32_t)((row_off + 256 + k * 32) >> 4), ahi, blo + (uint32_t)((b_off + 3 * kUpwWB + k * 32) >> 4), bhi, idesc64, 1u);
+      tcgen05_mma_f16_elect32(tmem_d + 64, alo + (uint32_t)((row_off + 256 + k * 32) >> 4), ahi, blo + (uint32_t)((b_off + 3 * kUpwWB + k * 32) >> 4), bhi, idesc64, 1u);
   }
 }
 

@@ -141,8 +141,8 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
           for (int k = 0; k < S::BK / 16; ++k) {
             // MN-major canonical layout: LBO = distance between swizzle atoms along M/N (one TMA box), SBO = 8 pixel rows;
             // a k-step advances 16 pixel rows
-            tcgen05_mma_f16(tmem_base + g * NCO, adesc + (uint64_t)((k * 16 * A_ROW) >> 4), bdesc + (uint64_t)((k * 16 * 128) >> 4), idesc,
-                            (kbl | k) != 0);
+            tcgen05_mma_f16_lohi(tmem_base + g * NCO, (uint32_t)adesc + (uint32_t)((k * 16 * A_ROW) >> 4), (uint32_t)(adesc >> 32),
+                                 (uint32_t)bdesc + (uint32_t)((k * 16 * 128) >> 4), (uint32_t)(bdesc >> 32), idesc, (kbl | k) != 0);
           }
           tcgen05_commit(&empty_bar[s]);
           if (++s == STAGES) { s = 0; ph ^= 1; }

@@ -74,6 +74,21 @@ __device__ __forceinline__ void tcgen05_mma_f16(uint32_t tmem_d, uint64_t adesc,
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// The same from the descriptors' 32-bit halves (see tcgen05_mma_f16_elect32): operand offsets are 32-bit adds on the low word
+__device__ __forceinline__ void tcgen05_mma_f16_lohi(uint32_t tmem_d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint32_t idesc,
+                                                     uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 da, db;\n"
+      "mov.b64 da, {%1, %2};\n"
+      "mov.b64 db, {%3, %4};\n"
+      "setp.ne.b32 p, %6, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // 256-bit global accesses (sm_100): one 32-byte sector per lane and instruction.  The epilogues read / write 32 bytes per
 // thread at a row stride, which costs one L1 wavefront per LANE per instruction whatever the width: 256-bit accesses halve the
 // number of instructions, i.e. the wavefronts.
@@ -100,6 +115,25 @@ __device__ __forceinline__ void tcgen05_mma_f16_elect(uint32_t tmem_d, uint64_t 
       "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
       "}\n" ::"r"(tmem_d),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// The same from the descriptors' 32-bit halves: offsets of shifted windows / weight slots / k-steps only touch the low word (the 14-bit
+// start-address field cannot carry: every shared-memory address stays below 256 KB), so an operand is ONE 32-bit add instead of a
+// 64-bit add.  The issuing warp's instruction stream is the pacing resource of the small-N kernels (measured on conv_up4w_tc_kernel:
+// 178 -> 150 us with the statistics epilogue, 241 -> 207 us with the BatchNorm-backward one).
+__device__ __forceinline__ void tcgen05_mma_f16_elect32(uint32_t tmem_d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint32_t idesc,
+                                                        uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, e;\n"
+      ".reg .b64 da, db;\n"
+      "mov.b64 da, {%1, %2};\n"
+      "mov.b64 db, {%3, %4};\n"
+      "elect.sync _|e, 0xffffffff;\n"
+      "setp.ne.b32 p, %6, 0;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 __device__ __forceinline__ void tcgen05_commit_elect(uint64_t* bar) {
