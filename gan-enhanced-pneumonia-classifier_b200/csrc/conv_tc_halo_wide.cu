@@ -15,6 +15,19 @@
 //     units of 8 output lines x 16 pixels x 64 channels: a 5-d tensor map (c, w, line parity, h/2, n) addresses the lines of one parity.
 // Shared memory: 128 KB weights + 2 x 23 KB input chunks + 3 x 16 KB staging units = 222 KB, one CTA per SM, all 512 TMEM columns
 // (4 accumulators of 128 columns).
+//
+// Measured at batch 512 (us per launch, alone with the L2 flushed / inside the iteration; generic kernel in brackets):
+//   no epilogue 114 [144], statistics 150 / 139 [169 / 153], BatchNorm backward 207 / 196 [228 / 210].
+// What the way there showed (tools/one_kernel.py d2_up, ncu --set full with source counters):
+//   * with ONE CTA per SM the issue slots are shared between the single MMA-issuing warp and the epilogue warps of its scheduler, and the
+//     tile time follows the epilogue's instruction count: eight epilogue warps ran the BatchNorm-backward epilogue (about 1500 instructions
+//     per warp and tile) at one instruction per 6 cycles each -- 316 us with the tensor pipe 24 % busy; sixteen warps: 241 us;
+//   * every MMA costs the issuing warp ELECT + VOTEU + five R2UR besides its descriptor arithmetic; 64-bit descriptor adds doubled the
+//     arithmetic part (tcgen05_mma_f16_elect32: 241 -> 207 us, 178 -> 150 us);
+//   * the result of the BatchNorm-backward variant leaves from registers: staged for a TMA store, a unit was held through load -> epilogue ->
+//     store, and three units are 1.5 tiles;
+//   * the statistics read-back must be branch-free (a shared-memory load under `if` is compiled to a branch per pixel);
+//   * L2 prefetch of the boxes two tiles ahead and two TMA stores in flight made no measurable difference.
 #include "tc_common.cuh"
 
 namespace b200gan {
@@ -27,7 +40,6 @@ struct Up4wParams {
   const float *prev_scale, *prev_shift, *prev_mean, *prev_invstd;
   float prev_neg;
   int off_res, off_io, off_bar;
-  int dbg;                              // B200GAN_UPW_DBG: timing experiments (bit 0: no statistics loop, 1: no wait for the staged unit, 2: one store in flight)
 };
 
 constexpr int kUpwTW = 8, kUpwTH = 16;
@@ -224,10 +236,7 @@ conv_up4w_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                        "r"(smem_u32(smem_io + (ys % kUpwYST) * kUpwUnit)), "r"(0), "r"(2 * tw_i * kUpwTW), "r"(py), "r"(th_i * kUpwTH + 8 * h), "r"(n)
                        : "memory");
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          if (p.dbg & 4) {
-            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            mbar_arrive(&y_empty[ys % kUpwYST]);
-          } else if (ys > 0) {
+          if (ys > 0) {
             // two stores in flight: the unit of the PREVIOUS store is handed back once that store has read it
             asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
             mbar_arrive(&y_empty[(ys - 1) % kUpwYST]);
@@ -235,7 +244,7 @@ conv_up4w_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           ++ys;
         }
       }
-      if (!(p.dbg & 4) && ys > 0) {
+      if (ys > 0) {
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         mbar_arrive(&y_empty[(ys - 1) % kUpwYST]);
       }
@@ -336,12 +345,11 @@ conv_up4w_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         if (lane == 0) mbar_arrive(&staged[ys]);
       }
       if (EPI == 1) {
-        if (!(p.dbg & 2)) mbar_wait(&staged[ys], yph);     // all eight warps have written (the store thread reads the unit concurrently)
+        mbar_wait(&staged[ys], yph);                       // all eight warps have written (the store thread reads the unit concurrently)
         // BatchNorm statistics from the staged (bf16-rounded) unit: warp wi owns pixels 16wi..16wi+15, lane l the channel pair 2l, 2l+1
         // (one conflict-free 4-byte shared load per pixel), accumulated in registers over all tiles of the CTA.  Branch-free: the load is
         // always inside the unit and the VALUE is masked -- a load under `if` compiles to a branch per pixel with the load's latency
         // exposed every time (measured on the sibling kernels: +40 us per launch)
-        if (!(p.dbg & 1))
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const int px2 = wi * 16 + i;
@@ -391,8 +399,8 @@ static int launch_up4w(const CUtensorMap& ma, const CUtensorMap& mb, const CUten
 
 // returns 1 when the problem is not the 128 -> 64 channel "up" shape (or carries an epilogue this kernel does not have)
 int tc_conv_up4w(const b200gan_view* in, const void* wpacked, const b200gan_view* out, const TcEpi& epi, cudaStream_t st) {
-  static const bool enabled = getenv("B200GAN_NO_UP4W") == nullptr;
-  if (!enabled || in->c != 128 || out->c != 64 || epi.mode == 3) return 1;
+  const char* off = getenv("B200GAN_NO_UP4W");                         // read per call: tests compare both kernels inside one process
+  if ((off != nullptr && atoi(off) != 0) || in->c != 128 || out->c != 64 || epi.mode == 3) return 1;
   if (in->h < 12 || in->w < 8) return 1;                               // small maps waste most of a 16 x 8 tile: generic kernel
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return B200GAN_ERR_CUDA; }
@@ -401,8 +409,6 @@ int tc_conv_up4w(const b200gan_view* in, const void* wpacked, const b200gan_view
   p.num_tiles = p.tiles_w * p.tiles_h * in->n;
   p.QH = in->h; p.QW = in->w; p.NB = in->n;
   p.out = reinterpret_cast<__nv_bfloat16*>(out->ptr);
-  static const int dbg = getenv("B200GAN_UPW_DBG") ? atoi(getenv("B200GAN_UPW_DBG")) : 0;
-  p.dbg = dbg;
   if (epi.mode != 0) {
     p.sums = epi.sums;
     B200_CUDA(cudaMemsetAsync(epi.sums, 0, sizeof(double) * 128, st));
