@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 lib = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, 'gan-enhanced-pneumonia-classifier_b200', 'libb200gan.so')
 sass = subprocess.run(['cuobjdump', '-sass', lib], capture_output=True, text=True).stdout
 names = subprocess.run(['cu++filt'], input='\n'.join(re.findall(r'Function : (\S+)', sass)), capture_output=True, text=True).stdout.split('\n')
-OPS = ['UTCHMMA.2CTA', 'UTCHMMA', 'LDTM', 'UTMALDG', 'UTMASTG', 'UTCBAR', 'HMMA', 'LDGSTS']
+OPS = ['UTCHMMA.2CTA', 'UTCHMMA', 'LDTM', 'UTMALDG', 'UTMASTG', 'UTMAPF', 'UTCBAR', 'HMMA', 'LDGSTS']
 rows, cur, k = collections.OrderedDict(), None, 0
 for line in sass.split('\n'):
     m = re.search(r'Function : (\S+)', line)
