@@ -57,6 +57,7 @@ PROTOTYPES = {
     'b200gan_pack_conv_weight': [_vp, _i32, _i32, _i32, _i32, _vp, _vp],
     'b200gan_bn_stats': [_VP, _vp, _vp],
     'b200gan_bn_finalize': [_vp, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _vp, _vp, _vp, _vp, _vp],
+    'b200gan_bn_finalize_act_fwd': [_vp, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _vp, _vp, _vp, _vp, _VP, _i32, _f32, _VP, _vp],
     'b200gan_bn_eval_coeffs': [_i32, _vp, _vp, _vp, _vp, _f32, _vp, _vp, _vp],
     'b200gan_bn_act_fwd': [_VP, _vp, _vp, _i32, _f32, _VP, _vp],
     'b200gan_bn_act_bwd_reduce': [_VP, _VP, _VP, _vp, _vp, _vp, _vp, _i32, _f32, _vp, _vp],

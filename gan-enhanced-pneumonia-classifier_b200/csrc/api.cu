@@ -79,6 +79,8 @@ int ew_bn_finalize(double*, int, int64_t, const float*, const float*, float*, fl
                    float*, float*, cudaStream_t);
 int ew_bn_eval_coeffs(int, const float*, const float*, const float*, const float*, float, float*, float*, cudaStream_t);
 int ew_bn_act_fwd(const b200gan_view*, const float*, const float*, int, float, const b200gan_view*, cudaStream_t);
+int ew_bn_finalize_act_fwd(double*, int, int64_t, const float*, const float*, float*, float*, int64_t*, float, float, float*, float*, float*, float*,
+                           const b200gan_view*, int, float, const b200gan_view*, cudaStream_t);
 int ew_bn_act_bwd_apply(const b200gan_view*, const b200gan_view*, const b200gan_view*, const float*, const float*, const float*,
                         const float*, const float*, double*, int64_t, int, float, const b200gan_view*, float*, float*,
                         cudaStream_t);
@@ -386,6 +388,28 @@ int b200gan_bn_act_fwd(const b200gan_view* y, const float* scale, const float* s
   if ((rc = check_view(a, "bn_act_fwd"))) return rc;
   B200_CHECK_ARG((scale == nullptr) == (shift == nullptr), "bn_act_fwd: scale/shift must both be given or both NULL");
   B200_CHECK_ARG(act >= B200GAN_ACT_NONE && act <= B200GAN_ACT_SIGMOID, "bn_act_fwd: bad activation %d", act);
+  return ew_bn_act_fwd(y, scale, shift, act, slope, a, (cudaStream_t)stream);
+}
+
+int b200gan_bn_finalize_act_fwd(double* sums, int32_t channels, int64_t count, const float* gamma, const float* beta, float* running_mean,
+                                float* running_var, int64_t* num_batches_tracked, float momentum, float eps, float* scale, float* shift,
+                                float* save_mean, float* save_invstd, const b200gan_view* y, int32_t act, float slope, const b200gan_view* a,
+                                void* stream) {
+  int rc;
+  if ((rc = check_view(y, "bn_finalize_act_fwd"))) return rc;
+  if ((rc = check_view(a, "bn_finalize_act_fwd"))) return rc;
+  B200_CHECK_ARG(sums && gamma && beta && scale && shift && save_mean && save_invstd, "bn_finalize_act_fwd: null pointer");
+  B200_CHECK_ARG(channels > 0 && count > 0 && y->c == channels, "bn_finalize_act_fwd: channels=%d count=%lld (tensor has %d)", channels, (long long)count, y->c);
+  B200_CHECK_ARG((running_mean == nullptr) == (running_var == nullptr), "bn_finalize_act_fwd: running_mean/var must both be given or both NULL");
+  B200_CHECK_ARG(act >= B200GAN_ACT_NONE && act <= B200GAN_ACT_SIGMOID, "bn_finalize_act_fwd: bad activation %d", act);
+  B200_CHECK_ARG(y->n == a->n && y->h == a->h && y->w == a->w && y->c == a->c, "bn_finalize_act_fwd: extent mismatch");
+  rc = ew_bn_finalize_act_fwd(sums, channels, count, gamma, beta, running_mean, running_var, num_batches_tracked, momentum, eps, scale, shift,
+                              save_mean, save_invstd, y, act, slope, a, (cudaStream_t)stream);
+  if (rc != 1) return rc;
+  // layouts the one-launch kernel does not take: the two passes it stands for
+  if ((rc = ew_bn_finalize(sums, channels, count, gamma, beta, running_mean, running_var, num_batches_tracked, momentum, eps, scale, shift,
+                           save_mean, save_invstd, (cudaStream_t)stream)))
+    return rc;
   return ew_bn_act_fwd(y, scale, shift, act, slope, a, (cudaStream_t)stream);
 }
 

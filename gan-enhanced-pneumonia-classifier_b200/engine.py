@@ -291,21 +291,32 @@ class NetEngine:
                     invstd = torch.empty(cch, device=dev, dtype=torch.float32)
                     self._fprop(i, cur, p.w, y, st, wp_down, wp_up, fuse=L.fuse(bn_sums=sums))
                     ranks = 1
+                    fused_apply = self.sync_bn is None and os.environ.get('B200GAN_BN_ONE_LAUNCH', '1') != '0'
                     if self.sync_bn is not None:
                         self.sync_bn.allreduce_f64(sums)
                         ranks = self.sync_bn.world
-                    L.call('b200gan_bn_finalize', L.ptr(sums), cch, cur.v.n * oh * ow * ranks, L.ptr(p.gamma), L.ptr(p.beta),
-                           L.ptr(p.rm), L.ptr(p.rv), L.ptr(p.nbt), BN_MOMENTUM, BN_EPS, L.ptr(scale), L.ptr(shift),
-                           L.ptr(mean), L.ptr(invstd), st)
+                    if fused_apply:
+                        # finalize + normalise + activation in one launch (local statistics): one launch less per BatchNorm layer
+                        a = Act(torch.empty(shape, device=dev, dtype=self.dtype), nchw=False)
+                        L.call('b200gan_bn_finalize_act_fwd', L.ptr(sums), cch, cur.v.n * oh * ow, L.ptr(p.gamma), L.ptr(p.beta),
+                               L.ptr(p.rm), L.ptr(p.rv), L.ptr(p.nbt), BN_MOMENTUM, BN_EPS, L.ptr(scale), L.ptr(shift),
+                               L.ptr(mean), L.ptr(invstd), C.byref(y.v), sp.act, LRELU_SLOPE, C.byref(a.v), st)
+                        self.launches += 1
+                    else:
+                        L.call('b200gan_bn_finalize', L.ptr(sums), cch, cur.v.n * oh * ow * ranks, L.ptr(p.gamma), L.ptr(p.beta),
+                               L.ptr(p.rm), L.ptr(p.rv), L.ptr(p.nbt), BN_MOMENTUM, BN_EPS, L.ptr(scale), L.ptr(shift),
+                               L.ptr(mean), L.ptr(invstd), st)
                     if save:
                         lc.mean, lc.invstd = mean, invstd
                 else:
                     self._fprop(i, cur, p.w, y, st, wp_down, wp_up)
+                    fused_apply = False
                     L.call('b200gan_bn_eval_coeffs', cch, L.ptr(p.gamma), L.ptr(p.beta), L.ptr(p.rm), L.ptr(p.rv), BN_EPS,
                            L.ptr(scale), L.ptr(shift), st)
-                a = Act(torch.empty(shape, device=dev, dtype=self.dtype), nchw=False)
-                L.call('b200gan_bn_act_fwd', C.byref(y.v), L.ptr(scale), L.ptr(shift), sp.act, LRELU_SLOPE, C.byref(a.v), st)
-                self.launches += 2
+                if not fused_apply:
+                    a = Act(torch.empty(shape, device=dev, dtype=self.dtype), nchw=False)
+                    L.call('b200gan_bn_act_fwd', C.byref(y.v), L.ptr(scale), L.ptr(shift), sp.act, LRELU_SLOPE, C.byref(a.v), st)
+                    self.launches += 2
                 if save:
                     lc.y, lc.scale, lc.shift = y, scale, shift
             elif last and not last_act:

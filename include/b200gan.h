@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define B200GAN_VERSION 430   /* major*10000 + minor*100 + patch */
+#define B200GAN_VERSION 440   /* major*10000 + minor*100 + patch */
 
 typedef enum b200gan_status {
   B200GAN_OK = 0,
@@ -166,6 +166,15 @@ int b200gan_bn_eval_coeffs(int32_t channels, const float* gamma, const float* be
 /* a = act(y*scale[c] + shift[c]); scale == NULL means no BatchNorm (dcgan.py:66 first D layer, :47 tanh, :85). */
 int b200gan_bn_act_fwd(const b200gan_view* y, const float* scale, const float* shift, int32_t act, float slope,
                        const b200gan_view* a, void* stream);
+
+/* b200gan_bn_finalize followed by b200gan_bn_act_fwd on the layer's tensor, as ONE launch where the tensors are dense NHWC of one dtype
+ * (otherwise the library runs the two passes): the training-mode forward of BatchNorm2d + activation (dcgan.py:31-32, :72-73) behind a
+ * convolution that accumulated `sums` in its epilogue (b200gan_fuse.bn_sums).  Coefficients are bit-identical to b200gan_bn_finalize's. */
+int b200gan_bn_finalize_act_fwd(double* sums, int32_t channels, int64_t count, const float* gamma, const float* beta,
+                                float* running_mean, float* running_var, int64_t* num_batches_tracked,
+                                float momentum, float eps, float* scale, float* shift, float* save_mean,
+                                float* save_invstd, const b200gan_view* y, int32_t act, float slope,
+                                const b200gan_view* a, void* stream);
 
 /* Backward of act(BN(y)).  da: gradient w.r.t. the activation output; y: the saved conv output;
  * a: the saved activation output (only read for TANH / SIGMOID, may be NULL otherwise).

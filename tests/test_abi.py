@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f'{n} declared in include/b200gan.h but not exported'
     assert sorted(list(L.PROTOTYPES) + L.OTHER_SYMBOLS) == names, 'ctypes prototypes and header differ'
-    assert lib.b200gan_version() == 430        # 0.4.3: + conditional-GAN entry points (incl. the VGG16 perceptual pieces), b200gan_dp_allreduce_f64
+    assert lib.b200gan_version() == 440        # 0.4.4: + b200gan_bn_finalize_act_fwd (0.4.3: conditional-GAN entry points, b200gan_dp_allreduce_f64)
 
 
 def test_bad_arguments_fail_loudly_without_a_gpu():

@@ -169,6 +169,40 @@ def test_batchnorm_act_forward_backward(mode, act, shape):
         grad_close(to_nchw(dyd), dy_o, 'bn dgrad', bulk=5e-3, l2=2e-2, worst=5e-2)
 
 
+@pytest.mark.parametrize('mode', ['fp32', 'bf16'])
+@pytest.mark.parametrize('shape', [(3, 8, 7, 7), (2, 64, 14, 10), (2, 1024, 3, 5), (2, 300, 3, 5)])
+def test_bn_finalize_act_fwd_one_launch_is_bit_identical_to_the_two_passes(mode, shape):
+    """b200gan_bn_finalize_act_fwd (one launch: coefficients + running statistics + normalise + activation) against b200gan_bn_finalize
+    followed by b200gan_bn_act_fwd: the same arithmetic, so every output is BIT-identical; 300 channels (not a multiple of the vector
+    width in bf16) take the library's two-pass route inside the call."""
+    rng = np.random.RandomState(5)
+    n, c, h, w = shape
+    dt = DT[mode]
+    yd = nhwc((rng.randn(*shape) * 1.3 + 0.2).astype(np.float32), dt)
+    gamma, beta = dev(rng.normal(1, 0.2, c).astype(np.float32)), dev(rng.normal(0, 0.2, c).astype(np.float32))
+    rm0, rv0 = rng.randn(c).astype(np.float32), (rng.rand(c) + 0.5).astype(np.float32)
+    sums = torch.empty(2 * c, device='cuda', dtype=torch.float64)
+    L.call('b200gan_bn_stats', C.byref(L.view_nhwc(yd)), L.ptr(sums), st())
+    outs = []
+    for fused in (False, True):
+        rmd, rvd, nbtd = dev(rm0), dev(rv0), torch.tensor(7, device='cuda', dtype=torch.int64)
+        scale, shift, mean, istd = (torch.full((c,), float('nan'), device='cuda') for _ in range(4))
+        a = torch.full_like(yd, float('nan'))
+        if fused:
+            L.call('b200gan_bn_finalize_act_fwd', L.ptr(sums), c, n * h * w, L.ptr(gamma), L.ptr(beta), L.ptr(rmd), L.ptr(rvd), L.ptr(nbtd), 0.1, 1e-5,
+                   L.ptr(scale), L.ptr(shift), L.ptr(mean), L.ptr(istd), C.byref(L.view_nhwc(yd)), L.ACT_LRELU, 0.2, C.byref(L.view_nhwc(a)), st())
+        else:
+            L.call('b200gan_bn_finalize', L.ptr(sums), c, n * h * w, L.ptr(gamma), L.ptr(beta), L.ptr(rmd), L.ptr(rvd), L.ptr(nbtd), 0.1, 1e-5,
+                   L.ptr(scale), L.ptr(shift), L.ptr(mean), L.ptr(istd), st())
+            L.call('b200gan_bn_act_fwd', C.byref(L.view_nhwc(yd)), L.ptr(scale), L.ptr(shift), L.ACT_LRELU, 0.2, C.byref(L.view_nhwc(a)), st())
+        torch.cuda.synchronize()
+        assert int(nbtd) == 8
+        outs.append([t.clone() for t in (a, scale, shift, mean, istd, rmd, rvd)])
+    for name, t0, t1 in zip(('a', 'scale', 'shift', 'mean', 'invstd', 'running_mean', 'running_var'), *outs):
+        assert not torch.isnan(t1.float()).any(), name
+        assert torch.equal(t0, t1), f'{name}: one-launch result differs from the two passes'
+
+
 def test_bn_eval_tanh_sigmoid_and_copy():
     rng = np.random.RandomState(2)
     c = 6

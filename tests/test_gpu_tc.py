@@ -106,15 +106,16 @@ def test_tc_up_conv_matches_simt(case):
 @pytest.mark.parametrize('case', [(5, 128, 28, 28, 64), (3, 128, 24, 20, 64)])
 def test_halo_wide_kernel_agrees_with_generic_kernel(case, monkeypatch):
     """conv_up4w_tc_kernel (128 -> 64 channels "up", conv_tc_halo_wide.cu) against the generic implicit-GEMM kernel on the same operands
-    (B200GAN_NO_UP4W=1 is read per call): the same bf16 products accumulated in fp32 in a different order, so at most one bf16 ulp apart;
-    both are held to the numpy oracle by test_tc_up_conv_matches_simt."""
+    (B200GAN_NO_UP4W=1 is read per call): the same bf16 products accumulated in fp32 in a different order, so the two bf16 results are at
+    most one ulp apart -- 2^-7 relative at the bottom of a binade; both are held to the numpy oracle (2^-8) by test_tc_up_conv_matches_simt."""
     n, co, h, w_, ci = case
     monkeypatch.setenv('B200GAN_NO_UP4W', '0')
     dy, wt, dx_new, _ = run_pair(n, ci, h, w_, co, 'up')
     monkeypatch.setenv('B200GAN_NO_UP4W', '1')
     _, _, dx_gen, _ = run_pair(n, ci, h, w_, co, 'up')
     assert not torch.isnan(dx_new.float()).any()
-    close(dx_new.float().cpu().numpy(), dx_gen.float().cpu().numpy(), rtol=1.05 * BF16_ULP, atol=1e-4, what='halo-wide vs generic kernel')
+    close(dx_new.float().cpu().numpy(), dx_gen.float().cpu().numpy(), rtol=2.1 * BF16_ULP, atol=1e-4, what='halo-wide vs generic kernel')
+    assert (dx_new != dx_gen).float().mean().item() < 0.05, 'more than 5 % of the elements differ by an ulp'
     oracle_close(dx_new, orc.conv2d_dgrad(nchw(dy), wt.cpu().numpy(), 2, 1, (2 * h, 2 * w_)), f'halo-wide up {case}')
 
 
