@@ -38,3 +38,20 @@ def test_committed_b200_line_carries_every_contract_key():
     assert line['cpu_baseline']['kind'] == 'port' and line['cpu_baseline']['value'] > 0
     names = ' '.join(m.get('model', '') for m in line['more_configs'])
     assert 'WGAN-GP' in names and 'CGAN' in names and any(m.get('nc') == 3 and 'model' not in m for m in line['more_configs'])
+
+
+def test_class_fractions_use_the_launches_actually_profiled():
+    """`tensor_core_classes` / `roofline.class_frac`: FLOPs of a kernel class = its PROFILED launches x one layer-operation each (a class that
+    lost launches to another kernel must not keep their FLOPs), against both measured peaks."""
+    sys.path.insert(0, ROOT)
+    import bench
+    peaks = {'tf_sustained': 1400.0, 'tf_burst': 1600.0}
+    breakdown = {'conv_gemm_tc_kernel<256, 64, 4, 1>': (7.0, 560.0), 'conv_gemm_tc_kernel<128, 64, 3, 2>': (4.0, 520.0),
+                 'conv_up4w_tc_kernel<2>': (3.0, 600.0), 'bn_act_bwd_apply_dense_kernel': (17.0, 970.0)}
+    cls = bench.class_fractions(breakdown, 512, peaks)
+    assert set(cls) == {'conv_gemm_tc_kernel', 'conv_up4w_tc_kernel'}
+    g = cls['conv_gemm_tc_kernel']
+    want = 11 * bench.LAYER_OP_FLOP * 512 / (1080.0 * 1e-6) / 1e12
+    assert g['launches_per_step'] == 11 and abs(g['tflops'] - want) < 1e-9 * want
+    assert abs(g['frac_of_sustained_peak'] - want / 1400.0) < 1e-12 and abs(g['frac_of_burst_peak'] - want / 1600.0) < 1e-12
+    assert cls['conv_up4w_tc_kernel']['launches_per_step'] == 3
