@@ -584,9 +584,9 @@ def run_ours(args):
         import torch_cpu_port as port
         cpu = None
         if not args.no_cpu_baseline:
-            r = port.time_cpu_steps(batch=64, steps=3, warmup=1, nc=nc, threads=port.host_threads())
+            r = port.time_cpu_steps(batch=64, steps=12, warmup=1, nc=nc, threads=port.host_threads())     # ~10 s of CPU work on the box's 16-24 threads
             cpu = {'value': r['images_per_s'], 'unit': UNIT, 'cores': r['threads'], 'kind': 'port',
-                   'sample': '3 iterations x batch 64 after 1 warm-up (oracle/torch_cpu_port.py: stock torch.nn CPU path of dcgan.py/train_gan.py; '
+                   'sample': '12 iterations x batch 64 after 1 warm-up (oracle/torch_cpu_port.py: stock torch.nn CPU path of dcgan.py/train_gan.py; '
                              'a PORT: /root/reference does not exist on the GPU box)'}
         top = sorted(breakdown.items(), key=lambda kv: -kv[1][1])[:12]
         line = {
